@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the PIC hot path (one "step" = one lap of mainloop over one rank's particles).
+
+Workload (config.workload): 3D Weibel, 2nd-order shapes (dd2, nghost 7), 16 ppc, filter2 with ntimes = 32, per-GPU slab
+512x256x128 cells -- the per-GPU share of BASELINE.json configs[2] (512^3 over 8 B200 as sizey x sizez = 2 x 4).  The slab
+per GPU is fixed as N grows (weak scaling); at N = 8 the job IS configs[2].
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path through the C ABI
+  python bench.py --impl reference ...                     # the reference's CPU algorithm (oracle restatement; the
+                                                           # Fortran build cannot be compiled in this image) on host cores
+Prints ONE JSON line (see the task contract): value = resident throughput, e2e = mirror-mode throughput with the full
+state crossing PCIe every lap, roofline for the dominant kernels, cpu_baseline on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRID = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}       # sizey, sizez
+PPC = 16.0
+ORDER = 2
+NTIMES = 32
+FILTER_KIND = 2
+B_PER_PARTICLE = 52.0 + 36.0 / PPC                         # mover+deposit algorithmic bytes
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, nargs=3, default=[512, 256, 128], help="per-GPU slab (interior cells)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fused", type=int, default=1)
+    ap.add_argument("--cpu-cells", type=int, nargs=3, default=[128, 64, 64])
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# synthetic Weibel-like state on the host: two counter-streaming beams (+-0.5c in x) with a thermal spread,
+# uniform positions, small random seed fields.  Same recipe for every rank (seeded by rank).
+# ------------------------------------------------------------------------------------------------------------
+def make_state(tg, P, rank, pinned):
+    rng = np.random.default_rng(1234 + rank)
+    g, gz = P.nghost // 2, P.nghostz // 2
+    nx, ny, nz = P.mx - P.nghost, P.my - P.nghost, P.mz - P.nghostz
+    nhalf = int(0.5 * PPC * nx * ny * nz)                  # per species
+    maxhlf = P.maxptl // 2
+    assert nhalf <= maxhlf
+    if pinned:
+        import torch
+        buf = torch.empty(P.maxptl * 40, dtype=torch.uint8, pin_memory=True)
+        p = buf.numpy().view(tg.PARTICLE_DTYPE)
+        keep = buf
+    else:
+        p = np.zeros(P.maxptl, tg.PARTICLE_DTYPE)
+        keep = None
+    blk = 1 << 22
+    base = {k: rng.random(blk, dtype=np.float32) for k in "xyz"}
+    mom = {k: (rng.standard_normal(blk).astype(np.float32) * np.float32(0.05)) for k in "uvw"}
+    gam_beta = np.float32(0.5 / np.sqrt(1 - 0.25))
+    for s, lo in ((0, 0), (1, maxhlf)):
+        done = 0
+        while done < nhalf:
+            n = min(blk, nhalf - done)
+            sl = slice(lo + done, lo + done + n)
+            sh = rng.random(3).astype(np.float32)
+            p["x"][sl] = np.float32(g + 1) + np.float32(nx) * ((base["x"][:n] + sh[0]) % np.float32(1.0))
+            p["y"][sl] = np.float32(g + 1) + np.float32(ny) * ((base["y"][:n] + sh[1]) % np.float32(1.0))
+            p["z"][sl] = np.float32(gz + 1) + np.float32(nz) * ((base["z"][:n] + sh[2]) % np.float32(1.0))
+            sign = np.where((np.arange(n) & 1) == 0, np.float32(1), np.float32(-1))
+            p["u"][sl] = sign * gam_beta + mom["u"][:n]
+            p["v"][sl] = mom["v"][:n]
+            p["w"][sl] = mom["w"][:n]
+            p["ch"][sl] = 1.0
+            p["ind"][sl] = np.arange(done + 1, done + n + 1, dtype=np.int32) * 2 - s
+            p["proc"][sl] = rank
+            p["splitlev"][sl] = 1
+            done += n
+        # keep strictly inside the interior
+        for k, hi in (("x", P.mx - g), ("y", P.my - g), ("z", P.mz - gz)):
+            v = p[k][lo:lo + nhalf]
+            np.minimum(v, np.nextafter(np.float32(hi), np.float32(0)), out=v)
+    shape = (P.mz, P.my, P.mx)
+    fields = [(rng.standard_normal(shape).astype(np.float32) * np.float32(1e-3)) for _ in range(6)]
+    if pinned:
+        import torch
+        tf = [torch.from_numpy(f).pin_memory() for f in fields]
+        fields = [t.numpy() for t in tf]
+        keep = (keep, tf)
+    return p, nhalf, fields, keep
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU leg: the oracle restatement (kind "port"), one slab per OpenMP thread, bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------------------
+def cpu_leg(cells, steps, warmup):
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    sy = sz = 1
+    c = cores
+    while c >= 2 and (cells[1] // (sy * 2) >= 16 or cells[2] // (sz * 2) >= 16):
+        if cells[2] // sz >= cells[1] // sy and cells[2] // (sz * 2) >= 16:
+            sz *= 2
+        elif cells[1] // (sy * 2) >= 16:
+            sy *= 2
+        else:
+            break
+        c //= 2
+    os.environ["OMP_NUM_THREADS"] = str(sy * sz)
+    P = O.make_params(dim=3, order=ORDER, mx0=cells[0], my0=cells[1], mz0=cells[2], sizey=sy, sizez=sz, ppc0=PPC,
+                      ntimes=NTIMES, filter_kind=FILTER_KIND)
+    w = O.World(P)
+    w.init_uniform(ppc0=PPC, beta=0.5, uth=0.05, seed=3)
+    npart = sum(sum(r.counts) for r in w.ranks)
+    for _ in range(warmup):
+        w.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        w.step()
+    dt = time.perf_counter() - t0
+    return npart * steps / dt, sy * sz, npart, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    val, cores, npart, sec = cpu_leg(args.cpu_cells, steps, min(args.warmup, 1))
+    sample = f"3D Weibel dd2 {PPC:g} ppc filter2 ntimes={NTIMES}, {args.cpu_cells[0]}x{args.cpu_cells[1]}x{args.cpu_cells[2]} cells " \
+             f"({npart} particles), {steps} laps, one y/z slab per OpenMP thread"
+    line = {"impl": "reference", "metric": "particle-steps/sec", "value": val, "unit": "particle-steps/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = CPU oracle restatement of the Fortran routines (no Fortran/MPI toolchain in this image)"}
+    print(json.dumps(line))
+
+
+def workload_config(args, n):
+    sy, sz = GRID[n]
+    return {"workload": f"3D Weibel, dd2 (2nd-order Esirkepov), {PPC:g} ppc, filter2 ntimes={NTIMES}, per-GPU slab "
+                        f"{args.cells[0]}x{args.cells[1]}x{args.cells[2]} cells (configs[2] share), global "
+                        f"{args.cells[0]}x{args.cells[1] * sy}x{args.cells[2] * sz}",
+            "decomposition": f"sizey={sy} sizez={sz}", "ppc": PPC, "order": ORDER, "c": 0.45,
+            "l2": "inputs (>= 9 GB of particle SoA per GPU) larger than L2; no flush needed"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import __graft_entry__ as ge
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n = args.gpus
+    assert n in GRID and world in (1, n), "--gpus must be 1,2,4,8 and match WORLD_SIZE under torchrun"
+    import torch
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ge.build()
+    if dist:
+        dist.barrier()
+    import tristan_mp_pu_master_densdecomp_b200 as tg
+    sy, sz = GRID[n] if world > 1 else (1, 1)
+    cx, cy, cz = args.cells
+    nhalf_est = int(0.5 * PPC * cx * cy * cz)
+    P = tg.make_params(dim=3, order=ORDER, mx0=cx, my0=cy * sy, mz0=cz * sz, sizey=sy, sizez=sz, rank=rank, ntimes=NTIMES,
+                       filter_kind=FILTER_KIND, ppc0=PPC, maxptl=int(2 * nhalf_est * 1.25) + 8192,
+                       buffsize=max(int(nhalf_est * 0.05), 100000), device=local)
+    ctx = tg.Context(P)
+    ctx.set_option("fused", args.fused)
+    if world > 1:
+        ctx.comm_init_torch()
+    do_e2e = not args.no_e2e
+    p, nhalf, fields, keep = make_state(tg, P, rank, pinned=do_e2e)
+    ctx.fields_h2d(*fields)
+    ctx.particles_h2d(p, nhalf, nhalf)
+    npart = 2 * nhalf
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        ctx.step(1)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        ctx.step(1)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    sampler.stop_flag = True
+    counts = ctx.counts()
+    t = torch.tensor([ms, float(sum(counts))], dtype=torch.float64, device="cuda")
+    if dist:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms, total_particles = float(tm[0]), float(ts[1])
+    else:
+        total_particles = float(t[1])
+    value = total_particles * args.steps / (ms * 1e-3)
+
+    # per-phase device time (CUDA events on the library's stream around each phase), 3 extra laps
+    ctx.set_option("timing", 1)
+    ctx.timers(reset=True)
+    nphase = 3
+    for _ in range(nphase):
+        ctx.step(1)
+    ph = {k: v / nphase for k, v in ctx.timers(reset=True).items()}
+    ctx.set_option("timing", 0)
+    peak, peak_src = measured_peak()
+    md_ms = ph["mover"] + ph["deposit"]
+    alg_bytes = sum(counts) * B_PER_PARTICLE
+    achieved = alg_bytes / (md_ms * 1e-3) / 1e9 if md_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "mover+deposit (k_cellrun_fused / k_move+k_deposit), per lap",
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": md_ms, "peak_source": peak_src,
+                "phase_ms": ph}
+
+    e2e = None
+    if do_e2e:
+        # mirror mode: the host owns the state; every lap the full state crosses PCIe in both directions
+        outp = p
+        barrier()
+        t0 = time.perf_counter()
+        ni, ne = nhalf, nhalf
+        ci, ce = ctx.counts()
+        for _ in range(args.e2e_steps):
+            ctx.fields_h2d(*fields)
+            ctx.particles_h2d(outp, ci, ce)
+            ctx.step(1)
+            _, ci, ce = ctx.particles_d2h(outp)
+            ctx.fields_d2h(fields)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+        fbytes = 6 * P.mx * P.my * P.mz * 4
+        pbytes = (ci + ce) * 40
+        e2e = {"value": total_particles / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": fbytes + pbytes,
+               "d2h_bytes_per_step": fbytes + pbytes, "mode": "mirror: fields+particles H2D, one lap, fields+particles D2H "
+               "through tgpu_* with pinned host buffers", "ms_per_step": dt * 1e3}
+    ctx.close()
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if not args.no_cpu and world == 1:
+        val, cores, npc, sec = cpu_leg(args.cpu_cells, 2, 1)
+        cpu = {"value": val, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_cells[0]}x{args.cpu_cells[1]}x{args.cpu_cells[2]} cells, {npc} particles, 2 laps, same "
+                         f"physics (dd2, {PPC:g} ppc, filter2 ntimes={NTIMES}); oracle restatement, one slab per thread"}
+    line = {"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": n, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "ns_per_particle_step": 1e9 / value * n,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, n), "particles": total_particles, "gpu_launches": launches,
+            "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "hbm_roofline_frac_whole_step": (total_particles / n * B_PER_PARTICLE + 144.0 * cx * cy * cz) / (ms / args.steps * 1e-3) / 1e9 / peak}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,159 @@
+/*
+ * tristan_gpu.h -- C ABI of libtristan_gpu.so: the sm_100a implementation of TRISTAN-MP's
+ * per-timestep PIC hot path (mover, Esirkepov deposit, Yee half/full steps, current filter,
+ * ghost/current/particle exchanges).
+ *
+ * The reference has no plugin API for this path: mainloop() calls argument-less module
+ * procedures that work on module-global arrays (code/tristanmainloop.F90:107-344).  Each entry
+ * point below replaces one of those procedures (file:line given per function; all paths are
+ * relative to the reference checkout) so that `call move_particles()` becomes
+ * `ierr = tgpu_move_particles(h)` through the ISO_C_BINDING interface shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a TGPU_E* code otherwise; tgpu_last_error() gives text.
+ *     (The reference prints and `stop`s, e.g. code/particles.F90:362-370; the Fortran wrapper does
+ *     `if (ierr/=0) stop`.)
+ *   - arrays are Fortran column-major (mx,my,mz) fp32, exactly the reference's allocatables
+ *     (code/fields.F90:81-88); particles are the 40-byte `type particle` (code/particles.F90:51-55).
+ *   - one context per MPI rank / GPU; calls are synchronous with respect to host-visible outputs.
+ *   - no CPU fallback: every call fails with TGPU_ECUDA if no sm_100 device is usable.
+ */
+#ifndef TRISTAN_GPU_H
+#define TRISTAN_GPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    TGPU_OK = 0,
+    TGPU_EINVAL = 1,     /* bad argument / unsupported configuration */
+    TGPU_ECUDA = 2,      /* CUDA runtime error or no device */
+    TGPU_EOVERFLOW = 3,  /* particle or outbox capacity exceeded (check_overflow, particles.F90:362-385) */
+    TGPU_ENCCL = 4,      /* NCCL error / communicator not initialised */
+    TGPU_ESTATE = 5      /* call sequence error */
+};
+
+/* quirk switches: reproduce reference defects bit for bit */
+enum {
+    TGPU_Q1_MOVER2_RANGE = 1 << 0,
+    TGPU_Q2_BXBY_NO_KAVG = 1 << 1,
+    TGPU_Q4_DEPOSIT_CARRY = 1 << 2,   /* accepted, no effect on the GPU: the carries are 0 in exact arithmetic */
+    TGPU_Q5_FILTER_CURZ_J = 1 << 3,
+    TGPU_Q_REFERENCE = 0xF
+};
+
+/* 40-byte particle record: code/particles.F90:51-55 */
+typedef struct tgpu_particle {
+    float x, y, z, u, v, w, ch;
+    int32_t ind, proc, splitlev;
+} tgpu_particle;
+
+/* Everything the reference keeps in module globals that the kernels need
+ * (code/fields.F90:68-79, code/particles.F90:219-251,
+ * code/communications.F90:105-106, code/fieldboundaries.F90:86-88). */
+typedef struct tgpu_params {
+    int32_t dim;                 /* 2 (-DtwoD) or 3 */
+    int32_t order;               /* 0 = -Dzzag, 1/2/3 = -Ddd1/-Ddd2/-Ddd3 */
+    int32_t mx, my, mz;          /* this rank's array sizes, ghosts included (mz = 1 in 2D) */
+    int32_t nghost, nghostz;     /* 5 or 7 (fields.F90:166-184) */
+    float c, corr;               /* <time> c ; <algorithm> Corr */
+    float qi, qe, qmi, qme;      /* particles.F90:224-233 */
+    int32_t ntimes;              /* <algorithm> ntimes */
+    int32_t filter_kind;         /* 1 = apply_filter1_opt (filter.F90), 2 = apply_filter2_opt (optimized_filters.F90) */
+    int32_t periodicx, periodicy, periodicz;
+    float x1in, x2in, y1in, y2in, z1in, z2in;   /* particles.F90:339-344, global coordinates */
+    int32_t rank, sizex, sizey, sizez;          /* communications.F90:163-181 */
+    int32_t mxcum, mycum, mzcum;                /* fields.F90:316-328 */
+    const int32_t *mxl, *myl, *mzl;             /* per-rank sizes, size0 entries each (may be NULL when size0 == 1) */
+    int32_t maxptl;              /* per-rank particle capacity; maxhlf = maxptl/2 per species */
+    int32_t buffsize;            /* migration outbox capacity per direction (particles.F90:309) */
+    int32_t quirks;              /* TGPU_Q_* mask; TGPU_Q_REFERENCE reproduces the reference */
+    int32_t pusher;              /* 0 Boris, 1 Vay (-Dvay) */
+    int32_t external_fields;     /* constant external field model of get_external_fields */
+    float ext[6];                /* ex,ey,ez,bx,by,bz */
+    int32_t device;              /* CUDA device ordinal, or -1 for rank % device_count */
+    int32_t sort_every;          /* counting-sort cadence in laps for tgpu_step (reference: 10; 0 = library default) */
+} tgpu_params;
+
+typedef struct tgpu_ctx tgpu_ctx;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+/* after initialize() (code/initialize.F90:113-175): allocates device state for this rank */
+int tgpu_init(const tgpu_params *p, tgpu_ctx **out);
+int tgpu_finalize(tgpu_ctx *h);
+const char *tgpu_last_error(void);
+int tgpu_device_count(void);                     /* 0 when no usable GPU */
+
+/* ---- topology helpers (host only; usable without a GPU) ------------------------------------ */
+/* neighbour rank in direction dir = 0:-x 1:+x 2:-y 3:+y 4:-z 5:+z
+ * (fieldboundaries.F90:1170-1171, 1311-1314; particles.F90:1892-1895) */
+int tgpu_neighbour(int rank, int sizex, int sizey, int sizez, int dir);
+/* slab sizes and offsets of `rank` for a global interior mx0 x my0 x mz0 (fields.F90:259-328);
+ * out = {mx,my,mz,mxcum,mycum,mzcum} */
+int tgpu_decompose(int dim, int order, int mx0, int my0, int mz0, int sizex, int sizey, int sizez,
+                   int rank, int32_t out[6]);
+int tgpu_ghost_width(int dim, int order, int32_t *nghost, int32_t *nghostz);   /* fields.F90:166-184 */
+
+/* ---- communicator (NCCL over NVLink; replaces mpif.h SendRecv, communications.F90:127-161) -- */
+int tgpu_comm_unique_id(uint8_t id[128]);         /* rank 0 creates, host broadcasts (MPI_Bcast / torch.distributed) */
+int tgpu_comm_init(tgpu_ctx *h, const uint8_t id[128]);
+
+/* ---- state transfer (mirror / resident modes, SURVEY.md 8b "Ownership") --------------------- */
+int tgpu_fields_h2d(tgpu_ctx *h, const float *ex, const float *ey, const float *ez,
+                    const float *bx, const float *by, const float *bz);
+int tgpu_fields_d2h(tgpu_ctx *h, float *ex, float *ey, float *ez, float *bx, float *by, float *bz);
+int tgpu_currents_h2d(tgpu_ctx *h, const float *curx, const float *cury, const float *curz);
+int tgpu_currents_d2h(tgpu_ctx *h, float *curx, float *cury, float *curz);
+/* p is the reference's p(1:maxptl): ions at [0,ions), electrons at [maxhlf, maxhlf+lecs) */
+int tgpu_particles_h2d(tgpu_ctx *h, const tgpu_particle *p, int ions, int lecs);
+int tgpu_particles_d2h(tgpu_ctx *h, tgpu_particle *p, int *ions, int *lecs);
+int tgpu_counts(tgpu_ctx *h, int *ions, int *lecs);
+/* host injector output (inject_particles_user, user/user_shock.F90:303-331): n_ion ions then n_lec electrons */
+int tgpu_append_particles(tgpu_ctx *h, const tgpu_particle *p, int n_ion, int n_lec);
+
+/* ---- field solver: code/fields.F90 ---------------------------------------------------------- */
+int tgpu_advance_b_halfstep(tgpu_ctx *h);         /* fields.F90:586-728 */
+int tgpu_advance_e_fullstep(tgpu_ctx *h);         /* fields.F90:739-870 */
+int tgpu_reset_currents(tgpu_ctx *h);             /* fields.F90:499-506 */
+int tgpu_add_current(tgpu_ctx *h);                /* fields.F90:1372-1395 */
+
+/* ---- field boundaries: code/fieldboundaries.F90 ---------------------------------------------- */
+int tgpu_bc_b1(tgpu_ctx *h);                      /* fieldboundaries.F90:181-263 */
+int tgpu_bc_e1(tgpu_ctx *h);                      /* fieldboundaries.F90:306-392 */
+int tgpu_bc_b2(tgpu_ctx *h);                      /* :274-295 (radiation `surface` not ported: == bc_b1) */
+int tgpu_bc_e2(tgpu_ctx *h);                      /* :403-426 (== bc_e1) */
+int tgpu_exchange_current(tgpu_ctx *h);           /* fieldboundaries.F90:1768-2189 */
+
+/* ---- filter: code/filter.F90, code/optimized_filters.F90 ------------------------------------- */
+int tgpu_apply_filter(tgpu_ctx *h);               /* dispatch of tristanmainloop.F90:213-229 on filter_kind */
+int tgpu_apply_filter1_opt(tgpu_ctx *h);          /* filter.F90:8-221 */
+int tgpu_apply_filter2_opt(tgpu_ctx *h);          /* optimized_filters.F90:9-227 */
+
+/* ---- particles: code/particles_movedeposit.F90, code/particles.F90 --------------------------- */
+int tgpu_move_particles(tgpu_ctx *h);             /* particles_movedeposit.F90:63-88 -> mover / mover_{1,2,3}ord */
+int tgpu_deposit_particles(tgpu_ctx *h);          /* particles_movedeposit.F90:1281-2051 -> zigzag / densdecomp_{1,2,3}ord */
+int tgpu_exchange_particles(tgpu_ctx *h);         /* particles.F90:1865-2116 + inject_others :1368-1852, both rounds */
+int tgpu_inject_others(tgpu_ctx *h);              /* no-op: folded into tgpu_exchange_particles; kept for call-list parity */
+int tgpu_reorder_particles(tgpu_ctx *h);          /* particles.F90:394-497 (unconditional here; the lap%10 test stays in the caller) */
+
+/* ---- whole lap, resident mode: tristanmainloop.F90:107-344 with Appendix-B de-duplication ---- */
+int tgpu_step(tgpu_ctx *h, int nlaps);
+
+/* ---- instrumentation (print_timers, communications.F90:242-326) ------------------------------ */
+/* device milliseconds accumulated per phase since the last reset; out has TGPU_NPHASE entries */
+enum { TGPU_PH_FIELDS = 0, TGPU_PH_MOVER, TGPU_PH_DEPOSIT, TGPU_PH_PEXCH, TGPU_PH_CUREXCH, TGPU_PH_FILTER,
+       TGPU_PH_SORT, TGPU_PH_BC, TGPU_NPHASE };
+int tgpu_timers(tgpu_ctx *h, double *out_ms, int reset);
+/* number of kernels this library has launched since init (all streams) */
+int64_t tgpu_launch_count(tgpu_ctx *h);
+/* the CUDA stream all kernels of this context are launched on (cudaStream_t as void*) */
+void *tgpu_stream(tgpu_ctx *h);
+/* select the particle path: 0 = generic per-particle kernels, 1 = cell-run fused kernels where available */
+int tgpu_set_option(tgpu_ctx *h, const char *name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,250 @@
+"""GPU parity tests: every C-ABI entry point against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.md "Parity gates"):
+  * stencils, ghost refresh, current fold, filters: BIT-EXACT (no reduction reordering; fields.cu is built with
+    -fmad=false, the oracle with -ffp-contract=off);
+  * mover: positions within 2e-6 relative, momenta within 2e-5 of the momentum scale (FMA contraction only);
+  * deposit: currents within 1e-5 of the max-norm (atomic-sum reordering), charge conservation to round-off;
+  * particle counts and identities exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import common as T
+
+pytestmark = pytest.mark.gpu
+
+CUR_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def tgm(tg):
+    if tg.device_count() < 1:
+        pytest.fail("no CUDA device visible: the GPU tests must run on the B200 box")
+    return tg
+
+
+def make(tgm, **kw):
+    w = T.oracle_world(**kw)
+    ctxs = [tgm.Context(T.gpu_params(tgm, w, rank=i, device=0)) for i in range(1)]
+    T.upload(ctxs[0], w.ranks[0])
+    return w, ctxs[0]
+
+
+DIMS_ORDERS = [(d, o) for d in (2, 3) for o in (0, 1, 2, 3)]
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_field_solver_bit_exact(tgm, dim):
+    w, ctx = make(tgm, dim=dim, order=2, n=(20, 18, 14), ppc=1.0)
+    r = w.ranks[0]
+    for name in ["advance_b_halfstep", "advance_e_fullstep", "advance_b_halfstep"]:
+        getattr(ctx, name)()
+        r.call(name)
+    fg = ctx.fields_d2h()
+    for a in range(6):
+        assert np.array_equal(fg[a], r.arr(a)), O.ARR_NAMES[a]
+    ctx.close()
+
+
+@pytest.mark.parametrize("dim,order", [(2, 1), (2, 2), (3, 1), (3, 3)])
+def test_ghost_refresh_and_fold_bit_exact(tgm, dim, order):
+    w, ctx = make(tgm, dim=dim, order=order, n=(20, 18, 14), ppc=1.0)
+    r = w.ranks[0]
+    rng = np.random.default_rng(5)
+    for a in range(6, 9):
+        r.arr(a)[...] = rng.standard_normal(r.arr(a).shape).astype(np.float32)
+    T.upload(ctx, r)
+    ctx.bc_b1(); ctx.bc_e1(); ctx.exchange_current()
+    w.phase(O.PH_BC_B1); w.phase(O.PH_BC_E1); w.phase(O.PH_EXCH_CUR)
+    fg = ctx.fields_d2h() + ctx.currents_d2h()
+    for a in range(9):
+        assert np.array_equal(fg[a], r.arr(a)), O.ARR_NAMES[a]
+    ctx.close()
+
+
+@pytest.mark.parametrize("dim,kind,ntimes", [(2, 1, 5), (3, 1, 3), (3, 2, 4), (3, 2, 7), (2, 2, 6)])
+def test_filters_bit_exact(tgm, dim, kind, ntimes):
+    w, ctx = make(tgm, dim=dim, order=2, n=(20, 18, 14), ppc=1.0, ntimes=ntimes, filter_kind=kind)
+    r = w.ranks[0]
+    rng = np.random.default_rng(6)
+    for a in range(6, 9):
+        r.arr(a)[...] = rng.standard_normal(r.arr(a).shape).astype(np.float32)
+    T.upload(ctx, r)
+    ctx.apply_filter()
+    w.call("apply_filter")
+    cg = ctx.currents_d2h()
+    for c in range(3):
+        assert np.array_equal(T.interior(r, cg[c]), T.interior(r, r.arr(6 + c))), O.ARR_NAMES[6 + c]
+    ctx.add_current(); r.call("add_current")
+    fg = ctx.fields_d2h()
+    for a in range(3):
+        assert np.array_equal(T.interior(r, fg[a]), T.interior(r, r.arr(a)))
+    ctx.close()
+
+
+@pytest.mark.parametrize("dim,order", DIMS_ORDERS)
+@pytest.mark.parametrize("fused", [0, 1])
+def test_mover(tgm, dim, order, fused):
+    w, ctx = make(tgm, dim=dim, order=order, n=(16, 14, 12), ppc=6.0)
+    ctx.set_option("fused", fused)
+    r = w.ranks[0]
+    ctx.move_particles()
+    r.call("move_particles")
+    gi, ge = T.gpu_particles(ctx)
+    oi, oe = T.oracle_particles(r)
+    T.assert_particles_close(gi, oi, what="ions")
+    T.assert_particles_close(ge, oe, what="electrons")
+    ctx.close()
+
+
+@pytest.mark.parametrize("pusher,ext", [(1, None), (0, [0.01, -0.02, 0.03, 0.2, -0.1, 0.15])])
+def test_mover_vay_and_external_fields(tgm, pusher, ext):
+    w, ctx = make(tgm, dim=3, order=2, n=(12, 12, 12), ppc=4.0, pusher=pusher, ext=ext)
+    r = w.ranks[0]
+    ctx.move_particles(); r.call("move_particles")
+    gi, ge = T.gpu_particles(ctx)
+    oi, oe = T.oracle_particles(r)
+    T.assert_particles_close(gi, oi); T.assert_particles_close(ge, oe)
+    ctx.close()
+
+
+@pytest.mark.parametrize("dim,order", DIMS_ORDERS)
+@pytest.mark.parametrize("fused", [0, 1])
+def test_deposit(tgm, dim, order, fused):
+    """move (so that old != new position), then deposit from identical particle state"""
+    w, ctx = make(tgm, dim=dim, order=order, n=(16, 14, 12), ppc=6.0)
+    ctx.set_option("fused", fused)
+    r = w.ranks[0]
+    r.call("move_particles")
+    T.upload(ctx, r)                       # identical post-move state on both sides
+    ctx.reset_currents(); r.call("reset_currents")
+    ctx.deposit_particles(); r.call("deposit_particles")
+    cg = ctx.currents_d2h()
+    for c in range(3):
+        err = T.max_rel(cg[c], r.arr(6 + c))
+        assert err < CUR_TOL, f"{O.ARR_NAMES[6 + c]} err {err:.3e}"
+    # wrap / compaction: same particle sets, positions exact (the wrap is an exact fp32 operation)
+    gi, ge = T.gpu_particles(ctx)
+    oi, oe = T.oracle_particles(r)
+    T.assert_particles_close(gi, oi, rtol_pos=0, rtol_mom=0); T.assert_particles_close(ge, oe, rtol_pos=0, rtol_mom=0)
+    ctx.close()
+
+
+@pytest.mark.parametrize("dim,order", [(2, 1), (2, 2), (3, 1), (3, 2), (3, 3), (3, 0)])
+def test_fused_move_then_deposit_matches_separate_calls(tgm, dim, order):
+    """drop-in call order: move_particles ... reset_currents ... deposit_particles (tristanmainloop.F90:134-183)"""
+    w, ctx = make(tgm, dim=dim, order=order, n=(16, 14, 12), ppc=6.0)
+    r = w.ranks[0]
+    ctx.move_particles(); ctx.advance_b_halfstep(); ctx.reset_currents(); ctx.deposit_particles()
+    r.call("move_particles"); r.call("advance_b_halfstep"); r.call("reset_currents"); r.call("deposit_particles")
+    cg = ctx.currents_d2h()
+    for c in range(3):
+        assert T.max_rel(cg[c], r.arr(6 + c)) < 5e-5
+    assert ctx.counts() == r.counts
+    ctx.close()
+
+
+@pytest.mark.parametrize("dim,order,kind", [(2, 1, 1), (2, 2, 1), (3, 2, 2), (3, 1, 1), (3, 3, 2), (3, 0, 1), (2, 3, 1)])
+def test_full_lap(tgm, dim, order, kind):
+    """tgpu_step (de-duplicated call list) against the oracle's full mainloop lap, 3 laps from identical state"""
+    w, ctx = make(tgm, dim=dim, order=order, n=(16, 16, 12), ppc=6.0, ntimes=3, filter_kind=kind)
+    r = w.ranks[0]
+    for lap in range(3):
+        ctx.step(1); w.step()
+        fg = ctx.fields_d2h()
+        for a in range(6):
+            err = T.max_rel(T.interior(r, fg[a]), T.interior(r, r.arr(a)))
+            assert err < 3e-4 * (lap + 1), f"lap {lap} {O.ARR_NAMES[a]} err {err:.3e}"
+        assert ctx.counts() == r.counts
+        gi, ge = T.gpu_particles(ctx)
+        oi, oe = T.oracle_particles(r)
+        T.assert_particles_close(gi, oi, rtol_pos=2e-5 * (lap + 1), rtol_mom=2e-4 * (lap + 1))
+        T.assert_particles_close(ge, oe, rtol_pos=2e-5 * (lap + 1), rtol_mom=2e-4 * (lap + 1))
+    ctx.close()
+
+
+def test_mirror_call_list_equals_step(tgm):
+    """the reference's full call list (8 ghost refreshes) and tgpu_step (3) agree on the parity region"""
+    w, ctx = make(tgm, dim=3, order=2, n=(16, 16, 12), ppc=4.0, ntimes=2, filter_kind=2)
+    r = w.ranks[0]
+    ctx2 = tgm.Context(T.gpu_params(tgm, w, device=0))
+    T.upload(ctx2, r)
+    ctx.step(1)
+    for name in ["bc_b1", "bc_e1", "advance_b_halfstep", "bc_b1", "move_particles", "advance_b_halfstep", "bc_b1",
+                 "bc_b2", "advance_e_fullstep", "bc_e2", "reset_currents", "bc_e1", "bc_b1", "deposit_particles",
+                 "exchange_particles", "exchange_current", "apply_filter", "add_current", "inject_others",
+                 "exchange_particles", "inject_others"]:
+        getattr(ctx2, name)()
+    f1, f2 = ctx.fields_d2h(), ctx2.fields_d2h()
+    for a in range(6):
+        assert T.max_rel(T.interior(r, f1[a]), T.interior(r, f2[a])) < 1e-5
+    ctx.close(); ctx2.close()
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_charge_conservation_on_device(tgm, order):
+    """div(E) - rho changes by round-off only over a lap (filter off), at a size the oracle would not enjoy"""
+    n = (48, 40, 32)
+    w = T.oracle_world(dim=3, order=order, n=n, ppc=8.0, ntimes=0, init="uniform", seed_fields=0)
+    r = w.ranks[0]
+    ctx = tgm.Context(T.gpu_params(tgm, w, device=0))
+    T.upload(ctx, r)
+    rho0 = r.charge_density()
+    ctx.step(1)
+    p, ions, lecs = ctx.particles_d2h()
+    r.particles()[:] = p
+    r.set_counts(ions, lecs)
+    rho1 = r.charge_density()
+    ex, ey, ez = ctx.fields_d2h()[:3]
+    div = (ex - np.roll(ex, 1, 2)) + (ey - np.roll(ey, 1, 1)) + (ez - np.roll(ez, 1, 0))
+    d = T.interior(r, div, extra=3) - T.interior(r, rho1 - rho0, extra=3)
+    scale = np.abs(T.interior(r, rho1 - rho0, extra=3)).max()
+    assert np.abs(d).max() < 2e-5 * scale + 1e-9, (np.abs(d).max(), scale)
+    assert ions + lecs == sum(r.counts)
+    ctx.close()
+
+
+def test_sort_is_a_permutation_and_sorted(tgm):
+    w, ctx = make(tgm, dim=3, order=2, n=(16, 14, 12), ppc=6.0)
+    r = w.ranks[0]
+    ctx.reorder_particles()
+    p, ions, lecs = ctx.particles_d2h()
+    assert (ions, lecs) == r.counts
+    for lo, n in ((0, ions), (ctx.maxhlf, lecs)):
+        q = p[lo:lo + n]
+        key = q["x"].astype(np.int64) - 1 + r.mx * ((q["y"].astype(np.int64) - 1) + r.my * (q["z"].astype(np.int64) - 1))
+        assert np.all(np.diff(key) >= 0)
+    gi, ge = T.gpu_particles(ctx)
+    oi, oe = T.oracle_particles(r)
+    T.assert_particles_close(gi, oi, rtol_pos=0, rtol_mom=0)
+    ctx.reorder_particles()            # idempotent
+    gi2, _ = T.gpu_particles(ctx)
+    assert np.array_equal(gi, gi2)
+    ctx.close()
+
+
+def test_particle_roundtrip_and_append(tgm):
+    w, ctx = make(tgm, dim=2, order=1, n=(12, 12, 1), ppc=4.0)
+    r = w.ranks[0]
+    p, ions, lecs = ctx.particles_d2h()
+    assert (ions, lecs) == r.counts
+    assert np.array_equal(p[:ions], r.ions()) and np.array_equal(p[ctx.maxhlf:ctx.maxhlf + lecs], r.lecs())
+    extra = np.concatenate([r.ions()[:5], r.lecs()[:3]])
+    ctx.append_particles(extra, 5, 3)
+    assert ctx.counts() == (ions + 5, lecs + 3)
+    ctx.close()
+
+
+def test_errors_are_loud(tgm):
+    P = tgm.make_params(dim=3, order=2, mx0=8, my0=8, mz0=8, sizex=2)
+    with pytest.raises(tgm.TristanGPUError):
+        tgm.Context(P)
+    P = tgm.make_params(dim=3, order=2, mx0=8, my0=8, mz0=8, maxptl=64)
+    ctx = tgm.Context(P)
+    big = np.zeros(P.maxptl, tgm.PARTICLE_DTYPE)
+    with pytest.raises(tgm.TristanGPUError):
+        ctx.lib.tgpu_particles_h2d.argtypes  # keep linters quiet
+        ctx.particles_h2d(big, 40, 0)       # > maxhlf
+    ctx.close()

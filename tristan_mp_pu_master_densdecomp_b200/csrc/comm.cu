@@ -1,0 +1,157 @@
+// Rank topology (host arithmetic) and the NCCL transport that replaces the reference's blocking
+// MPI_SendRecv pairs (code/communications.F90:127-161; call sites in fieldboundaries.F90 / particles.F90).
+// NCCL is bound at run time with dlopen so that the library loads (and its host-only entry points work)
+// on machines without a GPU or without libnccl.
+#include <dlfcn.h>
+#include <stdlib.h>
+#include <string.h>
+#include "tgpu_internal.h"
+
+static int imodulo(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
+
+// fieldboundaries.F90:1170-1171 (x), :1311-1314 (y); particles.F90:1892-1895 (z)
+int topo_neighbour(int rank, int sx, int sy, int sz, int dir)
+{
+    switch (dir) {
+    case 0: return (rank / sx) * sx + imodulo(rank - 1, sx);
+    case 1: return (rank / sx) * sx + imodulo(rank + 1, sx);
+    case 2: return imodulo(rank / sx - 1, sy) * sx + rank / (sx * sy) * (sx * sy) + imodulo(rank, sx);
+    case 3: return imodulo(rank / sx + 1, sy) * sx + rank / (sx * sy) * (sx * sy) + imodulo(rank, sx);
+    case 4: return imodulo(rank / (sx * sy) - 1, sz) * (sx * sy) + imodulo(rank, sx * sy);
+    default: return imodulo(rank / (sx * sy) + 1, sz) * (sx * sy) + imodulo(rank, sx * sy);
+    }
+}
+
+// neighbour at offset (da, db) over the two decomposed axes: (y,z) in 3D, (x,y) in 2D
+int topo_neighbour2(const tgpu_ctx *h, int da, int db)
+{
+    const tgpu_params &P = h->P;
+    int r = P.rank;
+    int ax_a = P.dim == 3 ? 1 : 0, ax_b = P.dim == 3 ? 2 : 1;
+    if (da) r = topo_neighbour(r, P.sizex, P.sizey, P.sizez, 2 * ax_a + (da > 0));
+    if (db) r = topo_neighbour(r, P.sizex, P.sizey, P.sizez, 2 * ax_b + (db > 0));
+    return r;
+}
+
+extern "C" int tgpu_neighbour(int rank, int sizex, int sizey, int sizez, int dir)
+{
+    if (sizex < 1 || sizey < 1 || sizez < 1 || dir < 0 || dir > 5) return -1;
+    return topo_neighbour(rank, sizex, sizey, sizez, dir);
+}
+
+extern "C" int tgpu_ghost_width(int dim, int order, int32_t *nghost, int32_t *nghostz)
+{
+    if ((dim != 2 && dim != 3) || order < 0 || order > 3) return TGPU_EINVAL;
+    *nghost = order <= 1 ? 5 : 7; *nghostz = dim == 2 ? 5 : *nghost;     // fields.F90:166-184
+    return 0;
+}
+
+extern "C" int tgpu_decompose(int dim, int order, int mx0, int my0, int mz0, int sx, int sy, int sz, int rank, int32_t out[6])
+{
+    int32_t ng, ngz;
+    if (tgpu_ghost_width(dim, order, &ng, &ngz)) return TGPU_EINVAL;
+    if (dim == 2) sz = 1;
+    if (sx < 1 || sy < 1 || sz < 1 || rank < 0 || rank >= sx * sy * sz) return TGPU_EINVAL;
+    if (dim == 3 && sx != 1) return TGPU_EINVAL;                         // communications.F90:176-181
+    int gx = mx0 + ng, gy = my0 + ng, gz = dim == 2 ? 1 : mz0 + ngz;
+    // fields.F90:259-280
+    auto local = [&](int rk, int *mx, int *my, int *mz) {
+        *mx = (gx - ng) / sx + ng; *my = (gy - ng) / sy + ng; *mz = dim == 2 ? 1 : (gz - ngz) / sz + ngz;
+        if (rk % sx == sx - 1 && gx != (*mx - ng) * sx + ng) *mx = gx - (*mx - ng) * (sx - 1);
+        if ((rk % (sx * sy)) / sx == sy - 1 && gy != (*my - ng) * sy + ng) *my = gy - (*my - ng) * (sy - 1);
+        if (dim == 3 && rk / (sx * sy) == sz - 1 && gz != (*mz - ngz) * sz + ngz) *mz = gz - (*mz - ngz) * (sz - 1);
+    };
+    int mx, my, mz; local(rank, &mx, &my, &mz);
+    out[0] = mx; out[1] = my; out[2] = mz;
+    int cx = 0, cy = 0, cz = 0, a, b, c;
+    for (int i = 0; i < rank % sx; i++) { local((rank / sx) * sx + i, &a, &b, &c); cx += a - ng; }       // fields.F90:316-328
+    for (int j = 0; j < (rank % (sx * sy)) / sx; j++) { local(j * sx, &a, &b, &c); cy += b - ng; }
+    if (dim == 3) for (int k = 0; k < rank / (sx * sy); k++) { local(k * sx * sy, &a, &b, &c); cz += c - ngz; }
+    out[3] = cx; out[4] = cy; out[5] = cz;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen
+// ---------------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid;
+typedef void *nccl_comm_t;
+typedef int (*fn_GetUniqueId)(nccl_uid *);
+typedef int (*fn_CommInitRank)(nccl_comm_t *, int, nccl_uid, int);
+typedef int (*fn_CommDestroy)(nccl_comm_t);
+typedef int (*fn_Send)(const void *, size_t, int, int, nccl_comm_t, cudaStream_t);
+typedef int (*fn_Recv)(void *, size_t, int, int, nccl_comm_t, cudaStream_t);
+typedef int (*fn_Group)(void);
+typedef const char *(*fn_ErrStr)(int);
+static struct {
+    void *lib; fn_GetUniqueId GetUniqueId; fn_CommInitRank CommInitRank; fn_CommDestroy CommDestroy;
+    fn_Send Send; fn_Recv Recv; fn_Group GroupStart, GroupEnd; fn_ErrStr ErrStr;
+} N;
+
+static int nccl_load()
+{
+    if (N.lib) return 0;
+    const char *names[] = {getenv("TGPU_NCCL_LIB"), "libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; i < 3 && !N.lib; i++) if (names[i] && names[i][0]) N.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!N.lib) { tgpu_set_error(std::string("cannot load NCCL: ") + (dlerror() ? dlerror() : "?")); return TGPU_ENCCL; }
+#define SYM(n) N.n = (fn_##n)dlsym(N.lib, "nccl" #n); if (!N.n) { tgpu_set_error("NCCL symbol missing: nccl" #n); return TGPU_ENCCL; }
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv)
+#undef SYM
+    N.GroupStart = (fn_Group)dlsym(N.lib, "ncclGroupStart"); N.GroupEnd = (fn_Group)dlsym(N.lib, "ncclGroupEnd");
+    N.ErrStr = (fn_ErrStr)dlsym(N.lib, "ncclGetErrorString");
+    if (!N.GroupStart || !N.GroupEnd) { tgpu_set_error("NCCL group symbols missing"); return TGPU_ENCCL; }
+    return 0;
+}
+#define NCK(call) do { int r_ = (call); if (r_ != 0) { tgpu_set_error(std::string(#call) + ": " + (N.ErrStr ? N.ErrStr(r_) : "nccl error")); return TGPU_ENCCL; } } while (0)
+
+extern "C" int tgpu_comm_unique_id(uint8_t id[128])
+{
+    int rc = nccl_load(); if (rc) return rc;
+    nccl_uid u; NCK(N.GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return 0;
+}
+
+extern "C" int tgpu_comm_init(tgpu_ctx *h, const uint8_t id[128])
+{
+    if (!h) return TGPU_EINVAL;
+    if (h->size0 == 1) return 0;
+    int rc = nccl_load(); if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    nccl_uid u; memcpy(u.internal, id, 128);
+    nccl_comm_t c; NCK(N.CommInitRank(&c, h->size0, u, h->P.rank));
+    h->nccl_comm = c;
+    return 0;
+}
+
+int comm_destroy(tgpu_ctx *h)
+{
+    if (h->nccl_comm && N.CommDestroy) N.CommDestroy((nccl_comm_t)h->nccl_comm);
+    h->nccl_comm = nullptr;
+    return 0;
+}
+
+int comm_group_begin(tgpu_ctx *h)
+{
+    if (!h->nccl_comm) { tgpu_set_error("communicator not initialised (tgpu_comm_init)"); return TGPU_ENCCL; }
+    NCK(N.GroupStart());
+    return 0;
+}
+int comm_group_end(tgpu_ctx *h) { NCK(N.GroupEnd()); h->launches++; return 0; }
+int comm_send(tgpu_ctx *h, const void *buf, size_t bytes, int peer)
+{
+    NCK(N.Send(buf, bytes, /*ncclInt8*/ 0, peer, (nccl_comm_t)h->nccl_comm, h->stream));
+    return 0;
+}
+int comm_recv(tgpu_ctx *h, void *buf, size_t bytes, int peer)
+{
+    NCK(N.Recv(buf, bytes, 0, peer, (nccl_comm_t)h->nccl_comm, h->stream));
+    return 0;
+}
+int comm_sendrecv(tgpu_ctx *h, const void *sbuf, size_t sbytes, int dst, void *rbuf, size_t rbytes, int src)
+{
+    int rc = comm_group_begin(h); if (rc) return rc;
+    rc = comm_send(h, sbuf, sbytes, dst); if (rc) return rc;
+    rc = comm_recv(h, rbuf, rbytes, src); if (rc) return rc;
+    return comm_group_end(h);
+}

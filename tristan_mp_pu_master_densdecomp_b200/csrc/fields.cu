@@ -1,0 +1,555 @@
+// Field-side kernels: Yee half/full steps, ghost refresh, current fold, digital filters.
+// Compiled with -fmad=false: every fp32 operation is rounded separately, in the order the
+// reference writes it, so these kernels are bit-exact against the CPU restatement.
+//   advance_b_halfstep  code/fields.F90:586-728      advance_e_fullstep  code/fields.F90:739-870
+//   bc_b1 / bc_e1       code/fieldboundaries.F90:181-263, 306-392
+//   exchange_current    code/fieldboundaries.F90:1768-2189
+//   apply_filter1_opt   code/filter.F90:8-221        apply_filter2_opt   code/optimized_filters.F90:9-227
+#include "tgpu_internal.h"
+
+#define LIDX(i, j, k) ((size_t)((i)-1) + (size_t)mx * ((size_t)((j)-1) + (size_t)my * (size_t)((k)-1)))
+
+// ---------------------------------------------------------------------------------------------
+// stencil index ranges (fields.F90:599-669 for B, :752-819 for E)
+// ---------------------------------------------------------------------------------------------
+static void axis_info(const tgpu_ctx *h, int axis, int *m, int *g, int *per, int *size, int *pos)
+{
+    const tgpu_params &P = h->P;
+    *m = axis == 0 ? P.mx : axis == 1 ? P.my : P.mz;
+    *g = (axis == 2 ? P.nghostz : P.nghost) / 2;
+    *per = axis == 0 ? P.periodicx : axis == 1 ? P.periodicy : P.periodicz;
+    *size = axis == 0 ? P.sizex : axis == 1 ? P.sizey : P.sizez;
+    *pos = axis == 0 ? P.rank % P.sizex : axis == 1 ? (P.rank % (P.sizex * P.sizey)) / P.sizex : P.rank / (P.sizex * P.sizey);
+}
+static void range_b(const tgpu_ctx *h, int axis, int *a1, int *a2)
+{
+    int m, g, per, sz, pos; axis_info(h, axis, &m, &g, &per, &sz, &pos);
+    *a1 = g + 1; *a2 = m - (g + 1);
+    if (!per) {
+        if (pos == 0) { *a1 = 1; *a2 = m - (g + 1); }
+        if (pos == sz - 1) { *a1 = g + 1; *a2 = m - 1; }
+        if (axis == 2 ? (h->size0 == 1) : (h->size0 == 1 || sz == 1)) { *a1 = 1; *a2 = m - 1; }
+    }
+}
+static void range_e(const tgpu_ctx *h, int axis, int *a1, int *a2)
+{
+    int m, g, per, sz, pos; axis_info(h, axis, &m, &g, &per, &sz, &pos);
+    *a1 = g + 1; *a2 = m - (g + 1);
+    if (!per) {
+        if (pos == 0) { *a1 = g; *a2 = m - (g + 1); }
+        if (pos == sz - 1) { *a1 = g + 1; *a2 = m; }
+        if (axis == 2 ? (h->size0 == 1) : (h->size0 == 1 || sz == 1)) { *a1 = g; *a2 = m; }
+    }
+    if (axis == 2) { *a1 = g; *a2 = m; }      // fields.F90:818-819
+}
+
+struct Range3 { int i1, i2, j1, j2, k1, k2; };
+
+// One thread per cell, x fastest => fully coalesced; each array is read/written once per launch.
+template <int DIM>
+__global__ void __launch_bounds__(256) k_bhalf(float *__restrict__ bx, float *__restrict__ by, float *__restrict__ bz,
+                                               const float *__restrict__ ex, const float *__restrict__ ey,
+                                               const float *__restrict__ ez, int mx, int my, Range3 r, float cnst)
+{
+    int i = r.i1 + blockIdx.x * blockDim.x + threadIdx.x;
+    int j = r.j1 + blockIdx.y;
+    int k = r.k1 + blockIdx.z;
+    if (i > r.i2) return;
+    size_t l = LIDX(i, j, k), lip = l + 1, ljp = l + mx;
+    if (DIM == 3) {
+        size_t lkp = l + (size_t)mx * my;
+        bx[l] = bx[l] + cnst * (ey[lkp] - ey[l] - ez[ljp] + ez[l]);
+        by[l] = by[l] + cnst * (ez[lip] - ez[l] - ex[lkp] + ex[l]);
+        bz[l] = bz[l] + cnst * (ex[ljp] - ex[l] - ey[lip] + ey[l]);
+    } else {
+        bx[l] = bx[l] + cnst * (-ez[ljp] + ez[l]);
+        by[l] = by[l] + cnst * (ez[lip] - ez[l]);
+        bz[l] = bz[l] + cnst * (ex[ljp] - ex[l] - ey[lip] + ey[l]);
+    }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_efull(float *__restrict__ ex, float *__restrict__ ey, float *__restrict__ ez,
+                                               const float *__restrict__ bx, const float *__restrict__ by,
+                                               const float *__restrict__ bz, int mx, int my, Range3 r, float cnst)
+{
+    int i = r.i1 + blockIdx.x * blockDim.x + threadIdx.x;
+    int j = r.j1 + blockIdx.y;
+    int k = r.k1 + blockIdx.z;
+    if (i > r.i2) return;
+    size_t l = LIDX(i, j, k), lim = l - 1, ljm = l - mx;
+    if (DIM == 3) {
+        size_t lkm = l - (size_t)mx * my;
+        ex[l] = ex[l] + cnst * (by[lkm] - by[l] - bz[ljm] + bz[l]);
+        ey[l] = ey[l] + cnst * (bz[lim] - bz[l] - bx[lkm] + bx[l]);
+        ez[l] = ez[l] + cnst * (bx[ljm] - bx[l] - by[lim] + by[l]);
+    } else {
+        ex[l] = ex[l] + cnst * (-bz[ljm] + bz[l]);
+        ey[l] = ey[l] + cnst * (bz[lim] - bz[l]);
+        ez[l] = ez[l] + cnst * (bx[ljm] - bx[l] - by[lim] + by[l]);
+    }
+}
+
+int fld_bhalf(tgpu_ctx *h)
+{
+    Range3 r; r.k1 = r.k2 = 1;
+    range_b(h, 0, &r.i1, &r.i2); range_b(h, 1, &r.j1, &r.j2);
+    if (h->P.dim == 3) range_b(h, 2, &r.k1, &r.k2);
+    const float cnst = h->P.corr * (.5f * h->P.c);
+    dim3 grid(cdiv(r.i2 - r.i1 + 1, 256), r.j2 - r.j1 + 1, r.k2 - r.k1 + 1);
+    if (h->P.dim == 3)
+        k_bhalf<3><<<grid, 256, 0, h->stream>>>(h->f[3], h->f[4], h->f[5], h->f[0], h->f[1], h->f[2], h->P.mx, h->P.my, r, cnst);
+    else
+        k_bhalf<2><<<grid, 256, 0, h->stream>>>(h->f[3], h->f[4], h->f[5], h->f[0], h->f[1], h->f[2], h->P.mx, h->P.my, r, cnst);
+    CKK(h);
+    h->need_prim = 1;
+    return 0;
+}
+
+int fld_efull(tgpu_ctx *h)
+{
+    Range3 r; r.k1 = r.k2 = 1;
+    range_e(h, 0, &r.i1, &r.i2); range_e(h, 1, &r.j1, &r.j2);
+    if (h->P.dim == 3) range_e(h, 2, &r.k1, &r.k2);
+    // guard the reference's out-of-bounds reads at the array edge (i-1 with i = g >= 2 is fine)
+    const float cnst = h->P.corr * h->P.c;
+    dim3 grid(cdiv(r.i2 - r.i1 + 1, 256), r.j2 - r.j1 + 1, r.k2 - r.k1 + 1);
+    if (h->P.dim == 3)
+        k_efull<3><<<grid, 256, 0, h->stream>>>(h->f[0], h->f[1], h->f[2], h->f[3], h->f[4], h->f[5], h->P.mx, h->P.my, r, cnst);
+    else
+        k_efull<2><<<grid, 256, 0, h->stream>>>(h->f[0], h->f[1], h->f[2], h->f[3], h->f[4], h->f[5], h->P.mx, h->P.my, r, cnst);
+    CKK(h);
+    h->need_prim = 1;
+    return 0;
+}
+
+int fld_reset(tgpu_ctx *h)
+{
+    for (int c = 0; c < 3; c++) CK(cudaMemsetAsync(h->f[6 + c], 0, (size_t)h->G.lot * sizeof(float), h->stream));
+    return 0;
+}
+
+// e += cur over whole arrays (fields.F90:1391-1393); with SHADOW: cur += shadow; shadow = 0
+__global__ void __launch_bounds__(256) k_add3(float *__restrict__ a0, float *__restrict__ a1, float *__restrict__ a2,
+                                              float *__restrict__ b0, float *__restrict__ b1, float *__restrict__ b2,
+                                              size_t n, int zero_src)
+{
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += stride) {
+        a0[l] = a0[l] + b0[l]; a1[l] = a1[l] + b1[l]; a2[l] = a2[l] + b2[l];
+        if (zero_src) { b0[l] = 0.f; b1[l] = 0.f; b2[l] = 0.f; }
+    }
+}
+int fld_add(tgpu_ctx *h)
+{
+    size_t n = (size_t)h->G.lot;
+    int blocks = (int)((n + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    k_add3<<<blocks, 256, 0, h->stream>>>(h->f[0], h->f[1], h->f[2], h->f[6], h->f[7], h->f[8], n, 0);
+    CKK(h);
+    h->need_prim = 1;
+    return 0;
+}
+int fld_add_shadow(tgpu_ctx *h)
+{
+    size_t n = (size_t)h->G.lot;
+    int blocks = (int)((n + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    k_add3<<<blocks, 256, 0, h->stream>>>(h->f[6], h->f[7], h->f[8], h->shadow[0], h->shadow[1], h->shadow[2], n, 1);
+    CKK(h);
+    return 0;
+}
+
+// node-centred fields for the 3D shaped movers: particles_movedeposit.F90:395-404 / 658-667 / 982-991
+// (cshift is circular).  Quirk Q2: bx_p, by_p are not averaged in k.
+__global__ void __launch_bounds__(256) k_primal(const float *__restrict__ ex, const float *__restrict__ ey,
+                                                const float *__restrict__ ez, const float *__restrict__ bx,
+                                                const float *__restrict__ by, const float *__restrict__ bz,
+                                                float *__restrict__ p0, float *__restrict__ p1, float *__restrict__ p2,
+                                                float *__restrict__ p3, float *__restrict__ p4, float *__restrict__ p5,
+                                                int mx, int my, int mz, int q2)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    int j = blockIdx.y + 1, k = blockIdx.z + 1;
+    if (i > mx) return;
+    int im = i == 1 ? mx : i - 1, jm = j == 1 ? my : j - 1, km = k == 1 ? mz : k - 1;
+    size_t l = LIDX(i, j, k);
+    p0[l] = 0.5f * (ex[l] + ex[LIDX(im, j, k)]);
+    p1[l] = 0.5f * (ey[l] + ey[LIDX(i, jm, k)]);
+    p2[l] = 0.5f * (ez[l] + ez[LIDX(i, j, km)]);
+    float bxp = 0.5f * (bx[l] + bx[LIDX(i, jm, k)]);
+    float byp = 0.5f * (by[l] + by[LIDX(im, j, k)]);
+    if (!q2) {
+        float bxk = 0.5f * (bx[LIDX(i, j, km)] + bx[LIDX(i, jm, km)]);
+        float byk = 0.5f * (by[LIDX(i, j, km)] + by[LIDX(im, j, km)]);
+        bxp = 0.5f * (bxp + bxk); byp = 0.5f * (byp + byk);
+    }
+    p3[l] = bxp; p4[l] = byp;
+    p5[l] = 0.5f * (0.5f * (bz[l] + bz[LIDX(im, j, k)]) + 0.5f * (bz[LIDX(i, jm, k)] + bz[LIDX(im, jm, k)]));
+}
+int fld_primal(tgpu_ctx *h)
+{
+    if (!h->need_prim) return 0;
+    dim3 grid(cdiv(h->P.mx, 256), h->P.my, h->P.mz);
+    k_primal<<<grid, 256, 0, h->stream>>>(h->f[0], h->f[1], h->f[2], h->f[3], h->f[4], h->f[5], h->prim[0], h->prim[1],
+                                         h->prim[2], h->prim[3], h->prim[4], h->prim[5], h->P.mx, h->P.my, h->P.mz,
+                                         (h->P.quirks & TGPU_Q2_BXBY_NO_KAVG) != 0);
+    CKK(h);
+    h->need_prim = 0;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// box copy / pack / unpack over three component arrays at once
+// ---------------------------------------------------------------------------------------------
+struct Box { int lo[3]; int n[3]; };
+struct Arr3 { float *a[3]; };
+
+__device__ __forceinline__ void box_decode(const Box &b, size_t idx, int &c, int &i, int &j, int &k)
+{
+    size_t vol = (size_t)b.n[0] * b.n[1] * b.n[2];
+    c = (int)(idx / vol); size_t r = idx - (size_t)c * vol;
+    i = (int)(r % b.n[0]); r /= b.n[0];
+    j = (int)(r % b.n[1]); k = (int)(r / b.n[1]);
+}
+// mode 0: dst = src ; mode 1: dst += src
+__global__ void __launch_bounds__(256) k_box_copy(Arr3 A, Box src, Box dst, int mx, int my, int mode, size_t total)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int c, i, j, k; box_decode(src, idx, c, i, j, k);
+    size_t ls = LIDX(src.lo[0] + i, src.lo[1] + j, src.lo[2] + k);
+    size_t ld = LIDX(dst.lo[0] + i, dst.lo[1] + j, dst.lo[2] + k);
+    float v = A.a[c][ls];
+    if (mode) A.a[c][ld] = A.a[c][ld] + v; else A.a[c][ld] = v;
+}
+__global__ void __launch_bounds__(256) k_box_get(Arr3 A, Box src, float *__restrict__ buf, int mx, int my, size_t total)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int c, i, j, k; box_decode(src, idx, c, i, j, k);
+    buf[idx] = A.a[c][LIDX(src.lo[0] + i, src.lo[1] + j, src.lo[2] + k)];
+}
+__global__ void __launch_bounds__(256) k_box_put(Arr3 A, Box dst, const float *__restrict__ buf, int mx, int my, int mode, size_t total)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int c, i, j, k; box_decode(dst, idx, c, i, j, k);
+    size_t ld = LIDX(dst.lo[0] + i, dst.lo[1] + j, dst.lo[2] + k);
+    if (mode) A.a[c][ld] = A.a[c][ld] + buf[idx]; else A.a[c][ld] = buf[idx];
+}
+
+static Box full_box(const tgpu_ctx *h)
+{
+    Box b; b.lo[0] = b.lo[1] = b.lo[2] = 1; b.n[0] = h->P.mx; b.n[1] = h->P.my; b.n[2] = h->P.mz; return b;
+}
+static size_t box_total(const Box &b) { return (size_t)3 * b.n[0] * b.n[1] * b.n[2]; }
+
+// Move a box of three arrays from this rank's `src` to the `dst` box of the neighbour that lies in
+// direction `dir_to` (and receive the matching box from the opposite neighbour).  Local when the
+// axis has one rank.  recv_ok = 0 skips the unpack (open boundary, edge rank).
+static int box_shift(tgpu_ctx *h, Arr3 A, Box src, Box dst, int axis, int dir_to, int mode, int recv_ok)
+{
+    int m, g, per, sz, pos; axis_info(h, axis, &m, &g, &per, &sz, &pos);
+    size_t total = box_total(src);
+    if (total == 0) return 0;
+    if (sz == 1) {
+        if (!recv_ok) return 0;
+        k_box_copy<<<cdiv(total, 256), 256, 0, h->stream>>>(A, src, dst, h->P.mx, h->P.my, mode, total);
+        CKK(h);
+        return 0;
+    }
+    if (2 * total > h->halo_floats) { tgpu_set_error("halo scratch too small"); return TGPU_EINVAL; }
+    float *sb = h->halo, *rb = h->halo + total;
+    k_box_get<<<cdiv(total, 256), 256, 0, h->stream>>>(A, src, sb, h->P.mx, h->P.my, total);
+    CKK(h);
+    int to = topo_neighbour(h->P.rank, h->P.sizex, h->P.sizey, h->P.sizez, 2 * axis + (dir_to > 0 ? 1 : 0));
+    int from = topo_neighbour(h->P.rank, h->P.sizex, h->P.sizey, h->P.sizez, 2 * axis + (dir_to > 0 ? 0 : 1));
+    int rc = comm_sendrecv(h, sb, total * sizeof(float), to, rb, total * sizeof(float), from);
+    if (rc) return rc;
+    if (recv_ok) {
+        k_box_put<<<cdiv(total, 256), 256, 0, h->stream>>>(A, dst, rb, h->P.mx, h->P.my, mode, total);
+        CKK(h);
+    }
+    return 0;
+}
+
+// bc_b1 / bc_e1: for iter = 1..g: low ghost g+1-iter <- (-nbr) m-(g+iter); high ghost m-g-1+iter <- (+nbr) g+iter.
+// All g layers of one side move as one box: [1..g] <- [m-2g..m-g-1], [m-g..m-1] <- [g+1..2g].  Axis order x,y,z with
+// full extents in the other axes so that corners propagate (fieldboundaries.F90:186-262).
+int fld_bc(tgpu_ctx *h, int first)
+{
+    Arr3 A; for (int c = 0; c < 3; c++) A.a[c] = h->f[first + c];
+    int naxes = h->P.dim == 3 ? 3 : 2;
+    for (int axis = 0; axis < naxes; axis++) {
+        int m, g, per, sz, pos; axis_info(h, axis, &m, &g, &per, &sz, &pos);
+        if (!per && sz == 1 && axis != 2) continue;           // bc_b1: no copy at all
+        if (!per && sz == 1 && axis == 2) continue;           // copy_layrz2 on a single rank: both receives skipped
+        Box src = full_box(h), dst = full_box(h);
+        // send up: my layers [m-2g, m-g-1] become the + neighbour's low ghosts [1, g]
+        src.lo[axis] = m - 2 * g; src.n[axis] = g; dst.lo[axis] = 1; dst.n[axis] = g;
+        int rc = box_shift(h, A, src, dst, axis, +1, 0, per || pos != 0);
+        if (rc) return rc;
+        // send down: my layers [g+1, 2g] become the - neighbour's high ghosts [m-g, m-1]
+        src.lo[axis] = g + 1; dst.lo[axis] = m - g;
+        rc = box_shift(h, A, src, dst, axis, -1, 0, per || pos != sz - 1);
+        if (rc) return rc;
+    }
+    if (first < 6) h->need_prim = 1;
+    return 0;
+}
+// NOTE on uneven splits: the destination index m-g is evaluated with the receiving rank's m; ranks on one axis
+// line share m except the last one, and a box is always unpacked with the receiver's own geometry above.
+
+// exchange_current: high ghosts [m-g..m] are added to the + neighbour's [g+1..nghost]; low ghosts [1..g] to the
+// - neighbour's [m-nghost+1..m-g-1]; x, then y, then z (fieldboundaries.F90:1796-1813, 1990-2079, 2108-2185).
+int fld_fold(tgpu_ctx *h)
+{
+    Arr3 A; for (int c = 0; c < 3; c++) A.a[c] = h->f[6 + c];
+    int naxes = h->P.dim == 3 ? 3 : 2;
+    for (int axis = 0; axis < naxes; axis++) {
+        int m, g, per, sz, pos; axis_info(h, axis, &m, &g, &per, &sz, &pos);
+        int ng = axis == 2 ? h->P.nghostz : h->P.nghost;
+        if (sz == 1 && !per) continue;
+        Box src = full_box(h), dst = full_box(h);
+        src.lo[axis] = m - g; src.n[axis] = g + 1; dst.lo[axis] = g + 1; dst.n[axis] = g + 1;
+        int rc = box_shift(h, A, src, dst, axis, +1, 1, per || pos != 0);
+        if (rc) return rc;
+        src.lo[axis] = 1; src.n[axis] = g; dst.lo[axis] = m - (ng - 1); dst.n[axis] = g;
+        rc = box_shift(h, A, src, dst, axis, -1, 1, per || pos != sz - 1);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// filter1: one 9/27-point pass for all three components (filter.F90:102-216), ghosts refreshed one
+// layer per pass (filter.F90:71-99).
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(128) k_filter1(Arr3 S, Arr3 D, int mx, int my, int mz, int g, int gz, int q5)
+{
+    const float winv = DIM == 3 ? 1.f / 64.f : 1.f / 16.f;
+    const float w1 = (DIM == 3 ? 4.f : 2.f) * winv, w0 = (DIM == 3 ? 8.f : 4.f) * winv, w2 = (DIM == 3 ? 2.f : 1.f) * winv;
+    const float wz1 = 2.f * winv, wz0 = 4.f * winv, wz2 = 1.f * winv;
+    int i = g + 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    int j = g + 1 + blockIdx.y;
+    int nk = DIM == 3 ? mz - 2 * gz - 1 : 1;
+    int c = blockIdx.z / nk;
+    int k = DIM == 3 ? gz + 1 + blockIdx.z % nk : 1;
+    if (i > mx - (g + 1)) return;
+    int jmax = (c == 2 && q5) ? my - g + 1 : my - (g + 1);
+    if (j > jmax) return;
+    const float *cu = S.a[c];
+#define C(di, dj, dk) cu[LIDX(i + (di), j + (dj), k + (dk))]
+    float t = w1 * C(-1, 0, 0) + w0 * C(0, 0, 0) + w1 * C(1, 0, 0) + w1 * C(0, -1, 0) + w1 * C(0, 1, 0) +
+              w2 * C(-1, 1, 0) + w2 * C(1, 1, 0) + w2 * C(-1, -1, 0) + w2 * C(1, -1, 0);
+    if (DIM == 3) {
+        t = t + wz1 * C(-1, 0, -1) + wz0 * C(0, 0, -1) + wz1 * C(1, 0, -1) + wz1 * C(0, -1, -1) + wz1 * C(0, 1, -1) +
+            wz2 * C(-1, 1, -1) + wz2 * C(1, 1, -1) + wz2 * C(-1, -1, -1) + wz2 * C(1, -1, -1) +
+            wz1 * C(-1, 0, 1) + wz0 * C(0, 0, 1) + wz1 * C(1, 0, 1) + wz1 * C(0, -1, 1) + wz1 * C(0, 1, 1) +
+            wz2 * C(-1, 1, 1) + wz2 * C(1, 1, 1) + wz2 * C(-1, -1, 1) + wz2 * C(1, -1, 1);
+    }
+#undef C
+    D.a[c][LIDX(i, j, k)] = t;
+}
+
+// copy the filtered interior back (filter.F90:121-131)
+__global__ void __launch_bounds__(128) k_filter1_back(Arr3 S, Arr3 D, int mx, int my, int mz, int g, int gz, int dim, int q5)
+{
+    int i = g + 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    int j = g + 1 + blockIdx.y;
+    int nk = dim == 3 ? mz - 2 * gz - 1 : 1;
+    int c = blockIdx.z / nk;
+    int k = dim == 3 ? gz + 1 + blockIdx.z % nk : 1;
+    if (i > mx - (g + 1)) return;
+    int jmax = (c == 2 && q5) ? my - g + 1 : my - (g + 1);
+    if (j > jmax) return;
+    D.a[c][LIDX(i, j, k)] = S.a[c][LIDX(i, j, k)];
+}
+
+int fld_filter1(tgpu_ctx *h)
+{
+    const tgpu_params &P = h->P;
+    Arr3 A, T; for (int c = 0; c < 3; c++) { A.a[c] = h->f[6 + c]; T.a[c] = h->ftmp[c]; }
+    int g = P.nghost / 2, gz = P.nghostz / 2;
+    int q5 = (P.quirks & TGPU_Q5_FILTER_CURZ_J) != 0;
+    int naxes = P.dim == 3 ? 3 : 2;
+    int nk = P.dim == 3 ? P.mz - 2 * gz - 1 : 1;
+    int nj = P.my - 2 * g - 1 + (q5 ? 2 : 0);
+    dim3 grid(cdiv(P.mx - 2 * g - 1, 128), nj, 3 * nk);
+    for (int n = 1; n <= P.ntimes; n++) {
+        for (int axis = 0; axis < naxes; axis++) {
+            int m, ga, per, sz, pos; axis_info(h, axis, &m, &ga, &per, &sz, &pos);
+            Box src = full_box(h), dst = full_box(h);
+            src.n[axis] = dst.n[axis] = 1;
+            // (lt,ls,nt,ns) = (g, m-g-1, m-g, g+1); copy_layr*2_opt on open axes skips the outer receive
+            src.lo[axis] = m - ga - 1; dst.lo[axis] = ga;
+            int rc = box_shift(h, A, src, dst, axis, +1, 0, per || pos != 0);
+            if (rc) return rc;
+            src.lo[axis] = ga + 1; dst.lo[axis] = m - ga;
+            rc = box_shift(h, A, src, dst, axis, -1, 0, per || pos != sz - 1);
+            if (rc) return rc;
+        }
+        if (P.dim == 3) k_filter1<3><<<grid, 128, 0, h->stream>>>(A, T, P.mx, P.my, P.mz, g, gz, q5);
+        else k_filter1<2><<<grid, 128, 0, h->stream>>>(A, T, P.mx, P.my, P.mz, g, gz, q5);
+        CKK(h);
+        k_filter1_back<<<grid, 128, 0, h->stream>>>(T, A, P.mx, P.my, P.mz, g, gz, P.dim, q5);
+        CKK(h);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// filter2: ntimes fixed-end 1-2-1 passes per grid line, along x, then y, then z, for curx, cury, curz
+// (optimized_filters.F90:459-558 and the y/z twins), with ntimes-deep halos fetched once per axis
+// (deep_copy_layr*, :1387-1963).  A CTA stages NL whole extended lines in shared memory and runs
+// all passes there (ping-pong); each global element is read and written exactly once per axis.
+//   line element p in [0, nt)            : low halo  (neighbour cells fin-nt+1+p, or replicated edge)
+//                 p in [nt, nt+ncell)     : cur(str + p - nt)
+//                 p in [nt+ncell, L)      : high halo
+// ---------------------------------------------------------------------------------------------
+struct F2 {
+    int mx, my, mz;
+    int axis, str, ncell, nt;
+    int q_lo[2], q_n[2];       // ranges of the two other axes (a1 < a2)
+    int lowmode, highmode;     // 0 = wrap inside this array, 1 = from halo buffer, 2 = replicate edge
+};
+
+__device__ __forceinline__ size_t f2_addr(const F2 &f, int p_cell, int q1, int q2)
+{
+    int ijk[3];
+    int a1 = f.axis == 0 ? 1 : 0, a2 = f.axis == 2 ? 1 : 2;
+    ijk[f.axis] = p_cell; ijk[a1] = f.q_lo[0] + q1; ijk[a2] = f.q_lo[1] + q2;
+    return (size_t)(ijk[0] - 1) + (size_t)f.mx * ((size_t)(ijk[1] - 1) + (size_t)f.my * (size_t)(ijk[2] - 1));
+}
+
+// smem layout: axis 0 -> [line][p] (p fastest, matches the contiguous global walk); other axes -> [p][line]
+// (line = x index fastest).  Either way consecutive threads touch consecutive shared-memory words.
+template <int NL>
+__global__ void __launch_bounds__(256) k_filter2(float *__restrict__ cur, const float *__restrict__ halo_lo,
+                                                 const float *__restrict__ halo_hi, F2 f)
+{
+    extern __shared__ float sm[];
+    const int L = f.ncell + 2 * f.nt;
+    const int nlines = f.q_n[0] * f.q_n[1];
+    const int line0 = blockIdx.x * NL;
+    const int sp = f.axis == 0 ? 1 : NL, sl = f.axis == 0 ? L : 1;
+    float *A = sm, *B = sm + (size_t)L * NL;
+    for (int t = threadIdx.x; t < L * NL; t += blockDim.x) {
+        int p, ln;
+        if (f.axis == 0) { p = t % L; ln = t / L; } else { ln = t % NL; p = t / NL; }
+        int line = line0 + ln;
+        float v = 0.f;
+        if (line < nlines) {
+            int q1 = line % f.q_n[0], q2 = line / f.q_n[0];
+            int pc = p - f.nt;                      // cell offset relative to str
+            if (pc < 0) {
+                if (f.lowmode == 0) v = cur[f2_addr(f, f.str + f.ncell + pc, q1, q2)];
+                else if (f.lowmode == 1) v = halo_lo[(size_t)p + (size_t)f.nt * line];
+                else v = cur[f2_addr(f, f.str, q1, q2)];
+            } else if (pc >= f.ncell) {
+                if (f.highmode == 0) v = cur[f2_addr(f, f.str + pc - f.ncell, q1, q2)];
+                else if (f.highmode == 1) v = halo_hi[(size_t)(pc - f.ncell) + (size_t)f.nt * line];
+                else v = cur[f2_addr(f, f.str + f.ncell - 1, q1, q2)];
+            } else v = cur[f2_addr(f, f.str + pc, q1, q2)];
+        }
+        A[p * sp + ln * sl] = v;
+    }
+    __syncthreads();
+    for (int n = 0; n < f.nt; n++) {
+        for (int t = threadIdx.x; t < L * NL; t += blockDim.x) {
+            int p, ln;
+            if (f.axis == 0) { p = t % L; ln = t / L; } else { ln = t % NL; p = t / NL; }
+            const int o = p * sp + ln * sl;
+            float v;
+            if (p == 0 || p == L - 1) v = A[o];
+            else v = .25f * A[o - sp] + .5f * A[o] + .25f * A[o + sp];
+            B[o] = v;
+        }
+        __syncthreads();
+        float *t2 = A; A = B; B = t2;
+    }
+    for (int t = threadIdx.x; t < f.ncell * NL; t += blockDim.x) {
+        int p, ln;
+        if (f.axis == 0) { p = t % f.ncell; ln = t / f.ncell; } else { ln = t % NL; p = t / NL; }
+        int line = line0 + ln;
+        if (line < nlines) {
+            int q1 = line % f.q_n[0], q2 = line / f.q_n[0];
+            cur[f2_addr(f, f.str + p, q1, q2)] = A[(p + f.nt) * sp + ln * sl];
+        }
+    }
+}
+
+// pack the nt interior layers next to a face, restricted to the interior of the other axes, in the
+// [line][p] order k_filter2 reads its halo in
+__global__ void __launch_bounds__(256) k_f2_pack(const float *__restrict__ cur, float *__restrict__ buf, F2 f, int first_cell)
+{
+    size_t total = (size_t)f.nt * f.q_n[0] * f.q_n[1];
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int p = (int)(idx % f.nt); int line = (int)(idx / f.nt);
+    int q1 = line % f.q_n[0], q2 = line / f.q_n[0];
+    buf[idx] = cur[f2_addr(f, first_cell + p, q1, q2)];
+}
+
+int fld_filter2(tgpu_ctx *h)
+{
+    const tgpu_params &P = h->P;
+    if (P.ntimes <= 0) return 0;
+    int naxes = P.dim == 3 ? 3 : 2;
+    int lo[3], n[3];
+    for (int a = 0; a < 3; a++) {
+        int m, g, per, sz, pos; axis_info(h, a, &m, &g, &per, &sz, &pos);
+        lo[a] = g + 1; n[a] = m - 2 * g - 1;
+    }
+    if (P.dim == 2) { lo[2] = 1; n[2] = 1; }
+    for (int c = 0; c < 3; c++) {
+        for (int axis = 0; axis < naxes; axis++) {
+            int m, g, per, sz, pos; axis_info(h, axis, &m, &g, &per, &sz, &pos);
+            F2 f; f.mx = P.mx; f.my = P.my; f.mz = P.mz; f.axis = axis; f.str = lo[axis]; f.ncell = n[axis]; f.nt = P.ntimes;
+            int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2;
+            f.q_lo[0] = lo[a1]; f.q_n[0] = n[a1]; f.q_lo[1] = lo[a2]; f.q_n[1] = n[a2];
+            if (f.nt > f.ncell) { tgpu_set_error("filter2: ntimes exceeds the local extent"); return TGPU_EINVAL; }
+            f.lowmode = per ? 0 : 2; f.highmode = per ? 0 : 2;
+            float *hlo = nullptr, *hhi = nullptr;
+            if (sz > 1) {
+                size_t cnt = (size_t)f.nt * f.q_n[0] * f.q_n[1];
+                if (4 * cnt > h->halo_floats) { tgpu_set_error("halo scratch too small for filter2"); return TGPU_EINVAL; }
+                float *s_up = h->halo, *s_dn = h->halo + cnt; hlo = h->halo + 2 * cnt; hhi = h->halo + 3 * cnt;
+                // my last nt cells go up and become the + neighbour's low halo; my first nt cells go down
+                k_f2_pack<<<cdiv(cnt, 256), 256, 0, h->stream>>>(h->f[6 + c], s_up, f, f.str + f.ncell - f.nt); CKK(h);
+                k_f2_pack<<<cdiv(cnt, 256), 256, 0, h->stream>>>(h->f[6 + c], s_dn, f, f.str); CKK(h);
+                int up = topo_neighbour(P.rank, P.sizex, P.sizey, P.sizez, 2 * axis + 1);
+                int dn = topo_neighbour(P.rank, P.sizex, P.sizey, P.sizez, 2 * axis);
+                int rc = comm_group_begin(h); if (rc) return rc;
+                comm_send(h, s_up, cnt * 4, up); comm_recv(h, hlo, cnt * 4, dn);
+                comm_send(h, s_dn, cnt * 4, dn); comm_recv(h, hhi, cnt * 4, up);
+                rc = comm_group_end(h); if (rc) return rc;
+                f.lowmode = (per || pos != 0) ? 1 : 2;
+                f.highmode = (per || pos != sz - 1) ? 1 : 2;
+            }
+            const int L = f.ncell + 2 * f.nt;
+            int nlines = f.q_n[0] * f.q_n[1];
+            // lines per CTA: as many as fit in ~96 KB of ping-pong shared memory, capped at 32
+            int NL = 32;
+            while (NL > 1 && (size_t)2 * L * NL * 4 > 96 * 1024) NL >>= 1;
+            size_t smem = (size_t)2 * L * NL * 4;
+            if (smem > 200 * 1024) { tgpu_set_error("filter2: line too long for shared memory"); return TGPU_EINVAL; }
+#define LAUNCH_F2(NLV)                                                                                              \
+    {                                                                                                              \
+        CK(cudaFuncSetAttribute(k_filter2<NLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        k_filter2<NLV><<<cdiv(nlines, NLV), 256, smem, h->stream>>>(h->f[6 + c], hlo, hhi, f);                     \
+    }
+            switch (NL) {
+            case 32: LAUNCH_F2(32) break;
+            case 16: LAUNCH_F2(16) break;
+            case 8: LAUNCH_F2(8) break;
+            case 4: LAUNCH_F2(4) break;
+            case 2: LAUNCH_F2(2) break;
+            default: LAUNCH_F2(1) break;
+            }
+#undef LAUNCH_F2
+            CKK(h);
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,545 @@
+// Particle-side kernels, generic path: one thread per particle, any order (0..3), 2D and 3D.
+//   mover / mover_{1,2,3}ord       code/particles_movedeposit.F90:98-347, 356-610, 619-933, 943-1271
+//   zigzag / densdecomp_{1,2,3}ord code/particles.F90:550-669, 678-854, 864-1102, 1112-1358
+//   deposit_particles loops B, C   code/particles_movedeposit.F90:1546-1705 (wrap / leave / discard)
+//   reorder_particles_             code/particles.F90:418-497 (counting sort by cell)
+//   exchange_particles, inject_others code/particles.F90:1865-2116, 1368-1852
+// The cell-run (output-stationary) fast path for 3D orders 1 and 2 lives in cellrun.cu.
+#include <cub/device/device_scan.cuh>
+#include "tgpu_internal.h"
+#include "shapes.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// AoS (reference `type particle`, 40 B) <-> device SoA
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_aos2soa(const tgpu_particle *__restrict__ a, Species s, int off, int n)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    tgpu_particle p = a[t];
+    int d = off + t;
+    s.x[d] = p.x; s.y[d] = p.y; s.z[d] = p.z; s.u[d] = p.u; s.v[d] = p.v; s.w[d] = p.w; s.ch[d] = p.ch;
+    s.ind[d] = p.ind; s.tag[d] = (p.proc & 0xFFFFFF) | (p.splitlev << 24);
+}
+__global__ void __launch_bounds__(256) k_soa2aos(tgpu_particle *__restrict__ a, Species s, int off, int n)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int d = off + t;
+    tgpu_particle p;
+    p.x = s.x[d]; p.y = s.y[d]; p.z = s.z[d]; p.u = s.u[d]; p.v = s.v[d]; p.w = s.w[d]; p.ch = s.ch[d];
+    p.ind = s.ind[d]; int tg = s.tag[d]; p.proc = tg & 0xFFFFFF; p.splitlev = (tg >> 24) & 0xFF;
+    a[t] = p;
+}
+
+int prt_append(tgpu_ctx *h, int s, const tgpu_particle *p, int n, bool host)
+{
+    if (n <= 0) return 0;
+    Species &S = h->sp[s];
+    if (S.n + n > h->maxhlf) { tgpu_set_error("particle capacity (maxhlf) exceeded"); return TGPU_EOVERFLOW; }
+    int done = 0;
+    while (done < n) {
+        int chunk = n - done; if ((size_t)chunk > h->stage_particles) chunk = (int)h->stage_particles;
+        const tgpu_particle *src = p + done;
+        if (host) { CK(cudaMemcpyAsync(h->stage, src, (size_t)chunk * sizeof(tgpu_particle), cudaMemcpyHostToDevice, h->stream)); src = h->stage; }
+        k_aos2soa<<<cdiv(chunk, 256), 256, 0, h->stream>>>(src, S, S.n, chunk); CKK(h);
+        S.n += chunk; done += chunk;
+    }
+    return 0;
+}
+int prt_h2d(tgpu_ctx *h, const tgpu_particle *p, int ions, int lecs)
+{
+    if (ions < 0 || lecs < 0 || ions > h->maxhlf || lecs > h->maxhlf) { tgpu_set_error("bad particle counts"); return TGPU_EINVAL; }
+    h->sp[0].n = 0; h->sp[1].n = 0;
+    int rc = prt_append(h, 0, p, ions, true); if (rc) return rc;
+    rc = prt_append(h, 1, p + h->maxhlf, lecs, true); if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int prt_d2h(tgpu_ctx *h, tgpu_particle *p, int *ions, int *lecs)
+{
+    for (int s = 0; s < 2; s++) {
+        Species &S = h->sp[s];
+        tgpu_particle *dst = p + (s ? h->maxhlf : 0);
+        int done = 0;
+        while (done < S.n) {
+            int chunk = S.n - done; if ((size_t)chunk > h->stage_particles) chunk = (int)h->stage_particles;
+            k_soa2aos<<<cdiv(chunk, 256), 256, 0, h->stream>>>(h->stage, S, done, chunk); CKK(h);
+            CK(cudaMemcpyAsync(dst + done, h->stage, (size_t)chunk * sizeof(tgpu_particle), cudaMemcpyDeviceToHost, h->stream));
+            done += chunk;
+        }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    *ions = h->sp[0].n; *lecs = h->sp[1].n;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic mover
+// ---------------------------------------------------------------------------------------------
+struct Fields6 { const float *f[6]; };
+
+template <int ORDER, int DIM>
+__global__ void __launch_bounds__(256) k_move(Species s, int n, Fields6 F, DevGeom G, float qm, float qme_abs)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float x = s.x[t], y = s.y[t], z = s.z[t], u = s.u[t], v = s.v[t], w = s.w[t];
+    const float cinv = 1.f / G.c;
+    const long mx = G.mx, my = G.my;
+    float e0 = 0, e1 = 0, e2 = 0, b0 = 0, b1 = 0, b2 = 0;
+    float qm1 = qm;
+    if (ORDER == 0) {
+        // particles_movedeposit.F90:125-248 : trilinear staggered gather of the zigzag build
+        if (s.ind[t] < 0 && qm > 0) qm1 = qme_abs;
+        const float *ex = F.f[0], *ey = F.f[1], *ez = F.f[2], *bx = F.f[3], *by = F.f[4], *bz = F.f[5];
+        int i = (int)x; float dx = x - i;
+        int j = (int)y; float dy = y - j;
+        int k = (int)z; float dz = z - k;
+        const long ix = 1, iy = mx, iz = DIM == 3 ? mx * my : 0;
+        if (DIM == 2) { k = 1; dz = 0; }
+        long l = (i - 1) + iy * (j - 1) + iz * (k - 1);
+        float f, g;
+        f = ex[l] + ex[l - ix] + dx * (ex[l + ix] - ex[l - ix]);
+        f = f + dy * (ex[l + iy] + ex[l - ix + iy] + dx * (ex[l + ix + iy] - ex[l - ix + iy]) - f);
+        g = ex[l + iz] + ex[l - ix + iz] + dx * (ex[l + ix + iz] - ex[l - ix + iz]);
+        g = g + dy * (ex[l + iy + iz] + ex[l - ix + iy + iz] + dx * (ex[l + ix + iy + iz] - ex[l - ix + iy + iz]) - g);
+        e0 = (f + dz * (g - f)) * (.25f * qm1);
+        f = ey[l] + ey[l - iy] + dy * (ey[l + iy] - ey[l - iy]);
+        f = f + dz * (ey[l + iz] + ey[l - iy + iz] + dy * (ey[l + iy + iz] - ey[l - iy + iz]) - f);
+        g = ey[l + ix] + ey[l - iy + ix] + dy * (ey[l + iy + ix] - ey[l - iy + ix]);
+        g = g + dz * (ey[l + iz + ix] + ey[l - iy + iz + ix] + dy * (ey[l + iy + iz + ix] - ey[l - iy + iz + ix]) - g);
+        e1 = (f + dx * (g - f)) * (.25f * qm1);
+        f = ez[l] + ez[l - iz] + dz * (ez[l + iz] - ez[l - iz]);
+        f = f + dx * (ez[l + ix] + ez[l - iz + ix] + dz * (ez[l + iz + ix] - ez[l - iz + ix]) - f);
+        g = ez[l + iy] + ez[l - iz + iy] + dz * (ez[l + iz + iy] - ez[l - iz + iy]);
+        g = g + dx * (ez[l + ix + iy] + ez[l - iz + ix + iy] + dz * (ez[l + iz + ix + iy] - ez[l - iz + ix + iy]) - g);
+        e2 = (f + dy * (g - f)) * (.25f * qm1);
+        f = bx[l - iy] + bx[l - iy - iz] + dz * (bx[l - iy + iz] - bx[l - iy - iz]);
+        f = bx[l] + bx[l - iz] + dz * (bx[l + iz] - bx[l - iz]) + f +
+            dy * (bx[l + iy] + bx[l + iy - iz] + dz * (bx[l + iy + iz] - bx[l + iy - iz]) - f);
+        g = bx[l + ix - iy] + bx[l + ix - iy - iz] + dz * (bx[l + ix - iy + iz] - bx[l + ix - iy - iz]);
+        g = bx[l + ix] + bx[l + ix - iz] + dz * (bx[l + ix + iz] - bx[l + ix - iz]) + g +
+            dy * (bx[l + ix + iy] + bx[l + ix + iy - iz] + dz * (bx[l + ix + iy + iz] - bx[l + ix + iy - iz]) - g);
+        b0 = (f + dx * (g - f)) * (.125f * qm1 * cinv);
+        f = by[l - iz] + by[l - iz - ix] + dx * (by[l - iz + ix] - by[l - iz - ix]);
+        f = by[l] + by[l - ix] + dx * (by[l + ix] - by[l - ix]) + f +
+            dz * (by[l + iz] + by[l + iz - ix] + dx * (by[l + iz + ix] - by[l + iz - ix]) - f);
+        g = by[l + iy - iz] + by[l + iy - iz - ix] + dx * (by[l + iy - iz + ix] - by[l + iy - iz - ix]);
+        g = by[l + iy] + by[l + iy - ix] + dx * (by[l + iy + ix] - by[l + iy - ix]) + g +
+            dz * (by[l + iy + iz] + by[l + iy + iz - ix] + dx * (by[l + iy + iz + ix] - by[l + iy + iz - ix]) - g);
+        b1 = (f + dy * (g - f)) * (.125f * qm1 * cinv);
+        f = bz[l - ix] + bz[l - ix - iy] + dy * (bz[l - ix + iy] - bz[l - ix - iy]);
+        f = bz[l] + bz[l - iy] + dy * (bz[l + iy] - bz[l - iy]) + f +
+            dx * (bz[l + ix] + bz[l + ix - iy] + dy * (bz[l + ix + iy] - bz[l + ix - iy]) - f);
+        g = bz[l + iz - ix] + bz[l + iz - ix - iy] + dy * (bz[l + iz - ix + iy] - bz[l + iz - ix - iy]);
+        g = bz[l + iz] + bz[l + iz - iy] + dy * (bz[l + iz + iy] - bz[l + iz - iy]) + g +
+            dx * (bz[l + iz + ix] + bz[l + iz + ix - iy] + dy * (bz[l + iz + ix + iy] - bz[l + iz + ix - iy]) - g);
+        b2 = (f + dz * (g - f)) * (.125f * qm1 * cinv);
+    } else {
+        // particles_movedeposit.F90:686-839 (order 2; orders 1 and 3 alike)
+        const float half = 0.5f;
+        float Sxp[8], Syp[8], Szp[8], Sxd[8], Syd[8];
+        int pmin[3], pmax[3], dmin[3], dmax[3];
+        int ip = (int)x, jp = (int)y, kp = (int)z;
+        float dxp = x - ip, dyp = y - jp, dzp = z - kp;
+        int id = (int)(x - half), jd = (int)(y - half), kd = (int)(z - half);
+        float dxd = x - half - id, dyd = y - half - jd, dzd = (z - half) - kd;
+        shape_slots<ORDER>(dxp, 0, Sxp, pmin[0], pmax[0]);
+        shape_slots<ORDER>(dyp, 0, Syp, pmin[1], pmax[1]);
+        shape_slots<ORDER>(dxd, 0, Sxd, dmin[0], dmax[0]);
+        shape_slots<ORDER>(dyd, 0, Syd, dmin[1], dmax[1]);
+        pmin[2] = pmax[2] = dmin[2] = dmax[2] = 3;
+        if (DIM == 3) {
+            float Szd[8];
+            shape_slots<ORDER>(dzp, 0, Szp, pmin[2], pmax[2]);
+            shape_slots<ORDER>(dzd, 0, Szd, dmin[2], dmax[2]);
+        }
+        const bool q1 = ORDER == 2 && (G.quirks & TGPU_Q1_MOVER2_RANGE);
+        int imin[3], imax[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            if (q1) { imin[a] = dmin[a]; imax[a] = dmax[a]; }
+            else if (ORDER == 2 && DIM == 2) { imin[a] = 2; imax[a] = 5; }
+            else { imin[a] = pmin[a]; imax[a] = pmax[a]; }
+        }
+        if (DIM == 3) {
+            for (int i3 = imin[2]; i3 <= imax[2]; i3++)
+                for (int i2 = imin[1]; i2 <= imax[1]; i2++) {
+                    float sacc[6] = {0, 0, 0, 0, 0, 0};
+                    long base = (ip - 3 - 1) + mx * ((jp - 3 + i2 - 1) + my * (long)(kp - 3 + i3 - 1));
+                    for (int i1 = imin[0]; i1 <= imax[0]; i1++) {
+                        float wx = Sxp[i1];
+#pragma unroll
+                        for (int a = 0; a < 6; a++) sacc[a] = sacc[a] + __ldg(&F.f[a][base + i1]) * wx;
+                    }
+                    float wyz_y = Syp[i2], wyz_z = Szp[i3];
+                    e0 = e0 + sacc[0] * wyz_y * wyz_z; e1 = e1 + sacc[1] * wyz_y * wyz_z; e2 = e2 + sacc[2] * wyz_y * wyz_z;
+                    b0 = b0 + sacc[3] * wyz_y * wyz_z; b1 = b1 + sacc[4] * wyz_y * wyz_z; b2 = b2 + sacc[5] * wyz_y * wyz_z;
+                }
+        } else {
+            const float *ex = F.f[0], *ey = F.f[1], *ez = F.f[2], *bx = F.f[3], *by = F.f[4], *bz = F.f[5];
+            for (int i2 = imin[1]; i2 <= imax[1]; i2++)
+                for (int i1 = imin[0]; i1 <= imax[0]; i1++) {
+                    long lpp = (ip - 3 + i1) + mx * (jp - 3 + i2 - 1) - 1;
+                    long lpd = (ip - 3 + i1) + mx * (jd - 3 + i2 - 1) - 1;
+                    long ldp = (id - 3 + i1) + mx * (jp - 3 + i2 - 1) - 1;
+                    long ldd = (id - 3 + i1) + mx * (jd - 3 + i2 - 1) - 1;
+                    e0 = e0 + ex[ldp] * Sxd[i1] * Syp[i2];
+                    e1 = e1 + ey[lpd] * Sxp[i1] * Syd[i2];
+                    e2 = e2 + ez[lpp] * Sxp[i1] * Syp[i2];
+                    b0 = b0 + bx[lpd] * Sxp[i1] * Syd[i2];
+                    b1 = b1 + by[ldp] * Sxd[i1] * Syp[i2];
+                    b2 = b2 + bz[ldd] * Sxd[i1] * Syd[i2];
+                }
+        }
+        e0 = 0.5f * e0 * qm; e1 = 0.5f * e1 * qm; e2 = 0.5f * e2 * qm;
+        b0 = 0.5f * b0 * qm * cinv; b1 = 0.5f * b1 * qm * cinv; b2 = 0.5f * b2 * qm * cinv;
+    }
+    if (G.external_fields) {
+        b0 = b0 + G.ext[3] * 0.5f * qm1 * cinv; b1 = b1 + G.ext[4] * 0.5f * qm1 * cinv; b2 = b2 + G.ext[5] * 0.5f * qm1 * cinv;
+        e0 = e0 + G.ext[0] * 0.5f * qm1; e1 = e1 + G.ext[1] * 0.5f * qm1; e2 = e2 + G.ext[2] * 0.5f * qm1;
+    }
+    push_particle(G.c, G.pusher, e0, e1, e2, b0, b1, b2, x, y, z, u, v, w);
+    s.x[t] = x; s.y[t] = y; s.z[t] = z; s.u[t] = u; s.v[t] = v; s.w[t] = w;
+}
+
+template <int ORDER>
+static int launch_move(tgpu_ctx *h, int s, float qm)
+{
+    Species &S = h->sp[s];
+    if (S.n == 0) return 0;
+    Fields6 F;
+    bool prim = ORDER > 0 && h->P.dim == 3;
+    for (int a = 0; a < 6; a++) F.f[a] = prim ? h->prim[a] : h->f[a];
+    float qa = fabsf(h->P.qme);
+    if (h->P.dim == 3) k_move<ORDER, 3><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, S.n, F, h->G, qm, qa);
+    else k_move<ORDER, 2><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, S.n, F, h->G, qm, qa);
+    CKK(h);
+    return 0;
+}
+
+int prt_move_generic(tgpu_ctx *h)
+{
+    if (h->P.order > 0 && h->P.dim == 3) { int rc = fld_primal(h); if (rc) return rc; }
+    for (int s = 0; s < 2; s++) {
+        float qm = s ? h->P.qme : h->P.qmi;
+        int rc;
+        switch (h->P.order) {
+        case 0: rc = launch_move<0>(h, s, qm); break;
+        case 1: rc = launch_move<1>(h, s, qm); break;
+        case 2: rc = launch_move<2>(h, s, qm); break;
+        default: rc = launch_move<3>(h, s, qm); break;
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic deposit (global fp32 atomics = REDG.ADD.F32)
+// ---------------------------------------------------------------------------------------------
+template <int ORDER, int DIM>
+__global__ void __launch_bounds__(256) k_deposit(Species s, int n, float *__restrict__ curx, float *__restrict__ cury,
+                                                 float *__restrict__ curz, DevGeom G, float qs)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float x2 = s.x[t], y2 = s.y[t], z2 = s.z[t], u = s.u[t], v = s.v[t], w = s.w[t];
+    // particles_movedeposit.F90:1384-1390
+    float invgam = 1.f / sqrtf(1 + u * u + v * v + w * w);
+    float x1 = x2 - u * invgam * G.c, y1 = y2 - v * invgam * G.c, z1 = z2 - w * invgam * G.c;
+    float q = s.ch[t] * qs;
+    const long mx = G.mx, my = G.my;
+#define LI(i, j, k) ((size_t)((i)-1) + (size_t)mx * ((size_t)((j)-1) + (size_t)my * (size_t)((k)-1)))
+    if (ORDER == 0) {
+        // zigzag, particles.F90:578-664
+        int i1 = (int)x1, i2 = (int)x2, j1 = (int)y1, j2 = (int)y2, k1 = (int)z1, k2 = (int)z2;
+        float xr = fminf((float)(min(i1, i2) + 1), fmaxf((float)max(i1, i2), .5f * (x1 + x2)));
+        float yr = fminf((float)(min(j1, j2) + 1), fmaxf((float)max(j1, j2), .5f * (y1 + y2)));
+        float zr = fminf((float)(min(k1, k2) + 1), fmaxf((float)max(k1, k2), .5f * (z1 + z2)));
+        if (DIM == 2) { k1 = 1; k2 = 1; }
+        float Fx1 = -q * (xr - x1), Fy1 = -q * (yr - y1), Fz1 = -q * (zr - z1);
+        float Wx1 = .5f * (x1 + xr) - i1, Wy1 = .5f * (y1 + yr) - j1, Wz1 = DIM == 3 ? .5f * (z1 + zr) - k1 : 0.f;
+        float Wx2 = .5f * (x2 + xr) - i2, Wy2 = .5f * (y2 + yr) - j2, Wz2 = DIM == 3 ? .5f * (z2 + zr) - k2 : 0.f;
+        float Fx2 = -q * (x2 - xr), Fy2 = -q * (y2 - yr), Fz2 = -q * (z2 - zr);
+        atomicAdd(&curx[LI(i1, j1, k1)], Fx1 * (1.f - Wy1) * (1.f - Wz1));
+        atomicAdd(&curx[LI(i1, j1 + 1, k1)], Fx1 * Wy1 * (1.f - Wz1));
+        atomicAdd(&curx[LI(i2, j2, k2)], Fx2 * (1.f - Wy2) * (1.f - Wz2));
+        atomicAdd(&curx[LI(i2, j2 + 1, k2)], Fx2 * Wy2 * (1.f - Wz2));
+        atomicAdd(&cury[LI(i1, j1, k1)], Fy1 * (1.f - Wx1) * (1.f - Wz1));
+        atomicAdd(&cury[LI(i1 + 1, j1, k1)], Fy1 * Wx1 * (1.f - Wz1));
+        atomicAdd(&cury[LI(i2, j2, k2)], Fy2 * (1.f - Wx2) * (1.f - Wz2));
+        atomicAdd(&cury[LI(i2 + 1, j2, k2)], Fy2 * Wx2 * (1.f - Wz2));
+        if (DIM == 3) {
+            atomicAdd(&curx[LI(i1, j1, k1 + 1)], Fx1 * (1 - Wy1) * Wz1);
+            atomicAdd(&curx[LI(i1, j1 + 1, k1 + 1)], Fx1 * Wy1 * Wz1);
+            atomicAdd(&curx[LI(i2, j2, k2 + 1)], Fx2 * (1.f - Wy2) * Wz2);
+            atomicAdd(&curx[LI(i2, j2 + 1, k2 + 1)], Fx2 * Wy2 * Wz2);
+            atomicAdd(&cury[LI(i1, j1, k1 + 1)], Fy1 * (1.f - Wx1) * Wz1);
+            atomicAdd(&cury[LI(i1 + 1, j1, k1 + 1)], Fy1 * Wx1 * Wz1);
+            atomicAdd(&cury[LI(i2, j2, k2 + 1)], Fy2 * (1.f - Wx2) * Wz2);
+            atomicAdd(&cury[LI(i2 + 1, j2, k2 + 1)], Fy2 * Wx2 * Wz2);
+        }
+        atomicAdd(&curz[LI(i1, j1, k1)], Fz1 * (1.f - Wx1) * (1.f - Wy1));
+        atomicAdd(&curz[LI(i1 + 1, j1, k1)], Fz1 * Wx1 * (1.f - Wy1));
+        atomicAdd(&curz[LI(i1, j1 + 1, k1)], Fz1 * (1.f - Wx1) * Wy1);
+        atomicAdd(&curz[LI(i1 + 1, j1 + 1, k1)], Fz1 * Wx1 * Wy1);
+        atomicAdd(&curz[LI(i2, j2, k2)], Fz2 * (1.f - Wx2) * (1.f - Wy2));
+        atomicAdd(&curz[LI(i2 + 1, j2, k2)], Fz2 * Wx2 * (1.f - Wy2));
+        atomicAdd(&curz[LI(i2, j2 + 1, k2)], Fz2 * (1.f - Wx2) * Wy2);
+        atomicAdd(&curz[LI(i2 + 1, j2 + 1, k2)], Fz2 * Wx2 * Wy2);
+    } else {
+        // densdecomp_*: particles.F90:886-1097.  The prefix sums along x (curx), y (cury) and z (curz) are
+        // carried in registers; quirk Q4's stale carries are exactly zero in exact arithmetic and are dropped.
+        const float half = 0.5f, third = 1.f / 3.f;
+        float Sx1[8], Sy1[8], Sz1[8], Sx2[8], Sy2[8], Sz2[8];
+        int i1 = (int)x1, j1 = (int)y1, k1 = (int)z1;
+        int shifti = (int)x2 - i1, shiftj = (int)y2 - j1, shiftk = (int)z2 - k1;
+        float dx1 = x1 - (int)x1, dy1 = y1 - (int)y1, dz1 = z1 - (int)z1;
+        float dx2 = x2 - (int)x2, dy2 = y2 - (int)y2, dz2 = z2 - (int)z2;
+        float deltaz = z2 - z1;
+        int a1, b1, a2, b2, xmin, xmax, ymin, ymax, zmin = 3, zmax = 3;
+        shape_slots<ORDER>(dx1, 0, Sx1, a1, b1); shape_slots<ORDER>(dx2, shifti, Sx2, a2, b2);
+        xmin = min(a1, a2); xmax = max(b1, b2);
+        shape_slots<ORDER>(dy1, 0, Sy1, a1, b1); shape_slots<ORDER>(dy2, shiftj, Sy2, a2, b2);
+        ymin = min(a1, a2); ymax = max(b1, b2);
+        if (DIM == 3) {
+            shape_slots<ORDER>(dz1, 0, Sz1, a1, b1); shape_slots<ORDER>(dz2, shiftk, Sz2, a2, b2);
+            zmin = min(a1, a2); zmax = max(b1, b2);
+        } else k1 = 1;
+        if (DIM == 3) {
+            float cury_prev[8], curz_prev[8][8];
+#pragma unroll
+            for (int a = 0; a < 8; a++) { cury_prev[a] = 0.f;
+#pragma unroll
+                for (int b = 0; b < 8; b++) curz_prev[a][b] = 0.f; }
+            for (int it2 = zmin; it2 <= zmax; it2++) {
+                for (int a = 0; a < 8; a++) cury_prev[a] = 0.f;
+                for (int it1 = ymin; it1 <= ymax; it1++) {
+                    float cxp = 0.f;
+                    for (int it = xmin; it <= xmax; it++) {
+                        size_t l2 = LI(i1 - 3 + it, j1 - 3 + it1, k1 - 3 + it2);
+                        float cx = q * ((Sx2[it] - Sx1[it]) *
+                                        (Sy1[it1] * Sz1[it2] + half * (Sy2[it1] - Sy1[it1]) * Sz1[it2] +
+                                         half * Sy1[it1] * (Sz2[it2] - Sz1[it2]) +
+                                         third * (Sy2[it1] - Sy1[it1]) * (Sz2[it2] - Sz1[it2]))) + cxp;
+                        float cy = q * ((Sy2[it1] - Sy1[it1]) *
+                                        (Sx1[it] * Sz1[it2] + half * (Sx2[it] - Sx1[it]) * Sz1[it2] +
+                                         half * Sx1[it] * (Sz2[it2] - Sz1[it2]) +
+                                         third * (Sx2[it] - Sx1[it]) * (Sz2[it2] - Sz1[it2]))) + cury_prev[it];
+                        float cz = q * ((Sz2[it2] - Sz1[it2]) *
+                                        (Sx1[it] * Sy1[it1] + half * (Sx2[it] - Sx1[it]) * Sy1[it1] +
+                                         half * Sx1[it] * (Sy2[it1] - Sy1[it1]) +
+                                         third * (Sx2[it] - Sx1[it]) * (Sy2[it1] - Sy1[it1]))) + curz_prev[it][it1];
+                        atomicAdd(&curx[l2], cx); atomicAdd(&cury[l2], cy); atomicAdd(&curz[l2], cz);
+                        cxp = cx; cury_prev[it] = cy; curz_prev[it][it1] = cz;
+                    }
+                }
+            }
+        } else {
+            float cury_prev[8];
+#pragma unroll
+            for (int a = 0; a < 8; a++) cury_prev[a] = 0.f;
+            for (int it1 = ymin; it1 <= ymax; it1++) {
+                float cxp = 0.f;
+                for (int it = xmin; it <= xmax; it++) {
+                    size_t l2 = LI(i1 - 3 + it, j1 - 3 + it1, k1);
+                    float cx = q * ((Sx2[it] - Sx1[it]) * (Sy1[it1] + half * (Sy2[it1] - Sy1[it1]))) + cxp;
+                    float cy = q * ((Sy2[it1] - Sy1[it1]) * (Sx1[it] + half * (Sx2[it] - Sx1[it]))) + cury_prev[it];
+                    float cz = -1 * q * deltaz *
+                               (Sx1[it] * Sy1[it1] + half * (Sx2[it] - Sx1[it]) * Sy1[it1] +
+                                half * Sx1[it] * (Sy2[it1] - Sy1[it1]) + third * (Sx2[it] - Sx1[it]) * (Sy2[it1] - Sy1[it1]));
+                    atomicAdd(&curx[l2], cx); atomicAdd(&cury[l2], cy); atomicAdd(&curz[l2], cz);
+                    cxp = cx; cury_prev[it] = cy;
+                }
+            }
+        }
+    }
+#undef LI
+}
+
+template <int ORDER>
+static int launch_deposit(tgpu_ctx *h, int s, float qs)
+{
+    Species &S = h->sp[s];
+    if (S.n == 0) return 0;
+    if (h->P.dim == 3) k_deposit<ORDER, 3><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, S.n, h->f[6], h->f[7], h->f[8], h->G, qs);
+    else k_deposit<ORDER, 2><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, S.n, h->f[6], h->f[7], h->f[8], h->G, qs);
+    CKK(h);
+    return 0;
+}
+
+int prt_deposit_generic(tgpu_ctx *h)
+{
+    for (int s = 0; s < 2; s++) {
+        float qs = s ? h->P.qe : h->P.qi;
+        int rc;
+        switch (h->P.order) {
+        case 0: rc = launch_deposit<0>(h, s, qs); break;
+        case 1: rc = launch_deposit<1>(h, s, qs); break;
+        case 2: rc = launch_deposit<2>(h, s, qs); break;
+        default: rc = launch_deposit<3>(h, s, qs); break;
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// classification + counting sort.  Stayers are keyed by cell (the reference's reorder key,
+// particles.F90:441), leavers by neighbour code, discarded particles by the last bin; one scan and one
+// scatter then (a) sort by cell, (b) compact, (c) partition the outboxes -- loops B and C of
+// deposit_particles and reorder_particles_ in one pass.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void classify(const DevGeom &G, float &x, float &y, float &z, int &code, bool &discard)
+{
+    // particles_movedeposit.F90:1553-1633
+    int dx = 0, dy = 0, dz = 0;
+    if (x < G.minx) dx = -1; else if (x > G.maxx) dx = 1;
+    if (y < G.miny) dy = -1; else if (y > G.maxy) dy = 1;
+    if (z < G.minz) dz = -1; else if (z > G.maxz) dz = 1;
+    bool in = true;
+    if (!G.perx) in = (x + G.mxcum > G.x1in) && (x + G.mxcum < G.x2in);
+    if (!G.pery && in) in = (y + G.mycum > G.y1in) && (y + G.mycum < G.y2in);
+    if (G.dim == 3 && !G.perz && in) in = (z + G.mzcum > G.z1in) && (z + G.mzcum < G.z2in);
+    discard = !in;
+    code = 4;
+    if (!in) return;
+    if (dx < 0) x = x + G.shiftx_lo; else if (dx > 0) x = x - G.shiftx_hi;
+    if (dy < 0) y = y + G.shifty_lo; else if (dy > 0) y = y - G.shifty_hi;
+    if (dz < 0) z = z + G.shiftz_lo; else if (dz > 0) z = z - G.shiftz_hi;
+    int da, db;
+    if (G.dim == 3) { da = G.sendy ? dy : 0; db = G.sendz ? dz : 0; }
+    else { da = G.sendx ? dx : 0; db = G.sendy ? dy : 0; }
+    code = (da + 1) + 3 * (db + 1);
+}
+
+__global__ void __launch_bounds__(256) k_classify_key(Species s, int n, DevGeom G, uint32_t *__restrict__ key,
+                                                      int32_t *__restrict__ slot, int32_t *__restrict__ bincount)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float x = s.x[t], y = s.y[t], z = s.z[t];
+    int code; bool discard;
+    classify(G, x, y, z, code, discard);
+    s.x[t] = x; s.y[t] = y; s.z[t] = z;
+    uint32_t k;
+    if (discard) k = (uint32_t)G.lot + 9u;
+    else if (code != 4) k = (uint32_t)G.lot + (uint32_t)code;
+    else {
+        int i = (int)x, j = (int)y, kk = G.dim == 3 ? (int)z : 1;
+        i = min(max(i, 1), G.mx); j = min(max(j, 1), G.my); kk = min(max(kk, 1), G.mz);
+        k = (uint32_t)((i - 1) + G.mx * ((j - 1) + G.my * (kk - 1)));
+    }
+    key[t] = k;
+    slot[t] = atomicAdd(&bincount[k], 1);
+}
+
+__global__ void __launch_bounds__(256) k_scatter(Species a, Species b, int n, const uint32_t *__restrict__ key,
+                                                 const int32_t *__restrict__ slot, const int32_t *__restrict__ binoff)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int d = binoff[key[t]] + slot[t];
+    b.x[d] = a.x[t]; b.y[d] = a.y[t]; b.z[d] = a.z[t]; b.u[d] = a.u[t]; b.v[d] = a.v[t]; b.w[d] = a.w[t];
+    b.ch[d] = a.ch[t]; b.ind[d] = a.ind[t]; b.tag[d] = a.tag[t];
+}
+
+// After prt_sort: sp[s].n = stayers; h_small[s*16 + c] / [s*16 + 8.. ] hold leaver ranges (offset table of the 11 tail bins).
+int prt_sort(tgpu_ctx *h, bool)
+{
+    const int nb = (int)h->G.lot + TGPU_NBIN_EXTRA;
+    for (int s = 0; s < 2; s++) {
+        Species &S = h->sp[s];
+        int32_t *cnt = h->bincount + (size_t)s * nb;
+        CK(cudaMemsetAsync(cnt, 0, (size_t)nb * sizeof(int32_t), h->stream));
+        if (S.n == 0) continue;
+        k_classify_key<<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, S.n, h->G, h->key[s], h->slot + (size_t)s * h->maxhlf, cnt);
+        CKK(h);
+    }
+    for (int s = 0; s < 2; s++) {
+        size_t bytes = h->cub_bytes;
+        CK(cub::DeviceScan::ExclusiveSum(h->cub_tmp, bytes, h->bincount + (size_t)s * nb, h->binoff + (size_t)s * (nb + 1), nb + 1, h->stream));
+        h->launches++;
+    }
+    for (int s = 0; s < 2; s++) {
+        Species &S = h->sp[s];
+        if (S.n) {
+            k_scatter<<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->key[s], h->slot + (size_t)s * h->maxhlf,
+                                                            h->binoff + (size_t)s * (nb + 1));
+            CKK(h);
+        }
+        CK(cudaMemcpyAsync(h->h_small + s * 16, h->binoff + (size_t)s * (nb + 1) + (size_t)h->G.lot, 11 * sizeof(int32_t),
+                           cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    for (int s = 0; s < 2; s++) {
+        int n_old = h->sp[s].n;
+        Species tmp = h->sp[s]; h->sp[s] = h->alt[s]; h->alt[s] = tmp;
+        // h_small[s*16 + c] = offset of tail bin c (c = 0..9), [10] = total
+        h->sp[s].n = n_old ? h->h_small[s * 16 + 0] : 0;
+        if (!n_old) for (int c = 0; c < 11; c++) h->h_small[s * 16 + c] = 0;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// migration: one round over the (up to) 8 neighbours in the two decomposed axes replaces the reference's
+// z/y/x pairwise SendRecv + second corner round (particles.F90:1904-2112, tristanmainloop.F90:264-275).
+// Leavers sit, already shifted into the destination's frame, in the tail bins written by prt_sort.
+// ---------------------------------------------------------------------------------------------
+int prt_exchange(tgpu_ctx *h)
+{
+    if (h->size0 == 1) return 0;
+    if (!h->nccl_comm) { tgpu_set_error("tgpu_exchange_particles: communicator not initialised (tgpu_comm_init)"); return TGPU_ENCCL; }
+    const int B = h->P.buffsize;
+    int nout[2][9], off[2][9], nin[2][9];
+    for (int s = 0; s < 2; s++) for (int c = 0; c < 9; c++) {
+        off[s][c] = h->h_small[s * 16 + c]; nout[s][c] = h->h_small[s * 16 + c + 1] - h->h_small[s * 16 + c];
+        if (c == 4) nout[s][c] = 0;
+    }
+    // pack: sendbuf[c] = ions then electrons
+    int32_t *hc = h->h_small + 32;          // [c][2] counts out, then [c][2] counts in
+    for (int c = 0; c < 9; c++) {
+        if (c == 4) { hc[2 * c] = hc[2 * c + 1] = 0; continue; }
+        if (nout[0][c] + nout[1][c] > B) { tgpu_set_error("migration outbox overflow (buffsize)"); return TGPU_EOVERFLOW; }
+        int o = 0;
+        for (int s = 0; s < 2; s++) {
+            if (nout[s][c]) { k_soa2aos<<<cdiv(nout[s][c], 256), 256, 0, h->stream>>>(h->sendbuf + (size_t)c * B + o, h->sp[s], off[s][c], nout[s][c]); CKK(h); }
+            o += nout[s][c];
+            hc[2 * c + s] = nout[s][c];
+        }
+    }
+    CK(cudaMemcpyAsync(h->d_small, hc, 18 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    int rc = comm_group_begin(h); if (rc) return rc;
+    for (int c = 0; c < 9; c++) {
+        if (c == 4) continue;
+        int da = c % 3 - 1, db = c / 3 - 1;
+        int to = topo_neighbour2(h, da, db), from = topo_neighbour2(h, -da, -db);
+        comm_send(h, h->d_small + 2 * c, 2 * sizeof(int32_t), to);
+        comm_recv(h, h->d_small + 18 + 2 * c, 2 * sizeof(int32_t), from);
+    }
+    rc = comm_group_end(h); if (rc) return rc;
+    CK(cudaMemcpyAsync(hc + 18, h->d_small + 18, 18 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < 9; c++) for (int s = 0; s < 2; s++) nin[s][c] = c == 4 ? 0 : hc[18 + 2 * c + s];
+    rc = comm_group_begin(h); if (rc) return rc;
+    for (int c = 0; c < 9; c++) {
+        if (c == 4) continue;
+        int da = c % 3 - 1, db = c / 3 - 1;
+        int to = topo_neighbour2(h, da, db), from = topo_neighbour2(h, -da, -db);
+        int ns = nout[0][c] + nout[1][c], nr = nin[0][c] + nin[1][c];
+        if (nr > B) { tgpu_set_error("migration inbox overflow (buffsize)"); return TGPU_EOVERFLOW; }
+        if (ns) comm_send(h, h->sendbuf + (size_t)c * B, (size_t)ns * sizeof(tgpu_particle), to);
+        if (nr) comm_recv(h, h->recvbuf + (size_t)c * B, (size_t)nr * sizeof(tgpu_particle), from);
+    }
+    rc = comm_group_end(h); if (rc) return rc;
+    for (int c = 0; c < 9; c++) {
+        if (c == 4) continue;
+        rc = prt_append(h, 0, h->recvbuf + (size_t)c * B, nin[0][c], false); if (rc) return rc;
+        rc = prt_append(h, 1, h->recvbuf + (size_t)c * B + nin[0][c], nin[1][c], false); if (rc) return rc;
+    }
+    for (int s = 0; s < 2; s++) for (int c = 0; c < 11; c++) h->h_small[s * 16 + c] = h->sp[s].n;   // outboxes consumed
+    return 0;
+}

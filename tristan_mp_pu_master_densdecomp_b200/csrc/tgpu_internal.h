@@ -1,0 +1,103 @@
+// Internal declarations shared by the translation units of libtristan_gpu.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/tristan_gpu.h"
+
+#define TGPU_NDIR 9          // 3x3 neighbour codes over the two decomposed axes; code 4 = stay
+#define TGPU_NBIN_EXTRA 10   // sort bins after the `lot` cell bins: 9 direction codes (4 unused) + discard
+
+struct Species {
+    float *x, *y, *z, *u, *v, *w, *ch;
+    int32_t *ind, *tag;      // tag = proc | splitlev << 24
+    int n;                   // live particles (host copy)
+};
+
+struct DevGeom {             // passed by value to kernels
+    int dim, order;
+    int mx, my, mz;
+    int g, gz;               // nghost/2, nghostz/2
+    int nghost, nghostz;
+    long long lot;
+    float c, corr;
+    int quirks, pusher, external_fields;
+    float ext[6];
+    // classification (particles_movedeposit.F90:1359-1374, 1546-1633)
+    float minx, maxx, miny, maxy, minz, maxz;
+    float shiftx_lo, shiftx_hi, shifty_lo, shifty_hi, shiftz_lo, shiftz_hi;  // amount subtracted when leaving low/high side
+    int sendx, sendy, sendz;   // axis is split across ranks (leavers are sent, not wrapped)
+    int perx, pery, perz;      // periodic flags
+    float x1in, x2in, y1in, y2in, z1in, z2in;
+    int mxcum, mycum, mzcum;
+};
+
+struct tgpu_ctx {
+    tgpu_params P;
+    DevGeom G;
+    int size0, device, maxhlf;
+    std::vector<int> mxl, myl, mzl;
+    float *f[9];             // ex..bz, curx..curz
+    float *prim[6];          // node-centred fields (3D shaped movers)
+    float *ftmp[3];          // filter1 scratch (the reference's `temp`, one per component)
+    float *halo;             // pack/unpack scratch for exchanges and filter2 deep halos
+    size_t halo_floats;
+    Species sp[2], alt[2];
+    uint32_t *key[2];        // cell key per particle (per species)
+    int32_t *slot;           // rank of the particle inside its bin
+    int32_t *bincount, *binoff;   // lot + TGPU_NBIN_EXTRA (+1)
+    void *cub_tmp; size_t cub_bytes;
+    int32_t *d_small, *h_small;   // 64 ints device / pinned host
+    tgpu_particle *stage;    // device AoS staging for h2d/d2h and migration (2*buffsize*9 .. maxhlf)
+    size_t stage_particles;
+    tgpu_particle *sendbuf, *recvbuf;   // TGPU_NDIR * buffsize each
+    int need_prim;           // primal grids stale
+    int fused_pending;       // currents of the last move already deposited into shadow
+    float *shadow[3];
+    int opt_fused;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    void *nccl_comm;         // ncclComm_t
+    int lap;
+    int64_t launches;
+    double phase_ms[TGPU_NPHASE];
+    int timing;
+};
+
+void tgpu_set_error(const std::string &s);
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    tgpu_set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); return TGPU_ECUDA; } } while (0)
+#define CKK(h) do { cudaError_t e_ = cudaGetLastError(); (h)->launches++; if (e_ != cudaSuccess) { \
+    tgpu_set_error(std::string("kernel launch: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+    return TGPU_ECUDA; } } while (0)
+
+static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+// fields.cu
+int fld_bhalf(tgpu_ctx *h);
+int fld_efull(tgpu_ctx *h);
+int fld_reset(tgpu_ctx *h);
+int fld_add(tgpu_ctx *h);
+int fld_primal(tgpu_ctx *h);
+int fld_bc(tgpu_ctx *h, int first);
+int fld_fold(tgpu_ctx *h);
+int fld_filter1(tgpu_ctx *h);
+int fld_filter2(tgpu_ctx *h);
+int fld_add_shadow(tgpu_ctx *h);
+// particles.cu
+int prt_h2d(tgpu_ctx *h, const tgpu_particle *p, int ions, int lecs);
+int prt_d2h(tgpu_ctx *h, tgpu_particle *p, int *ions, int *lecs);
+int prt_append(tgpu_ctx *h, int s, const tgpu_particle *p, int n, bool host);
+int prt_move(tgpu_ctx *h);
+int prt_deposit(tgpu_ctx *h);
+int prt_sort(tgpu_ctx *h, bool classify_only);
+int prt_exchange(tgpu_ctx *h);
+// comm.cu
+int comm_sendrecv(tgpu_ctx *h, const void *sbuf, size_t sbytes, int dst, void *rbuf, size_t rbytes, int src);
+int comm_group_begin(tgpu_ctx *h);
+int comm_group_end(tgpu_ctx *h);
+int comm_send(tgpu_ctx *h, const void *buf, size_t bytes, int peer);
+int comm_recv(tgpu_ctx *h, void *buf, size_t bytes, int peer);
+int topo_neighbour(int rank, int sx, int sy, int sz, int dir);
+int topo_neighbour2(const tgpu_ctx *h, int da, int db);   // neighbour over the two decomposed axes
