@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests import common as T
+import pic_testlib as T
 
 pytestmark = pytest.mark.gpu
 
@@ -121,6 +121,9 @@ def test_deposit(tgm, dim, order, fused):
     T.upload(ctx, r)                       # identical post-move state on both sides
     ctx.reset_currents(); r.call("reset_currents")
     ctx.deposit_particles(); r.call("deposit_particles")
+    # in 3D the reference sends z-leavers through MPI even to itself: complete the migration on both sides
+    ctx.exchange_particles(); ctx.inject_others()
+    w.phase(O.PH_EXCH_P); w.phase(O.PH_INJECT_OTHERS)
     cg = ctx.currents_d2h()
     for c in range(3):
         err = T.max_rel(cg[c], r.arr(6 + c))
@@ -139,6 +142,7 @@ def test_fused_move_then_deposit_matches_separate_calls(tgm, dim, order):
     r = w.ranks[0]
     ctx.move_particles(); ctx.advance_b_halfstep(); ctx.reset_currents(); ctx.deposit_particles()
     r.call("move_particles"); r.call("advance_b_halfstep"); r.call("reset_currents"); r.call("deposit_particles")
+    ctx.exchange_particles(); w.phase(O.PH_EXCH_P); w.phase(O.PH_INJECT_OTHERS)
     cg = ctx.currents_d2h()
     for c in range(3):
         assert T.max_rel(cg[c], r.arr(6 + c)) < 5e-5
@@ -238,13 +242,15 @@ def test_particle_roundtrip_and_append(tgm):
 
 
 def test_errors_are_loud(tgm):
-    P = tgm.make_params(dim=3, order=2, mx0=8, my0=8, mz0=8, sizex=2)
     with pytest.raises(tgm.TristanGPUError):
-        tgm.Context(P)
+        tgm.make_params(dim=3, order=2, mx0=8, my0=8, mz0=8, sizex=2)       # 3D never splits x
+    P = tgm.make_params(dim=3, order=2, mx0=8, my0=8, mz0=8)
+    P.c = 0.7
+    with pytest.raises(tgm.TristanGPUError):
+        tgm.Context(P)                                                    # c >= 0.5 breaks the 6-slot stencils
     P = tgm.make_params(dim=3, order=2, mx0=8, my0=8, mz0=8, maxptl=64)
     ctx = tgm.Context(P)
     big = np.zeros(P.maxptl, tgm.PARTICLE_DTYPE)
     with pytest.raises(tgm.TristanGPUError):
-        ctx.lib.tgpu_particles_h2d.argtypes  # keep linters quiet
         ctx.particles_h2d(big, 40, 0)       # > maxhlf
     ctx.close()

@@ -96,7 +96,8 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     int rc = 0;
     for (int a = 0; a < 9; a++) rc |= dalloc(&h->f[a], lot);
     for (int a = 0; a < 3; a++) { rc |= dalloc(&h->ftmp[a], lot); rc |= dalloc(&h->shadow[a], lot); }
-    for (int a = 0; a < 6; a++) { h->prim[a] = nullptr; if (p->dim == 3 && p->order > 0) rc |= dalloc(&h->prim[a], lot); }
+    h->prim8 = nullptr;
+    if (p->dim == 3 && p->order > 0) rc |= dalloc(&h->prim8, 2 * lot);
     size_t plane = (size_t)p->mx * p->my;
     if ((size_t)p->mx * p->mz > plane) plane = (size_t)p->mx * p->mz;
     if ((size_t)p->my * p->mz > plane) plane = (size_t)p->my * p->mz;
@@ -139,7 +140,7 @@ extern "C" int tgpu_finalize(tgpu_ctx *h)
     comm_destroy(h);
     for (int a = 0; a < 9; a++) cudaFree(h->f[a]);
     for (int a = 0; a < 3; a++) { cudaFree(h->ftmp[a]); cudaFree(h->shadow[a]); }
-    for (int a = 0; a < 6; a++) if (h->prim[a]) cudaFree(h->prim[a]);
+    if (h->prim8) cudaFree(h->prim8);
     cudaFree(h->halo);
     for (int s = 0; s < 2; s++) { free_species(h->sp[s]); free_species(h->alt[s]); cudaFree(h->key[s]); }
     cudaFree(h->slot); cudaFree(h->bincount); cudaFree(h->binoff); cudaFree(h->cub_tmp); cudaFree(h->d_small);

@@ -1,5 +1,252 @@
-// placeholder, replaced below
+// Cell-run kernels: the fast path for 3D, shape orders 1 and 2 (-Ddd1 / -Ddd2).
+//
+// What they replace:  mover_1ord / mover_2ord        code/particles_movedeposit.F90:356-610, 619-933
+//                     densdecomp_1ord / _2ord        code/particles.F90:678-854, 864-1102
+//                     loop A of deposit_particles    code/particles_movedeposit.F90:1381-1401, 1717-1737
+//
+// Design.  Shared-memory fp32 atomics are CAS loops on sm_100 (ATOMS.CAST.SPIN) and a 2nd-order particle touches up
+// to 4x4x4 cells x 3 components, so a scatter-per-particle deposit is atomic-bound far below the HBM roofline.
+// Particles are kept sorted by cell (x fastest) by the counting sort that follows every deposit.  All particles of a
+// cell share the same 4x4x4 output footprint (slots 2..5 of the reference's 6-slot stencil; |dx| < c < 1/2 cell per
+// step keeps both the old and the new shape inside it).  So the deposit is made OUTPUT-STATIONARY:
+//   phase 1 (lane = particle): load SoA, [gather 3x3x3 node-centred fields + Boris push + store], recompute the old
+//           position exactly as the reference does (x - u/gamma*c), build the 1-D factors of the Esirkepov sum and
+//           park them in shared memory (44 floats per particle);
+//   phase 2 (half-warp = one footprint): lane (j,k) of a half-warp owns the 4 x-cells of row (j,k) of the footprint
+//           for all three components = 12 register accumulators.  It walks its 16 particles, reading the factors with
+//           broadcast 128-bit shared loads.  When the cell changes along x the window slides: completed x-planes are
+//           flushed with one fp32 RED per (cell, component) and the registers shift.
+// With ~8 particles per cell and species, that is ~6 global REDs per particle instead of up to 192 atomics, and the
+// arithmetic is the factorised form of Appendix A.3 (Jx = q*Wx(j,k)*prefix_i(dSx), ...).
+// Nothing here depends on the particles being sorted for correctness -- an unsorted tail (fresh arrivals) only makes
+// the window jump and flush more often.
 #include "tgpu_internal.h"
-int cellrun_supported(const tgpu_ctx *) { return 0; }
-int cellrun_move_deposit(tgpu_ctx *) { return TGPU_EINVAL; }
-int cellrun_deposit(tgpu_ctx *) { return TGPU_EINVAL; }
+#include "shapes.cuh"
+
+#define CR_WARPS 8
+#define CR_STRIDE 44
+#define CR_CHUNK 128          // particles per half-warp
+
+struct CRArgs {
+    Species s;
+    long long n;
+    const float4 *prim8;
+    float *cx, *cy, *cz;
+    DevGeom G;
+    float qm, qs;
+};
+
+__device__ __forceinline__ void red3(float *cx, float *cy, float *cz, size_t idx, float vx, float vy, float vz)
+{
+    if (vx != 0.f) atomicAdd(cx + idx, vx);
+    if (vy != 0.f) atomicAdd(cy + idx, vy);
+    if (vz != 0.f) atomicAdd(cz + idx, vz);
+}
+
+template <int ORDER, bool FUSED>
+__global__ void __launch_bounds__(CR_WARPS * 32, 2) k_cellrun(CRArgs A)
+{
+    __shared__ __align__(16) float stage[CR_WARPS][32][CR_STRIDE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, hl = lane & 15;
+    const long long gw = (long long)blockIdx.x * CR_WARPS + warp;
+    const long long base = gw * (2 * CR_CHUNK) + (long long)half * CR_CHUNK;
+    if (gw * (2 * CR_CHUNK) >= A.n) return;                  // whole warp idle (no block-level barriers are used)
+    const DevGeom &G = A.G;
+    const int mx = G.mx, my = G.my;
+    const int j = lane & 3, k = (lane >> 2) & 3;
+    const int loff = (j - 1) + my * (k - 1);
+
+    int wi = 0, wrow = -0x40000000;                          // window cell (1-based i, row id); none yet
+    bool have = false;
+    float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f}, az[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int it = 0; it < CR_CHUNK / 16; ++it) {
+        const long long t = base + it * 16 + hl;
+        float *st = &stage[warp][lane][0];
+        // ------------------------------------------------------------------ phase 1: lane = particle
+        if (t < A.n) {
+            float x = A.s.x[t], y = A.s.y[t], z = A.s.z[t], u = A.s.u[t], v = A.s.v[t], w = A.s.w[t];
+            const float ch = A.s.ch[t];
+            if (FUSED) {
+                constexpr int NW = ORDER == 2 ? 3 : 2;
+                const float half_ = 0.5f;
+                int ip = (int)x, jp = (int)y, kp = (int)z;
+                float dxp = x - ip, dyp = y - jp, dzp = z - kp;
+                float Wx[4], Wy[4], Wz[4];
+                shape_window<ORDER>(dxp, 0, Wx); shape_window<ORDER>(dyp, 0, Wy); shape_window<ORDER>(dzp, 0, Wz);
+                int lox, loy, loz;
+                if (ORDER == 2) {
+                    if (G.quirks & TGPU_Q1_MOVER2_RANGE) {
+                        // Q1: the loop bounds come from the dual (x - 1/2) branch, particles_movedeposit.F90:752-790
+                        float dxd = x - half_ - (int)(x - half_), dyd = y - half_ - (int)(y - half_), dzd = (z - half_) - (int)(z - half_);
+                        lox = dxd <= half_ ? 0 : 1; loy = dyd <= half_ ? 0 : 1; loz = dzd <= half_ ? 0 : 1;
+                    } else { lox = dxp <= half_ ? 0 : 1; loy = dyp <= half_ ? 0 : 1; loz = dzp <= half_ ? 0 : 1; }
+                } else { lox = loy = loz = 1; }
+                float wxs[NW], wys[NW], wzs[NW];
+#pragma unroll
+                for (int a = 0; a < NW; a++) {
+                    wxs[a] = lox ? Wx[a + 1] : Wx[a]; wys[a] = loy ? Wy[a + 1] : Wy[a]; wzs[a] = loz ? Wz[a + 1] : Wz[a];
+                }
+                float e0 = 0, e1 = 0, e2 = 0, b0 = 0, b1 = 0, b2 = 0;
+                const long long nbase = (ip - 2 + lox) + (long long)mx * ((jp - 2 + loy) + (long long)my * (kp - 2 + loz));
+#pragma unroll
+                for (int c3 = 0; c3 < NW; c3++) {
+#pragma unroll
+                    for (int c2 = 0; c2 < NW; c2++) {
+                        float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
+                        const float4 *row = A.prim8 + 2 * (nbase + (long long)mx * (c2 + (long long)my * c3));
+#pragma unroll
+                        for (int c1 = 0; c1 < NW; c1++) {
+                            float4 lo = __ldg(row + 2 * c1), hi = __ldg(row + 2 * c1 + 1);
+                            s0 = s0 + lo.x * wxs[c1]; s1 = s1 + lo.y * wxs[c1]; s2 = s2 + lo.z * wxs[c1];
+                            s3 = s3 + lo.w * wxs[c1]; s4 = s4 + hi.x * wxs[c1]; s5 = s5 + hi.y * wxs[c1];
+                        }
+                        const float wy_ = wys[c2], wz_ = wzs[c3];
+                        e0 = e0 + s0 * wy_ * wz_; e1 = e1 + s1 * wy_ * wz_; e2 = e2 + s2 * wy_ * wz_;
+                        b0 = b0 + s3 * wy_ * wz_; b1 = b1 + s4 * wy_ * wz_; b2 = b2 + s5 * wy_ * wz_;
+                    }
+                }
+                const float cinv = 1.f / G.c, qm = A.qm;
+                e0 = 0.5f * e0 * qm; e1 = 0.5f * e1 * qm; e2 = 0.5f * e2 * qm;
+                b0 = 0.5f * b0 * qm * cinv; b1 = 0.5f * b1 * qm * cinv; b2 = 0.5f * b2 * qm * cinv;
+                if (G.external_fields) {
+                    b0 = b0 + G.ext[3] * 0.5f * qm * cinv; b1 = b1 + G.ext[4] * 0.5f * qm * cinv; b2 = b2 + G.ext[5] * 0.5f * qm * cinv;
+                    e0 = e0 + G.ext[0] * 0.5f * qm; e1 = e1 + G.ext[1] * 0.5f * qm; e2 = e2 + G.ext[2] * 0.5f * qm;
+                }
+                push_particle(G.c, G.pusher, e0, e1, e2, b0, b1, b2, x, y, z, u, v, w);
+                A.s.x[t] = x; A.s.y[t] = y; A.s.z[t] = z; A.s.u[t] = u; A.s.v[t] = v; A.s.w[t] = w;
+            }
+            // deposit_particles loop A: old position recomputed from the new one (particles_movedeposit.F90:1384-1390)
+            const float invgam = 1.f / sqrtf(1 + u * u + v * v + w * w);
+            const float x1 = x - u * invgam * G.c, y1 = y - v * invgam * G.c, z1 = z - w * invgam * G.c;
+            const float q = ch * A.qs;
+            const int i1 = (int)x1, j1 = (int)y1, k1 = (int)z1;
+            const float third = 1.f / 3.f;
+            float S1[4], S2[4];
+            // x: q*prefix(dS), XA = S1 + dS/2, XB = S1/2 + dS/3
+            shape_window<ORDER>(x1 - i1, 0, S1); shape_window<ORDER>(x - (int)x, (int)x - i1, S2);
+            {
+                float d0 = S2[0] - S1[0], d1 = S2[1] - S1[1], d2 = S2[2] - S1[2], d3 = S2[3] - S1[3];
+                float p0 = d0, p1 = p0 + d1, p2 = p1 + d2, p3 = p2 + d3;
+                *(float4 *)(st + 0) = make_float4(q * p0, q * p1, q * p2, q * p3);
+                *(float4 *)(st + 4) = make_float4(S1[0] + 0.5f * d0, S1[1] + 0.5f * d1, S1[2] + 0.5f * d2, S1[3] + 0.5f * d3);
+                *(float4 *)(st + 8) = make_float4(0.5f * S1[0] + third * d0, 0.5f * S1[1] + third * d1,
+                                                  0.5f * S1[2] + third * d2, 0.5f * S1[3] + third * d3);
+            }
+            // y: per j (Sy1, dSy, q*prefix_j(dSy), i1)
+            shape_window<ORDER>(y1 - j1, 0, S1); shape_window<ORDER>(y - (int)y, (int)y - j1, S2);
+            {
+                float d0 = S2[0] - S1[0], d1 = S2[1] - S1[1], d2 = S2[2] - S1[2], d3 = S2[3] - S1[3];
+                float p0 = d0, p1 = p0 + d1, p2 = p1 + d2, p3 = p2 + d3;
+                const float fi = __int_as_float(i1);
+                *(float4 *)(st + 12) = make_float4(S1[0], d0, q * p0, fi);
+                *(float4 *)(st + 16) = make_float4(S1[1], d1, q * p1, fi);
+                *(float4 *)(st + 20) = make_float4(S1[2], d2, q * p2, fi);
+                *(float4 *)(st + 24) = make_float4(S1[3], d3, q * p3, fi);
+            }
+            // z: per k (Sz1, dSz, q*prefix_k(dSz), row id)
+            shape_window<ORDER>(z1 - k1, 0, S1); shape_window<ORDER>(z - (int)z, (int)z - k1, S2);
+            {
+                float d0 = S2[0] - S1[0], d1 = S2[1] - S1[1], d2 = S2[2] - S1[2], d3 = S2[3] - S1[3];
+                float p0 = d0, p1 = p0 + d1, p2 = p1 + d2, p3 = p2 + d3;
+                const float fr = __int_as_float((j1 - 1) + my * (k1 - 1));
+                *(float4 *)(st + 28) = make_float4(S1[0], d0, q * p0, fr);
+                *(float4 *)(st + 32) = make_float4(S1[1], d1, q * p1, fr);
+                *(float4 *)(st + 36) = make_float4(S1[2], d2, q * p2, fr);
+                *(float4 *)(st + 40) = make_float4(S1[3], d3, q * p3, fr);
+            }
+        }
+        __syncwarp();
+        // ------------------------------------------------------------------ phase 2: half-warp = footprint
+        long long rem = A.n - (base + it * 16);
+        const int cnt = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
+        for (int tt = 0; tt < cnt; ++tt) {
+            const float4 *sp = (const float4 *)&stage[warp][(half << 4) + tt][0];
+            const float4 yv = sp[3 + j], zv = sp[7 + k];
+            const int ni = __float_as_int(yv.w), nrow = __float_as_int(zv.w);
+            if (!have || ni != wi || nrow != wrow) {
+                if (have) {
+                    const size_t idx0 = (size_t)((long long)mx * (wrow + loff) + (wi - 2));
+                    const int di = ni - wi;
+                    if (nrow == wrow && di > 0 && di < 4) {
+                        // slide along x: planes 0..di-1 are complete
+                        red3(A.cx, A.cy, A.cz, idx0, ax[0], ay[0], az[0]);
+                        if (di > 1) red3(A.cx, A.cy, A.cz, idx0 + 1, ax[1], ay[1], az[1]);
+                        if (di > 2) red3(A.cx, A.cy, A.cz, idx0 + 2, ax[2], ay[2], az[2]);
+                        if (di == 1) {
+                            ax[0] = ax[1]; ax[1] = ax[2]; ax[2] = ax[3]; ax[3] = 0.f;
+                            ay[0] = ay[1]; ay[1] = ay[2]; ay[2] = ay[3]; ay[3] = 0.f;
+                            az[0] = az[1]; az[1] = az[2]; az[2] = az[3]; az[3] = 0.f;
+                        } else if (di == 2) {
+                            ax[0] = ax[2]; ax[1] = ax[3]; ax[2] = 0.f; ax[3] = 0.f;
+                            ay[0] = ay[2]; ay[1] = ay[3]; ay[2] = 0.f; ay[3] = 0.f;
+                            az[0] = az[2]; az[1] = az[3]; az[2] = 0.f; az[3] = 0.f;
+                        } else {
+                            ax[0] = ax[3]; ax[1] = 0.f; ax[2] = 0.f; ax[3] = 0.f;
+                            ay[0] = ay[3]; ay[1] = 0.f; ay[2] = 0.f; ay[3] = 0.f;
+                            az[0] = az[3]; az[1] = 0.f; az[2] = 0.f; az[3] = 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < 4; s++) { red3(A.cx, A.cy, A.cz, idx0 + s, ax[s], ay[s], az[s]); ax[s] = 0.f; ay[s] = 0.f; az[s] = 0.f; }
+                    }
+                }
+                wi = ni; wrow = nrow; have = true;
+            }
+            const float4 qpsx = sp[0], xa = sp[1], xb = sp[2];
+            const float sy1 = yv.x, dsy = yv.y, qpsy = yv.z;
+            const float sz1 = zv.x, dsz = zv.y, qpsz = zv.z;
+            const float ya = sy1 + 0.5f * dsy, yb = 0.5f * sy1 + (1.f / 3.f) * dsy;
+            const float wx = ya * sz1 + yb * dsz;          // Wx(j,k)
+            const float a = qpsy * sz1, b = qpsy * dsz;    // Jy = XA*a + XB*b
+            const float c = qpsz * sy1, d = qpsz * dsy;    // Jz = XA*c + XB*d
+            ax[0] += qpsx.x * wx; ax[1] += qpsx.y * wx; ax[2] += qpsx.z * wx; ax[3] += qpsx.w * wx;
+            ay[0] += xa.x * a + xb.x * b; ay[1] += xa.y * a + xb.y * b; ay[2] += xa.z * a + xb.z * b; ay[3] += xa.w * a + xb.w * b;
+            az[0] += xa.x * c + xb.x * d; az[1] += xa.y * c + xb.y * d; az[2] += xa.z * c + xb.z * d; az[3] += xa.w * c + xb.w * d;
+        }
+        __syncwarp();
+    }
+    if (have) {
+        const size_t idx0 = (size_t)((long long)mx * (wrow + loff) + (wi - 2));
+#pragma unroll
+        for (int s = 0; s < 4; s++) red3(A.cx, A.cy, A.cz, idx0 + s, ax[s], ay[s], az[s]);
+    }
+}
+
+int cellrun_supported(const tgpu_ctx *h)
+{
+    return h->P.dim == 3 && (h->P.order == 1 || h->P.order == 2);
+}
+
+template <bool FUSED>
+static int launch(tgpu_ctx *h, float *cx, float *cy, float *cz)
+{
+    for (int s = 0; s < 2; s++) {
+        Species &S = h->sp[s];
+        if (S.n == 0) continue;
+        CRArgs A;
+        A.s = S; A.n = S.n; A.prim8 = h->prim8; A.cx = cx; A.cy = cy; A.cz = cz; A.G = h->G;
+        A.qm = s ? h->P.qme : h->P.qmi; A.qs = s ? h->P.qe : h->P.qi;
+        long long warps = (S.n + 2 * CR_CHUNK - 1) / (2 * CR_CHUNK);
+        int blocks = (int)((warps + CR_WARPS - 1) / CR_WARPS);
+        if (h->P.order == 2) k_cellrun<2, FUSED><<<blocks, CR_WARPS * 32, 0, h->stream>>>(A);
+        else k_cellrun<1, FUSED><<<blocks, CR_WARPS * 32, 0, h->stream>>>(A);
+        CKK(h);
+    }
+    return 0;
+}
+
+// tgpu_move_particles fast path: gather + push + deposit in one pass over the particles.  The currents go to shadow[]
+// because mainloop resets cur between move_particles and deposit_particles (tristanmainloop.F90:134-183).
+int cellrun_move_deposit(tgpu_ctx *h)
+{
+    int rc = fld_primal(h); if (rc) return rc;
+    return launch<true>(h, h->shadow[0], h->shadow[1], h->shadow[2]);
+}
+
+// tgpu_deposit_particles fast path when the particles were moved elsewhere (mirror mode, tests)
+int cellrun_deposit(tgpu_ctx *h)
+{
+    return launch<false>(h, h->f[6], h->f[7], h->f[8]);
+}

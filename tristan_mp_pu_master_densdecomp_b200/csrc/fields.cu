@@ -159,22 +159,22 @@ int fld_add_shadow(tgpu_ctx *h)
 }
 
 // node-centred fields for the 3D shaped movers: particles_movedeposit.F90:395-404 / 658-667 / 982-991
-// (cshift is circular).  Quirk Q2: bx_p, by_p are not averaged in k.
+// (cshift is circular).  Quirk Q2: bx_p, by_p are not averaged in k.  The six components of a node are
+// interleaved (ex,ey,ez,bx | by,bz,0,0) = 32 B so that the gather issues two 128-bit loads per node.
 __global__ void __launch_bounds__(256) k_primal(const float *__restrict__ ex, const float *__restrict__ ey,
                                                 const float *__restrict__ ez, const float *__restrict__ bx,
                                                 const float *__restrict__ by, const float *__restrict__ bz,
-                                                float *__restrict__ p0, float *__restrict__ p1, float *__restrict__ p2,
-                                                float *__restrict__ p3, float *__restrict__ p4, float *__restrict__ p5,
-                                                int mx, int my, int mz, int q2)
+                                                float4 *__restrict__ prim8, int mx, int my, int mz, int q2)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     int j = blockIdx.y + 1, k = blockIdx.z + 1;
     if (i > mx) return;
     int im = i == 1 ? mx : i - 1, jm = j == 1 ? my : j - 1, km = k == 1 ? mz : k - 1;
     size_t l = LIDX(i, j, k);
-    p0[l] = 0.5f * (ex[l] + ex[LIDX(im, j, k)]);
-    p1[l] = 0.5f * (ey[l] + ey[LIDX(i, jm, k)]);
-    p2[l] = 0.5f * (ez[l] + ez[LIDX(i, j, km)]);
+    float4 lo, hi;
+    lo.x = 0.5f * (ex[l] + ex[LIDX(im, j, k)]);
+    lo.y = 0.5f * (ey[l] + ey[LIDX(i, jm, k)]);
+    lo.z = 0.5f * (ez[l] + ez[LIDX(i, j, km)]);
     float bxp = 0.5f * (bx[l] + bx[LIDX(i, jm, k)]);
     float byp = 0.5f * (by[l] + by[LIDX(im, j, k)]);
     if (!q2) {
@@ -182,16 +182,17 @@ __global__ void __launch_bounds__(256) k_primal(const float *__restrict__ ex, co
         float byk = 0.5f * (by[LIDX(i, j, km)] + by[LIDX(im, j, km)]);
         bxp = 0.5f * (bxp + bxk); byp = 0.5f * (byp + byk);
     }
-    p3[l] = bxp; p4[l] = byp;
-    p5[l] = 0.5f * (0.5f * (bz[l] + bz[LIDX(im, j, k)]) + 0.5f * (bz[LIDX(i, jm, k)] + bz[LIDX(im, jm, k)]));
+    lo.w = bxp; hi.x = byp;
+    hi.y = 0.5f * (0.5f * (bz[l] + bz[LIDX(im, j, k)]) + 0.5f * (bz[LIDX(i, jm, k)] + bz[LIDX(im, jm, k)]));
+    hi.z = 0.f; hi.w = 0.f;
+    prim8[2 * l] = lo; prim8[2 * l + 1] = hi;
 }
 int fld_primal(tgpu_ctx *h)
 {
     if (!h->need_prim) return 0;
     dim3 grid(cdiv(h->P.mx, 256), h->P.my, h->P.mz);
-    k_primal<<<grid, 256, 0, h->stream>>>(h->f[0], h->f[1], h->f[2], h->f[3], h->f[4], h->f[5], h->prim[0], h->prim[1],
-                                         h->prim[2], h->prim[3], h->prim[4], h->prim[5], h->P.mx, h->P.my, h->P.mz,
-                                         (h->P.quirks & TGPU_Q2_BXBY_NO_KAVG) != 0);
+    k_primal<<<grid, 256, 0, h->stream>>>(h->f[0], h->f[1], h->f[2], h->f[3], h->f[4], h->f[5], h->prim8, h->P.mx, h->P.my,
+                                         h->P.mz, (h->P.quirks & TGPU_Q2_BXBY_NO_KAVG) != 0);
     CKK(h);
     h->need_prim = 0;
     return 0;

@@ -77,7 +77,7 @@ int prt_d2h(tgpu_ctx *h, tgpu_particle *p, int *ions, int *lecs)
 // ---------------------------------------------------------------------------------------------
 // generic mover
 // ---------------------------------------------------------------------------------------------
-struct Fields6 { const float *f[6]; };
+struct Fields6 { const float *f[6]; const float4 *prim8; };
 
 template <int ORDER, int DIM>
 __global__ void __launch_bounds__(256) k_move(Species s, int n, Fields6 F, DevGeom G, float qm, float qme_abs)
@@ -170,8 +170,9 @@ __global__ void __launch_bounds__(256) k_move(Species s, int n, Fields6 F, DevGe
                     long base = (ip - 3 - 1) + mx * ((jp - 3 + i2 - 1) + my * (long)(kp - 3 + i3 - 1));
                     for (int i1 = imin[0]; i1 <= imax[0]; i1++) {
                         float wx = Sxp[i1];
-#pragma unroll
-                        for (int a = 0; a < 6; a++) sacc[a] = sacc[a] + __ldg(&F.f[a][base + i1]) * wx;
+                        float4 lo = __ldg(&F.prim8[2 * (base + i1)]), hi = __ldg(&F.prim8[2 * (base + i1) + 1]);
+                        sacc[0] = sacc[0] + lo.x * wx; sacc[1] = sacc[1] + lo.y * wx; sacc[2] = sacc[2] + lo.z * wx;
+                        sacc[3] = sacc[3] + lo.w * wx; sacc[4] = sacc[4] + hi.x * wx; sacc[5] = sacc[5] + hi.y * wx;
                     }
                     float wyz_y = Syp[i2], wyz_z = Szp[i3];
                     e0 = e0 + sacc[0] * wyz_y * wyz_z; e1 = e1 + sacc[1] * wyz_y * wyz_z; e2 = e2 + sacc[2] * wyz_y * wyz_z;
@@ -210,8 +211,8 @@ static int launch_move(tgpu_ctx *h, int s, float qm)
     Species &S = h->sp[s];
     if (S.n == 0) return 0;
     Fields6 F;
-    bool prim = ORDER > 0 && h->P.dim == 3;
-    for (int a = 0; a < 6; a++) F.f[a] = prim ? h->prim[a] : h->f[a];
+    for (int a = 0; a < 6; a++) F.f[a] = h->f[a];
+    F.prim8 = h->prim8;
     float qa = fabsf(h->P.qme);
     if (h->P.dim == 3) k_move<ORDER, 3><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, S.n, F, h->G, qm, qa);
     else k_move<ORDER, 2><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, S.n, F, h->G, qm, qa);

@@ -39,7 +39,7 @@ struct tgpu_ctx {
     int size0, device, maxhlf;
     std::vector<int> mxl, myl, mzl;
     float *f[9];             // ex..bz, curx..curz
-    float *prim[6];          // node-centred fields (3D shaped movers)
+    float4 *prim8;           // node-centred fields, 8 floats per node (3D shaped movers)
     float *ftmp[3];          // filter1 scratch (the reference's `temp`, one per component)
     float *halo;             // pack/unpack scratch for exchanges and filter2 deep halos
     size_t halo_floats;
@@ -48,7 +48,7 @@ struct tgpu_ctx {
     int32_t *slot;           // rank of the particle inside its bin
     int32_t *bincount, *binoff;   // lot + TGPU_NBIN_EXTRA (+1)
     void *cub_tmp; size_t cub_bytes;
-    int32_t *d_small, *h_small;   // 64 ints device / pinned host
+    int32_t *d_small, *h_small;   // 128 ints device / pinned host
     tgpu_particle *stage;    // device AoS staging for h2d/d2h and migration (2*buffsize*9 .. maxhlf)
     size_t stage_particles;
     tgpu_particle *sendbuf, *recvbuf;   // TGPU_NDIR * buffsize each
