@@ -125,7 +125,7 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
         rc |= dalloc(&h->sendbuf, (size_t)TGPU_NDIR * p->buffsize); rc |= dalloc(&h->recvbuf, (size_t)TGPU_NDIR * p->buffsize);
     }
     if (rc) { tgpu_set_error("device allocation failed: " + g_err); return TGPU_ECUDA; }
-    h->need_prim = 1; h->fused_pending = 0; h->opt_fused = 1; h->nccl_comm = nullptr; h->lap = 0; h->launches = 0; h->timing = 0;
+    h->need_prim = 1; h->fused_pending = 0; h->keys_valid = 0; h->opt_fused = 1; h->nccl_comm = nullptr; h->lap = 0; h->launches = 0; h->timing = 0;
     for (int i = 0; i < TGPU_NPHASE; i++) h->phase_ms[i] = 0;
     CK(cudaDeviceSynchronize());
     *out = h;

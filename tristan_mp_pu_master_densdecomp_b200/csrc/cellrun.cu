@@ -9,9 +9,10 @@
 // Particles are kept sorted by cell (x fastest) by the counting sort that follows every deposit.  All particles of a
 // cell share the same 4x4x4 output footprint (slots 2..5 of the reference's 6-slot stencil; |dx| < c < 1/2 cell per
 // step keeps both the old and the new shape inside it).  So the deposit is made OUTPUT-STATIONARY:
-//   phase 1 (lane = particle): load SoA, [gather 3x3x3 node-centred fields + Boris push + store], recompute the old
-//           position exactly as the reference does (x - u/gamma*c), build the 1-D factors of the Esirkepov sum and
-//           park them in shared memory (44 floats per particle);
+//   phase 1 (lane = particle): load SoA, [gather node-centred fields + Boris push + store + sort key of the new cell],
+//           build the 1-D factors of the Esirkepov sum from the old and new shapes and park them in shared memory
+//           (44 floats per particle).  Deposit-only launches recompute the old position as the reference does
+//           (x - u/gamma*c); fused launches use the gather's shape at the true pre-push position (equal to round-off);
 //   phase 2 (half-warp = one footprint): lane (j,k) of a half-warp owns the 4 x-cells of row (j,k) of the footprint
 //           for all three components = 12 register accumulators.  It walks its 16 particles, reading the factors with
 //           broadcast 128-bit shared loads.  When the cell changes along x the window slides: completed x-planes are
@@ -34,6 +35,8 @@ struct CRArgs {
     float *cx, *cy, *cz;
     DevGeom G;
     float qm, qs;
+    uint32_t *key;            // FUSED: sort key of the pushed particle (prt_sort skips its classify pass)
+    int32_t *slot, *bincount;
 };
 
 __device__ __forceinline__ void red3(float *cx, float *cy, float *cz, size_t idx, float vx, float vy, float vz)
@@ -41,6 +44,74 @@ __device__ __forceinline__ void red3(float *cx, float *cy, float *cz, size_t idx
     if (vx != 0.f) atomicAdd(cx + idx, vx);
     if (vy != 0.f) atomicAdd(cy + idx, vy);
     if (vz != 0.f) atomicAdd(cz + idx, vz);
+}
+
+// sum over an NW^3 block of node-centred fields, in the reference's order: x innermost (sum()), then *Sy*Sz
+// (particles_movedeposit.F90:801-815)
+template <int NW>
+__device__ __forceinline__ void gather_nodes(const float4 *__restrict__ prim8, long long nbase, int mx, int my,
+                                             const float *wxs, const float *wys, const float *wzs,
+                                             float &e0, float &e1, float &e2, float &b0, float &b1, float &b2)
+{
+#pragma unroll
+    for (int c3 = 0; c3 < NW; c3++) {
+#pragma unroll
+        for (int c2 = 0; c2 < NW; c2++) {
+            float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
+            const float4 *row = prim8 + 2 * (nbase + (long long)mx * (c2 + (long long)my * c3));
+#pragma unroll
+            for (int c1 = 0; c1 < NW; c1++) {
+                float4 lo = __ldg(row + 2 * c1), hi = __ldg(row + 2 * c1 + 1);
+                s0 = s0 + lo.x * wxs[c1]; s1 = s1 + lo.y * wxs[c1]; s2 = s2 + lo.z * wxs[c1];
+                s3 = s3 + lo.w * wxs[c1]; s4 = s4 + hi.x * wxs[c1]; s5 = s5 + hi.y * wxs[c1];
+            }
+            const float wy_ = wys[c2], wz_ = wzs[c3];
+            e0 = e0 + s0 * wy_ * wz_; e1 = e1 + s1 * wy_ * wz_; e2 = e2 + s2 * wy_ * wz_;
+            b0 = b0 + s3 * wy_ * wz_; b1 = b1 + s4 * wy_ * wz_; b2 = b2 + s5 * wy_ * wz_;
+        }
+    }
+}
+
+// 1-D factors of one axis -> shared staging.  MODE 0: x (q*prefix, XA, XB); MODE 1: y/z rows (S1, dS, q*prefix, tag)
+template <int MODE>
+__device__ __forceinline__ void stage_axis(float *st, const float S1[4], const float S2[4], float q, float tag)
+{
+    const float third = 1.f / 3.f;
+    const float d0 = S2[0] - S1[0], d1 = S2[1] - S1[1], d2 = S2[2] - S1[2], d3 = S2[3] - S1[3];
+    const float p0 = d0, p1 = p0 + d1, p2 = p1 + d2, p3 = p2 + d3;
+    if (MODE == 0) {
+        *(float4 *)(st + 0) = make_float4(q * p0, q * p1, q * p2, q * p3);
+        *(float4 *)(st + 4) = make_float4(S1[0] + 0.5f * d0, S1[1] + 0.5f * d1, S1[2] + 0.5f * d2, S1[3] + 0.5f * d3);
+        *(float4 *)(st + 8) = make_float4(0.5f * S1[0] + third * d0, 0.5f * S1[1] + third * d1,
+                                          0.5f * S1[2] + third * d2, 0.5f * S1[3] + third * d3);
+    } else {
+        *(float4 *)(st + 0) = make_float4(S1[0], d0, q * p0, tag);
+        *(float4 *)(st + 4) = make_float4(S1[1], d1, q * p1, tag);
+        *(float4 *)(st + 8) = make_float4(S1[2], d2, q * p2, tag);
+        *(float4 *)(st + 12) = make_float4(S1[3], d3, q * p3, tag);
+    }
+}
+
+// same classification as k_classify_key (particles.cu), on a copy of the position
+__device__ __forceinline__ uint32_t sort_key(const DevGeom &G, float x, float y, float z)
+{
+    int dx = 0, dy = 0, dz = 0;
+    if (x < G.minx) dx = -1; else if (x > G.maxx) dx = 1;
+    if (y < G.miny) dy = -1; else if (y > G.maxy) dy = 1;
+    if (z < G.minz) dz = -1; else if (z > G.maxz) dz = 1;
+    bool in = true;
+    if (!G.perx) in = (x + G.mxcum > G.x1in) && (x + G.mxcum < G.x2in);
+    if (!G.pery && in) in = (y + G.mycum > G.y1in) && (y + G.mycum < G.y2in);
+    if (!G.perz && in) in = (z + G.mzcum > G.z1in) && (z + G.mzcum < G.z2in);
+    if (!in) return (uint32_t)G.lot + 9u;
+    if (dx < 0) x = x + G.shiftx_lo; else if (dx > 0) x = x - G.shiftx_hi;
+    if (dy < 0) y = y + G.shifty_lo; else if (dy > 0) y = y - G.shifty_hi;
+    if (dz < 0) z = z + G.shiftz_lo; else if (dz > 0) z = z - G.shiftz_hi;
+    const int da = G.sendy ? dy : 0, db = G.sendz ? dz : 0;
+    const int code = (da + 1) + 3 * (db + 1);
+    if (code != 4) return (uint32_t)G.lot + (uint32_t)code;
+    int i = min(max((int)x, 1), G.mx), j = min(max((int)y, 1), G.my), k = min(max((int)z, 1), G.mz);
+    return (uint32_t)((i - 1) + G.mx * ((j - 1) + G.my * (k - 1)));
 }
 
 template <int ORDER, bool FUSED>
@@ -57,55 +128,48 @@ __global__ void __launch_bounds__(CR_WARPS * 32, 2) k_cellrun(CRArgs A)
     const int j = lane & 3, k = (lane >> 2) & 3;
     const int loff = (j - 1) + my * (k - 1);
 
-    int wi = 0, wrow = -0x40000000;                          // window cell (1-based i, row id); none yet
+    int wi = 0, wrow = 0;                                    // window cell (1-based i, row id)
     bool have = false;
     float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f}, az[4] = {0.f, 0.f, 0.f, 0.f};
 
     for (int it = 0; it < CR_CHUNK / 16; ++it) {
         const long long t = base + it * 16 + hl;
         float *st = &stage[warp][lane][0];
+        int ci = -1, crow = -1;                              // deposit base cell of this lane's particle
         // ------------------------------------------------------------------ phase 1: lane = particle
         if (t < A.n) {
             float x = A.s.x[t], y = A.s.y[t], z = A.s.z[t], u = A.s.u[t], v = A.s.v[t], w = A.s.w[t];
-            const float ch = A.s.ch[t];
+            const float q = A.s.ch[t] * A.qs;
+            float S1[4], S2[4];
             if (FUSED) {
-                constexpr int NW = ORDER == 2 ? 3 : 2;
                 const float half_ = 0.5f;
-                int ip = (int)x, jp = (int)y, kp = (int)z;
-                float dxp = x - ip, dyp = y - jp, dzp = z - kp;
+                const int ip = (int)x, jp = (int)y, kp = (int)z;
+                const float dxp = x - ip, dyp = y - jp, dzp = z - kp;
                 float Wx[4], Wy[4], Wz[4];
                 shape_window<ORDER>(dxp, 0, Wx); shape_window<ORDER>(dyp, 0, Wy); shape_window<ORDER>(dzp, 0, Wz);
-                int lox, loy, loz;
-                if (ORDER == 2) {
-                    if (G.quirks & TGPU_Q1_MOVER2_RANGE) {
-                        // Q1: the loop bounds come from the dual (x - 1/2) branch, particles_movedeposit.F90:752-790
-                        float dxd = x - half_ - (int)(x - half_), dyd = y - half_ - (int)(y - half_), dzd = (z - half_) - (int)(z - half_);
+                float e0 = 0, e1 = 0, e2 = 0, b0 = 0, b1 = 0, b2 = 0;
+                // Order 1, and order 2 under quirk Q1 (loop bounds taken from the dual branch,
+                // particles_movedeposit.F90:752-790): only slots 3,4 carry weight inside the loop range unless the
+                // particle sits exactly on a node, so the sum runs over 2x2x2 nodes (the dropped terms are exact zeros).
+                const bool q1 = ORDER == 2 && (G.quirks & TGPU_Q1_MOVER2_RANGE);
+                const bool fast = ORDER == 1 || (q1 && dxp != 0.f && dyp != 0.f && dzp != 0.f);
+                if (fast) {
+                    const float wxs[2] = {Wx[1], Wx[2]}, wys[2] = {Wy[1], Wy[2]}, wzs[2] = {Wz[1], Wz[2]};
+                    const long long nbase = (ip - 1) + (long long)mx * ((jp - 1) + (long long)my * (kp - 1));
+                    gather_nodes<2>(A.prim8, nbase, mx, my, wxs, wys, wzs, e0, e1, e2, b0, b1, b2);
+                } else if (ORDER == 2) {
+                    int lox, loy, loz;
+                    if (q1) {
+                        const float dxd = x - half_ - (int)(x - half_), dyd = y - half_ - (int)(y - half_), dzd = (z - half_) - (int)(z - half_);
                         lox = dxd <= half_ ? 0 : 1; loy = dyd <= half_ ? 0 : 1; loz = dzd <= half_ ? 0 : 1;
                     } else { lox = dxp <= half_ ? 0 : 1; loy = dyp <= half_ ? 0 : 1; loz = dzp <= half_ ? 0 : 1; }
-                } else { lox = loy = loz = 1; }
-                float wxs[NW], wys[NW], wzs[NW];
+                    float wxs[3], wys[3], wzs[3];
 #pragma unroll
-                for (int a = 0; a < NW; a++) {
-                    wxs[a] = lox ? Wx[a + 1] : Wx[a]; wys[a] = loy ? Wy[a + 1] : Wy[a]; wzs[a] = loz ? Wz[a + 1] : Wz[a];
-                }
-                float e0 = 0, e1 = 0, e2 = 0, b0 = 0, b1 = 0, b2 = 0;
-                const long long nbase = (ip - 2 + lox) + (long long)mx * ((jp - 2 + loy) + (long long)my * (kp - 2 + loz));
-#pragma unroll
-                for (int c3 = 0; c3 < NW; c3++) {
-#pragma unroll
-                    for (int c2 = 0; c2 < NW; c2++) {
-                        float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
-                        const float4 *row = A.prim8 + 2 * (nbase + (long long)mx * (c2 + (long long)my * c3));
-#pragma unroll
-                        for (int c1 = 0; c1 < NW; c1++) {
-                            float4 lo = __ldg(row + 2 * c1), hi = __ldg(row + 2 * c1 + 1);
-                            s0 = s0 + lo.x * wxs[c1]; s1 = s1 + lo.y * wxs[c1]; s2 = s2 + lo.z * wxs[c1];
-                            s3 = s3 + lo.w * wxs[c1]; s4 = s4 + hi.x * wxs[c1]; s5 = s5 + hi.y * wxs[c1];
-                        }
-                        const float wy_ = wys[c2], wz_ = wzs[c3];
-                        e0 = e0 + s0 * wy_ * wz_; e1 = e1 + s1 * wy_ * wz_; e2 = e2 + s2 * wy_ * wz_;
-                        b0 = b0 + s3 * wy_ * wz_; b1 = b1 + s4 * wy_ * wz_; b2 = b2 + s5 * wy_ * wz_;
+                    for (int a = 0; a < 3; a++) {
+                        wxs[a] = lox ? Wx[a + 1] : Wx[a]; wys[a] = loy ? Wy[a + 1] : Wy[a]; wzs[a] = loz ? Wz[a + 1] : Wz[a];
                     }
+                    const long long nbase = (ip - 2 + lox) + (long long)mx * ((jp - 2 + loy) + (long long)my * (kp - 2 + loz));
+                    gather_nodes<3>(A.prim8, nbase, mx, my, wxs, wys, wzs, e0, e1, e2, b0, b1, b2);
                 }
                 const float cinv = 1.f / G.c, qm = A.qm;
                 e0 = 0.5f * e0 * qm; e1 = 0.5f * e1 * qm; e2 = 0.5f * e2 * qm;
@@ -116,94 +180,92 @@ __global__ void __launch_bounds__(CR_WARPS * 32, 2) k_cellrun(CRArgs A)
                 }
                 push_particle(G.c, G.pusher, e0, e1, e2, b0, b1, b2, x, y, z, u, v, w);
                 A.s.x[t] = x; A.s.y[t] = y; A.s.z[t] = z; A.s.u[t] = u; A.s.v[t] = v; A.s.w[t] = w;
-            }
-            // deposit_particles loop A: old position recomputed from the new one (particles_movedeposit.F90:1384-1390)
-            const float invgam = 1.f / sqrtf(1 + u * u + v * v + w * w);
-            const float x1 = x - u * invgam * G.c, y1 = y - v * invgam * G.c, z1 = z - w * invgam * G.c;
-            const float q = ch * A.qs;
-            const int i1 = (int)x1, j1 = (int)y1, k1 = (int)z1;
-            const float third = 1.f / 3.f;
-            float S1[4], S2[4];
-            // x: q*prefix(dS), XA = S1 + dS/2, XB = S1/2 + dS/3
-            shape_window<ORDER>(x1 - i1, 0, S1); shape_window<ORDER>(x - (int)x, (int)x - i1, S2);
-            {
-                float d0 = S2[0] - S1[0], d1 = S2[1] - S1[1], d2 = S2[2] - S1[2], d3 = S2[3] - S1[3];
-                float p0 = d0, p1 = p0 + d1, p2 = p1 + d2, p3 = p2 + d3;
-                *(float4 *)(st + 0) = make_float4(q * p0, q * p1, q * p2, q * p3);
-                *(float4 *)(st + 4) = make_float4(S1[0] + 0.5f * d0, S1[1] + 0.5f * d1, S1[2] + 0.5f * d2, S1[3] + 0.5f * d3);
-                *(float4 *)(st + 8) = make_float4(0.5f * S1[0] + third * d0, 0.5f * S1[1] + third * d1,
-                                                  0.5f * S1[2] + third * d2, 0.5f * S1[3] + third * d3);
-            }
-            // y: per j (Sy1, dSy, q*prefix_j(dSy), i1)
-            shape_window<ORDER>(y1 - j1, 0, S1); shape_window<ORDER>(y - (int)y, (int)y - j1, S2);
-            {
-                float d0 = S2[0] - S1[0], d1 = S2[1] - S1[1], d2 = S2[2] - S1[2], d3 = S2[3] - S1[3];
-                float p0 = d0, p1 = p0 + d1, p2 = p1 + d2, p3 = p2 + d3;
-                const float fi = __int_as_float(i1);
-                *(float4 *)(st + 12) = make_float4(S1[0], d0, q * p0, fi);
-                *(float4 *)(st + 16) = make_float4(S1[1], d1, q * p1, fi);
-                *(float4 *)(st + 20) = make_float4(S1[2], d2, q * p2, fi);
-                *(float4 *)(st + 24) = make_float4(S1[3], d3, q * p3, fi);
-            }
-            // z: per k (Sz1, dSz, q*prefix_k(dSz), row id)
-            shape_window<ORDER>(z1 - k1, 0, S1); shape_window<ORDER>(z - (int)z, (int)z - k1, S2);
-            {
-                float d0 = S2[0] - S1[0], d1 = S2[1] - S1[1], d2 = S2[2] - S1[2], d3 = S2[3] - S1[3];
-                float p0 = d0, p1 = p0 + d1, p2 = p1 + d2, p3 = p2 + d3;
-                const float fr = __int_as_float((j1 - 1) + my * (k1 - 1));
-                *(float4 *)(st + 28) = make_float4(S1[0], d0, q * p0, fr);
-                *(float4 *)(st + 32) = make_float4(S1[1], d1, q * p1, fr);
-                *(float4 *)(st + 36) = make_float4(S1[2], d2, q * p2, fr);
-                *(float4 *)(st + 40) = make_float4(S1[3], d3, q * p3, fr);
+                // The deposit's "old" shape is the gather's shape at the true pre-push position (the reference
+                // recomputes it as x - u/gamma*c, particles_movedeposit.F90:1384-1388, equal to round-off).
+                crow = (jp - 1) + my * (kp - 1); ci = ip;
+                shape_window<ORDER>(x - (int)x, (int)x - ip, S2);
+                stage_axis<0>(st, Wx, S2, q, 0.f);
+                shape_window<ORDER>(y - (int)y, (int)y - jp, S2);
+                stage_axis<1>(st + 12, Wy, S2, q, __int_as_float(ci));
+                shape_window<ORDER>(z - (int)z, (int)z - kp, S2);
+                stage_axis<1>(st + 28, Wz, S2, q, __int_as_float(crow));
+                // sort key of the pushed particle + its rank inside the destination bin
+                const uint32_t ky = sort_key(G, x, y, z);
+                A.key[t] = ky;
+                A.slot[t] = atomicAdd(&A.bincount[ky], 1);
+            } else {
+                // deposit_particles loop A: old position recomputed from the new one (particles_movedeposit.F90:1384-1390)
+                const float invgam = 1.f / sqrtf(1 + u * u + v * v + w * w);
+                const float x1 = x - u * invgam * G.c, y1 = y - v * invgam * G.c, z1 = z - w * invgam * G.c;
+                const int i1 = (int)x1, j1 = (int)y1, k1 = (int)z1;
+                crow = (j1 - 1) + my * (k1 - 1); ci = i1;
+                shape_window<ORDER>(x1 - i1, 0, S1); shape_window<ORDER>(x - (int)x, (int)x - i1, S2);
+                stage_axis<0>(st, S1, S2, q, 0.f);
+                shape_window<ORDER>(y1 - j1, 0, S1); shape_window<ORDER>(y - (int)y, (int)y - j1, S2);
+                stage_axis<1>(st + 12, S1, S2, q, __int_as_float(ci));
+                shape_window<ORDER>(z1 - k1, 0, S1); shape_window<ORDER>(z - (int)z, (int)z - k1, S2);
+                stage_axis<1>(st + 28, S1, S2, q, __int_as_float(crow));
             }
         }
-        __syncwarp();
+        // run starts inside each half: a particle whose cell differs from its predecessor's
+        const int pci = __shfl_up_sync(0xffffffffu, ci, 1), pcrow = __shfl_up_sync(0xffffffffu, crow, 1);
+        const bool start = hl == 0 || ci != pci || crow != pcrow;
+        unsigned starts = (__ballot_sync(0xffffffffu, start) >> (half << 4)) & 0xFFFFu;
+        __syncwarp();                                        // staging written by all lanes is visible to the warp
         // ------------------------------------------------------------------ phase 2: half-warp = footprint
-        long long rem = A.n - (base + it * 16);
+        const long long rem = A.n - (base + it * 16);
         const int cnt = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
-        for (int tt = 0; tt < cnt; ++tt) {
-            const float4 *sp = (const float4 *)&stage[warp][(half << 4) + tt][0];
-            const float4 yv = sp[3 + j], zv = sp[7 + k];
-            const int ni = __float_as_int(yv.w), nrow = __float_as_int(zv.w);
-            if (!have || ni != wi || nrow != wrow) {
-                if (have) {
-                    const size_t idx0 = (size_t)((long long)mx * (wrow + loff) + (wi - 2));
-                    const int di = ni - wi;
-                    if (nrow == wrow && di > 0 && di < 4) {
-                        // slide along x: planes 0..di-1 are complete
-                        red3(A.cx, A.cy, A.cz, idx0, ax[0], ay[0], az[0]);
-                        if (di > 1) red3(A.cx, A.cy, A.cz, idx0 + 1, ax[1], ay[1], az[1]);
-                        if (di > 2) red3(A.cx, A.cy, A.cz, idx0 + 2, ax[2], ay[2], az[2]);
-                        if (di == 1) {
+        int tt = 0;
+        while (tt < cnt) {
+            // particle tt opens a run of particles that share one footprint
+            const unsigned later = starts >> (tt + 1);
+            int next = later ? tt + __ffs(later) : 16;
+            if (next > cnt) next = cnt;
+            {
+                const float4 *sp = (const float4 *)&stage[warp][(half << 4) + tt][0];
+                const int ni = __float_as_int(sp[3].w), nrow = __float_as_int(sp[7].w);
+                if (!have || ni != wi || nrow != wrow) {
+                    if (have) {
+                        const size_t idx0 = (size_t)((long long)mx * (wrow + loff) + (wi - 2));
+                        const int di = ni - wi;
+                        if (nrow == wrow && di == 1) {
+                            // the common case in sorted order: slide one cell along x, plane 0 is complete
+                            red3(A.cx, A.cy, A.cz, idx0, ax[0], ay[0], az[0]);
                             ax[0] = ax[1]; ax[1] = ax[2]; ax[2] = ax[3]; ax[3] = 0.f;
                             ay[0] = ay[1]; ay[1] = ay[2]; ay[2] = ay[3]; ay[3] = 0.f;
                             az[0] = az[1]; az[1] = az[2]; az[2] = az[3]; az[3] = 0.f;
-                        } else if (di == 2) {
-                            ax[0] = ax[2]; ax[1] = ax[3]; ax[2] = 0.f; ax[3] = 0.f;
-                            ay[0] = ay[2]; ay[1] = ay[3]; ay[2] = 0.f; ay[3] = 0.f;
-                            az[0] = az[2]; az[1] = az[3]; az[2] = 0.f; az[3] = 0.f;
+                        } else if (nrow == wrow && (di == 2 || di == 3)) {
+                            red3(A.cx, A.cy, A.cz, idx0, ax[0], ay[0], az[0]);
+                            red3(A.cx, A.cy, A.cz, idx0 + 1, ax[1], ay[1], az[1]);
+                            if (di == 2) {
+                                ax[0] = ax[2]; ax[1] = ax[3]; ay[0] = ay[2]; ay[1] = ay[3]; az[0] = az[2]; az[1] = az[3];
+                            } else {
+                                red3(A.cx, A.cy, A.cz, idx0 + 2, ax[2], ay[2], az[2]);
+                                ax[0] = ax[3]; ax[1] = 0.f; ay[0] = ay[3]; ay[1] = 0.f; az[0] = az[3]; az[1] = 0.f;
+                            }
+                            ax[2] = 0.f; ax[3] = 0.f; ay[2] = 0.f; ay[3] = 0.f; az[2] = 0.f; az[3] = 0.f;
                         } else {
-                            ax[0] = ax[3]; ax[1] = 0.f; ax[2] = 0.f; ax[3] = 0.f;
-                            ay[0] = ay[3]; ay[1] = 0.f; ay[2] = 0.f; ay[3] = 0.f;
-                            az[0] = az[3]; az[1] = 0.f; az[2] = 0.f; az[3] = 0.f;
-                        }
-                    } else {
 #pragma unroll
-                        for (int s = 0; s < 4; s++) { red3(A.cx, A.cy, A.cz, idx0 + s, ax[s], ay[s], az[s]); ax[s] = 0.f; ay[s] = 0.f; az[s] = 0.f; }
+                            for (int s = 0; s < 4; s++) { red3(A.cx, A.cy, A.cz, idx0 + s, ax[s], ay[s], az[s]); ax[s] = 0.f; ay[s] = 0.f; az[s] = 0.f; }
+                        }
                     }
+                    wi = ni; wrow = nrow; have = true;
                 }
-                wi = ni; wrow = nrow; have = true;
             }
-            const float4 qpsx = sp[0], xa = sp[1], xb = sp[2];
-            const float sy1 = yv.x, dsy = yv.y, qpsy = yv.z;
-            const float sz1 = zv.x, dsz = zv.y, qpsz = zv.z;
-            const float ya = sy1 + 0.5f * dsy, yb = 0.5f * sy1 + (1.f / 3.f) * dsy;
-            const float wx = ya * sz1 + yb * dsz;          // Wx(j,k)
-            const float a = qpsy * sz1, b = qpsy * dsz;    // Jy = XA*a + XB*b
-            const float c = qpsz * sy1, d = qpsz * dsy;    // Jz = XA*c + XB*d
-            ax[0] += qpsx.x * wx; ax[1] += qpsx.y * wx; ax[2] += qpsx.z * wx; ax[3] += qpsx.w * wx;
-            ay[0] += xa.x * a + xb.x * b; ay[1] += xa.y * a + xb.y * b; ay[2] += xa.z * a + xb.z * b; ay[3] += xa.w * a + xb.w * b;
-            az[0] += xa.x * c + xb.x * d; az[1] += xa.y * c + xb.y * d; az[2] += xa.z * c + xb.z * d; az[3] += xa.w * c + xb.w * d;
+            for (; tt < next; ++tt) {
+                const float4 *sp = (const float4 *)&stage[warp][(half << 4) + tt][0];
+                const float4 yv = sp[3 + j], zv = sp[7 + k];
+                const float4 qpsx = sp[0], xa = sp[1], xb = sp[2];
+                const float sy1 = yv.x, dsy = yv.y, qpsy = yv.z;
+                const float sz1 = zv.x, dsz = zv.y, qpsz = zv.z;
+                const float ya = sy1 + 0.5f * dsy, yb = 0.5f * sy1 + (1.f / 3.f) * dsy;
+                const float wx = ya * sz1 + yb * dsz;          // Wx(j,k)
+                const float a = qpsy * sz1, b = qpsy * dsz;    // Jy = XA*a + XB*b
+                const float c = qpsz * sy1, d = qpsz * dsy;    // Jz = XA*c + XB*d
+                ax[0] += qpsx.x * wx; ax[1] += qpsx.y * wx; ax[2] += qpsx.z * wx; ax[3] += qpsx.w * wx;
+                ay[0] += xa.x * a + xb.x * b; ay[1] += xa.y * a + xb.y * b; ay[2] += xa.z * a + xb.z * b; ay[3] += xa.w * a + xb.w * b;
+                az[0] += xa.x * c + xb.x * d; az[1] += xa.y * c + xb.y * d; az[2] += xa.z * c + xb.z * d; az[3] += xa.w * c + xb.w * d;
+            }
         }
         __syncwarp();
     }
@@ -228,6 +290,9 @@ static int launch(tgpu_ctx *h, float *cx, float *cy, float *cz)
         CRArgs A;
         A.s = S; A.n = S.n; A.prim8 = h->prim8; A.cx = cx; A.cy = cy; A.cz = cz; A.G = h->G;
         A.qm = s ? h->P.qme : h->P.qmi; A.qs = s ? h->P.qe : h->P.qi;
+        const size_t nb = (size_t)h->G.lot + TGPU_NBIN_EXTRA;
+        A.key = h->key[s]; A.slot = h->slot + (size_t)s * h->maxhlf; A.bincount = h->bincount + (size_t)s * nb;
+        if (FUSED) CK(cudaMemsetAsync(A.bincount, 0, nb * sizeof(int32_t), h->stream));
         long long warps = (S.n + 2 * CR_CHUNK - 1) / (2 * CR_CHUNK);
         int blocks = (int)((warps + CR_WARPS - 1) / CR_WARPS);
         if (h->P.order == 2) k_cellrun<2, FUSED><<<blocks, CR_WARPS * 32, 0, h->stream>>>(A);
@@ -242,7 +307,9 @@ static int launch(tgpu_ctx *h, float *cx, float *cy, float *cz)
 int cellrun_move_deposit(tgpu_ctx *h)
 {
     int rc = fld_primal(h); if (rc) return rc;
-    return launch<true>(h, h->shadow[0], h->shadow[1], h->shadow[2]);
+    rc = launch<true>(h, h->shadow[0], h->shadow[1], h->shadow[2]); if (rc) return rc;
+    h->keys_valid = 1;                       // prt_sort may skip its classify pass
+    return 0;
 }
 
 // tgpu_deposit_particles fast path when the particles were moved elsewhere (mirror mode, tests)

@@ -423,19 +423,24 @@ __device__ __forceinline__ size_t f2_addr(const F2 &f, int p_cell, int q1, int q
     return (size_t)(ijk[0] - 1) + (size_t)f.mx * ((size_t)(ijk[1] - 1) + (size_t)f.my * (size_t)(ijk[2] - 1));
 }
 
-// smem layout: axis 0 -> [line][p] (p fastest, matches the contiguous global walk); other axes -> [p][line]
-// (line = x index fastest).  Either way consecutive threads touch consecutive shared-memory words.
-template <int NL>
-__global__ void __launch_bounds__(256) k_filter2(float *__restrict__ cur, const float *__restrict__ halo_lo,
-                                                 const float *__restrict__ halo_hi, F2 f)
+// Shared memory holds the tile only for the coalesced load/store; the passes themselves run in registers: thread
+// (line, strip) keeps R consecutive line elements and exchanges one edge value per side per pass with its strip
+// neighbours through a double-buffered shared array (one __syncthreads per pass).
+// tile layout: axis 0 -> [line][p] with an odd pitch (p contiguous in memory); other axes -> [p][line] (line = x index).
+template <int R>
+__global__ void __launch_bounds__(1024) k_filter2(float *__restrict__ cur, const float *__restrict__ halo_lo,
+                                                  const float *__restrict__ halo_hi, F2 f, int NL, int NS)
 {
     extern __shared__ float sm[];
     const int L = f.ncell + 2 * f.nt;
+    const int Lp = L | 1;
     const int nlines = f.q_n[0] * f.q_n[1];
     const int line0 = blockIdx.x * NL;
-    const int sp = f.axis == 0 ? 1 : NL, sl = f.axis == 0 ? L : 1;
-    float *A = sm, *B = sm + (size_t)L * NL;
-    for (int t = threadIdx.x; t < L * NL; t += blockDim.x) {
+    const int sp = f.axis == 0 ? 1 : NL, sl = f.axis == 0 ? Lp : 1;
+    float *tile = sm;
+    float *edge = sm + (size_t)Lp * NL;                 // [2 parity][2 side][NS][NL]
+    const int nthr = blockDim.x;
+    for (int t = threadIdx.x; t < L * NL; t += nthr) {
         int p, ln;
         if (f.axis == 0) { p = t % L; ln = t / L; } else { ln = t % NL; p = t / NL; }
         int line = line0 + ln;
@@ -453,29 +458,44 @@ __global__ void __launch_bounds__(256) k_filter2(float *__restrict__ cur, const 
                 else v = cur[f2_addr(f, f.str + f.ncell - 1, q1, q2)];
             } else v = cur[f2_addr(f, f.str + pc, q1, q2)];
         }
-        A[p * sp + ln * sl] = v;
+        tile[p * sp + ln * sl] = v;
     }
     __syncthreads();
+    const int ln = threadIdx.x % NL, strip = threadIdx.x / NL;
+    const int p0 = strip * R;
+    float v[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) v[r] = (p0 + r < L) ? tile[(p0 + r) * sp + ln * sl] : 0.f;
+    const int es = NS * NL;                              // one side of one parity
     for (int n = 0; n < f.nt; n++) {
-        for (int t = threadIdx.x; t < L * NL; t += blockDim.x) {
-            int p, ln;
-            if (f.axis == 0) { p = t % L; ln = t / L; } else { ln = t % NL; p = t / NL; }
-            const int o = p * sp + ln * sl;
-            float v;
-            if (p == 0 || p == L - 1) v = A[o];
-            else v = .25f * A[o - sp] + .5f * A[o] + .25f * A[o + sp];
-            B[o] = v;
-        }
+        float *e = edge + (size_t)(n & 1) * 2 * es;
+        e[strip * NL + ln] = v[0];
+        e[es + strip * NL + ln] = v[R - 1];
         __syncthreads();
-        float *t2 = A; A = B; B = t2;
+        const float left = strip > 0 ? e[es + (strip - 1) * NL + ln] : 0.f;
+        const float right = strip < NS - 1 ? e[(strip + 1) * NL + ln] : 0.f;
+        float prev = left;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int p = p0 + r;
+            const float c = v[r];
+            const float nx = r < R - 1 ? v[r + 1] : right;
+            const float nv = .25f * prev + .5f * c + .25f * nx;
+            v[r] = (p == 0 || p >= L - 1) ? c : nv;
+            prev = c;
+        }
     }
-    for (int t = threadIdx.x; t < f.ncell * NL; t += blockDim.x) {
-        int p, ln;
-        if (f.axis == 0) { p = t % f.ncell; ln = t / f.ncell; } else { ln = t % NL; p = t / NL; }
-        int line = line0 + ln;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; r++) if (p0 + r < L) tile[(p0 + r) * sp + ln * sl] = v[r];
+    __syncthreads();
+    for (int t = threadIdx.x; t < f.ncell * NL; t += nthr) {
+        int p, l2;
+        if (f.axis == 0) { p = t % f.ncell; l2 = t / f.ncell; } else { l2 = t % NL; p = t / NL; }
+        int line = line0 + l2;
         if (line < nlines) {
             int q1 = line % f.q_n[0], q2 = line / f.q_n[0];
-            cur[f2_addr(f, f.str + p, q1, q2)] = A[(p + f.nt) * sp + ln * sl];
+            cur[f2_addr(f, f.str + p, q1, q2)] = tile[(p + f.nt) * sp + l2 * sl];
         }
     }
 }
@@ -528,25 +548,26 @@ int fld_filter2(tgpu_ctx *h)
                 f.lowmode = (per || pos != 0) ? 1 : 2;
                 f.highmode = (per || pos != sz - 1) ? 1 : 2;
             }
-            const int L = f.ncell + 2 * f.nt;
+            const int L = f.ncell + 2 * f.nt, Lp = L | 1;
             int nlines = f.q_n[0] * f.q_n[1];
-            // lines per CTA: as many as fit in ~96 KB of ping-pong shared memory, capped at 32
+            // strip length R: smallest of 8/16/32/64 that keeps NS = ceil(L/R) <= 32 strips (<= 1024 threads at NL = 32)
+            int R = 8; while (R < 64 && (L + R - 1) / R > 32) R <<= 1;
+            int NS = (L + R - 1) / R;
             int NL = 32;
-            while (NL > 1 && (size_t)2 * L * NL * 4 > 96 * 1024) NL >>= 1;
-            size_t smem = (size_t)2 * L * NL * 4;
-            if (smem > 200 * 1024) { tgpu_set_error("filter2: line too long for shared memory"); return TGPU_EINVAL; }
-#define LAUNCH_F2(NLV)                                                                                              \
+            while (NL > 1 && ((size_t)Lp * NL + 4 * (size_t)NS * NL) * 4 > 200 * 1024) NL >>= 1;
+            while (NL * NS > 1024) NL >>= 1;
+            size_t smem = ((size_t)Lp * NL + 4 * (size_t)NS * NL) * 4;
+            if (NL < 1 || smem > 220 * 1024) { tgpu_set_error("filter2: line too long for shared memory"); return TGPU_EINVAL; }
+#define LAUNCH_F2(RV)                                                                                              \
     {                                                                                                              \
-        CK(cudaFuncSetAttribute(k_filter2<NLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-        k_filter2<NLV><<<cdiv(nlines, NLV), 256, smem, h->stream>>>(h->f[6 + c], hlo, hhi, f);                     \
+        CK(cudaFuncSetAttribute(k_filter2<RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        k_filter2<RV><<<cdiv(nlines, NL), NL * NS, smem, h->stream>>>(h->f[6 + c], hlo, hhi, f, NL, NS);           \
     }
-            switch (NL) {
-            case 32: LAUNCH_F2(32) break;
-            case 16: LAUNCH_F2(16) break;
+            switch (R) {
             case 8: LAUNCH_F2(8) break;
-            case 4: LAUNCH_F2(4) break;
-            case 2: LAUNCH_F2(2) break;
-            default: LAUNCH_F2(1) break;
+            case 16: LAUNCH_F2(16) break;
+            case 32: LAUNCH_F2(32) break;
+            default: LAUNCH_F2(64) break;
             }
 #undef LAUNCH_F2
             CKK(h);

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) k_soa2aos(tgpu_particle *__restrict__ a, 
 int prt_append(tgpu_ctx *h, int s, const tgpu_particle *p, int n, bool host)
 {
     if (n <= 0) return 0;
+    h->keys_valid = 0;
     Species &S = h->sp[s];
     if (S.n + n > h->maxhlf) { tgpu_set_error("particle capacity (maxhlf) exceeded"); return TGPU_EOVERFLOW; }
     int done = 0;
@@ -50,7 +51,7 @@ int prt_append(tgpu_ctx *h, int s, const tgpu_particle *p, int n, bool host)
 int prt_h2d(tgpu_ctx *h, const tgpu_particle *p, int ions, int lecs)
 {
     if (ions < 0 || lecs < 0 || ions > h->maxhlf || lecs > h->maxhlf) { tgpu_set_error("bad particle counts"); return TGPU_EINVAL; }
-    h->sp[0].n = 0; h->sp[1].n = 0;
+    h->sp[0].n = 0; h->sp[1].n = 0; h->keys_valid = 0;
     int rc = prt_append(h, 0, p, ions, true); if (rc) return rc;
     rc = prt_append(h, 1, p + h->maxhlf, lecs, true); if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
@@ -437,13 +438,17 @@ __global__ void __launch_bounds__(256) k_classify_key(Species s, int n, DevGeom 
     slot[t] = atomicAdd(&bincount[k], 1);
 }
 
+// WRAP: the keys were computed by the fused mover on a copy of the position; apply the periodic wrap / frame shift here
+template <bool WRAP>
 __global__ void __launch_bounds__(256) k_scatter(Species a, Species b, int n, const uint32_t *__restrict__ key,
-                                                 const int32_t *__restrict__ slot, const int32_t *__restrict__ binoff)
+                                                 const int32_t *__restrict__ slot, const int32_t *__restrict__ binoff, DevGeom G)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     int d = binoff[key[t]] + slot[t];
-    b.x[d] = a.x[t]; b.y[d] = a.y[t]; b.z[d] = a.z[t]; b.u[d] = a.u[t]; b.v[d] = a.v[t]; b.w[d] = a.w[t];
+    float x = a.x[t], y = a.y[t], z = a.z[t];
+    if (WRAP) { int code; bool discard; classify(G, x, y, z, code, discard); }
+    b.x[d] = x; b.y[d] = y; b.z[d] = z; b.u[d] = a.u[t]; b.v[d] = a.v[t]; b.w[d] = a.w[t];
     b.ch[d] = a.ch[t]; b.ind[d] = a.ind[t]; b.tag[d] = a.tag[t];
 }
 
@@ -451,7 +456,9 @@ __global__ void __launch_bounds__(256) k_scatter(Species a, Species b, int n, co
 int prt_sort(tgpu_ctx *h, bool)
 {
     const int nb = (int)h->G.lot + TGPU_NBIN_EXTRA;
-    for (int s = 0; s < 2; s++) {
+    const bool wrap_in_scatter = h->keys_valid != 0;
+    h->keys_valid = 0;
+    for (int s = 0; s < 2 && !wrap_in_scatter; s++) {
         Species &S = h->sp[s];
         int32_t *cnt = h->bincount + (size_t)s * nb;
         CK(cudaMemsetAsync(cnt, 0, (size_t)nb * sizeof(int32_t), h->stream));
@@ -467,8 +474,12 @@ int prt_sort(tgpu_ctx *h, bool)
     for (int s = 0; s < 2; s++) {
         Species &S = h->sp[s];
         if (S.n) {
-            k_scatter<<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->key[s], h->slot + (size_t)s * h->maxhlf,
-                                                            h->binoff + (size_t)s * (nb + 1));
+            if (wrap_in_scatter)
+                k_scatter<true><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->key[s], h->slot + (size_t)s * h->maxhlf,
+                                                                      h->binoff + (size_t)s * (nb + 1), h->G);
+            else
+                k_scatter<false><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->key[s], h->slot + (size_t)s * h->maxhlf,
+                                                                       h->binoff + (size_t)s * (nb + 1), h->G);
             CKK(h);
         }
         CK(cudaMemcpyAsync(h->h_small + s * 16, h->binoff + (size_t)s * (nb + 1) + (size_t)h->G.lot, 11 * sizeof(int32_t),

@@ -56,6 +56,7 @@ struct tgpu_ctx {
     int fused_pending;       // currents of the last move already deposited into shadow
     float *shadow[3];
     int opt_fused;
+    int keys_valid;          // key[]/slot[]/bincount[] already hold this lap's sort keys (written by the fused mover)
     cudaStream_t stream;
     cudaEvent_t ev0, ev1;
     void *nccl_comm;         // ncclComm_t
