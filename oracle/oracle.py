@@ -78,6 +78,11 @@ def lib():
         L.orc_step_phase.argtypes = [vp, ci]
         L.orc_shape.argtypes = [ci, cf, ci, C.POINTER(cf), C.POINTER(ci), C.POINTER(ci)]
         L.orc_filter2_line.argtypes = [C.POINTER(cf), ci, ci]
+        L.orc_filter2_rank.argtypes = [vp, ci, ci, C.POINTER(cf), C.POINTER(cf)]
+        L.orc_filter2_send_box.argtypes = [vp, ci, ci, C.POINTER(ci), C.POINTER(ci)]
+        L.orc_rank_box.restype = vp
+        L.orc_rank_box.argtypes = [vp, ci, ci, C.POINTER(ci), C.POINTER(ci)]
+        L.orc_rank_box_set_counts.argtypes = [vp, ci, ci, ci, ci]
         L.orc_neighbour.restype = ci
         L.orc_neighbour.argtypes = [vp, ci]
         i3 = C.POINTER(ci)

@@ -123,6 +123,17 @@ void orc_rank_dims(const orc_rank *r, int *o)
 }
 void orc_rank_counts(const orc_rank *r, int *ions, int *lecs) { *ions = r->ions; *lecs = r->lecs; }
 void orc_rank_set_counts(orc_rank *r, int ions, int lecs) { r->ions = ions; r->lecs = lecs; }
+orc_particle *orc_rank_box(orc_rank *r, int which, int dir, int *nion, int *nlec)
+{
+    orc_box *b = which ? &r->in[dir] : &r->out[dir];
+    if (nion) *nion = b->nion; if (nlec) *nlec = b->nlec;
+    return b->p;
+}
+void orc_rank_box_set_counts(orc_rank *r, int which, int dir, int nion, int nlec)
+{
+    orc_box *b = which ? &r->in[dir] : &r->out[dir];
+    b->nion = nion; b->nlec = nlec;
+}
 
 /* neighbour formulas: fieldboundaries.F90:1170-1171 (x), :1311-1314 (y); particles.F90:1892-1895 (z) */
 int orc_neighbour(const orc_rank *r, int dir)
@@ -518,80 +529,68 @@ void orc_filter2_line(float *line, int len, int ntimes)
 /* deep_copy_layr{x,y,z}{1,2}: optimized_filters.F90:1387-1963.
    ghost(1:n) <- (-neighbour) cur(fin-n+1:fin); ghost(n+1:2n) <- (+neighbour) cur(str:str+n-1),
    rows restricted to the interior of the other axes; open edge replicates the edge value. */
+/* per-rank part: filter every line of component c along `axis`, given the two nt-deep halo slabs in
+   orc_box_get order over the restricted box (x fastest).  Open edges replicate cur(str) / cur(fin). */
+void orc_filter2_rank(orc_rank *r, int c, int axis, const float *glo, const float *ghi)
+{
+    const int nt = r->P.ntimes;
+    int lo[3], hi[3];
+    for (int a = 0; a < 3; a++) { lo[a] = axis_g(r, a) + 1; hi[a] = axis_m(r, a) - (axis_g(r, a) + 1); }
+    if (r->P.dim == 2) { lo[2] = hi[2] = 1; }
+    int per = axis_per(r, axis), pos = axis_pos(r, axis), sz = axis_size(r, axis);
+    int str = lo[axis], fin = hi[axis], ncell = fin - str + 1, len = ncell + 2 * nt;
+    int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+    if (a1 > a2) { int t = a1; a1 = a2; a2 = t; }           /* a1 < a2: a1 is the faster of the two */
+    int n1 = hi[a1] - lo[a1] + 1, n2 = hi[a2] - lo[a2] + 1;
+    float *line = (float *)malloc((size_t)len * sizeof(float));
+    float *cu = r->f[ORC_CURX + c];
+    int lowrep = !(per || pos != 0), highrep = !(per || pos != sz - 1);
+    for (int q2 = 0; q2 < n2; q2++) for (int q1 = 0; q1 < n1; q1++) {
+        int ijk[3]; ijk[a1] = lo[a1] + q1; ijk[a2] = lo[a2] + q2;
+        for (int t = 0; t < nt; t++) {
+            size_t off;
+            if (axis == 0) off = (size_t)t + (size_t)nt * ((size_t)q1 + (size_t)n1 * q2);
+            else if (axis == 1) off = (size_t)q1 + (size_t)n1 * ((size_t)t + (size_t)nt * q2);
+            else off = (size_t)q1 + (size_t)n1 * ((size_t)q2 + (size_t)n2 * t);
+            ijk[axis] = str; float elo = cu[IDX(r, ijk[0], ijk[1], ijk[2])];
+            ijk[axis] = fin; float ehi = cu[IDX(r, ijk[0], ijk[1], ijk[2])];
+            line[t] = lowrep ? elo : glo[off];
+            line[nt + ncell + t] = highrep ? ehi : ghi[off];
+        }
+        for (int s = 0; s < ncell; s++) { ijk[axis] = str + s; line[nt + s] = cu[IDX(r, ijk[0], ijk[1], ijk[2])]; }
+        orc_filter2_line(line, len, nt);
+        for (int s = 0; s < ncell; s++) { ijk[axis] = str + s; cu[IDX(r, ijk[0], ijk[1], ijk[2])] = line[nt + s]; }
+    }
+    free(line);
+}
+
+/* boxes a rank contributes to / expects from its axis neighbours: what = 0 -> my last nt cells (sent up, becomes the
+   + neighbour's low halo), what = 1 -> my first nt cells (sent down) */
+void orc_filter2_send_box(const orc_rank *r, int axis, int what, int lo[3], int hi[3])
+{
+    for (int a = 0; a < 3; a++) { lo[a] = axis_g(r, a) + 1; hi[a] = axis_m(r, a) - (axis_g(r, a) + 1); }
+    if (r->P.dim == 2) { lo[2] = hi[2] = 1; }
+    int nt = r->P.ntimes, str = lo[axis], fin = hi[axis];
+    if (what == 0) { lo[axis] = fin - nt + 1; hi[axis] = fin; } else { lo[axis] = str; hi[axis] = str + nt - 1; }
+}
+
 static void filter2_axis(orc_world *w, int c, int axis)
 {
-    int nr = w->size0, nt = w->P.ntimes;
-    /* gather ghosts for every rank first (they are fetched before the in-place filter) */
+    int nr = w->size0;
     float **glo = (float **)calloc(nr, sizeof(float *)), **ghi = (float **)calloc(nr, sizeof(float *));
     for (int rk = 0; rk < nr; rk++) {
         orc_rank *r = w->r[rk];
-        int lo[3], hi[3];
-        for (int a = 0; a < 3; a++) { lo[a] = axis_g(r, a) + 1; hi[a] = axis_m(r, a) - (axis_g(r, a) + 1); }
-        if (w->P.dim == 2) { lo[2] = hi[2] = 1; }
-        int per = axis_per(r, axis), pos = axis_pos(r, axis), sz = axis_size(r, axis);
-        int str = lo[axis], fin = hi[axis];
-        size_t plane = box_count(lo, hi) / (size_t)(fin - str + 1);
-        glo[rk] = (float *)malloc(plane * nt * sizeof(float));
-        ghi[rk] = (float *)malloc(plane * nt * sizeof(float));
-        /* low ghosts from the - neighbour */
         orc_rank *rm = w->r[orc_neighbour(r, 2 * axis)], *rp = w->r[orc_neighbour(r, 2 * axis + 1)];
-        int l2[3], h2[3];
-        memcpy(l2, lo, sizeof l2); memcpy(h2, hi, sizeof h2);
-        if (per || pos != 0) {
-            int finm = axis_m(rm, axis) - (axis_g(rm, axis) + 1);
-            l2[axis] = finm - nt + 1; h2[axis] = finm;
-            /* other-axis extents are identical between axis-neighbours */
-            orc_box_get(rm, ORC_CURX + c, l2, h2, glo[rk]);
-        } else {
-            /* replicate cur(str) : optimized_filters.F90:1590-1613 */
-            for (int t = 0; t < nt; t++) { l2[axis] = h2[axis] = str;
-                float *tmp = (float *)malloc(plane * sizeof(float)); orc_box_get(r, ORC_CURX + c, l2, h2, tmp);
-                memcpy(glo[rk] + (size_t)t * plane, tmp, plane * sizeof(float)); free(tmp); }
-        }
-        memcpy(l2, lo, sizeof l2); memcpy(h2, hi, sizeof h2);
-        if (per || pos != sz - 1) {
-            int strp = axis_g(rp, axis) + 1;
-            l2[axis] = strp; h2[axis] = strp + nt - 1;
-            orc_box_get(rp, ORC_CURX + c, l2, h2, ghi[rk]);
-        } else {
-            for (int t = 0; t < nt; t++) { l2[axis] = h2[axis] = fin;
-                float *tmp = (float *)malloc(plane * sizeof(float)); orc_box_get(r, ORC_CURX + c, l2, h2, tmp);
-                memcpy(ghi[rk] + (size_t)t * plane, tmp, plane * sizeof(float)); free(tmp); }
-        }
-    }
-    /* now filter each line */
-#pragma omp parallel for schedule(static)
-    for (int rk = 0; rk < nr; rk++) {
-        orc_rank *r = w->r[rk];
         int lo[3], hi[3];
-        for (int a = 0; a < 3; a++) { lo[a] = axis_g(r, a) + 1; hi[a] = axis_m(r, a) - (axis_g(r, a) + 1); }
-        if (w->P.dim == 2) { lo[2] = hi[2] = 1; }
-        int per = axis_per(r, axis), pos = axis_pos(r, axis), sz = axis_size(r, axis);
-        int str = lo[axis], fin = hi[axis], ncell = fin - str + 1, len = ncell + 2 * nt;
-        int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
-        if (a1 > a2) { int t = a1; a1 = a2; a2 = t; }       /* a1 < a2: a1 is the faster of the two */
-        int n1 = hi[a1] - lo[a1] + 1, n2 = hi[a2] - lo[a2] + 1;
-        float *line = (float *)malloc((size_t)len * sizeof(float));
-        float *cu = r->f[ORC_CURX + c];
-        int lowrep = !(per || pos != 0), highrep = !(per || pos != sz - 1);
-        for (int q2 = 0; q2 < n2; q2++) for (int q1 = 0; q1 < n1; q1++) {
-            int ijk[3]; ijk[a1] = lo[a1] + q1; ijk[a2] = lo[a2] + q2;
-            /* ghost slab layout = orc_box_get order: x fastest, then y, then z over the restricted box */
-            for (int t = 0; t < nt; t++) {
-                size_t off;
-                if (axis == 0) off = (size_t)t + (size_t)nt * ((size_t)q1 + (size_t)n1 * q2);
-                else if (axis == 1) off = (size_t)q1 + (size_t)n1 * ((size_t)t + (size_t)nt * q2);
-                else off = (size_t)q1 + (size_t)n1 * ((size_t)q2 + (size_t)n2 * t);
-                size_t offrep = (size_t)t * n1 * n2 + (size_t)q1 + (size_t)n1 * q2;
-                line[t] = glo[rk][lowrep ? offrep : off];
-                line[nt + ncell + t] = ghi[rk][highrep ? offrep : off];
-            }
-            for (int s = 0; s < ncell; s++) { ijk[axis] = str + s; line[nt + s] = cu[IDX(r, ijk[0], ijk[1], ijk[2])]; }
-            orc_filter2_line(line, len, nt);
-            for (int s = 0; s < ncell; s++) { ijk[axis] = str + s; cu[IDX(r, ijk[0], ijk[1], ijk[2])] = line[nt + s]; }
-        }
-        free(line);
+        orc_filter2_send_box(rm, axis, 0, lo, hi);
+        glo[rk] = (float *)malloc(box_count(lo, hi) * sizeof(float));
+        orc_box_get(rm, ORC_CURX + c, lo, hi, glo[rk]);
+        orc_filter2_send_box(rp, axis, 1, lo, hi);
+        ghi[rk] = (float *)malloc(box_count(lo, hi) * sizeof(float));
+        orc_box_get(rp, ORC_CURX + c, lo, hi, ghi[rk]);
     }
+#pragma omp parallel for schedule(static)
+    for (int rk = 0; rk < nr; rk++) orc_filter2_rank(w->r[rk], c, axis, glo[rk], ghi[rk]);
     for (int rk = 0; rk < nr; rk++) { free(glo[rk]); free(ghi[rk]); }
     free(glo); free(ghi);
 }

@@ -106,6 +106,8 @@ orc_particle *orc_rank_particles(orc_rank *r);
 void orc_rank_dims(const orc_rank *r, int *out /* mx,my,mz,nghost,nghostz,mxcum,mycum,mzcum,maxhlf */);
 void orc_rank_counts(const orc_rank *r, int *ions, int *lecs);
 void orc_rank_set_counts(orc_rank *r, int ions, int lecs);
+orc_particle *orc_rank_box(orc_rank *r, int which /* 0 out, 1 in */, int dir, int *nion, int *nlec);
+void orc_rank_box_set_counts(orc_rank *r, int which, int dir, int nion, int nlec);
 
 /* --- shape weights (Appendix A.1) --- */
 void orc_shape(int order, float d, int shift, float S[8], int *smin, int *smax);
@@ -124,6 +126,8 @@ void orc_inject_others(orc_rank *r);
 void orc_reorder_particles(orc_rank *r);
 void orc_filter1_pass(orc_rank *r);               /* one 9/27-point pass, ghosts assumed fresh */
 void orc_filter2_line(float *line, int len, int ntimes); /* ntimes fixed-end 1-2-1 passes on an extended line */
+void orc_filter2_rank(orc_rank *r, int c, int axis, const float *glo, const float *ghi);
+void orc_filter2_send_box(const orc_rank *r, int axis, int what, int lo[3], int hi[3]);
 
 /* box primitives the exchanges are built from (also used by the gloo tests) */
 void orc_box_get(const orc_rank *r, int which, const int lo[3], const int hi[3], float *buf);
