@@ -1,0 +1,103 @@
+"""Multi-GPU parity: N processes, one GPU each, slabs exchanged over NCCL inside libtristan_gpu.so; every rank is
+compared with the same rank of the in-process multi-rank oracle.  Needs >= 2 GPUs (skipped otherwise)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, case, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import tristan_mp_pu_master_densdecomp_b200 as tg
+        import pic_testlib as T
+        from oracle import oracle as O
+        kw = dict(ppc=4.0, ntimes=3, delgam=0.05)
+        kw.update(case)
+        w = T.oracle_world(**kw)
+        r = w.ranks[rank]
+        ctx = tg.Context(T.gpu_params(tg, w, rank=rank, device=rank))
+        ctx.comm_init_torch()
+        T.upload(ctx, r)
+        err = ""
+        for lap in range(3):
+            ctx.step(1); w.step()
+            fg = ctx.fields_d2h()
+            for a in range(6):
+                e = T.max_rel(T.interior(r, fg[a]), T.interior(r, r.arr(a)))
+                if e > 4e-4 * (lap + 1):
+                    err += f"lap {lap} rank {rank} {O.ARR_NAMES[a]} err {e:.2e}; "
+            if ctx.counts() != r.counts:
+                err += f"lap {lap} rank {rank} counts {ctx.counts()} != {r.counts}; "
+            else:
+                gi, ge = T.gpu_particles(ctx)
+                oi, oe = T.oracle_particles(r)
+                try:
+                    T.assert_particles_close(gi, oi, rtol_pos=3e-5 * (lap + 1), rtol_mom=3e-4 * (lap + 1))
+                    T.assert_particles_close(ge, oe, rtol_pos=3e-5 * (lap + 1), rtol_mom=3e-4 * (lap + 1))
+                except AssertionError as ex:
+                    err += f"lap {lap} rank {rank} particles: {ex}; "
+        moved = int((r.ions()["proc"] != rank).sum())
+        ctx.close()
+        q.put((rank, err, moved))
+    except Exception as ex:  # noqa
+        import traceback
+        q.put((rank, "EXC " + traceback.format_exc()[-1500:], 0))
+    finally:
+        dist.destroy_process_group()
+
+
+CASES = {
+    2: [dict(dim=3, order=2, n=(12, 12, 16), sizes=(1, 1, 2), filter_kind=2),
+        dict(dim=3, order=1, n=(12, 16, 12), sizes=(1, 2, 1), filter_kind=1),
+        dict(dim=3, order=3, n=(12, 12, 16), sizes=(1, 1, 2), filter_kind=2),
+        dict(dim=2, order=2, n=(16, 16, 1), sizes=(2, 1, 1), filter_kind=1)],
+    4: [dict(dim=3, order=2, n=(12, 16, 16), sizes=(1, 2, 2), filter_kind=2),
+        dict(dim=2, order=1, n=(16, 16, 1), sizes=(2, 2, 1), filter_kind=1)],
+    8: [dict(dim=3, order=2, n=(12, 16, 32), sizes=(1, 2, 4), filter_kind=2)],
+}
+
+
+def _run(world, case):
+    import tristan_mp_pu_master_densdecomp_b200 as tg
+    if tg.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+    errs = [e for _, e, _ in res if e]
+    assert not errs, errs
+    assert sum(m for _, _, m in res) > 0, "no particle migrated"
+
+
+@pytest.mark.parametrize("case", CASES[2], ids=["3d-z", "3d-y", "3d-z-o3", "2d-x"])
+def test_two_gpus(tg, case):
+    _run(2, case)
+
+
+@pytest.mark.parametrize("case", CASES[4], ids=["3d-yz", "2d-xy"])
+def test_four_gpus(tg, case):
+    _run(4, case)
+
+
+@pytest.mark.parametrize("case", CASES[8], ids=["3d-2x4"])
+def test_eight_gpus(tg, case):
+    _run(8, case)

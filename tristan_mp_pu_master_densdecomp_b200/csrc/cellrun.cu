@@ -26,6 +26,9 @@
 
 #define CR_WARPS 8
 #define CR_STRIDE 44
+#ifndef CR_MINB
+#define CR_MINB 3
+#endif
 #define CR_CHUNK 128          // particles per half-warp
 
 struct CRArgs {
@@ -72,6 +75,32 @@ __device__ __forceinline__ void gather_nodes(const float4 *__restrict__ prim8, l
     }
 }
 
+// 3x3x3 path (particle exactly on a node under Q1, or quirks = fixed): kept out of line so that its register
+// demand does not set the occupancy of the common 2x2x2 path
+__device__ __noinline__ void gather27(const float4 *__restrict__ prim8, long long nbase, int mx, int my, const float *w9, float *eb)
+{
+    float e0 = 0, e1 = 0, e2 = 0, b0 = 0, b1 = 0, b2 = 0;
+#pragma unroll 1
+    for (int c3 = 0; c3 < 3; c3++) {
+#pragma unroll 1
+        for (int c2 = 0; c2 < 3; c2++) {
+            float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
+            const float4 *row = prim8 + 2 * (nbase + (long long)mx * (c2 + (long long)my * c3));
+#pragma unroll 1
+            for (int c1 = 0; c1 < 3; c1++) {
+                const float4 lo = __ldg(row + 2 * c1), hi = __ldg(row + 2 * c1 + 1);
+                const float wx = w9[c1];
+                s0 = s0 + lo.x * wx; s1 = s1 + lo.y * wx; s2 = s2 + lo.z * wx;
+                s3 = s3 + lo.w * wx; s4 = s4 + hi.x * wx; s5 = s5 + hi.y * wx;
+            }
+            const float wy_ = w9[3 + c2], wz_ = w9[6 + c3];
+            e0 = e0 + s0 * wy_ * wz_; e1 = e1 + s1 * wy_ * wz_; e2 = e2 + s2 * wy_ * wz_;
+            b0 = b0 + s3 * wy_ * wz_; b1 = b1 + s4 * wy_ * wz_; b2 = b2 + s5 * wy_ * wz_;
+        }
+    }
+    eb[0] = e0; eb[1] = e1; eb[2] = e2; eb[3] = b0; eb[4] = b1; eb[5] = b2;
+}
+
 // 1-D factors of one axis -> shared staging.  MODE 0: x (q*prefix, XA, XB); MODE 1: y/z rows (S1, dS, q*prefix, tag)
 template <int MODE>
 __device__ __forceinline__ void stage_axis(float *st, const float S1[4], const float S2[4], float q, float tag)
@@ -115,7 +144,7 @@ __device__ __forceinline__ uint32_t sort_key(const DevGeom &G, float x, float y,
 }
 
 template <int ORDER, bool FUSED>
-__global__ void __launch_bounds__(CR_WARPS * 32, 2) k_cellrun(CRArgs A)
+__global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
 {
     __shared__ __align__(16) float stage[CR_WARPS][32][CR_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -163,13 +192,14 @@ __global__ void __launch_bounds__(CR_WARPS * 32, 2) k_cellrun(CRArgs A)
                         const float dxd = x - half_ - (int)(x - half_), dyd = y - half_ - (int)(y - half_), dzd = (z - half_) - (int)(z - half_);
                         lox = dxd <= half_ ? 0 : 1; loy = dyd <= half_ ? 0 : 1; loz = dzd <= half_ ? 0 : 1;
                     } else { lox = dxp <= half_ ? 0 : 1; loy = dyp <= half_ ? 0 : 1; loz = dzp <= half_ ? 0 : 1; }
-                    float wxs[3], wys[3], wzs[3];
+                    float w9[9], eb[6];
 #pragma unroll
                     for (int a = 0; a < 3; a++) {
-                        wxs[a] = lox ? Wx[a + 1] : Wx[a]; wys[a] = loy ? Wy[a + 1] : Wy[a]; wzs[a] = loz ? Wz[a + 1] : Wz[a];
+                        w9[a] = lox ? Wx[a + 1] : Wx[a]; w9[3 + a] = loy ? Wy[a + 1] : Wy[a]; w9[6 + a] = loz ? Wz[a + 1] : Wz[a];
                     }
                     const long long nbase = (ip - 2 + lox) + (long long)mx * ((jp - 2 + loy) + (long long)my * (kp - 2 + loz));
-                    gather_nodes<3>(A.prim8, nbase, mx, my, wxs, wys, wzs, e0, e1, e2, b0, b1, b2);
+                    gather27(A.prim8, nbase, mx, my, w9, eb);
+                    e0 = eb[0]; e1 = eb[1]; e2 = eb[2]; b0 = eb[3]; b1 = eb[4]; b2 = eb[5];
                 }
                 const float cinv = 1.f / G.c, qm = A.qm;
                 e0 = 0.5f * e0 * qm; e1 = 0.5f * e1 * qm; e2 = 0.5f * e2 * qm;
@@ -215,14 +245,13 @@ __global__ void __launch_bounds__(CR_WARPS * 32, 2) k_cellrun(CRArgs A)
         // ------------------------------------------------------------------ phase 2: half-warp = footprint
         const long long rem = A.n - (base + it * 16);
         const int cnt = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
-        int tt = 0;
-        while (tt < cnt) {
-            // particle tt opens a run of particles that share one footprint
-            const unsigned later = starts >> (tt + 1);
-            int next = later ? tt + __ffs(later) : 16;
-            if (next > cnt) next = cnt;
-            {
-                const float4 *sp = (const float4 *)&stage[warp][(half << 4) + tt][0];
+        // Both halves walk their 16 particles in lockstep; only the (rare) window moves diverge.
+        const float4 *sp = (const float4 *)&stage[warp][half << 4][0];
+#pragma unroll 2
+        for (int tt = 0; tt < 16; ++tt, sp += CR_STRIDE / 4) {
+            if (tt >= cnt) break;
+            if ((starts >> tt) & 1u) {
+                // particle tt opens a run of particles that share one footprint
                 const int ni = __float_as_int(sp[3].w), nrow = __float_as_int(sp[7].w);
                 if (!have || ni != wi || nrow != wrow) {
                     if (have) {
@@ -252,20 +281,20 @@ __global__ void __launch_bounds__(CR_WARPS * 32, 2) k_cellrun(CRArgs A)
                     wi = ni; wrow = nrow; have = true;
                 }
             }
-            for (; tt < next; ++tt) {
-                const float4 *sp = (const float4 *)&stage[warp][(half << 4) + tt][0];
-                const float4 yv = sp[3 + j], zv = sp[7 + k];
-                const float4 qpsx = sp[0], xa = sp[1], xb = sp[2];
-                const float sy1 = yv.x, dsy = yv.y, qpsy = yv.z;
-                const float sz1 = zv.x, dsz = zv.y, qpsz = zv.z;
-                const float ya = sy1 + 0.5f * dsy, yb = 0.5f * sy1 + (1.f / 3.f) * dsy;
-                const float wx = ya * sz1 + yb * dsz;          // Wx(j,k)
-                const float a = qpsy * sz1, b = qpsy * dsz;    // Jy = XA*a + XB*b
-                const float c = qpsz * sy1, d = qpsz * dsy;    // Jz = XA*c + XB*d
-                ax[0] += qpsx.x * wx; ax[1] += qpsx.y * wx; ax[2] += qpsx.z * wx; ax[3] += qpsx.w * wx;
-                ay[0] += xa.x * a + xb.x * b; ay[1] += xa.y * a + xb.y * b; ay[2] += xa.z * a + xb.z * b; ay[3] += xa.w * a + xb.w * b;
-                az[0] += xa.x * c + xb.x * d; az[1] += xa.y * c + xb.y * d; az[2] += xa.z * c + xb.z * d; az[3] += xa.w * c + xb.w * d;
-            }
+            const float4 yv = sp[3 + j], zv = sp[7 + k];
+            const float4 qpsx = sp[0], xa = sp[1], xb = sp[2];
+            const float sy1 = yv.x, dsy = yv.y, qpsy = yv.z;
+            const float sz1 = zv.x, dsz = zv.y, qpsz = zv.z;
+            const float ya = fmaf(0.5f, dsy, sy1), yb = fmaf(1.f / 3.f, dsy, 0.5f * sy1);
+            const float wx = fmaf(yb, dsz, ya * sz1);      // Wx(j,k)
+            const float a = qpsy * sz1, b = qpsy * dsz;    // Jy = XA*a + XB*b
+            const float c = qpsz * sy1, d = qpsz * dsy;    // Jz = XA*c + XB*d
+            ax[0] = fmaf(qpsx.x, wx, ax[0]); ax[1] = fmaf(qpsx.y, wx, ax[1]);
+            ax[2] = fmaf(qpsx.z, wx, ax[2]); ax[3] = fmaf(qpsx.w, wx, ax[3]);
+            ay[0] = fmaf(xa.x, a, fmaf(xb.x, b, ay[0])); ay[1] = fmaf(xa.y, a, fmaf(xb.y, b, ay[1]));
+            ay[2] = fmaf(xa.z, a, fmaf(xb.z, b, ay[2])); ay[3] = fmaf(xa.w, a, fmaf(xb.w, b, ay[3]));
+            az[0] = fmaf(xa.x, c, fmaf(xb.x, d, az[0])); az[1] = fmaf(xa.y, c, fmaf(xb.y, d, az[1]));
+            az[2] = fmaf(xa.z, c, fmaf(xb.z, d, az[2])); az[3] = fmaf(xa.w, c, fmaf(xb.w, d, az[3]));
         }
         __syncwarp();
     }

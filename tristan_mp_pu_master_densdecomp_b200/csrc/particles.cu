@@ -408,9 +408,15 @@ __device__ __forceinline__ void classify(const DevGeom &G, float &x, float &y, f
     discard = !in;
     code = 4;
     if (!in) return;
+    // The reference tests x, then y, then z; once a particle is marked for sending along a split axis the remaining
+    // shifts are zeroed (:1583-1586, :1598-1602).  In 3D the receiver re-tests z (inject_others, particles.F90:1431),
+    // so every shift ends up applied.  In 2D a particle sent in x keeps an out-of-range y when y is not split, and any
+    // sent particle keeps an out-of-range z: those wraps happen one lap later, at the next deposit_particles.
+    const bool sent_x = G.dim == 2 && G.sendx && dx != 0;
+    const bool sent_y = G.sendy && dy != 0;
     if (dx < 0) x = x + G.shiftx_lo; else if (dx > 0) x = x - G.shiftx_hi;
-    if (dy < 0) y = y + G.shifty_lo; else if (dy > 0) y = y - G.shifty_hi;
-    if (dz < 0) z = z + G.shiftz_lo; else if (dz > 0) z = z - G.shiftz_hi;
+    if (!sent_x || G.sendy) { if (dy < 0) y = y + G.shifty_lo; else if (dy > 0) y = y - G.shifty_hi; }
+    if (G.dim == 3 || !(sent_x || sent_y)) { if (dz < 0) z = z + G.shiftz_lo; else if (dz > 0) z = z - G.shiftz_hi; }
     int da, db;
     if (G.dim == 3) { da = G.sendy ? dy : 0; db = G.sendz ? dz : 0; }
     else { da = G.sendx ? dx : 0; db = G.sendy ? dy : 0; }
