@@ -423,22 +423,21 @@ __device__ __forceinline__ size_t f2_addr(const F2 &f, int p_cell, int q1, int q
     return (size_t)(ijk[0] - 1) + (size_t)f.mx * ((size_t)(ijk[1] - 1) + (size_t)f.my * (size_t)(ijk[2] - 1));
 }
 
-// Shared memory holds the tile only for the coalesced load/store; the passes themselves run in registers: thread
-// (line, strip) keeps R consecutive line elements and exchanges one edge value per side per pass with its strip
-// neighbours through a double-buffered shared array (one __syncthreads per pass).
-// tile layout: axis 0 -> [line][p] with an odd pitch (p contiguous in memory); other axes -> [p][line] (line = x index).
+// Shared memory holds the tile only for the coalesced load/store.  The passes run in registers with no block-level
+// synchronisation: one warp owns one whole extended line, lane l keeps R consecutive elements (R odd, so the strided
+// shared-memory reads are conflict-free) and trades one edge value per side per pass with its lane neighbours through
+// warp shuffles.  Every global element is read and written once per axis; the arithmetic per pass is exactly
+// new(p) = .25*old(p-1) + .5*old(p) + .25*old(p+1) with both end points of the extended line held fixed.
+// tile layout: [line][Lp], Lp = 32*R + 1.
 template <int R>
-__global__ void __launch_bounds__(1024) k_filter2(float *__restrict__ cur, const float *__restrict__ halo_lo,
-                                                  const float *__restrict__ halo_hi, F2 f, int NL, int NS)
+__global__ void __launch_bounds__(512) k_filter2(float *__restrict__ cur, const float *__restrict__ halo_lo,
+                                                 const float *__restrict__ halo_hi, F2 f, int NL)
 {
-    extern __shared__ float sm[];
+    extern __shared__ float tile[];
     const int L = f.ncell + 2 * f.nt;
-    const int Lp = L | 1;
+    constexpr int Lp = 32 * R + 1;
     const int nlines = f.q_n[0] * f.q_n[1];
     const int line0 = blockIdx.x * NL;
-    const int sp = f.axis == 0 ? 1 : NL, sl = f.axis == 0 ? Lp : 1;
-    float *tile = sm;
-    float *edge = sm + (size_t)Lp * NL;                 // [2 parity][2 side][NS][NL]
     const int nthr = blockDim.x;
     for (int t = threadIdx.x; t < L * NL; t += nthr) {
         int p, ln;
@@ -458,36 +457,33 @@ __global__ void __launch_bounds__(1024) k_filter2(float *__restrict__ cur, const
                 else v = cur[f2_addr(f, f.str + f.ncell - 1, q1, q2)];
             } else v = cur[f2_addr(f, f.str + pc, q1, q2)];
         }
-        tile[p * sp + ln * sl] = v;
+        tile[ln * Lp + p] = v;
     }
     __syncthreads();
-    const int ln = threadIdx.x % NL, strip = threadIdx.x / NL;
-    const int p0 = strip * R;
-    float v[R];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int p0 = lane * R;
+    for (int ln = warp; ln < NL; ln += nwarps) {
+        float *row = tile + ln * Lp + p0;
+        float v[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) v[r] = (p0 + r < L) ? tile[(p0 + r) * sp + ln * sl] : 0.f;
-    const int es = NS * NL;                              // one side of one parity
-    for (int n = 0; n < f.nt; n++) {
-        float *e = edge + (size_t)(n & 1) * 2 * es;
-        e[strip * NL + ln] = v[0];
-        e[es + strip * NL + ln] = v[R - 1];
-        __syncthreads();
-        const float left = strip > 0 ? e[es + (strip - 1) * NL + ln] : 0.f;
-        const float right = strip < NS - 1 ? e[(strip + 1) * NL + ln] : 0.f;
-        float prev = left;
+        for (int r = 0; r < R; r++) v[r] = (p0 + r < L) ? row[r] : 0.f;
+        for (int n = 0; n < f.nt; n++) {
+            const float left = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
+            const float right = __shfl_down_sync(0xffffffffu, v[0], 1);
+            float prev = left;
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int p = p0 + r;
-            const float c = v[r];
-            const float nx = r < R - 1 ? v[r + 1] : right;
-            const float nv = .25f * prev + .5f * c + .25f * nx;
-            v[r] = (p == 0 || p >= L - 1) ? c : nv;
-            prev = c;
+            for (int r = 0; r < R; r++) {
+                const int p = p0 + r;
+                const float c = v[r];
+                const float nx = r < R - 1 ? v[r + 1] : right;
+                const float nv = .25f * prev + .5f * c + .25f * nx;
+                v[r] = (p == 0 || p >= L - 1) ? c : nv;
+                prev = c;
+            }
         }
-    }
-    __syncthreads();
 #pragma unroll
-    for (int r = 0; r < R; r++) if (p0 + r < L) tile[(p0 + r) * sp + ln * sl] = v[r];
+        for (int r = 0; r < R; r++) if (p0 + r < L) row[r] = v[r];
+    }
     __syncthreads();
     for (int t = threadIdx.x; t < f.ncell * NL; t += nthr) {
         int p, l2;
@@ -495,7 +491,7 @@ __global__ void __launch_bounds__(1024) k_filter2(float *__restrict__ cur, const
         int line = line0 + l2;
         if (line < nlines) {
             int q1 = line % f.q_n[0], q2 = line / f.q_n[0];
-            cur[f2_addr(f, f.str + p, q1, q2)] = tile[(p + f.nt) * sp + l2 * sl];
+            cur[f2_addr(f, f.str + p, q1, q2)] = tile[l2 * Lp + p + f.nt];
         }
     }
 }
@@ -548,26 +544,26 @@ int fld_filter2(tgpu_ctx *h)
                 f.lowmode = (per || pos != 0) ? 1 : 2;
                 f.highmode = (per || pos != sz - 1) ? 1 : 2;
             }
-            const int L = f.ncell + 2 * f.nt, Lp = L | 1;
+            const int L = f.ncell + 2 * f.nt;
             int nlines = f.q_n[0] * f.q_n[1];
-            // strip length R: smallest of 8/16/32/64 that keeps NS = ceil(L/R) <= 32 strips (<= 1024 threads at NL = 32)
-            int R = 8; while (R < 64 && (L + R - 1) / R > 32) R <<= 1;
-            int NS = (L + R - 1) / R;
+            // strip length R (odd): smallest instantiated value with 32*R >= L
+            int R = L <= 224 ? 7 : L <= 352 ? 11 : L <= 608 ? 19 : L <= 1120 ? 35 : 0;
+            if (!R) { tgpu_set_error("filter2: extended line longer than 1120 elements is not instantiated"); return TGPU_EINVAL; }
+            const int Lp = 32 * R + 1;
             int NL = 32;
-            while (NL > 1 && ((size_t)Lp * NL + 4 * (size_t)NS * NL) * 4 > 200 * 1024) NL >>= 1;
-            while (NL * NS > 1024) NL >>= 1;
-            size_t smem = ((size_t)Lp * NL + 4 * (size_t)NS * NL) * 4;
-            if (NL < 1 || smem > 220 * 1024) { tgpu_set_error("filter2: line too long for shared memory"); return TGPU_EINVAL; }
+            while (NL > 1 && (size_t)Lp * NL * 4 > 100 * 1024) NL >>= 1;
+            size_t smem = (size_t)Lp * NL * 4;
+            int threads = NL >= 16 ? 512 : NL * 32;
 #define LAUNCH_F2(RV)                                                                                              \
     {                                                                                                              \
         CK(cudaFuncSetAttribute(k_filter2<RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-        k_filter2<RV><<<cdiv(nlines, NL), NL * NS, smem, h->stream>>>(h->f[6 + c], hlo, hhi, f, NL, NS);           \
+        k_filter2<RV><<<cdiv(nlines, NL), threads, smem, h->stream>>>(h->f[6 + c], hlo, hhi, f, NL);               \
     }
             switch (R) {
-            case 8: LAUNCH_F2(8) break;
-            case 16: LAUNCH_F2(16) break;
-            case 32: LAUNCH_F2(32) break;
-            default: LAUNCH_F2(64) break;
+            case 7: LAUNCH_F2(7) break;
+            case 11: LAUNCH_F2(11) break;
+            case 19: LAUNCH_F2(19) break;
+            default: LAUNCH_F2(35) break;
             }
 #undef LAUNCH_F2
             CKK(h);
