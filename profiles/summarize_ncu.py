@@ -60,8 +60,8 @@ def main():
         print(f"\n== {name[:90]} ==  warp-instructions {tot}" + (f"  = {tot / units:.1f} per unit" if units else ""))
         stall = collections.Counter()
         for i, c in enumerate(hdr2):
-            if c.startswith("stall_") and "Not Issued" not in c:
-                stall[c] += sum(num(r[i]) for r in d["sass"])
+            if c.startswith("stall_") and "Not Issued" not in c and i < len(d["sass"][0]):
+                stall[c] += sum(num(r[i]) for r in d["sass"] if i < len(r))
         ssum = sum(stall.values()) or 1
         print("  stalls: " + ", ".join(f"{k[6:]} {100 * v / ssum:.1f}%" for k, v in stall.most_common(8)))
         ops = collections.Counter()

@@ -2,6 +2,7 @@
 // replacements of the procedures mainloop() calls (code/tristanmainloop.F90:107-344).
 #include <cub/device/device_scan.cuh>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include "tgpu_internal.h"
 
@@ -69,14 +70,22 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     CK(cudaSetDevice(h->device));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, h->device));
     if (prop.major < 10) { delete h; tgpu_set_error(std::string("device is not sm_100 class: ") + prop.name); return TGPU_ECUDA; }
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    // the field kernels are short and latency-bound, the particle scatter is long and HBM-bound: giving the field stream
+    // the higher priority lets its CTAs slip in between the scatter's instead of queueing behind them
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&h->stream_main, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&h->stream_prt, cudaStreamNonBlocking, prio_lo));
+    h->stream = h->stream_main;
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+    CK(cudaEventCreateWithFlags(&h->ev_move, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_prt, cudaEventDisableTiming));
+    h->prt_pending = 0; h->opt_overlap = getenv("TGPU_OVERLAP") ? atoi(getenv("TGPU_OVERLAP")) : 1; h->nccl_main = h->nccl_prt = nullptr;
     h->maxhlf = p->maxptl / 2;
     DevGeom &G = h->G;
     G.dim = p->dim; G.order = p->order; G.mx = p->mx; G.my = p->my; G.mz = p->mz;
     G.nghost = p->nghost; G.nghostz = p->nghostz; G.g = p->nghost / 2; G.gz = p->nghostz / 2;
     G.lot = (long long)p->mx * p->my * p->mz;
-    G.c = p->c; G.corr = p->corr; G.quirks = p->quirks; G.pusher = p->pusher; G.external_fields = p->external_fields;
+    G.c = p->c; G.corr = p->corr; G.cinv = 1.f / p->c; G.quirks = p->quirks; G.pusher = p->pusher; G.external_fields = p->external_fields;
     for (int i = 0; i < 6; i++) G.ext[i] = p->ext[i];
     // particles_movedeposit.F90:1359-1374
     G.minx = 1.f * (G.g + 1); G.maxx = p->mx - 1.f * G.g; G.miny = 1.f * (G.g + 1); G.maxy = p->my - 1.f * G.g;
@@ -125,7 +134,7 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
         rc |= dalloc(&h->sendbuf, (size_t)TGPU_NDIR * p->buffsize); rc |= dalloc(&h->recvbuf, (size_t)TGPU_NDIR * p->buffsize);
     }
     if (rc) { tgpu_set_error("device allocation failed: " + g_err); return TGPU_ECUDA; }
-    h->need_prim = 1; h->fused_pending = 0; h->keys_valid = 0; h->opt_fused = 1; h->nccl_comm = nullptr; h->lap = 0; h->launches = 0; h->timing = 0;
+    h->need_prim = 1; h->fused_pending = 0; h->keys_valid = 0; h->in_step = 0; h->opt_fused = 1; h->nccl_comm = nullptr; h->lap = 0; h->launches = 0; h->timing = 0;
     for (int i = 0; i < TGPU_NPHASE; i++) h->phase_ms[i] = 0;
     CK(cudaDeviceSynchronize());
     *out = h;
@@ -136,7 +145,7 @@ extern "C" int tgpu_finalize(tgpu_ctx *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->stream_main); cudaStreamSynchronize(h->stream_prt);
     comm_destroy(h);
     for (int a = 0; a < 9; a++) cudaFree(h->f[a]);
     for (int a = 0; a < 3; a++) { cudaFree(h->ftmp[a]); cudaFree(h->shadow[a]); }
@@ -147,13 +156,20 @@ extern "C" int tgpu_finalize(tgpu_ctx *h)
     cudaFreeHost(h->h_small); cudaFree(h->stage);
     if (h->sendbuf) cudaFree(h->sendbuf);
     if (h->recvbuf) cudaFree(h->recvbuf);
-    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
-    cudaStreamDestroy(h->stream);
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev_move); cudaEventDestroy(h->ev_prt);
+    cudaStreamDestroy(h->stream_main); cudaStreamDestroy(h->stream_prt);
     delete h;
     return 0;
 }
 
-#define ENTER(h) do { if (!(h)) { tgpu_set_error("null context"); return TGPU_EINVAL; } CK(cudaSetDevice((h)->device)); } while (0)
+// Every public entry point runs on stream_main.  If tgpu_step left particle work in flight on stream_prt, order it first.
+static int join_prt(tgpu_ctx *h)
+{
+    if (h->prt_pending) { CK(cudaStreamWaitEvent(h->stream_main, h->ev_prt, 0)); h->prt_pending = 0; }
+    return 0;
+}
+#define ENTER(h) do { if (!(h)) { tgpu_set_error("null context"); return TGPU_EINVAL; } CK(cudaSetDevice((h)->device)); \
+                      if (!(h)->in_step) { int rcj_ = join_prt(h); if (rcj_) return rcj_; } } while (0)
 
 // per-phase device timing (print_timers analogue); only when enabled, because it synchronises
 struct PhaseTimer {
@@ -285,25 +301,54 @@ extern "C" int tgpu_step(tgpu_ctx *h, int nlaps)
 {
     ENTER(h);
     int rc = 0;
-#define DO(x) do { rc = (x); if (rc) return rc; } while (0)
+#define DO(x) do { rc = (x); if (rc) { h->in_step = 0; return rc; } } while (0)
+    // Overlap: once the fused mover has written the sort keys, the scan + scatter + migration of the particles depends
+    // on nothing the field phase does (and vice versa), so it runs on stream_prt while B-half/E-full/fold/filter/add run
+    // on stream_main.  Needs the fused mover (keys in hand) and is skipped while per-phase timing is on.
+    const bool overlap = h->opt_overlap && h->opt_fused && cellrun_supported(h) && !h->timing;
+    h->in_step = 1;
     for (int l = 0; l < nlaps; l++) {
         h->lap++;
         DO(tgpu_bc_e1(h));                 // :118 (E changed by add_current)
         DO(tgpu_advance_b_halfstep(h));    // :119
         DO(tgpu_bc_b1(h));                 // :122
+        DO(join_prt(h));                   // particles of the previous lap are sorted and migrated
         DO(tgpu_move_particles(h));        // :134
-        DO(tgpu_advance_b_halfstep(h));    // :139
-        DO(tgpu_bc_b1(h));                 // :140
-        DO(tgpu_advance_e_fullstep(h));    // :159
-        DO(tgpu_reset_currents(h));        // :171
-        DO(tgpu_deposit_particles(h));     // :183
-        DO(tgpu_exchange_particles(h));    // :190, :257-272
-        DO(tgpu_exchange_current(h));      // :203
-        DO(tgpu_apply_filter(h));          // :213-229
-        DO(tgpu_add_current(h));           // :242
+        if (overlap) {
+            CK(cudaEventRecord(h->ev_move, h->stream_main));
+            DO(tgpu_advance_b_halfstep(h));    // :139
+            DO(tgpu_bc_b1(h));                 // :140
+            DO(tgpu_advance_e_fullstep(h));    // :159
+            DO(tgpu_reset_currents(h));        // :171
+            DO(fld_add_shadow(h)); h->fused_pending = 0;      // :183, current part of deposit_particles
+            DO(tgpu_exchange_current(h));      // :203
+            DO(tgpu_apply_filter(h));          // :213-229
+            DO(tgpu_add_current(h));           // :242
+            // particle side, concurrently
+            h->stream = h->stream_prt; h->nccl_comm = h->nccl_prt;
+            rc = cudaStreamWaitEvent(h->stream_prt, h->ev_move, 0) == cudaSuccess ? 0 : TGPU_ECUDA;
+            if (!rc) rc = prt_sort(h, false);                  // :183 loops B, C (+ counting sort)
+            if (!rc) rc = prt_exchange(h);                     // :190, :257-272
+            if (!rc) rc = cudaEventRecord(h->ev_prt, h->stream_prt) == cudaSuccess ? 0 : TGPU_ECUDA;
+            h->stream = h->stream_main; h->nccl_comm = h->nccl_main;
+            if (rc) { h->in_step = 0; if (rc == TGPU_ECUDA) tgpu_set_error("stream overlap failed"); return rc; }
+            h->prt_pending = 1;
+        } else {
+            DO(tgpu_advance_b_halfstep(h));    // :139
+            DO(tgpu_bc_b1(h));                 // :140
+            DO(tgpu_advance_e_fullstep(h));    // :159
+            DO(tgpu_reset_currents(h));        // :171
+            DO(tgpu_deposit_particles(h));     // :183
+            DO(tgpu_exchange_particles(h));    // :190, :257-272
+            DO(tgpu_exchange_current(h));      // :203
+            DO(tgpu_apply_filter(h));          // :213-229
+            DO(tgpu_add_current(h));           // :242
+        }
     }
+    h->in_step = 0;
 #undef DO
-    return 0;
+    // anything recorded on stream_main after this call (the caller's timing events) must also cover the particle stream
+    return join_prt(h);
 }
 
 extern "C" int tgpu_timers(tgpu_ctx *h, double *out_ms, int reset)
@@ -320,6 +365,7 @@ extern "C" int tgpu_set_option(tgpu_ctx *h, const char *name, int value)
     if (!h || !name) return TGPU_EINVAL;
     if (!strcmp(name, "fused")) { h->opt_fused = value; return 0; }
     if (!strcmp(name, "timing")) { h->timing = value; return 0; }
+    if (!strcmp(name, "overlap")) { h->opt_overlap = value; return 0; }
     tgpu_set_error(std::string("unknown option ") + name);
     return TGPU_EINVAL;
 }

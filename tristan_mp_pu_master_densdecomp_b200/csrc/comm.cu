@@ -112,6 +112,8 @@ extern "C" int tgpu_comm_unique_id(uint8_t id[128])
     return 0;
 }
 
+typedef int (*fn_Bcast)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t);
+
 extern "C" int tgpu_comm_init(tgpu_ctx *h, const uint8_t id[128])
 {
     if (!h) return TGPU_EINVAL;
@@ -120,14 +122,27 @@ extern "C" int tgpu_comm_init(tgpu_ctx *h, const uint8_t id[128])
     CK(cudaSetDevice(h->device));
     nccl_uid u; memcpy(u.internal, id, 128);
     nccl_comm_t c; NCK(N.CommInitRank(&c, h->size0, u, h->P.rank));
-    h->nccl_comm = c;
+    h->nccl_main = c; h->nccl_comm = c;
+    // second communicator for the particle stream: its id is made on rank 0 and broadcast over the first one
+    fn_Bcast Bcast = (fn_Bcast)dlsym(N.lib, "ncclBroadcast");
+    if (!Bcast) { tgpu_set_error("NCCL symbol missing: ncclBroadcast"); return TGPU_ENCCL; }
+    nccl_uid u2; memset(&u2, 0, sizeof u2);
+    if (h->P.rank == 0) NCK(N.GetUniqueId(&u2));
+    uint8_t *d = (uint8_t *)h->d_small;                 // 512 bytes of device scratch
+    CK(cudaMemcpyAsync(d, u2.internal, 128, cudaMemcpyHostToDevice, h->stream));
+    NCK(Bcast(d, d, 128, /*ncclInt8*/ 0, 0, c, h->stream));
+    CK(cudaMemcpyAsync(u2.internal, d, 128, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    nccl_comm_t c2; NCK(N.CommInitRank(&c2, h->size0, u2, h->P.rank));
+    h->nccl_prt = c2;
     return 0;
 }
 
 int comm_destroy(tgpu_ctx *h)
 {
-    if (h->nccl_comm && N.CommDestroy) N.CommDestroy((nccl_comm_t)h->nccl_comm);
-    h->nccl_comm = nullptr;
+    if (h->nccl_main && N.CommDestroy) N.CommDestroy((nccl_comm_t)h->nccl_main);
+    if (h->nccl_prt && N.CommDestroy) N.CommDestroy((nccl_comm_t)h->nccl_prt);
+    h->nccl_comm = h->nccl_main = h->nccl_prt = nullptr;
     return 0;
 }
 

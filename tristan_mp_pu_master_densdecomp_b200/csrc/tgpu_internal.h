@@ -21,7 +21,7 @@ struct DevGeom {             // passed by value to kernels
     int g, gz;               // nghost/2, nghostz/2
     int nghost, nghostz;
     long long lot;
-    float c, corr;
+    float c, corr, cinv;
     int quirks, pusher, external_fields;
     float ext[6];
     // classification (particles_movedeposit.F90:1359-1374, 1546-1633)
@@ -57,9 +57,14 @@ struct tgpu_ctx {
     float *shadow[3];
     int opt_fused;
     int keys_valid;          // key[]/slot[]/bincount[] already hold this lap's sort keys (written by the fused mover)
-    cudaStream_t stream;
-    cudaEvent_t ev0, ev1;
-    void *nccl_comm;         // ncclComm_t
+    cudaStream_t stream;     // the stream every launch helper uses (normally == stream_main)
+    cudaStream_t stream_main, stream_prt;   // tgpu_step overlaps the particle sort/migration (stream_prt) with the field phase
+    cudaEvent_t ev0, ev1, ev_move, ev_prt;
+    int in_step;
+    int prt_pending;         // ev_prt must be waited for before the particle arrays are touched on stream_main
+    int opt_overlap;
+    void *nccl_comm;         // ncclComm_t used on `stream` (normally == nccl_main)
+    void *nccl_main, *nccl_prt;   // two communicators: NCCL calls from two streams must not share one
     int lap;
     int64_t launches;
     double phase_ms[TGPU_NPHASE];
