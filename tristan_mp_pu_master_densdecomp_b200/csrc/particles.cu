@@ -449,14 +449,14 @@ template <bool WRAP>
 __global__ void __launch_bounds__(256) k_scatter(Species a, Species b, int n, const uint32_t *__restrict__ key,
                                                  const int32_t *__restrict__ slot, const int32_t *__restrict__ binoff, DevGeom G)
 {
-    // grid-stride over a bounded grid (64 CTAs per SM)
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        int d = binoff[key[t]] + slot[t];
-        float x = a.x[t], y = a.y[t], z = a.z[t];
-        if (WRAP) { int code; bool discard; classify(G, x, y, z, code, discard); }
-        b.x[d] = x; b.y[d] = y; b.z[d] = z; b.u[d] = a.u[t]; b.v[d] = a.v[t]; b.w[d] = a.w[t];
-        b.ch[d] = a.ch[t]; b.ind[d] = a.ind[t]; b.tag[d] = a.tag[t];
-    }
+    // one thread per particle (measured faster than grid-stride loops over a bounded grid: 6.3 vs 8.2 ms per lap)
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int d = binoff[key[t]] + slot[t];
+    float x = a.x[t], y = a.y[t], z = a.z[t];
+    if (WRAP) { int code; bool discard; classify(G, x, y, z, code, discard); }
+    b.x[d] = x; b.y[d] = y; b.z[d] = z; b.u[d] = a.u[t]; b.v[d] = a.v[t]; b.w[d] = a.w[t];
+    b.ch[d] = a.ch[t]; b.ind[d] = a.ind[t]; b.tag[d] = a.tag[t];
 }
 
 // After prt_sort: sp[s].n = stayers; h_small[s*16 + c] / [s*16 + 8.. ] hold leaver ranges (offset table of the 11 tail bins).
@@ -482,10 +482,10 @@ int prt_sort(tgpu_ctx *h, bool)
         Species &S = h->sp[s];
         if (S.n) {
             if (wrap_in_scatter)
-                k_scatter<true><<<min(cdiv(S.n, 256), 148 * 64), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->key[s], h->slot + (size_t)s * h->maxhlf,
+                k_scatter<true><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->key[s], h->slot + (size_t)s * h->maxhlf,
                                                                       h->binoff + (size_t)s * (nb + 1), h->G);
             else
-                k_scatter<false><<<min(cdiv(S.n, 256), 148 * 64), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->key[s], h->slot + (size_t)s * h->maxhlf,
+                k_scatter<false><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->key[s], h->slot + (size_t)s * h->maxhlf,
                                                                        h->binoff + (size_t)s * (nb + 1), h->G);
             CKK(h);
         }
