@@ -283,8 +283,17 @@ def main():
     md_ms = ph["mover"] + ph["deposit"]
     alg_bytes = sum(counts) * B_PER_PARTICLE
     achieved = alg_bytes / (md_ms * 1e-3) / 1e9 if md_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tj = json.load(f)
+        if list(args.cells) == [512, 256, 128] and args.fused:
+            traffic = 2 * tj["traffic_per_launch"]            # two launches (ions, electrons) per lap
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "mover+deposit (k_cellrun_fused / k_move+k_deposit), per lap",
+                "traffic": traffic, "kernel": "k_cellrun<2,fused> (gather + Boris push + Esirkepov deposit + sort keys), the two "
+                "launches (ions, electrons) of one lap",
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": md_ms, "peak_source": peak_src,
                 "phase_ms": ph}
 
