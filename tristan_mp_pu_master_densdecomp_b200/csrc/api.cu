@@ -79,6 +79,7 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     h->stream = h->stream_main;
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
     CK(cudaEventCreateWithFlags(&h->ev_move, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_prt, cudaEventDisableTiming));
+    h->opt_lazy = getenv("TGPU_LAZY") ? atoi(getenv("TGPU_LAZY")) : 1;
     h->prt_pending = 0; h->opt_overlap = getenv("TGPU_OVERLAP") ? atoi(getenv("TGPU_OVERLAP")) : 1; h->nccl_main = h->nccl_prt = nullptr;
     h->maxhlf = p->maxptl / 2;
     DevGeom &G = h->G;
@@ -115,7 +116,8 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     rc |= dalloc(&h->halo, h->halo_floats);
     for (int s = 0; s < 2; s++) {
         rc |= alloc_species(h->sp[s], h->maxhlf); rc |= alloc_species(h->alt[s], h->maxhlf);
-        rc |= dalloc(&h->key[s], (size_t)h->maxhlf);
+        rc |= dalloc(&h->key[s], (size_t)h->maxhlf); rc |= dalloc(&h->perm[s], (size_t)h->maxhlf);
+        h->lazy[s] = 0; h->nphys[s] = 0;
     }
     rc |= dalloc(&h->slot, (size_t)2 * h->maxhlf);
     size_t nb = lot + TGPU_NBIN_EXTRA;
@@ -151,7 +153,7 @@ extern "C" int tgpu_finalize(tgpu_ctx *h)
     for (int a = 0; a < 3; a++) { cudaFree(h->ftmp[a]); cudaFree(h->shadow[a]); }
     if (h->prim8) cudaFree(h->prim8);
     cudaFree(h->halo);
-    for (int s = 0; s < 2; s++) { free_species(h->sp[s]); free_species(h->alt[s]); cudaFree(h->key[s]); }
+    for (int s = 0; s < 2; s++) { free_species(h->sp[s]); free_species(h->alt[s]); cudaFree(h->key[s]); cudaFree(h->perm[s]); }
     cudaFree(h->slot); cudaFree(h->bincount); cudaFree(h->binoff); cudaFree(h->cub_tmp); cudaFree(h->d_small);
     cudaFreeHost(h->h_small); cudaFree(h->stage);
     if (h->sendbuf) cudaFree(h->sendbuf);
@@ -274,6 +276,7 @@ extern "C" int tgpu_move_particles(tgpu_ctx *h)
         h->fused_pending = 1;
         return 0;
     }
+    { int rc = prt_materialize(h); if (rc) return rc; }
     return prt_move_generic(h);
 }
 extern "C" int tgpu_deposit_particles(tgpu_ctx *h)
@@ -283,8 +286,7 @@ extern "C" int tgpu_deposit_particles(tgpu_ctx *h)
     {
         PhaseTimer t(h, TGPU_PH_DEPOSIT);
         if (h->fused_pending) { rc = fld_add_shadow(h); h->fused_pending = 0; }     // currents were deposited by the fused mover
-        else if (h->opt_fused && cellrun_supported(h)) rc = cellrun_deposit(h);
-        else rc = prt_deposit_generic(h);
+        else { rc = prt_materialize(h); if (!rc) rc = (h->opt_fused && cellrun_supported(h)) ? cellrun_deposit(h) : prt_deposit_generic(h); }
         if (rc) return rc;
     }
     PhaseTimer t2(h, TGPU_PH_SORT);
@@ -366,6 +368,7 @@ extern "C" int tgpu_set_option(tgpu_ctx *h, const char *name, int value)
     if (!strcmp(name, "fused")) { h->opt_fused = value; return 0; }
     if (!strcmp(name, "timing")) { h->timing = value; return 0; }
     if (!strcmp(name, "overlap")) { h->opt_overlap = value; return 0; }
+    if (!strcmp(name, "lazy_sort")) { h->opt_lazy = value; return 0; }
     tgpu_set_error(std::string("unknown option ") + name);
     return TGPU_EINVAL;
 }

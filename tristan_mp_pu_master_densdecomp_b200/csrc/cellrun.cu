@@ -32,7 +32,9 @@
 #define CR_CHUNK 128          // particles per half-warp
 
 struct CRArgs {
-    Species s;
+    Species s;                // source records
+    Species d;                // FUSED: destination records (logical order); may alias s when perm == nullptr
+    const int32_t *perm;      // FUSED: logical position t reads physical record perm[t] (lazy sort), or nullptr
     long long n;
     const float4 *prim8;
     float *cx, *cy, *cz;
@@ -190,8 +192,18 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
         int ci = -1, crow = -1;                              // deposit base cell of this lane's particle
         // ------------------------------------------------------------------ phase 1: lane = particle
         if (t < A.n) {
-            float x = A.s.x[t], y = A.s.y[t], z = A.s.z[t], u = A.s.u[t], v = A.s.v[t], w = A.s.w[t];
-            const float q = A.s.ch[t] * A.qs;
+            const long long p = (FUSED && A.perm) ? (long long)A.perm[t] : t;
+            float x = A.s.x[p], y = A.s.y[p], z = A.s.z[p], u = A.s.u[p], v = A.s.v[p], w = A.s.w[p];
+            const float ch = A.s.ch[p];
+            if (FUSED && A.perm) {
+                // lazily sorted input: the record still carries last lap's unwrapped position; apply the periodic wrap /
+                // frame shift its sort key was computed with (deposit_particles loop B), and carry the passive fields along
+                if (x < A.G.minx) x += A.G.shiftx_lo; else if (x > A.G.maxx) x -= A.G.shiftx_hi;
+                if (y < A.G.miny) y += A.G.shifty_lo; else if (y > A.G.maxy) y -= A.G.shifty_hi;
+                if (z < A.G.minz) z += A.G.shiftz_lo; else if (z > A.G.maxz) z -= A.G.shiftz_hi;
+                A.d.ch[t] = ch; A.d.ind[t] = A.s.ind[p]; A.d.tag[t] = A.s.tag[p];
+            }
+            const float q = ch * A.qs;
             float S1[4], S2[4];
             if (FUSED) {
                 const float half_ = 0.5f;
@@ -232,7 +244,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
                     e0 = e0 + G.ext[0] * 0.5f * qm; e1 = e1 + G.ext[1] * 0.5f * qm; e2 = e2 + G.ext[2] * 0.5f * qm;
                 }
                 push_particle(G.c, G.pusher, e0, e1, e2, b0, b1, b2, x, y, z, u, v, w);
-                A.s.x[t] = x; A.s.y[t] = y; A.s.z[t] = z; A.s.u[t] = u; A.s.v[t] = v; A.s.w[t] = w;
+                A.d.x[t] = x; A.d.y[t] = y; A.d.z[t] = z; A.d.u[t] = u; A.d.v[t] = v; A.d.w[t] = w;
                 // The deposit's "old" shape is the gather's shape at the true pre-push position (the reference
                 // recomputes it as x - u/gamma*c, particles_movedeposit.F90:1384-1388, equal to round-off).
                 crow = (jp - 1) + my * (kp - 1); ci = ip;
@@ -322,16 +334,24 @@ static int launch(tgpu_ctx *h, float *cx, float *cy, float *cz)
         Species &S = h->sp[s];
         if (S.n == 0) continue;
         CRArgs A;
-        A.s = S; A.n = S.n; A.prim8 = h->prim8; A.cx = cx; A.cy = cy; A.cz = cz; A.G = h->G;
+        A.s = S; A.d = S; A.perm = nullptr;
+        A.n = S.n; A.prim8 = h->prim8; A.cx = cx; A.cy = cy; A.cz = cz; A.G = h->G;
         A.qm = s ? h->P.qme : h->P.qmi; A.qs = s ? h->P.qe : h->P.qi;
         const size_t nb = (size_t)h->G.lot + TGPU_NBIN_EXTRA;
         A.key = h->key[s]; A.slot = h->slot + (size_t)s * h->maxhlf; A.bincount = h->bincount + (size_t)s * nb;
         if (FUSED) CK(cudaMemsetAsync(A.bincount, 0, nb * sizeof(int32_t), h->stream));
+        if (FUSED && h->lazy[s]) { A.perm = h->perm[s]; A.d = h->alt[s]; }     // gather through the pending permutation
         long long warps = (S.n + 2 * CR_CHUNK - 1) / (2 * CR_CHUNK);
         int blocks = (int)((warps + CR_WARPS - 1) / CR_WARPS);
         if (h->P.order == 2) k_cellrun<2, FUSED><<<blocks, CR_WARPS * 32, 0, h->stream>>>(A);
         else k_cellrun<1, FUSED><<<blocks, CR_WARPS * 32, 0, h->stream>>>(A);
         CKK(h);
+        if (FUSED && h->lazy[s]) {
+            // the pushed records now sit, in sorted order and wrapped, in the other buffer
+            int n = S.n;
+            Species tmp = h->sp[s]; h->sp[s] = h->alt[s]; h->alt[s] = tmp;
+            h->sp[s].n = n; h->lazy[s] = 0; h->nphys[s] = n;
+        }
     }
     return 0;
 }
@@ -349,5 +369,6 @@ int cellrun_move_deposit(tgpu_ctx *h)
 // tgpu_deposit_particles fast path when the particles were moved elsewhere (mirror mode, tests)
 int cellrun_deposit(tgpu_ctx *h)
 {
+    { int rc = prt_materialize(h); if (rc) return rc; }
     return launch<false>(h, h->f[6], h->f[7], h->f[8]);
 }

@@ -32,26 +32,40 @@ __global__ void __launch_bounds__(256) k_soa2aos(tgpu_particle *__restrict__ a, 
     a[t] = p;
 }
 
+__global__ void __launch_bounds__(256) k_iota(int32_t *__restrict__ a, int first, int n)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) a[t] = first + t;
+}
+
 int prt_append(tgpu_ctx *h, int s, const tgpu_particle *p, int n, bool host)
 {
     if (n <= 0) return 0;
     h->keys_valid = 0;
     Species &S = h->sp[s];
-    if (S.n + n > h->maxhlf) { tgpu_set_error("particle capacity (maxhlf) exceeded"); return TGPU_EOVERFLOW; }
+    if (h->lazy[s] && h->nphys[s] + n > h->maxhlf) { int rc = prt_materialize(h); if (rc) return rc; }
+    const int phys0 = h->lazy[s] ? h->nphys[s] : S.n;          // where the new records physically go
+    if (phys0 + n > h->maxhlf) { tgpu_set_error("particle capacity (maxhlf) exceeded"); return TGPU_EOVERFLOW; }
     int done = 0;
     while (done < n) {
         int chunk = n - done; if ((size_t)chunk > h->stage_particles) chunk = (int)h->stage_particles;
         const tgpu_particle *src = p + done;
         if (host) { CK(cudaMemcpyAsync(h->stage, src, (size_t)chunk * sizeof(tgpu_particle), cudaMemcpyHostToDevice, h->stream)); src = h->stage; }
-        k_aos2soa<<<cdiv(chunk, 256), 256, 0, h->stream>>>(src, S, S.n, chunk); CKK(h);
-        S.n += chunk; done += chunk;
+        k_aos2soa<<<cdiv(chunk, 256), 256, 0, h->stream>>>(src, S, phys0 + done, chunk); CKK(h);
+        done += chunk;
     }
+    if (h->lazy[s]) {
+        k_iota<<<cdiv(n, 256), 256, 0, h->stream>>>(h->perm[s] + S.n, phys0, n); CKK(h);
+        h->nphys[s] += n;
+    }
+    S.n += n;
     return 0;
 }
 int prt_h2d(tgpu_ctx *h, const tgpu_particle *p, int ions, int lecs)
 {
     if (ions < 0 || lecs < 0 || ions > h->maxhlf || lecs > h->maxhlf) { tgpu_set_error("bad particle counts"); return TGPU_EINVAL; }
     h->sp[0].n = 0; h->sp[1].n = 0; h->keys_valid = 0;
+    h->lazy[0] = h->lazy[1] = 0; h->nphys[0] = h->nphys[1] = 0;
     int rc = prt_append(h, 0, p, ions, true); if (rc) return rc;
     rc = prt_append(h, 1, p + h->maxhlf, lecs, true); if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
@@ -59,6 +73,7 @@ int prt_h2d(tgpu_ctx *h, const tgpu_particle *p, int ions, int lecs)
 }
 int prt_d2h(tgpu_ctx *h, tgpu_particle *p, int *ions, int *lecs)
 {
+    { int rc = prt_materialize(h); if (rc) return rc; }
     for (int s = 0; s < 2; s++) {
         Species &S = h->sp[s];
         tgpu_particle *dst = p + (s ? h->maxhlf : 0);
@@ -459,13 +474,59 @@ __global__ void __launch_bounds__(256) k_scatter(Species a, Species b, int n, co
     b.ch[d] = a.ch[t]; b.ind[d] = a.ind[t]; b.tag[d] = a.tag[t];
 }
 
+// lazy sort: instead of moving the records, remember where each sorted position's record is
+__global__ void __launch_bounds__(256) k_build_perm(int32_t *__restrict__ perm, int n, const uint32_t *__restrict__ key,
+                                                    const int32_t *__restrict__ slot, const int32_t *__restrict__ binoff)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) perm[binoff[key[t]] + slot[t]] = t;
+}
+// apply the permutation (and the wrap that the key was computed with)
+__global__ void __launch_bounds__(256) k_gather_perm(Species a, Species b, int n, const int32_t *__restrict__ perm, DevGeom G)
+{
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    int t = perm[d];
+    float x = a.x[t], y = a.y[t], z = a.z[t];
+    int code; bool discard; classify(G, x, y, z, code, discard);
+    b.x[d] = x; b.y[d] = y; b.z[d] = z; b.u[d] = a.u[t]; b.v[d] = a.v[t]; b.w[d] = a.w[t];
+    b.ch[d] = a.ch[t]; b.ind[d] = a.ind[t]; b.tag[d] = a.tag[t];
+}
+__global__ void __launch_bounds__(256) k_soa2aos_perm(tgpu_particle *__restrict__ a, Species s, const int32_t *__restrict__ perm, int off, int n, DevGeom G)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int d = perm[off + t];
+    tgpu_particle p;
+    p.x = s.x[d]; p.y = s.y[d]; p.z = s.z[d];
+    int code; bool discard; classify(G, p.x, p.y, p.z, code, discard);     // into the destination's frame
+    p.u = s.u[d]; p.v = s.v[d]; p.w = s.w[d]; p.ch = s.ch[d];
+    p.ind = s.ind[d]; int tg = s.tag[d]; p.proc = tg & 0xFFFFFF; p.splitlev = (tg >> 24) & 0xFF;
+    a[t] = p;
+}
+
+int prt_materialize(tgpu_ctx *h)
+{
+    for (int s = 0; s < 2; s++) {
+        if (!h->lazy[s]) continue;
+        Species &S = h->sp[s];
+        if (S.n) { k_gather_perm<<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->perm[s], h->G); CKK(h); }
+        int n = S.n;
+        Species tmp = h->sp[s]; h->sp[s] = h->alt[s]; h->alt[s] = tmp;
+        h->sp[s].n = n; h->lazy[s] = 0; h->nphys[s] = n;
+    }
+    return 0;
+}
+
 // After prt_sort: sp[s].n = stayers; h_small[s*16 + c] / [s*16 + 8.. ] hold leaver ranges (offset table of the 11 tail bins).
 int prt_sort(tgpu_ctx *h, bool)
 {
     const int nb = (int)h->G.lot + TGPU_NBIN_EXTRA;
-    const bool wrap_in_scatter = h->keys_valid != 0;
+    const bool have_keys = h->keys_valid != 0;      // written by the fused mover for the records as they now sit in sp[]
     h->keys_valid = 0;
-    for (int s = 0; s < 2 && !wrap_in_scatter; s++) {
+    if (!have_keys) { int rc = prt_materialize(h); if (rc) return rc; }
+    const bool lazy = have_keys && h->opt_lazy;
+    for (int s = 0; s < 2 && !have_keys; s++) {
         Species &S = h->sp[s];
         int32_t *cnt = h->bincount + (size_t)s * nb;
         CK(cudaMemsetAsync(cnt, 0, (size_t)nb * sizeof(int32_t), h->stream));
@@ -480,22 +541,20 @@ int prt_sort(tgpu_ctx *h, bool)
     }
     for (int s = 0; s < 2; s++) {
         Species &S = h->sp[s];
+        const int32_t *slot = h->slot + (size_t)s * h->maxhlf, *off = h->binoff + (size_t)s * (nb + 1);
         if (S.n) {
-            if (wrap_in_scatter)
-                k_scatter<true><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->key[s], h->slot + (size_t)s * h->maxhlf,
-                                                                      h->binoff + (size_t)s * (nb + 1), h->G);
-            else
-                k_scatter<false><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->key[s], h->slot + (size_t)s * h->maxhlf,
-                                                                       h->binoff + (size_t)s * (nb + 1), h->G);
+            if (lazy) k_build_perm<<<cdiv(S.n, 256), 256, 0, h->stream>>>(h->perm[s], S.n, h->key[s], slot, off);
+            else if (have_keys) k_scatter<true><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->key[s], slot, off, h->G);
+            else k_scatter<false><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->key[s], slot, off, h->G);
             CKK(h);
         }
-        CK(cudaMemcpyAsync(h->h_small + s * 16, h->binoff + (size_t)s * (nb + 1) + (size_t)h->G.lot, 11 * sizeof(int32_t),
-                           cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_small + s * 16, off + (size_t)h->G.lot, 11 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
     for (int s = 0; s < 2; s++) {
         int n_old = h->sp[s].n;
-        Species tmp = h->sp[s]; h->sp[s] = h->alt[s]; h->alt[s] = tmp;
+        if (lazy) { h->lazy[s] = n_old > 0; h->nphys[s] = n_old; }
+        else { Species tmp = h->sp[s]; h->sp[s] = h->alt[s]; h->alt[s] = tmp; h->lazy[s] = 0; h->nphys[s] = 0; }
         // h_small[s*16 + c] = offset of tail bin c (c = 0..9), [10] = total
         h->sp[s].n = n_old ? h->h_small[s * 16 + 0] : 0;
         if (!n_old) for (int c = 0; c < 11; c++) h->h_small[s * 16 + c] = 0;
@@ -525,7 +584,11 @@ int prt_exchange(tgpu_ctx *h)
         if (nout[0][c] + nout[1][c] > B) { tgpu_set_error("migration outbox overflow (buffsize)"); return TGPU_EOVERFLOW; }
         int o = 0;
         for (int s = 0; s < 2; s++) {
-            if (nout[s][c]) { k_soa2aos<<<cdiv(nout[s][c], 256), 256, 0, h->stream>>>(h->sendbuf + (size_t)c * B + o, h->sp[s], off[s][c], nout[s][c]); CKK(h); }
+            if (nout[s][c]) {
+                if (h->lazy[s]) k_soa2aos_perm<<<cdiv(nout[s][c], 256), 256, 0, h->stream>>>(h->sendbuf + (size_t)c * B + o, h->sp[s], h->perm[s], off[s][c], nout[s][c], h->G);
+                else k_soa2aos<<<cdiv(nout[s][c], 256), 256, 0, h->stream>>>(h->sendbuf + (size_t)c * B + o, h->sp[s], off[s][c], nout[s][c]);
+                CKK(h);
+            }
             o += nout[s][c];
             hc[2 * c + s] = nout[s][c];
         }

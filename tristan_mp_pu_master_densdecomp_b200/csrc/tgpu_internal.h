@@ -44,6 +44,10 @@ struct tgpu_ctx {
     float *halo;             // pack/unpack scratch for exchanges and filter2 deep halos
     size_t halo_floats;
     Species sp[2], alt[2];
+    int32_t *perm[2];        // lazy sort: logical position d of species s lives at physical index perm[s][d] of sp[s]
+    int lazy[2];             // perm[s] is in force (positions in sp[s] are still unwrapped)
+    int nphys[2];            // physical records in sp[s] while lazy (stayers, leavers and appended arrivals)
+    int opt_lazy;
     uint32_t *key[2];        // cell key per particle (per species)
     int32_t *slot;           // rank of the particle inside its bin
     int32_t *bincount, *binoff;   // lot + TGPU_NBIN_EXTRA (+1)
@@ -98,6 +102,7 @@ int prt_append(tgpu_ctx *h, int s, const tgpu_particle *p, int n, bool host);
 int prt_move(tgpu_ctx *h);
 int prt_deposit(tgpu_ctx *h);
 int prt_sort(tgpu_ctx *h, bool classify_only);
+int prt_materialize(tgpu_ctx *h);     // apply a pending lazy permutation (+ wrap) physically
 int prt_exchange(tgpu_ctx *h);
 // comm.cu
 int comm_sendrecv(tgpu_ctx *h, const void *sbuf, size_t sbytes, int dst, void *rbuf, size_t rbytes, int src);
