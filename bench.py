@@ -319,7 +319,17 @@ def main():
         dt = float(tt[0])
         fbytes = 6 * P.mx * P.my * P.mz * 4
         pbytes = (ci + ce) * 40
+        # what the link itself gives (1 GiB pinned copies), to read the mirror number against
+        probe = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+        dev = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+        link = {}
+        for name, (dst, src) in (("h2d", (dev, probe)), ("d2h", (probe, dev))):
+            dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+            t1 = time.perf_counter(); dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+            link[name] = (1 << 30) / (time.perf_counter() - t1) / 1e9
+        del probe, dev
         e2e = {"value": total_particles / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": fbytes + pbytes,
+               "pcie_gbs_measured": link,
                "d2h_bytes_per_step": fbytes + pbytes, "mode": "mirror: fields+particles H2D, one lap, fields+particles D2H "
                "through tgpu_* with pinned host buffers", "ms_per_step": dt * 1e3}
     ctx.close()

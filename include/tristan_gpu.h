@@ -138,6 +138,16 @@ int tgpu_exchange_particles(tgpu_ctx *h);         /* particles.F90:1865-2116 + i
 int tgpu_inject_others(tgpu_ctx *h);              /* no-op: folded into tgpu_exchange_particles; kept for call-list parity */
 int tgpu_reorder_particles(tgpu_ctx *h);          /* particles.F90:394-497 (unconditional here; the lap%10 test stays in the caller) */
 
+/* ---- user hooks of the shock problem (user/user_shock.F90), SURVEY.md 8(f) row 1 ---------------------------- */
+/* field_bc_user, user_shock.F90:342-373: conductor behind the left wall (ey = ez = 0 for x < leftwall-10) and upstream
+ * fields clamped on the last three x cells.  beta is the upstream drift v/c (particles.F90:222). */
+int tgpu_field_bc_user_shock(tgpu_ctx *h, float leftwall, float binit, float btheta, float bphi, float beta);
+/* particle_bc_user, user_shock.F90:377-457: specular wall at global x = leftwall with the two zigzag deposits */
+int tgpu_particle_bc_user_wall(tgpu_ctx *h, float leftwall);
+/* make tgpu_step call the two hooks at mainloop's hook points (tristanmainloop.F90:146,160,166,177,243);
+ * params = {leftwall, binit, btheta, bphi, beta}; kind 0 = none, 1 = shock */
+int tgpu_set_user_hooks(tgpu_ctx *h, int kind, const float params[5]);
+
 /* ---- whole lap, resident mode: tristanmainloop.F90:107-344 with Appendix-B de-duplication ---- */
 int tgpu_step(tgpu_ctx *h, int nlaps);
 

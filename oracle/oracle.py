@@ -94,6 +94,9 @@ def lib():
         L.orc_init_weibel.argtypes = [vp, cf, cf, cf, cf, cf, cf, ci]
         L.orc_init_twostream.argtypes = [vp, cf, cf, cf, cf, cf, cf]
         L.orc_init_uniform.argtypes = [vp, cf, cf, cf, C.c_uint64]
+        L.orc_field_bc_shock.argtypes = [vp, cf, cf, cf, cf, cf]
+        L.orc_particle_bc_wall.argtypes = [vp, cf]
+        L.orc_step_shock.argtypes = [vp, cf, cf, cf, cf, cf]
         L.orc_charge_density.argtypes = [vp, C.POINTER(cf)]
         L.orc_sum_array.restype = C.c_double
         L.orc_sum_array.argtypes = [vp, ci]

@@ -94,6 +94,7 @@ orc_world *orc_world_create(const orc_params *Pin)
         r->x1in = (float)(nghost / 2 + 1);  r->x2in = (float)(w->mx0g - nghost / 2);
         r->y1in = (float)(nghost / 2 + 1);  r->y2in = (float)(w->my0g - nghost / 2);
         r->z1in = (float)(nghostz / 2 + 1); r->z2in = (float)(w->mz0g - nghostz / 2);
+        r->mx0g = w->mx0g;
         r->dseed = 123457.0 + rk;                           /* communications.F90:228-229 */
         r->totalpartnum = 0;
     }
@@ -1507,6 +1508,90 @@ void orc_init_uniform(orc_world *w, float ppc0, float beta_drift, float uth, uin
             }
         }
     }
+}
+
+/* ------------------------------------------------------------------------- */
+/* shock-problem user hooks: user/user_shock.F90                                */
+/* ------------------------------------------------------------------------- */
+static int iloc(const orc_rank *r, int iglob)
+{
+    /* fields.F90:384-390 */
+    int i = iglob - r->mxcum;
+    if (i < r->nghost / 2 + 1) i = 1;
+    if (i > r->mx - (r->nghost / 2)) i = r->mx;
+    return i;
+}
+static void fill_x(orc_rank *r, int which, int i1, int i2, float v)
+{
+    for (int k = 1; k <= r->mz; k++) for (int j = 1; j <= r->my; j++) for (int i = i1; i <= i2; i++) r->f[which][IDX(r, i, j, k)] = v;
+}
+/* field_bc_user, user_shock.F90:342-373: conductor behind the left wall, upstream fields clamped at the right edge */
+void orc_field_bc_shock(orc_rank *r, float leftwall, float binit, float btheta, float bphi, float beta)
+{
+    float xmin = 1.f, xmax = leftwall - 10.f;
+    int i1 = iloc(r, (int)xmin), i2 = iloc(r, (int)xmax);
+    if (i1 != i2) { fill_x(r, ORC_EY, i1, i2, 0.f); fill_x(r, ORC_EZ, i1, i2, 0.f); }
+    xmin = r->mx0g - 2.f; xmax = (float)r->mx0g;
+    i1 = iloc(r, (int)xmin); i2 = iloc(r, (int)xmax);
+    if (i1 != i2) {
+        float bxv = binit * cosf(btheta), byv = binit * sinf(btheta) * sinf(bphi), bzv = binit * sinf(btheta) * cosf(bphi);
+        fill_x(r, ORC_BX, i1, i2, bxv); fill_x(r, ORC_BY, i1, i2, byv); fill_x(r, ORC_BZ, i1, i2, bzv);
+        fill_x(r, ORC_EX, i1, i2, 0.f);
+        fill_x(r, ORC_EY, i1, i2, (-beta) * bzv);
+        fill_x(r, ORC_EZ, i1, i2, -(-beta) * byv);
+    }
+}
+/* particle_bc_user, user_shock.F90:377-457 with gammawall = 1, betawall = 0: specular wall at x = leftwall (global) */
+void orc_particle_bc_wall(orc_rank *r, float leftwall)
+{
+    const float c = r->P.c, gammawall = 1.f, betawall = 0.f, walloc = leftwall;
+    for (int iter = 1; iter <= 2; iter++) {
+        int i0 = iter == 1 ? 0 : r->maxhlf, cnt = iter == 1 ? r->ions : r->lecs;
+        float q0 = iter == 1 ? r->P.qi : r->P.qe;
+        for (int n = 0; n < cnt; n++) {
+            orc_particle *p = &r->p[i0 + n];
+            if (p->x + r->mxcum < walloc) {
+                float gamma = sqrtf(1 + (p->u * p->u + p->v * p->v + p->w * p->w));
+                float x0 = p->x - p->u / gamma * c, y0 = p->y, z0 = p->z;
+                float walloc0 = walloc - betawall * c - r->mxcum;
+                float tfrac = fabsf((x0 - walloc0) / (betawall * c - p->u / gamma * c));
+                float xcolis = x0 + p->u / gamma * c * tfrac, ycolis = y0, zcolis = z0;
+                float q = p->ch * q0;
+                zigzag(r, xcolis, ycolis, zcolis, x0, y0, z0, q);
+                p->u = gammawall * gammawall * gamma * (2 * betawall - p->u / gamma * (1 + betawall * betawall));
+                gamma = sqrtf(1 + (p->u * p->u + p->v * p->v + p->w * p->w));
+                float den = fabsf(p->x - x0); if (den < 1e-9f) den = 1e-9f;
+                tfrac = fabsf((p->x - xcolis) / den); if (tfrac > 1.f) tfrac = 1.f;
+                p->x = xcolis + p->u / gamma * c * tfrac;
+                p->y = ycolis; p->z = zcolis;
+                q = -q;
+                zigzag(r, xcolis, ycolis, zcolis, p->x - p->u / gamma * c, p->y - p->v / gamma * c, p->z - p->w / gamma * c, q);
+            }
+        }
+    }
+}
+/* one lap with the shock hooks at mainloop's hook points (tristanmainloop.F90:146-243); injector not included */
+void orc_step_shock(orc_world *w, float leftwall, float binit, float btheta, float bphi, float beta)
+{
+    int n = w->size0;
+#define FBC() for (int rk = 0; rk < n; rk++) orc_field_bc_shock(w->r[rk], leftwall, binit, btheta, bphi, beta)
+    w->lap++;
+    orc_step_phase(w, PH_BC_B1); orc_step_phase(w, PH_BC_E1); orc_step_phase(w, PH_BHALF); orc_step_phase(w, PH_BC_B1);
+    orc_step_phase(w, PH_MOVE); orc_step_phase(w, PH_BHALF); orc_step_phase(w, PH_BC_B1); orc_step_phase(w, PH_BC_B1);
+    FBC();                                   /* :146 */
+    orc_step_phase(w, PH_EFULL);
+    FBC();                                   /* :160 */
+    orc_step_phase(w, PH_BC_E1);
+    FBC();                                   /* :166 */
+    orc_step_phase(w, PH_RESET);
+    for (int rk = 0; rk < n; rk++) orc_particle_bc_wall(w->r[rk], leftwall);   /* :177 */
+    orc_step_phase(w, PH_BC_E1); orc_step_phase(w, PH_BC_B1);
+    orc_step_phase(w, PH_DEPOSIT); orc_step_phase(w, PH_EXCH_P); orc_step_phase(w, PH_EXCH_CUR); orc_step_phase(w, PH_FILTER);
+    orc_step_phase(w, PH_ADD_CUR);
+    FBC();                                   /* :243 */
+    orc_step_phase(w, PH_INJECT_OTHERS); orc_step_phase(w, PH_EXCH_P); orc_step_phase(w, PH_INJECT_OTHERS);
+    if (w->lap % 10 == 0) orc_step_phase(w, PH_REORDER);
+#undef FBC
 }
 
 /* ------------------------------------------------------------------------- */

@@ -1,7 +1,7 @@
 /*
  * pic_oracle.h -- CPU restatement of the TRISTAN-MP per-timestep PIC hot path.
  *
- * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (tristan_mp_b200/,
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (tristan_mp_pu_master_densdecomp_b200/,
  * libtristan_gpu.so) may include, link or call this.  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
  *
@@ -84,6 +84,7 @@ typedef struct orc_rank {
     int totalpartnum;
     const int *mxl, *myl, *mzl;   /* owned by the world */
     int lap;
+    int mx0g;                     /* global mx0 (ghosts included), for the user hooks */
 } orc_rank;
 
 typedef struct {
@@ -163,6 +164,11 @@ void orc_init_twostream(orc_world *w, float ppc0, float gamma0_in, float delgam,
                         float temperature_ratio);
 /* fast synthetic loader for benchmarks: uniform positions, drifting Maxwellian-ish momenta */
 void orc_init_uniform(orc_world *w, float ppc0, float beta_drift, float uth, uint64_t seed);
+
+/* --- shock-problem user hooks (user/user_shock.F90) --- */
+void orc_field_bc_shock(orc_rank *r, float leftwall, float binit, float btheta, float bphi, float beta);   /* :342-373 */
+void orc_particle_bc_wall(orc_rank *r, float leftwall);                                                     /* :377-457 */
+void orc_step_shock(orc_world *w, float leftwall, float binit, float btheta, float bphi, float beta);       /* lap with the hooks */
 
 /* diagnostics */
 void orc_charge_density(const orc_rank *r, float *rho /* lot floats */);

@@ -262,3 +262,41 @@ def test_plasma_oscillation_period():
     period = 2 * np.mean(np.diff(zc))
     expect = 2 * np.pi * 10.0 / 0.45
     assert abs(period / expect - 1) < 0.05, (period, expect)
+
+
+def test_reflecting_wall_is_specular():
+    """user_shock.F90:377-457 (gammawall = 1, betawall = 0): a particle that crossed the wall comes back with u_x flipped,
+    v, w and |u| unchanged, at the mirror position; nothing ends up behind the wall.  Away from the wall the lap still
+    conserves charge (the reference's wall ignores the y, z motion during the bounce, so cells next to it are excluded)."""
+    leftwall = 12.0
+    w = T.oracle_world(dim=2, order=1, n=(32, 16, 1), ppc=4.0, ntimes=0, seed_fields=0, periodic=(0, 1, 1), delgam=0.05, gamma0=0.4)
+    r = w.ranks[0]
+    g = r.nghost // 2
+    for p in (r.ions(), r.lecs()):
+        p["x"] = (leftwall + 0.05 + (p["x"] - (g + 1)) * (r.mx - g - 4 - leftwall) / (r.mx - 2 * g - 1)).astype(np.float32)
+    # single-particle check of the bounce itself
+    q = r.ions()[0].copy()
+    x_old = np.float32(leftwall + 0.1)
+    gam = np.sqrt(1 + 0.5 ** 2 + 0.1 ** 2 + 0.05 ** 2)
+    moved = x_old - np.float32(0.5 / gam * w.P.c)
+    r.ions()[0] = (moved, 8.3, 3.5, -0.5, 0.1, 0.05, 1.0, q["ind"], q["proc"], 1)
+    r.call("particle_bc_wall", leftwall)
+    b = r.ions()[0]
+    assert abs(b["u"] - 0.5) < 1e-6 and b["v"] == np.float32(0.1) and b["w"] == np.float32(0.05)
+    assert abs((b["x"] - leftwall) - (leftwall - moved)) < 2e-6            # mirror image
+    r.call("reset_currents")
+    n_hit = 0
+    for lap in range(4):
+        rho0 = r.charge_density()
+        ex, ey = r.arr(0), r.arr(1)
+        d0 = ((ex - np.roll(ex, 1, 2)) + (ey - np.roll(ey, 1, 1))).copy()
+        before = r.ions().copy()
+        w.call("step_shock", leftwall, 0.0, 0.0, 0.0, 0.0)
+        rho1 = r.charge_density()
+        d1 = (ex - np.roll(ex, 1, 2)) + (ey - np.roll(ey, 1, 1))
+        sl = (slice(0, 1), slice(g + 2, r.my - g - 3), slice(int(leftwall) + 2, r.mx - g - 6))
+        a, b2 = (d1 - d0)[sl], (rho1 - rho0)[sl]
+        assert np.abs(a - b2).max() < 1e-4 * np.abs(b2).max()
+        n_hit += int(((before["u"] < 0) & (before["x"] < leftwall + 0.15)).sum())
+        assert r.ions()["x"].min() >= leftwall - 1e-3 and r.lecs()["x"].min() >= leftwall - 1e-3
+    assert n_hit > 5

@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "tgpu_add_current", "tgpu_bc_b1", "tgpu_bc_e1", "tgpu_bc_b2", "tgpu_bc_e2", "tgpu_exchange_current",
     "tgpu_apply_filter", "tgpu_apply_filter1_opt", "tgpu_apply_filter2_opt", "tgpu_move_particles",
     "tgpu_deposit_particles", "tgpu_exchange_particles", "tgpu_inject_others", "tgpu_reorder_particles",
-    "tgpu_step", "tgpu_timers", "tgpu_launch_count", "tgpu_stream", "tgpu_set_option",
+    "tgpu_field_bc_user_shock", "tgpu_particle_bc_user_wall", "tgpu_set_user_hooks", "tgpu_step", "tgpu_timers", "tgpu_launch_count", "tgpu_stream", "tgpu_set_option",
 ]
 
 _lib = None
@@ -90,6 +90,9 @@ def load_library(path=None):
                  "tgpu_apply_filter1_opt", "tgpu_apply_filter2_opt", "tgpu_move_particles", "tgpu_deposit_particles",
                  "tgpu_exchange_particles", "tgpu_inject_others", "tgpu_reorder_particles"]:
         getattr(L, name).argtypes = [vp]
+    L.tgpu_field_bc_user_shock.argtypes = [vp] + [C.c_float] * 5
+    L.tgpu_particle_bc_user_wall.argtypes = [vp, C.c_float]
+    L.tgpu_set_user_hooks.argtypes = [vp, ci, C.POINTER(C.c_float)]
     L.tgpu_step.argtypes = [vp, ci]
     L.tgpu_timers.argtypes = [vp, C.POINTER(C.c_double), ci]
     L.tgpu_launch_count.restype = C.c_int64
@@ -273,6 +276,16 @@ class Context:
 
     def set_option(self, name, value):
         self._ck(self.lib.tgpu_set_option(self.h, name.encode(), int(value)), "set_option")
+
+    def field_bc_user_shock(self, leftwall, binit, btheta, bphi, beta):
+        self._ck(self.lib.tgpu_field_bc_user_shock(self.h, leftwall, binit, btheta, bphi, beta), "field_bc_user_shock")
+
+    def particle_bc_user_wall(self, leftwall):
+        self._ck(self.lib.tgpu_particle_bc_user_wall(self.h, leftwall), "particle_bc_user_wall")
+
+    def set_user_hooks(self, kind, params=None):
+        arr = (C.c_float * 5)(*(params or [0] * 5))
+        self._ck(self.lib.tgpu_set_user_hooks(self.h, kind, arr), "set_user_hooks")
 
     def step(self, nlaps=1):
         self._ck(self.lib.tgpu_step(self.h, nlaps), "step")

@@ -136,7 +136,7 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
         rc |= dalloc(&h->sendbuf, (size_t)TGPU_NDIR * p->buffsize); rc |= dalloc(&h->recvbuf, (size_t)TGPU_NDIR * p->buffsize);
     }
     if (rc) { tgpu_set_error("device allocation failed: " + g_err); return TGPU_ECUDA; }
-    h->need_prim = 1; h->fused_pending = 0; h->keys_valid = 0; h->in_step = 0; h->opt_fused = 1; h->nccl_comm = nullptr; h->lap = 0; h->launches = 0; h->timing = 0;
+    h->need_prim = 1; h->fused_pending = 0; h->keys_valid = 0; h->hook_kind = 0; h->in_step = 0; h->opt_fused = 1; h->nccl_comm = nullptr; h->lap = 0; h->launches = 0; h->timing = 0;
     for (int i = 0; i < TGPU_NPHASE; i++) h->phase_ms[i] = 0;
     CK(cudaDeviceSynchronize());
     *out = h;
@@ -296,6 +296,26 @@ extern "C" int tgpu_exchange_particles(tgpu_ctx *h) { ENTER(h); PhaseTimer t(h, 
 extern "C" int tgpu_inject_others(tgpu_ctx *h) { ENTER(h); return 0; }
 extern "C" int tgpu_reorder_particles(tgpu_ctx *h) { ENTER(h); PhaseTimer t(h, TGPU_PH_SORT); return prt_sort(h, false); }
 
+// ---- shock-problem user hooks -----------------------------------------------------------------------
+extern "C" int tgpu_field_bc_user_shock(tgpu_ctx *h, float leftwall, float binit, float btheta, float bphi, float beta)
+{
+    ENTER(h); PhaseTimer t(h, TGPU_PH_BC);
+    return fld_bc_shock(h, leftwall, binit, btheta, bphi, beta);
+}
+extern "C" int tgpu_particle_bc_user_wall(tgpu_ctx *h, float leftwall)
+{
+    ENTER(h); PhaseTimer t(h, TGPU_PH_DEPOSIT);
+    if (h->fused_pending) { tgpu_set_error("particle_bc_user needs the un-fused mover: set_option(\"fused\", 0) or tgpu_set_user_hooks"); return TGPU_ESTATE; }
+    return prt_wall(h, leftwall);
+}
+extern "C" int tgpu_set_user_hooks(tgpu_ctx *h, int kind, const float params[5])
+{
+    if (!h || kind < 0 || kind > 1 || (kind && !params)) return TGPU_EINVAL;
+    h->hook_kind = kind;
+    for (int i = 0; i < 5; i++) h->hook[i] = kind ? params[i] : 0.f;
+    return 0;
+}
+
 // ---- whole lap -------------------------------------------------------------------------------------
 // Call order of tristanmainloop.F90:107-344 with the redundant ghost refreshes of Appendix B removed: three
 // refreshes per lap instead of eight.  Results on the parity region are identical to the full call list.
@@ -309,7 +329,28 @@ extern "C" int tgpu_step(tgpu_ctx *h, int nlaps)
     // on stream_main.  Needs the fused mover (keys in hand) and is skipped while per-phase timing is on.
     const bool overlap = h->opt_overlap && h->opt_fused && cellrun_supported(h) && !h->timing;
     h->in_step = 1;
-    for (int l = 0; l < nlaps; l++) {
+    for (int l = 0; l < nlaps && h->hook_kind == 1; l++) {
+        // shock problem: the reflecting wall edits particles between the mover and the deposit, so the mover is not fused
+        // and the full call list with its hook points is replayed (tristanmainloop.F90:117-243)
+        const float *q = h->hook;
+        const int fused0 = h->opt_fused;
+        h->lap++;
+        DO(tgpu_bc_b1(h)); DO(tgpu_bc_e1(h)); DO(tgpu_advance_b_halfstep(h)); DO(tgpu_bc_b1(h));
+        h->opt_fused = 0; rc = tgpu_move_particles(h); h->opt_fused = fused0; if (rc) { h->in_step = 0; return rc; }
+        DO(tgpu_advance_b_halfstep(h)); DO(tgpu_bc_b1(h)); DO(tgpu_bc_b2(h));
+        DO(fld_bc_shock(h, q[0], q[1], q[2], q[3], q[4]));            // :146
+        DO(tgpu_advance_e_fullstep(h));
+        DO(fld_bc_shock(h, q[0], q[1], q[2], q[3], q[4]));            // :160
+        DO(tgpu_bc_e2(h));
+        DO(fld_bc_shock(h, q[0], q[1], q[2], q[3], q[4]));            // :166
+        DO(tgpu_reset_currents(h));
+        DO(prt_wall(h, q[0]));                                        // :177
+        DO(tgpu_bc_e1(h)); DO(tgpu_bc_b1(h));
+        DO(tgpu_deposit_particles(h)); DO(tgpu_exchange_particles(h)); DO(tgpu_exchange_current(h));
+        DO(tgpu_apply_filter(h)); DO(tgpu_add_current(h));
+        DO(fld_bc_shock(h, q[0], q[1], q[2], q[3], q[4]));            // :243
+    }
+    for (int l = 0; l < nlaps && h->hook_kind == 0; l++) {
         h->lap++;
         DO(tgpu_bc_e1(h));                 // :118 (E changed by add_current)
         DO(tgpu_advance_b_halfstep(h));    // :119

@@ -571,3 +571,48 @@ int fld_filter2(tgpu_ctx *h)
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// field_bc_user of the shock problem: user/user_shock.F90:342-373
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fill_x(float *__restrict__ a, int mx, int my, int mz, int i1, int i2, float v)
+{
+    size_t n = (size_t)(i2 - i1 + 1) * my * mz;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    int w = i2 - i1 + 1;
+    int i = i1 + (int)(idx % w); size_t r = idx / w;
+    int j = 1 + (int)(r % my), k = 1 + (int)(r / my);
+    a[LIDX(i, j, k)] = v;
+}
+static int iloc_x(const tgpu_ctx *h, int iglob)
+{
+    int i = iglob - h->P.mxcum;                        // fields.F90:384-390
+    if (i < h->P.nghost / 2 + 1) i = 1;
+    if (i > h->P.mx - h->P.nghost / 2) i = h->P.mx;
+    return i;
+}
+static int fill_x(tgpu_ctx *h, int which, int i1, int i2, float v)
+{
+    size_t n = (size_t)(i2 - i1 + 1) * h->P.my * h->P.mz;
+    k_fill_x<<<cdiv(n, 256), 256, 0, h->stream>>>(h->f[which], h->P.mx, h->P.my, h->P.mz, i1, i2, v);
+    CKK(h);
+    return 0;
+}
+int fld_bc_shock(tgpu_ctx *h, float leftwall, float binit, float btheta, float bphi, float beta)
+{
+    // global mx0 (ghosts included) = x2in + nghost/2 (particles.F90:339-344)
+    const int mx0g = (int)h->P.x2in + h->P.nghost / 2;
+    float xmin = 1.f, xmax = leftwall - 10.f;
+    int i1 = iloc_x(h, (int)xmin), i2 = iloc_x(h, (int)xmax), rc = 0;
+    if (i1 != i2) { rc |= fill_x(h, 1, i1, i2, 0.f); rc |= fill_x(h, 2, i1, i2, 0.f); }
+    xmin = mx0g - 2.f; xmax = (float)mx0g;
+    i1 = iloc_x(h, (int)xmin); i2 = iloc_x(h, (int)xmax);
+    if (i1 != i2) {
+        const float bxv = binit * cosf(btheta), byv = binit * sinf(btheta) * sinf(bphi), bzv = binit * sinf(btheta) * cosf(bphi);
+        rc |= fill_x(h, 3, i1, i2, bxv); rc |= fill_x(h, 4, i1, i2, byv); rc |= fill_x(h, 5, i1, i2, bzv);
+        rc |= fill_x(h, 0, i1, i2, 0.f); rc |= fill_x(h, 1, i1, i2, (-beta) * bzv); rc |= fill_x(h, 2, i1, i2, -(-beta) * byv);
+    }
+    h->need_prim = 1;
+    return rc ? TGPU_ECUDA : 0;
+}

@@ -625,3 +625,92 @@ int prt_exchange(tgpu_ctx *h)
     for (int s = 0; s < 2; s++) for (int c = 0; c < 11; c++) h->h_small[s * 16 + c] = h->sp[s].n;   // outboxes consumed
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// particle_bc_user of the shock problem: user/user_shock.F90:377-457 (gammawall = 1, betawall = 0).
+// Runs between the mover and deposit_particles; deposits two zigzag segments (particles.F90:550-669) per reflected
+// particle: the path up to the wall, and minus the piece behind the wall that deposit_particles will add.
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+__device__ __forceinline__ void zigzag_dev(float *curx, float *cury, float *curz, const DevGeom &G, float x2, float y2,
+                                           float z2, float x1, float y1, float z1, float q)
+{
+    const long mx = G.mx, my = G.my;
+#define LI(i, j, k) ((size_t)((i)-1) + (size_t)mx * ((size_t)((j)-1) + (size_t)my * (size_t)((k)-1)))
+    int i1 = (int)x1, i2 = (int)x2, j1 = (int)y1, j2 = (int)y2, k1 = (int)z1, k2 = (int)z2;
+    float xr = fminf((float)(min(i1, i2) + 1), fmaxf((float)max(i1, i2), .5f * (x1 + x2)));
+    float yr = fminf((float)(min(j1, j2) + 1), fmaxf((float)max(j1, j2), .5f * (y1 + y2)));
+    float zr = fminf((float)(min(k1, k2) + 1), fmaxf((float)max(k1, k2), .5f * (z1 + z2)));
+    if (DIM == 2) { k1 = 1; k2 = 1; }
+    float Fx1 = -q * (xr - x1), Fy1 = -q * (yr - y1), Fz1 = -q * (zr - z1);
+    float Wx1 = .5f * (x1 + xr) - i1, Wy1 = .5f * (y1 + yr) - j1, Wz1 = DIM == 3 ? .5f * (z1 + zr) - k1 : 0.f;
+    float Wx2 = .5f * (x2 + xr) - i2, Wy2 = .5f * (y2 + yr) - j2, Wz2 = DIM == 3 ? .5f * (z2 + zr) - k2 : 0.f;
+    float Fx2 = -q * (x2 - xr), Fy2 = -q * (y2 - yr), Fz2 = -q * (z2 - zr);
+    atomicAdd(&curx[LI(i1, j1, k1)], Fx1 * (1.f - Wy1) * (1.f - Wz1));
+    atomicAdd(&curx[LI(i1, j1 + 1, k1)], Fx1 * Wy1 * (1.f - Wz1));
+    atomicAdd(&curx[LI(i2, j2, k2)], Fx2 * (1.f - Wy2) * (1.f - Wz2));
+    atomicAdd(&curx[LI(i2, j2 + 1, k2)], Fx2 * Wy2 * (1.f - Wz2));
+    atomicAdd(&cury[LI(i1, j1, k1)], Fy1 * (1.f - Wx1) * (1.f - Wz1));
+    atomicAdd(&cury[LI(i1 + 1, j1, k1)], Fy1 * Wx1 * (1.f - Wz1));
+    atomicAdd(&cury[LI(i2, j2, k2)], Fy2 * (1.f - Wx2) * (1.f - Wz2));
+    atomicAdd(&cury[LI(i2 + 1, j2, k2)], Fy2 * Wx2 * (1.f - Wz2));
+    if (DIM == 3) {
+        atomicAdd(&curx[LI(i1, j1, k1 + 1)], Fx1 * (1 - Wy1) * Wz1);
+        atomicAdd(&curx[LI(i1, j1 + 1, k1 + 1)], Fx1 * Wy1 * Wz1);
+        atomicAdd(&curx[LI(i2, j2, k2 + 1)], Fx2 * (1.f - Wy2) * Wz2);
+        atomicAdd(&curx[LI(i2, j2 + 1, k2 + 1)], Fx2 * Wy2 * Wz2);
+        atomicAdd(&cury[LI(i1, j1, k1 + 1)], Fy1 * (1.f - Wx1) * Wz1);
+        atomicAdd(&cury[LI(i1 + 1, j1, k1 + 1)], Fy1 * Wx1 * Wz1);
+        atomicAdd(&cury[LI(i2, j2, k2 + 1)], Fy2 * (1.f - Wx2) * Wz2);
+        atomicAdd(&cury[LI(i2 + 1, j2, k2 + 1)], Fy2 * Wx2 * Wz2);
+    }
+    atomicAdd(&curz[LI(i1, j1, k1)], Fz1 * (1.f - Wx1) * (1.f - Wy1));
+    atomicAdd(&curz[LI(i1 + 1, j1, k1)], Fz1 * Wx1 * (1.f - Wy1));
+    atomicAdd(&curz[LI(i1, j1 + 1, k1)], Fz1 * (1.f - Wx1) * Wy1);
+    atomicAdd(&curz[LI(i1 + 1, j1 + 1, k1)], Fz1 * Wx1 * Wy1);
+    atomicAdd(&curz[LI(i2, j2, k2)], Fz2 * (1.f - Wx2) * (1.f - Wy2));
+    atomicAdd(&curz[LI(i2 + 1, j2, k2)], Fz2 * Wx2 * (1.f - Wy2));
+    atomicAdd(&curz[LI(i2, j2 + 1, k2)], Fz2 * (1.f - Wx2) * Wy2);
+    atomicAdd(&curz[LI(i2 + 1, j2 + 1, k2)], Fz2 * Wx2 * Wy2);
+#undef LI
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_wall(Species s, int n, DevGeom G, float walloc, float q0, float *curx, float *cury, float *curz)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float x = s.x[t];
+    if (!(x + G.mxcum < walloc)) return;
+    const float c = G.c, gammawall = 1.f, betawall = 0.f;
+    float y = s.y[t], z = s.z[t], u = s.u[t], v = s.v[t], w = s.w[t];
+    float gamma = sqrtf(1 + (u * u + v * v + w * w));
+    float x0 = x - u / gamma * c, y0 = y, z0 = z;
+    float walloc0 = walloc - betawall * c - G.mxcum;
+    float tfrac = fabsf((x0 - walloc0) / (betawall * c - u / gamma * c));
+    float xcolis = x0 + u / gamma * c * tfrac, ycolis = y0, zcolis = z0;
+    float q = s.ch[t] * q0;
+    zigzag_dev<DIM>(curx, cury, curz, G, xcolis, ycolis, zcolis, x0, y0, z0, q);
+    u = gammawall * gammawall * gamma * (2 * betawall - u / gamma * (1 + betawall * betawall));
+    gamma = sqrtf(1 + (u * u + v * v + w * w));
+    tfrac = fminf(fabsf((x - xcolis) / fmaxf(fabsf(x - x0), 1e-9f)), 1.f);
+    x = xcolis + u / gamma * c * tfrac; y = ycolis; z = zcolis;
+    q = -q;
+    zigzag_dev<DIM>(curx, cury, curz, G, xcolis, ycolis, zcolis, x - u / gamma * c, y - v / gamma * c, z - w / gamma * c, q);
+    s.x[t] = x; s.y[t] = y; s.z[t] = z; s.u[t] = u;
+}
+
+int prt_wall(tgpu_ctx *h, float leftwall)
+{
+    int rc = prt_materialize(h); if (rc) return rc;
+    h->keys_valid = 0;
+    for (int s = 0; s < 2; s++) {
+        Species &S = h->sp[s];
+        if (!S.n) continue;
+        float q0 = s ? h->P.qe : h->P.qi;
+        if (h->P.dim == 3) k_wall<3><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, S.n, h->G, leftwall, q0, h->f[6], h->f[7], h->f[8]);
+        else k_wall<2><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, S.n, h->G, leftwall, q0, h->f[6], h->f[7], h->f[8]);
+        CKK(h);
+    }
+    return 0;
+}

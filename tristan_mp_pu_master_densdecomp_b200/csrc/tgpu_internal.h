@@ -60,6 +60,7 @@ struct tgpu_ctx {
     int fused_pending;       // currents of the last move already deposited into shadow
     float *shadow[3];
     int opt_fused;
+    int hook_kind; float hook[5];   // user hooks for tgpu_step (1 = shock: leftwall, binit, btheta, bphi, beta)
     int keys_valid;          // key[]/slot[]/bincount[] already hold this lap's sort keys (written by the fused mover)
     cudaStream_t stream;     // the stream every launch helper uses (normally == stream_main)
     cudaStream_t stream_main, stream_prt;   // tgpu_step overlaps the particle sort/migration (stream_prt) with the field phase
@@ -95,6 +96,7 @@ int fld_fold(tgpu_ctx *h);
 int fld_filter1(tgpu_ctx *h);
 int fld_filter2(tgpu_ctx *h);
 int fld_add_shadow(tgpu_ctx *h);
+int fld_bc_shock(tgpu_ctx *h, float leftwall, float binit, float btheta, float bphi, float beta);
 // particles.cu
 int prt_h2d(tgpu_ctx *h, const tgpu_particle *p, int ions, int lecs);
 int prt_d2h(tgpu_ctx *h, tgpu_particle *p, int *ions, int *lecs);
@@ -104,6 +106,7 @@ int prt_deposit(tgpu_ctx *h);
 int prt_sort(tgpu_ctx *h, bool classify_only);
 int prt_materialize(tgpu_ctx *h);     // apply a pending lazy permutation (+ wrap) physically
 int prt_exchange(tgpu_ctx *h);
+int prt_wall(tgpu_ctx *h, float leftwall);
 // comm.cu
 int comm_sendrecv(tgpu_ctx *h, const void *sbuf, size_t sbytes, int dst, void *rbuf, size_t rbytes, int src);
 int comm_group_begin(tgpu_ctx *h);
