@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fused", type=int, default=1)
+    ap.add_argument("--order", type=int, default=ORDER, help="shape order (headline = 2)")
+    ap.add_argument("--ppc", type=float, default=PPC)
     ap.add_argument("--cpu-cells", type=int, nargs=3, default=[128, 64, 64])
     return ap.parse_args()
 
@@ -200,7 +202,10 @@ def workload_config(args, n):
 
 
 def main():
+    global ORDER, PPC, B_PER_PARTICLE
     args = parse()
+    ORDER, PPC = args.order, args.ppc
+    B_PER_PARTICLE = 52.0 + 36.0 / PPC
     if args.impl == "reference":
         return run_reference(args)
     import __graft_entry__ as ge

@@ -16,6 +16,8 @@ int prt_deposit_generic(tgpu_ctx *h);
 int cellrun_supported(const tgpu_ctx *h);
 int cellrun_move_deposit(tgpu_ctx *h);      // fused gather + push + deposit into shadow[]
 int cellrun_deposit(tgpu_ctx *h);           // deposit only, into cur
+int cellrun3_supported(const tgpu_ctx *h);
+int cellrun3_deposit(tgpu_ctx *h);          // 3rd-order deposit only, into cur
 
 extern "C" int tgpu_device_count(void)
 {
@@ -286,7 +288,11 @@ extern "C" int tgpu_deposit_particles(tgpu_ctx *h)
     {
         PhaseTimer t(h, TGPU_PH_DEPOSIT);
         if (h->fused_pending) { rc = fld_add_shadow(h); h->fused_pending = 0; }     // currents were deposited by the fused mover
-        else { rc = prt_materialize(h); if (!rc) rc = (h->opt_fused && cellrun_supported(h)) ? cellrun_deposit(h) : prt_deposit_generic(h); }
+        else {
+            rc = prt_materialize(h);
+            if (!rc) rc = (h->opt_fused && cellrun_supported(h)) ? cellrun_deposit(h)
+                        : (h->opt_fused && cellrun3_supported(h)) ? cellrun3_deposit(h) : prt_deposit_generic(h);
+        }
         if (rc) return rc;
     }
     PhaseTimer t2(h, TGPU_PH_SORT);
