@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--fused", type=int, default=1)
     ap.add_argument("--order", type=int, default=ORDER, help="shape order (headline = 2)")
     ap.add_argument("--ppc", type=float, default=PPC)
-    ap.add_argument("--cpu-cells", type=int, nargs=3, default=[128, 64, 64])
+    ap.add_argument("--cpu-cells", type=int, nargs=3, default=[128, 32, 32], help="CPU sample: cells per host-thread slab")
     return ap.parse_args()
 
 
@@ -147,19 +147,17 @@ def measured_peak():
 # CPU leg: the oracle restatement (kind "port"), one slab per OpenMP thread, bounded sample of the same workload
 # ------------------------------------------------------------------------------------------------------------
 def cpu_leg(cells, steps, warmup):
+    """cells = (nx, ny_per_slab, nz_per_slab): one y/z slab per host thread (filter2 needs slabs at least ntimes thick)"""
     from oracle import oracle as O
     cores = os.cpu_count() or 1
     sy = sz = 1
-    c = cores
-    while c >= 2 and (cells[1] // (sy * 2) >= 16 or cells[2] // (sz * 2) >= 16):
-        if cells[2] // sz >= cells[1] // sy and cells[2] // (sz * 2) >= 16:
+    while sy * sz * 2 <= cores:
+        if sz <= sy:
             sz *= 2
-        elif cells[1] // (sy * 2) >= 16:
-            sy *= 2
         else:
-            break
-        c //= 2
+            sy *= 2
     os.environ["OMP_NUM_THREADS"] = str(sy * sz)
+    cells = (cells[0], cells[1] * sy, cells[2] * sz)
     P = O.make_params(dim=3, order=ORDER, mx0=cells[0], my0=cells[1], mz0=cells[2], sizey=sy, sizez=sz, ppc0=PPC,
                       ntimes=NTIMES, filter_kind=FILTER_KIND)
     w = O.World(P)
@@ -171,7 +169,7 @@ def cpu_leg(cells, steps, warmup):
     for _ in range(steps):
         w.step()
     dt = time.perf_counter() - t0
-    return npart * steps / dt, sy * sz, npart, dt / steps
+    return npart * steps / dt, sy * sz, npart, dt / steps, cells
 
 
 def run_reference(args):
@@ -179,8 +177,8 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 3))
-    val, cores, npart, sec = cpu_leg(args.cpu_cells, steps, min(args.warmup, 1))
-    sample = f"3D Weibel dd2 {PPC:g} ppc filter2 ntimes={NTIMES}, {args.cpu_cells[0]}x{args.cpu_cells[1]}x{args.cpu_cells[2]} cells " \
+    val, cores, npart, sec, cc = cpu_leg(args.cpu_cells, steps, min(args.warmup, 1))
+    sample = f"3D Weibel dd2 {PPC:g} ppc filter2 ntimes={NTIMES}, {cc[0]}x{cc[1]}x{cc[2]} cells " \
              f"({npart} particles), {steps} laps, one y/z slab per OpenMP thread"
     line = {"impl": "reference", "metric": "particle-steps/sec", "value": val, "unit": "particle-steps/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
@@ -344,9 +342,9 @@ def main():
         return
     cpu = None
     if not args.no_cpu and world == 1:
-        val, cores, npc, sec = cpu_leg(args.cpu_cells, 2, 1)
+        val, cores, npc, sec, cc = cpu_leg(args.cpu_cells, 2, 1)
         cpu = {"value": val, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_cells[0]}x{args.cpu_cells[1]}x{args.cpu_cells[2]} cells, {npc} particles, 2 laps, same "
+               "sample": f"{cc[0]}x{cc[1]}x{cc[2]} cells, {npc} particles, 2 laps, same "
                          f"physics (dd2, {PPC:g} ppc, filter2 ntimes={NTIMES}); oracle restatement, one slab per thread"}
     line = {"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": n, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "ns_per_particle_step": 1e9 / value * n,

@@ -604,10 +604,21 @@ void orc_apply_filter2(orc_world *w)
         for (int axis = 0; axis < naxes; axis++) filter2_axis(w, c, axis);
 }
 
+/* filter2 needs an ntimes-deep halo from the axis neighbour, i.e. ntimes <= that rank's interior extent on every
+   filtered axis.  The reference guards this (loosely) in tristanmainloop.F90:217-224 and otherwise runs filter1. */
+int orc_filter2_fits(const orc_world *w)
+{
+    int naxes = w->P.dim == 3 ? 3 : 2;
+    for (int rk = 0; rk < w->size0; rk++)
+        for (int a = 0; a < naxes; a++)
+            if (w->P.ntimes > axis_m(w->r[rk], a) - 2 * axis_g(w->r[rk], a) - 1) return 0;
+    return 1;
+}
+
 void orc_apply_filter(orc_world *w)
 {
     /* tristanmainloop.F90:213-229 */
-    if (w->P.filter_kind == 2) orc_apply_filter2(w); else orc_apply_filter1(w);
+    if (w->P.filter_kind == 2 && orc_filter2_fits(w)) orc_apply_filter2(w); else orc_apply_filter1(w);
 }
 
 /* ------------------------------------------------------------------------- */

@@ -263,9 +263,15 @@ extern "C" int tgpu_apply_filter2_opt(tgpu_ctx *h) { ENTER(h); PhaseTimer t(h, T
 extern "C" int tgpu_apply_filter(tgpu_ctx *h)
 {
     ENTER(h);
-    // tristanmainloop.F90:213-229: 2D builds always run filter1; filter2 only if compiled in and ntimes fits
-    if (h->P.filter_kind == 2) return tgpu_apply_filter2_opt(h);
-    return tgpu_apply_filter1_opt(h);
+    // tristanmainloop.F90:213-229: filter2 only if compiled in (filter_kind == 2) and its ntimes-deep halo fits inside the
+    // neighbour's interior on every filtered axis (all ranks must take the same branch: test the smallest slab), else filter1
+    bool f2 = h->P.filter_kind == 2;
+    const int naxes = h->P.dim == 3 ? 3 : 2;
+    for (int r = 0; r < h->size0 && f2; r++) {
+        const int m[3] = {h->mxl[r], h->myl[r], h->mzl[r]}, g[3] = {h->P.nghost / 2, h->P.nghost / 2, h->P.nghostz / 2};
+        for (int a = 0; a < naxes; a++) if (h->P.ntimes > m[a] - 2 * g[a] - 1) f2 = false;
+    }
+    return f2 ? tgpu_apply_filter2_opt(h) : tgpu_apply_filter1_opt(h);
 }
 
 // ---- particles -----------------------------------------------------------------------------------
