@@ -192,7 +192,7 @@ def run_reference(args):
 
 def workload_config(args, n):
     sy, sz = GRID[n]
-    return {"workload": f"3D Weibel, dd2 (2nd-order Esirkepov), {PPC:g} ppc, filter2 ntimes={NTIMES}, per-GPU slab "
+    return {"workload": f"3D Weibel, dd{ORDER} (order-{ORDER} Esirkepov), {PPC:g} ppc, filter2 ntimes={NTIMES}, per-GPU slab "
                         f"{args.cells[0]}x{args.cells[1]}x{args.cells[2]} cells (configs[2] share), global "
                         f"{args.cells[0]}x{args.cells[1] * sy}x{args.cells[2] * sz}",
             "decomposition": f"sizey={sy} sizez={sz}", "ppc": PPC, "order": ORDER, "c": 0.45,
