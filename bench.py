@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--cells", type=int, nargs=3, default=[512, 256, 128], help="per-GPU slab (interior cells)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-diag", action="store_true", help="diagnostic: time a second lap right after the mirror lap")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fused", type=int, default=1)
     ap.add_argument("--order", type=int, default=ORDER, help="shape order (headline = 2)")
@@ -308,12 +309,35 @@ def main():
         t0 = time.perf_counter()
         ni, ne = nhalf, nhalf
         ci, ce = ctx.counts()
+        # untimed warm-up: the host copy becomes what a mirror-mode host would hold (the state the device returned)
+        _, ci, ce = ctx.particles_d2h(outp)
+        ctx.fields_d2h(fields)
+        barrier()
+        t0 = time.perf_counter()
+        parts = {"h2d": 0.0, "lap": 0.0, "d2h": 0.0}
         for _ in range(args.e2e_steps):
+            ta = time.perf_counter()
             ctx.fields_h2d(*fields)
             ctx.particles_h2d(outp, ci, ce)
+            tb = time.perf_counter()
+            if args.e2e_diag:
+                ctx.set_option("timing", 1); ctx.timers(reset=True)
             ctx.step(1)
+            if args.e2e_diag:
+                print("diag phases of the mirror lap:", ctx.timers(reset=True), file=sys.stderr); ctx.set_option("timing", 0)
+            ctx.counts()
+            torch.cuda.synchronize()
+            tc = time.perf_counter()
+            if args.e2e_diag:
+                ctx.step(1); torch.cuda.synchronize()
+                parts["lap2"] = parts.get("lap2", 0.0) + time.perf_counter() - tc
+                ctx.set_option("timing", 1); ctx.timers(reset=True); ctx.step(1); parts["diag_phases"] = 0.0
+                print("diag phases of a lap after the mirror lap:", ctx.timers(reset=True), file=sys.stderr); ctx.set_option("timing", 0)
+                tc = time.perf_counter()
             _, ci, ce = ctx.particles_d2h(outp)
             ctx.fields_d2h(fields)
+            td = time.perf_counter()
+            parts["h2d"] += tb - ta; parts["lap"] += tc - tb; parts["d2h"] += td - tc
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / args.e2e_steps
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -334,7 +358,8 @@ def main():
         e2e = {"value": total_particles / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": fbytes + pbytes,
                "pcie_gbs_measured": link,
                "d2h_bytes_per_step": fbytes + pbytes, "mode": "mirror: fields+particles H2D, one lap, fields+particles D2H "
-               "through tgpu_* with pinned host buffers", "ms_per_step": dt * 1e3}
+               "through tgpu_* with pinned host buffers", "ms_per_step": dt * 1e3,
+               "ms_parts": {k: v / args.e2e_steps * 1e3 for k, v in parts.items()}}
     ctx.close()
     if rank != 0:
         if dist:

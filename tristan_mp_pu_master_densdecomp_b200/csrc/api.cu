@@ -82,6 +82,7 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
     CK(cudaEventCreateWithFlags(&h->ev_move, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_prt, cudaEventDisableTiming));
     h->opt_lazy = getenv("TGPU_LAZY") ? atoi(getenv("TGPU_LAZY")) : 1;
+    for (int b = 0; b < 2; b++) { CK(cudaEventCreateWithFlags(&h->ev_stage_full[b], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_stage_free[b], cudaEventDisableTiming)); }
     h->prt_pending = 0; h->opt_overlap = getenv("TGPU_OVERLAP") ? atoi(getenv("TGPU_OVERLAP")) : 1; h->nccl_main = h->nccl_prt = nullptr;
     h->maxhlf = p->maxptl / 2;
     DevGeom &G = h->G;
@@ -131,6 +132,7 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     CK(cudaMallocHost((void **)&h->h_small, 128 * sizeof(int32_t)));
     memset(h->h_small, 0, 128 * sizeof(int32_t));
     h->stage_particles = (size_t)h->maxhlf < ((size_t)1 << 24) ? (size_t)h->maxhlf : ((size_t)1 << 24);
+    if (h->stage_particles < 2) h->stage_particles = 2;     // two halves (double buffering)
     rc |= dalloc(&h->stage, h->stage_particles);
     h->sendbuf = h->recvbuf = nullptr;
     if (h->size0 > 1) {
@@ -161,6 +163,7 @@ extern "C" int tgpu_finalize(tgpu_ctx *h)
     if (h->sendbuf) cudaFree(h->sendbuf);
     if (h->recvbuf) cudaFree(h->recvbuf);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev_move); cudaEventDestroy(h->ev_prt);
+    for (int b = 0; b < 2; b++) { cudaEventDestroy(h->ev_stage_full[b]); cudaEventDestroy(h->ev_stage_free[b]); }
     cudaStreamDestroy(h->stream_main); cudaStreamDestroy(h->stream_prt);
     delete h;
     return 0;

@@ -46,13 +46,26 @@ int prt_append(tgpu_ctx *h, int s, const tgpu_particle *p, int n, bool host)
     if (h->lazy[s] && h->nphys[s] + n > h->maxhlf) { int rc = prt_materialize(h); if (rc) return rc; }
     const int phys0 = h->lazy[s] ? h->nphys[s] : S.n;          // where the new records physically go
     if (phys0 + n > h->maxhlf) { tgpu_set_error("particle capacity (maxhlf) exceeded"); return TGPU_EOVERFLOW; }
-    int done = 0;
-    while (done < n) {
-        int chunk = n - done; if ((size_t)chunk > h->stage_particles) chunk = (int)h->stage_particles;
-        const tgpu_particle *src = p + done;
-        if (host) { CK(cudaMemcpyAsync(h->stage, src, (size_t)chunk * sizeof(tgpu_particle), cudaMemcpyHostToDevice, h->stream)); src = h->stage; }
-        k_aos2soa<<<cdiv(chunk, 256), 256, 0, h->stream>>>(src, S, phys0 + done, chunk); CKK(h);
-        done += chunk;
+    if (!host) {
+        k_aos2soa<<<cdiv(n, 256), 256, 0, h->stream>>>(p, S, phys0, n); CKK(h);
+    } else {
+        // double-buffered: the PCIe copy of chunk i+1 (copy stream) overlaps the AoS->SoA transpose of chunk i
+        const size_t half = h->stage_particles / 2;
+        cudaStream_t ck = h->stream, cc = h->stream == h->stream_main ? h->stream_prt : h->stream_main;
+        CK(cudaEventRecord(h->ev_stage_free[0], ck)); CK(cudaEventRecord(h->ev_stage_free[1], ck));
+        int done = 0, i = 0;
+        while (done < n) {
+            const int b = i & 1;
+            int chunk = n - done; if ((size_t)chunk > half) chunk = (int)half;
+            tgpu_particle *stg = h->stage + (size_t)b * half;
+            CK(cudaStreamWaitEvent(cc, h->ev_stage_free[b], 0));
+            CK(cudaMemcpyAsync(stg, p + done, (size_t)chunk * sizeof(tgpu_particle), cudaMemcpyHostToDevice, cc));
+            CK(cudaEventRecord(h->ev_stage_full[b], cc));
+            CK(cudaStreamWaitEvent(ck, h->ev_stage_full[b], 0));
+            k_aos2soa<<<cdiv(chunk, 256), 256, 0, ck>>>(stg, S, phys0 + done, chunk); CKK(h);
+            CK(cudaEventRecord(h->ev_stage_free[b], ck));
+            done += chunk; i++;
+        }
     }
     if (h->lazy[s]) {
         k_iota<<<cdiv(n, 256), 256, 0, h->stream>>>(h->perm[s] + S.n, phys0, n); CKK(h);
@@ -74,17 +87,29 @@ int prt_h2d(tgpu_ctx *h, const tgpu_particle *p, int ions, int lecs)
 int prt_d2h(tgpu_ctx *h, tgpu_particle *p, int *ions, int *lecs)
 {
     { int rc = prt_materialize(h); if (rc) return rc; }
+    // double-buffered: the PCIe copy of chunk i (copy stream) overlaps the SoA->AoS transpose of chunk i+1
+    const size_t half = h->stage_particles / 2;
+    cudaStream_t ck = h->stream, cc = h->stream == h->stream_main ? h->stream_prt : h->stream_main;
+    CK(cudaEventRecord(h->ev_stage_free[0], cc)); CK(cudaEventRecord(h->ev_stage_free[1], cc));
+    int i = 0;
     for (int s = 0; s < 2; s++) {
         Species &S = h->sp[s];
         tgpu_particle *dst = p + (s ? h->maxhlf : 0);
         int done = 0;
         while (done < S.n) {
-            int chunk = S.n - done; if ((size_t)chunk > h->stage_particles) chunk = (int)h->stage_particles;
-            k_soa2aos<<<cdiv(chunk, 256), 256, 0, h->stream>>>(h->stage, S, done, chunk); CKK(h);
-            CK(cudaMemcpyAsync(dst + done, h->stage, (size_t)chunk * sizeof(tgpu_particle), cudaMemcpyDeviceToHost, h->stream));
-            done += chunk;
+            const int b = i & 1;
+            int chunk = S.n - done; if ((size_t)chunk > half) chunk = (int)half;
+            tgpu_particle *stg = h->stage + (size_t)b * half;
+            CK(cudaStreamWaitEvent(ck, h->ev_stage_free[b], 0));
+            k_soa2aos<<<cdiv(chunk, 256), 256, 0, ck>>>(stg, S, done, chunk); CKK(h);
+            CK(cudaEventRecord(h->ev_stage_full[b], ck));
+            CK(cudaStreamWaitEvent(cc, h->ev_stage_full[b], 0));
+            CK(cudaMemcpyAsync(dst + done, stg, (size_t)chunk * sizeof(tgpu_particle), cudaMemcpyDeviceToHost, cc));
+            CK(cudaEventRecord(h->ev_stage_free[b], cc));
+            done += chunk; i++;
         }
     }
+    CK(cudaStreamSynchronize(cc));
     CK(cudaStreamSynchronize(h->stream));
     *ions = h->sp[0].n; *lecs = h->sp[1].n;
     return 0;

@@ -65,6 +65,7 @@ struct tgpu_ctx {
     cudaStream_t stream;     // the stream every launch helper uses (normally == stream_main)
     cudaStream_t stream_main, stream_prt;   // tgpu_step overlaps the particle sort/migration (stream_prt) with the field phase
     cudaEvent_t ev0, ev1, ev_move, ev_prt;
+    cudaEvent_t ev_stage_full[2], ev_stage_free[2];   // double-buffered AoS staging for h2d / d2h
     int in_step;
     int prt_pending;         // ev_prt must be waited for before the particle arrays are touched on stream_main
     int opt_overlap;
