@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtristan_gpu.so")
+# TGPU_LIB selects an A/B build of the same library (csrc/Makefile: BUILD=... OUT=... CRFLAGS=...)
+LIB_PATH = os.environ.get("TGPU_LIB") or os.path.join(_HERE, "libtristan_gpu.so")
 
 PARTICLE_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4"), ("u", "f4"), ("v", "f4"), ("w", "f4"),
                            ("ch", "f4"), ("ind", "i4"), ("proc", "i4"), ("splitlev", "i4")])

@@ -108,7 +108,8 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     size_t lot = (size_t)G.lot;
     int rc = 0;
     for (int a = 0; a < 9; a++) rc |= dalloc(&h->f[a], lot);
-    for (int a = 0; a < 3; a++) { rc |= dalloc(&h->ftmp[a], lot); rc |= dalloc(&h->shadow[a], lot); }
+    h->nty = (p->my + 3) / 4; h->ntz = (p->mz + 3) / 4; h->shadow_floats = (size_t)h->nty * h->ntz * p->mx * 16;
+    for (int a = 0; a < 3; a++) { rc |= dalloc(&h->ftmp[a], lot); rc |= dalloc(&h->shadow[a], h->shadow_floats); }
     h->prim8 = nullptr;
     if (p->dim == 3 && p->order > 0) rc |= dalloc(&h->prim8, 2 * lot);
     size_t plane = (size_t)p->mx * p->my;

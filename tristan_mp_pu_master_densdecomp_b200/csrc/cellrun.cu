@@ -29,7 +29,13 @@
 #ifndef CR_MINB
 #define CR_MINB 3
 #endif
+#ifndef CR_CHUNK
 #define CR_CHUNK 128          // particles per half-warp
+#endif
+#ifndef CR_FFMA2
+#define CR_FFMA2 1            // packed fp32 (FFMA2/FMUL2) in the gather and the deposit accumulation: measured 2-3 % faster
+#endif
+#define CR_SMEM_BYTES (sizeof(float) * CR_WARPS * 32 * CR_STRIDE + sizeof(uint32_t) * CR_WARPS * 2 * 9 * 32)
 
 struct CRArgs {
     Species s;                // source records
@@ -37,7 +43,8 @@ struct CRArgs {
     const int32_t *perm;      // FUSED: logical position t reads physical record perm[t] (lazy sort), or nullptr
     long long n;
     const float4 *prim8;
-    float *cx, *cy, *cz;
+    float *cx, *cy, *cz;     // FUSED: the tiled shadow arrays (see row_index), else curx, cury, curz in Fortran order
+    int nty;                  // FUSED: number of 4-row tiles along y
     DevGeom G;
     float qm, qs;
     uint32_t *key;            // FUSED: sort key of the pushed particle (prt_sort skips its classify pass)
@@ -57,19 +64,56 @@ __device__ __forceinline__ void red3(float *cx, float *cy, float *cz, size_t idx
     red_nz(cx + idx, vx); red_nz(cy + idx, vy); red_nz(cz + idx, vz);
 }
 
+// Asynchronous 4-byte global -> shared copy (LDGSTS): the particle record of the NEXT 16-particle step of a half-warp is
+// fetched into per-lane landing slots while the current step is being deposited, so neither the permutation lookup nor
+// the record loads sit on the critical path of phase 1 and no registers are held across phase 2.
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // sum over an NW^3 block of node-centred fields, in the reference's order: x innermost (sum()), then *Sy*Sz
 // (particles_movedeposit.F90:801-815)
 template <int NW>
-__device__ __forceinline__ void gather_nodes(const float4 *__restrict__ prim8, long long nbase, int mx, int my,
+__device__ __forceinline__ void gather_nodes(const float4 *__restrict__ prim8, int nbase, int mx, int my,
                                              const float *wxs, const float *wys, const float *wzs,
                                              float &e0, float &e1, float &e2, float &b0, float &b1, float &b2)
 {
+#if CR_FFMA2
+    // packed fp32 (FFMA2 / FMUL2): the six components sit in three aligned register pairs straight out of the two
+    // 128-bit loads; same operations and roundings as the scalar form below
+    float2 e01 = make_float2(e0, e1), e2b0 = make_float2(e2, b0), b12 = make_float2(b1, b2);
+#pragma unroll
+    for (int c3 = 0; c3 < NW; c3++) {
+#pragma unroll
+        for (int c2 = 0; c2 < NW; c2++) {
+            float2 s01 = make_float2(0.f, 0.f), s23 = s01, s45 = s01;
+            const float4 *row = prim8 + (unsigned)(2 * (nbase + mx * (c2 + my * c3)));
+#pragma unroll
+            for (int c1 = 0; c1 < NW; c1++) {
+                const float4 lo = __ldg(row + 2 * c1), hi = __ldg(row + 2 * c1 + 1);
+                const float2 w2 = make_float2(wxs[c1], wxs[c1]);
+                s01 = __ffma2_rn(make_float2(lo.x, lo.y), w2, s01);
+                s23 = __ffma2_rn(make_float2(lo.z, lo.w), w2, s23);
+                s45 = __ffma2_rn(make_float2(hi.x, hi.y), w2, s45);
+            }
+            const float2 wy2 = make_float2(wys[c2], wys[c2]), wz2 = make_float2(wzs[c3], wzs[c3]);
+            e01 = __ffma2_rn(__fmul2_rn(s01, wy2), wz2, e01);
+            e2b0 = __ffma2_rn(__fmul2_rn(s23, wy2), wz2, e2b0);
+            b12 = __ffma2_rn(__fmul2_rn(s45, wy2), wz2, b12);
+        }
+    }
+    e0 = e01.x; e1 = e01.y; e2 = e2b0.x; b0 = e2b0.y; b1 = b12.x; b2 = b12.y;
+#else
 #pragma unroll
     for (int c3 = 0; c3 < NW; c3++) {
 #pragma unroll
         for (int c2 = 0; c2 < NW; c2++) {
             float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
-            const float4 *row = prim8 + 2 * (nbase + (long long)mx * (c2 + (long long)my * c3));
+            // 32-bit node index: the fast path is only taken for grids below 2^30 nodes (cellrun_supported)
+            const float4 *row = prim8 + (unsigned)(2 * (nbase + mx * (c2 + my * c3)));
 #pragma unroll
             for (int c1 = 0; c1 < NW; c1++) {
                 float4 lo = __ldg(row + 2 * c1), hi = __ldg(row + 2 * c1 + 1);
@@ -81,6 +125,7 @@ __device__ __forceinline__ void gather_nodes(const float4 *__restrict__ prim8, l
             b0 = b0 + s3 * wy_ * wz_; b1 = b1 + s4 * wy_ * wz_; b2 = b2 + s5 * wy_ * wz_;
         }
     }
+#endif
 }
 
 // 3x3x3 path (particle exactly on a node under Q1, or quirks = fixed): kept out of line so that its register
@@ -141,26 +186,43 @@ __device__ __forceinline__ void stage_axis(float *st, const float S1[4], const f
 
 // flush the accumulators of the first `nplanes` x-planes of the window whose first cell is wi-1 (plane t lives in
 // physical register (wi - 1 + t) & 3) and clear them
+template <int PS>
 __device__ __forceinline__ void flush_planes(float *cx, float *cy, float *cz, size_t idx0, int wi, int nplanes,
                                              float (&ax)[4], float (&ay)[4], float (&az)[4])
 {
 #pragma unroll
     for (int m = 0; m < 4; m++) {
         const int t = (m - (wi - 1)) & 3;                    // plane held by register m
-        if (t < nplanes) { red3(cx, cy, cz, idx0 + t, ax[m], ay[m], az[m]); ax[m] = 0.f; ay[m] = 0.f; az[m] = 0.f; }
+        if (t < nplanes) { red3(cx, cy, cz, idx0 + (size_t)(t * PS), ax[m], ay[m], az[m]); ax[m] = 0.f; ay[m] = 0.f; az[m] = 0.f; }
     }
 }
 
-// the common case in sorted order: the window slides one cell along x, plane 0 (register (wi-1)&3) is complete
+// the common case in sorted order: the window slides one cell along x, plane 0 (register (wi-1)&3) is complete.
+// The ring register is uniform across the half-warp, so a 4-way switch costs one short divergent body instead of
+// select chains over all twelve accumulators.
 __device__ __forceinline__ void flush_one(float *cx, float *cy, float *cz, size_t idx0, int wi, float (&ax)[4], float (&ay)[4], float (&az)[4])
 {
-    const int m = (wi - 1) & 3;
-    const float vx = m == 0 ? ax[0] : m == 1 ? ax[1] : m == 2 ? ax[2] : ax[3];
-    const float vy = m == 0 ? ay[0] : m == 1 ? ay[1] : m == 2 ? ay[2] : ay[3];
-    const float vz = m == 0 ? az[0] : m == 1 ? az[1] : m == 2 ? az[2] : az[3];
-    red3(cx, cy, cz, idx0, vx, vy, vz);
-#pragma unroll
-    for (int q = 0; q < 4; q++) { ax[q] = m == q ? 0.f : ax[q]; ay[q] = m == q ? 0.f : ay[q]; az[q] = m == q ? 0.f : az[q]; }
+    float *px = cx + idx0, *py = cy + idx0, *pz = cz + idx0;
+    switch ((wi - 1) & 3) {
+    case 0: red_nz(px, ax[0]); red_nz(py, ay[0]); red_nz(pz, az[0]); ax[0] = 0.f; ay[0] = 0.f; az[0] = 0.f; break;
+    case 1: red_nz(px, ax[1]); red_nz(py, ay[1]); red_nz(pz, az[1]); ax[1] = 0.f; ay[1] = 0.f; az[1] = 0.f; break;
+    case 2: red_nz(px, ax[2]); red_nz(py, ay[2]); red_nz(pz, az[2]); ax[2] = 0.f; ay[2] = 0.f; az[2] = 0.f; break;
+    default: red_nz(px, ax[3]); red_nz(py, ay[3]); red_nz(pz, az[3]); ax[3] = 0.f; ay[3] = 0.f; az[3] = 0.f; break;
+    }
+}
+
+// Address of the lane's row (J, K) (0-based) at x-plane i0 (0-based).
+//   TILED = false: the reference's Fortran-order arrays, element i0 + mx*(J + my*K); consecutive planes are 1 apart.
+//   TILED = true : the shadow arrays of the fused mover.  The 16 lanes of a half-warp flush one x-plane of the 4x4 (y,z)
+//     footprint; in Fortran order that is 16 different cache lines per RED instruction.  The shadow arrays therefore keep
+//     every 4x4 (y,z) tile of an x-plane contiguous (64 B): element ((tz*nty + ty)*mx + i0)*16 + (K&3)*4 + (J&3), so a flush
+//     touches at most 2x2 tiles (<= 4 short segments) and consecutive planes are 16 apart.  k_add_shadow_tiled (fields.cu)
+//     folds them back into curx/cury/curz.
+template <bool TILED>
+__device__ __forceinline__ size_t row_index(int mx, int my, int nty, int J, int K, int i0)
+{
+    if (TILED) return ((size_t)(((K >> 2) * nty + (J >> 2)) * (long long)mx + i0) << 4) + (size_t)(((K & 3) << 2) | (J & 3));
+    return (size_t)((long long)mx * (J + (long long)my * K) + i0);
 }
 
 // same classification as k_classify_key (particles.cu), on a copy of the position
@@ -188,7 +250,10 @@ __device__ __forceinline__ uint32_t sort_key(const DevGeom &G, float x, float y,
 template <int ORDER, bool FUSED>
 __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
 {
-    __shared__ __align__(16) float stage[CR_WARPS][32][CR_STRIDE];
+    // dynamic shared memory (CR_SMEM_BYTES > 48 KB): the factor staging of phase 1 -> phase 2, then the record pipeline
+    extern __shared__ __align__(16) unsigned char cr_smem[];
+    float (*stage)[32][CR_STRIDE] = reinterpret_cast<float (*)[32][CR_STRIDE]>(cr_smem);
+    uint32_t (*rec)[2][9][32] = reinterpret_cast<uint32_t (*)[2][9][32]>(cr_smem + sizeof(float) * CR_WARPS * 32 * CR_STRIDE);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int half = lane >> 4, hl = lane & 15;
     const long long gw = (long long)blockIdx.x * CR_WARPS + warp;
@@ -197,28 +262,56 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
     const DevGeom &G = A.G;
     const int mx = G.mx, my = G.my;
     const int j = lane & 3, k = (lane >> 2) & 3;
-    const int loff = (j - 1) + my * (k - 1);
+    constexpr bool TILED = FUSED && TGPU_SHADOW_TILED;
+    constexpr int PS = TILED ? 16 : 1;                       // distance between consecutive x-planes of a row
 
     int wi = 0, wrow = 0;                                    // window cell (1-based i, row id)
     bool have = false;
     float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f}, az[4] = {0.f, 0.f, 0.f, 0.f};
 
-    for (int it = 0; it < CR_CHUNK / 16; ++it) {
+    // ---- record pipeline: rec[buf][field][lane], fields x y z u v w ch ind tag; each lane only ever touches its own slots
+    const bool lazy = FUSED && A.perm != nullptr;
+    constexpr int NIT = CR_CHUNK / 16;
+    auto fetch = [&](int buf, long long tt, long long pp) {
+        if (tt < A.n) {
+            uint32_t *r = &rec[warp][buf][0][lane];
+            cp_async4(r + 0 * 32, A.s.x + pp); cp_async4(r + 1 * 32, A.s.y + pp); cp_async4(r + 2 * 32, A.s.z + pp);
+            cp_async4(r + 3 * 32, A.s.u + pp); cp_async4(r + 4 * 32, A.s.v + pp); cp_async4(r + 5 * 32, A.s.w + pp);
+            cp_async4(r + 6 * 32, A.s.ch + pp);
+            if (lazy) { cp_async4(r + 7 * 32, A.s.ind + pp); cp_async4(r + 8 * 32, A.s.tag + pp); }
+        }
+        cp_async_commit();
+    };
+    {
+        const long long t0 = base + hl;
+        fetch(0, t0, (lazy && t0 < A.n) ? (long long)A.perm[t0] : t0);
+    }
+    long long pnext = base + 16 + hl;                        // physical index of this lane's particle of the next step
+    if (lazy && pnext < A.n) pnext = A.perm[pnext];
+
+    for (int it = 0; it < NIT; ++it) {
         const long long t = base + it * 16 + hl;
         float *st = &stage[warp][lane][0];
         int ci = -1, crow = -1;                              // deposit base cell of this lane's particle
+        cp_async_wait_all();                                 // this step's record has landed in rec[it & 1]
+        if (it + 1 < NIT) {
+            fetch((it + 1) & 1, t + 16, pnext);              // next step's record, in flight during this step
+            pnext = t + 32;
+            if (lazy && it + 2 < NIT && pnext < A.n) pnext = A.perm[pnext];
+        }
         // ------------------------------------------------------------------ phase 1: lane = particle
         if (t < A.n) {
-            const long long p = (FUSED && A.perm) ? (long long)A.perm[t] : t;
-            float x = A.s.x[p], y = A.s.y[p], z = A.s.z[p], u = A.s.u[p], v = A.s.v[p], w = A.s.w[p];
-            const float ch = A.s.ch[p];
-            if (FUSED && A.perm) {
+            const uint32_t *r = &rec[warp][it & 1][0][lane];
+            float x = __uint_as_float(r[0 * 32]), y = __uint_as_float(r[1 * 32]), z = __uint_as_float(r[2 * 32]);
+            float u = __uint_as_float(r[3 * 32]), v = __uint_as_float(r[4 * 32]), w = __uint_as_float(r[5 * 32]);
+            const float ch = __uint_as_float(r[6 * 32]);
+            if (lazy) {
                 // lazily sorted input: the record still carries last lap's unwrapped position; apply the periodic wrap /
                 // frame shift its sort key was computed with (deposit_particles loop B), and carry the passive fields along
                 if (x < A.G.minx) x += A.G.shiftx_lo; else if (x > A.G.maxx) x -= A.G.shiftx_hi;
                 if (y < A.G.miny) y += A.G.shifty_lo; else if (y > A.G.maxy) y -= A.G.shifty_hi;
                 if (z < A.G.minz) z += A.G.shiftz_lo; else if (z > A.G.maxz) z -= A.G.shiftz_hi;
-                A.d.ch[t] = ch; A.d.ind[t] = A.s.ind[p]; A.d.tag[t] = A.s.tag[p];
+                A.d.ch[t] = ch; A.d.ind[t] = (int32_t)r[7 * 32]; A.d.tag[t] = (int32_t)r[8 * 32];
             }
             const float q = ch * A.qs;
             float S1[4], S2[4];
@@ -236,7 +329,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
                 const bool fast = ORDER == 1 || (q1 && dxp != 0.f && dyp != 0.f && dzp != 0.f);
                 if (fast) {
                     const float wxs[2] = {Wx[1], Wx[2]}, wys[2] = {Wy[1], Wy[2]}, wzs[2] = {Wz[1], Wz[2]};
-                    const long long nbase = (ip - 1) + (long long)mx * ((jp - 1) + (long long)my * (kp - 1));
+                    const int nbase = (ip - 1) + mx * ((jp - 1) + my * (kp - 1));
                     gather_nodes<2>(A.prim8, nbase, mx, my, wxs, wys, wzs, e0, e1, e2, b0, b1, b2);
                 } else if (ORDER == 2) {
                     int lox, loy, loz;
@@ -260,27 +353,29 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
                     b0 = b0 + G.ext[3] * 0.5f * qm * cinv; b1 = b1 + G.ext[4] * 0.5f * qm * cinv; b2 = b2 + G.ext[5] * 0.5f * qm * cinv;
                     e0 = e0 + G.ext[0] * 0.5f * qm; e1 = e1 + G.ext[1] * 0.5f * qm; e2 = e2 + G.ext[2] * 0.5f * qm;
                 }
-                push_particle(G.c, G.pusher, e0, e1, e2, b0, b1, b2, x, y, z, u, v, w);
+                push_particle<true>(G.c, G.pusher, e0, e1, e2, b0, b1, b2, x, y, z, u, v, w, cinv);
                 A.d.x[t] = x; A.d.y[t] = y; A.d.z[t] = z; A.d.u[t] = u; A.d.v[t] = v; A.d.w[t] = w;
                 // The deposit's "old" shape is the gather's shape at the true pre-push position (the reference
                 // recomputes it as x - u/gamma*c, particles_movedeposit.F90:1384-1388, equal to round-off).
-                crow = (jp - 1) + my * (kp - 1); ci = ip;
+                // sort key of the pushed particle + its rank inside the destination bin; the rank comes back from L2 while
+                // the deposit factors are being staged and is stored at the end of the phase
+                const uint32_t ky = sort_key(G, x, y, z);
+                A.key[t] = ky;
+                const int rank_in_bin = atomicAdd(&A.bincount[ky], 1);
+                crow = (jp - 1) | ((kp - 1) << 16); ci = ip;
                 shape_window<ORDER>(x - (int)x, (int)x - ip, S2);
                 stage_axis<0>(st, Wx, S2, q, 0.f, (ip - 1) & 3);
                 shape_window<ORDER>(y - (int)y, (int)y - jp, S2);
                 stage_axis<1>(st + 12, Wy, S2, q, __int_as_float(ci), 0);
                 shape_window<ORDER>(z - (int)z, (int)z - kp, S2);
                 stage_axis<1>(st + 28, Wz, S2, q, __int_as_float(crow), 0);
-                // sort key of the pushed particle + its rank inside the destination bin
-                const uint32_t ky = sort_key(G, x, y, z);
-                A.key[t] = ky;
-                A.slot[t] = atomicAdd(&A.bincount[ky], 1);
+                A.slot[t] = rank_in_bin;
             } else {
                 // deposit_particles loop A: old position recomputed from the new one (particles_movedeposit.F90:1384-1390)
                 const float invgam = 1.f / sqrtf(1 + u * u + v * v + w * w);
                 const float x1 = x - u * invgam * G.c, y1 = y - v * invgam * G.c, z1 = z - w * invgam * G.c;
                 const int i1 = (int)x1, j1 = (int)y1, k1 = (int)z1;
-                crow = (j1 - 1) + my * (k1 - 1); ci = i1;
+                crow = (j1 - 1) | ((k1 - 1) << 16); ci = i1;
                 shape_window<ORDER>(x1 - i1, 0, S1); shape_window<ORDER>(x - (int)x, (int)x - i1, S2);
                 stage_axis<0>(st, S1, S2, q, 0.f, (i1 - 1) & 3);
                 shape_window<ORDER>(y1 - j1, 0, S1); shape_window<ORDER>(y - (int)y, (int)y - j1, S2);
@@ -289,30 +384,32 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
                 stage_axis<1>(st + 28, S1, S2, q, __int_as_float(crow), 0);
             }
         }
+        else {
+            // past the end (last warp only): stage zeros so that phase 2 can always walk all 16 slots of the half
+#pragma unroll
+            for (int q4 = 0; q4 < CR_STRIDE / 4; q4++) *(float4 *)(st + 4 * q4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         // run starts inside each half: a particle whose cell differs from its predecessor's
         const int pci = __shfl_up_sync(0xffffffffu, ci, 1), pcrow = __shfl_up_sync(0xffffffffu, crow, 1);
-        const bool start = hl == 0 || ci != pci || crow != pcrow;
+        const bool start = t < A.n && (hl == 0 || ci != pci || crow != pcrow);
         unsigned starts = (__ballot_sync(0xffffffffu, start) >> (half << 4)) & 0xFFFFu;
         __syncwarp();                                        // staging written by all lanes is visible to the warp
         // ------------------------------------------------------------------ phase 2: half-warp = footprint
-        const long long rem = A.n - (base + it * 16);
-        const int cnt = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
         // Both halves walk their 16 particles in lockstep; only the (rare) window moves diverge.
         const float4 *sp = (const float4 *)&stage[warp][half << 4][0];
 #pragma unroll 2
         for (int tt = 0; tt < 16; ++tt, sp += CR_STRIDE / 4) {
-            if (tt >= cnt) break;
             if ((starts >> tt) & 1u) {
                 // particle tt opens a run of particles that share one footprint
                 const int ni = __float_as_int(sp[3].w), nrow = __float_as_int(sp[7].w);
                 if (!have || ni != wi || nrow != wrow) {
                     if (have) {
-                        const size_t idx0 = (size_t)((long long)mx * (wrow + loff) + (wi - 2));
+                        const size_t idx0 = row_index<TILED>(mx, my, A.nty, (wrow & 0xFFFF) + j - 1, (wrow >> 16) + k - 1, wi - 2);
                         const int di = ni - wi;
                         // sliding 1..3 cells along x completes that many planes; anything else flushes the window
                         // sliding 1..3 cells along x completes that many planes; anything else flushes the window
                         if (nrow == wrow && di == 1) flush_one(A.cx, A.cy, A.cz, idx0, wi, ax, ay, az);
-                        else flush_planes(A.cx, A.cy, A.cz, idx0, wi, (nrow == wrow && di > 1 && di < 4) ? di : 4, ax, ay, az);
+                        else flush_planes<PS>(A.cx, A.cy, A.cz, idx0, wi, (nrow == wrow && di > 1 && di < 4) ? di : 4, ax, ay, az);
                     }
                     wi = ni; wrow = nrow; have = true;
                 }
@@ -325,24 +422,43 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
             const float wx = fmaf(yb, dsz, ya * sz1);      // Wx(j,k)
             const float a = qpsy * sz1, b = qpsy * dsz;    // Jy = XA*a + XB*b
             const float c = qpsz * sy1, d = qpsz * dsy;    // Jz = XA*c + XB*d
+#if CR_FFMA2
+            // sm_100 packed fp32 (FFMA2, fma.rn.f32x2): the x-ring registers pair up as (0,1) and (2,3), the per-lane
+            // factors are broadcast into both halves of a 64-bit register; 10 issue slots instead of 20
+            {
+                const float2 wx2 = make_float2(wx, wx), a2 = make_float2(a, a), b2 = make_float2(b, b),
+                             c2 = make_float2(c, c), d2 = make_float2(d, d);
+                const float2 px01 = make_float2(qpsx.x, qpsx.y), px23 = make_float2(qpsx.z, qpsx.w);
+                const float2 xa01 = make_float2(xa.x, xa.y), xa23 = make_float2(xa.z, xa.w);
+                const float2 xb01 = make_float2(xb.x, xb.y), xb23 = make_float2(xb.z, xb.w);
+                float2 t;
+                t = __ffma2_rn(px01, wx2, make_float2(ax[0], ax[1])); ax[0] = t.x; ax[1] = t.y;
+                t = __ffma2_rn(px23, wx2, make_float2(ax[2], ax[3])); ax[2] = t.x; ax[3] = t.y;
+                t = __ffma2_rn(xa01, a2, __ffma2_rn(xb01, b2, make_float2(ay[0], ay[1]))); ay[0] = t.x; ay[1] = t.y;
+                t = __ffma2_rn(xa23, a2, __ffma2_rn(xb23, b2, make_float2(ay[2], ay[3]))); ay[2] = t.x; ay[3] = t.y;
+                t = __ffma2_rn(xa01, c2, __ffma2_rn(xb01, d2, make_float2(az[0], az[1]))); az[0] = t.x; az[1] = t.y;
+                t = __ffma2_rn(xa23, c2, __ffma2_rn(xb23, d2, make_float2(az[2], az[3]))); az[2] = t.x; az[3] = t.y;
+            }
+#else
             ax[0] = fmaf(qpsx.x, wx, ax[0]); ax[1] = fmaf(qpsx.y, wx, ax[1]);
             ax[2] = fmaf(qpsx.z, wx, ax[2]); ax[3] = fmaf(qpsx.w, wx, ax[3]);
             ay[0] = fmaf(xa.x, a, fmaf(xb.x, b, ay[0])); ay[1] = fmaf(xa.y, a, fmaf(xb.y, b, ay[1]));
             ay[2] = fmaf(xa.z, a, fmaf(xb.z, b, ay[2])); ay[3] = fmaf(xa.w, a, fmaf(xb.w, b, ay[3]));
             az[0] = fmaf(xa.x, c, fmaf(xb.x, d, az[0])); az[1] = fmaf(xa.y, c, fmaf(xb.y, d, az[1]));
             az[2] = fmaf(xa.z, c, fmaf(xb.z, d, az[2])); az[3] = fmaf(xa.w, c, fmaf(xb.w, d, az[3]));
+#endif
         }
         __syncwarp();
     }
     if (have) {
-        const size_t idx0 = (size_t)((long long)mx * (wrow + loff) + (wi - 2));
-        flush_planes(A.cx, A.cy, A.cz, idx0, wi, 4, ax, ay, az);
+        const size_t idx0 = row_index<TILED>(mx, my, A.nty, (wrow & 0xFFFF) + j - 1, (wrow >> 16) + k - 1, wi - 2);
+        flush_planes<PS>(A.cx, A.cy, A.cz, idx0, wi, 4, ax, ay, az);
     }
 }
 
 int cellrun_supported(const tgpu_ctx *h)
 {
-    return h->P.dim == 3 && (h->P.order == 1 || h->P.order == 2);
+    return h->P.dim == 3 && (h->P.order == 1 || h->P.order == 2) && h->G.lot < (1ll << 30) && h->P.my < 65536 && h->P.mz < 32768;
 }
 
 template <bool FUSED>
@@ -353,7 +469,7 @@ static int launch(tgpu_ctx *h, float *cx, float *cy, float *cz)
         if (S.n == 0) continue;
         CRArgs A;
         A.s = S; A.d = S; A.perm = nullptr;
-        A.n = S.n; A.prim8 = h->prim8; A.cx = cx; A.cy = cy; A.cz = cz; A.G = h->G;
+        A.n = S.n; A.prim8 = h->prim8; A.cx = cx; A.cy = cy; A.cz = cz; A.nty = h->nty; A.G = h->G;
         A.qm = s ? h->P.qme : h->P.qmi; A.qs = s ? h->P.qe : h->P.qi;
         const size_t nb = (size_t)h->G.lot + TGPU_NBIN_EXTRA;
         A.key = h->key[s]; A.slot = h->slot + (size_t)s * h->maxhlf; A.bincount = h->bincount + (size_t)s * nb;
@@ -361,8 +477,13 @@ static int launch(tgpu_ctx *h, float *cx, float *cy, float *cz)
         if (FUSED && h->lazy[s]) { A.perm = h->perm[s]; A.d = h->alt[s]; }     // gather through the pending permutation
         long long warps = (S.n + 2 * CR_CHUNK - 1) / (2 * CR_CHUNK);
         int blocks = (int)((warps + CR_WARPS - 1) / CR_WARPS);
-        if (h->P.order == 2) k_cellrun<2, FUSED><<<blocks, CR_WARPS * 32, 0, h->stream>>>(A);
-        else k_cellrun<1, FUSED><<<blocks, CR_WARPS * 32, 0, h->stream>>>(A);
+        if (h->P.order == 2) {
+            CK(cudaFuncSetAttribute(k_cellrun<2, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM_BYTES));
+            k_cellrun<2, FUSED><<<blocks, CR_WARPS * 32, CR_SMEM_BYTES, h->stream>>>(A);
+        } else {
+            CK(cudaFuncSetAttribute(k_cellrun<1, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM_BYTES));
+            k_cellrun<1, FUSED><<<blocks, CR_WARPS * 32, CR_SMEM_BYTES, h->stream>>>(A);
+        }
         CKK(h);
         if (FUSED && h->lazy[s]) {
             // the pushed records now sit, in sorted order and wrapped, in the other buffer

@@ -149,11 +149,47 @@ int fld_add(tgpu_ctx *h)
     h->need_prim = 1;
     return 0;
 }
+// cur += shadow; shadow = 0, where shadow is the fused mover's tiled deposit target (cellrun.cu row_index): each 4x4 (y,z)
+// tile of an x-plane is 16 contiguous floats, y fastest.  One thread = (i, four consecutive y, one z): one 128-bit load per
+// component from the tile (lanes = consecutive i), twelve independent read-modify-writes of the Fortran-order arrays,
+// each coalesced along x.  All loads are issued before the first store.
+__global__ void __launch_bounds__(256) k_add_shadow_tiled(float *__restrict__ c0, float *__restrict__ c1, float *__restrict__ c2,
+                                                          float4 *__restrict__ s0, float4 *__restrict__ s1, float4 *__restrict__ s2,
+                                                          int mx, int my, int mz, int nty)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y, K = blockIdx.z;
+    if (i >= mx) return;
+    const size_t a = (((size_t)((K >> 2) * nty + ty) * mx + i) << 2) + (K & 3);      // in float4 units
+    const float4 v0 = s0[a], v1 = s1[a], v2 = s2[a];
+    const float sv[3][4] = {{v0.x, v0.y, v0.z, v0.w}, {v1.x, v1.y, v1.z, v1.w}, {v2.x, v2.y, v2.z, v2.w}};
+    float *const cc[3] = {c0, c1, c2};
+    const size_t l0 = (size_t)i + (size_t)mx * (4 * ty + (size_t)my * K);
+    float cv[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) cv[c][q] = (4 * ty + q < my) ? cc[c][l0 + (size_t)q * mx] : 0.f;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    s0[a] = zero; s1[a] = zero; s2[a] = zero;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (4 * ty + q < my) cc[c][l0 + (size_t)q * mx] = cv[c][q] + sv[c][q];
+}
 int fld_add_shadow(tgpu_ctx *h)
 {
-    size_t n = (size_t)h->G.lot;
-    int blocks = (int)((n + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-    k_add3<<<blocks, 256, 0, h->stream>>>(h->f[6], h->f[7], h->f[8], h->shadow[0], h->shadow[1], h->shadow[2], n, 1);
+#if !TGPU_SHADOW_TILED
+    {
+        size_t n = (size_t)h->G.lot;
+        int blocks = (int)((n + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+        k_add3<<<blocks, 256, 0, h->stream>>>(h->f[6], h->f[7], h->f[8], h->shadow[0], h->shadow[1], h->shadow[2], n, 1);
+        CKK(h);
+        return 0;
+    }
+#endif
+    dim3 grid((h->G.mx + 127) / 128, h->nty, h->G.mz);
+    k_add_shadow_tiled<<<grid, 128, 0, h->stream>>>(h->f[6], h->f[7], h->f[8], (float4 *)h->shadow[0], (float4 *)h->shadow[1],
+                                                    (float4 *)h->shadow[2], h->G.mx, h->G.my, h->G.mz, h->nty);
     CKK(h);
     return 0;
 }

@@ -59,11 +59,32 @@ __device__ __forceinline__ void shape_window(float d, int shift, float W[4])
     else { W[0] = a1; W[1] = a2; W[2] = a3; W[3] = 0.f; }                      // a0 == 0 whenever shift = -1 is reachable
 }
 
+// FAST (cell-run kernels): reciprocals and reciprocal square roots through the SFU (MUFU.RCP / MUFU.RSQ, <= 2 ulp) instead
+// of the IEEE division / square-root sequences; the difference is of the order of the FMA-contraction noise that the
+// mover tolerance already covers (tests/test_gpu_parity.py).
+template <bool FAST = false>
 __device__ __forceinline__ void push_particle(float c, int pusher, float ex0, float ey0, float ez0, float bx0, float by0,
-                                              float bz0, float &x, float &y, float &z, float &u, float &v, float &w)
+                                              float bz0, float &x, float &y, float &z, float &u, float &v, float &w,
+                                              float cinv_host = 0.f)
 {
-    const float cinv = 1.f / c;
+    const float cinv = FAST ? cinv_host : 1.f / c;      // cinv_host = the host's 1.f / c (same rounding)
     float u0, v0, w0, u1, v1, w1, g, f;
+    if (FAST && pusher != 1) {
+        u0 = c * u + ex0; v0 = c * v + ey0; w0 = c * w + ez0;
+        g = c * rsqrtf(c * c + u0 * u0 + v0 * v0 + w0 * w0);
+        bx0 = g * bx0; by0 = g * by0; bz0 = g * bz0;
+        f = __fdividef(2.f, 1.f + bx0 * bx0 + by0 * by0 + bz0 * bz0);
+        u1 = (u0 + v0 * bz0 - w0 * by0) * f;
+        v1 = (v0 + w0 * bx0 - u0 * bz0) * f;
+        w1 = (w0 + u0 * by0 - v0 * bx0) * f;
+        u0 = u0 + v1 * bz0 - w1 * by0 + ex0;
+        v0 = v0 + w1 * bx0 - u1 * bz0 + ey0;
+        w0 = w0 + u1 * by0 - v1 * bx0 + ez0;
+        u = u0 * cinv; v = v0 * cinv; w = w0 * cinv;
+        g = c * rsqrtf(c * c + u0 * u0 + v0 * v0 + w0 * w0);
+        x = x + u * g * c; y = y + v * g * c; z = z + w * g * c;
+        return;
+    }
     if (pusher == 1) {
         g = 1.f / sqrtf(1.f + u * u + v * v + w * w);
         float vx0 = c * u * g, vy0 = c * v * g, vz0 = c * w * g;

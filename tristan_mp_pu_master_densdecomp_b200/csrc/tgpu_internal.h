@@ -6,6 +6,9 @@
 #include <vector>
 #include "../../include/tristan_gpu.h"
 
+#ifndef TGPU_SHADOW_TILED
+#define TGPU_SHADOW_TILED 1  // fused mover deposits into 4x4 (y,z)-tiled shadow arrays (cellrun.cu row_index); 0 = Fortran order (A/B)
+#endif
 #define TGPU_NDIR 9          // 3x3 neighbour codes over the two decomposed axes; code 4 = stay
 #define TGPU_NBIN_EXTRA 10   // sort bins after the `lot` cell bins: 9 direction codes (4 unused) + discard
 
@@ -58,7 +61,8 @@ struct tgpu_ctx {
     tgpu_particle *sendbuf, *recvbuf;   // TGPU_NDIR * buffsize each
     int need_prim;           // primal grids stale
     int fused_pending;       // currents of the last move already deposited into shadow
-    float *shadow[3];
+    float *shadow[3];        // tiled: [tz][ty][i][4x4 (y,z) tile] (cellrun.cu row_index), nty x ntz tiles
+    int nty, ntz; size_t shadow_floats;
     int opt_fused;
     int hook_kind; float hook[5];   // user hooks for tgpu_step (1 = shock: leftwall, binit, btheta, bphi, beta)
     int keys_valid;          // key[]/slot[]/bincount[] already hold this lap's sort keys (written by the fused mover)
