@@ -24,7 +24,9 @@
 #include "tgpu_internal.h"
 #include "shapes.cuh"
 
+#ifndef CR_WARPS
 #define CR_WARPS 8
+#endif
 #define CR_STRIDE 44
 #ifndef CR_MINB
 #define CR_MINB 3
@@ -32,10 +34,17 @@
 #ifndef CR_CHUNK
 #define CR_CHUNK 128          // particles per half-warp
 #endif
+#ifndef CR_PREFETCH
+#define CR_PREFETCH 0         // L1 prefetch of the next step's field nodes (A/B switch)
+#endif
 #ifndef CR_FFMA2
 #define CR_FFMA2 1            // packed fp32 (FFMA2/FMUL2) in the gather and the deposit accumulation: measured 2-3 % faster
 #endif
-#define CR_SMEM_BYTES (sizeof(float) * CR_WARPS * 32 * CR_STRIDE + sizeof(uint32_t) * CR_WARPS * 2 * 9 * 32)
+// factor staging of one warp: two halves of 16 particles x CR_STRIDE floats; the second half starts 16 floats (half of
+// the 32 banks) further on, so the lockstep phase-2 loads of the two half-warps never fall into the same banks
+#define CR_HALF_FLOATS (16 * CR_STRIDE + 16)
+#define CR_WARP_FLOATS (2 * CR_HALF_FLOATS)
+#define CR_SMEM_BYTES (sizeof(float) * CR_WARPS * CR_WARP_FLOATS + sizeof(uint32_t) * CR_WARPS * 2 * 9 * 32)
 
 struct CRArgs {
     Species s;                // source records
@@ -252,8 +261,8 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
 {
     // dynamic shared memory (CR_SMEM_BYTES > 48 KB): the factor staging of phase 1 -> phase 2, then the record pipeline
     extern __shared__ __align__(16) unsigned char cr_smem[];
-    float (*stage)[32][CR_STRIDE] = reinterpret_cast<float (*)[32][CR_STRIDE]>(cr_smem);
-    uint32_t (*rec)[2][9][32] = reinterpret_cast<uint32_t (*)[2][9][32]>(cr_smem + sizeof(float) * CR_WARPS * 32 * CR_STRIDE);
+    float *stage = reinterpret_cast<float *>(cr_smem);
+    uint32_t (*rec)[2][9][32] = reinterpret_cast<uint32_t (*)[2][9][32]>(cr_smem + sizeof(float) * CR_WARPS * CR_WARP_FLOATS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int half = lane >> 4, hl = lane & 15;
     const long long gw = (long long)blockIdx.x * CR_WARPS + warp;
@@ -272,8 +281,9 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
     // ---- record pipeline: rec[buf][field][lane], fields x y z u v w ch ind tag; each lane only ever touches its own slots
     const bool lazy = FUSED && A.perm != nullptr;
     constexpr int NIT = CR_CHUNK / 16;
-    auto fetch = [&](int buf, long long tt, long long pp) {
+    auto fetch = [&](int buf, long long tt, int pp32) {
         if (tt < A.n) {
+            const long long pp = lazy ? (long long)pp32 : tt;
             uint32_t *r = &rec[warp][buf][0][lane];
             cp_async4(r + 0 * 32, A.s.x + pp); cp_async4(r + 1 * 32, A.s.y + pp); cp_async4(r + 2 * 32, A.s.z + pp);
             cp_async4(r + 3 * 32, A.s.u + pp); cp_async4(r + 4 * 32, A.s.v + pp); cp_async4(r + 5 * 32, A.s.w + pp);
@@ -284,20 +294,21 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
     };
     {
         const long long t0 = base + hl;
-        fetch(0, t0, (lazy && t0 < A.n) ? (long long)A.perm[t0] : t0);
+        fetch(0, t0, (lazy && t0 < A.n) ? A.perm[t0] : 0);
     }
-    long long pnext = base + 16 + hl;                        // physical index of this lane's particle of the next step
-    if (lazy && pnext < A.n) pnext = A.perm[pnext];
+    // permutation entry of this lane's particle of the next step: loaded one step ahead and kept as the raw 32-bit
+    // value (no instruction touches it until the following step, so the load never stalls the warp)
+    int pnext = 0;
+    if (lazy && base + 16 + hl < A.n) pnext = A.perm[base + 16 + hl];
 
     for (int it = 0; it < NIT; ++it) {
         const long long t = base + it * 16 + hl;
-        float *st = &stage[warp][lane][0];
+        float *st = stage + warp * CR_WARP_FLOATS + half * CR_HALF_FLOATS + hl * CR_STRIDE;
         int ci = -1, crow = -1;                              // deposit base cell of this lane's particle
         cp_async_wait_all();                                 // this step's record has landed in rec[it & 1]
         if (it + 1 < NIT) {
             fetch((it + 1) & 1, t + 16, pnext);              // next step's record, in flight during this step
-            pnext = t + 32;
-            if (lazy && it + 2 < NIT && pnext < A.n) pnext = A.perm[pnext];
+            if (lazy && it + 2 < NIT && t + 32 < A.n) pnext = A.perm[t + 32];
         }
         // ------------------------------------------------------------------ phase 1: lane = particle
         if (t < A.n) {
@@ -330,6 +341,14 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
                 if (fast) {
                     const float wxs[2] = {Wx[1], Wx[2]}, wys[2] = {Wy[1], Wy[2]}, wzs[2] = {Wz[1], Wz[2]};
                     const int nbase = (ip - 1) + mx * ((jp - 1) + my * (kp - 1));
+#if CR_PREFETCH
+                    {
+                        // the next 16-particle step of this half-warp works one or two cells further along x: pull the
+                        // field nodes it will gather (4 rows x nodes ip+1..ip+4, one 32 B node per lane) into L1 now
+                        const int pn = nbase + mx * ((hl & 1) + my * ((hl >> 1) & 1)) + 2 + (hl >> 2);
+                        if (pn < (int)G.lot) asm volatile("prefetch.global.L1 [%0];" :: "l"(A.prim8 + 2 * (unsigned)pn));
+                    }
+#endif
                     gather_nodes<2>(A.prim8, nbase, mx, my, wxs, wys, wzs, e0, e1, e2, b0, b1, b2);
                 } else if (ORDER == 2) {
                     int lox, loy, loz;
@@ -396,7 +415,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
         __syncwarp();                                        // staging written by all lanes is visible to the warp
         // ------------------------------------------------------------------ phase 2: half-warp = footprint
         // Both halves walk their 16 particles in lockstep; only the (rare) window moves diverge.
-        const float4 *sp = (const float4 *)&stage[warp][half << 4][0];
+        const float4 *sp = (const float4 *)(stage + warp * CR_WARP_FLOATS + half * CR_HALF_FLOATS);
 #pragma unroll 2
         for (int tt = 0; tt < 16; ++tt, sp += CR_STRIDE / 4) {
             if ((starts >> tt) & 1u) {
