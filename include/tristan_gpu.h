@@ -122,8 +122,8 @@ int tgpu_add_current(tgpu_ctx *h);                /* fields.F90:1372-1395 */
 /* ---- field boundaries: code/fieldboundaries.F90 ---------------------------------------------- */
 int tgpu_bc_b1(tgpu_ctx *h);                      /* fieldboundaries.F90:181-263 */
 int tgpu_bc_e1(tgpu_ctx *h);                      /* fieldboundaries.F90:306-392 */
-int tgpu_bc_b2(tgpu_ctx *h);                      /* :274-295 (radiation `surface` not ported: == bc_b1) */
-int tgpu_bc_e2(tgpu_ctx *h);                      /* :403-426 (== bc_e1) */
+int tgpu_bc_b2(tgpu_ctx *h);                      /* :274-295, 493-606: radiation `surface` on radiating axes, then bc_b1 */
+int tgpu_bc_e2(tgpu_ctx *h);                      /* :403-426: `surface` (low faces, E<->B), then bc_e1 */
 int tgpu_exchange_current(tgpu_ctx *h);           /* fieldboundaries.F90:1768-2189 */
 
 /* ---- filter: code/filter.F90, code/optimized_filters.F90 ------------------------------------- */

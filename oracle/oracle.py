@@ -17,6 +17,7 @@ EX, EY, EZ, BX, BY, BZ, CURX, CURY, CURZ = range(9)
 ARR_NAMES = ["ex", "ey", "ez", "bx", "by", "bz", "curx", "cury", "curz"]
 (PH_BC_B1, PH_BC_E1, PH_BHALF, PH_MOVE, PH_EFULL, PH_RESET, PH_DEPOSIT, PH_EXCH_P, PH_EXCH_CUR,
  PH_FILTER, PH_ADD_CUR, PH_INJECT_OTHERS, PH_REORDER) = range(13)
+PH_SURF_B, PH_SURF_E = 100, 101   # the `surface` part of bc_b2 / bc_e2 (radiating axes)
 Q_REFERENCE = 0xF
 
 PARTICLE_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4"), ("u", "f4"), ("v", "f4"), ("w", "f4"),
@@ -67,7 +68,7 @@ def lib():
         for name in ["orc_advance_b_halfstep", "orc_advance_e_fullstep", "orc_reset_currents",
                      "orc_add_current", "orc_move_particles", "orc_deposit_currents_only",
                      "orc_deposit_particles", "orc_inject_others", "orc_reorder_particles",
-                     "orc_filter1_pass"]:
+                     "orc_filter1_pass", "orc_surface_b", "orc_surface_e"]:
             getattr(L, name).argtypes = [vp]
         L.orc_deposit_one.argtypes = [vp] + [cf] * 7
         L.orc_mover_range.argtypes = [vp, ci, ci, cf]

@@ -350,6 +350,88 @@ void orc_bc_fields(orc_world *w, int first)
 }
 
 /* ------------------------------------------------------------------------- */
+/* radiation boundary `surface` (Lindman-type absorbing face):                  */
+/* fieldboundaries.F90:493-606, called by bc_b2 (:274-295) on the high face of   */
+/* every radiating axis and by bc_e2 (:403-426) on the low face with mirrored    */
+/* strides and the roles of E and B exchanged.  The arguments keep the           */
+/* reference's meaning: 1-based flat indices, strides (ix,iy,iz) of the three    */
+/* rotated axes (iz = the axis normal to the face), first element m00.           */
+/* The #ifdef twoD variants (one stride is zero) are the two branches below.     */
+/* ------------------------------------------------------------------------- */
+static void surface(float *bx, float *by, float *bz, const float *ex, const float *ey, const float *ez,
+                    long ix, long iy, long iz, int mx, int my, int mz, long m00, float c, int twod)
+{
+#define A1(a, n) (a)[(n) - 1]
+    const float rs = 2.f * c / (1.f + c);
+    const float s = .4142136f;
+    const float os = .5f * (1.f - s) * rs;
+    const long mf = m00 + iz * (mz - 1);                      /* first element of the face */
+#define BZ_HALF(n) A1(bz, n) = A1(bz, n) + .5f * c * (A1(ex, (n) + iy) - A1(ex, n) - A1(ey, (n) + ix) + A1(ey, n))
+#define BX_UPD(n) A1(bx, n) = A1(bx, n) + rs * (A1(bx, (n) - iz) - A1(bx, n) + s * (A1(bz, n) - A1(bz, (n) - ix)))      \
+        - os * (A1(ez, (n) + iy) - A1(ez, n)) - (os - c) * (A1(ez, (n) + iy - iz) - A1(ez, (n) - iz))                  \
+        - c * (A1(ey, n) - A1(ey, (n) - iz))
+#define BY_UPD(n) A1(by, n) = A1(by, n) + rs * (A1(by, (n) - iz) - A1(by, n) + s * (A1(bz, n) - A1(bz, (n) - iy)))      \
+        + os * (A1(ez, (n) + ix) - A1(ez, n)) + (os - c) * (A1(ez, (n) + ix - iz) - A1(ez, (n) - iz))                  \
+        + c * (A1(ex, n) - A1(ex, (n) - iz))
+    if (!twod) {                                              /* :515-537 */
+        for (int jj = 0; jj <= my - 2; jj++) {
+            const long m = mf + iy * jj;
+            for (int ii = 0; ii <= mx - 2; ii++) { const long n = m + ix * ii; BZ_HALF(n); }
+            for (int ii = 1; ii <= mx - 2; ii++) { const long n = m + ix * ii; BX_UPD(n); }
+        }
+        for (int ii = 0; ii <= mx - 2; ii++) {
+            const long m = mf + ix * ii;
+            for (int jj = 1; jj <= my - 2; jj++) { const long n = m + iy * jj; BY_UPD(n); }
+            for (int jj = 0; jj <= my - 2; jj++) { const long n = m + iy * jj; BZ_HALF(n); }
+        }
+    } else if (ix == 0) {                                     /* :540-560 */
+        for (int jj = 0; jj <= my - 2; jj++) { const long n = mf + iy * jj; BZ_HALF(n); BX_UPD(n); }
+        for (int jj = 1; jj <= my - 2; jj++) { const long n = mf + iy * jj; BY_UPD(n); }
+        for (int jj = 0; jj <= my - 2; jj++) { const long n = mf + iy * jj; BZ_HALF(n); }
+    } else if (iy == 0) {                                     /* :565-583 */
+        for (int ii = 0; ii <= mx - 2; ii++) { const long n = mf + ix * ii; BZ_HALF(n); }
+        for (int ii = 1; ii <= mx - 2; ii++) { const long n = mf + ix * ii; BX_UPD(n); }
+        for (int ii = 0; ii <= mx - 2; ii++) { const long n = mf + ix * ii; BY_UPD(n); BZ_HALF(n); }
+    }
+#undef BZ_HALF
+#undef BX_UPD
+#undef BY_UPD
+#undef A1
+}
+/* radiation flags: fieldboundaries.F90:90-94 */
+static void radiation_flags(const orc_rank *r, int rad[3])
+{
+    rad[0] = 1 - r->P.periodicx; rad[1] = 1 - r->P.periodicy; rad[2] = 1 - r->P.periodicz;
+    if (rad[1] == 1) rad[2] = 1;
+    if (r->P.dim == 2) rad[2] = 0;                            /* the z call is #ifndef twoD (:287-291, 418-422) */
+}
+/* the `surface` part of bc_b2 (high faces) / bc_e2 (low faces); the ghost refresh that follows is orc_bc_fields */
+void orc_surface_b(orc_rank *r)
+{
+    float *ex = r->f[ORC_EX], *ey = r->f[ORC_EY], *ez = r->f[ORC_EZ];
+    float *bx = r->f[ORC_BX], *by = r->f[ORC_BY], *bz = r->f[ORC_BZ];
+    const long ix = 1, iy = r->mx, iz = r->P.dim == 3 ? (long)r->mx * r->my : 0;
+    const int mx = r->mx, my = r->my, mz = r->P.dim == 3 ? r->mz : 1, twod = r->P.dim == 2;
+    int rad[3]; radiation_flags(r, rad);
+    const float c = r->P.c;
+    if (rad[0]) surface(by, bz, bx, ey, ez, ex, iy, iz, ix, my, mz, mx, 1, c, twod);     /* :279-281 */
+    if (rad[1]) surface(bz, bx, by, ez, ex, ey, iz, ix, iy, mz, mx, my, 1, c, twod);     /* :283-285 */
+    if (rad[2]) surface(bx, by, bz, ex, ey, ez, ix, iy, iz, mx, my, mz, 1, c, twod);     /* :288-290 */
+}
+void orc_surface_e(orc_rank *r)
+{
+    float *ex = r->f[ORC_EX], *ey = r->f[ORC_EY], *ez = r->f[ORC_EZ];
+    float *bx = r->f[ORC_BX], *by = r->f[ORC_BY], *bz = r->f[ORC_BZ];
+    const long ix = 1, iy = r->mx, iz = r->P.dim == 3 ? (long)r->mx * r->my : 0;
+    const int mx = r->mx, my = r->my, mz = r->P.dim == 3 ? r->mz : 1, twod = r->P.dim == 2;
+    int rad[3]; radiation_flags(r, rad);
+    const float c = r->P.c; const long lot = (long)r->lot;
+    if (rad[0]) surface(ey, ez, ex, by, bz, bx, -iy, -iz, -ix, my, mz, mx, lot, c, twod);   /* :410-412 */
+    if (rad[1]) surface(ez, ex, ey, bz, bx, by, -iz, -ix, -iy, mz, mx, my, lot, c, twod);   /* :414-416 */
+    if (rad[2]) surface(ex, ey, ez, bx, by, bz, -ix, -iy, -iz, mx, my, mz, lot, c, twod);   /* :419-421 */
+}
+
+/* ------------------------------------------------------------------------- */
 /* exchange_current: fieldboundaries.F90:1768-2189                              */
 /* high ghosts m-g..m (g+1 layers) are ADDED into the +neighbour's g+1..nghost; */
 /* low ghosts 1..g are added into the -neighbour's m-nghost+1..m-g-1.           */
@@ -1254,8 +1336,10 @@ void orc_reorder_particles(orc_rank *r)
 
 /* ------------------------------------------------------------------------- */
 /* one lap: tristanmainloop.F90:107-344 (periodic / plain-open configurations;  */
-/* radiation `surface`, user hooks and injectors are outside this restatement)  */
+/* user hooks and injectors are in orc_step_shock; pre/post_bc_* edge fixes of an    */
+/* all-open box (fieldboundaries.F90:120,154,442,468) are outside this restatement) */
 /* ------------------------------------------------------------------------- */
+enum { PH_SURF_B = 100, PH_SURF_E };
 enum { PH_BC_B1, PH_BC_E1, PH_BHALF, PH_MOVE, PH_EFULL, PH_RESET, PH_DEPOSIT, PH_EXCH_P, PH_EXCH_CUR,
        PH_FILTER, PH_ADD_CUR, PH_INJECT_OTHERS, PH_REORDER };
 
@@ -1281,6 +1365,8 @@ void orc_step_phase(orc_world *w, int phase)
             case PH_ADD_CUR: orc_add_current(r); break;
             case PH_INJECT_OTHERS: orc_inject_others(r); break;
             case PH_REORDER: orc_reorder_particles(r); break;
+            case PH_SURF_B: orc_surface_b(r); break;
+            case PH_SURF_E: orc_surface_e(r); break;
             }
         }
     }
@@ -1296,9 +1382,11 @@ void orc_step(orc_world *w)
     orc_step_phase(w, PH_MOVE);           /* :134 */
     orc_step_phase(w, PH_BHALF);          /* :139 */
     orc_step_phase(w, PH_BC_B1);          /* :140 */
-    orc_step_phase(w, PH_BC_B1);          /* :145 bc_b2 == bc_b1 when no axis radiates */
+    orc_step_phase(w, PH_SURF_B);         /* :145 bc_b2 = surface on every radiating axis ... */
+    orc_step_phase(w, PH_BC_B1);          /*      ... then bc_b1 */
     orc_step_phase(w, PH_EFULL);          /* :159 */
-    orc_step_phase(w, PH_BC_E1);          /* :164 bc_e2 */
+    orc_step_phase(w, PH_SURF_E);         /* :164 bc_e2 = surface ... */
+    orc_step_phase(w, PH_BC_E1);          /*      ... then bc_e1 */
     orc_step_phase(w, PH_RESET);          /* :171 */
     orc_step_phase(w, PH_BC_E1);          /* :181 */
     orc_step_phase(w, PH_BC_B1);          /* :182 */
@@ -1588,11 +1676,12 @@ void orc_step_shock(orc_world *w, float leftwall, float binit, float btheta, flo
 #define FBC() for (int rk = 0; rk < n; rk++) orc_field_bc_shock(w->r[rk], leftwall, binit, btheta, bphi, beta)
     w->lap++;
     orc_step_phase(w, PH_BC_B1); orc_step_phase(w, PH_BC_E1); orc_step_phase(w, PH_BHALF); orc_step_phase(w, PH_BC_B1);
-    orc_step_phase(w, PH_MOVE); orc_step_phase(w, PH_BHALF); orc_step_phase(w, PH_BC_B1); orc_step_phase(w, PH_BC_B1);
+    orc_step_phase(w, PH_MOVE); orc_step_phase(w, PH_BHALF); orc_step_phase(w, PH_BC_B1);
+    orc_step_phase(w, PH_SURF_B); orc_step_phase(w, PH_BC_B1);   /* :145 bc_b2 (x radiates) */
     FBC();                                   /* :146 */
     orc_step_phase(w, PH_EFULL);
     FBC();                                   /* :160 */
-    orc_step_phase(w, PH_BC_E1);
+    orc_step_phase(w, PH_SURF_E); orc_step_phase(w, PH_BC_E1);   /* :164 bc_e2 */
     FBC();                                   /* :166 */
     orc_step_phase(w, PH_RESET);
     for (int rk = 0; rk < n; rk++) orc_particle_bc_wall(w->r[rk], leftwall);   /* :177 */

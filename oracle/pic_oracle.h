@@ -166,6 +166,10 @@ void orc_init_twostream(orc_world *w, float ppc0, float gamma0_in, float delgam,
 void orc_init_uniform(orc_world *w, float ppc0, float beta_drift, float uth, uint64_t seed);
 
 /* --- shock-problem user hooks (user/user_shock.F90) --- */
+/* radiation boundary `surface` of bc_b2 / bc_e2: fieldboundaries.F90:274-295, 403-426, 493-606 (per rank; the
+   ghost refresh that completes bc_b2 / bc_e2 is orc_bc_fields) */
+void orc_surface_b(orc_rank *r);
+void orc_surface_e(orc_rank *r);
 void orc_field_bc_shock(orc_rank *r, float leftwall, float binit, float btheta, float bphi, float beta);   /* :342-373 */
 void orc_particle_bc_wall(orc_rank *r, float leftwall);                                                     /* :377-457 */
 void orc_step_shock(orc_world *w, float leftwall, float binit, float btheta, float bphi, float beta);       /* lap with the hooks */

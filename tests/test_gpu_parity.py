@@ -64,6 +64,40 @@ def test_ghost_refresh_and_fold_bit_exact(tgm, dim, order):
     ctx.close()
 
 
+@pytest.mark.parametrize("dim,periodic", [(3, (0, 1, 1)), (3, (1, 0, 1)), (3, (0, 0, 0)), (2, (0, 1, 1)), (2, (1, 0, 1)), (2, (0, 0, 1))])
+def test_radiation_surface_bit_exact(tgm, dim, periodic):
+    """bc_b2 / bc_e2 with radiating axes: `surface` (fieldboundaries.F90:493-606) then the ghost refresh; bit-exact"""
+    w, ctx = make(tgm, dim=dim, order=1, n=(20, 18, 14), ppc=1.0, periodic=periodic)
+    r = w.ranks[0]
+    T.upload(ctx, r)
+    for _ in range(2):
+        ctx.bc_b2(); ctx.bc_e2()
+        w.phase(O.PH_SURF_B); w.phase(O.PH_BC_B1); w.phase(O.PH_SURF_E); w.phase(O.PH_BC_E1)
+    fg = ctx.fields_d2h()
+    for a in range(6):
+        assert np.array_equal(fg[a], r.arr(a)), O.ARR_NAMES[a]
+    ctx.close()
+
+
+@pytest.mark.parametrize("dim,order", [(3, 2), (2, 1)])
+def test_full_lap_open_x(tgm, dim, order):
+    """laps with an open (radiating) x axis: leavers are discarded, bc_b2 / bc_e2 run `surface`"""
+    w, ctx = make(tgm, dim=dim, order=order, n=(24, 16, 12), ppc=4.0, ntimes=2, filter_kind=1, periodic=(0, 1, 1))
+    r = w.ranks[0]
+    T.upload(ctx, r)
+    for lap in range(2):
+        ctx.step(1); w.step()
+        fg = ctx.fields_d2h()
+        for a in range(6):
+            assert T.max_rel(T.interior(r, fg[a]), T.interior(r, r.arr(a))) < 2e-4, (lap, O.ARR_NAMES[a])
+        pg_i, pg_e = T.gpu_particles(ctx)
+        po_i, po_e = T.oracle_particles(r)
+        T.assert_particles_close(pg_i, po_i, what=f"open-x ions lap {lap}")
+        T.assert_particles_close(pg_e, po_e, what=f"open-x electrons lap {lap}")
+        T.upload(ctx, r)                               # compare every lap from identical state
+    ctx.close()
+
+
 @pytest.mark.parametrize("dim,kind,ntimes", [(2, 1, 5), (3, 1, 3), (3, 2, 4), (3, 2, 7), (2, 2, 6)])
 def test_filters_bit_exact(tgm, dim, kind, ntimes):
     w, ctx = make(tgm, dim=dim, order=2, n=(20, 18, 14), ppc=1.0, ntimes=ntimes, filter_kind=kind)

@@ -300,3 +300,59 @@ def test_reflecting_wall_is_specular():
         n_hit += int(((before["u"] < 0) & (before["x"] < leftwall + 0.15)).sum())
         assert r.ions()["x"].min() >= leftwall - 1e-3 and r.lecs()["x"].min() >= leftwall - 1e-3
     assert n_hit > 5
+
+
+# ------------------------------------------------------------------ radiation boundary (bc_b2 / bc_e2 `surface`)
+def _pulse_energy(dim, periodic, axis, direction, absorb, laps=260):
+    """vacuum pulse travelling along `axis` (+1 / -1); returns interior field energy history relative to t = 0"""
+    n = {0: (64, 4, 4), 1: (4, 64, 4)}[axis] if dim == 3 else {0: (64, 4, 1), 1: (4, 64, 1)}[axis]
+    w = T.oracle_world(dim=dim, order=1, n=n, ppc=0.0, init="none", seed_fields=0, periodic=periodic)
+    r = w.ranks[0]
+    m = (r.mx, r.my)[axis]
+    s = np.arange(m)
+    f = lambda x: np.exp(-((x - 30.0) / 5.0) ** 2)
+    shape = [1, 1, 1]; shape[2 - axis] = m
+    # +axis-going vacuum wave on the Yee mesh: (Ey, Bz) for x, (Ez, Bx) for y; B is staggered by +1/2 along the axis
+    e_arr, b_arr = (O.EY, O.BZ) if axis == 0 else (O.EZ, O.BX)
+    r.arr(e_arr)[...] = f(s).reshape(shape).astype(np.float32)
+    r.arr(b_arr)[...] = (direction * f(s + 0.5)).reshape(shape).astype(np.float32)
+
+    def energy():
+        g, gz = r.nghost // 2, r.nghostz // 2
+        tot = 0.0
+        for a in range(6):
+            A = r.arr(a).astype(np.float64)
+            sl = [slice(None)] * 3
+            for ax, (mm, gg) in enumerate(((r.mx, g), (r.my, g), (r.mz, gz))):
+                if ax != axis and mm > 1:
+                    sl[2 - ax] = slice(gg, mm - gg - 1)       # periodic axes: interior only (ghost index m is never refreshed)
+            tot += float((A[tuple(sl)] ** 2).sum())
+        return tot
+
+    e0 = energy()
+    seq = [O.PH_BC_B1, O.PH_BC_E1, O.PH_BHALF, O.PH_BC_B1, O.PH_BHALF, O.PH_BC_B1]
+    seq += ([O.PH_SURF_B] if absorb else []) + [O.PH_BC_B1, O.PH_EFULL] + ([O.PH_SURF_E] if absorb else []) + [O.PH_BC_E1]
+    hist = []
+    for lap in range(laps):
+        for ph in seq:
+            w.phase(ph)
+        hist.append(energy() / e0)
+    return np.array(hist)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("direction", [1, -1])
+def test_radiation_boundary_absorbs_a_normally_incident_pulse(dim, direction):
+    """`surface` (fieldboundaries.F90:493-606) known answer: a plane pulse that hits the open x faces at normal incidence
+    leaves the box (high face: bc_b2, low face: bc_e2); without it the same faces reflect everything."""
+    h = _pulse_energy(dim, (0, 1, 1), 0, direction, absorb=True)
+    assert h[:20].min() > 0.97                      # nothing happens before the pulse reaches the face
+    assert h[-1] < 1e-3, h[-1]                      # > 99.9 % of the energy has left
+    h0 = _pulse_energy(dim, (0, 1, 1), 0, direction, absorb=False)
+    assert h0[-1] > 0.9                             # plain open faces (bc_b1 only) reflect
+
+
+def test_radiation_boundary_y_faces_3d():
+    """open y in 3D also switches the z faces to radiating (fieldboundaries.F90:94); a y-going pulse is absorbed"""
+    h = _pulse_energy(3, (1, 0, 1), 1, 1, absorb=True)
+    assert h[-1] < 1e-3, h[-1]

@@ -259,8 +259,19 @@ extern "C" int tgpu_reset_currents(tgpu_ctx *h) { ENTER(h); PhaseTimer t(h, TGPU
 extern "C" int tgpu_add_current(tgpu_ctx *h) { ENTER(h); PhaseTimer t(h, TGPU_PH_FIELDS); return fld_add(h); }
 extern "C" int tgpu_bc_b1(tgpu_ctx *h) { ENTER(h); PhaseTimer t(h, TGPU_PH_BC); return fld_bc(h, 3); }
 extern "C" int tgpu_bc_e1(tgpu_ctx *h) { ENTER(h); PhaseTimer t(h, TGPU_PH_BC); return fld_bc(h, 0); }
-extern "C" int tgpu_bc_b2(tgpu_ctx *h) { return tgpu_bc_b1(h); }
-extern "C" int tgpu_bc_e2(tgpu_ctx *h) { return tgpu_bc_e1(h); }
+// bc_b2 / bc_e2 = radiation `surface` on every radiating axis (no launch when all axes are periodic), then bc_b1 / bc_e1
+extern "C" int tgpu_bc_b2(tgpu_ctx *h)
+{
+    ENTER(h);
+    { PhaseTimer t(h, TGPU_PH_BC); int rc = fld_surface(h, 0); if (rc) return rc; }
+    return tgpu_bc_b1(h);
+}
+extern "C" int tgpu_bc_e2(tgpu_ctx *h)
+{
+    ENTER(h);
+    { PhaseTimer t(h, TGPU_PH_BC); int rc = fld_surface(h, 1); if (rc) return rc; }
+    return tgpu_bc_e1(h);
+}
 extern "C" int tgpu_exchange_current(tgpu_ctx *h) { ENTER(h); PhaseTimer t(h, TGPU_PH_CUREXCH); return fld_fold(h); }
 extern "C" int tgpu_apply_filter1_opt(tgpu_ctx *h) { ENTER(h); PhaseTimer t(h, TGPU_PH_FILTER); return fld_filter1(h); }
 extern "C" int tgpu_apply_filter2_opt(tgpu_ctx *h) { ENTER(h); PhaseTimer t(h, TGPU_PH_FILTER); return fld_filter2(h); }
@@ -344,6 +355,8 @@ extern "C" int tgpu_step(tgpu_ctx *h, int nlaps)
     // on nothing the field phase does (and vice versa), so it runs on stream_prt while B-half/E-full/fold/filter/add run
     // on stream_main.  Needs the fused mover (keys in hand) and is skipped while per-phase timing is on.
     const bool overlap = h->opt_overlap && h->opt_fused && cellrun_supported(h) && !h->timing;
+    // bc_b2 / bc_e2 differ from bc_b1 / bc_e1 only when an axis radiates (fieldboundaries.F90:90-94, 274-295, 403-426)
+    const bool rad = !h->P.periodicx || !h->P.periodicy || (h->P.dim == 3 && !h->P.periodicz);
     h->in_step = 1;
     for (int l = 0; l < nlaps && h->hook_kind == 1; l++) {
         // shock problem: the reflecting wall edits particles between the mover and the deposit, so the mover is not fused
@@ -377,7 +390,9 @@ extern "C" int tgpu_step(tgpu_ctx *h, int nlaps)
             CK(cudaEventRecord(h->ev_move, h->stream_main));
             DO(tgpu_advance_b_halfstep(h));    // :139
             DO(tgpu_bc_b1(h));                 // :140
+            if (rad) DO(tgpu_bc_b2(h));        // :145
             DO(tgpu_advance_e_fullstep(h));    // :159
+            if (rad) DO(tgpu_bc_e2(h));        // :164
             DO(tgpu_reset_currents(h));        // :171
             DO(fld_add_shadow(h)); h->fused_pending = 0;      // :183, current part of deposit_particles
             DO(tgpu_exchange_current(h));      // :203
@@ -395,7 +410,9 @@ extern "C" int tgpu_step(tgpu_ctx *h, int nlaps)
         } else {
             DO(tgpu_advance_b_halfstep(h));    // :139
             DO(tgpu_bc_b1(h));                 // :140
+            if (rad) DO(tgpu_bc_b2(h));        // :145
             DO(tgpu_advance_e_fullstep(h));    // :159
+            if (rad) DO(tgpu_bc_e2(h));        // :164
             DO(tgpu_reset_currents(h));        // :171
             DO(tgpu_deposit_particles(h));     // :183
             DO(tgpu_exchange_particles(h));    // :190, :257-272

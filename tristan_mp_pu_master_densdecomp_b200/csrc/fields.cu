@@ -475,25 +475,31 @@ __global__ void __launch_bounds__(512) k_filter2(float *__restrict__ cur, const 
     const int nlines = f.q_n[0] * f.q_n[1];
     const int line0 = blockIdx.x * NL;
     const int nthr = blockDim.x;
-    for (int t = threadIdx.x; t < L * NL; t += nthr) {
-        int p, ln;
-        if (f.axis == 0) { p = t % L; ln = t / L; } else { ln = t % NL; p = t / NL; }
-        int line = line0 + ln;
-        float v = 0.f;
-        if (line < nlines) {
-            int q1 = line % f.q_n[0], q2 = line / f.q_n[0];
-            int pc = p - f.nt;                      // cell offset relative to str
-            if (pc < 0) {
-                if (f.lowmode == 0) v = cur[f2_addr(f, f.str + f.ncell + pc, q1, q2)];
-                else if (f.lowmode == 1) v = halo_lo[(size_t)p + (size_t)f.nt * line];
-                else v = cur[f2_addr(f, f.str, q1, q2)];
-            } else if (pc >= f.ncell) {
-                if (f.highmode == 0) v = cur[f2_addr(f, f.str + pc - f.ncell, q1, q2)];
-                else if (f.highmode == 1) v = halo_hi[(size_t)(pc - f.ncell) + (size_t)f.nt * line];
-                else v = cur[f2_addr(f, f.str + f.ncell - 1, q1, q2)];
-            } else v = cur[f2_addr(f, f.str + pc, q1, q2)];
+    // Load/store index arithmetic without per-element divisions: a line's (q1, q2) and base address are computed once.
+    //   axis 0: the line is contiguous in memory -> one warp per line, lanes along the line;
+    //   axis 1, 2: consecutive lines are consecutive in x -> a thread keeps one line (NL is a power of two) and walks p.
+    const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5, nwarps_ = blockDim.x >> 5;
+    int ln_first, ln_step, p_first, p_step;
+    if (f.axis == 0) { ln_first = warp_; ln_step = nwarps_; p_first = lane_; p_step = 32; }
+    else { ln_first = threadIdx.x & (NL - 1); ln_step = NL; p_first = threadIdx.x / NL; p_step = nthr / NL; }
+    const size_t pstride = f.axis == 0 ? 1 : f.axis == 1 ? (size_t)f.mx : (size_t)f.mx * f.my;
+    for (int ln = ln_first; ln < NL; ln += ln_step) {
+        const int line = line0 + ln;
+        float *trow = tile + ln * Lp;
+        if (line >= nlines) { for (int p = p_first; p < L; p += p_step) trow[p] = 0.f; continue; }
+        const int q1 = line % f.q_n[0], q2 = line / f.q_n[0];
+        const float *cbase = cur + f2_addr(f, f.str, q1, q2);            // cell `str` of this line
+        const float *hl_ = halo_lo + (size_t)f.nt * line, *hh_ = halo_hi + (size_t)f.nt * line;
+        for (int p = p_first; p < L; p += p_step) {
+            const int pc = p - f.nt;                                     // cell offset relative to str
+            float v;
+            if (pc < 0) v = f.lowmode == 0 ? cbase[(size_t)(f.ncell + pc) * pstride] : f.lowmode == 1 ? hl_[p] : cbase[0];
+            else if (pc >= f.ncell)
+                v = f.highmode == 0 ? cbase[(size_t)(pc - f.ncell) * pstride] : f.highmode == 1 ? hh_[pc - f.ncell]
+                                                                                             : cbase[(size_t)(f.ncell - 1) * pstride];
+            else v = cbase[(size_t)pc * pstride];
+            trow[p] = v;
         }
-        tile[ln * Lp + p] = v;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -521,14 +527,13 @@ __global__ void __launch_bounds__(512) k_filter2(float *__restrict__ cur, const 
         for (int r = 0; r < R; r++) if (p0 + r < L) row[r] = v[r];
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < f.ncell * NL; t += nthr) {
-        int p, l2;
-        if (f.axis == 0) { p = t % f.ncell; l2 = t / f.ncell; } else { l2 = t % NL; p = t / NL; }
-        int line = line0 + l2;
-        if (line < nlines) {
-            int q1 = line % f.q_n[0], q2 = line / f.q_n[0];
-            cur[f2_addr(f, f.str + p, q1, q2)] = tile[l2 * Lp + p + f.nt];
-        }
+    for (int ln = ln_first; ln < NL; ln += ln_step) {
+        const int line = line0 + ln;
+        if (line >= nlines) continue;
+        const int q1 = line % f.q_n[0], q2 = line / f.q_n[0];
+        float *cbase = cur + f2_addr(f, f.str, q1, q2);
+        const float *trow = tile + ln * Lp + f.nt;
+        for (int p = p_first; p < f.ncell; p += p_step) cbase[(size_t)p * pstride] = trow[p];
     }
 }
 
@@ -606,6 +611,100 @@ int fld_filter2(tgpu_ctx *h)
         }
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Radiation boundary `surface` (fieldboundaries.F90:493-606): the Lindman-type absorbing face that bc_b2 (:274-295) applies
+// to the high face of every radiating axis and bc_e2 (:403-426) to the low face, with mirrored strides and E <-> B.
+// Arguments keep the reference's meaning (rotated components b1,b2,b3 / e1,e2,e3, strides s1,s2,s3 with s3 normal to the
+// face, 1-based first element m00).  The reference sweeps rows then columns; its data flow is
+//   (1) b3 += h over the face, (2) b1 and b2 from that b3, (3) b3 += h again,   h = c/2 * curl_3(e),
+// so two launches suffice: k_surface_b12 recomputes b3 + h locally (for the point and its two lower neighbours, same
+// expression -> same bits) and writes only b1, b2; k_surface_b3 then applies the two half updates.  The twoD variants of the
+// reference (:540-583, one stride zero) are the same formulas with a one-point range on the degenerate axis.
+// ---------------------------------------------------------------------------------------------
+struct SurfArgs {
+    float *b1, *b2, *b3; const float *e1, *e2, *e3;
+    long long s1, s2, s3, mf;       // strides; mf = 1-based index of the first face element
+    int n1, n2;                     // points along s1, s2 that receive the b3 update
+    int b1_first, b2_first;         // first index along s1 (s2) that receives the b1 (b2) update
+    float c, rs, s, os;
+};
+#define SF(a, n) (a)[(n) - 1]
+__device__ __forceinline__ float surf_h(const SurfArgs &A, long long n)
+{
+    return .5f * A.c * (SF(A.e1, n + A.s2) - SF(A.e1, n) - SF(A.e2, n + A.s1) + SF(A.e2, n));
+}
+__global__ void __launch_bounds__(256) k_surface_b12(SurfArgs A)
+{
+    const int ii = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y;
+    if (ii >= A.n1) return;
+    const long long n = A.mf + A.s1 * ii + A.s2 * jj;
+    const float bz_n = SF(A.b3, n) + surf_h(A, n);
+    if (ii >= A.b1_first) {
+        const float bz_m = SF(A.b3, n - A.s1) + surf_h(A, n - A.s1);
+        SF(A.b1, n) = SF(A.b1, n) + A.rs * (SF(A.b1, n - A.s3) - SF(A.b1, n) + A.s * (bz_n - bz_m))
+                      - A.os * (SF(A.e3, n + A.s2) - SF(A.e3, n)) - (A.os - A.c) * (SF(A.e3, n + A.s2 - A.s3) - SF(A.e3, n - A.s3))
+                      - A.c * (SF(A.e2, n) - SF(A.e2, n - A.s3));
+    }
+    if (jj >= A.b2_first) {
+        const float bz_m = SF(A.b3, n - A.s2) + surf_h(A, n - A.s2);
+        SF(A.b2, n) = SF(A.b2, n) + A.rs * (SF(A.b2, n - A.s3) - SF(A.b2, n) + A.s * (bz_n - bz_m))
+                      + A.os * (SF(A.e3, n + A.s1) - SF(A.e3, n)) + (A.os - A.c) * (SF(A.e3, n + A.s1 - A.s3) - SF(A.e3, n - A.s3))
+                      + A.c * (SF(A.e1, n) - SF(A.e1, n - A.s3));
+    }
+}
+__global__ void __launch_bounds__(256) k_surface_b3(SurfArgs A)
+{
+    const int ii = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y;
+    if (ii >= A.n1) return;
+    const long long n = A.mf + A.s1 * ii + A.s2 * jj;
+    const float hh = surf_h(A, n);
+    SF(A.b3, n) = (SF(A.b3, n) + hh) + hh;
+}
+#undef SF
+static int surface_face(tgpu_ctx *h, float *b1, float *b2, float *b3, const float *e1, const float *e2, const float *e3,
+                        long long s1, long long s2, long long s3, int m1, int m2, int m3, long long m00)
+{
+    SurfArgs A;
+    A.b1 = b1; A.b2 = b2; A.b3 = b3; A.e1 = e1; A.e2 = e2; A.e3 = e3; A.s1 = s1; A.s2 = s2; A.s3 = s3;
+    A.mf = m00 + s3 * (m3 - 1);
+    A.c = h->P.c; A.rs = 2.f * A.c / (1.f + A.c); A.s = .4142136f; A.os = .5f * (1.f - A.s) * A.rs;
+    A.n1 = m1 - 1; A.n2 = m2 - 1; A.b1_first = 1; A.b2_first = 1;
+    if (h->P.dim == 2) {
+        if (s1 == 0) { A.n1 = 1; A.b1_first = 0; }            // fieldboundaries.F90:540-560
+        else if (s2 == 0) { A.n2 = 1; A.b2_first = 0; }       // :565-583
+        else return 0;
+    }
+    if (A.n1 <= 0 || A.n2 <= 0) return 0;
+    dim3 grid((A.n1 + 255) / 256, A.n2);
+    k_surface_b12<<<grid, 256, 0, h->stream>>>(A); CKK(h);
+    k_surface_b3<<<grid, 256, 0, h->stream>>>(A); CKK(h);
+    return 0;
+}
+// is_e = 0: the `surface` calls of bc_b2; 1: those of bc_e2
+int fld_surface(tgpu_ctx *h, int is_e)
+{
+    const tgpu_params &P = h->P;
+    int rad[3] = {1 - P.periodicx, 1 - P.periodicy, 1 - P.periodicz};                 // fieldboundaries.F90:90-94
+    if (rad[1] == 1) rad[2] = 1;
+    if (P.dim == 2) rad[2] = 0;                                                       // the z call is #ifndef twoD
+    if (!rad[0] && !rad[1] && !rad[2]) return 0;
+    float *ex = h->f[0], *ey = h->f[1], *ez = h->f[2], *bx = h->f[3], *by = h->f[4], *bz = h->f[5];
+    const long long ix = 1, iy = P.mx, iz = P.dim == 3 ? (long long)P.mx * P.my : 0, lot = h->G.lot;
+    const int mx = P.mx, my = P.my, mz = P.dim == 3 ? P.mz : 1;
+    int rc = 0;
+    if (!is_e) {
+        if (rad[0]) rc |= surface_face(h, by, bz, bx, ey, ez, ex, iy, iz, ix, my, mz, mx, 1);
+        if (rad[1]) rc |= surface_face(h, bz, bx, by, ez, ex, ey, iz, ix, iy, mz, mx, my, 1);
+        if (rad[2]) rc |= surface_face(h, bx, by, bz, ex, ey, ez, ix, iy, iz, mx, my, mz, 1);
+    } else {
+        if (rad[0]) rc |= surface_face(h, ey, ez, ex, by, bz, bx, -iy, -iz, -ix, my, mz, mx, lot);
+        if (rad[1]) rc |= surface_face(h, ez, ex, ey, bz, bx, by, -iz, -ix, -iy, mz, mx, my, lot);
+        if (rad[2]) rc |= surface_face(h, ex, ey, ez, bx, by, bz, -ix, -iy, -iz, mx, my, mz, lot);
+    }
+    h->need_prim = 1;
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------

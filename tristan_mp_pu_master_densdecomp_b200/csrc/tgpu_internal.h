@@ -101,6 +101,7 @@ int fld_fold(tgpu_ctx *h);
 int fld_filter1(tgpu_ctx *h);
 int fld_filter2(tgpu_ctx *h);
 int fld_add_shadow(tgpu_ctx *h);
+int fld_surface(tgpu_ctx *h, int is_e);     // radiation `surface` of bc_b2 (0) / bc_e2 (1)
 int fld_bc_shock(tgpu_ctx *h, float leftwall, float binit, float btheta, float bphi, float beta);
 // particles.cu
 int prt_h2d(tgpu_ctx *h, const tgpu_particle *p, int ions, int lecs);
