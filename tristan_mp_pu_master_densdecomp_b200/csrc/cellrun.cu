@@ -220,20 +220,6 @@ __device__ __forceinline__ void flush_one(float *cx, float *cy, float *cz, size_
     }
 }
 
-// Address of the lane's row (J, K) (0-based) at x-plane i0 (0-based).
-//   TILED = false: the reference's Fortran-order arrays, element i0 + mx*(J + my*K); consecutive planes are 1 apart.
-//   TILED = true : the shadow arrays of the fused mover.  The 16 lanes of a half-warp flush one x-plane of the 4x4 (y,z)
-//     footprint; in Fortran order that is 16 different cache lines per RED instruction.  The shadow arrays therefore keep
-//     every 4x4 (y,z) tile of an x-plane contiguous (64 B): element ((tz*nty + ty)*mx + i0)*16 + (K&3)*4 + (J&3), so a flush
-//     touches at most 2x2 tiles (<= 4 short segments) and consecutive planes are 16 apart.  k_add_shadow_tiled (fields.cu)
-//     folds them back into curx/cury/curz.
-template <bool TILED>
-__device__ __forceinline__ size_t row_index(int mx, int my, int nty, int J, int K, int i0)
-{
-    if (TILED) return ((size_t)(((K >> 2) * nty + (J >> 2)) * (long long)mx + i0) << 4) + (size_t)(((K & 3) << 2) | (J & 3));
-    return (size_t)((long long)mx * (J + (long long)my * K) + i0);
-}
-
 // same classification as k_classify_key (particles.cu), on a copy of the position
 __device__ __forceinline__ uint32_t sort_key(const DevGeom &G, float x, float y, float z)
 {

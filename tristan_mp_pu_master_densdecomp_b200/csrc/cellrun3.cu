@@ -8,8 +8,9 @@
 // (slot 1 or 6 in both y and z) only receive charge from a particle that changes cell in y AND z in the same step;
 // that particle's own lane deposits its single corner row with plain atomics in phase 1.
 // The six x-planes form a ring: plane t of the window that starts at cell wi-2 lives in register (wi-2+t) mod 6, so
-// sliding along x flushes and clears registers without moving any; the accumulate code is instantiated for the six
-// rotations and selected with one uniform switch per particle.
+// sliding along x flushes and clears registers without moving any.  Phase 1 stores each particle's x factors already
+// rotated into ring order (component m of the staged vectors belongs to the cell congruent to m mod 6), so phase 2 is one
+// fixed sequence of 15 packed FMAs (FFMA2, register pairs (0,1) (2,3) (4,5)) with no rotation switch.
 #include "tgpu_internal.h"
 #include "shapes.cuh"
 
@@ -20,10 +21,13 @@
 struct C3Args {
     Species s;
     long long n;
-    float *cx, *cy, *cz;
+    float *cx, *cy, *cz;     // the tiled shadow arrays (tgpu_internal.h row_index) when TGPU_SHADOW_TILED, else curx..curz
+    int nty;
     DevGeom G;
     float qs;
 };
+#define C3_TILED (TGPU_SHADOW_TILED != 0)
+#define C3_PS (C3_TILED ? 16 : 1)          // distance between consecutive x-planes of a row
 
 // cubic B-spline weights on slots 2..5 (particles.F90:1175-1188); W6[0..5] <-> slots 1..6 of the cell `base`,
 // for a particle whose own cell is base + shift
@@ -50,21 +54,15 @@ __device__ __forceinline__ void shape6(float d, int shift, float W6[6])
     W6[5] = shift > 0 ? s5 : 0.f;
 }
 
+__device__ __forceinline__ void red_nz3(float *p, float v)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %1, 0f00000000;\n\t@p red.global.add.f32 [%0], %1;\n\t}"
+                 :: "l"(p), "f"(v) : "memory");
+}
 __device__ __forceinline__ void red3c(float *cx, float *cy, float *cz, size_t idx, float vx, float vy, float vz)
 {
-    if (vx != 0.f) atomicAdd(cx + idx, vx);
-    if (vy != 0.f) atomicAdd(cy + idx, vy);
-    if (vz != 0.f) atomicAdd(cz + idx, vz);
+    red_nz3(cx + idx, vx); red_nz3(cy + idx, vy); red_nz3(cz + idx, vz);
 }
-
-// accumulate one particle into the ring, logical plane s -> register (R + s) % 6
-#define C3_ACC1(m, s)                                                                 \
-    ax[m] = fmaf(XQ[s], wx, ax[m]);                                                   \
-    ay[m] = fmaf(XAv[s], a, fmaf(XBv[s], b, ay[m]));                                  \
-    az[m] = fmaf(XAv[s], c, fmaf(XBv[s], d, az[m]));
-#define C3_ACC(R)                                                                     \
-    C3_ACC1((R + 0) % 6, 0) C3_ACC1((R + 1) % 6, 1) C3_ACC1((R + 2) % 6, 2)           \
-    C3_ACC1((R + 3) % 6, 3) C3_ACC1((R + 4) % 6, 4) C3_ACC1((R + 5) % 6, 5)
 
 __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
 {
@@ -78,7 +76,6 @@ __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
     // lane -> one of the 32 non-corner rows of the 6x6 (j,k) footprint
     const int nrow = lane < 4 ? lane + 1 : lane < 28 ? lane + 2 : lane + 3;
     const int j = nrow % 6, k = nrow / 6;
-    const int loff = (j - 2) + my * (k - 2);
     float *wst = stage3 + (size_t)warp * 32 * C3_STRIDE;
 
     int wi = 0, wrow = 0, rot = 0;
@@ -97,17 +94,21 @@ __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
             const float x1 = x - u * invgam * G.c, y1 = y - v * invgam * G.c, z1 = z - w * invgam * G.c;
             const int i1 = (int)x1, j1 = (int)y1, k1 = (int)z1;
             const int shi = (int)x - i1, shj = (int)y - j1, shk = (int)z - k1;
-            ci = i1; crow = (j1 - 1) + my * (k1 - 1);
+            ci = i1; crow = (j1 - 1) | ((k1 - 1) << 16);
             const float third = 1.f / 3.f;
             float S1[6], S2[6], dSy[6], dSz[6], XB6[6], qPSx[6], qPSy[6], qPSz[6];
             shape6(x1 - i1, 0, S1); shape6(x - (int)x, shi, S2);
             {
+                // ring order: the factor of logical plane s (cell i1-2+s) goes to component (i1-2+s) mod 6
+                int m = (i1 - 2) % 6; m = m < 0 ? m + 6 : m;
                 float ps = 0.f;
 #pragma unroll
                 for (int s = 0; s < 6; s++) {
                     const float dS = S2[s] - S1[s];
                     ps = ps + dS; qPSx[s] = q * ps;
-                    st[s] = qPSx[s]; st[6 + s] = S1[s] + 0.5f * dS; XB6[s] = 0.5f * S1[s] + third * dS; st[12 + s] = XB6[s];
+                    XB6[s] = 0.5f * S1[s] + third * dS;
+                    st[m] = qPSx[s]; st[6 + m] = S1[s] + 0.5f * dS; st[12 + m] = XB6[s];
+                    m = m == 5 ? 0 : m + 1;
                 }
                 st[18] = 0.f; st[19] = 0.f;
             }
@@ -134,10 +135,10 @@ __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
                 const int jc = shj < 0 ? 0 : 5, kc = shk < 0 ? 0 : 5;
                 const float dy = jc ? dSy[5] : dSy[0], dz = kc ? dSz[5] : dSz[0];
                 const float py = jc ? qPSy[5] : qPSy[0], pz = kc ? qPSz[5] : qPSz[0];
-                const size_t idx0 = (size_t)((long long)mx * (crow + (jc - 2) + my * (kc - 2)) + (i1 - 3));
+                const size_t idx0 = row_index<C3_TILED>(mx, my, A.nty, (j1 - 1) + jc - 2, (k1 - 1) + kc - 2, i1 - 3);
                 const float wxc = third * dy * dz;
 #pragma unroll
-                for (int s = 0; s < 6; s++) red3c(A.cx, A.cy, A.cz, idx0 + s, qPSx[s] * wxc, py * (XB6[s] * dz), pz * (XB6[s] * dy));
+                for (int s = 0; s < 6; s++) red3c(A.cx, A.cy, A.cz, idx0 + (size_t)(s * C3_PS), qPSx[s] * wxc, py * (XB6[s] * dz), pz * (XB6[s] * dy));
             }
         }
         const int pci = __shfl_up_sync(0xffffffffu, ci, 1), pcrow = __shfl_up_sync(0xffffffffu, crow, 1);
@@ -151,13 +152,25 @@ __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
                 const int ni = __float_as_int(sp[23]), nrw = __float_as_int(sp[47]);
                 if (!have || ni != wi || nrw != wrow) {
                     if (have) {
-                        const size_t idx0 = (size_t)((long long)mx * (wrow + loff) + (wi - 3));
+                        const size_t idx0 = row_index<C3_TILED>(mx, my, A.nty, (wrow & 0xFFFF) + j - 2, (wrow >> 16) + k - 2, wi - 3);
                         const int di = ni - wi;
-                        const int nplanes = (nrw == wrow && di > 0 && di < 6) ? di : 6;
+                        if (nrw == wrow && di == 1) {
+                            // the common case in sorted order: the window slides one cell, plane 0 (register rot) is complete;
+                            // rot is uniform across the warp, so this is one short non-divergent case
+                            float *px = A.cx + idx0, *py = A.cy + idx0, *pz = A.cz + idx0;
+                            switch (rot) {
+#define C3_FL(q) case q: red_nz3(px, ax[q]); red_nz3(py, ay[q]); red_nz3(pz, az[q]); ax[q] = 0.f; ay[q] = 0.f; az[q] = 0.f; break;
+                            C3_FL(0) C3_FL(1) C3_FL(2) C3_FL(3) C3_FL(4)
+                            default: red_nz3(px, ax[5]); red_nz3(py, ay[5]); red_nz3(pz, az[5]); ax[5] = 0.f; ay[5] = 0.f; az[5] = 0.f; break;
+#undef C3_FL
+                            }
+                        } else {
+                            const int nplanes = (nrw == wrow && di > 0 && di < 6) ? di : 6;
 #pragma unroll
-                        for (int m = 0; m < 6; m++) {
-                            int tp = m - rot; tp = tp < 0 ? tp + 6 : tp;          // plane held by register m
-                            if (tp < nplanes) { red3c(A.cx, A.cy, A.cz, idx0 + tp, ax[m], ay[m], az[m]); ax[m] = 0.f; ay[m] = 0.f; az[m] = 0.f; }
+                            for (int m = 0; m < 6; m++) {
+                                int tp = m - rot; tp = tp < 0 ? tp + 6 : tp;          // plane held by register m
+                                if (tp < nplanes) { red3c(A.cx, A.cy, A.cz, idx0 + (size_t)(tp * C3_PS), ax[m], ay[m], az[m]); ax[m] = 0.f; ay[m] = 0.f; az[m] = 0.f; }
+                            }
                         }
                     }
                     wi = ni; wrow = nrw; have = true;
@@ -167,35 +180,42 @@ __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
             const float4 x0 = *(const float4 *)(sp + 0), x1v = *(const float4 *)(sp + 4), x2v = *(const float4 *)(sp + 8),
                          x3 = *(const float4 *)(sp + 12), x4 = *(const float4 *)(sp + 16);
             const float4 yv = *(const float4 *)(sp + 20 + 4 * j), zv = *(const float4 *)(sp + 44 + 4 * k);
-            const float XQ[6] = {x0.x, x0.y, x0.z, x0.w, x1v.x, x1v.y};
-            const float XAv[6] = {x1v.z, x1v.w, x2v.x, x2v.y, x2v.z, x2v.w};
-            const float XBv[6] = {x3.x, x3.y, x3.z, x3.w, x4.x, x4.y};
             const float sy1 = yv.x, dsy = yv.y, qpsy = yv.z, sz1 = zv.x, dsz = zv.y, qpsz = zv.z;
             const float ya = fmaf(0.5f, dsy, sy1), yb = fmaf(1.f / 3.f, dsy, 0.5f * sy1);
             const float wx = fmaf(yb, dsz, ya * sz1);
             const float a = qpsy * sz1, b = qpsy * dsz, c = qpsz * sy1, d = qpsz * dsy;
-            switch (rot) {
-            case 0: C3_ACC(0) break;
-            case 1: C3_ACC(1) break;
-            case 2: C3_ACC(2) break;
-            case 3: C3_ACC(3) break;
-            case 4: C3_ACC(4) break;
-            default: C3_ACC(5) break;
-            }
+            // staged vectors are in ring order: XQ = (x0, x1v.xy), XA = (x1v.zw, x2v), XB = (x3, x4.xy)
+            const float2 w2 = make_float2(wx, wx), a2 = make_float2(a, a), b2 = make_float2(b, b), c2 = make_float2(c, c),
+                         d2 = make_float2(d, d);
+            const float2 q01 = make_float2(x0.x, x0.y), q23 = make_float2(x0.z, x0.w), q45 = make_float2(x1v.x, x1v.y);
+            const float2 A01 = make_float2(x1v.z, x1v.w), A23 = make_float2(x2v.x, x2v.y), A45 = make_float2(x2v.z, x2v.w);
+            const float2 B01 = make_float2(x3.x, x3.y), B23 = make_float2(x3.z, x3.w), B45 = make_float2(x4.x, x4.y);
+            float2 t2;
+#define C3_P(acc, m, expr) t2 = expr; acc[m] = t2.x; acc[m + 1] = t2.y;
+            C3_P(ax, 0, __ffma2_rn(q01, w2, make_float2(ax[0], ax[1])))
+            C3_P(ax, 2, __ffma2_rn(q23, w2, make_float2(ax[2], ax[3])))
+            C3_P(ax, 4, __ffma2_rn(q45, w2, make_float2(ax[4], ax[5])))
+            C3_P(ay, 0, __ffma2_rn(A01, a2, __ffma2_rn(B01, b2, make_float2(ay[0], ay[1]))))
+            C3_P(ay, 2, __ffma2_rn(A23, a2, __ffma2_rn(B23, b2, make_float2(ay[2], ay[3]))))
+            C3_P(ay, 4, __ffma2_rn(A45, a2, __ffma2_rn(B45, b2, make_float2(ay[4], ay[5]))))
+            C3_P(az, 0, __ffma2_rn(A01, c2, __ffma2_rn(B01, d2, make_float2(az[0], az[1]))))
+            C3_P(az, 2, __ffma2_rn(A23, c2, __ffma2_rn(B23, d2, make_float2(az[2], az[3]))))
+            C3_P(az, 4, __ffma2_rn(A45, c2, __ffma2_rn(B45, d2, make_float2(az[4], az[5]))))
+#undef C3_P
         }
         __syncwarp();
     }
     if (have) {
-        const size_t idx0 = (size_t)((long long)mx * (wrow + loff) + (wi - 3));
+        const size_t idx0 = row_index<C3_TILED>(mx, my, A.nty, (wrow & 0xFFFF) + j - 2, (wrow >> 16) + k - 2, wi - 3);
 #pragma unroll
         for (int m = 0; m < 6; m++) {
             int tp = m - rot; tp = tp < 0 ? tp + 6 : tp;
-            red3c(A.cx, A.cy, A.cz, idx0 + tp, ax[m], ay[m], az[m]);
+            red3c(A.cx, A.cy, A.cz, idx0 + (size_t)(tp * C3_PS), ax[m], ay[m], az[m]);
         }
     }
 }
 
-int cellrun3_supported(const tgpu_ctx *h) { return h->P.dim == 3 && h->P.order == 3; }
+int cellrun3_supported(const tgpu_ctx *h) { return h->P.dim == 3 && h->P.order == 3 && h->P.my < 65536 && h->P.mz < 32768; }
 
 // tgpu_deposit_particles fast path for -Ddd3 (currents only; wrap / compaction / sort follow in prt_sort)
 int cellrun3_deposit(tgpu_ctx *h)
@@ -207,11 +227,14 @@ int cellrun3_deposit(tgpu_ctx *h)
         Species &S = h->sp[s];
         if (S.n == 0) continue;
         C3Args A;
-        A.s = S; A.n = S.n; A.cx = h->f[6]; A.cy = h->f[7]; A.cz = h->f[8]; A.G = h->G; A.qs = s ? h->P.qe : h->P.qi;
+        A.s = S; A.n = S.n; A.G = h->G; A.qs = s ? h->P.qe : h->P.qi; A.nty = h->nty;
+        // deposits go to the shadow arrays (tiled: a flush touches a few 64 B tile rows instead of 32 cache lines) and
+        // are folded into curx..curz by fld_add_shadow below
+        A.cx = h->shadow[0]; A.cy = h->shadow[1]; A.cz = h->shadow[2];
         long long warps = (S.n + C3_CHUNK - 1) / C3_CHUNK;
         int blocks = (int)((warps + C3_WARPS - 1) / C3_WARPS);
         k_cellrun3<<<blocks, C3_WARPS * 32, smem, h->stream>>>(A);
         CKK(h);
     }
-    return 0;
+    return fld_add_shadow(h);
 }

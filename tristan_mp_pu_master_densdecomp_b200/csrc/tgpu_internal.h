@@ -81,6 +81,20 @@ struct tgpu_ctx {
     int timing;
 };
 
+// Address of the lane's row (J, K) (0-based) at x-plane i0 (0-based).
+//   TILED = false: the reference's Fortran-order arrays, element i0 + mx*(J + my*K); consecutive planes are 1 apart.
+//   TILED = true : the shadow arrays of the fused mover.  The 16 lanes of a half-warp flush one x-plane of the 4x4 (y,z)
+//     footprint; in Fortran order that is 16 different cache lines per RED instruction.  The shadow arrays therefore keep
+//     every 4x4 (y,z) tile of an x-plane contiguous (64 B): element ((tz*nty + ty)*mx + i0)*16 + (K&3)*4 + (J&3), so a flush
+//     touches at most 2x2 tiles (<= 4 short segments) and consecutive planes are 16 apart.  k_add_shadow_tiled (fields.cu)
+//     folds them back into curx/cury/curz.
+template <bool TILED>
+__device__ __forceinline__ size_t row_index(int mx, int my, int nty, int J, int K, int i0)
+{
+    if (TILED) return ((size_t)(((K >> 2) * nty + (J >> 2)) * (long long)mx + i0) << 4) + (size_t)(((K & 3) << 2) | (J & 3));
+    return (size_t)((long long)mx * (J + (long long)my * K) + i0);
+}
+
 void tgpu_set_error(const std::string &s);
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     tgpu_set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); return TGPU_ECUDA; } } while (0)
