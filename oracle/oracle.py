@@ -34,7 +34,8 @@ class Params(C.Structure):
                 ("periodicx", C.c_int), ("periodicy", C.c_int), ("periodicz", C.c_int),
                 ("qi", C.c_float), ("qe", C.c_float), ("qmi", C.c_float), ("qme", C.c_float),
                 ("maxptl", C.c_int), ("buffsize", C.c_int), ("quirks", C.c_int), ("pusher", C.c_int),
-                ("external_fields", C.c_int), ("ext", C.c_float * 6)]
+                ("external_fields", C.c_int), ("ext", C.c_float * 6),
+                ("highorder", C.c_int), ("wall_i2", C.c_int)]
 
 
 def build(force=False):
@@ -77,6 +78,7 @@ def lib():
                      "orc_apply_filter2", "orc_apply_filter", "orc_step"]:
             getattr(L, name).argtypes = [vp]
         L.orc_step_phase.argtypes = [vp, ci]
+        L.orc_meanq_fld_cur.argtypes = [vp, C.c_char_p]
         L.orc_shape.argtypes = [ci, cf, ci, C.POINTER(cf), C.POINTER(ci), C.POINTER(ci)]
         L.orc_filter2_line.argtypes = [C.POINTER(cf), ci, ci]
         L.orc_filter2_rank.argtypes = [vp, ci, ci, C.POINTER(cf), C.POINTER(cf)]
@@ -107,8 +109,9 @@ def lib():
 
 def make_params(dim=2, order=1, mx0=32, my0=32, mz0=1, sizex=1, sizey=1, sizez=1, c=0.45, corr=1.025,
                 ntimes=0, filter_kind=1, periodic=(1, 1, 1), ppc0=16.0, c_omp=10.0, gamma0=0.5, me=1.0,
-                mi=1.0, maxptl=None, buffsize=None, quirks=Q_REFERENCE, pusher=0, ext=None):
+                mi=1.0, maxptl=None, buffsize=None, quirks=Q_REFERENCE, pusher=0, ext=None, highorder=0, wall_i2=0):
     P = Params()
+    P.highorder, P.wall_i2 = highorder, wall_i2
     P.dim, P.order = dim, order
     P.mx0, P.my0, P.mz0 = mx0, my0, (mz0 if dim == 3 else 1)
     P.sizex, P.sizey, P.sizez = sizex, sizey, (sizez if dim == 3 else 1)
@@ -183,6 +186,8 @@ class World:
     def __init__(self, P):
         self.P = P
         self.h = lib().orc_world_create(C.byref(P))
+        if not self.h:
+            raise ValueError("unsupported configuration (highorder = 1 with open y on a split axis or open z)")
         self.n = P.sizex * P.sizey * P.sizez
         self.ranks = [Rank(self, i) for i in range(self.n)]
 
@@ -202,6 +207,10 @@ class World:
 
     def step(self):
         lib().orc_step(self.h)
+
+    def meanq_fld_cur(self, totname):
+        """output.F90:5229-5486: moment `totname` ('tdens', 'ibetx', ...) into curx; cury holds the weight"""
+        lib().orc_meanq_fld_cur(self.h, totname.encode())
 
     def init_weibel(self, ppc0=16.0, gamma0=0.5, delgam=2e-5, me=1.0, mi=1.0, tratio=1.0, distr_dim=2):
         lib().orc_init_weibel(self.h, ppc0, gamma0, delgam, me, mi, tratio, distr_dim)

@@ -34,8 +34,10 @@ static void ghost_widths(int dim, int order, int *nghost, int *nghostz)
     if (dim == 2) *nghostz = 5;
 }
 
+int orc_range42_ok(const orc_params *P);
 orc_world *orc_world_create(const orc_params *Pin)
 {
+    if (!orc_range42_ok(Pin)) return NULL;               /* _42 ranges that read outside the arrays in the reference */
     orc_world *w = (orc_world *)calloc(1, sizeof(orc_world));
     w->P = *Pin;
     orc_params *P = &w->P;
@@ -188,8 +190,121 @@ static void stencil_range_e(const orc_rank *r, int axis, int *a1, int *a2)
     if (axis == 2) { *a1 = g; *a2 = m; }                    /* unconditional override, fields.F90:818-819 */
 }
 
+/* ------------------------------------------------------------------------- */
+/* 4th-order `_42` solver (highorder = 1): fields.F90:1039-1212 (B), 1223-1361 (E) */
+/* Index ranges are the reference's.  Where those ranges make the reference read  */
+/* outside its arrays (open y or z on a split axis; open z in the E step, :1262-   */
+/* 1277 "FIX range") the configuration is rejected by range42_ok().               */
+/* ------------------------------------------------------------------------- */
+int orc_range42_ok(const orc_params *P)
+{
+    int size0 = P->sizex * P->sizey * P->sizez;
+    if (!P->highorder) return 1;
+    if (P->dim == 3 && !P->periodicz) return 0;
+    if (!P->periodicy && size0 != 1) return 0;
+    return 1;
+}
+static void range42_b(const orc_rank *r, int axis, int *a1, int *a2)
+{
+    int g = (axis == 2 ? r->nghostz : r->nghost) / 2;
+    int m = axis == 0 ? r->mx : axis == 1 ? r->my : r->mz;
+    int per = axis == 0 ? r->P.periodicx : axis == 1 ? r->P.periodicy : r->P.periodicz;
+    if (per) { *a1 = g + 1; *a2 = m - (g + 1); }            /* :1054-1056, 1067-1069, 1088-1090 */
+    else { *a1 = g; *a2 = m - g; }                          /* :1057-1059; y, z: the size0 == 1 branch (:1080-1083, 1102-1105) */
+    if (axis == 0 && r->P.wall_i2 > 0 && r->P.wall_i2 < *a2) *a2 = r->P.wall_i2;   /* :1062-1065 */
+}
+static void range42_e(const orc_rank *r, int axis, int *a1, int *a2)
+{
+    int g = (axis == 2 ? r->nghostz : r->nghost) / 2;
+    int m = axis == 0 ? r->mx : axis == 1 ? r->my : r->mz;
+    int per = axis == 0 ? r->P.periodicx : axis == 1 ? r->P.periodicy : r->P.periodicz;
+    *a1 = g + 1; *a2 = per ? m - (g + 1) : m - 1;           /* :1238-1244, 1251-1257, 1260-1262 */
+    if (axis == 0 && r->P.wall_i2 > 0 && r->P.wall_i2 < *a2) *a2 = r->P.wall_i2;   /* :1246-1249 */
+}
+static void advance_b_halfstep_42(orc_rank *r)
+{
+    float *ex = r->f[ORC_EX], *ey = r->f[ORC_EY], *ez = r->f[ORC_EZ];
+    float *bx = r->f[ORC_BX], *by = r->f[ORC_BY], *bz = r->f[ORC_BZ];
+    int i1, i2, j1, j2, k1 = 1, k2 = 1;
+    range42_b(r, 0, &i1, &i2); range42_b(r, 1, &j1, &j2);
+    if (r->P.dim == 3) range42_b(r, 2, &k1, &k2);
+    const float cnst = r->P.corr * (.5f * r->P.c);                       /* :1050-1052 */
+    const float coef1 = 9.f / 8.f * r->P.corr * (.5f * r->P.c);
+    const float coef2 = -1.f / 24.f * r->P.corr * (.5f * r->P.c);
+    const int three = r->P.dim == 3;
+#define L(i, j, k) IDX(r, i, j, k)
+    for (int k = k1; k <= k2; k++) for (int j = j1; j <= j2; j++) for (int i = i1; i <= i2; i++) {
+        const size_t l = L(i, j, k);
+        if (three) {                                                     /* :1124-1132 */
+            bx[l] = bx[l] + coef1 * (ey[L(i, j, k + 1)] - ey[l] - ez[L(i, j + 1, k)] + ez[l])
+                          + coef2 * (ey[L(i, j, k + 2)] - ey[L(i, j, k - 1)] - ez[L(i, j + 2, k)] + ez[L(i, j - 1, k)]);
+            by[l] = by[l] + coef1 * (ez[L(i + 1, j, k)] - ez[l] - ex[L(i, j, k + 1)] + ex[l])
+                          + coef2 * (ez[L(i + 2, j, k)] - ez[L(i - 1, j, k)] - ex[L(i, j, k + 2)] + ex[L(i, j, k - 1)]);
+        } else {                                                         /* :1147-1150 */
+            bx[l] = bx[l] + coef1 * (-ez[L(i, j + 1, k)] + ez[l]) + coef2 * (-ez[L(i, j + 2, k)] + ez[L(i, j - 1, k)]);
+            by[l] = by[l] + coef1 * (ez[L(i + 1, j, k)] - ez[l]) + coef2 * (ez[L(i + 2, j, k)] - ez[L(i - 1, j, k)]);
+        }
+        bz[l] = bz[l] + coef1 * (ex[L(i, j + 1, k)] - ex[l] - ey[L(i + 1, j, k)] + ey[l])
+                      + coef2 * (ex[L(i, j + 2, k)] - ex[L(i, j - 1, k)] - ey[L(i + 2, j, k)] + ey[L(i - 1, j, k)]);
+    }
+    if (!r->P.periodicx) {                                               /* :1158-1190: 2nd-order update of i = 1 and mx-1 */
+        for (int k = k1; k <= k2; k++) for (int j = j1; j <= j2; j++) for (int i = 1; i <= r->mx - 1; i += r->mx - 2) {
+            const size_t l = L(i, j, k);
+            if (three) {
+                bx[l] = bx[l] + cnst * (ey[L(i, j, k + 1)] - ey[l] - ez[L(i, j + 1, k)] + ez[l]);
+                by[l] = by[l] + cnst * (ez[L(i + 1, j, k)] - ez[l] - ex[L(i, j, k + 1)] + ex[l]);
+            } else {
+                bx[l] = bx[l] + cnst * (-ez[L(i, j + 1, k)] + ez[l]);
+                by[l] = by[l] + cnst * (ez[L(i + 1, j, k)] - ez[l]);
+            }
+            bz[l] = bz[l] + cnst * (ex[L(i, j + 1, k)] - ex[l] - ey[L(i + 1, j, k)] + ey[l]);
+        }
+    }
+}
+static void advance_e_fullstep_42(orc_rank *r)
+{
+    float *ex = r->f[ORC_EX], *ey = r->f[ORC_EY], *ez = r->f[ORC_EZ];
+    float *bx = r->f[ORC_BX], *by = r->f[ORC_BY], *bz = r->f[ORC_BZ];
+    int i1, i2, j1, j2, k1 = 1, k2 = 1;
+    range42_e(r, 0, &i1, &i2); range42_e(r, 1, &j1, &j2);
+    if (r->P.dim == 3) range42_e(r, 2, &k1, &k2);
+    const float cnst = r->P.corr * r->P.c;                               /* :1234-1236 */
+    const float coef1 = 9.f / 8.f * r->P.corr * r->P.c;
+    const float coef2 = -1.f / 24.f * r->P.corr * r->P.c;
+    const int three = r->P.dim == 3;
+    for (int k = k1; k <= k2; k++) for (int j = j1; j <= j2; j++) for (int i = i1; i <= i2; i++) {
+        const size_t l = L(i, j, k);
+        if (three) {                                                     /* :1293-1301 */
+            ex[l] = ex[l] + coef1 * (by[L(i, j, k - 1)] - by[l] - bz[L(i, j - 1, k)] + bz[l])
+                          + coef2 * (by[L(i, j, k - 2)] - by[L(i, j, k + 1)] - bz[L(i, j - 2, k)] + bz[L(i, j + 1, k)]);
+            ey[l] = ey[l] + coef1 * (bz[L(i - 1, j, k)] - bz[l] - bx[L(i, j, k - 1)] + bx[l])
+                          + coef2 * (bz[L(i - 2, j, k)] - bz[L(i + 1, j, k)] - bx[L(i, j, k - 2)] + bx[L(i, j, k + 1)]);
+        } else {                                                         /* :1316-1319 */
+            ex[l] = ex[l] + coef1 * (-bz[L(i, j - 1, k)] + bz[l]) + coef2 * (-bz[L(i, j - 2, k)] + bz[L(i, j + 1, k)]);
+            ey[l] = ey[l] + coef1 * (bz[L(i - 1, j, k)] - bz[l]) + coef2 * (bz[L(i - 2, j, k)] - bz[L(i + 1, j, k)]);
+        }
+        ez[l] = ez[l] + coef1 * (bx[L(i, j - 1, k)] - bx[l] - by[L(i - 1, j, k)] + by[l])
+                      + coef2 * (bx[L(i, j - 2, k)] - bx[L(i, j + 1, k)] - by[L(i - 2, j, k)] + by[L(i + 1, j, k)]);
+    }
+    if (!r->P.periodicx) {                                               /* :1327-1357: 2nd-order update of i = 2 and mx */
+        for (int k = k1; k <= k2; k++) for (int j = j1; j <= j2; j++) for (int i = 2; i <= r->mx; i += r->mx - 2) {
+            const size_t l = L(i, j, k);
+            if (three) {
+                ex[l] = ex[l] + cnst * (by[L(i, j, k - 1)] - by[l] - bz[L(i, j - 1, k)] + bz[l]);
+                ey[l] = ey[l] + cnst * (bz[L(i - 1, j, k)] - bz[l] - bx[L(i, j, k - 1)] + bx[l]);
+            } else {
+                ex[l] = ex[l] + cnst * (-bz[L(i, j - 1, k)] + bz[l]);
+                ey[l] = ey[l] + cnst * (bz[L(i - 1, j, k)] - bz[l]);
+            }
+            ez[l] = ez[l] + cnst * (bx[L(i, j - 1, k)] - bx[l] - by[L(i - 1, j, k)] + by[l]);
+        }
+    }
+#undef L
+}
+
 void orc_advance_b_halfstep(orc_rank *r)
 {
+    if (r->P.highorder) { advance_b_halfstep_42(r); return; }          /* dispatcher, fields.F90:1407-1417 */
     float *ex = r->f[ORC_EX], *ey = r->f[ORC_EY], *ez = r->f[ORC_EZ];
     float *bx = r->f[ORC_BX], *by = r->f[ORC_BY], *bz = r->f[ORC_BZ];
     int i1, i2, j1, j2, k1 = 1, k2 = 1;
@@ -218,6 +333,7 @@ void orc_advance_b_halfstep(orc_rank *r)
 
 void orc_advance_e_fullstep(orc_rank *r)
 {
+    if (r->P.highorder) { advance_e_fullstep_42(r); return; }          /* dispatcher, fields.F90:1429-1440 */
     float *ex = r->f[ORC_EX], *ey = r->f[ORC_EY], *ez = r->f[ORC_EZ];
     float *bx = r->f[ORC_BX], *by = r->f[ORC_BY], *bz = r->f[ORC_BZ];
     int i1, i2, j1, j2, k1 = 1, k2 = 1;
@@ -1692,6 +1808,86 @@ void orc_step_shock(orc_world *w, float leftwall, float binit, float btheta, flo
     orc_step_phase(w, PH_INJECT_OTHERS); orc_step_phase(w, PH_EXCH_P); orc_step_phase(w, PH_INJECT_OTHERS);
     if (w->lap % 10 == 0) orc_step_phase(w, PH_REORDER);
 #undef FBC
+}
+
+/* ------------------------------------------------------------------------- */
+/* output-side moments: meanq_fld_cur(totname), output.F90:5229-5486            */
+/* Every live particle adds `addprtx` (and the weight `addprty`) to the box of   */
+/* half-width idx = idy = idz = 2 (idz = 0 in 2D, output.F90:189-195) around its  */
+/* cell, clipped to the local array; curx/cury are the scratch arrays, as in the  */
+/* reference.  The per-rank part is here; exchange_current() (:5436) and the      */
+/* normalisation (:5439-5479) follow in orc_meanq_fld_cur.                        */
+/* ------------------------------------------------------------------------- */
+static void meanq_terms(const char *name, const orc_particle *q, int is_ion, float *ax, float *ay)
+{
+    const float gam = 1.f / sqrtf(1.f + q->u * q->u + q->v * q->v + q->w * q->w);      /* gamprt, :5264 */
+    const int is_lec = !is_ion;
+    float x = 0.f, y = 0.f;
+#define IS(s) (strncmp(name, s, 5) == 0)
+    if (IS("tdens")) x = q->ch;
+    else if (IS("idens")) { if (is_ion) x = q->ch; }
+    else if (IS("hdens")) { if (is_lec && q->ind > 0) x = q->ch; }
+    else if (IS("ldens")) { if (is_lec && q->ind < 0) x = 1.f; }
+    else if (IS("btden")) { if (q->ind < 0) x = q->ch; }
+    else if (IS("biden")) { if (is_ion && q->ind < 0) x = q->ch; }
+    else if ((name[0] == 't' || name[0] == 'e' || name[0] == 'i') && strncmp(name + 1, "bet", 3) == 0) {
+        const float uu = name[4] == 'x' ? q->u : name[4] == 'y' ? q->v : q->w;
+        if (name[0] == 't' || (name[0] == 'e' && is_lec) || (name[0] == 'i' && is_ion)) { x = uu * gam * q->ch; y = q->ch; }
+    } else if ((name[0] == 't' || name[0] == 'i') && strncmp(name + 1, "mom", 3) == 0) {
+        const float uu = name[4] == 'x' ? q->u : name[4] == 'y' ? q->v : q->w;
+        if (name[0] == 't' || is_ion) { x = uu * q->ch; y = q->ch; }
+    } else if (IS("eener")) { if (is_lec) { x = (1.f / gam - 1.f) * q->ch; y = q->ch; } }
+    else if (IS("iener")) { if (is_ion) { x = (1.f / gam - 1.f) * q->ch; y = q->ch; } }
+    else if ((name[0] == 'e' || name[0] == 'i') && name[1] == 'e' && name[2] == 't' && name[4] == '2') {
+        const float uu = name[3] == 'x' ? q->u : name[3] == 'y' ? q->v : q->w;
+        if ((name[0] == 'e' && is_lec) || (name[0] == 'i' && is_ion)) { x = (uu * gam) * (uu * gam) * q->ch; y = q->ch; }
+    }
+#undef IS
+    *ax = x; *ay = y;
+}
+static void meanq_accumulate(orc_rank *r, const char *name)
+{
+    float *cx = r->f[ORC_CURX], *cy = r->f[ORC_CURY];
+    const int idx = 2, idy = 2, idz = r->P.dim == 3 ? 2 : 0;
+    orc_reset_currents(r);                                                             /* :5257-5259 */
+    for (int sp = 0; sp < 2; sp++) {
+        const int first = sp ? r->maxhlf : 0, cnt = sp ? r->lecs : r->ions;
+        for (int n = 0; n < cnt; n++) {
+            const orc_particle *q = &r->p[first + n];
+            float ax, ay; meanq_terms(name, q, sp == 0, &ax, &ay);
+            const int i = (int)q->x, j = (int)q->y, k = (int)q->z;                     /* :5405-5407 */
+            int lz1 = k - idz < 1 ? 1 : k - idz, lz2 = k + idz > r->mz ? r->mz : k + idz;
+            if (r->P.dim == 2) { lz1 = 1; lz2 = 1; }
+            const int ly1 = j - idy < 1 ? 1 : j - idy, ly2 = j + idy > r->my ? r->my : j + idy;
+            const int lx1 = i - idx < 1 ? 1 : i - idx, lx2 = i + idx > r->mx ? r->mx : i + idx;
+            for (int kk = lz1; kk <= lz2; kk++) for (int jj = ly1; jj <= ly2; jj++) for (int ii = lx1; ii <= lx2; ii++) {
+                const size_t l = IDX(r, ii, jj, kk);
+                cx[l] = cx[l] + ax; cy[l] = cy[l] + ay;
+            }
+        }
+    }
+}
+static void meanq_normalise(orc_rank *r, const char *name)
+{
+    float *cx = r->f[ORC_CURX], *cy = r->f[ORC_CURY];
+    const int idx = 2, idy = 2, idz = r->P.dim == 3 ? 2 : 0;
+    for (int k = 1; k <= r->mz; k++) for (int j = 1; j <= r->my; j++) for (int i = 1; i <= r->mx; i++) {
+        int lz1 = k - idz < 1 ? 1 : k - idz, lz2 = k + idz > r->mz ? r->mz : k + idz;
+        if (r->P.dim == 2) { lz1 = 1; lz2 = 1; }
+        const int ly1 = j - idy < 1 ? 1 : j - idy, ly2 = j + idy > r->my ? r->my : j + idy;
+        const int lx1 = i - idx < 1 ? 1 : i - idx, lx2 = i + idx > r->mx ? r->mx : i + idx;
+        const float vol = (float)((lx2 - lx1 + 1) * (ly2 - ly1 + 1) * (lz2 - lz1 + 1));
+        const size_t l = IDX(r, i, j, k);
+        cx[l] = cx[l] / vol; cy[l] = cy[l] / vol;                                      /* :5458-5459 */
+    }
+    if (strncmp(name, "tdens", 5) && strncmp(name, "idens", 5) && strncmp(name, "hdens", 5) && strncmp(name, "ldens", 5))
+        for (size_t l = 0; l < r->lot; l++) cx[l] = cy[l] != 0.f ? cx[l] / cy[l] : 0.f;   /* :5470-5477 */
+}
+void orc_meanq_fld_cur(orc_world *w, const char *totname)
+{
+    for (int rk = 0; rk < w->size0; rk++) meanq_accumulate(w->r[rk], totname);
+    orc_exchange_current(w);
+    for (int rk = 0; rk < w->size0; rk++) meanq_normalise(w->r[rk], totname);
 }
 
 /* ------------------------------------------------------------------------- */

@@ -57,6 +57,8 @@ typedef struct {
     int pusher;              /* 0 Boris, 1 Vay (-Dvay) */
     int external_fields;     /* constant external field model of get_external_fields */
     float ext[6];            /* ex,ey,ez,bx,by,bz */
+    int highorder;           /* <algorithm> highorder: 1 = 4th-order `_42` field solver (fields.F90:1039-1361) */
+    int wall_i2;             /* `wall` clamp of the _42 solver's x range, int(xinject2)+10 (fields.F90:1062-1065); 0 = no wall */
 } orc_params;
 
 typedef struct {
@@ -145,6 +147,8 @@ void orc_exchange_particles(orc_world *w);
 void orc_apply_filter1(orc_world *w);
 void orc_apply_filter2(orc_world *w);
 void orc_apply_filter(orc_world *w);
+/* moments of the particle distribution into curx (cury = weight): meanq_fld_cur(totname), output.F90:5229-5486 */
+void orc_meanq_fld_cur(orc_world *w, const char *totname);
 void orc_step(orc_world *w);                      /* one lap of tristanmainloop.F90:107-344 */
 void orc_step_phase(orc_world *w, int phase);     /* single named phase, for A/B tests */
 
@@ -168,6 +172,7 @@ void orc_init_uniform(orc_world *w, float ppc0, float beta_drift, float uth, uin
 /* --- shock-problem user hooks (user/user_shock.F90) --- */
 /* radiation boundary `surface` of bc_b2 / bc_e2: fieldboundaries.F90:274-295, 403-426, 493-606 (per rank; the
    ghost refresh that completes bc_b2 / bc_e2 is orc_bc_fields) */
+int orc_range42_ok(const orc_params *P);   /* 0: highorder = 1 with index ranges that are out of bounds in the reference */
 void orc_surface_b(orc_rank *r);
 void orc_surface_e(orc_rank *r);
 void orc_field_bc_shock(orc_rank *r, float leftwall, float binit, float btheta, float bphi, float beta);   /* :342-373 */

@@ -8,10 +8,11 @@ from oracle import oracle as O
 
 
 def oracle_world(dim=3, order=2, n=(16, 16, 16), sizes=(1, 1, 1), ppc=4.0, ntimes=0, filter_kind=1, delgam=1e-2,
-                 quirks=O.Q_REFERENCE, init="weibel", seed_fields=1, periodic=(1, 1, 1), ext=None, pusher=0, gamma0=0.5):
+                 quirks=O.Q_REFERENCE, init="weibel", seed_fields=1, periodic=(1, 1, 1), ext=None, pusher=0, gamma0=0.5,
+                 highorder=0):
     P = O.make_params(dim=dim, order=order, mx0=n[0], my0=n[1], mz0=n[2], sizex=sizes[0], sizey=sizes[1], sizez=sizes[2],
                       ppc0=ppc if ppc > 0 else 16.0, ntimes=ntimes, maxptl=None if ppc > 0 else 65536, filter_kind=filter_kind, quirks=quirks, periodic=periodic, ext=ext,
-                      pusher=pusher, gamma0=gamma0)
+                      pusher=pusher, gamma0=gamma0, highorder=highorder)
     w = O.World(P)
     if init == "weibel":
         w.init_weibel(ppc0=ppc, delgam=delgam, distr_dim=3 if dim == 3 else 2, gamma0=gamma0)
@@ -33,7 +34,8 @@ def gpu_params(tg, w, rank=0, device=-1):
     gp = tg.make_params(dim=P.dim, order=P.order, mx0=P.mx0, my0=P.my0, mz0=P.mz0, sizex=P.sizex, sizey=P.sizey,
                         sizez=P.sizez, rank=rank, c=P.c, corr=P.corr, ntimes=P.ntimes, filter_kind=P.filter_kind,
                         periodic=(P.periodicx, P.periodicy, P.periodicz), maxptl=P.maxptl, buffsize=P.buffsize,
-                        quirks=P.quirks, pusher=P.pusher, ext=list(P.ext) if P.external_fields else None, device=device)
+                        quirks=P.quirks, pusher=P.pusher, ext=list(P.ext) if P.external_fields else None, device=device,
+                        highorder=P.highorder, wall_i2=P.wall_i2)
     gp.qi, gp.qe, gp.qmi, gp.qme = P.qi, P.qe, P.qmi, P.qme
     r = w.ranks[rank]
     assert (gp.mx, gp.my, gp.mz, gp.mxcum, gp.mycum, gp.mzcum) == (r.mx, r.my, r.mz, r.mxcum, r.mycum, r.mzcum)

@@ -64,6 +64,32 @@ def test_ghost_refresh_and_fold_bit_exact(tgm, dim, order):
     ctx.close()
 
 
+@pytest.mark.parametrize("dim,periodic", [(3, (1, 1, 1)), (3, (0, 1, 1)), (3, (0, 0, 1)), (2, (1, 1, 1)), (2, (0, 0, 1))])
+def test_field_solver_42_bit_exact(tgm, dim, periodic):
+    """highorder = 1: the 4th-order `_42` solver (fields.F90:1039-1361) incl. the 2nd-order edge planes of an open x axis"""
+    w, ctx = make(tgm, dim=dim, order=2, n=(20, 18, 14), ppc=1.0, periodic=periodic, highorder=1)
+    r = w.ranks[0]
+    for name in ["advance_b_halfstep", "advance_e_fullstep", "advance_b_halfstep"]:
+        getattr(ctx, name)()
+        r.call(name)
+    fg = ctx.fields_d2h()
+    for a in range(6):
+        assert np.array_equal(fg[a], r.arr(a)), O.ARR_NAMES[a]
+    ctx.close()
+
+
+def test_full_lap_highorder(tgm):
+    w, ctx = make(tgm, dim=3, order=2, n=(16, 16, 12), ppc=4.0, ntimes=2, filter_kind=2, highorder=1)
+    r = w.ranks[0]
+    for lap in range(2):
+        ctx.step(1); w.step()
+        fg = ctx.fields_d2h()
+        for a in range(6):
+            assert T.max_rel(T.interior(r, fg[a]), T.interior(r, r.arr(a))) < 2e-4, (lap, O.ARR_NAMES[a])
+        T.upload(ctx, r)
+    ctx.close()
+
+
 @pytest.mark.parametrize("dim,periodic", [(3, (0, 1, 1)), (3, (1, 0, 1)), (3, (0, 0, 0)), (2, (0, 1, 1)), (2, (1, 0, 1)), (2, (0, 0, 1))])
 def test_radiation_surface_bit_exact(tgm, dim, periodic):
     """bc_b2 / bc_e2 with radiating axes: `surface` (fieldboundaries.F90:493-606) then the ghost refresh; bit-exact"""

@@ -356,3 +356,34 @@ def test_radiation_boundary_y_faces_3d():
     """open y in 3D also switches the z faces to radiating (fieldboundaries.F90:94); a y-going pulse is absorbed"""
     h = _pulse_energy(3, (1, 0, 1), 1, 1, absorb=True)
     assert h[-1] < 1e-3, h[-1]
+
+
+@pytest.mark.parametrize("highorder", [0, 1])
+@pytest.mark.parametrize("dim,axis", [(2, 0), (3, 0), (3, 1), (3, 2)])
+def test_vacuum_dispersion_of_both_field_solvers(highorder, dim, axis):
+    """A standing vacuum mode oscillates as cos(w t) with sin(w/2) = Corr*c*K:  K = sin(k/2) for the 2nd-order solver
+    (fields.F90:586-870) and K = 9/8 sin(k/2) - 1/24 sin(3k/2) for the 4th-order `_42` solver (fields.F90:1039-1361).
+    For a single frequency a(n+1) + a(n-1) = 2 cos(w) a(n) holds exactly, which pins cos(w) to ~1e-7."""
+    n = [8, 8, 8 if dim == 3 else 1]
+    n[axis] = 32
+    w = T.oracle_world(dim=dim, order=1, n=tuple(n), ppc=0.0, init="none", seed_fields=0, highorder=highorder)
+    r = w.ranks[0]
+    m = (r.mx, r.my, r.mz)[axis]
+    g = (r.nghost // 2, r.nghost // 2, r.nghostz // 2)[axis]
+    kk = 2 * np.pi * 4 / 32
+    shape = [1, 1, 1]; shape[2 - axis] = m
+    comp = (O.EY, O.EZ, O.EX)[axis]                         # a component transverse to the propagation axis
+    r.arr(comp)[...] = np.sin(kk * (np.arange(m) - g)).reshape(shape).astype(np.float32)
+    s = np.sin(kk * np.arange(32))
+    a = []
+    for _ in range(120):
+        for ph in (O.PH_BC_B1, O.PH_BC_E1, O.PH_BHALF, O.PH_BC_B1, O.PH_BHALF, O.PH_BC_B1, O.PH_EFULL):
+            w.phase(ph)
+        f = np.moveaxis(T.interior(r, r.arr(comp)).astype(np.float64), 2 - axis, 0)
+        a.append(float((f.reshape(32, -1)[:, 0] * s).sum()))
+    a = np.array(a)
+    cosw = (a[1:-1] * (a[2:] + a[:-2])).sum() / (2 * (a[1:-1] ** 2).sum())
+    K = 9 / 8 * np.sin(kk / 2) - 1 / 24 * np.sin(3 * kk / 2) if highorder else np.sin(kk / 2)
+    assert abs(cosw - (1 - 2 * (w.P.corr * w.P.c * K) ** 2)) < 2e-6
+    other = np.sin(kk / 2) if highorder else 9 / 8 * np.sin(kk / 2) - 1 / 24 * np.sin(3 * kk / 2)
+    assert abs(cosw - (1 - 2 * (w.P.corr * w.P.c * other) ** 2)) > 1e-3      # and it is not the other scheme's

@@ -41,7 +41,8 @@ class Params(C.Structure):
                 ("mxl", C.POINTER(C.c_int32)), ("myl", C.POINTER(C.c_int32)), ("mzl", C.POINTER(C.c_int32)),
                 ("maxptl", C.c_int32), ("buffsize", C.c_int32), ("quirks", C.c_int32), ("pusher", C.c_int32),
                 ("external_fields", C.c_int32), ("ext", C.c_float * 6),
-                ("device", C.c_int32), ("sort_every", C.c_int32)]
+                ("device", C.c_int32), ("sort_every", C.c_int32),
+                ("highorder", C.c_int32), ("wall_i2", C.c_int32)]
 
 
 ABI_SYMBOLS = [
@@ -140,7 +141,7 @@ def charge_normalisation(c, c_omp, ppc0, gamma0, me, mi):
 
 def make_params(dim=3, order=2, mx0=32, my0=32, mz0=32, sizex=1, sizey=1, sizez=1, rank=0, c=0.45, corr=1.025,
                 ntimes=32, filter_kind=1, periodic=(1, 1, 1), ppc0=16.0, c_omp=10.0, gamma0=0.5, me=1.0, mi=1.0,
-                maxptl=None, buffsize=None, quirks=Q_REFERENCE, pusher=0, ext=None, device=-1):
+                maxptl=None, buffsize=None, quirks=Q_REFERENCE, pusher=0, ext=None, device=-1, highorder=0, wall_i2=0):
     """Build a tgpu_params the way initialize() fills the reference's module globals for one rank."""
     if dim == 2:
         sizez, mz0 = 1, 1
@@ -176,6 +177,7 @@ def make_params(dim=3, order=2, mx0=32, my0=32, mz0=32, sizex=1, sizey=1, sizez=
         P.ext[i] = 0.0 if ext is None else ext[i]
     P.device = device
     P.sort_every = 0
+    P.highorder, P.wall_i2 = highorder, wall_i2
     return P
 
 

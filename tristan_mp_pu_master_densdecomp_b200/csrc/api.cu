@@ -54,6 +54,10 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     if (p->mx < 2 * p->nghost || p->my < 2 * p->nghost || (p->dim == 3 && p->mz < 2 * p->nghostz)) { tgpu_set_error("grid smaller than its ghost zones"); return TGPU_EINVAL; }
     if (p->dim == 2 && p->mz != 1) { tgpu_set_error("2D needs mz = 1 (fields.F90:228-232)"); return TGPU_EINVAL; }
     if (p->dim == 3 && p->sizex != 1) { tgpu_set_error("3D never splits x (communications.F90:176-181)"); return TGPU_EINVAL; }
+    if (p->highorder && ((p->dim == 3 && !p->periodicz) || (!p->periodicy && p->sizex * p->sizey * (p->dim == 3 ? p->sizez : 1) != 1))) {
+        // fields.F90:1071-1079, 1092-1101, 1262-1277: those index ranges make the reference itself read outside its arrays
+        tgpu_set_error("highorder = 1 with open z, or open y on more than one rank: index ranges undefined in the reference"); return TGPU_EINVAL;
+    }
     if (p->sizex < 1 || p->sizey < 1 || p->sizez < 1 || p->maxptl < 2 || p->c <= 0.f || p->c >= 0.5f) { tgpu_set_error("bad sizes / c (need 0 < c < 0.5)"); return TGPU_EINVAL; }
     int ndev = tgpu_device_count();
     if (ndev <= 0) { tgpu_set_error("no CUDA device: libtristan_gpu has no CPU fallback"); return TGPU_ECUDA; }

@@ -34,6 +34,11 @@
 #ifndef CR_CHUNK
 #define CR_CHUNK 128          // particles per half-warp
 #endif
+#ifndef CR_UNROLL
+#define CR_UNROLL 4           // phase-2 unroll (particles per half-warp per loop trip)
+#endif
+#define CR_STR(x) #x
+#define CR_DO_PRAGMA(x) _Pragma(CR_STR(x))
 #ifndef CR_PREFETCH
 #define CR_PREFETCH 0         // L1 prefetch of the next step's field nodes (A/B switch)
 #endif
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
         // ------------------------------------------------------------------ phase 2: half-warp = footprint
         // Both halves walk their 16 particles in lockstep; only the (rare) window moves diverge.
         const float4 *sp = (const float4 *)(stage + warp * CR_WARP_FLOATS + half * CR_HALF_FLOATS);
-#pragma unroll 2
+CR_DO_PRAGMA(unroll CR_UNROLL)
         for (int tt = 0; tt < 16; ++tt, sp += CR_STRIDE / 4) {
             if ((starts >> tt) & 1u) {
                 // particle tt opens a run of particles that share one footprint

@@ -90,8 +90,129 @@ __global__ void __launch_bounds__(256) k_efull(float *__restrict__ ex, float *__
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 4th-order `_42` solver (highorder = 1): fields.F90:1039-1212 (B half step), 1223-1361 (E full step).
+// coef1 = 9/8, coef2 = -1/24 of the 2nd-order constant; on an open x axis the two outermost planes get the 2nd-order
+// update (:1158-1190, 1327-1357).  EDGE launches run that update on the plane pair (i = ia, ib).
+// ---------------------------------------------------------------------------------------------
+static void range42_b(const tgpu_ctx *h, int axis, int *a1, int *a2)
+{
+    int m, g, per, sz, pos; axis_info(h, axis, &m, &g, &per, &sz, &pos);
+    if (per) { *a1 = g + 1; *a2 = m - (g + 1); } else { *a1 = g; *a2 = m - g; }
+    if (axis == 0 && h->P.wall_i2 > 0 && h->P.wall_i2 < *a2) *a2 = h->P.wall_i2;
+}
+static void range42_e(const tgpu_ctx *h, int axis, int *a1, int *a2)
+{
+    int m, g, per, sz, pos; axis_info(h, axis, &m, &g, &per, &sz, &pos);
+    *a1 = g + 1; *a2 = per ? m - (g + 1) : m - 1;
+    if (axis == 0 && h->P.wall_i2 > 0 && h->P.wall_i2 < *a2) *a2 = h->P.wall_i2;
+}
+template <int DIM, bool EDGE>
+__global__ void __launch_bounds__(256) k_bhalf42(float *__restrict__ bx, float *__restrict__ by, float *__restrict__ bz,
+                                                 const float *__restrict__ ex, const float *__restrict__ ey,
+                                                 const float *__restrict__ ez, int mx, int my, Range3 r, float coef1, float coef2)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = EDGE ? (t == 0 ? r.i1 : r.i2) : r.i1 + t;
+    const int j = r.j1 + blockIdx.y, k = r.k1 + blockIdx.z;
+    if (EDGE ? t > 1 : i > r.i2) return;
+    const size_t sx = 1, sy = mx, sz = (size_t)mx * my;
+    const size_t l = LIDX(i, j, k);
+    if (EDGE) {                       // coef1 carries the plain 2nd-order constant
+        if (DIM == 3) {
+            bx[l] = bx[l] + coef1 * (ey[l + sz] - ey[l] - ez[l + sy] + ez[l]);
+            by[l] = by[l] + coef1 * (ez[l + sx] - ez[l] - ex[l + sz] + ex[l]);
+        } else {
+            bx[l] = bx[l] + coef1 * (-ez[l + sy] + ez[l]);
+            by[l] = by[l] + coef1 * (ez[l + sx] - ez[l]);
+        }
+        bz[l] = bz[l] + coef1 * (ex[l + sy] - ex[l] - ey[l + sx] + ey[l]);
+        return;
+    }
+    if (DIM == 3) {
+        bx[l] = bx[l] + coef1 * (ey[l + sz] - ey[l] - ez[l + sy] + ez[l])
+                      + coef2 * (ey[l + 2 * sz] - ey[l - sz] - ez[l + 2 * sy] + ez[l - sy]);
+        by[l] = by[l] + coef1 * (ez[l + sx] - ez[l] - ex[l + sz] + ex[l])
+                      + coef2 * (ez[l + 2 * sx] - ez[l - sx] - ex[l + 2 * sz] + ex[l - sz]);
+    } else {
+        bx[l] = bx[l] + coef1 * (-ez[l + sy] + ez[l]) + coef2 * (-ez[l + 2 * sy] + ez[l - sy]);
+        by[l] = by[l] + coef1 * (ez[l + sx] - ez[l]) + coef2 * (ez[l + 2 * sx] - ez[l - sx]);
+    }
+    bz[l] = bz[l] + coef1 * (ex[l + sy] - ex[l] - ey[l + sx] + ey[l])
+                  + coef2 * (ex[l + 2 * sy] - ex[l - sy] - ey[l + 2 * sx] + ey[l - sx]);
+}
+template <int DIM, bool EDGE>
+__global__ void __launch_bounds__(256) k_efull42(float *__restrict__ ex, float *__restrict__ ey, float *__restrict__ ez,
+                                                 const float *__restrict__ bx, const float *__restrict__ by,
+                                                 const float *__restrict__ bz, int mx, int my, Range3 r, float coef1, float coef2)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = EDGE ? (t == 0 ? r.i1 : r.i2) : r.i1 + t;
+    const int j = r.j1 + blockIdx.y, k = r.k1 + blockIdx.z;
+    if (EDGE ? t > 1 : i > r.i2) return;
+    const size_t sx = 1, sy = mx, sz = (size_t)mx * my;
+    const size_t l = LIDX(i, j, k);
+    if (EDGE) {
+        if (DIM == 3) {
+            ex[l] = ex[l] + coef1 * (by[l - sz] - by[l] - bz[l - sy] + bz[l]);
+            ey[l] = ey[l] + coef1 * (bz[l - sx] - bz[l] - bx[l - sz] + bx[l]);
+        } else {
+            ex[l] = ex[l] + coef1 * (-bz[l - sy] + bz[l]);
+            ey[l] = ey[l] + coef1 * (bz[l - sx] - bz[l]);
+        }
+        ez[l] = ez[l] + coef1 * (bx[l - sy] - bx[l] - by[l - sx] + by[l]);
+        return;
+    }
+    if (DIM == 3) {
+        ex[l] = ex[l] + coef1 * (by[l - sz] - by[l] - bz[l - sy] + bz[l])
+                      + coef2 * (by[l - 2 * sz] - by[l + sz] - bz[l - 2 * sy] + bz[l + sy]);
+        ey[l] = ey[l] + coef1 * (bz[l - sx] - bz[l] - bx[l - sz] + bx[l])
+                      + coef2 * (bz[l - 2 * sx] - bz[l + sx] - bx[l - 2 * sz] + bx[l + sz]);
+    } else {
+        ex[l] = ex[l] + coef1 * (-bz[l - sy] + bz[l]) + coef2 * (-bz[l - 2 * sy] + bz[l + sy]);
+        ey[l] = ey[l] + coef1 * (bz[l - sx] - bz[l]) + coef2 * (bz[l - 2 * sx] - bz[l + sx]);
+    }
+    ez[l] = ez[l] + coef1 * (bx[l - sy] - bx[l] - by[l - sx] + by[l])
+                  + coef2 * (bx[l - 2 * sy] - bx[l + sy] - by[l - 2 * sx] + by[l + sx]);
+}
+static int fld_step42(tgpu_ctx *h, bool is_e)
+{
+    Range3 r; r.k1 = r.k2 = 1;
+    if (is_e) { range42_e(h, 0, &r.i1, &r.i2); range42_e(h, 1, &r.j1, &r.j2); if (h->P.dim == 3) range42_e(h, 2, &r.k1, &r.k2); }
+    else { range42_b(h, 0, &r.i1, &r.i2); range42_b(h, 1, &r.j1, &r.j2); if (h->P.dim == 3) range42_b(h, 2, &r.k1, &r.k2); }
+    const float base = is_e ? h->P.corr * h->P.c : h->P.corr * (.5f * h->P.c);
+    const float coef1 = is_e ? 9.f / 8.f * h->P.corr * h->P.c : 9.f / 8.f * h->P.corr * (.5f * h->P.c);
+    const float coef2 = is_e ? -1.f / 24.f * h->P.corr * h->P.c : -1.f / 24.f * h->P.corr * (.5f * h->P.c);
+    float *e0 = h->f[0], *e1 = h->f[1], *e2 = h->f[2], *b0 = h->f[3], *b1 = h->f[4], *b2 = h->f[5];
+    const int mx = h->P.mx, my = h->P.my;
+    dim3 grid(cdiv(r.i2 - r.i1 + 1, 256), r.j2 - r.j1 + 1, r.k2 - r.k1 + 1);
+    if (is_e) {
+        if (h->P.dim == 3) k_efull42<3, false><<<grid, 256, 0, h->stream>>>(e0, e1, e2, b0, b1, b2, mx, my, r, coef1, coef2);
+        else k_efull42<2, false><<<grid, 256, 0, h->stream>>>(e0, e1, e2, b0, b1, b2, mx, my, r, coef1, coef2);
+    } else {
+        if (h->P.dim == 3) k_bhalf42<3, false><<<grid, 256, 0, h->stream>>>(b0, b1, b2, e0, e1, e2, mx, my, r, coef1, coef2);
+        else k_bhalf42<2, false><<<grid, 256, 0, h->stream>>>(b0, b1, b2, e0, e1, e2, mx, my, r, coef1, coef2);
+    }
+    CKK(h);
+    if (!h->P.periodicx) {
+        Range3 e = r; dim3 ge(1, grid.y, grid.z);
+        if (is_e) { e.i1 = 2; e.i2 = mx; } else { e.i1 = 1; e.i2 = mx - 1; }
+        if (is_e) {
+            if (h->P.dim == 3) k_efull42<3, true><<<ge, 32, 0, h->stream>>>(e0, e1, e2, b0, b1, b2, mx, my, e, base, 0.f);
+            else k_efull42<2, true><<<ge, 32, 0, h->stream>>>(e0, e1, e2, b0, b1, b2, mx, my, e, base, 0.f);
+        } else {
+            if (h->P.dim == 3) k_bhalf42<3, true><<<ge, 32, 0, h->stream>>>(b0, b1, b2, e0, e1, e2, mx, my, e, base, 0.f);
+            else k_bhalf42<2, true><<<ge, 32, 0, h->stream>>>(b0, b1, b2, e0, e1, e2, mx, my, e, base, 0.f);
+        }
+        CKK(h);
+    }
+    h->need_prim = 1;
+    return 0;
+}
+
 int fld_bhalf(tgpu_ctx *h)
 {
+    if (h->P.highorder) return fld_step42(h, false);          // dispatcher, fields.F90:1407-1417
     Range3 r; r.k1 = r.k2 = 1;
     range_b(h, 0, &r.i1, &r.i2); range_b(h, 1, &r.j1, &r.j2);
     if (h->P.dim == 3) range_b(h, 2, &r.k1, &r.k2);
@@ -108,6 +229,7 @@ int fld_bhalf(tgpu_ctx *h)
 
 int fld_efull(tgpu_ctx *h)
 {
+    if (h->P.highorder) return fld_step42(h, true);           // dispatcher, fields.F90:1429-1440
     Range3 r; r.k1 = r.k2 = 1;
     range_e(h, 0, &r.i1, &r.i2); range_e(h, 1, &r.j1, &r.j2);
     if (h->P.dim == 3) range_e(h, 2, &r.k1, &r.k2);
