@@ -150,6 +150,12 @@ int tgpu_particle_bc_user_wall(tgpu_ctx *h, float leftwall);
  * params = {leftwall, binit, btheta, bphi, beta}; kind 0 = none, 1 = shock */
 int tgpu_set_user_hooks(tgpu_ctx *h, int kind, const float params[5]);
 
+/* ---- output-side reductions (device-resident state) ---------------- */
+/* meanq_fld_cur(totname), code/output.F90:5229-5486: totname = 'tdens' 'idens' 'hdens' 'ldens' 'btden' 'biden',
+ * '[tei]bet[xyz]', '[ti]mom[xyz]', 'eener' 'iener', '[ei]et[xyz]2'.  As in the reference the result is left in curx
+ * (cury = weight, curz = 0): read it with tgpu_currents_d2h.  Destroys the currents, like the reference (output laps only). */
+int tgpu_meanq_fld_cur(tgpu_ctx *h, const char *totname);
+
 /* ---- whole lap, resident mode: tristanmainloop.F90:107-344 with Appendix-B de-duplication ---- */
 int tgpu_step(tgpu_ctx *h, int nlaps);
 

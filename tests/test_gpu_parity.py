@@ -314,3 +314,26 @@ def test_errors_are_loud(tgm):
     with pytest.raises(tgm.TristanGPUError):
         ctx.particles_h2d(big, 40, 0)       # > maxhlf
     ctx.close()
+
+
+@pytest.mark.parametrize("dim,order", [(3, 2), (2, 1)])
+def test_meanq_fld_cur_moments(tgm, dim, order):
+    """device-side meanq_fld_cur (output.F90:5229-5486) against the oracle, every family of totname"""
+    w, ctx = make(tgm, dim=dim, order=order, n=(14, 12, 10), ppc=4.0)
+    r = w.ranks[0]
+    p = r.particles()
+    p["ind"][::3] *= -1                                  # some "beam" (ind < 0) particles for hdens / ldens / btden / biden
+    T.upload(ctx, r)
+    ctx.step(1); w.step()                                # lazily sorted, unwrapped state on the device
+    T.upload(ctx, r)
+    ctx.step(1)                                          # one more lap on the device only: state differs -> re-sync the oracle
+    pg, ions, lecs = ctx.particles_d2h()
+    r.particles()[:] = pg; r.set_counts(ions, lecs)
+    for name in ["tdens", "idens", "hdens", "ldens", "btden", "biden", "tbetx", "ebety", "ibetz", "tmomy", "imomz",
+                 "eener", "iener", "eetx2", "iety2", "tener"]:
+        ctx.meanq_fld_cur(name)
+        w.meanq_fld_cur(name)
+        got = ctx.currents_d2h()[0]
+        ref = r.arr(O.CURX)
+        assert T.max_rel(T.interior(r, got), T.interior(r, ref)) < 2e-5, name
+    ctx.close()

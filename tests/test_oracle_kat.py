@@ -387,3 +387,35 @@ def test_vacuum_dispersion_of_both_field_solvers(highorder, dim, axis):
     assert abs(cosw - (1 - 2 * (w.P.corr * w.P.c * K) ** 2)) < 2e-6
     other = np.sin(kk / 2) if highorder else 9 / 8 * np.sin(kk / 2) - 1 / 24 * np.sin(3 * kk / 2)
     assert abs(cosw - (1 - 2 * (w.P.corr * w.P.c * other) ** 2)) > 1e-3      # and it is not the other scheme's
+
+
+def test_meanq_density_and_velocity_known_answers():
+    """meanq_fld_cur (output.F90:5229-5486): a uniform plasma of n particles per cell with weight 1 gives density n
+    (box sum / box volume) and a cold beam moving at beta gives <beta_x> = beta everywhere it has particles"""
+    n = (12, 10, 8)
+    w = T.oracle_world(dim=3, order=1, n=n, ppc=0.0, init="none", seed_fields=0)
+    r = w.ranks[0]
+    g = r.nghost // 2
+    xs, ys, zs = [np.arange(m) + g + 1.5 for m in n]
+    X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij")
+    npart = X.size
+    p = r.particles()
+    for first in (0, r.maxhlf):
+        q = p[first:first + npart]
+        q["x"], q["y"], q["z"] = X.ravel(), Y.ravel(), Z.ravel()
+        q["u"] = 0.75 if first == 0 else -0.25
+        q["v"] = 0; q["w"] = 0; q["ch"] = 1; q["ind"] = np.arange(npart) + 1; q["proc"] = 0; q["splitlev"] = 1
+    r.set_counts(npart, npart)
+    w.meanq_fld_cur("tdens")
+    d = T.interior(r, r.arr(O.CURX))
+    assert np.allclose(d, 2.0, rtol=2e-5)                       # one ion + one electron per cell (periodic fold fills the edges)
+    w.meanq_fld_cur("idens")
+    assert np.allclose(T.interior(r, r.arr(O.CURX)), 1.0, rtol=2e-5)
+    w.meanq_fld_cur("ibetx")
+    assert np.allclose(T.interior(r, r.arr(O.CURX)), 0.75 / np.sqrt(1 + 0.75 ** 2), rtol=2e-5)
+    w.meanq_fld_cur("ebetx")
+    assert np.allclose(T.interior(r, r.arr(O.CURX)), -0.25 / np.sqrt(1 + 0.25 ** 2), rtol=2e-5)
+    w.meanq_fld_cur("tmomx")
+    assert np.allclose(T.interior(r, r.arr(O.CURX)), 0.25, rtol=2e-5)
+    w.meanq_fld_cur("iener")
+    assert np.allclose(T.interior(r, r.arr(O.CURX)), np.sqrt(1 + 0.75 ** 2) - 1, rtol=2e-5)

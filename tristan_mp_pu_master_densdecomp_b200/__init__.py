@@ -53,7 +53,7 @@ ABI_SYMBOLS = [
     "tgpu_add_current", "tgpu_bc_b1", "tgpu_bc_e1", "tgpu_bc_b2", "tgpu_bc_e2", "tgpu_exchange_current",
     "tgpu_apply_filter", "tgpu_apply_filter1_opt", "tgpu_apply_filter2_opt", "tgpu_move_particles",
     "tgpu_deposit_particles", "tgpu_exchange_particles", "tgpu_inject_others", "tgpu_reorder_particles",
-    "tgpu_field_bc_user_shock", "tgpu_particle_bc_user_wall", "tgpu_set_user_hooks", "tgpu_step", "tgpu_timers", "tgpu_launch_count", "tgpu_stream", "tgpu_set_option",
+    "tgpu_meanq_fld_cur", "tgpu_field_bc_user_shock", "tgpu_particle_bc_user_wall", "tgpu_set_user_hooks", "tgpu_step", "tgpu_timers", "tgpu_launch_count", "tgpu_stream", "tgpu_set_option",
 ]
 
 _lib = None
@@ -93,6 +93,7 @@ def load_library(path=None):
                  "tgpu_exchange_particles", "tgpu_inject_others", "tgpu_reorder_particles"]:
         getattr(L, name).argtypes = [vp]
     L.tgpu_field_bc_user_shock.argtypes = [vp] + [C.c_float] * 5
+    L.tgpu_meanq_fld_cur.argtypes = [vp, C.c_char_p]
     L.tgpu_particle_bc_user_wall.argtypes = [vp, C.c_float]
     L.tgpu_set_user_hooks.argtypes = [vp, ci, C.POINTER(C.c_float)]
     L.tgpu_step.argtypes = [vp, ci]
@@ -282,6 +283,10 @@ class Context:
 
     def field_bc_user_shock(self, leftwall, binit, btheta, bphi, beta):
         self._ck(self.lib.tgpu_field_bc_user_shock(self.h, leftwall, binit, btheta, bphi, beta), "field_bc_user_shock")
+
+    def meanq_fld_cur(self, totname):
+        """output.F90:5229-5486 on the device: moment `totname` into curx (read it with currents_d2h()[0])."""
+        self._ck(self.lib.tgpu_meanq_fld_cur(self.h, totname.encode()), "meanq_fld_cur")
 
     def particle_bc_user_wall(self, leftwall):
         self._ck(self.lib.tgpu_particle_bc_user_wall(self.h, leftwall), "particle_bc_user_wall")

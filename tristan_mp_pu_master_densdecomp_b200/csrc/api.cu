@@ -347,6 +347,11 @@ extern "C" int tgpu_set_user_hooks(tgpu_ctx *h, int kind, const float params[5])
     return 0;
 }
 
+// ---- output-side reductions -------------------------------------------------------------------------
+// meanq_fld_cur(totname), output.F90:5229-5486: the moment lands in curx (cury = weight), as in the reference; the host
+// reads it with tgpu_currents_d2h instead of pulling every particle across PCIe on an output lap
+extern "C" int tgpu_meanq_fld_cur(tgpu_ctx *h, const char *totname) { ENTER(h); return prt_meanq(h, totname); }
+
 // ---- whole lap -------------------------------------------------------------------------------------
 // Call order of tristanmainloop.F90:107-344 with the redundant ghost refreshes of Appendix B removed: three
 // refreshes per lap instead of eight.  Results on the parity region are identical to the full call list.

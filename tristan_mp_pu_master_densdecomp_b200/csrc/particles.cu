@@ -739,3 +739,113 @@ int prt_wall(tgpu_ctx *h, float leftwall)
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Output-side moments on the device: meanq_fld_cur(totname), output.F90:5229-5486.  The reference adds every particle's
+// term to the (2*2+1)^3 box around its cell (idx = idy = idz = 2, idz = 0 in 2D; :189-195), folds the ghosts with
+// exchange_current, divides by the (clipped) box volume and, for the averaged quantities, by the weight.  Here each
+// particle adds once to its own cell (cell-sorted particles -> contiguous atomics), the box sum is a stencil over
+// those cell sums, and only curx needs to travel to the host instead of the whole particle array.
+// curx / cury are the scratch arrays, exactly as in the reference.
+// ---------------------------------------------------------------------------------------------
+struct MeanQ { int kind, comp, species, ind_sign, ratio, weight; };   // kind 0 ch, 1 one, 2 beta, 3 momentum, 4 energy, 5 beta^2
+static bool meanq_parse(const char *name, MeanQ *q)
+{
+    auto is = [&](const char *s) { return strncmp(name, s, 5) == 0; };
+    auto comp_of = [](char c) { return c == 'x' ? 0 : c == 'y' ? 1 : 2; };
+    q->kind = 0; q->comp = 0; q->species = 3; q->ind_sign = 0; q->ratio = 1; q->weight = 1;
+    if (is("tdens")) { q->ratio = 0; return true; }
+    if (is("idens")) { q->species = 1; q->ratio = 0; return true; }
+    if (is("hdens")) { q->species = 2; q->ind_sign = 1; q->ratio = 0; return true; }
+    if (is("ldens")) { q->kind = 1; q->species = 2; q->ind_sign = -1; q->ratio = 0; return true; }
+    // the beam densities set no weight (addprty stays 0, output.F90:5289-5297) but are not in the density list of :5470-5471,
+    // so the reference's final where(cury /= 0) zeroes them; reproduced as is
+    if (is("btden")) { q->ind_sign = -1; q->weight = 0; return true; }
+    if (is("biden")) { q->species = 1; q->ind_sign = -1; q->weight = 0; return true; }
+    const char f = name[0];
+    if ((f == 't' || f == 'e' || f == 'i') && strncmp(name + 1, "bet", 3) == 0 && strchr("xyz", name[4]) && name[4]) {
+        q->kind = 2; q->comp = comp_of(name[4]); q->species = f == 't' ? 3 : f == 'e' ? 2 : 1; return true;
+    }
+    if ((f == 't' || f == 'i') && strncmp(name + 1, "mom", 3) == 0 && strchr("xyz", name[4]) && name[4]) {
+        q->kind = 3; q->comp = comp_of(name[4]); q->species = f == 't' ? 3 : 1; return true;
+    }
+    if (is("eener") || is("iener")) { q->kind = 4; q->species = f == 'e' ? 2 : 1; return true; }
+    if ((f == 'e' || f == 'i') && name[1] == 'e' && name[2] == 't' && name[3] && strchr("xyz", name[3]) && name[4] == '2') {
+        q->kind = 5; q->comp = comp_of(name[3]); q->species = f == 'e' ? 2 : 1; return true;
+    }
+    return false;
+}
+__global__ void __launch_bounds__(256) k_meanq_cells(Species s, int n, MeanQ q, DevGeom G, float *__restrict__ sx, float *__restrict__ sy)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int ind = s.ind[t];
+    if ((q.ind_sign > 0 && !(ind > 0)) || (q.ind_sign < 0 && !(ind < 0))) return;
+    const float u = s.u[t], v = s.v[t], w = s.w[t], ch = s.ch[t];
+    const float gam = 1.f / sqrtf(1.f + u * u + v * v + w * w);
+    const float uu = q.comp == 0 ? u : q.comp == 1 ? v : w;
+    float ax, ay = ch;
+    switch (q.kind) {
+    case 0: ax = ch; break;
+    case 1: ax = 1.f; break;
+    case 2: ax = uu * gam * ch; break;
+    case 3: ax = uu * ch; break;
+    case 4: ax = (1.f / gam - 1.f) * ch; break;
+    default: ax = (uu * gam) * (uu * gam) * ch; break;
+    }
+    const int i = (int)s.x[t], j = (int)s.y[t], k = G.dim == 3 ? (int)s.z[t] : 1;
+    const size_t l = (size_t)(i - 1) + (size_t)G.mx * ((size_t)(j - 1) + (size_t)G.my * (size_t)(k - 1));
+    atomicAdd(sx + l, ax);
+    if (q.ratio && q.weight) atomicAdd(sy + l, ay);
+}
+// box sum of the cell sums, then nothing else: the fold and the normalisation follow
+__global__ void __launch_bounds__(256) k_meanq_box(const float *__restrict__ sx, const float *__restrict__ sy,
+                                                   float *__restrict__ cx, float *__restrict__ cy, int mx, int my, int mz, int idz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1, k = blockIdx.z + 1;
+    if (i > mx) return;
+    float a = 0.f, b = 0.f;
+    for (int kk = max(k - idz, 1); kk <= min(k + idz, mz); kk++)
+        for (int jj = max(j - 2, 1); jj <= min(j + 2, my); jj++)
+            for (int ii = max(i - 2, 1); ii <= min(i + 2, mx); ii++) {
+                const size_t l = (size_t)(ii - 1) + (size_t)mx * ((size_t)(jj - 1) + (size_t)my * (size_t)(kk - 1));
+                a += sx[l]; b += sy[l];
+            }
+    const size_t l = (size_t)(i - 1) + (size_t)mx * ((size_t)(j - 1) + (size_t)my * (size_t)(k - 1));
+    cx[l] = a; cy[l] = b;
+}
+__global__ void __launch_bounds__(256) k_meanq_norm(float *__restrict__ cx, float *__restrict__ cy, int mx, int my, int mz, int idz, int ratio)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1, k = blockIdx.z + 1;
+    if (i > mx) return;
+    const int nx = min(i + 2, mx) - max(i - 2, 1) + 1, ny = min(j + 2, my) - max(j - 2, 1) + 1, nz = min(k + idz, mz) - max(k - idz, 1) + 1;
+    const float vol = (float)(nx * ny * nz);
+    const size_t l = (size_t)(i - 1) + (size_t)mx * ((size_t)(j - 1) + (size_t)my * (size_t)(k - 1));
+    float a = cx[l] / vol, b = cy[l] / vol;                  // output.F90:5458-5459
+    if (ratio) a = b != 0.f ? a / b : 0.f;                   // :5470-5477
+    cx[l] = a; cy[l] = b;
+}
+int prt_meanq(tgpu_ctx *h, const char *totname)
+{
+    MeanQ q;
+    if (!totname || strlen(totname) < 5) { tgpu_set_error("meanq_fld_cur: totname must have 5 characters"); return TGPU_EINVAL; }
+    const bool known = meanq_parse(totname, &q);
+    int rc = prt_materialize(h); if (rc) return rc;
+    const size_t lot = (size_t)h->G.lot;
+    for (int c = 0; c < 3; c++) CK(cudaMemsetAsync(h->f[6 + c], 0, lot * sizeof(float), h->stream));     // :5257-5259
+    h->fused_pending = 0;
+    if (!known) return 0;                                    // unknown names add nothing (select case falls through)
+    float *sx = h->ftmp[0], *sy = h->ftmp[1];
+    CK(cudaMemsetAsync(sx, 0, lot * sizeof(float), h->stream)); CK(cudaMemsetAsync(sy, 0, lot * sizeof(float), h->stream));
+    for (int s = 0; s < 2; s++) {
+        Species &S = h->sp[s];
+        if (!S.n || !(q.species & (s ? 2 : 1))) continue;
+        k_meanq_cells<<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, S.n, q, h->G, sx, sy); CKK(h);
+    }
+    const int mx = h->P.mx, my = h->P.my, mz = h->P.dim == 3 ? h->P.mz : 1, idz = h->P.dim == 3 ? 2 : 0;
+    dim3 grid(cdiv(mx, 256), my, mz);
+    k_meanq_box<<<grid, 256, 0, h->stream>>>(sx, sy, h->f[6], h->f[7], mx, my, mz, idz); CKK(h);
+    rc = fld_fold(h); if (rc) return rc;                     // exchange_current(), :5436
+    k_meanq_norm<<<grid, 256, 0, h->stream>>>(h->f[6], h->f[7], mx, my, mz, idz, q.ratio); CKK(h);
+    return 0;
+}

@@ -127,6 +127,7 @@ int prt_sort(tgpu_ctx *h, bool classify_only);
 int prt_materialize(tgpu_ctx *h);     // apply a pending lazy permutation (+ wrap) physically
 int prt_exchange(tgpu_ctx *h);
 int prt_wall(tgpu_ctx *h, float leftwall);
+int prt_meanq(tgpu_ctx *h, const char *totname);   // meanq_fld_cur, output.F90:5229-5486
 // comm.cu
 int comm_sendrecv(tgpu_ctx *h, const void *sbuf, size_t sbytes, int dst, void *rbuf, size_t rbytes, int src);
 int comm_group_begin(tgpu_ctx *h);
