@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--cells", type=int, nargs=3, default=[512, 256, 128], help="per-GPU slab (interior cells)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-diag", action="store_true", help="diagnostic: time a second lap right after the mirror lap")
+    ap.add_argument("--e2e-plain", action="store_true", help="mirror lap as separate h2d / step / d2h calls instead of tgpu_step_mirror")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fused", type=int, default=1)
     ap.add_argument("--order", type=int, default=ORDER, help="shape order (headline = 2)")
@@ -317,27 +317,24 @@ def main():
         parts = {"h2d": 0.0, "lap": 0.0, "d2h": 0.0}
         for _ in range(args.e2e_steps):
             ta = time.perf_counter()
-            ctx.fields_h2d(*fields)
-            ctx.particles_h2d(outp, ci, ce)
-            tb = time.perf_counter()
-            if args.e2e_diag:
-                ctx.set_option("timing", 1); ctx.timers(reset=True)
-            ctx.step(1)
-            if args.e2e_diag:
-                print("diag phases of the mirror lap:", ctx.timers(reset=True), file=sys.stderr); ctx.set_option("timing", 0)
-            ctx.counts()
-            torch.cuda.synchronize()
-            tc = time.perf_counter()
-            if args.e2e_diag:
-                ctx.step(1); torch.cuda.synchronize()
-                parts["lap2"] = parts.get("lap2", 0.0) + time.perf_counter() - tc
-                ctx.set_option("timing", 1); ctx.timers(reset=True); ctx.step(1); parts["diag_phases"] = 0.0
-                print("diag phases of a lap after the mirror lap:", ctx.timers(reset=True), file=sys.stderr); ctx.set_option("timing", 0)
+            if args.e2e_plain:
+                # the call-for-call sequence: upload everything, run the lap, download everything
+                ctx.fields_h2d(*fields)
+                ctx.particles_h2d(outp, ci, ce)
+                tb = time.perf_counter()
+                ctx.step(1)
+                ctx.counts()
+                torch.cuda.synchronize()
                 tc = time.perf_counter()
-            _, ci, ce = ctx.particles_d2h(outp)
-            ctx.fields_d2h(fields)
-            td = time.perf_counter()
-            parts["h2d"] += tb - ta; parts["lap"] += tc - tb; parts["d2h"] += td - tc
+                _, ci, ce = ctx.particles_d2h(outp)
+                ctx.fields_d2h(fields)
+                td = time.perf_counter()
+                parts["h2d"] += tb - ta; parts["lap"] += tc - tb; parts["d2h"] += td - tc
+            else:
+                # tgpu_step_mirror: the same lap with host arrays in and out; on one periodic rank the particle records are
+                # streamed through the fused mover with both PCIe directions busy (elsewhere it is the sequence above)
+                ci, ce = ctx.step_mirror(fields, outp, ci, ce)
+                parts["lap"] += time.perf_counter() - ta
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / args.e2e_steps
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -357,8 +354,13 @@ def main():
         del probe, dev
         e2e = {"value": total_particles / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": fbytes + pbytes,
                "pcie_gbs_measured": link,
-               "d2h_bytes_per_step": fbytes + pbytes, "mode": "mirror: fields+particles H2D, one lap, fields+particles D2H "
-               "through tgpu_* with pinned host buffers", "ms_per_step": dt * 1e3,
+               "d2h_bytes_per_step": fbytes + pbytes,
+               "mode": ("mirror: fields+particles H2D, one lap, fields+particles D2H as separate tgpu_* calls, pinned host buffers"
+                        if args.e2e_plain else
+                        "mirror: tgpu_step_mirror, host arrays in and out every lap (pinned); " +
+                        ("particle records streamed through the fused mover, both PCIe directions busy" if world == 1 else
+                         "plain h2d + lap + d2h sequence (streaming needs a single periodic rank)")),
+               "ms_per_step": dt * 1e3,
                "ms_parts": {k: v / args.e2e_steps * 1e3 for k, v in parts.items()}}
     ctx.close()
     if rank != 0:

@@ -150,6 +150,15 @@ int tgpu_particle_bc_user_wall(tgpu_ctx *h, float leftwall);
  * params = {leftwall, binit, btheta, bphi, beta}; kind 0 = none, 1 = shock */
 int tgpu_set_user_hooks(tgpu_ctx *h, int kind, const float params[5]);
 
+/* ---- mirror mode, whole lap --------------------------------------------------------------------- */
+/* One lap with the state owned by the host (what a call-for-call GPU build of mainloop does per lap): fields and particles
+ * are read from, and written back to, the host arrays of code/fields.F90:81-88 and code/particles.F90:100 (p = the full
+ * array, ions at p[0..ions), electrons at p[maxhlf..maxhlf+lecs)).  On one rank with all axes periodic the 40-byte records
+ * are streamed through the fused mover while both PCIe directions are busy; otherwise it is fields_h2d + particles_h2d +
+ * tgpu_step + particles_d2h + fields_d2h.  Pinned host memory is needed for the copies to overlap. */
+int tgpu_step_mirror(tgpu_ctx *h, float *ex, float *ey, float *ez, float *bx, float *by, float *bz,
+                     tgpu_particle *p, int *ions, int *lecs);
+
 /* ---- output-side reductions (device-resident state) ---------------- */
 /* meanq_fld_cur(totname), code/output.F90:5229-5486: totname = 'tdens' 'idens' 'hdens' 'ldens' 'btden' 'biden',
  * '[tei]bet[xyz]', '[ti]mom[xyz]', 'eener' 'iener', '[ei]et[xyz]2'.  As in the reference the result is left in curx

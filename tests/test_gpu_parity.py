@@ -337,3 +337,29 @@ def test_meanq_fld_cur_moments(tgm, dim, order):
         ref = r.arr(O.CURX)
         assert T.max_rel(T.interior(r, got), T.interior(r, ref)) < 2e-5, name
     ctx.close()
+
+
+@pytest.mark.parametrize("order,plain", [(2, False), (1, False), (2, True)])
+def test_step_mirror_lap(tgm, order, plain):
+    """tgpu_step_mirror: host arrays in, one lap, host arrays out.  Streamed (duplex PCIe, chunked fused mover) on a
+    periodic single rank; the plain h2d + step + d2h sequence otherwise (forced here by switching phase timing on)."""
+    w, ctx = make(tgm, dim=3, order=order, n=(16, 16, 12), ppc=4.0, ntimes=2, filter_kind=2)
+    r = w.ranks[0]
+    if plain:
+        ctx.set_option("timing", 1)
+    for lap in range(2):
+        fields = [np.ascontiguousarray(a).copy() for a in r.fields()]
+        p = r.particles().copy()
+        ions, lecs = r.counts
+        ni, ne = ctx.step_mirror(fields, p, ions, lecs)
+        w.step()
+        assert (ni, ne) == tuple(r.counts)
+        for a in range(6):
+            assert T.max_rel(T.interior(r, fields[a]), T.interior(r, r.arr(a))) < 2e-4, (lap, O.ARR_NAMES[a])
+        po_i, po_e = T.oracle_particles(r)
+        T.assert_particles_close(T.sort_particles(p[:ni].copy()), po_i, what=f"mirror ions lap {lap}")
+        T.assert_particles_close(T.sort_particles(p[ctx.maxhlf:ctx.maxhlf + ne].copy()), po_e, what=f"mirror electrons lap {lap}")
+        # the device copy is consistent with what went back to the host
+        pg_i, pg_e = T.gpu_particles(ctx)
+        T.assert_particles_close(pg_i, po_i, what="device copy after the mirror lap")
+    ctx.close()

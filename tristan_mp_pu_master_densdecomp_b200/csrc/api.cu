@@ -87,6 +87,8 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     CK(cudaEventCreateWithFlags(&h->ev_move, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_prt, cudaEventDisableTiming));
     h->opt_lazy = getenv("TGPU_LAZY") ? atoi(getenv("TGPU_LAZY")) : 1;
     for (int b = 0; b < 2; b++) { CK(cudaEventCreateWithFlags(&h->ev_stage_full[b], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_stage_free[b], cudaEventDisableTiming)); }
+    for (int b = 0; b < 2; b++) { CK(cudaEventCreateWithFlags(&h->ev_out_full[b], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_out_free[b], cudaEventDisableTiming)); }
+    CK(cudaStreamCreateWithFlags(&h->stream_d2h, cudaStreamNonBlocking));
     h->prt_pending = 0; h->opt_overlap = getenv("TGPU_OVERLAP") ? atoi(getenv("TGPU_OVERLAP")) : 1; h->nccl_main = h->nccl_prt = nullptr;
     h->maxhlf = p->maxptl / 2;
     DevGeom &G = h->G;
@@ -165,6 +167,8 @@ extern "C" int tgpu_finalize(tgpu_ctx *h)
     for (int s = 0; s < 2; s++) { free_species(h->sp[s]); free_species(h->alt[s]); cudaFree(h->key[s]); cudaFree(h->perm[s]); }
     cudaFree(h->slot); cudaFree(h->bincount); cudaFree(h->binoff); cudaFree(h->cub_tmp); cudaFree(h->d_small);
     cudaFreeHost(h->h_small); cudaFree(h->stage);
+    for (int b = 0; b < 2; b++) { cudaEventDestroy(h->ev_out_full[b]); cudaEventDestroy(h->ev_out_free[b]); }
+    cudaStreamDestroy(h->stream_d2h);
     if (h->sendbuf) cudaFree(h->sendbuf);
     if (h->recvbuf) cudaFree(h->recvbuf);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev_move); cudaEventDestroy(h->ev_prt);
@@ -344,6 +348,59 @@ extern "C" int tgpu_set_user_hooks(tgpu_ctx *h, int kind, const float params[5])
     if (!h || kind < 0 || kind > 1 || (kind && !params)) return TGPU_EINVAL;
     h->hook_kind = kind;
     for (int i = 0; i < 5; i++) h->hook[i] = kind ? params[i] : 0.f;
+    return 0;
+}
+
+// ---- mirror mode, whole lap ----------------------------------------------------------------------------
+// One lap with the state owned by the host: fields and particles come in from host arrays and go back to them, i.e. what
+// a call-for-call GPU build of mainloop would do per lap (fields_h2d, particles_h2d, every tgpu_* of the lap,
+// particles_d2h, fields_d2h).  When nobody can leave the rank (one rank, all axes periodic) and the fused mover applies,
+// the particle array is STREAMED: inbound chunks, the fused mover + deposit and outbound chunks overlap, so the lap costs
+// max(H2D, D2H) of the 40-byte records instead of their sum.  Otherwise the plain sequence runs.
+// Returns the particles in the host's order (streamed) or cell-sorted (plain); compare by (proc, ind).
+extern "C" int tgpu_step_mirror(tgpu_ctx *h, float *ex, float *ey, float *ez, float *bx, float *by, float *bz,
+                                tgpu_particle *p, int *ions, int *lecs)
+{
+    ENTER(h);
+    if (!ex || !ey || !ez || !bx || !by || !bz || !p || !ions || !lecs) { tgpu_set_error("null argument"); return TGPU_EINVAL; }
+    const bool stream_ok = h->size0 == 1 && h->P.periodicx && h->P.periodicy && (h->P.dim == 2 || h->P.periodicz) &&
+                           h->opt_fused && cellrun_supported(h) && h->hook_kind == 0 && h->stage_particles >= 4 && !h->timing;
+    int rc;
+    if (!stream_ok) {
+        rc = tgpu_fields_h2d(h, ex, ey, ez, bx, by, bz); if (rc) return rc;
+        rc = tgpu_particles_h2d(h, p, *ions, *lecs); if (rc) return rc;
+        rc = tgpu_step(h, 1); if (rc) return rc;
+        rc = tgpu_particles_d2h(h, p, ions, lecs); if (rc) return rc;
+        return tgpu_fields_d2h(h, ex, ey, ez, bx, by, bz);
+    }
+    float *hf[6] = {ex, ey, ez, bx, by, bz};
+    const size_t fbytes = (size_t)h->G.lot * sizeof(float);
+    h->in_step = 1;
+#define DO(x) do { rc = (x); if (rc) { h->in_step = 0; return rc; } } while (0)
+#define CKS(x) do { if ((x) != cudaSuccess) { h->in_step = 0; tgpu_set_error(#x); return TGPU_ECUDA; } } while (0)
+    for (int a = 0; a < 6; a++) CKS(cudaMemcpyAsync(h->f[a], hf[a], fbytes, cudaMemcpyHostToDevice, h->stream_main));
+    h->need_prim = 1; h->fused_pending = 0; h->lap++;
+    DO(tgpu_bc_e1(h));                 // :118
+    DO(tgpu_advance_b_halfstep(h));    // :119
+    DO(tgpu_bc_b1(h));                 // :122
+    DO(fld_primal(h));
+    DO(prt_mirror_stream(h, p, *ions, *lecs));       // :134 + particle part of :183, streamed
+    DO(tgpu_advance_b_halfstep(h));    // :139
+    DO(tgpu_bc_b1(h));                 // :140
+    DO(tgpu_advance_e_fullstep(h));    // :159
+    DO(tgpu_reset_currents(h));        // :171
+    DO(fld_add_shadow(h));             // :183, current part
+    DO(tgpu_exchange_current(h));      // :203
+    DO(tgpu_apply_filter(h));          // :213-229
+    DO(tgpu_add_current(h));           // :242
+    for (int a = 0; a < 6; a++) CKS(cudaMemcpyAsync(hf[a], h->f[a], fbytes, cudaMemcpyDeviceToHost, h->stream_main));
+    CKS(cudaStreamSynchronize(h->stream_d2h));
+    CKS(cudaStreamSynchronize(h->stream_main));
+#undef DO
+#undef CKS
+    h->in_step = 0;
+    *ions = h->sp[0].n; *lecs = h->sp[1].n;
+    for (int s = 0; s < 2; s++) for (int c = 0; c < 11; c++) h->h_small[s * 16 + c] = h->sp[s].n;
     return 0;
 }
 

@@ -515,6 +515,34 @@ int cellrun_move_deposit(tgpu_ctx *h)
     return 0;
 }
 
+// Streamed mirror lap (api.cu tgpu_step_mirror): fused gather + push + deposit of the records [off, off + cnt) of species s,
+// in place.  The caller has refreshed the node-centred fields (fld_primal) and zeroed nothing: key / slot / bincount are
+// written as in a resident lap but not used.
+int cellrun_move_deposit_range(tgpu_ctx *h, int s, int off, int cnt)
+{
+    if (cnt <= 0) return 0;
+    const Species &S = h->sp[s];
+    CRArgs A;
+    Species R = S;
+    R.x += off; R.y += off; R.z += off; R.u += off; R.v += off; R.w += off; R.ch += off; R.ind += off; R.tag += off; R.n = cnt;
+    A.s = R; A.d = R; A.perm = nullptr;
+    A.n = cnt; A.prim8 = h->prim8; A.cx = h->shadow[0]; A.cy = h->shadow[1]; A.cz = h->shadow[2]; A.nty = h->nty; A.G = h->G;
+    A.qm = s ? h->P.qme : h->P.qmi; A.qs = s ? h->P.qe : h->P.qi;
+    const size_t nb = (size_t)h->G.lot + TGPU_NBIN_EXTRA;
+    A.key = h->key[s] + off; A.slot = h->slot + (size_t)s * h->maxhlf + off; A.bincount = h->bincount + (size_t)s * nb;
+    long long warps = ((long long)cnt + 2 * CR_CHUNK - 1) / (2 * CR_CHUNK);
+    int blocks = (int)((warps + CR_WARPS - 1) / CR_WARPS);
+    if (h->P.order == 2) {
+        CK(cudaFuncSetAttribute(k_cellrun<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM_BYTES));
+        k_cellrun<2, true><<<blocks, CR_WARPS * 32, CR_SMEM_BYTES, h->stream>>>(A);
+    } else {
+        CK(cudaFuncSetAttribute(k_cellrun<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM_BYTES));
+        k_cellrun<1, true><<<blocks, CR_WARPS * 32, CR_SMEM_BYTES, h->stream>>>(A);
+    }
+    CKK(h);
+    return 0;
+}
+
 // tgpu_deposit_particles fast path when the particles were moved elsewhere (mirror mode, tests)
 int cellrun_deposit(tgpu_ctx *h)
 {

@@ -32,6 +32,24 @@ __global__ void __launch_bounds__(256) k_soa2aos(tgpu_particle *__restrict__ a, 
     a[t] = p;
 }
 
+// SoA -> AoS of freshly pushed records, applying the periodic wrap of deposit_particles loop B
+// (particles_movedeposit.F90:1546-1633) on the way; the wrapped position is also written back to the SoA
+__global__ void __launch_bounds__(256) k_soa2aos_wrap(tgpu_particle *__restrict__ a, Species s, int off, int n, DevGeom G)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int d = off + t;
+    tgpu_particle p;
+    float x = s.x[d], y = s.y[d], z = s.z[d];
+    if (x < G.minx) x += G.shiftx_lo; else if (x > G.maxx) x -= G.shiftx_hi;
+    if (y < G.miny) y += G.shifty_lo; else if (y > G.maxy) y -= G.shifty_hi;
+    if (G.dim == 3) { if (z < G.minz) z += G.shiftz_lo; else if (z > G.maxz) z -= G.shiftz_hi; }
+    s.x[d] = x; s.y[d] = y; s.z[d] = z;
+    p.x = x; p.y = y; p.z = z; p.u = s.u[d]; p.v = s.v[d]; p.w = s.w[d]; p.ch = s.ch[d];
+    p.ind = s.ind[d]; int tg = s.tag[d]; p.proc = tg & 0xFFFFFF; p.splitlev = (tg >> 24) & 0xFF;
+    a[t] = p;
+}
+
 __global__ void __launch_bounds__(256) k_iota(int32_t *__restrict__ a, int first, int n)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -848,4 +866,51 @@ int prt_meanq(tgpu_ctx *h, const char *totname)
     rc = fld_fold(h); if (rc) return rc;                     // exchange_current(), :5436
     k_meanq_norm<<<grid, 256, 0, h->stream>>>(h->f[6], h->f[7], mx, my, mz, idz, q.ratio); CKK(h);
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streamed mirror lap, particle side (tgpu_step_mirror): the host array crosses PCIe in both directions at once.
+// Four staging quarters (two inbound, two outbound); per chunk:  H2D copy (stream_prt)  ->  AoS->SoA, fused mover +
+// deposit, wrap + SoA->AoS (stream_main)  ->  D2H copy (stream_d2h).  Chunk k+1 is inbound while chunk k is pushed and
+// chunk k-1 is outbound, so a lap costs max(H2D, D2H) instead of H2D + lap + D2H.
+// Only for one rank with all axes periodic (nobody leaves or is discarded): the caller checks.
+// ---------------------------------------------------------------------------------------------
+int cellrun_move_deposit_range(tgpu_ctx *h, int s, int off, int cnt);
+int prt_mirror_stream(tgpu_ctx *h, tgpu_particle *p, int ions, int lecs)
+{
+    if (ions < 0 || lecs < 0 || ions > h->maxhlf || lecs > h->maxhlf) { tgpu_set_error("bad particle counts"); return TGPU_EINVAL; }
+    const size_t quarter = h->stage_particles / 4;
+    if (quarter < 1) { tgpu_set_error("staging buffer too small for the streamed mirror lap"); return TGPU_EINVAL; }
+    cudaStream_t sm = h->stream_main, sh = h->stream_prt, sd = h->stream_d2h;
+    h->sp[0].n = ions; h->sp[1].n = lecs; h->keys_valid = 0;
+    h->lazy[0] = h->lazy[1] = 0; h->nphys[0] = ions; h->nphys[1] = lecs;
+    const size_t nb = (size_t)h->G.lot + TGPU_NBIN_EXTRA;
+    CK(cudaMemsetAsync(h->bincount, 0, 2 * nb * sizeof(int32_t), sm));
+    for (int b = 0; b < 2; b++) { CK(cudaEventRecord(h->ev_stage_free[b], sm)); CK(cudaEventRecord(h->ev_out_free[b], sd)); }
+    int i = 0;
+    for (int s = 0; s < 2; s++) {
+        Species &S = h->sp[s];
+        tgpu_particle *hp = p + (s ? h->maxhlf : 0);
+        int done = 0;
+        while (done < S.n) {
+            const int b = i & 1;
+            int chunk = S.n - done; if ((size_t)chunk > quarter) chunk = (int)quarter;
+            tgpu_particle *sin = h->stage + (size_t)b * quarter, *sout = h->stage + (size_t)(2 + b) * quarter;
+            CK(cudaStreamWaitEvent(sh, h->ev_stage_free[b], 0));
+            CK(cudaMemcpyAsync(sin, hp + done, (size_t)chunk * sizeof(tgpu_particle), cudaMemcpyHostToDevice, sh));
+            CK(cudaEventRecord(h->ev_stage_full[b], sh));
+            CK(cudaStreamWaitEvent(sm, h->ev_stage_full[b], 0));
+            k_aos2soa<<<cdiv(chunk, 256), 256, 0, sm>>>(sin, S, done, chunk); CKK(h);
+            CK(cudaEventRecord(h->ev_stage_free[b], sm));
+            { int rc = cellrun_move_deposit_range(h, s, done, chunk); if (rc) return rc; }
+            CK(cudaStreamWaitEvent(sm, h->ev_out_free[b], 0));
+            k_soa2aos_wrap<<<cdiv(chunk, 256), 256, 0, sm>>>(sout, S, done, chunk, h->G); CKK(h);
+            CK(cudaEventRecord(h->ev_out_full[b], sm));
+            CK(cudaStreamWaitEvent(sd, h->ev_out_full[b], 0));
+            CK(cudaMemcpyAsync(hp + done, sout, (size_t)chunk * sizeof(tgpu_particle), cudaMemcpyDeviceToHost, sd));
+            CK(cudaEventRecord(h->ev_out_free[b], sd));
+            done += chunk; i++;
+        }
+    }
+    return 0;          // the caller joins stream_d2h after the field phase
 }

@@ -70,6 +70,8 @@ struct tgpu_ctx {
     cudaStream_t stream_main, stream_prt;   // tgpu_step overlaps the particle sort/migration (stream_prt) with the field phase
     cudaEvent_t ev0, ev1, ev_move, ev_prt;
     cudaEvent_t ev_stage_full[2], ev_stage_free[2];   // double-buffered AoS staging for h2d / d2h
+    cudaEvent_t ev_out_full[2], ev_out_free[2];       // outbound staging of the streamed mirror lap
+    cudaStream_t stream_d2h;                          // device -> host copies of the streamed mirror lap
     int in_step;
     int prt_pending;         // ev_prt must be waited for before the particle arrays are touched on stream_main
     int opt_overlap;
@@ -127,7 +129,8 @@ int prt_sort(tgpu_ctx *h, bool classify_only);
 int prt_materialize(tgpu_ctx *h);     // apply a pending lazy permutation (+ wrap) physically
 int prt_exchange(tgpu_ctx *h);
 int prt_wall(tgpu_ctx *h, float leftwall);
-int prt_meanq(tgpu_ctx *h, const char *totname);   // meanq_fld_cur, output.F90:5229-5486
+int prt_meanq(tgpu_ctx *h, const char *totname);
+int prt_mirror_stream(tgpu_ctx *h, tgpu_particle *p, int ions, int lecs);   // particle side of tgpu_step_mirror   // meanq_fld_cur, output.F90:5229-5486
 // comm.cu
 int comm_sendrecv(tgpu_ctx *h, const void *sbuf, size_t sbytes, int dst, void *rbuf, size_t rbytes, int src);
 int comm_group_begin(tgpu_ctx *h);
