@@ -54,6 +54,10 @@ __device__ __forceinline__ void shape6(float d, int shift, float W6[6])
     W6[5] = shift > 0 ? s5 : 0.f;
 }
 
+__device__ __forceinline__ void c3_cp_async4(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void red_nz3(float *p, float v)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %1, 0f00000000;\n\t@p red.global.add.f32 [%0], %1;\n\t}"
@@ -66,7 +70,7 @@ __device__ __forceinline__ void red3c(float *cx, float *cy, float *cz, size_t id
 
 __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
 {
-    extern __shared__ __align__(16) float stage3[];        // [C3_WARPS][32][C3_STRIDE]
+    extern __shared__ __align__(16) float stage3[];        // [C3_WARPS][32][C3_STRIDE] factor staging, then the record pipeline
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long gw = (long long)blockIdx.x * C3_WARPS + warp;
     const long long base = gw * C3_CHUNK;
@@ -82,13 +86,30 @@ __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
     bool have = false;
     float ax[6] = {0, 0, 0, 0, 0, 0}, ay[6] = {0, 0, 0, 0, 0, 0}, az[6] = {0, 0, 0, 0, 0, 0};
 
+    // record pipeline (same idea as cellrun.cu): the next step's seven floats per lane are fetched with 4-byte cp.async
+    // into per-lane landing slots while the current step is being deposited
+    uint32_t *rec = reinterpret_cast<uint32_t *>(stage3 + (size_t)C3_WARPS * 32 * C3_STRIDE) + (size_t)warp * 2 * 7 * 32;
+    auto fetch = [&](int buf, long long tt) {
+        if (tt < A.n) {
+            uint32_t *r = rec + (size_t)buf * 7 * 32 + lane;
+            c3_cp_async4(r + 0 * 32, A.s.x + tt); c3_cp_async4(r + 1 * 32, A.s.y + tt); c3_cp_async4(r + 2 * 32, A.s.z + tt);
+            c3_cp_async4(r + 3 * 32, A.s.u + tt); c3_cp_async4(r + 4 * 32, A.s.v + tt); c3_cp_async4(r + 5 * 32, A.s.w + tt);
+            c3_cp_async4(r + 6 * 32, A.s.ch + tt);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(0, base + lane);
     for (int it = 0; it < C3_CHUNK / 32; ++it) {
         const long long t = base + it * 32 + lane;
         float *st = wst + lane * C3_STRIDE;
         int ci = -1, crow = -1;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (it + 1 < C3_CHUNK / 32) fetch((it + 1) & 1, t + 32);
         if (t < A.n) {
-            const float x = A.s.x[t], y = A.s.y[t], z = A.s.z[t], u = A.s.u[t], v = A.s.v[t], w = A.s.w[t];
-            const float q = A.s.ch[t] * A.qs;
+            const uint32_t *r = rec + (size_t)(it & 1) * 7 * 32 + lane;
+            const float x = __uint_as_float(r[0 * 32]), y = __uint_as_float(r[1 * 32]), z = __uint_as_float(r[2 * 32]);
+            const float u = __uint_as_float(r[3 * 32]), v = __uint_as_float(r[4 * 32]), w = __uint_as_float(r[5 * 32]);
+            const float q = __uint_as_float(r[6 * 32]) * A.qs;
             // old position recomputed from the new one (particles_movedeposit.F90:1384-1390)
             const float invgam = 1.f / sqrtf(1 + u * u + v * v + w * w);
             const float x1 = x - u * invgam * G.c, y1 = y - v * invgam * G.c, z1 = z - w * invgam * G.c;
@@ -221,7 +242,7 @@ int cellrun3_supported(const tgpu_ctx *h) { return h->P.dim == 3 && h->P.order =
 int cellrun3_deposit(tgpu_ctx *h)
 {
     int rc = prt_materialize(h); if (rc) return rc;
-    const size_t smem = (size_t)C3_WARPS * 32 * C3_STRIDE * sizeof(float);
+    const size_t smem = (size_t)C3_WARPS * 32 * C3_STRIDE * sizeof(float) + (size_t)C3_WARPS * 2 * 7 * 32 * sizeof(uint32_t);
     CK(cudaFuncSetAttribute(k_cellrun3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int s = 0; s < 2; s++) {
         Species &S = h->sp[s];
