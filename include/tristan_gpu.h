@@ -164,6 +164,10 @@ int tgpu_step_mirror(tgpu_ctx *h, float *ex, float *ey, float *ez, float *bx, fl
  * '[tei]bet[xyz]', '[ti]mom[xyz]', 'eener' 'iener', '[ei]et[xyz]2'.  As in the reference the result is left in curx
  * (cury = weight, curz = 0): read it with tgpu_currents_d2h.  Destroys the currents, like the reference (output laps only). */
 int tgpu_meanq_fld_cur(tgpu_ctx *h, const char *totname);
+/* the prtl.tot sub-sample, code/output.F90:3526-3551: every particle with modulo(ind/2, stride) == 0, compacted on the
+ * device; ions to out[0 .. *n_ion), electrons to out[capacity .. capacity + *n_lec).  Positions are rank-local (the host adds
+ * mxcum/mycum/mzcum as output.F90 does).  TGPU_EOVERFLOW if a species selects more than `capacity`. */
+int tgpu_select_particles(tgpu_ctx *h, int stride, tgpu_particle *out, int capacity, int *n_ion, int *n_lec);
 
 /* ---- whole lap, resident mode: tristanmainloop.F90:107-344 with Appendix-B de-duplication ---- */
 int tgpu_step(tgpu_ctx *h, int nlaps);

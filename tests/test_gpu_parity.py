@@ -363,3 +363,24 @@ def test_step_mirror_lap(tgm, order, plain):
         pg_i, pg_e = T.gpu_particles(ctx)
         T.assert_particles_close(pg_i, po_i, what="device copy after the mirror lap")
     ctx.close()
+
+
+def test_select_particles_prtl_tot(tgm):
+    """prtl.tot selection (output.F90:3526-3551): modulo(ind/2, stride) == 0, compacted on the device"""
+    w, ctx = make(tgm, dim=3, order=2, n=(12, 10, 8), ppc=4.0)
+    r = w.ranks[0]
+    r.particles()["ind"][::5] *= -1
+    T.upload(ctx, r)
+    ctx.step(1)                                            # selection works on lazily sorted device state too
+    pall, ions, lecs = ctx.particles_d2h()
+    for stride in (1, 3, 20):
+        gi, ge = ctx.select_particles(stride, capacity=max(ions, lecs))
+        for got, ref in ((gi, pall[:ions]), (ge, pall[ctx.maxhlf:ctx.maxhlf + lecs])):
+            # Fortran: ind/2 truncates toward zero; modulo(., stride) == 0 <=> divisible
+            keep = (np.trunc(ref["ind"] / 2).astype(np.int64) % stride) == 0
+            want = T.sort_particles(ref[keep].copy())
+            got = T.sort_particles(got)
+            assert got.size == want.size and np.array_equal(got, want), stride
+    with pytest.raises(tgm.TristanGPUError):
+        ctx.select_particles(1, capacity=8)                # overflow is loud
+    ctx.close()

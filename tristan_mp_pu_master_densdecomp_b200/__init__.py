@@ -53,7 +53,7 @@ ABI_SYMBOLS = [
     "tgpu_add_current", "tgpu_bc_b1", "tgpu_bc_e1", "tgpu_bc_b2", "tgpu_bc_e2", "tgpu_exchange_current",
     "tgpu_apply_filter", "tgpu_apply_filter1_opt", "tgpu_apply_filter2_opt", "tgpu_move_particles",
     "tgpu_deposit_particles", "tgpu_exchange_particles", "tgpu_inject_others", "tgpu_reorder_particles",
-    "tgpu_meanq_fld_cur", "tgpu_step_mirror", "tgpu_field_bc_user_shock", "tgpu_particle_bc_user_wall", "tgpu_set_user_hooks", "tgpu_step", "tgpu_timers", "tgpu_launch_count", "tgpu_stream", "tgpu_set_option",
+    "tgpu_meanq_fld_cur", "tgpu_select_particles", "tgpu_step_mirror", "tgpu_field_bc_user_shock", "tgpu_particle_bc_user_wall", "tgpu_set_user_hooks", "tgpu_step", "tgpu_timers", "tgpu_launch_count", "tgpu_stream", "tgpu_set_option",
 ]
 
 _lib = None
@@ -94,6 +94,7 @@ def load_library(path=None):
         getattr(L, name).argtypes = [vp]
     L.tgpu_field_bc_user_shock.argtypes = [vp] + [C.c_float] * 5
     L.tgpu_meanq_fld_cur.argtypes = [vp, C.c_char_p]
+    L.tgpu_select_particles.argtypes = [vp, ci, vp, ci, C.POINTER(ci), C.POINTER(ci)]
     L.tgpu_step_mirror.argtypes = [vp] + [fp] * 6 + [vp, C.POINTER(ci), C.POINTER(ci)]
     L.tgpu_particle_bc_user_wall.argtypes = [vp, C.c_float]
     L.tgpu_set_user_hooks.argtypes = [vp, ci, C.POINTER(C.c_float)]
@@ -293,6 +294,14 @@ class Context:
         self._ck(self.lib.tgpu_step_mirror(self.h, *[_fptr(a) for a in fields], p.ctypes.data_as(C.c_void_p),
                                            C.byref(ni), C.byref(ne)), "step_mirror")
         return ni.value, ne.value
+
+    def select_particles(self, stride, capacity):
+        """prtl.tot sub-sample (output.F90:3526-3551): returns (ions, electrons) with modulo(ind/2, stride) == 0."""
+        out = np.zeros(2 * capacity, PARTICLE_DTYPE)
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.lib.tgpu_select_particles(self.h, stride, out.ctypes.data_as(C.c_void_p), capacity, C.byref(a), C.byref(b)),
+                 "select_particles")
+        return out[:a.value].copy(), out[capacity:capacity + b.value].copy()
 
     def meanq_fld_cur(self, totname):
         """output.F90:5229-5486 on the device: moment `totname` into curx (read it with currents_d2h()[0])."""

@@ -408,6 +408,11 @@ extern "C" int tgpu_step_mirror(tgpu_ctx *h, float *ex, float *ey, float *ez, fl
 // meanq_fld_cur(totname), output.F90:5229-5486: the moment lands in curx (cury = weight), as in the reference; the host
 // reads it with tgpu_currents_d2h instead of pulling every particle across PCIe on an output lap
 extern "C" int tgpu_meanq_fld_cur(tgpu_ctx *h, const char *totname) { ENTER(h); return prt_meanq(h, totname); }
+// the prtl.tot sub-sample, output.F90:3526-3551: particles with modulo(ind/2, stride) == 0
+extern "C" int tgpu_select_particles(tgpu_ctx *h, int stride, tgpu_particle *out, int capacity, int *n_ion, int *n_lec)
+{
+    ENTER(h); return prt_select(h, stride, out, capacity, n_ion, n_lec);
+}
 
 // ---- whole lap -------------------------------------------------------------------------------------
 // Call order of tristanmainloop.F90:107-344 with the redundant ghost refreshes of Appendix B removed: three

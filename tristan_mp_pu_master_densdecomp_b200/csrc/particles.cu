@@ -914,3 +914,45 @@ int prt_mirror_stream(tgpu_ctx *h, tgpu_particle *p, int ions, int lecs)
     }
     return 0;          // the caller joins stream_d2h after the field phase
 }
+
+// ---------------------------------------------------------------------------------------------
+// Output-side particle sub-sampling: the prtl.tot selection of output.F90:3526-3551, modulo(ind/2, stride) == 0.
+// Stream compaction on the device so that an output lap moves 1/stride of the particles across PCIe, not all of them.
+// Selected ions land at out[0 .. n_ion), electrons at out[capacity .. capacity + n_lec) (order within a species is not the
+// array order of the reference; identify particles by (proc, ind)).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_select(Species s, int n, int stride, tgpu_particle *__restrict__ out, int cap, int32_t *__restrict__ counter)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int ind = s.ind[t];
+    if ((ind / 2) % stride != 0) return;                       // Fortran integer division truncates, like C
+    const int pos = atomicAdd(counter, 1);
+    if (pos >= cap) return;
+    tgpu_particle p;
+    p.x = s.x[t]; p.y = s.y[t]; p.z = s.z[t]; p.u = s.u[t]; p.v = s.v[t]; p.w = s.w[t]; p.ch = s.ch[t];
+    p.ind = ind; const int tg = s.tag[t]; p.proc = tg & 0xFFFFFF; p.splitlev = (tg >> 24) & 0xFF;
+    out[pos] = p;
+}
+int prt_select(tgpu_ctx *h, int stride, tgpu_particle *out_host, int capacity, int *n_ion, int *n_lec)
+{
+    if (stride < 1 || capacity < 0 || !out_host || !n_ion || !n_lec) { tgpu_set_error("select_particles: bad arguments"); return TGPU_EINVAL; }
+    int rc = prt_materialize(h); if (rc) return rc;
+    const size_t half = h->stage_particles / 2;
+    if ((size_t)capacity > half) { tgpu_set_error("select_particles: capacity exceeds the staging buffer (stage_particles / 2)"); return TGPU_EINVAL; }
+    CK(cudaMemsetAsync(h->d_small + 64, 0, 2 * sizeof(int32_t), h->stream));
+    for (int s = 0; s < 2; s++) {
+        Species &S = h->sp[s];
+        if (!S.n || !capacity) continue;
+        k_select<<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, S.n, stride, h->stage + (size_t)s * half, capacity, h->d_small + 64 + s); CKK(h);
+    }
+    int32_t cnt[2];
+    CK(cudaMemcpyAsync(cnt, h->d_small + 64, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (cnt[0] > capacity || cnt[1] > capacity) { tgpu_set_error("select_particles: more selected particles than capacity"); return TGPU_EOVERFLOW; }
+    for (int s = 0; s < 2; s++)
+        if (cnt[s]) CK(cudaMemcpyAsync(out_host + (size_t)s * capacity, h->stage + (size_t)s * half, (size_t)cnt[s] * sizeof(tgpu_particle), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *n_ion = cnt[0]; *n_lec = cnt[1];
+    return 0;
+}

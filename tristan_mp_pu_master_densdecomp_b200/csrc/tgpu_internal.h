@@ -130,6 +130,7 @@ int prt_materialize(tgpu_ctx *h);     // apply a pending lazy permutation (+ wra
 int prt_exchange(tgpu_ctx *h);
 int prt_wall(tgpu_ctx *h, float leftwall);
 int prt_meanq(tgpu_ctx *h, const char *totname);
+int prt_select(tgpu_ctx *h, int stride, tgpu_particle *out_host, int capacity, int *n_ion, int *n_lec);   // prtl.tot selection
 int prt_mirror_stream(tgpu_ctx *h, tgpu_particle *p, int ions, int lecs);   // particle side of tgpu_step_mirror   // meanq_fld_cur, output.F90:5229-5486
 // comm.cu
 int comm_sendrecv(tgpu_ctx *h, const void *sbuf, size_t sbytes, int dst, void *rbuf, size_t rbytes, int src);
