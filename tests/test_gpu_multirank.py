@@ -63,7 +63,12 @@ CASES = {
     2: [dict(dim=3, order=2, n=(12, 12, 16), sizes=(1, 1, 2), filter_kind=2),
         dict(dim=3, order=1, n=(12, 16, 12), sizes=(1, 2, 1), filter_kind=1),
         dict(dim=3, order=3, n=(12, 12, 16), sizes=(1, 1, 2), filter_kind=2),
-        dict(dim=2, order=2, n=(16, 16, 1), sizes=(2, 1, 1), filter_kind=1)],
+        dict(dim=2, order=2, n=(16, 16, 1), sizes=(2, 1, 1), filter_kind=1),
+        # open (radiating) x: bc_b2 / bc_e2 run `surface`, leavers through the x faces are discarded
+        dict(dim=3, order=2, n=(16, 12, 16), sizes=(1, 1, 2), filter_kind=2, periodic=(0, 1, 1)),
+        dict(dim=2, order=1, n=(24, 16, 1), sizes=(2, 1, 1), filter_kind=1, periodic=(0, 1, 1)),
+        # 4th-order field solver across a slab boundary
+        dict(dim=3, order=2, n=(12, 12, 16), sizes=(1, 1, 2), filter_kind=2, highorder=1)],
     4: [dict(dim=3, order=2, n=(12, 16, 16), sizes=(1, 2, 2), filter_kind=2),
         dict(dim=2, order=1, n=(16, 16, 1), sizes=(2, 2, 1), filter_kind=1)],
     8: [dict(dim=3, order=2, n=(12, 16, 32), sizes=(1, 2, 4), filter_kind=2)],
@@ -88,7 +93,7 @@ def _run(world, case):
     assert sum(m for _, _, m in res) > 0, "no particle migrated"
 
 
-@pytest.mark.parametrize("case", CASES[2], ids=["3d-z", "3d-y", "3d-z-o3", "2d-x"])
+@pytest.mark.parametrize("case", CASES[2], ids=["3d-z", "3d-y", "3d-z-o3", "2d-x", "3d-z-openx", "2d-x-openx", "3d-z-highorder"])
 def test_two_gpus(tg, case):
     _run(2, case)
 

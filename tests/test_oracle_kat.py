@@ -93,12 +93,17 @@ def test_particle_count_and_identity_conserved_across_ranks():
             assert p["z"].min() >= g + 1 and p["z"].max() <= r.mz - g
 
 
-@pytest.mark.parametrize("dim,sizes", [(3, (1, 2, 2)), (3, (1, 1, 2)), (2, (2, 2, 1)), (2, (1, 2, 1))])
+@pytest.mark.parametrize("dim,sizes,periodic", [(3, (1, 2, 2), (1, 1, 1)), (3, (1, 1, 2), (1, 1, 1)), (2, (2, 2, 1), (1, 1, 1)),
+                                                (2, (1, 2, 1), (1, 1, 1)), (3, (1, 1, 2), (0, 1, 1)), (2, (2, 1, 1), (0, 1, 1)),
+                                                (2, (1, 2, 1), (0, 1, 1))])
 @pytest.mark.parametrize("order,kind", [(1, 1), (2, 2)])
-def test_decomposition_invariance(dim, sizes, order, kind):
-    """the multi-rank world reproduces the single-rank world: fields to reordering round-off, particles exactly matched"""
+def test_decomposition_invariance(dim, sizes, periodic, order, kind):
+    """the multi-rank world reproduces the single-rank world: fields to reordering round-off, particles exactly matched
+    (also with an open, radiating x axis: `surface` runs on every rank's outer planes and the ghost refresh overwrites
+    the ones that are not physical boundaries)"""
     n = (12, 12, 12) if dim == 3 else (16, 16, 1)
-    kw = dict(dim=dim, order=order, n=n, ppc=4.0, ntimes=3, filter_kind=kind if dim == 3 else 1, delgam=0.02, seed_fields=0)
+    kw = dict(dim=dim, order=order, n=n, ppc=4.0, ntimes=3, filter_kind=kind if dim == 3 else 1, delgam=0.02, seed_fields=0,
+              periodic=periodic)
     w1 = T.oracle_world(sizes=(1, 1, 1), **kw)
     wn = T.oracle_world(sizes=sizes, **kw)
     # same particles: scatter the single-rank load onto the slabs
