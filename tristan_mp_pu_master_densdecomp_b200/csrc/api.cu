@@ -89,6 +89,7 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     for (int b = 0; b < 2; b++) { CK(cudaEventCreateWithFlags(&h->ev_stage_full[b], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_stage_free[b], cudaEventDisableTiming)); }
     for (int b = 0; b < 2; b++) { CK(cudaEventCreateWithFlags(&h->ev_out_full[b], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_out_free[b], cudaEventDisableTiming)); }
     CK(cudaStreamCreateWithFlags(&h->stream_d2h, cudaStreamNonBlocking));
+    h->presort = 0;
     h->prt_pending = 0; h->opt_overlap = getenv("TGPU_OVERLAP") ? atoi(getenv("TGPU_OVERLAP")) : 1; h->nccl_main = h->nccl_prt = nullptr;
     h->maxhlf = p->maxptl / 2;
     DevGeom &G = h->G;

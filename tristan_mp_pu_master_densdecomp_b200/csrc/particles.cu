@@ -100,6 +100,7 @@ int prt_h2d(tgpu_ctx *h, const tgpu_particle *p, int ions, int lecs)
     int rc = prt_append(h, 0, p, ions, true); if (rc) return rc;
     rc = prt_append(h, 1, p + h->maxhlf, lecs, true); if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
+    h->presort = 1;          // host order (the reference sorts only every 10 laps): see cellrun_move_deposit
     return 0;
 }
 int prt_d2h(tgpu_ctx *h, tgpu_particle *p, int *ions, int *lecs)

@@ -60,6 +60,7 @@ struct tgpu_ctx {
     size_t stage_particles;
     tgpu_particle *sendbuf, *recvbuf;   // TGPU_NDIR * buffsize each
     int need_prim;           // primal grids stale
+    int presort;             // records were uploaded in host order: cell-sort them once before the next fused mover
     int fused_pending;       // currents of the last move already deposited into shadow
     float *shadow[3];        // tiled: [tz][ty][i][4x4 (y,z) tile] (cellrun.cu row_index), nty x ntz tiles
     int nty, ntz; size_t shadow_floats;
