@@ -9,18 +9,25 @@
 // Particles are kept sorted by cell (x fastest) by the counting sort that follows every deposit.  All particles of a
 // cell share the same 4x4x4 output footprint (slots 2..5 of the reference's 6-slot stencil; |dx| < c < 1/2 cell per
 // step keeps both the old and the new shape inside it).  So the deposit is made OUTPUT-STATIONARY:
-//   phase 1 (lane = particle): load SoA, [gather node-centred fields + Boris push + store + sort key of the new cell],
-//           build the 1-D factors of the Esirkepov sum from the old and new shapes and park them in shared memory
-//           (44 floats per particle).  Deposit-only launches recompute the old position as the reference does
-//           (x - u/gamma*c); fused launches use the gather's shape at the true pre-push position (equal to round-off);
+//   record pipeline: each lane fetches the record of its NEXT step (through the lazy sort's permutation, whose entry was
+//           loaded one step earlier) with 4-byte cp.async into per-lane landing slots while the current step is deposited;
+//   phase 1 (lane = particle): read the landed record, [gather node-centred fields (packed FFMA2) + Boris push + store +
+//           sort key of the new cell + rank in its bin], build the 1-D factors of the Esirkepov sum from the old and new
+//           shapes and park them in shared memory (44 floats per particle).  Deposit-only launches recompute the old
+//           position as the reference does (x - u/gamma*c); fused launches use the gather's shape at the true pre-push
+//           position (equal to round-off);
 //   phase 2 (half-warp = one footprint): lane (j,k) of a half-warp owns the 4 x-cells of row (j,k) of the footprint
-//           for all three components = 12 register accumulators.  It walks its 16 particles, reading the factors with
-//           broadcast 128-bit shared loads.  When the cell changes along x the window slides: completed x-planes are
-//           flushed with one fp32 RED per (cell, component) and the registers shift.
+//           for all three components = 12 register accumulators (6 FFMA2 pairs).  It walks its 16 particles, reading the
+//           factors with broadcast 128-bit shared loads; the two half-warps run in lockstep.  The x-planes form a ring
+//           (plane of cell x lives in register x mod 4, phase 1 stores the x factors pre-rotated): when the cell advances
+//           along x the completed plane is flushed with one predicated fp32 RED per (cell, component) into the tiled
+//           shadow arrays (tgpu_internal.h row_index) and cleared; nothing moves between registers.
 // With ~8 particles per cell and species, that is ~6 global REDs per particle instead of up to 192 atomics, and the
 // arithmetic is the factorised form of Appendix A.3 (Jx = q*Wx(j,k)*prefix_i(dSx), ...).
 // Nothing here depends on the particles being sorted for correctness -- an unsorted tail (fresh arrivals) only makes
-// the window jump and flush more often.
+// the window jump and flush more often (which is why freshly uploaded records are sorted once, cellrun_move_deposit).
+// Measured character (profiles/README.md): 56 warp-instructions per particle, issue slots 70 % and the L1/shared data
+// pipe 78 % busy, DRAM 24 % of peak: co-limited by instruction issue and LSU wavefronts, not by HBM.
 #include "tgpu_internal.h"
 #include "shapes.cuh"
 
@@ -39,9 +46,6 @@
 #endif
 #define CR_STR(x) #x
 #define CR_DO_PRAGMA(x) _Pragma(CR_STR(x))
-#ifndef CR_PREFETCH
-#define CR_PREFETCH 0         // L1 prefetch of the next step's field nodes (A/B switch)
-#endif
 #ifndef CR_FFMA2
 #define CR_FFMA2 1            // packed fp32 (FFMA2/FMUL2) in the gather and the deposit accumulation: measured 2-3 % faster
 #endif
@@ -65,28 +69,11 @@ struct CRArgs {
     int32_t *slot, *bincount;
 };
 
-// fp32 reduction into global memory, skipped when the addend is exactly zero.  Written as predicated PTX so that the
-// compiler emits `@p RED` instead of a branch + reconvergence barrier around every atomic.
-__device__ __forceinline__ void red_nz(float *p, float v)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %1, 0f00000000;\n\t@p red.global.add.f32 [%0], %1;\n\t}"
-                 :: "l"(p), "f"(v) : "memory");
-}
 __device__ __forceinline__ void red3(float *cx, float *cy, float *cz, size_t idx, float vx, float vy, float vz)
 {
     // (a 16-byte red.global.add.v4.f32 into an interleaved array was measured 4 % slower than three scalar REDs)
     red_nz(cx + idx, vx); red_nz(cy + idx, vy); red_nz(cz + idx, vz);
 }
-
-// Asynchronous 4-byte global -> shared copy (LDGSTS): the particle record of the NEXT 16-particle step of a half-warp is
-// fetched into per-lane landing slots while the current step is being deposited, so neither the permutation lookup nor
-// the record loads sit on the critical path of phase 1 and no registers are held across phase 2.
-__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // sum over an NW^3 block of node-centred fields, in the reference's order: x innermost (sum()), then *Sy*Sz
 // (particles_movedeposit.F90:801-815)
@@ -332,14 +319,6 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
                 if (fast) {
                     const float wxs[2] = {Wx[1], Wx[2]}, wys[2] = {Wy[1], Wy[2]}, wzs[2] = {Wz[1], Wz[2]};
                     const int nbase = (ip - 1) + mx * ((jp - 1) + my * (kp - 1));
-#if CR_PREFETCH
-                    {
-                        // the next 16-particle step of this half-warp works one or two cells further along x: pull the
-                        // field nodes it will gather (4 rows x nodes ip+1..ip+4, one 32 B node per lane) into L1 now
-                        const int pn = nbase + mx * ((hl & 1) + my * ((hl >> 1) & 1)) + 2 + (hl >> 2);
-                        if (pn < (int)G.lot) asm volatile("prefetch.global.L1 [%0];" :: "l"(A.prim8 + 2 * (unsigned)pn));
-                    }
-#endif
                     gather_nodes<2>(A.prim8, nbase, mx, my, wxs, wys, wzs, e0, e1, e2, b0, b1, b2);
                 } else if (ORDER == 2) {
                     int lox, loy, loz;

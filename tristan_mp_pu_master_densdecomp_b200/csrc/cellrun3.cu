@@ -54,18 +54,9 @@ __device__ __forceinline__ void shape6(float d, int shift, float W6[6])
     W6[5] = shift > 0 ? s5 : 0.f;
 }
 
-__device__ __forceinline__ void c3_cp_async4(void *smem, const void *gmem)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void red_nz3(float *p, float v)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %1, 0f00000000;\n\t@p red.global.add.f32 [%0], %1;\n\t}"
-                 :: "l"(p), "f"(v) : "memory");
-}
 __device__ __forceinline__ void red3c(float *cx, float *cy, float *cz, size_t idx, float vx, float vy, float vz)
 {
-    red_nz3(cx + idx, vx); red_nz3(cy + idx, vy); red_nz3(cz + idx, vz);
+    red_nz(cx + idx, vx); red_nz(cy + idx, vy); red_nz(cz + idx, vz);
 }
 
 __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
@@ -92,18 +83,18 @@ __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
     auto fetch = [&](int buf, long long tt) {
         if (tt < A.n) {
             uint32_t *r = rec + (size_t)buf * 7 * 32 + lane;
-            c3_cp_async4(r + 0 * 32, A.s.x + tt); c3_cp_async4(r + 1 * 32, A.s.y + tt); c3_cp_async4(r + 2 * 32, A.s.z + tt);
-            c3_cp_async4(r + 3 * 32, A.s.u + tt); c3_cp_async4(r + 4 * 32, A.s.v + tt); c3_cp_async4(r + 5 * 32, A.s.w + tt);
-            c3_cp_async4(r + 6 * 32, A.s.ch + tt);
+            cp_async4(r + 0 * 32, A.s.x + tt); cp_async4(r + 1 * 32, A.s.y + tt); cp_async4(r + 2 * 32, A.s.z + tt);
+            cp_async4(r + 3 * 32, A.s.u + tt); cp_async4(r + 4 * 32, A.s.v + tt); cp_async4(r + 5 * 32, A.s.w + tt);
+            cp_async4(r + 6 * 32, A.s.ch + tt);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        cp_async_commit();
     };
     fetch(0, base + lane);
     for (int it = 0; it < C3_CHUNK / 32; ++it) {
         const long long t = base + it * 32 + lane;
         float *st = wst + lane * C3_STRIDE;
         int ci = -1, crow = -1;
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        cp_async_wait_all();
         if (it + 1 < C3_CHUNK / 32) fetch((it + 1) & 1, t + 32);
         if (t < A.n) {
             const uint32_t *r = rec + (size_t)(it & 1) * 7 * 32 + lane;
@@ -180,9 +171,9 @@ __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
                             // rot is uniform across the warp, so this is one short non-divergent case
                             float *px = A.cx + idx0, *py = A.cy + idx0, *pz = A.cz + idx0;
                             switch (rot) {
-#define C3_FL(q) case q: red_nz3(px, ax[q]); red_nz3(py, ay[q]); red_nz3(pz, az[q]); ax[q] = 0.f; ay[q] = 0.f; az[q] = 0.f; break;
+#define C3_FL(q) case q: red_nz(px, ax[q]); red_nz(py, ay[q]); red_nz(pz, az[q]); ax[q] = 0.f; ay[q] = 0.f; az[q] = 0.f; break;
                             C3_FL(0) C3_FL(1) C3_FL(2) C3_FL(3) C3_FL(4)
-                            default: red_nz3(px, ax[5]); red_nz3(py, ay[5]); red_nz3(pz, az[5]); ax[5] = 0.f; ay[5] = 0.f; az[5] = 0.f; break;
+                            default: red_nz(px, ax[5]); red_nz(py, ay[5]); red_nz(pz, az[5]); ax[5] = 0.f; ay[5] = 0.f; az[5] = 0.f; break;
 #undef C3_FL
                             }
                         } else {

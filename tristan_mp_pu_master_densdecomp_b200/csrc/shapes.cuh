@@ -4,6 +4,25 @@
 //   push   : code/particles_movedeposit.F90:861-929
 #pragma once
 
+// ---- inline-PTX helpers shared by the cell-run kernels (cellrun.cu, cellrun3.cu) ----
+// fp32 reduction into global memory, skipped when the addend is exactly zero.  Written as predicated PTX so that the
+// compiler emits `@p RED` instead of a branch + reconvergence barrier around every atomic.
+__device__ __forceinline__ void red_nz(float *p, float v)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %1, 0f00000000;\n\t@p red.global.add.f32 [%0], %1;\n\t}"
+                 :: "l"(p), "f"(v) : "memory");
+}
+// Asynchronous 4-byte global -> shared copy (LDGSTS): the particle record of the NEXT 16-particle step of a half-warp is
+// fetched into per-lane landing slots while the current step is being deposited, so neither the permutation lookup nor
+// the record loads sit on the critical path of phase 1 and no registers are held across phase 2.
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+
 // S has 8 entries; entries 1..6 are the reference's Sx(1:6); slot 3 <-> cell aint(x).
 template <int ORDER>
 __device__ __forceinline__ void shape_slots(float d, int shift, float S[8], int &smin, int &smax)
