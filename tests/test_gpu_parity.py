@@ -144,6 +144,24 @@ def test_filters_bit_exact(tgm, dim, kind, ntimes):
     ctx.close()
 
 
+@pytest.mark.parametrize("n,ntimes", [((112, 144, 16), 8), ((176, 48, 304), 8), ((64, 96, 32), 32)])
+def test_filter2_exact_fit_lines_bit_exact(tgm, n, ntimes):
+    """filter2 lines whose extended length ncell + 2*ntimes is exactly 32*R take the predicate-free kernel (odd and even R;
+    the bench workload 512x256x128 with ntimes = 32 is such a case on all three axes): still bit-exact"""
+    w, ctx = make(tgm, dim=3, order=1, n=n, ppc=0.0, init="none", ntimes=ntimes, filter_kind=2)
+    r = w.ranks[0]
+    rng = np.random.default_rng(11)
+    for a in range(6, 9):
+        r.arr(a)[...] = rng.standard_normal(r.arr(a).shape).astype(np.float32)
+    T.upload(ctx, r)
+    ctx.apply_filter()
+    w.call("apply_filter")
+    cg = ctx.currents_d2h()
+    for c in range(3):
+        assert np.array_equal(T.interior(r, cg[c]), T.interior(r, r.arr(6 + c))), O.ARR_NAMES[6 + c]
+    ctx.close()
+
+
 @pytest.mark.parametrize("dim,order", DIMS_ORDERS)
 @pytest.mark.parametrize("fused", [0, 1])
 def test_mover(tgm, dim, order, fused):

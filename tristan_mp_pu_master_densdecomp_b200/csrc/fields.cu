@@ -587,7 +587,11 @@ __device__ __forceinline__ size_t f2_addr(const F2 &f, int p_cell, int q1, int q
 // warp shuffles.  Every global element is read and written once per axis; the arithmetic per pass is exactly
 // new(p) = .25*old(p-1) + .5*old(p) + .25*old(p+1) with both end points of the extended line held fixed.
 // tile layout: [line][Lp], Lp = 32*R + 1.
-template <int R>
+// EXACT: the extended line fills the warp exactly (L == 32*R), so the two fixed end points sit at compile-time positions
+// (lane 0, r = 0) and (lane 31, r = R-1) and the per-element "is this an end point" predicate of the general form disappears
+// from the pass loop: 4 instead of 5 instructions per element-pass, same arithmetic.  (R may then be even: its 2-way bank
+// conflicts only touch the two register load/store phases.)
+template <int R, bool EXACT = false>
 __global__ void __launch_bounds__(512) k_filter2(float *__restrict__ cur, const float *__restrict__ halo_lo,
                                                  const float *__restrict__ halo_hi, F2 f, int NL)
 {
@@ -631,6 +635,24 @@ __global__ void __launch_bounds__(512) k_filter2(float *__restrict__ cur, const 
         float v[R];
 #pragma unroll
         for (int r = 0; r < R; r++) v[r] = (p0 + r < L) ? row[r] : 0.f;
+        if (EXACT) {
+            const float f0 = v[0], fl = v[R - 1];
+            const bool first = lane == 0, last = lane == 31;
+            for (int n = 0; n < f.nt; n++) {
+                const float left = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
+                const float right = __shfl_down_sync(0xffffffffu, v[0], 1);
+                float prev = left;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const float c = v[r];
+                    const float nx = r < R - 1 ? v[r + 1] : right;
+                    v[r] = .25f * prev + .5f * c + .25f * nx;
+                    prev = c;
+                }
+                v[0] = first ? f0 : v[0];
+                v[R - 1] = last ? fl : v[R - 1];
+            }
+        } else
         for (int n = 0; n < f.nt; n++) {
             const float left = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
             const float right = __shfl_down_sync(0xffffffffu, v[0], 1);
@@ -709,9 +731,11 @@ int fld_filter2(tgpu_ctx *h)
             }
             const int L = f.ncell + 2 * f.nt;
             int nlines = f.q_n[0] * f.q_n[1];
-            // strip length R (odd): smallest instantiated value with 32*R >= L
+            // strip length R (odd): smallest instantiated value with 32*R >= L; or the exact-fit kernel when L == 32*R
             int R = L <= 224 ? 7 : L <= 352 ? 11 : L <= 608 ? 19 : L <= 1120 ? 35 : 0;
             if (!R) { tgpu_set_error("filter2: extended line longer than 1120 elements is not instantiated"); return TGPU_EINVAL; }
+            const bool exact = L % 32 == 0 && L / 32 >= 4 && L / 32 <= 20;
+            if (exact) R = L / 32;
             const int Lp = 32 * R + 1;
             int NL = 32;
             while (NL > 1 && (size_t)Lp * NL * 4 > 100 * 1024) NL >>= 1;
@@ -722,12 +746,25 @@ int fld_filter2(tgpu_ctx *h)
         CK(cudaFuncSetAttribute(k_filter2<RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         k_filter2<RV><<<cdiv(nlines, NL), threads, smem, h->stream>>>(h->f[6 + c], hlo, hhi, f, NL);               \
     }
+#define LAUNCH_F2X(RV)                                                                                             \
+    case RV: {                                                                                                     \
+        CK(cudaFuncSetAttribute(k_filter2<RV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        k_filter2<RV, true><<<cdiv(nlines, NL), threads, smem, h->stream>>>(h->f[6 + c], hlo, hhi, f, NL);         \
+    } break;
+            if (exact) {
+                switch (R) {
+                    LAUNCH_F2X(4) LAUNCH_F2X(5) LAUNCH_F2X(6) LAUNCH_F2X(7) LAUNCH_F2X(8) LAUNCH_F2X(9) LAUNCH_F2X(10)
+                    LAUNCH_F2X(11) LAUNCH_F2X(12) LAUNCH_F2X(13) LAUNCH_F2X(14) LAUNCH_F2X(15) LAUNCH_F2X(16) LAUNCH_F2X(17)
+                    LAUNCH_F2X(18) LAUNCH_F2X(19) LAUNCH_F2X(20)
+                }
+            } else
             switch (R) {
             case 7: LAUNCH_F2(7) break;
             case 11: LAUNCH_F2(11) break;
             case 19: LAUNCH_F2(19) break;
             default: LAUNCH_F2(35) break;
             }
+#undef LAUNCH_F2X
 #undef LAUNCH_F2
             CKK(h);
         }
