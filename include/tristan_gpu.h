@@ -164,6 +164,14 @@ int tgpu_step_mirror(tgpu_ctx *h, float *ex, float *ey, float *ez, float *bx, fl
  * '[tei]bet[xyz]', '[ti]mom[xyz]', 'eener' 'iener', '[ei]et[xyz]2'.  As in the reference the result is left in curx
  * (cury = weight, curz = 0): read it with tgpu_currents_d2h.  Destroys the currents, like the reference (output laps only). */
 int tgpu_meanq_fld_cur(tgpu_ctx *h, const char *totname);
+/* per-rank part of save_spectrum, code/output.F90:380-633.  tgpu_spectrum_gamma_range: local min / max of gamma (both start
+ * at 1, :424-455); the host allreduces them (:458-463) and passes the global values to tgpu_spectrum, which fills the four
+ * nbins x gambins histograms (Fortran order, x-slice fastest; nbins = max((mx0-5)/100, 1), gambins = 200 in the reference):
+ * lab-frame ions / electrons and flow-rest-frame ions / electrons, as this rank's sums before mpi_allreduce and before the
+ * division by xgamma (:539-552).  mx0 = global x size incl. ghosts; splitratio as in the input file. */
+int tgpu_spectrum_gamma_range(tgpu_ctx *h, float *gammin, float *gammax);
+int tgpu_spectrum(tgpu_ctx *h, float gammin, float gammax, int mx0, float splitratio, int nbins, int gambins,
+                  float *specp, float *spece, float *specprest, float *specerest);
 /* the prtl.tot sub-sample, code/output.F90:3526-3551: every particle with modulo(ind/2, stride) == 0, compacted on the
  * device; ions to out[0 .. *n_ion), electrons to out[capacity .. capacity + *n_lec).  Positions are rank-local (the host adds
  * mxcum/mycum/mzcum as output.F90 does).  TGPU_EOVERFLOW if a species selects more than `capacity`. */

@@ -79,6 +79,8 @@ def lib():
             getattr(L, name).argtypes = [vp]
         L.orc_step_phase.argtypes = [vp, ci]
         L.orc_meanq_fld_cur.argtypes = [vp, C.c_char_p]
+        L.orc_spectrum_gamma_range.argtypes = [vp, C.POINTER(cf), C.POINTER(cf)]
+        L.orc_spectrum.argtypes = [vp, cf, cf, ci, cf, ci, ci] + [C.POINTER(cf)] * 4
         L.orc_shape.argtypes = [ci, cf, ci, C.POINTER(cf), C.POINTER(ci), C.POINTER(ci)]
         L.orc_filter2_line.argtypes = [C.POINTER(cf), ci, ci]
         L.orc_filter2_rank.argtypes = [vp, ci, ci, C.POINTER(cf), C.POINTER(cf)]
@@ -180,6 +182,18 @@ class Rank:
 
     def call(self, name, *a):
         return getattr(lib(), "orc_" + name)(self.h, *a)
+
+    def spectrum(self, mx0, splitratio=10.0, gambins=200, gamma_range=None):
+        """per-rank part of save_spectrum (output.F90:380-633) -> (gammin, gammax, specp, spece, specprest, specerest),
+        arrays shaped (gambins, nbins) (C order == Fortran (nbins, gambins))"""
+        cf = C.c_float
+        lo, hi = cf(), cf()
+        lib().orc_spectrum_gamma_range(self.h, C.byref(lo), C.byref(hi))
+        glo, ghi = (lo.value, hi.value) if gamma_range is None else gamma_range      # the allreduced range
+        nbins = max((mx0 - 2 - 3) // 100, 1)
+        out = [np.zeros((gambins, nbins), np.float32) for _ in range(4)]
+        lib().orc_spectrum(self.h, glo, ghi, mx0, splitratio, nbins, gambins, *[a.ctypes.data_as(C.POINTER(cf)) for a in out])
+        return (lo.value, hi.value, *out)
 
 
 class World:

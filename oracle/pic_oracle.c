@@ -1891,6 +1891,77 @@ void orc_meanq_fld_cur(orc_world *w, const char *totname)
 }
 
 /* ------------------------------------------------------------------------- */
+/* output-side spectra: the per-rank part of save_spectrum, output.F90:380-633   */
+/* gamma range (:440-455, before the allreduce of :458-463), then per species:    */
+/* slice-mean flow velocity (:477-497, 561-578), lab-frame spectrum (:503-511)    */
+/* and flow-rest-frame spectrum (:513-537) on nbins x-slices x gambins log bins.   */
+/* The sums are returned as the ranks hold them BEFORE mpi_allreduce and before    */
+/* the division by xgamma (:539-552).  The electron loops of the reference start   */
+/* one slot early (i = maxhlf, a dead record, :562, 583); that slot is not read.   */
+/* spec arrays are Fortran order (xbin fastest).                                   */
+/* ------------------------------------------------------------------------- */
+void orc_spectrum_gamma_range(const orc_rank *r, float *gammin, float *gammax)
+{
+    float lo = 1.f, hi = 1.f;
+    for (int sp = 0; sp < 2; sp++) {
+        const int first = sp ? r->maxhlf : 0, cnt = sp ? r->lecs : r->ions;
+        for (int n = 0; n < cnt; n++) {
+            const orc_particle *q = &r->p[first + n];
+            const float gam = sqrtf(1.f + (q->u * q->u + q->v * q->v + q->w * q->w));
+            if (gam > hi) hi = gam;
+            if (gam < lo) lo = gam;
+        }
+    }
+    *gammin = lo; *gammax = hi;
+}
+void orc_spectrum(const orc_rank *r, float gammin, float gammax, int mx0, float splitratio, int nbins, int gambins,
+                  float *specp, float *spece, float *specpprime, float *speceprime)
+{
+    const int mxmin = 3, mxmax = mx0 - 2;
+    const float dxslice = 1.f * (mxmax - mxmin) / nbins;
+    gammin = gammin > 1.f + 1e-6f ? gammin : 1.f + 1e-6f;                              /* :465 */
+    const float lg0 = log10f(gammin - 1.f);
+    const float dgam = (log10f(gammax - 1.f) - lg0) / gambins;                          /* :466 */
+    float *um = (float *)calloc(4 * (size_t)nbins, sizeof(float)), *vm = um + nbins, *wm = vm + nbins, *nd = wm + nbins;
+    for (int sp = 0; sp < 2; sp++) {
+        const int first = sp ? r->maxhlf : 0, cnt = sp ? r->lecs : r->ions;
+        float *spec = sp ? spece : specp, *specr = sp ? speceprime : specpprime;
+        memset(um, 0, 4 * (size_t)nbins * sizeof(float));
+        memset(spec, 0, (size_t)nbins * gambins * sizeof(float)); memset(specr, 0, (size_t)nbins * gambins * sizeof(float));
+        for (int n = 0; n < cnt; n++) {
+            const orc_particle *q = &r->p[first + n];
+            const int xbin = (int)((q->x + r->mxcum - mxmin) / dxslice + 1);
+            if (xbin < 1 || xbin > nbins) continue;
+            const float wgt = powf(splitratio, 1.f - (float)q->splitlev) * q->ch;
+            const float gam = sqrtf(1.f + (q->u * q->u + q->v * q->v + q->w * q->w));
+            nd[xbin - 1] += wgt; um[xbin - 1] += q->u / gam * wgt; vm[xbin - 1] += q->v / gam * wgt; wm[xbin - 1] += q->w / gam * wgt;
+        }
+        for (int b = 0; b < nbins; b++) { um[b] /= nd[b]; vm[b] /= nd[b]; wm[b] /= nd[b]; }
+        for (int n = 0; n < cnt; n++) {
+            const orc_particle *q = &r->p[first + n];
+            const int xbin = (int)((q->x + r->mxcum - mxmin) / dxslice + 1);
+            if (xbin < 1 || xbin > nbins) continue;
+            const float wgt = powf(splitratio, 1.f - (float)q->splitlev) * q->ch;
+            const float gam = sqrtf(1.f + (q->u * q->u + q->v * q->v + q->w * q->w));
+            int gbin = (int)((log10f(gam - 1.f) - lg0) / dgam + 1);
+            if (gbin >= 1 && gbin <= gambins) spec[(xbin - 1) + (size_t)nbins * (gbin - 1)] += wgt;
+            const float vx = um[xbin - 1], vy = vm[xbin - 1], vz = wm[xbin - 1];
+            const float vr = sqrtf(vx * vx + vy * vy + vz * vz), gvr = 1.f / sqrtf(1.f - vr * vr);
+            const float up = -vx * gvr * gam + (1 + (gvr - 1) * vx * vx / (vr * vr)) * q->u + (gvr - 1) * vx * vy / (vr * vr) * q->v
+                             + (gvr - 1) * vx * vz / (vr * vr) * q->w;
+            const float vp = -vy * gvr * gam + (gvr - 1) * vx * vy / (vr * vr) * q->u + (1 + (gvr - 1) * vy * vy / (vr * vr)) * q->v
+                             + (gvr - 1) * vy * vz / (vr * vr) * q->w;
+            const float wp = -vz * gvr * gam + (gvr - 1) * vx * vz / (vr * vr) * q->u + (gvr - 1) * vy * vz / (vr * vr) * q->v
+                             + (1 + (gvr - 1) * vz * vz / (vr * vr)) * q->w;
+            const float gp = sqrtf(1.f + (up * up + vp * vp + wp * wp));
+            gbin = (int)((log10f(gp - 1.f) - lg0) / dgam + 1);
+            if (gbin >= 1 && gbin <= gambins) specr[(xbin - 1) + (size_t)nbins * (gbin - 1)] += wgt;
+        }
+    }
+    free(um);
+}
+
+/* ------------------------------------------------------------------------- */
 /* diagnostics used by the known-answer tests                                   */
 /* ------------------------------------------------------------------------- */
 /* node charge density with the deposit's own shape function: rho(i,j,k) = sum q S(i) S(j) S(k),

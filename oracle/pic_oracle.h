@@ -149,6 +149,10 @@ void orc_apply_filter2(orc_world *w);
 void orc_apply_filter(orc_world *w);
 /* moments of the particle distribution into curx (cury = weight): meanq_fld_cur(totname), output.F90:5229-5486 */
 void orc_meanq_fld_cur(orc_world *w, const char *totname);
+/* per-rank part of save_spectrum (output.F90:380-633): gamma range, then the four nbins x gambins histograms (xbin fastest) */
+void orc_spectrum_gamma_range(const orc_rank *r, float *gammin, float *gammax);
+void orc_spectrum(const orc_rank *r, float gammin, float gammax, int mx0, float splitratio, int nbins, int gambins,
+                  float *specp, float *spece, float *specpprime, float *speceprime);
 void orc_step(orc_world *w);                      /* one lap of tristanmainloop.F90:107-344 */
 void orc_step_phase(orc_world *w, int phase);     /* single named phase, for A/B tests */
 

@@ -424,3 +424,33 @@ def test_meanq_density_and_velocity_known_answers():
     assert np.allclose(T.interior(r, r.arr(O.CURX)), 0.25, rtol=2e-5)
     w.meanq_fld_cur("iener")
     assert np.allclose(T.interior(r, r.arr(O.CURX)), np.sqrt(1 + 0.75 ** 2) - 1, rtol=2e-5)
+
+
+def test_spectrum_known_answers():
+    """save_spectrum restatement (output.F90:380-633): a mono-energetic beam fills one gamma bin per x-slice with the slice's
+    particle weight; in the flow rest frame the same cold beam has gamma' -> 1, i.e. it leaves the histogram range"""
+    n = (210, 4, 4)
+    w = T.oracle_world(dim=3, order=1, n=n, ppc=0.0, init="none", seed_fields=0)
+    r = w.ranks[0]
+    g = r.nghost // 2
+    rng = np.random.default_rng(2)
+    npart = 5000
+    p = r.particles()
+    q = p[:npart]
+    q["x"] = rng.uniform(g + 1, n[0] + g + 1, npart); q["y"] = g + 2.5; q["z"] = g + 2.5
+    q["u"] = 2.0; q["v"] = 0; q["w"] = 0; q["ch"] = 1; q["ind"] = np.arange(npart) + 1; q["proc"] = 0; q["splitlev"] = 1
+    r.set_counts(npart, 0)
+    mx0 = w.P.mx0 + r.nghost
+    # a fixed global range (what the allreduce would hand back), wide enough to hold gamma = sqrt(5)
+    lo, hi, sp, se, spr, ser = r.spectrum(mx0, splitratio=10.0, gamma_range=(1.1, 10.0))
+    assert (lo, hi) == (1.0, np.float32(np.sqrt(np.float32(5.0))))
+    nb = max((mx0 - 5) // 100, 1)
+    assert sp.shape == (200, nb) and se.sum() == 0 and ser.sum() == 0
+    dgam = (np.log10(9.0) - np.log10(0.1)) / 200
+    gbin = int((np.log10(np.sqrt(5.0) - 1) - np.log10(0.1)) / dgam + 1)
+    dx = (mx0 - 2 - 3) / nb
+    xb = ((q["x"] + r.mxcum - 3) / dx + 1).astype(int)
+    for b in range(nb):
+        assert sp[gbin - 1, b] == np.count_nonzero(xb == b + 1)
+    assert sp.sum() == np.count_nonzero((xb >= 1) & (xb <= nb))
+    assert spr.sum() == 0                                  # cold beam: at rest in its own flow frame

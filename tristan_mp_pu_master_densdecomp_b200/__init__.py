@@ -53,7 +53,7 @@ ABI_SYMBOLS = [
     "tgpu_add_current", "tgpu_bc_b1", "tgpu_bc_e1", "tgpu_bc_b2", "tgpu_bc_e2", "tgpu_exchange_current",
     "tgpu_apply_filter", "tgpu_apply_filter1_opt", "tgpu_apply_filter2_opt", "tgpu_move_particles",
     "tgpu_deposit_particles", "tgpu_exchange_particles", "tgpu_inject_others", "tgpu_reorder_particles",
-    "tgpu_meanq_fld_cur", "tgpu_select_particles", "tgpu_step_mirror", "tgpu_field_bc_user_shock", "tgpu_particle_bc_user_wall", "tgpu_set_user_hooks", "tgpu_step", "tgpu_timers", "tgpu_launch_count", "tgpu_stream", "tgpu_set_option",
+    "tgpu_meanq_fld_cur", "tgpu_spectrum_gamma_range", "tgpu_spectrum", "tgpu_select_particles", "tgpu_step_mirror", "tgpu_field_bc_user_shock", "tgpu_particle_bc_user_wall", "tgpu_set_user_hooks", "tgpu_step", "tgpu_timers", "tgpu_launch_count", "tgpu_stream", "tgpu_set_option",
 ]
 
 _lib = None
@@ -94,6 +94,8 @@ def load_library(path=None):
         getattr(L, name).argtypes = [vp]
     L.tgpu_field_bc_user_shock.argtypes = [vp] + [C.c_float] * 5
     L.tgpu_meanq_fld_cur.argtypes = [vp, C.c_char_p]
+    L.tgpu_spectrum_gamma_range.argtypes = [vp, fp, fp]
+    L.tgpu_spectrum.argtypes = [vp, C.c_float, C.c_float, ci, C.c_float, ci, ci] + [fp] * 4
     L.tgpu_select_particles.argtypes = [vp, ci, vp, ci, C.POINTER(ci), C.POINTER(ci)]
     L.tgpu_step_mirror.argtypes = [vp] + [fp] * 6 + [vp, C.POINTER(ci), C.POINTER(ci)]
     L.tgpu_particle_bc_user_wall.argtypes = [vp, C.c_float]
@@ -294,6 +296,17 @@ class Context:
         self._ck(self.lib.tgpu_step_mirror(self.h, *[_fptr(a) for a in fields], p.ctypes.data_as(C.c_void_p),
                                            C.byref(ni), C.byref(ne)), "step_mirror")
         return ni.value, ne.value
+
+    def spectrum(self, mx0, splitratio=10.0, gambins=200, gamma_range=None):
+        """per-rank part of save_spectrum (output.F90:380-633) -> (gammin, gammax, specp, spece, specprest, specerest);
+        arrays shaped (gambins, nbins).  `gamma_range` = the allreduced (gammin, gammax) when there are several ranks."""
+        lo, hi = C.c_float(), C.c_float()
+        self._ck(self.lib.tgpu_spectrum_gamma_range(self.h, C.byref(lo), C.byref(hi)), "spectrum_gamma_range")
+        glo, ghi = (lo.value, hi.value) if gamma_range is None else gamma_range
+        nbins = max((mx0 - 2 - 3) // 100, 1)
+        out = [np.zeros((gambins, nbins), np.float32) for _ in range(4)]
+        self._ck(self.lib.tgpu_spectrum(self.h, glo, ghi, mx0, splitratio, nbins, gambins, *[_fptr(a) for a in out]), "spectrum")
+        return (lo.value, hi.value, *out)
 
     def select_particles(self, stride, capacity):
         """prtl.tot sub-sample (output.F90:3526-3551): returns (ions, electrons) with modulo(ind/2, stride) == 0."""

@@ -409,6 +409,17 @@ extern "C" int tgpu_step_mirror(tgpu_ctx *h, float *ex, float *ey, float *ez, fl
 // meanq_fld_cur(totname), output.F90:5229-5486: the moment lands in curx (cury = weight), as in the reference; the host
 // reads it with tgpu_currents_d2h instead of pulling every particle across PCIe on an output lap
 extern "C" int tgpu_meanq_fld_cur(tgpu_ctx *h, const char *totname) { ENTER(h); return prt_meanq(h, totname); }
+// per-rank part of save_spectrum, output.F90:380-633 (the host keeps the two allreduces and the division by xgamma)
+extern "C" int tgpu_spectrum_gamma_range(tgpu_ctx *h, float *gammin, float *gammax)
+{
+    ENTER(h); if (!gammin || !gammax) return TGPU_EINVAL;
+    return prt_gamma_range(h, gammin, gammax);
+}
+extern "C" int tgpu_spectrum(tgpu_ctx *h, float gammin, float gammax, int mx0, float splitratio, int nbins, int gambins,
+                             float *specp, float *spece, float *specprest, float *specerest)
+{
+    ENTER(h); return prt_spectrum(h, gammin, gammax, mx0, splitratio, nbins, gambins, specp, spece, specprest, specerest);
+}
 // the prtl.tot sub-sample, output.F90:3526-3551: particles with modulo(ind/2, stride) == 0
 extern "C" int tgpu_select_particles(tgpu_ctx *h, int stride, tgpu_particle *out, int capacity, int *n_ion, int *n_lec)
 {

@@ -957,3 +957,127 @@ int prt_select(tgpu_ctx *h, int stride, tgpu_particle *out_host, int capacity, i
     *n_ion = cnt[0]; *n_lec = cnt[1];
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Output-side spectra: the per-rank part of save_spectrum (output.F90:380-633) on the device.
+//   tgpu_spectrum_gamma_range : local min / max of gamma (:440-455); the host allreduces them (:458-463)
+//   tgpu_spectrum             : per species, slice-mean flow velocity (:477-497, 561-578), lab-frame spectrum (:503-511)
+//                               and flow-rest-frame spectrum (:513-537), nbins x-slices x gambins logarithmic bins,
+//                               returned as this rank's sums BEFORE mpi_allreduce and the division by xgamma (:539-552).
+// Histograms are accumulated per block in shared memory (when they fit) and merged with one atomic per bin per block.
+// The reference's electron loops start one slot early (a dead record, :562, 583); that slot is not read here.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gamma_range(Species s, int n, unsigned *__restrict__ mm)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    float g = 1.f;
+    if (t < n) { const float u = s.u[t], v = s.v[t], w = s.w[t]; g = sqrtf(1.f + (u * u + v * v + w * w)); }
+    float lo = g, hi = g;
+    for (int o = 16; o; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(mm, __float_as_uint(lo)); atomicMax(mm + 1, __float_as_uint(hi)); }   // gamma >= 1 > 0
+}
+struct SpecArgs { int mxcum, mxmin, nbins, gambins; float dxslice, splitratio, lg0, dgam; };
+__device__ __forceinline__ bool spec_particle(const Species &s, int t, const SpecArgs &A, int &xbin, float &wgt, float &gam,
+                                              float &u, float &v, float &w)
+{
+    xbin = (int)((s.x[t] + A.mxcum - A.mxmin) / A.dxslice + 1);
+    if (xbin < 1 || xbin > A.nbins) return false;
+    u = s.u[t]; v = s.v[t]; w = s.w[t];
+    const int splitlev = (s.tag[t] >> 24) & 0xFF;
+    wgt = powf(A.splitratio, 1.f - (float)splitlev) * s.ch[t];
+    gam = sqrtf(1.f + (u * u + v * v + w * w));
+    return true;
+}
+// acc[0..nbins) = numdens, then umean, vmean, wmean sums
+__global__ void __launch_bounds__(256) k_spec_means(Species s, int n, SpecArgs A, float *__restrict__ acc)
+{
+    extern __shared__ float sh[];
+    for (int i = threadIdx.x; i < 4 * A.nbins; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int xbin; float wgt, gam, u, v, w;
+    if (t < n && spec_particle(s, t, A, xbin, wgt, gam, u, v, w)) {
+        atomicAdd(sh + xbin - 1, wgt); atomicAdd(sh + A.nbins + xbin - 1, u / gam * wgt);
+        atomicAdd(sh + 2 * A.nbins + xbin - 1, v / gam * wgt); atomicAdd(sh + 3 * A.nbins + xbin - 1, w / gam * wgt);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * A.nbins; i += blockDim.x) if (sh[i] != 0.f) atomicAdd(acc + i, sh[i]);
+}
+__global__ void k_spec_norm(float *acc, int nbins)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbins) { const float nd = acc[b]; acc[nbins + b] /= nd; acc[2 * nbins + b] /= nd; acc[3 * nbins + b] /= nd; }
+}
+// spec[0 .. nb*gb) = lab frame, spec[nb*gb .. 2*nb*gb) = flow rest frame; SMEM: per-block shared histogram
+template <bool SMEM>
+__global__ void __launch_bounds__(256) k_spec_hist(Species s, int n, SpecArgs A, const float *__restrict__ mean, float *__restrict__ spec)
+{
+    extern __shared__ float sh[];
+    const int nh = 2 * A.nbins * A.gambins;
+    if (SMEM) { for (int i = threadIdx.x; i < nh; i += blockDim.x) sh[i] = 0.f; __syncthreads(); }
+    float *dst = SMEM ? sh : spec;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int xbin; float wgt, gam, u, v, w;
+    if (t < n && spec_particle(s, t, A, xbin, wgt, gam, u, v, w)) {
+        int gbin = (int)((log10f(gam - 1.f) - A.lg0) / A.dgam + 1);
+        if (gbin >= 1 && gbin <= A.gambins) atomicAdd(dst + (xbin - 1) + A.nbins * (gbin - 1), wgt);
+        const float vx = mean[A.nbins + xbin - 1], vy = mean[2 * A.nbins + xbin - 1], vz = mean[3 * A.nbins + xbin - 1];
+        const float vr = sqrtf(vx * vx + vy * vy + vz * vz), gvr = 1.f / sqrtf(1.f - vr * vr);
+        const float up = -vx * gvr * gam + (1 + (gvr - 1) * vx * vx / (vr * vr)) * u + (gvr - 1) * vx * vy / (vr * vr) * v
+                         + (gvr - 1) * vx * vz / (vr * vr) * w;
+        const float vp = -vy * gvr * gam + (gvr - 1) * vx * vy / (vr * vr) * u + (1 + (gvr - 1) * vy * vy / (vr * vr)) * v
+                         + (gvr - 1) * vy * vz / (vr * vr) * w;
+        const float wp = -vz * gvr * gam + (gvr - 1) * vx * vz / (vr * vr) * u + (gvr - 1) * vy * vz / (vr * vr) * v
+                         + (1 + (gvr - 1) * vz * vz / (vr * vr)) * w;
+        const float gp = sqrtf(1.f + (up * up + vp * vp + wp * wp));
+        gbin = (int)((log10f(gp - 1.f) - A.lg0) / A.dgam + 1);
+        if (gbin >= 1 && gbin <= A.gambins) atomicAdd(dst + A.nbins * A.gambins + (xbin - 1) + A.nbins * (gbin - 1), wgt);
+    }
+    if (SMEM) { __syncthreads(); for (int i = threadIdx.x; i < nh; i += blockDim.x) if (sh[i] != 0.f) atomicAdd(spec + i, sh[i]); }
+}
+int prt_gamma_range(tgpu_ctx *h, float *gammin, float *gammax)
+{
+    int rc = prt_materialize(h); if (rc) return rc;
+    unsigned init[2] = {0x3f800000u, 0x3f800000u}, out[2];             // gammin = gammax = 1 (:424-425)
+    unsigned *mm = (unsigned *)(h->d_small + 66);
+    CK(cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+    for (int s = 0; s < 2; s++) if (h->sp[s].n) { k_gamma_range<<<cdiv(h->sp[s].n, 256), 256, 0, h->stream>>>(h->sp[s], h->sp[s].n, mm); CKK(h); }
+    CK(cudaMemcpyAsync(out, mm, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(gammin, &out[0], 4); memcpy(gammax, &out[1], 4);
+    return 0;
+}
+int prt_spectrum(tgpu_ctx *h, float gammin, float gammax, int mx0, float splitratio, int nbins, int gambins,
+                 float *specp, float *spece, float *specprest, float *specerest)
+{
+    if (nbins < 1 || gambins < 1 || !specp || !spece || !specprest || !specerest || !(gammax > 1.f)) {
+        tgpu_set_error("spectrum: bad arguments (need nbins, gambins >= 1 and gammax > 1)"); return TGPU_EINVAL;
+    }
+    int rc = prt_materialize(h); if (rc) return rc;
+    SpecArgs A;
+    A.mxcum = h->P.mxcum; A.mxmin = 3; A.nbins = nbins; A.gambins = gambins; A.splitratio = splitratio;
+    A.dxslice = 1.f * ((mx0 - 2) - A.mxmin) / nbins;                                    // :432-438
+    gammin = gammin > 1.f + 1e-6f ? gammin : 1.f + 1e-6f;                               // :465
+    A.lg0 = log10f(gammin - 1.f); A.dgam = (log10f(gammax - 1.f) - A.lg0) / gambins;   // :466
+    const size_t nh = 2 * (size_t)nbins * gambins, nacc = 4 * (size_t)nbins;
+    float *buf = nullptr;
+    CK(cudaMalloc(&buf, (nh + nacc) * sizeof(float)));
+    float *hout[2][2] = {{specp, specprest}, {spece, specerest}};
+    for (int s = 0; s < 2; s++) {
+        Species &S = h->sp[s];
+        CK(cudaMemsetAsync(buf, 0, (nh + nacc) * sizeof(float), h->stream));
+        float *acc = buf + nh;
+        if (S.n) {
+            k_spec_means<<<cdiv(S.n, 256), 256, nacc * sizeof(float), h->stream>>>(S, S.n, A, acc); CKK(h);
+            k_spec_norm<<<cdiv(nbins, 64), 64, 0, h->stream>>>(acc, nbins); CKK(h);
+            if (nh * sizeof(float) <= 40 * 1024) k_spec_hist<true><<<cdiv(S.n, 256), 256, nh * sizeof(float), h->stream>>>(S, S.n, A, acc, buf);
+            else k_spec_hist<false><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, S.n, A, acc, buf);
+            CKK(h);
+        }
+        CK(cudaMemcpyAsync(hout[s][0], buf, nh / 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(hout[s][1], buf + nh / 2, nh / 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    cudaFree(buf);
+    return 0;
+}

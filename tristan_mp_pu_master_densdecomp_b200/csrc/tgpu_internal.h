@@ -131,6 +131,9 @@ int prt_materialize(tgpu_ctx *h);     // apply a pending lazy permutation (+ wra
 int prt_exchange(tgpu_ctx *h);
 int prt_wall(tgpu_ctx *h, float leftwall);
 int prt_meanq(tgpu_ctx *h, const char *totname);
+int prt_gamma_range(tgpu_ctx *h, float *gammin, float *gammax);
+int prt_spectrum(tgpu_ctx *h, float gammin, float gammax, int mx0, float splitratio, int nbins, int gambins,
+                 float *specp, float *spece, float *specprest, float *specerest);   // save_spectrum, per-rank part
 int prt_select(tgpu_ctx *h, int stride, tgpu_particle *out_host, int capacity, int *n_ion, int *n_lec);   // prtl.tot selection
 int prt_mirror_stream(tgpu_ctx *h, tgpu_particle *p, int ions, int lecs);   // particle side of tgpu_step_mirror   // meanq_fld_cur, output.F90:5229-5486
 // comm.cu
