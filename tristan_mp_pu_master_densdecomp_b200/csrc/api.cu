@@ -122,7 +122,7 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     size_t plane = (size_t)p->mx * p->my;
     if ((size_t)p->mx * p->mz > plane) plane = (size_t)p->mx * p->mz;
     if ((size_t)p->my * p->mz > plane) plane = (size_t)p->my * p->mz;
-    size_t per = 6 * (size_t)(G.g + 1); if ((size_t)4 * p->ntimes > per) per = 4 * (size_t)p->ntimes;
+    size_t per = 6 * (size_t)(G.g + 1); if ((size_t)12 * p->ntimes > per) per = 12 * (size_t)p->ntimes;   // filter2: 4 slabs x 3 components
     h->halo_floats = per * plane;
     rc |= dalloc(&h->halo, h->halo_floats);
     for (int s = 0; s < 2; s++) {

@@ -704,31 +704,40 @@ int fld_filter2(tgpu_ctx *h)
         lo[a] = g + 1; n[a] = m - 2 * g - 1;
     }
     if (P.dim == 2) { lo[2] = 1; n[2] = 1; }
-    for (int c = 0; c < 3; c++) {
-        for (int axis = 0; axis < naxes; axis++) {
-            int m, g, per, sz, pos; axis_info(h, axis, &m, &g, &per, &sz, &pos);
-            F2 f; f.mx = P.mx; f.my = P.my; f.mz = P.mz; f.axis = axis; f.str = lo[axis]; f.ncell = n[axis]; f.nt = P.ntimes;
-            int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2;
-            f.q_lo[0] = lo[a1]; f.q_n[0] = n[a1]; f.q_lo[1] = lo[a2]; f.q_n[1] = n[a2];
-            if (f.nt > f.ncell) { tgpu_set_error("filter2: ntimes exceeds the local extent"); return TGPU_EINVAL; }
-            f.lowmode = per ? 0 : 2; f.highmode = per ? 0 : 2;
-            float *hlo = nullptr, *hhi = nullptr;
-            if (sz > 1) {
-                size_t cnt = (size_t)f.nt * f.q_n[0] * f.q_n[1];
-                if (4 * cnt > h->halo_floats) { tgpu_set_error("halo scratch too small for filter2"); return TGPU_EINVAL; }
-                float *s_up = h->halo, *s_dn = h->halo + cnt; hlo = h->halo + 2 * cnt; hhi = h->halo + 3 * cnt;
+    // The three components are independent, so the loops run axis-major: the ntimes-deep halos of all three components of an
+    // axis travel in ONE NCCL group (2 groups per lap on a y/z-decomposed box instead of 6), then the three kernels run.
+    for (int axis = 0; axis < naxes; axis++) {
+        int m, g, per, sz, pos; axis_info(h, axis, &m, &g, &per, &sz, &pos);
+        F2 f; f.mx = P.mx; f.my = P.my; f.mz = P.mz; f.axis = axis; f.str = lo[axis]; f.ncell = n[axis]; f.nt = P.ntimes;
+        int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2;
+        f.q_lo[0] = lo[a1]; f.q_n[0] = n[a1]; f.q_lo[1] = lo[a2]; f.q_n[1] = n[a2];
+        if (f.nt > f.ncell) { tgpu_set_error("filter2: ntimes exceeds the local extent"); return TGPU_EINVAL; }
+        f.lowmode = per ? 0 : 2; f.highmode = per ? 0 : 2;
+        float *hlo_c[3] = {nullptr, nullptr, nullptr}, *hhi_c[3] = {nullptr, nullptr, nullptr};
+        if (sz > 1) {
+            size_t cnt = (size_t)f.nt * f.q_n[0] * f.q_n[1];
+            if (12 * cnt > h->halo_floats) { tgpu_set_error("halo scratch too small for filter2"); return TGPU_EINVAL; }
+            int up = topo_neighbour(P.rank, P.sizex, P.sizey, P.sizez, 2 * axis + 1);
+            int dn = topo_neighbour(P.rank, P.sizex, P.sizey, P.sizez, 2 * axis);
+            for (int c = 0; c < 3; c++) {
+                float *s_up = h->halo + (4 * c) * cnt, *s_dn = h->halo + (4 * c + 1) * cnt;
+                hlo_c[c] = h->halo + (4 * c + 2) * cnt; hhi_c[c] = h->halo + (4 * c + 3) * cnt;
                 // my last nt cells go up and become the + neighbour's low halo; my first nt cells go down
                 k_f2_pack<<<cdiv(cnt, 256), 256, 0, h->stream>>>(h->f[6 + c], s_up, f, f.str + f.ncell - f.nt); CKK(h);
                 k_f2_pack<<<cdiv(cnt, 256), 256, 0, h->stream>>>(h->f[6 + c], s_dn, f, f.str); CKK(h);
-                int up = topo_neighbour(P.rank, P.sizex, P.sizey, P.sizez, 2 * axis + 1);
-                int dn = topo_neighbour(P.rank, P.sizex, P.sizey, P.sizez, 2 * axis);
-                int rc = comm_group_begin(h); if (rc) return rc;
-                comm_send(h, s_up, cnt * 4, up); comm_recv(h, hlo, cnt * 4, dn);
-                comm_send(h, s_dn, cnt * 4, dn); comm_recv(h, hhi, cnt * 4, up);
-                rc = comm_group_end(h); if (rc) return rc;
-                f.lowmode = (per || pos != 0) ? 1 : 2;
-                f.highmode = (per || pos != sz - 1) ? 1 : 2;
             }
+            int rc = comm_group_begin(h); if (rc) return rc;
+            for (int c = 0; c < 3; c++) {
+                float *s_up = h->halo + (4 * c) * cnt, *s_dn = h->halo + (4 * c + 1) * cnt;
+                comm_send(h, s_up, cnt * 4, up); comm_recv(h, hlo_c[c], cnt * 4, dn);
+                comm_send(h, s_dn, cnt * 4, dn); comm_recv(h, hhi_c[c], cnt * 4, up);
+            }
+            rc = comm_group_end(h); if (rc) return rc;
+            f.lowmode = (per || pos != 0) ? 1 : 2;
+            f.highmode = (per || pos != sz - 1) ? 1 : 2;
+        }
+        for (int c = 0; c < 3; c++) {
+            float *hlo = hlo_c[c], *hhi = hhi_c[c];
             const int L = f.ncell + 2 * f.nt;
             int nlines = f.q_n[0] * f.q_n[1];
             // strip length R (odd): smallest instantiated value with 32*R >= L; or the exact-fit kernel when L == 32*R
