@@ -1060,8 +1060,9 @@ int prt_spectrum(tgpu_ctx *h, float gammin, float gammax, int mx0, float splitra
     gammin = gammin > 1.f + 1e-6f ? gammin : 1.f + 1e-6f;                               // :465
     A.lg0 = log10f(gammin - 1.f); A.dgam = (log10f(gammax - 1.f) - A.lg0) / gambins;   // :466
     const size_t nh = 2 * (size_t)nbins * gambins, nacc = 4 * (size_t)nbins;
-    float *buf = nullptr;
-    CK(cudaMalloc(&buf, (nh + nacc) * sizeof(float)));
+    struct Scratch { float *p = nullptr; ~Scratch() { if (p) cudaFree(p); } } scratch;     // freed on every return path
+    CK(cudaMalloc(&scratch.p, (nh + nacc) * sizeof(float)));
+    float *buf = scratch.p;
     float *hout[2][2] = {{specp, specprest}, {spece, specerest}};
     for (int s = 0; s < 2; s++) {
         Species &S = h->sp[s];
@@ -1078,6 +1079,5 @@ int prt_spectrum(tgpu_ctx *h, float gammin, float gammax, int mx0, float splitra
         CK(cudaMemcpyAsync(hout[s][1], buf + nh / 2, nh / 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
-    cudaFree(buf);
     return 0;
 }
