@@ -91,3 +91,75 @@ def test_gpu_reproduces_golden(tg, path):
     gi, ge = T.gpu_particles(ctx3)
     T.assert_particles_close(gi, g["lap2_ions"], rtol_pos=4e-5, rtol_mom=4e-4)
     ctx3.close(); ctx.close()
+
+
+# ------------------------------------------------------------------ feature fixtures: surface, _42 solver, moments
+FEAT = {"d3": dict(dim=3, n=(12, 10, 8)), "d2": dict(dim=2, n=(14, 12, 1))}
+MOMENTS = ["tdens", "idens", "ibetx", "ebetz", "tmomy", "eener", "iety2"]
+
+
+def _feat_world(c, **kw):
+    return T.oracle_world(dim=c["dim"], order=2, n=c["n"], ppc=2.0, delgam=0.05, seed_fields=4, **kw)
+
+
+@pytest.mark.parametrize("name", sorted(FEAT))
+def test_oracle_reproduces_feature_golden(name):
+    c = FEAT[name]
+    g = np.load(os.path.join(HERE, "golden", f"feat_{name}.npz"))
+    w = _feat_world(c, periodic=(0, 1, 1)); r = w.ranks[0]
+    for a in range(6):
+        assert np.array_equal(r.arr(a), g["surf_in_" + O.ARR_NAMES[a]])
+    for _ in range(2):
+        for ph in (O.PH_SURF_B, O.PH_BC_B1, O.PH_SURF_E, O.PH_BC_E1):
+            w.phase(ph)
+    for a in range(6):
+        assert np.array_equal(r.arr(a), g["surf_out_" + O.ARR_NAMES[a]])
+    w = _feat_world(c, highorder=1); r = w.ranks[0]
+    for nm in ("advance_b_halfstep", "advance_e_fullstep", "advance_b_halfstep"):
+        r.call(nm)
+    for a in range(6):
+        assert np.array_equal(r.arr(a), g["s42_out_" + O.ARR_NAMES[a]])
+    w = _feat_world(c); r = w.ranks[0]
+    for m in MOMENTS:
+        w.meanq_fld_cur(m)
+        assert np.array_equal(r.arr(O.CURX), g["mom_" + m])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(FEAT))
+def test_gpu_reproduces_feature_golden(tg, name):
+    """radiation `surface` and the 4th-order solver bit-exact, the moments to 2e-5 — from files, without the oracle's arithmetic"""
+    c = FEAT[name]
+    g = np.load(os.path.join(HERE, "golden", f"feat_{name}.npz"))
+
+    def ctx_for(**kw):
+        P = tg.make_params(dim=c["dim"], order=2, mx0=c["n"][0], my0=c["n"][1], mz0=c["n"][2], ntimes=0, ppc0=2.0, maxptl=65536,
+                           device=0, **kw)
+        Po = O.make_params(dim=c["dim"], order=2, mx0=c["n"][0], my0=c["n"][1], mz0=c["n"][2], ppc0=2.0)
+        P.qi, P.qe, P.qmi, P.qme = Po.qi, Po.qe, Po.qmi, Po.qme
+        return tg.Context(P)
+
+    ctx = ctx_for(periodic=(0, 1, 1))
+    ctx.fields_h2d(*[np.ascontiguousarray(g["surf_in_" + O.ARR_NAMES[a]]) for a in range(6)])
+    for _ in range(2):
+        ctx.bc_b2(); ctx.bc_e2()
+    for a, f in enumerate(ctx.fields_d2h()):
+        assert np.array_equal(f, g["surf_out_" + O.ARR_NAMES[a]]), O.ARR_NAMES[a]
+    ctx.close()
+    ctx = ctx_for(highorder=1)
+    ctx.fields_h2d(*[np.ascontiguousarray(g["s42_in_" + O.ARR_NAMES[a]]) for a in range(6)])
+    ctx.advance_b_halfstep(); ctx.advance_e_fullstep(); ctx.advance_b_halfstep()
+    for a, f in enumerate(ctx.fields_d2h()):
+        assert np.array_equal(f, g["s42_out_" + O.ARR_NAMES[a]]), O.ARR_NAMES[a]
+    ctx.close()
+    ctx = ctx_for()
+    p = np.zeros(ctx.maxptl, tg.PARTICLE_DTYPE)
+    ni, ne = g["mom_ions"].size, g["mom_lecs"].size
+    p[:ni] = g["mom_ions"]; p[ctx.maxhlf:ctx.maxhlf + ne] = g["mom_lecs"]
+    ctx.particles_h2d(p, ni, ne)
+    w = T.oracle_world(dim=c["dim"], order=2, n=c["n"], ppc=2.0, init="none")     # geometry only
+    r = w.ranks[0]
+    for m in MOMENTS:
+        ctx.meanq_fld_cur(m)
+        assert T.max_rel(T.interior(r, ctx.currents_d2h()[0]), T.interior(r, g["mom_" + m])) < 2e-5, m
+    ctx.close()
