@@ -454,3 +454,58 @@ def test_spectrum_known_answers():
         assert sp[gbin - 1, b] == np.count_nonzero(xb == b + 1)
     assert sp.sum() == np.count_nonzero((xb >= 1) & (xb <= nb))
     assert spr.sum() == 0                                  # cold beam: at rest in its own flow frame
+
+
+def _split_world(w1, sizes, **kw):
+    """a multi-rank world holding exactly the particles of the single-rank world w1 (same helper logic as the
+    decomposition-invariance test)"""
+    wn = T.oracle_world(sizes=sizes, **kw)
+    r1 = w1.ranks[0]
+    g, gz = r1.nghost // 2, r1.nghostz // 2
+    dim3 = r1.mz > 1
+    for r in wn.ranks:
+        r.set_counts(0, 0)
+    for src, lecs in ((r1.ions(), 0), (r1.lecs(), 1)):
+        for r in wn.ranks:
+            m = ((src["x"] - r.mxcum >= g + 1) & (src["x"] - r.mxcum < r.mx - g) &
+                 (src["y"] - r.mycum >= g + 1) & (src["y"] - r.mycum < r.my - g))
+            if dim3:
+                m &= (src["z"] - r.mzcum >= gz + 1) & (src["z"] - r.mzcum < r.mz - gz)
+            q = src[m].copy()
+            q["x"] -= r.mxcum; q["y"] -= r.mycum
+            if dim3:
+                q["z"] -= r.mzcum
+            ions, lec = r.counts
+            if lecs:
+                r.particles()[r.maxhlf:r.maxhlf + q.size] = q; r.set_counts(ions, q.size)
+            else:
+                r.particles()[:q.size] = q; r.set_counts(q.size, lec)
+    assert sum(sum(r.counts) for r in wn.ranks) == sum(r1.counts)
+    return wn
+
+
+@pytest.mark.parametrize("sizes", [(1, 2, 1), (1, 1, 2), (1, 2, 2)])
+def test_moments_and_spectra_are_decomposition_invariant(sizes):
+    """meanq_fld_cur folds its box sums across ranks with exchange_current (output.F90:5436) and save_spectrum sums the
+    per-rank histograms (mpi_allreduce, :531-537): both must give what a single rank gives"""
+    kw = dict(dim=3, order=2, n=(16, 12, 12), ppc=4.0, delgam=0.05, seed_fields=0)
+    w1 = T.oracle_world(sizes=(1, 1, 1), **kw)
+    wn = _split_world(w1, sizes, **kw)
+    r1 = w1.ranks[0]
+    g, gz = r1.nghost // 2, r1.nghostz // 2
+    for name in ("tdens", "ebetx", "iener"):
+        w1.meanq_fld_cur(name); wn.meanq_fld_cur(name)
+        full = r1.arr(O.CURX)
+        for r in wn.ranks:
+            loc = T.interior(r, r.arr(O.CURX))
+            ref = full[gz + r.mzcum:gz + r.mzcum + loc.shape[0], g + r.mycum:g + r.mycum + loc.shape[1],
+                       g + r.mxcum:g + r.mxcum + loc.shape[2]]
+            assert np.abs(loc - ref).max() <= 3e-5 * max(np.abs(full).max(), 1e-20), (name, r.idx)
+    mx0 = w1.P.mx0 + r1.nghost
+    lo, hi, *ref = r1.spectrum(mx0)
+    parts = [r.spectrum(mx0, gamma_range=(lo, hi)) for r in wn.ranks]
+    assert min(p[0] for p in parts) == lo and max(p[1] for p in parts) == hi           # the allreduce of :458-463
+    # (the rest-frame spectra use each rank's own slice-mean flow, :477-497 has no allreduce, so they are not invariant)
+    for k in (0, 1):                                                                    # lab-frame ions, electrons: exact sums
+        tot = sum(p[2 + k].astype(np.float64) for p in parts)
+        assert np.array_equal(tot, ref[k].astype(np.float64))
