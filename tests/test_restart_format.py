@@ -45,13 +45,23 @@ def test_restart_record_layout_is_fortran_sequential(tmp_path):
     """byte-level check of the framing: 4-byte marker, payload in write(7) order, 4-byte marker"""
     fields, p, ions, lecs, maxptl = _state(n=(3, 2, 2))
     ff = tmp_path / "f.d"
-    R.write_fields(ff, fields, dseed=1.5, lap=7)
+    R.write_fields(ff, fields, dseed=1.5, lap=7, xinject=20.125, xinject2=510.5, xinject3=3.25, leftwall=15.0, walloc=21.0625)
     raw = ff.read_bytes()
-    nbytes = 12 + 6 * 12 * 4 + 8 + 4 + 20
+    # tail after lap: xinject, xinject2, xinject3 real(dprec) (fields.F90:58), leftwall real(sprec) (particles.F90:67-68),
+    # walloc real(dprec) (particles.F90:74) = 3*8 + 4 + 8 = 36 bytes, unpadded (output.F90:2198)
+    nbytes = 12 + 6 * 12 * 4 + 8 + 4 + 36
     assert struct.unpack("<i", raw[:4])[0] == nbytes and struct.unpack("<i", raw[-4:])[0] == nbytes and len(raw) == nbytes + 8
     assert struct.unpack("<3i", raw[4:16]) == (3, 2, 2)
     assert np.array_equal(np.frombuffer(raw, np.float32, 12, 16), fields[0].ravel())      # ex, x fastest
     assert struct.unpack("<d", raw[16 + 288:16 + 296])[0] == 1.5 and struct.unpack("<i", raw[16 + 296:16 + 300])[0] == 7
+    assert struct.unpack("<3d", raw[16 + 300:16 + 324]) == (20.125, 510.5, 3.25)            # float64 offsets
+    assert struct.unpack("<f", raw[16 + 324:16 + 328])[0] == 15.0 and struct.unpack("<d", raw[16 + 328:16 + 336])[0] == 21.0625
+    # a record of the wrong length (e.g. the five-float32 tail an earlier version wrote) is refused, not mis-decoded
+    bad = tmp_path / "bad.d"
+    body = raw[4:-4][:-36] + np.zeros(5, np.float32).tobytes()
+    bad.write_bytes(struct.pack("<i", len(body)) + body + struct.pack("<i", len(body)))
+    with pytest.raises(ValueError, match="restflds record"):
+        R.read_fields(bad)
     # split records: leading marker negative while another sub-record follows, trailing marker negative when one precedes
     R.write_fields(ff, fields, max_subrecord=100)
     raw = ff.read_bytes()

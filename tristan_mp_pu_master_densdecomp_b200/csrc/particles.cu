@@ -617,15 +617,22 @@ int prt_exchange(tgpu_ctx *h)
     if (!h->nccl_comm) { tgpu_set_error("tgpu_exchange_particles: communicator not initialised (tgpu_comm_init)"); return TGPU_ENCCL; }
     const int B = h->P.buffsize;
     int nout[2][9], off[2][9], nin[2][9];
+    // Error protocol.  The reference `stop`s the whole job on a full buffer (particles.F90:1933-1938).  Here nothing may
+    // return between ncclGroupStart and ncclGroupEnd, and no rank may skip a group its neighbours enter: a rank whose
+    // outbox overflows still takes part in both groups -- sending zero particles and an overflow flag with its counts --
+    // and reports TGPU_EOVERFLOW afterwards, together with every neighbour that saw the flag.
+    int overflow = 0;
     for (int s = 0; s < 2; s++) for (int c = 0; c < 9; c++) {
         off[s][c] = h->h_small[s * 16 + c]; nout[s][c] = h->h_small[s * 16 + c + 1] - h->h_small[s * 16 + c];
         if (c == 4) nout[s][c] = 0;
     }
+    for (int c = 0; c < 9; c++) if (nout[0][c] + nout[1][c] > B) overflow = 1;
+    if (overflow) for (int s = 0; s < 2; s++) for (int c = 0; c < 9; c++) nout[s][c] = 0;
     // pack: sendbuf[c] = ions then electrons
-    int32_t *hc = h->h_small + 32;          // [c][2] counts out, then [c][2] counts in
+    int32_t *hc = h->h_small + 32;          // [c][3] out: ions, electrons, overflow flag; then [c][3] in
     for (int c = 0; c < 9; c++) {
-        if (c == 4) { hc[2 * c] = hc[2 * c + 1] = 0; continue; }
-        if (nout[0][c] + nout[1][c] > B) { tgpu_set_error("migration outbox overflow (buffsize)"); return TGPU_EOVERFLOW; }
+        hc[3 * c + 2] = overflow;
+        if (c == 4) { hc[3 * c] = hc[3 * c + 1] = 0; continue; }
         int o = 0;
         for (int s = 0; s < 2; s++) {
             if (nout[s][c]) {
@@ -634,39 +641,49 @@ int prt_exchange(tgpu_ctx *h)
                 CKK(h);
             }
             o += nout[s][c];
-            hc[2 * c + s] = nout[s][c];
+            hc[3 * c + s] = nout[s][c];
         }
     }
-    CK(cudaMemcpyAsync(h->d_small, hc, 18 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_small, hc, 27 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     int rc = comm_group_begin(h); if (rc) return rc;
+    int rc_in = 0;
     for (int c = 0; c < 9; c++) {
         if (c == 4) continue;
         int da = c % 3 - 1, db = c / 3 - 1;
         int to = topo_neighbour2(h, da, db), from = topo_neighbour2(h, -da, -db);
-        comm_send(h, h->d_small + 2 * c, 2 * sizeof(int32_t), to);
-        comm_recv(h, h->d_small + 18 + 2 * c, 2 * sizeof(int32_t), from);
+        int r1 = comm_send(h, h->d_small + 3 * c, 3 * sizeof(int32_t), to);
+        int r2 = comm_recv(h, h->d_small + 27 + 3 * c, 3 * sizeof(int32_t), from);
+        if (!rc_in) rc_in = r1 ? r1 : r2;
     }
-    rc = comm_group_end(h); if (rc) return rc;
-    CK(cudaMemcpyAsync(hc + 18, h->d_small + 18, 18 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    rc = comm_group_end(h); if (rc_in) return rc_in; if (rc) return rc;
+    CK(cudaMemcpyAsync(hc + 27, h->d_small + 27, 27 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    for (int c = 0; c < 9; c++) for (int s = 0; s < 2; s++) nin[s][c] = c == 4 ? 0 : hc[18 + 2 * c + s];
+    int remote_overflow = 0;
+    for (int c = 0; c < 9; c++) {
+        for (int s = 0; s < 2; s++) nin[s][c] = c == 4 ? 0 : hc[27 + 3 * c + s];
+        if (c != 4 && hc[27 + 3 * c + 2]) remote_overflow = 1;
+        // cannot happen with a job-wide buffsize (the sender clips at the same B); checked BEFORE the payload group opens
+        if (nin[0][c] + nin[1][c] > B) { tgpu_set_error("migration inbox overflow: buffsize differs between ranks"); return TGPU_EOVERFLOW; }
+    }
     rc = comm_group_begin(h); if (rc) return rc;
     for (int c = 0; c < 9; c++) {
         if (c == 4) continue;
         int da = c % 3 - 1, db = c / 3 - 1;
         int to = topo_neighbour2(h, da, db), from = topo_neighbour2(h, -da, -db);
         int ns = nout[0][c] + nout[1][c], nr = nin[0][c] + nin[1][c];
-        if (nr > B) { tgpu_set_error("migration inbox overflow (buffsize)"); return TGPU_EOVERFLOW; }
-        if (ns) comm_send(h, h->sendbuf + (size_t)c * B, (size_t)ns * sizeof(tgpu_particle), to);
-        if (nr) comm_recv(h, h->recvbuf + (size_t)c * B, (size_t)nr * sizeof(tgpu_particle), from);
+        int r1 = ns ? comm_send(h, h->sendbuf + (size_t)c * B, (size_t)ns * sizeof(tgpu_particle), to) : 0;
+        int r2 = nr ? comm_recv(h, h->recvbuf + (size_t)c * B, (size_t)nr * sizeof(tgpu_particle), from) : 0;
+        if (!rc_in) rc_in = r1 ? r1 : r2;
     }
-    rc = comm_group_end(h); if (rc) return rc;
+    rc = comm_group_end(h); if (rc_in) return rc_in; if (rc) return rc;
     for (int c = 0; c < 9; c++) {
         if (c == 4) continue;
         rc = prt_append(h, 0, h->recvbuf + (size_t)c * B, nin[0][c], false); if (rc) return rc;
         rc = prt_append(h, 1, h->recvbuf + (size_t)c * B + nin[0][c], nin[1][c], false); if (rc) return rc;
     }
     for (int s = 0; s < 2; s++) for (int c = 0; c < 11; c++) h->h_small[s * 16 + c] = h->sp[s].n;   // outboxes consumed
+    if (overflow) { tgpu_set_error("migration outbox overflow (buffsize)"); return TGPU_EOVERFLOW; }
+    if (remote_overflow) { tgpu_set_error("migration outbox overflow (buffsize) on a neighbouring rank"); return TGPU_EOVERFLOW; }
     return 0;
 }
 

@@ -4,7 +4,9 @@ The reference writes two Fortran *unformatted sequential* files per rank, one re
 (code/output.F90:2194-2226 writes them, code/restart.F90:209-253 reads them back):
 
   restflds.<job>.<rank>.d :  mx, my, mz (int32) | ex, ey, ez, bx, by, bz (float32, Fortran order (mx,my,mz)) |
-                             dseed (float64) | lap (int32) | xinject, xinject2, xinject3, leftwall, walloc (float32)
+                             dseed (float64) | lap (int32) | xinject, xinject2, xinject3 (float64: real(dprec),
+                             fields.F90:58) | leftwall (float32: real(sprec), particles.F90:67-68) | walloc (float64,
+                             particles.F90:74) -- a 36-byte tail, no padding inside a Fortran record
   restprtl.<job>.<rank>.d :  ions, lecs, maxptl, maxhlf, totalpartnum (int32) | then, attribute by attribute, the ions
                              followed by the electrons: x y z u v w ch (float32), ind proc splitlev (int32)
 
@@ -13,6 +15,8 @@ length markers (gfortran and ifort defaults); a record longer than `max_subrecor
 into sub-records whose leading marker is negative when another sub-record follows and whose trailing marker is negative
 when one precedes (the gfortran convention).  This module is host-side glue: it is not on the hot path.
 """
+import struct
+
 import numpy as np
 
 from . import PARTICLE_DTYPE
@@ -20,6 +24,7 @@ from . import PARTICLE_DTYPE
 _FLOAT_ATTRS = ("x", "y", "z", "u", "v", "w", "ch")
 _INT_ATTRS = ("ind", "proc", "splitlev")
 GFORTRAN_MAX_SUBRECORD = 2 ** 31 - 9
+_TAIL_FMT = "<3dfd"          # xinject, xinject2, xinject3 (dprec), leftwall (sprec), walloc (dprec): 36 bytes
 
 
 def _write_record(f, payload, max_subrecord=GFORTRAN_MAX_SUBRECORD):
@@ -68,7 +73,7 @@ def write_fields(path, fields, dseed=0.0, lap=0, xinject=0.0, xinject2=0.0, xinj
         blob.append(np.ascontiguousarray(a).tobytes())
     blob.append(np.float64(dseed).tobytes())
     blob.append(np.int32(lap).tobytes())
-    blob.append(np.array([xinject, xinject2, xinject3, leftwall, walloc], np.float32).tobytes())
+    blob.append(struct.pack(_TAIL_FMT, xinject, xinject2, xinject3, leftwall, walloc))
     with open(path, "wb") as f:
         _write_record(f, b"".join(blob), max_subrecord)
 
@@ -79,6 +84,10 @@ def read_fields(path):
         rec = _read_record(f)
     mx, my, mz = (int(v) for v in np.frombuffer(rec, np.int32, 3))
     n = mx * my * mz
+    want = 12 + 24 * n + 8 + 4 + struct.calcsize(_TAIL_FMT)
+    if len(rec) != want:
+        raise ValueError(f"restflds record is {len(rec)} bytes, expected {want} for {mx}x{my}x{mz} "
+                         "(output.F90:2198: 3 int32, 6 float32 arrays, dseed f64, lap i32, 3 f64, f32, f64)")
     off = 12
     fields = []
     for _ in range(6):
@@ -86,9 +95,9 @@ def read_fields(path):
         off += 4 * n
     dseed = float(np.frombuffer(rec, np.float64, 1, off)[0]); off += 8
     lap = int(np.frombuffer(rec, np.int32, 1, off)[0]); off += 4
-    tail = np.frombuffer(rec, np.float32, 5, off)
-    scal = dict(dseed=dseed, lap=lap, xinject=float(tail[0]), xinject2=float(tail[1]), xinject3=float(tail[2]),
-                leftwall=float(tail[3]), walloc=float(tail[4]))
+    tail = struct.unpack_from(_TAIL_FMT, rec, off)
+    scal = dict(dseed=dseed, lap=lap, xinject=tail[0], xinject2=tail[1], xinject3=tail[2],
+                leftwall=tail[3], walloc=tail[4])
     return fields, scal
 
 
