@@ -518,8 +518,8 @@ static void surface(float *bx, float *by, float *bz, const float *ex, const floa
 static void radiation_flags(const orc_rank *r, int rad[3])
 {
     rad[0] = 1 - r->P.periodicx; rad[1] = 1 - r->P.periodicy; rad[2] = 1 - r->P.periodicz;
-    if (rad[1] == 1) rad[2] = 1;
-    if (r->P.dim == 2) rad[2] = 0;                            /* the z call is #ifndef twoD (:287-291, 418-422) */
+    /* the "open y opens z" promotion (:91-93) is #ifdef twoD only, and there the z call is compiled out (:287-291, 418-422) */
+    if (r->P.dim == 2) rad[2] = 0;
 }
 /* the `surface` part of bc_b2 (high faces) / bc_e2 (low faces); the ghost refresh that follows is orc_bc_fields */
 void orc_surface_b(orc_rank *r)

@@ -46,6 +46,8 @@ static void free_species(Species &S)
     cudaFree(S.ind); cudaFree(S.tag);
 }
 
+static int init_impl(tgpu_ctx *h, const tgpu_params *p, int ndev);
+
 extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
 {
     if (!p || !out) { tgpu_set_error("null argument"); return TGPU_EINVAL; }
@@ -61,12 +63,21 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     if (p->sizex < 1 || p->sizey < 1 || p->sizez < 1 || p->maxptl < 2 || p->c <= 0.f || p->c >= 0.5f) { tgpu_set_error("bad sizes / c (need 0 < c < 0.5)"); return TGPU_EINVAL; }
     int ndev = tgpu_device_count();
     if (ndev <= 0) { tgpu_set_error("no CUDA device: libtristan_gpu has no CPU fallback"); return TGPU_ECUDA; }
-    tgpu_ctx *h = new tgpu_ctx();
-    memset(h->f, 0, sizeof h->f);
+    const int size0 = p->sizex * p->sizey * (p->dim == 3 ? p->sizez : 1);
+    if (size0 > 1 && (!p->mxl || !p->myl || (p->dim == 3 && !p->mzl))) { tgpu_set_error("mxl/myl/mzl required when size0 > 1"); return TGPU_EINVAL; }
+    if (size0 > 1 && p->buffsize < 1) { tgpu_set_error("buffsize must be positive when size0 > 1"); return TGPU_EINVAL; }
+    tgpu_ctx *h = new tgpu_ctx();        // value-initialised: every pointer, stream and event starts out null
+    const int rc = init_impl(h, p, ndev);
+    if (rc) { const std::string why = g_err; tgpu_finalize(h); tgpu_set_error(why); return rc; }   // one cleanup path for every failure
+    *out = h;
+    return 0;
+}
+
+static int init_impl(tgpu_ctx *h, const tgpu_params *p, int ndev)
+{
     h->P = *p;
     h->size0 = p->sizex * p->sizey * (p->dim == 3 ? p->sizez : 1);
     if (p->dim == 2) h->P.sizez = 1;
-    if (h->size0 > 1 && (!p->mxl || !p->myl || (p->dim == 3 && !p->mzl))) { delete h; tgpu_set_error("mxl/myl/mzl required when size0 > 1"); return TGPU_EINVAL; }
     for (int r = 0; r < h->size0; r++) {
         h->mxl.push_back(p->mxl ? p->mxl[r] : p->mx); h->myl.push_back(p->myl ? p->myl[r] : p->my);
         h->mzl.push_back(p->mzl ? p->mzl[r] : p->mz);
@@ -75,7 +86,7 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     h->device = p->device >= 0 ? p->device : p->rank % ndev;
     CK(cudaSetDevice(h->device));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, h->device));
-    if (prop.major < 10) { delete h; tgpu_set_error(std::string("device is not sm_100 class: ") + prop.name); return TGPU_ECUDA; }
+    if (prop.major < 10) { tgpu_set_error(std::string("device is not sm_100 class: ") + prop.name); return TGPU_ECUDA; }
     // the field kernels are short and latency-bound, the particle scatter is long and HBM-bound: giving the field stream
     // the higher priority lets its CTAs slip in between the scatter's instead of queueing behind them
     int prio_lo = 0, prio_hi = 0;
@@ -144,14 +155,12 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     rc |= dalloc(&h->stage, h->stage_particles);
     h->sendbuf = h->recvbuf = nullptr;
     if (h->size0 > 1) {
-        if (p->buffsize < 1) { tgpu_set_error("buffsize must be positive when size0 > 1"); return TGPU_EINVAL; }
         rc |= dalloc(&h->sendbuf, (size_t)TGPU_NDIR * p->buffsize); rc |= dalloc(&h->recvbuf, (size_t)TGPU_NDIR * p->buffsize);
     }
     if (rc) { tgpu_set_error("device allocation failed: " + g_err); return TGPU_ECUDA; }
     h->need_prim = 1; h->fused_pending = 0; h->keys_valid = 0; h->hook_kind = 0; h->in_step = 0; h->opt_fused = 1; h->nccl_comm = nullptr; h->lap = 0; h->launches = 0; h->timing = 0;
     for (int i = 0; i < TGPU_NPHASE; i++) h->phase_ms[i] = 0;
     CK(cudaDeviceSynchronize());
-    *out = h;
     return 0;
 }
 
@@ -159,7 +168,8 @@ extern "C" int tgpu_finalize(tgpu_ctx *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream_main); cudaStreamSynchronize(h->stream_prt);
+    if (h->stream_main) cudaStreamSynchronize(h->stream_main);
+    if (h->stream_prt) cudaStreamSynchronize(h->stream_prt);
     comm_destroy(h);
     for (int a = 0; a < 9; a++) cudaFree(h->f[a]);
     for (int a = 0; a < 3; a++) { cudaFree(h->ftmp[a]); cudaFree(h->shadow[a]); }
@@ -167,14 +177,18 @@ extern "C" int tgpu_finalize(tgpu_ctx *h)
     cudaFree(h->halo);
     for (int s = 0; s < 2; s++) { free_species(h->sp[s]); free_species(h->alt[s]); cudaFree(h->key[s]); cudaFree(h->perm[s]); }
     cudaFree(h->slot); cudaFree(h->bincount); cudaFree(h->binoff); cudaFree(h->cub_tmp); cudaFree(h->d_small);
-    cudaFreeHost(h->h_small); cudaFree(h->stage);
-    for (int b = 0; b < 2; b++) { cudaEventDestroy(h->ev_out_full[b]); cudaEventDestroy(h->ev_out_free[b]); }
-    cudaStreamDestroy(h->stream_d2h);
+    if (h->h_small) cudaFreeHost(h->h_small);
+    cudaFree(h->stage);
+    auto ev_free = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
+    auto st_free = [](cudaStream_t s) { if (s) cudaStreamDestroy(s); };
+    for (int b = 0; b < 2; b++) { ev_free(h->ev_out_full[b]); ev_free(h->ev_out_free[b]); }
+    st_free(h->stream_d2h);
     if (h->sendbuf) cudaFree(h->sendbuf);
     if (h->recvbuf) cudaFree(h->recvbuf);
-    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev_move); cudaEventDestroy(h->ev_prt);
-    for (int b = 0; b < 2; b++) { cudaEventDestroy(h->ev_stage_full[b]); cudaEventDestroy(h->ev_stage_free[b]); }
-    cudaStreamDestroy(h->stream_main); cudaStreamDestroy(h->stream_prt);
+    ev_free(h->ev0); ev_free(h->ev1); ev_free(h->ev_move); ev_free(h->ev_prt);
+    for (int b = 0; b < 2; b++) { ev_free(h->ev_stage_full[b]); ev_free(h->ev_stage_free[b]); }
+    st_free(h->stream_main); st_free(h->stream_prt);
+    cudaGetLastError();
     delete h;
     return 0;
 }
@@ -228,7 +242,9 @@ extern "C" int tgpu_currents_h2d(tgpu_ctx *h, const float *cx, const float *cy, 
 extern "C" int tgpu_currents_d2h(tgpu_ctx *h, float *cx, float *cy, float *cz)
 {
     ENTER(h);
-    if (h->fused_pending) { int rc = fld_add_shadow(h); if (rc) return rc; h->fused_pending = 0; }
+    // Between a fused tgpu_move_particles and tgpu_deposit_particles the lap's deposit sits in the shadow arrays; it is NOT
+    // folded in here: the host sees cur exactly as the reference would at this point (e.g. zeros after reset_currents),
+    // and tgpu_deposit_particles still finds its pending deposit.
     float *d[3] = {cx, cy, cz};
     return arrays_copy(h, 6, 3, nullptr, d, false);
 }
@@ -236,6 +252,11 @@ extern "C" int tgpu_particles_h2d(tgpu_ctx *h, const tgpu_particle *p, int ions,
 {
     ENTER(h); if (!p) { tgpu_set_error("null particles"); return TGPU_EINVAL; }
     for (int i = 0; i < 32; i++) h->h_small[i] = 0;
+    if (h->fused_pending) {
+        // the uploaded records replace the ones whose motion was deposited into the shadow arrays: drop that deposit
+        for (int a = 0; a < 3; a++) CK(cudaMemsetAsync(h->shadow[a], 0, h->shadow_floats * sizeof(float), h->stream));
+        h->fused_pending = 0;
+    }
     int rc = prt_h2d(h, p, ions, lecs);
     for (int s = 0; s < 2; s++) for (int c = 0; c < 11; c++) h->h_small[s * 16 + c] = h->sp[s].n;
     return rc;
@@ -470,7 +491,7 @@ extern "C" int tgpu_step(tgpu_ctx *h, int nlaps)
         DO(join_prt(h));                   // particles of the previous lap are sorted and migrated
         DO(tgpu_move_particles(h));        // :134
         if (overlap) {
-            CK(cudaEventRecord(h->ev_move, h->stream_main));
+            DO(cudaEventRecord(h->ev_move, h->stream_main) == cudaSuccess ? 0 : (tgpu_set_error("cudaEventRecord(ev_move)"), TGPU_ECUDA));
             DO(tgpu_advance_b_halfstep(h));    // :139
             DO(tgpu_bc_b1(h));                 // :140
             if (rad) DO(tgpu_bc_b2(h));        // :145

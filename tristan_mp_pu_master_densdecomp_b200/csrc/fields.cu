@@ -854,9 +854,10 @@ static int surface_face(tgpu_ctx *h, float *b1, float *b2, float *b3, const floa
 int fld_surface(tgpu_ctx *h, int is_e)
 {
     const tgpu_params &P = h->P;
-    int rad[3] = {1 - P.periodicx, 1 - P.periodicy, 1 - P.periodicz};                 // fieldboundaries.F90:90-94
-    if (rad[1] == 1) rad[2] = 1;
-    if (P.dim == 2) rad[2] = 0;                                                       // the z call is #ifndef twoD
+    // fieldboundaries.F90:88-94: "open y also opens z" exists only under #ifdef twoD, where the z call itself is compiled
+    // out (:287-291, 418-422) -- so in 3D an open y with periodic z radiates on y only
+    int rad[3] = {1 - P.periodicx, 1 - P.periodicy, 1 - P.periodicz};
+    if (P.dim == 2) rad[2] = 0;
     if (!rad[0] && !rad[1] && !rad[2]) return 0;
     float *ex = h->f[0], *ey = h->f[1], *ez = h->f[2], *bx = h->f[3], *by = h->f[4], *bz = h->f[5];
     const long long ix = 1, iy = P.mx, iz = P.dim == 3 ? (long long)P.mx * P.my : 0, lot = h->G.lot;
