@@ -1,0 +1,149 @@
+"""GPU parity at the sizes BASELINE.json's configs name, and the fused cell-run kernels at a size where long cell runs,
+multi-cell window slides, the lazy sort's permutation and the 4x4 tiled shadow padding all engage.
+
+  configs[0]  2D Weibel, user/input.weibel: 128 x 128 cells, dd1 (nghost 5), 16 ppc, c = .45, c_omp = 10, gamma0 = .5
+              (beta), delgam = 2e-5, Corr = 1.025, ntimes = 32, filter1 (the default build has no -Dfilter2), periodic;
+              262 144 particles drawn by the seeded loader (particles.F90:2549-2938, user/user_weibel.F90:283-310).
+  configs[1]  2D two-stream, user/input.twostream: 128 x 2 cells, dd2 (nghost 7), 64 ppc, electrons only
+              (user/user_twostream.F90:299-300); 8 192 particles.
+  3D          dd2 / dd1 / dd3 at 128 x 64 x 64 cells, 16 ppc (8.4e6 particles): one mainloop lap from identical state,
+              currents at 1e-5 of the max-norm, particles matched by (proc, ind).
+
+Every lap is compared from identical state (chaotic divergence, SURVEY hard part 6): after the comparison the oracle's
+state is uploaded again.  Bars are those of test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+import pic_testlib as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tgm(tg):
+    if tg.device_count() < 1:
+        pytest.fail("no CUDA device visible: the GPU tests must run on the B200 box")
+    return tg
+
+
+def _compare_lap(ctx, w, lap, ftol, what, rtol_pos=2e-6, rtol_mom=2e-5):
+    r = w.ranks[0]
+    fg = ctx.fields_d2h()
+    for a in range(6):
+        err = T.max_rel(T.interior(r, fg[a]), T.interior(r, r.arr(a)))
+        assert err < ftol, f"{what} lap {lap} {O.ARR_NAMES[a]} err {err:.3e}"
+    assert ctx.counts() == r.counts, f"{what} lap {lap}: counts {ctx.counts()} != {r.counts}"
+    gi, ge = T.gpu_particles(ctx)
+    oi, oe = T.oracle_particles(r)
+    T.assert_particles_close(gi, oi, rtol_pos=rtol_pos, rtol_mom=rtol_mom, what=f"{what} ions lap {lap}")
+    T.assert_particles_close(ge, oe, rtol_pos=rtol_pos, rtol_mom=rtol_mom, what=f"{what} electrons lap {lap}")
+
+
+def test_config0_weibel_2d_dd1(tgm):
+    """configs[0] exactly as user/input.weibel ships it; 3 laps through tgpu_step, each from identical state"""
+    w = T.oracle_world(dim=2, order=1, n=(128, 128, 1), ppc=16.0, ntimes=32, filter_kind=1, delgam=2e-5, gamma0=0.5,
+                       init="weibel", seed_fields=0)
+    r = w.ranks[0]
+    assert sum(r.counts) == 262144 and (r.mx, r.my, r.mz) == (133, 133, 1)
+    ctx = tgm.Context(T.gpu_params(tgm, w, device=0))
+    T.upload(ctx, r)
+    for lap in range(3):
+        ctx.step(1); w.step()
+        # fields start at zero: everything in E is the filtered current of this lap -> compare against its own max-norm
+        _compare_lap(ctx, w, lap, 2e-5, "configs[0]")
+        cg = ctx.currents_d2h()
+        for c in range(3):
+            err = T.max_rel(T.interior(r, cg[c]), T.interior(r, r.arr(6 + c)))
+            assert err < 2e-5, f"configs[0] lap {lap} {O.ARR_NAMES[6 + c]} err {err:.3e}"
+        T.upload(ctx, r)
+    ctx.close()
+
+
+def test_config0_weibel_2d_dd1_resident_invariants(tgm):
+    """the same problem run resident for 20 laps (no re-sync): particle count and identities are conserved, the total
+    field + kinetic energy stays within 1 % (cold beams, growth has not started), B stays divergence-free to round-off"""
+    w = T.oracle_world(dim=2, order=1, n=(128, 128, 1), ppc=16.0, ntimes=32, filter_kind=1, delgam=2e-5, gamma0=0.5,
+                       init="weibel", seed_fields=0)
+    r = w.ranks[0]
+    ctx = tgm.Context(T.gpu_params(tgm, w, device=0))
+    T.upload(ctx, r)
+    p0, i0, l0 = ctx.particles_d2h()
+
+    def kinetic(p, ions, lecs):
+        e = 0.0
+        for lo, n in ((0, ions), (ctx.maxhlf, lecs)):
+            q = p[lo:lo + n]
+            g = np.sqrt(1.0 + q["u"].astype(np.float64) ** 2 + q["v"].astype(np.float64) ** 2 + q["w"].astype(np.float64) ** 2)
+            e += float((g - 1.0).sum())
+        return e
+    k0 = kinetic(p0, i0, l0)
+    ctx.step(20)
+    p1, i1, l1 = ctx.particles_d2h()
+    assert (i1, l1) == (i0, l0)
+    for lo, n in ((0, i0), (ctx.maxhlf, l0)):
+        a, b = T.sort_particles(p0[lo:lo + n].copy()), T.sort_particles(p1[lo:lo + n].copy())
+        assert np.array_equal(a["ind"], b["ind"]) and np.array_equal(a["proc"], b["proc"])
+    k1 = kinetic(p1, i1, l1)
+    assert abs(k1 - k0) < 1e-2 * k0
+    bx, by, bz = ctx.fields_d2h()[3:]
+    g = r.nghost // 2
+    # 2D: div B = d bx/dx + d by/dy on the interior (bx at (i, j+1/2), by at (i+1/2, j): fields.F90:716-719)
+    div = (np.roll(bx, -1, 2) - bx) + (np.roll(by, -1, 1) - by)
+    scale = max(float(np.abs(bx).max()), float(np.abs(by).max()), 1e-30)
+    assert np.abs(div[:, g + 1:r.my - g - 2, g + 1:r.mx - g - 2]).max() < 1e-4 * scale + 1e-12
+    ctx.close()
+
+
+def test_config1_twostream_2d_dd2(tgm):
+    """configs[1] exactly as user/input.twostream ships it: electrons only, 3 laps from identical state"""
+    w = T.oracle_world(dim=2, order=2, n=(128, 2, 1), ppc=64.0, ntimes=32, filter_kind=1, delgam=2e-5, gamma0=0.5,
+                       init="twostream", seed_fields=0)
+    r = w.ranks[0]
+    ions, lecs = r.counts
+    assert ions == 0 and lecs == 8192 and (r.mx, r.my, r.mz) == (135, 9, 1)
+    ctx = tgm.Context(T.gpu_params(tgm, w, device=0))
+    T.upload(ctx, r)
+    for lap in range(3):
+        ctx.step(1); w.step()
+        _compare_lap(ctx, w, lap, 2e-5, "configs[1]")
+        T.upload(ctx, r)
+    ctx.close()
+
+
+@pytest.mark.parametrize("order", [2, 1, 3])
+def test_fused_kernels_against_oracle_at_size(tgm, order):
+    """3D, 128 x 64 x 64 cells, 16 ppc, uniform drifting plasma with seeded fields: one lap of tgpu_step (fused mover +
+    deposit + lazy sort for orders 1/2, cell-run deposit for order 3) against the oracle; then a second lap from the same
+    state so that the fused kernel also reads through a pending permutation with unwrapped positions."""
+    n = (128, 64, 64)
+    w = T.oracle_world(dim=3, order=order, n=n, ppc=16.0, ntimes=4, filter_kind=2, init="uniform", seed_fields=3)
+    r = w.ranks[0]
+    assert sum(r.counts) == 16 * n[0] * n[1] * n[2]
+    ctx = tgm.Context(T.gpu_params(tgm, w, device=0))
+    T.upload(ctx, r)
+    # currents alone first: move + deposit from identical state, before the filter spreads them
+    ctx.bc_b1(); ctx.bc_e1(); ctx.advance_b_halfstep(); ctx.bc_b1()
+    ctx.move_particles(); ctx.reset_currents(); ctx.deposit_particles()
+    for ph in (O.PH_BC_B1, O.PH_BC_E1, O.PH_BHALF, O.PH_BC_B1, O.PH_MOVE, O.PH_RESET, O.PH_DEPOSIT):
+        w.phase(ph)
+    cg = ctx.currents_d2h()
+    for c in range(3):
+        err = T.max_rel(cg[c], r.arr(6 + c))
+        assert err < 1e-5, f"order {order} {O.ARR_NAMES[6 + c]} err {err:.3e}"
+    ctx.exchange_particles(); ctx.inject_others()
+    w.phase(O.PH_EXCH_P); w.phase(O.PH_INJECT_OTHERS)
+    gi, ge = T.gpu_particles(ctx)
+    oi, oe = T.oracle_particles(r)
+    T.assert_particles_close(gi, oi, what="ions"); T.assert_particles_close(ge, oe, what="electrons")
+    # one full lap from the oracle's state, then two more WITHOUT a device -> host read in between, so that the second
+    # one runs the fused kernel through the pending permutation on unwrapped positions (a d2h would materialise it);
+    # tolerances doubled for the second lap as in test_full_lap (per-lap round-off compounds)
+    T.upload(ctx, r)
+    ctx.step(1); w.step()
+    _compare_lap(ctx, w, 0, 3e-4, f"3D dd{order}")
+    T.upload(ctx, r)
+    ctx.step(2); w.step(); w.step()
+    _compare_lap(ctx, w, 2, 9e-4, f"3D dd{order} (through the pending permutation)", rtol_pos=4e-5, rtol_mom=4e-4)
+    ctx.close()
