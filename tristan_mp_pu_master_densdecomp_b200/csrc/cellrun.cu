@@ -11,55 +11,61 @@
 // step keeps both the old and the new shape inside it).  So the deposit is made OUTPUT-STATIONARY:
 //   record pipeline: each lane fetches the record of its NEXT step (through the lazy sort's permutation, whose entry was
 //           loaded one step earlier) with 4-byte cp.async into per-lane landing slots while the current step is deposited;
-//   phase 1 (lane = particle): read the landed record, [gather node-centred fields (packed FFMA2) + Boris push + store +
-//           sort key of the new cell + rank in its bin], build the 1-D factors of the Esirkepov sum from the old and new
-//           shapes and park them in shared memory (44 floats per particle).  Deposit-only launches recompute the old
-//           position as the reference does (x - u/gamma*c); fused launches use the gather's shape at the true pre-push
-//           position (equal to round-off);
-//   phase 2 (half-warp = one footprint): lane (j,k) of a half-warp owns the 4 x-cells of row (j,k) of the footprint
-//           for all three components = 12 register accumulators (6 FFMA2 pairs).  It walks its 16 particles, reading the
-//           factors with broadcast 128-bit shared loads; the two half-warps run in lockstep.  The x-planes form a ring
-//           (plane of cell x lives in register x mod 4, phase 1 stores the x factors pre-rotated): when the cell advances
-//           along x the completed plane is flushed with one predicated fp32 RED per (cell, component) into the tiled
-//           shadow arrays (tgpu_internal.h row_index) and cleared; nothing moves between registers.
+//   phase 1 (lane = particle, 32 particles per warp step): read the landed record, [gather node-centred fields (packed
+//           FFMA2) + Boris push + store + sort key of the new cell + rank in its bin], build the 1-D factors of the
+//           Esirkepov sum from the old and new shapes and park them in shared memory (40 floats per particle).
+//           Deposit-only launches recompute the old position as the reference does (x - u/gamma*c); fused launches use
+//           the gather's shape at the true pre-push position (equal to round-off);
+//   phase 2 (QUARTER-warp = one footprint): lane (j, kp) of a quarter owns the 4 x-cells of the two footprint rows
+//           (j, kp) and (j, kp + 2) for all three components = 24 register accumulators (12 FFMA2 pairs).  It walks the 8
+//           particles its quarter staged; the four quarters run in lockstep.  The x-planes form a ring (plane of cell x
+//           lives in register x mod 4, phase 1 stores the x factors pre-rotated): when the cell advances along x the
+//           completed plane is flushed with predicated fp32 REDs into the tiled shadow arrays (tgpu_internal.h
+//           row_index) and cleared; nothing moves between registers.
+// Why a quarter-warp: the factors reach phase 2 through shared memory, and profiles/micro/lds_rate.cu measures what that
+// costs on B200 -- an LDS.128 takes 2 LSU cycles per warp when consecutive lanes share addresses and 4 otherwise (an
+// LDS.32 takes 1): the data path delivers 8 bytes per lane per cycle whatever the broadcast.  With 16 lanes per
+// footprint every particle cost 6 LSU cycles (of the ~14 the whole kernel spent per particle, 78 % of the pipe); with 8
+// lanes owning two rows each the x factors are loaded once for twice the outputs: 13 cycles per 4 particles.  The same
+// move cuts the per-lane preparation (9 scalar FP per 12 outputs -> 3 scalar + 6 packed per 24 outputs).
 // With ~8 particles per cell and species, that is ~6 global REDs per particle instead of up to 192 atomics, and the
 // arithmetic is the factorised form of Appendix A.3 (Jx = q*Wx(j,k)*prefix_i(dSx), ...).
 // Nothing here depends on the particles being sorted for correctness -- an unsorted tail (fresh arrivals) only makes
 // the window jump and flush more often (which is why freshly uploaded records are sorted once, cellrun_move_deposit).
-// Measured character (profiles/README.md): 56 warp-instructions per particle, issue slots 70 % and the L1/shared data
-// pipe 78 % busy, DRAM 24 % of peak: co-limited by instruction issue and LSU wavefronts, not by HBM.
 #include "tgpu_internal.h"
 #include "shapes.cuh"
 
 #ifndef CR_WARPS
 #define CR_WARPS 8
 #endif
-#define CR_STRIDE 44
 #ifndef CR_MINB
 #define CR_MINB 3
 #endif
 #ifndef CR_CHUNK
-#define CR_CHUNK 128          // particles per half-warp
+#define CR_CHUNK 128          // particles per quarter-warp
 #endif
-#ifndef CR_UNROLL
-#define CR_UNROLL 4           // phase-2 unroll (particles per half-warp per loop trip)
-#endif
-#define CR_STR(x) #x
-#define CR_DO_PRAGMA(x) _Pragma(CR_STR(x))
-#ifndef CR_FFMA2
-#define CR_FFMA2 1            // packed fp32 (FFMA2/FMUL2) in the gather and the deposit accumulation: measured 2-3 % faster
-#endif
-// factor staging of one warp: two halves of 16 particles x CR_STRIDE floats; the second half starts 16 floats (half of
-// the 32 banks) further on, so the lockstep phase-2 loads of the two half-warps never fall into the same banks
-#define CR_HALF_FLOATS (16 * CR_STRIDE + 16)
-#define CR_WARP_FLOATS (2 * CR_HALF_FLOATS)
-#define CR_SMEM_BYTES (sizeof(float) * CR_WARPS * CR_WARP_FLOATS + sizeof(uint32_t) * CR_WARPS * 2 * 9 * 32)
+#define CR_STRIDE 44          // floats between the staged factors of consecutive particles (40 used; 44 keeps the
+                              // phase-1 STS.128 of a quarter-warp conflict-free: 12 banks apart)
+#define CR_QFLOATS (8 * CR_STRIDE + 8)     // one quarter's staging; the four quarters start 8 banks apart so that their
+                                           // lockstep phase-2 loads never fall into the same banks
+#define CR_WARP_FLOATS (4 * CR_QFLOATS)
+#define CR_REC_WORDS (2 * 9 * 32)          // record landing slots of one warp: [buf][field][lane]
+#define CR_SMEM_BYTES (sizeof(float) * CR_WARPS * CR_WARP_FLOATS + sizeof(uint32_t) * CR_WARPS * CR_REC_WORDS)
+#define CR_NOWIN (-0x40000000)             // "no window yet"
+
+// staging layout of one particle (floats):
+//    0.. 3  q * prefix(dSx)   \  rotated by (i1 - 1) & 3: component m belongs to the footprint cell whose x index is
+//    4.. 7  XA = S1 + dS/2     > congruent to m mod 4, so the phase-2 accumulators never move when the window slides
+//    8..11  XB = S1/2 + dS/3  /
+//   12..15  Sy1[0..3]    16..19  dSy[0..3]    20..23  q * prefix(dSy)[0..3]          (read as scalars: lane's row j)
+//   24..27  (Sz1[0], Sz1[2], dSz[0], dSz[2])   28..31  (Sz1[1], Sz1[3], dSz[1], dSz[3])     row pair kp = 0 / 1
+//   32..35  (qPz[0], qPz[2], cell i, row id)   36..39  (qPz[1], qPz[3], cell i, row id)
 
 struct CRArgs {
     Species s;                // source records
     Species d;                // FUSED: destination records (logical order); may alias s when perm == nullptr
-    const int32_t *perm;      // FUSED: logical position t reads physical record perm[t] (lazy sort), or nullptr
-    long long n;
+    const int32_t *perm;      // LAZY: logical position t reads physical record perm[t] (lazy sort)
+    unsigned n;
     const float4 *prim8;
     float *cx, *cy, *cz;     // FUSED: the tiled shadow arrays (see row_index), else curx, cury, curz in Fortran order
     int nty;                  // FUSED: number of 4-row tiles along y
@@ -67,34 +73,39 @@ struct CRArgs {
     float qm, qs;
     uint32_t *key;            // FUSED: sort key of the pushed particle (prt_sort skips its classify pass)
     int32_t *slot, *bincount;
+    unsigned keyoff;          // 1 + mx + mx*my: key = i + mx*(j + my*k) - keyoff for 1-based cell indices
+    int general;              // any open axis or any split axis: the key needs the slow classification
 };
 
-__device__ __forceinline__ void red3(float *cx, float *cy, float *cz, size_t idx, float vx, float vy, float vz)
+// sum over an NW^3 block of node-centred fields, in the reference's order: x innermost (sum()), then *Sy*Sz
+// (particles_movedeposit.F90:801-815); packed fp32 (FFMA2 / FMUL2): the six components sit in three aligned register
+// pairs straight out of the two 128-bit loads; same operations and roundings as the scalar form
+// node-centred fields are re-read by the following steps of the same warp (same or neighbouring cell) while the particle
+// records stream through L1 exactly once; with ~190 KB of the SM's 256 KB configured as shared memory only ~30 KB of L1
+// remain, so the field lines are loaded with the evict_last priority (ncu: L1 sector hit rate 19 % without it)
+__device__ __forceinline__ float4 ldg_keep(const float4 *p)
 {
-    // (a 16-byte red.global.add.v4.f32 into an interleaved array was measured 4 % slower than three scalar REDs)
-    red_nz(cx + idx, vx); red_nz(cy + idx, vy); red_nz(cz + idx, vz);
+    float4 v;
+    asm("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
 }
 
-// sum over an NW^3 block of node-centred fields, in the reference's order: x innermost (sum()), then *Sy*Sz
-// (particles_movedeposit.F90:801-815)
 template <int NW>
 __device__ __forceinline__ void gather_nodes(const float4 *__restrict__ prim8, int nbase, int mx, int my,
                                              const float *wxs, const float *wys, const float *wzs,
                                              float &e0, float &e1, float &e2, float &b0, float &b1, float &b2)
 {
-#if CR_FFMA2
-    // packed fp32 (FFMA2 / FMUL2): the six components sit in three aligned register pairs straight out of the two
-    // 128-bit loads; same operations and roundings as the scalar form below
     float2 e01 = make_float2(e0, e1), e2b0 = make_float2(e2, b0), b12 = make_float2(b1, b2);
 #pragma unroll
     for (int c3 = 0; c3 < NW; c3++) {
 #pragma unroll
         for (int c2 = 0; c2 < NW; c2++) {
             float2 s01 = make_float2(0.f, 0.f), s23 = s01, s45 = s01;
+            // 32-bit node index: the fast path is only taken for grids below 2^30 nodes (cellrun_supported)
             const float4 *row = prim8 + (unsigned)(2 * (nbase + mx * (c2 + my * c3)));
 #pragma unroll
             for (int c1 = 0; c1 < NW; c1++) {
-                const float4 lo = __ldg(row + 2 * c1), hi = __ldg(row + 2 * c1 + 1);
+                const float4 lo = ldg_keep(row + 2 * c1), hi = ldg_keep(row + 2 * c1 + 1);
                 const float2 w2 = make_float2(wxs[c1], wxs[c1]);
                 s01 = __ffma2_rn(make_float2(lo.x, lo.y), w2, s01);
                 s23 = __ffma2_rn(make_float2(lo.z, lo.w), w2, s23);
@@ -107,26 +118,6 @@ __device__ __forceinline__ void gather_nodes(const float4 *__restrict__ prim8, i
         }
     }
     e0 = e01.x; e1 = e01.y; e2 = e2b0.x; b0 = e2b0.y; b1 = b12.x; b2 = b12.y;
-#else
-#pragma unroll
-    for (int c3 = 0; c3 < NW; c3++) {
-#pragma unroll
-        for (int c2 = 0; c2 < NW; c2++) {
-            float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
-            // 32-bit node index: the fast path is only taken for grids below 2^30 nodes (cellrun_supported)
-            const float4 *row = prim8 + (unsigned)(2 * (nbase + mx * (c2 + my * c3)));
-#pragma unroll
-            for (int c1 = 0; c1 < NW; c1++) {
-                float4 lo = __ldg(row + 2 * c1), hi = __ldg(row + 2 * c1 + 1);
-                s0 = s0 + lo.x * wxs[c1]; s1 = s1 + lo.y * wxs[c1]; s2 = s2 + lo.z * wxs[c1];
-                s3 = s3 + lo.w * wxs[c1]; s4 = s4 + hi.x * wxs[c1]; s5 = s5 + hi.y * wxs[c1];
-            }
-            const float wy_ = wys[c2], wz_ = wzs[c3];
-            e0 = e0 + s0 * wy_ * wz_; e1 = e1 + s1 * wy_ * wz_; e2 = e2 + s2 * wy_ * wz_;
-            b0 = b0 + s3 * wy_ * wz_; b1 = b1 + s4 * wy_ * wz_; b2 = b2 + s5 * wy_ * wz_;
-        }
-    }
-#endif
 }
 
 // 3x3x3 path (particle exactly on a node under Q1, or quirks = fixed): kept out of line so that its register
@@ -155,159 +146,192 @@ __device__ __noinline__ void gather27(const float4 *__restrict__ prim8, long lon
     eb[0] = e0; eb[1] = e1; eb[2] = e2; eb[3] = b0; eb[4] = b1; eb[5] = b2;
 }
 
-// 1-D factors of one axis -> shared staging.  MODE 0: x (q*prefix, XA, XB); MODE 1: y/z rows (S1, dS, q*prefix, tag)
-// rotate a 4-vector left... component (s + r) & 3 of the result holds v[s]
+// rotate a 4-vector left: component (s + r) & 3 of the result holds v[s]
 __device__ __forceinline__ float4 rot4(float v0, float v1, float v2, float v3, int r)
 {
-    float a0 = (r & 2) ? v2 : v0, a1 = (r & 2) ? v3 : v1, a2 = (r & 2) ? v0 : v2, a3 = (r & 2) ? v1 : v3;   // by 2
-    return (r & 1) ? make_float4(a3, a0, a1, a2) : make_float4(a0, a1, a2, a3);                          // by 1
+    const bool r2 = (r & 2) != 0, r1 = (r & 1) != 0;
+    const float a0 = r2 ? v2 : v0, a1 = r2 ? v3 : v1, a2 = r2 ? v0 : v2, a3 = r2 ? v1 : v3;           // by 2
+    return r1 ? make_float4(a3, a0, a1, a2) : make_float4(a0, a1, a2, a3);                            // by 1
 }
 
-// MODE 0: x factors (q*prefix, XA, XB), stored ROTATED by r = (i1 - 1) & 3: component m belongs to the footprint cell
-// whose x index is congruent to m mod 4, so the phase-2 accumulators never have to move when the window slides.
-// MODE 1: y/z rows (S1, dS, q*prefix, tag).
-template <int MODE>
-__device__ __forceinline__ void stage_axis(float *st, const float S1[4], const float S2[4], float q, float tag, int r)
+// 1-D factors of the three axes -> shared staging (layout above)
+__device__ __forceinline__ void stage_x(float *st, const float S1[4], const float S2[4], float q, int r)
 {
     const float third = 1.f / 3.f;
     const float d0 = S2[0] - S1[0], d1 = S2[1] - S1[1], d2 = S2[2] - S1[2], d3 = S2[3] - S1[3];
     const float p0 = d0, p1 = p0 + d1, p2 = p1 + d2, p3 = p2 + d3;
-    if (MODE == 0) {
-        *(float4 *)(st + 0) = rot4(q * p0, q * p1, q * p2, q * p3, r);
-        *(float4 *)(st + 4) = rot4(S1[0] + 0.5f * d0, S1[1] + 0.5f * d1, S1[2] + 0.5f * d2, S1[3] + 0.5f * d3, r);
-        *(float4 *)(st + 8) = rot4(0.5f * S1[0] + third * d0, 0.5f * S1[1] + third * d1,
-                                   0.5f * S1[2] + third * d2, 0.5f * S1[3] + third * d3, r);
-    } else {
-        *(float4 *)(st + 0) = make_float4(S1[0], d0, q * p0, tag);
-        *(float4 *)(st + 4) = make_float4(S1[1], d1, q * p1, tag);
-        *(float4 *)(st + 8) = make_float4(S1[2], d2, q * p2, tag);
-        *(float4 *)(st + 12) = make_float4(S1[3], d3, q * p3, tag);
-    }
+    *(float4 *)(st + 0) = rot4(q * p0, q * p1, q * p2, q * p3, r);
+    *(float4 *)(st + 4) = rot4(fmaf(0.5f, d0, S1[0]), fmaf(0.5f, d1, S1[1]), fmaf(0.5f, d2, S1[2]), fmaf(0.5f, d3, S1[3]), r);
+    *(float4 *)(st + 8) = rot4(fmaf(third, d0, 0.5f * S1[0]), fmaf(third, d1, 0.5f * S1[1]),
+                               fmaf(third, d2, 0.5f * S1[2]), fmaf(third, d3, 0.5f * S1[3]), r);
+}
+__device__ __forceinline__ void stage_y(float *st, const float S1[4], const float S2[4], float q)
+{
+    const float d0 = S2[0] - S1[0], d1 = S2[1] - S1[1], d2 = S2[2] - S1[2], d3 = S2[3] - S1[3];
+    const float p0 = d0, p1 = p0 + d1, p2 = p1 + d2, p3 = p2 + d3;
+    *(float4 *)(st + 12) = make_float4(S1[0], S1[1], S1[2], S1[3]);
+    *(float4 *)(st + 16) = make_float4(d0, d1, d2, d3);
+    *(float4 *)(st + 20) = make_float4(q * p0, q * p1, q * p2, q * p3);
+}
+__device__ __forceinline__ void stage_z(float *st, const float S1[4], const float S2[4], float q, int ci, int crow)
+{
+    const float d0 = S2[0] - S1[0], d1 = S2[1] - S1[1], d2 = S2[2] - S1[2], d3 = S2[3] - S1[3];
+    const float p0 = d0, p1 = p0 + d1, p2 = p1 + d2, p3 = p2 + d3;
+    const float fi = __int_as_float(ci), fr = __int_as_float(crow);
+    *(float4 *)(st + 24) = make_float4(S1[0], S1[2], d0, d2);
+    *(float4 *)(st + 28) = make_float4(S1[1], S1[3], d1, d3);
+    *(float4 *)(st + 32) = make_float4(q * p0, q * p2, fi, fr);
+    *(float4 *)(st + 36) = make_float4(q * p1, q * p3, fi, fr);
 }
 
-// flush the accumulators of the first `nplanes` x-planes of the window whose first cell is wi-1 (plane t lives in
-// physical register (wi - 1 + t) & 3) and clear them
-template <int PS>
-__device__ __forceinline__ void flush_planes(float *cx, float *cy, float *cz, size_t idx0, int wi, int nplanes,
-                                             float (&ax)[4], float (&ay)[4], float (&az)[4])
+// periodic wrap / shift into the destination's frame (deposit_particles loop B, particles_movedeposit.F90:1553-1633),
+// branch-free; lo / hi tell which side was crossed
+__device__ __forceinline__ float wrap1(float x, float lo_edge, float hi_edge, float shift_lo, float shift_hi, bool &lo, bool &hi)
 {
-#pragma unroll
-    for (int m = 0; m < 4; m++) {
-        const int t = (m - (wi - 1)) & 3;                    // plane held by register m
-        if (t < nplanes) { red3(cx, cy, cz, idx0 + (size_t)(t * PS), ax[m], ay[m], az[m]); ax[m] = 0.f; ay[m] = 0.f; az[m] = 0.f; }
-    }
-}
-
-// the common case in sorted order: the window slides one cell along x, plane 0 (register (wi-1)&3) is complete.
-// The ring register is uniform across the half-warp, so a 4-way switch costs one short divergent body instead of
-// select chains over all twelve accumulators.
-__device__ __forceinline__ void flush_one(float *cx, float *cy, float *cz, size_t idx0, int wi, float (&ax)[4], float (&ay)[4], float (&az)[4])
-{
-    float *px = cx + idx0, *py = cy + idx0, *pz = cz + idx0;
-    switch ((wi - 1) & 3) {
-    case 0: red_nz(px, ax[0]); red_nz(py, ay[0]); red_nz(pz, az[0]); ax[0] = 0.f; ay[0] = 0.f; az[0] = 0.f; break;
-    case 1: red_nz(px, ax[1]); red_nz(py, ay[1]); red_nz(pz, az[1]); ax[1] = 0.f; ay[1] = 0.f; az[1] = 0.f; break;
-    case 2: red_nz(px, ax[2]); red_nz(py, ay[2]); red_nz(pz, az[2]); ax[2] = 0.f; ay[2] = 0.f; az[2] = 0.f; break;
-    default: red_nz(px, ax[3]); red_nz(py, ay[3]); red_nz(pz, az[3]); ax[3] = 0.f; ay[3] = 0.f; az[3] = 0.f; break;
-    }
+    lo = x < lo_edge; hi = x > hi_edge;
+    return x + (lo ? shift_lo : hi ? -shift_hi : 0.f);
 }
 
 // same classification as k_classify_key (particles.cu), on a copy of the position
-__device__ __forceinline__ uint32_t sort_key(const DevGeom &G, float x, float y, float z)
+__device__ __forceinline__ uint32_t sort_key(const DevGeom &G, unsigned keyoff, int general, float x, float y, float z)
 {
-    int dx = 0, dy = 0, dz = 0;
-    if (x < G.minx) dx = -1; else if (x > G.maxx) dx = 1;
-    if (y < G.miny) dy = -1; else if (y > G.maxy) dy = 1;
-    if (z < G.minz) dz = -1; else if (z > G.maxz) dz = 1;
-    bool in = true;
-    if (!G.perx) in = (x + G.mxcum > G.x1in) && (x + G.mxcum < G.x2in);
-    if (!G.pery && in) in = (y + G.mycum > G.y1in) && (y + G.mycum < G.y2in);
-    if (!G.perz && in) in = (z + G.mzcum > G.z1in) && (z + G.mzcum < G.z2in);
-    if (!in) return (uint32_t)G.lot + 9u;
-    if (dx < 0) x = x + G.shiftx_lo; else if (dx > 0) x = x - G.shiftx_hi;
-    if (dy < 0) y = y + G.shifty_lo; else if (dy > 0) y = y - G.shifty_hi;
-    if (dz < 0) z = z + G.shiftz_lo; else if (dz > 0) z = z - G.shiftz_hi;
-    const int da = G.sendy ? dy : 0, db = G.sendz ? dz : 0;
-    const int code = (da + 1) + 3 * (db + 1);
-    if (code != 4) return (uint32_t)G.lot + (uint32_t)code;
-    int i = min(max((int)x, 1), G.mx), j = min(max((int)y, 1), G.my), k = min(max((int)z, 1), G.mz);
-    return (uint32_t)((i - 1) + G.mx * ((j - 1) + G.my * (k - 1)));
+    bool lx, hx, ly, hy, lz, hz;
+    const float xs = wrap1(x, G.minx, G.maxx, G.shiftx_lo, G.shiftx_hi, lx, hx);
+    const float ys = wrap1(y, G.miny, G.maxy, G.shifty_lo, G.shifty_hi, ly, hy);
+    const float zs = wrap1(z, G.minz, G.maxz, G.shiftz_lo, G.shiftz_hi, lz, hz);
+    // (a NaN position converts to 0 and the unsigned min below keeps the key inside the table)
+    uint32_t key = (uint32_t)((int)xs + G.mx * ((int)ys + G.my * (int)zs)) - keyoff;
+    key = min(key, (uint32_t)G.lot - 1u);
+    if (general) {                                           // kernel-uniform: open or split axes
+        bool in = true;
+        if (!G.perx) in = (x + G.mxcum > G.x1in) && (x + G.mxcum < G.x2in);
+        if (!G.pery && in) in = (y + G.mycum > G.y1in) && (y + G.mycum < G.y2in);
+        if (!G.perz && in) in = (z + G.mzcum > G.z1in) && (z + G.mzcum < G.z2in);
+        const int dy = (int)hy - (int)ly, dz = (int)hz - (int)lz;
+        const int code = ((G.sendy ? dy : 0) + 1) + 3 * ((G.sendz ? dz : 0) + 1);
+        if (code != 4) key = (uint32_t)G.lot + (uint32_t)code;
+        if (!in) key = (uint32_t)G.lot + 9u;
+    }
+    return key;
 }
 
-template <int ORDER, bool FUSED>
-__global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
+template <int ORDER, bool FUSED, bool LAZY>
+__global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(const CRArgs A)
 {
     // dynamic shared memory (CR_SMEM_BYTES > 48 KB): the factor staging of phase 1 -> phase 2, then the record pipeline
     extern __shared__ __align__(16) unsigned char cr_smem[];
-    float *stage = reinterpret_cast<float *>(cr_smem);
-    uint32_t (*rec)[2][9][32] = reinterpret_cast<uint32_t (*)[2][9][32]>(cr_smem + sizeof(float) * CR_WARPS * CR_WARP_FLOATS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int half = lane >> 4, hl = lane & 15;
-    const long long gw = (long long)blockIdx.x * CR_WARPS + warp;
-    const long long base = gw * (2 * CR_CHUNK) + (long long)half * CR_CHUNK;
-    if (gw * (2 * CR_CHUNK) >= A.n) return;                  // whole warp idle (no block-level barriers are used)
+    const int qtr = lane >> 3, ql = lane & 7;
+    const unsigned n = A.n;
+    const unsigned wbase = (blockIdx.x * CR_WARPS + warp) * (4u * CR_CHUNK);
+    if (wbase >= n) return;                                  // whole warp idle (no block-level barriers are used)
+    const unsigned base = wbase + qtr * CR_CHUNK;
     const DevGeom &G = A.G;
     const int mx = G.mx, my = G.my;
-    const int j = lane & 3, k = (lane >> 2) & 3;
+    const int j = ql & 3, kp = ql >> 2;                      // this lane's footprint rows: (j, kp) and (j, kp + 2)
     constexpr bool TILED = FUSED && TGPU_SHADOW_TILED;
-    constexpr int PS = TILED ? 16 : 1;                       // distance between consecutive x-planes of a row
+    constexpr unsigned PS = TILED ? 16 : 1;                  // distance between consecutive x-planes of a row
 
-    int wi = 0, wrow = 0;                                    // window cell (1-based i, row id)
-    bool have = false;
-    float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f}, az[4] = {0.f, 0.f, 0.f, 0.f};
+    float *const sq = reinterpret_cast<float *>(cr_smem) + warp * CR_WARP_FLOATS + qtr * CR_QFLOATS;   // quarter's staging
+    float *const st = sq + ql * CR_STRIDE;                   // phase 1: this lane's particle
+    const float *const syl = sq + 12 + j;                    // phase 2: row j of the y block
+    const float4 *const szl = reinterpret_cast<const float4 *>(sq + 24 + 4 * kp);   // phase 2: row pair kp of the z block
+    uint32_t *const rec = reinterpret_cast<uint32_t *>(cr_smem + sizeof(float) * CR_WARPS * CR_WARP_FLOATS) + warp * CR_REC_WORDS + lane;
+
+    // window: cell wi (1-based), row id wrow = (j0 - 1) | (k0 - 1) << 16, element offsets of the lane's two rows at plane wi - 1
+    int wi = CR_NOWIN, wrow = -1;
+    unsigned woffA = 0, woffB = 0;
+    float2 axA01 = make_float2(0.f, 0.f), axA23 = axA01, ayA01 = axA01, ayA23 = axA01, azA01 = axA01, azA23 = axA01;
+    float2 axB01 = axA01, axB23 = axA01, ayB01 = axA01, ayB23 = axA01, azB01 = axA01, azB23 = axA01;
+
+    // flush the lowest plane of the window (cell wi - 1, ring register (wi - 1) & 3), clear it and slide the window by one
+    // cell.  The ring register is uniform across the quarter, so the 4-way switch costs one short divergent body.
+    // (order 1 leaves half of the 4-wide window exactly zero: skip those; order 2 fills it, the test would only cost issue slots)
+    auto red = [&](float *p, float v) { if (ORDER == 1) red_nz(p, v); else red_add(p, v); };
+    auto flush_slide = [&]() {
+        float *pxA = A.cx + woffA, *pyA = A.cy + woffA, *pzA = A.cz + woffA;
+        float *pxB = A.cx + woffB, *pyB = A.cy + woffB, *pzB = A.cz + woffB;
+        switch ((wi - 1) & 3) {
+        case 0: red(pxA, axA01.x); red(pyA, ayA01.x); red(pzA, azA01.x); red(pxB, axB01.x); red(pyB, ayB01.x); red(pzB, azB01.x);
+                axA01.x = ayA01.x = azA01.x = axB01.x = ayB01.x = azB01.x = 0.f; break;
+        case 1: red(pxA, axA01.y); red(pyA, ayA01.y); red(pzA, azA01.y); red(pxB, axB01.y); red(pyB, ayB01.y); red(pzB, azB01.y);
+                axA01.y = ayA01.y = azA01.y = axB01.y = ayB01.y = azB01.y = 0.f; break;
+        case 2: red(pxA, axA23.x); red(pyA, ayA23.x); red(pzA, azA23.x); red(pxB, axB23.x); red(pyB, ayB23.x); red(pzB, azB23.x);
+                axA23.x = ayA23.x = azA23.x = axB23.x = ayB23.x = azB23.x = 0.f; break;
+        default: red(pxA, axA23.y); red(pyA, ayA23.y); red(pzA, azA23.y); red(pxB, axB23.y); red(pyB, ayB23.y); red(pzB, azB23.y);
+                axA23.y = ayA23.y = azA23.y = axB23.y = ayB23.y = azB23.y = 0.f; break;
+        }
+        wi += 1; woffA += PS; woffB += PS;
+    };
+    // the particle that opens a run sits in cell ni of row nrow: bring the window there
+    auto move_window = [&](int ni, int nrow) {
+        const int di = ni - wi;
+        const bool slide = nrow == wrow && (unsigned)di < 4u;     // 0: a run continued from the last step; 1: the common case
+        // sliding 1..3 cells along x completes that many planes; anything else flushes the whole window (one inlined copy of
+        // the flush: the code of this kernel has to stay inside the instruction cache)
+        const int ns = slide ? di : (wi != CR_NOWIN ? 4 : 0);
+#pragma unroll 1
+        for (int s = 0; s < ns; s++) flush_slide();
+        if (!slide) {
+            wi = ni; wrow = nrow;
+            const int J = (nrow & 0xFFFF) + j - 1, K = (nrow >> 16) + kp - 1;
+            woffA = (unsigned)row_index<TILED>(mx, my, A.nty, J, K, ni - 2);
+            woffB = (unsigned)row_index<TILED>(mx, my, A.nty, J, K + 2, ni - 2);
+        }
+    };
 
     // ---- record pipeline: rec[buf][field][lane], fields x y z u v w ch ind tag; each lane only ever touches its own slots
-    const bool lazy = FUSED && A.perm != nullptr;
-    constexpr int NIT = CR_CHUNK / 16;
-    auto fetch = [&](int buf, long long tt, int pp32) {
-        if (tt < A.n) {
-            const long long pp = lazy ? (long long)pp32 : tt;
-            uint32_t *r = &rec[warp][buf][0][lane];
+    constexpr int NIT = CR_CHUNK / 8;
+    auto fetch = [&](int buf, unsigned tt, int pp32) {
+        if (tt < n) {
+            const unsigned pp = LAZY ? (unsigned)pp32 : tt;
+            uint32_t *r = rec + buf * (9 * 32);
             cp_async4(r + 0 * 32, A.s.x + pp); cp_async4(r + 1 * 32, A.s.y + pp); cp_async4(r + 2 * 32, A.s.z + pp);
             cp_async4(r + 3 * 32, A.s.u + pp); cp_async4(r + 4 * 32, A.s.v + pp); cp_async4(r + 5 * 32, A.s.w + pp);
             cp_async4(r + 6 * 32, A.s.ch + pp);
-            if (lazy) { cp_async4(r + 7 * 32, A.s.ind + pp); cp_async4(r + 8 * 32, A.s.tag + pp); }
+            if (LAZY) { cp_async4(r + 7 * 32, A.s.ind + pp); cp_async4(r + 8 * 32, A.s.tag + pp); }
         }
         cp_async_commit();
     };
     {
-        const long long t0 = base + hl;
-        fetch(0, t0, (lazy && t0 < A.n) ? A.perm[t0] : 0);
+        const unsigned t0 = base + ql;
+        fetch(0, t0, (LAZY && t0 < n) ? __ldcs(A.perm + t0) : 0);
     }
     // permutation entry of this lane's particle of the next step: loaded one step ahead and kept as the raw 32-bit
     // value (no instruction touches it until the following step, so the load never stalls the warp)
     int pnext = 0;
-    if (lazy && base + 16 + hl < A.n) pnext = A.perm[base + 16 + hl];
+    if (LAZY && base + 8 + ql < n) pnext = __ldcs(A.perm + base + 8 + ql);
 
+#pragma unroll 1
     for (int it = 0; it < NIT; ++it) {
-        const long long t = base + it * 16 + hl;
-        float *st = stage + warp * CR_WARP_FLOATS + half * CR_HALF_FLOATS + hl * CR_STRIDE;
+        const unsigned t = base + it * 8 + ql;
         int ci = -1, crow = -1;                              // deposit base cell of this lane's particle
         cp_async_wait_all();                                 // this step's record has landed in rec[it & 1]
         if (it + 1 < NIT) {
-            fetch((it + 1) & 1, t + 16, pnext);              // next step's record, in flight during this step
-            if (lazy && it + 2 < NIT && t + 32 < A.n) pnext = A.perm[t + 32];
+            fetch((it + 1) & 1, t + 8, pnext);               // next step's record, in flight during this step
+            if (LAZY && it + 2 < NIT && t + 16 < n) pnext = __ldcs(A.perm + t + 16);
         }
         // ------------------------------------------------------------------ phase 1: lane = particle
-        if (t < A.n) {
-            const uint32_t *r = &rec[warp][it & 1][0][lane];
+        if (t < n) {
+            const uint32_t *r = rec + (it & 1) * (9 * 32);
             float x = __uint_as_float(r[0 * 32]), y = __uint_as_float(r[1 * 32]), z = __uint_as_float(r[2 * 32]);
             float u = __uint_as_float(r[3 * 32]), v = __uint_as_float(r[4 * 32]), w = __uint_as_float(r[5 * 32]);
             const float ch = __uint_as_float(r[6 * 32]);
-            if (lazy) {
+            if (LAZY) {
                 // lazily sorted input: the record still carries last lap's unwrapped position; apply the periodic wrap /
                 // frame shift its sort key was computed with (deposit_particles loop B), and carry the passive fields along
-                if (x < A.G.minx) x += A.G.shiftx_lo; else if (x > A.G.maxx) x -= A.G.shiftx_hi;
-                if (y < A.G.miny) y += A.G.shifty_lo; else if (y > A.G.maxy) y -= A.G.shifty_hi;
-                if (z < A.G.minz) z += A.G.shiftz_lo; else if (z > A.G.maxz) z -= A.G.shiftz_hi;
+                bool lo, hi;
+                x = wrap1(x, G.minx, G.maxx, G.shiftx_lo, G.shiftx_hi, lo, hi);
+                y = wrap1(y, G.miny, G.maxy, G.shifty_lo, G.shifty_hi, lo, hi);
+                z = wrap1(z, G.minz, G.maxz, G.shiftz_lo, G.shiftz_hi, lo, hi);
                 A.d.ch[t] = ch; A.d.ind[t] = (int32_t)r[7 * 32]; A.d.tag[t] = (int32_t)r[8 * 32];
             }
             const float q = ch * A.qs;
             float S1[4], S2[4];
             if (FUSED) {
                 const float half_ = 0.5f;
-                const int ip = (int)x, jp = (int)y, kp = (int)z;
-                const float dxp = x - ip, dyp = y - jp, dzp = z - kp;
+                const int ip = (int)x, jp = (int)y, kq = (int)z;
+                const float dxp = x - ip, dyp = y - jp, dzp = z - kq;
                 float Wx[4], Wy[4], Wz[4];
                 shape_window<ORDER>(dxp, 0, Wx); shape_window<ORDER>(dyp, 0, Wy); shape_window<ORDER>(dzp, 0, Wz);
                 float e0 = 0, e1 = 0, e2 = 0, b0 = 0, b1 = 0, b2 = 0;
@@ -318,7 +342,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
                 const bool fast = ORDER == 1 || (q1 && dxp != 0.f && dyp != 0.f && dzp != 0.f);
                 if (fast) {
                     const float wxs[2] = {Wx[1], Wx[2]}, wys[2] = {Wy[1], Wy[2]}, wzs[2] = {Wz[1], Wz[2]};
-                    const int nbase = (ip - 1) + mx * ((jp - 1) + my * (kp - 1));
+                    const int nbase = (ip - 1) + mx * ((jp - 1) + my * (kq - 1));
                     gather_nodes<2>(A.prim8, nbase, mx, my, wxs, wys, wzs, e0, e1, e2, b0, b1, b2);
                 } else if (ORDER == 2) {
                     int lox, loy, loz;
@@ -331,7 +355,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
                     for (int a = 0; a < 3; a++) {
                         w9[a] = lox ? Wx[a + 1] : Wx[a]; w9[3 + a] = loy ? Wy[a + 1] : Wy[a]; w9[6 + a] = loz ? Wz[a + 1] : Wz[a];
                     }
-                    const long long nbase = (ip - 2 + lox) + (long long)mx * ((jp - 2 + loy) + (long long)my * (kp - 2 + loz));
+                    const long long nbase = (ip - 2 + lox) + (long long)mx * ((jp - 2 + loy) + (long long)my * (kq - 2 + loz));
                     gather27(A.prim8, nbase, mx, my, w9, eb);
                     e0 = eb[0]; e1 = eb[1]; e2 = eb[2]; b0 = eb[3]; b1 = eb[4]; b2 = eb[5];
                 }
@@ -344,20 +368,21 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
                 }
                 push_particle<true>(G.c, G.pusher, e0, e1, e2, b0, b1, b2, x, y, z, u, v, w, cinv);
                 A.d.x[t] = x; A.d.y[t] = y; A.d.z[t] = z; A.d.u[t] = u; A.d.v[t] = v; A.d.w[t] = w;
-                // The deposit's "old" shape is the gather's shape at the true pre-push position (the reference
-                // recomputes it as x - u/gamma*c, particles_movedeposit.F90:1384-1388, equal to round-off).
                 // sort key of the pushed particle + its rank inside the destination bin; the rank comes back from L2 while
                 // the deposit factors are being staged and is stored at the end of the phase
-                const uint32_t ky = sort_key(G, x, y, z);
+                const uint32_t ky = sort_key(G, A.keyoff, A.general, x, y, z);
                 A.key[t] = ky;
                 const int rank_in_bin = atomicAdd(&A.bincount[ky], 1);
-                crow = (jp - 1) | ((kp - 1) << 16); ci = ip;
-                shape_window<ORDER>(x - (int)x, (int)x - ip, S2);
-                stage_axis<0>(st, Wx, S2, q, 0.f, (ip - 1) & 3);
-                shape_window<ORDER>(y - (int)y, (int)y - jp, S2);
-                stage_axis<1>(st + 12, Wy, S2, q, __int_as_float(ci), 0);
-                shape_window<ORDER>(z - (int)z, (int)z - kp, S2);
-                stage_axis<1>(st + 28, Wz, S2, q, __int_as_float(crow), 0);
+                // The deposit's "old" shape is the gather's shape at the true pre-push position (the reference
+                // recomputes it as x - u/gamma*c, particles_movedeposit.F90:1384-1388, equal to round-off).
+                crow = (jp - 1) | ((kq - 1) << 16); ci = ip;
+                const int in_ = (int)x, jn = (int)y, kn = (int)z;
+                shape_window<ORDER>(x - in_, in_ - ip, S2);
+                stage_x(st, Wx, S2, q, (ip - 1) & 3);
+                shape_window<ORDER>(y - jn, jn - jp, S2);
+                stage_y(st, Wy, S2, q);
+                shape_window<ORDER>(z - kn, kn - kq, S2);
+                stage_z(st, Wz, S2, q, ci, crow);
                 A.slot[t] = rank_in_bin;
             } else {
                 // deposit_particles loop A: old position recomputed from the new one (particles_movedeposit.F90:1384-1390)
@@ -366,88 +391,103 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(CRArgs A)
                 const int i1 = (int)x1, j1 = (int)y1, k1 = (int)z1;
                 crow = (j1 - 1) | ((k1 - 1) << 16); ci = i1;
                 shape_window<ORDER>(x1 - i1, 0, S1); shape_window<ORDER>(x - (int)x, (int)x - i1, S2);
-                stage_axis<0>(st, S1, S2, q, 0.f, (i1 - 1) & 3);
+                stage_x(st, S1, S2, q, (i1 - 1) & 3);
                 shape_window<ORDER>(y1 - j1, 0, S1); shape_window<ORDER>(y - (int)y, (int)y - j1, S2);
-                stage_axis<1>(st + 12, S1, S2, q, __int_as_float(ci), 0);
+                stage_y(st, S1, S2, q);
                 shape_window<ORDER>(z1 - k1, 0, S1); shape_window<ORDER>(z - (int)z, (int)z - k1, S2);
-                stage_axis<1>(st + 28, S1, S2, q, __int_as_float(crow), 0);
+                stage_z(st, S1, S2, q, ci, crow);
             }
         }
         else {
-            // past the end (last warp only): stage zeros so that phase 2 can always walk all 16 slots of the half
+            // past the end (last warp only): stage zeros so that phase 2 can always walk all 8 slots of the quarter
 #pragma unroll
-            for (int q4 = 0; q4 < CR_STRIDE / 4; q4++) *(float4 *)(st + 4 * q4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q4 = 0; q4 < 10; q4++) *(float4 *)(st + 4 * q4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        // run starts inside each half: a particle whose cell differs from its predecessor's
+        // run starts inside each quarter: a particle whose cell differs from its predecessor's
         const int pci = __shfl_up_sync(0xffffffffu, ci, 1), pcrow = __shfl_up_sync(0xffffffffu, crow, 1);
-        const bool start = t < A.n && (hl == 0 || ci != pci || crow != pcrow);
-        unsigned starts = (__ballot_sync(0xffffffffu, start) >> (half << 4)) & 0xFFFFu;
-        __syncwarp();                                        // staging written by all lanes is visible to the warp
-        // ------------------------------------------------------------------ phase 2: half-warp = footprint
-        // Both halves walk their 16 particles in lockstep; only the (rare) window moves diverge.
-        const float4 *sp = (const float4 *)(stage + warp * CR_WARP_FLOATS + half * CR_HALF_FLOATS);
-CR_DO_PRAGMA(unroll CR_UNROLL)
-        for (int tt = 0; tt < 16; ++tt, sp += CR_STRIDE / 4) {
-            if ((starts >> tt) & 1u) {
-                // particle tt opens a run of particles that share one footprint
-                const int ni = __float_as_int(sp[3].w), nrow = __float_as_int(sp[7].w);
-                if (!have || ni != wi || nrow != wrow) {
-                    if (have) {
-                        const size_t idx0 = row_index<TILED>(mx, my, A.nty, (wrow & 0xFFFF) + j - 1, (wrow >> 16) + k - 1, wi - 2);
-                        const int di = ni - wi;
-                        // sliding 1..3 cells along x completes that many planes; anything else flushes the window
-                        // sliding 1..3 cells along x completes that many planes; anything else flushes the window
-                        if (nrow == wrow && di == 1) flush_one(A.cx, A.cy, A.cz, idx0, wi, ax, ay, az);
-                        else flush_planes<PS>(A.cx, A.cy, A.cz, idx0, wi, (nrow == wrow && di > 1 && di < 4) ? di : 4, ax, ay, az);
-                    }
-                    wi = ni; wrow = nrow; have = true;
-                }
+        const bool start = t < n && (ql == 0 || ci != pci || crow != pcrow);
+        const unsigned sb = __ballot_sync(0xffffffffu, start);         // staging written by all lanes is visible after this
+        const unsigned any = (sb | (sb >> 8) | (sb >> 16) | (sb >> 24)) & 0xFFu;    // warp-uniform: some quarter starts a run at tt
+        const unsigned mine = (sb >> (qtr << 3)) & 0xFFu;
+        __syncwarp();
+        // ------------------------------------------------------------------ phase 2: quarter-warp = footprint
+        // The four quarters walk their 8 particles in lockstep; only the window moves diverge.
+#pragma unroll 2
+        for (int tt = 0; tt < 8; ++tt) {
+            const float4 v1 = szl[tt * (CR_STRIDE / 4) + 2];             // (qPz[kp], qPz[kp + 2], cell i, row id)
+            if (any & (1u << tt)) {
+                if (mine & (1u << tt)) move_window(__float_as_int(v1.z), __float_as_int(v1.w));
             }
-            const float4 yv = sp[3 + j], zv = sp[7 + k];
-            const float4 qpsx = sp[0], xa = sp[1], xb = sp[2];
-            const float sy1 = yv.x, dsy = yv.y, qpsy = yv.z;
-            const float sz1 = zv.x, dsz = zv.y, qpsz = zv.z;
+            const float4 *sx = reinterpret_cast<const float4 *>(sq + tt * CR_STRIDE);
+            const float4 qpx = sx[0], xa = sx[1], xb = sx[2];
+            const float sy1 = syl[tt * CR_STRIDE], dsy = syl[tt * CR_STRIDE + 4], qpy = syl[tt * CR_STRIDE + 8];
+            const float4 v0 = szl[tt * (CR_STRIDE / 4)];                 // (Sz1[kp], Sz1[kp + 2], dSz[kp], dSz[kp + 2])
             const float ya = fmaf(0.5f, dsy, sy1), yb = fmaf(1.f / 3.f, dsy, 0.5f * sy1);
-            const float wx = fmaf(yb, dsz, ya * sz1);      // Wx(j,k)
-            const float a = qpsy * sz1, b = qpsy * dsz;    // Jy = XA*a + XB*b
-            const float c = qpsz * sy1, d = qpsz * dsy;    // Jz = XA*c + XB*d
-#if CR_FFMA2
-            // sm_100 packed fp32 (FFMA2, fma.rn.f32x2): the x-ring registers pair up as (0,1) and (2,3), the per-lane
-            // factors are broadcast into both halves of a 64-bit register; 10 issue slots instead of 20
+            // packed over the lane's two rows (.x = row kp, .y = row kp + 2); FFMA2 / FMUL2 take the per-lane scalar as a
+            // broadcast operand
+            const float2 sz1 = make_float2(v0.x, v0.y), dsz = make_float2(v0.z, v0.w), qpz = make_float2(v1.x, v1.y);
+            const float2 wx = __ffma2_rn(dsz, make_float2(yb, yb), __fmul2_rn(sz1, make_float2(ya, ya)));   // Wx(j,k)
+            const float2 ja = __fmul2_rn(sz1, make_float2(qpy, qpy)), jb = __fmul2_rn(dsz, make_float2(qpy, qpy));   // Jy = XA*ja + XB*jb
+            const float2 jc = __fmul2_rn(qpz, make_float2(sy1, sy1)), jd = __fmul2_rn(qpz, make_float2(dsy, dsy));   // Jz = XA*jc + XB*jd
+            const float2 px01 = make_float2(qpx.x, qpx.y), px23 = make_float2(qpx.z, qpx.w);
+            const float2 xa01 = make_float2(xa.x, xa.y), xa23 = make_float2(xa.z, xa.w);
+            const float2 xb01 = make_float2(xb.x, xb.y), xb23 = make_float2(xb.z, xb.w);
             {
-                const float2 wx2 = make_float2(wx, wx), a2 = make_float2(a, a), b2 = make_float2(b, b),
-                             c2 = make_float2(c, c), d2 = make_float2(d, d);
-                const float2 px01 = make_float2(qpsx.x, qpsx.y), px23 = make_float2(qpsx.z, qpsx.w);
-                const float2 xa01 = make_float2(xa.x, xa.y), xa23 = make_float2(xa.z, xa.w);
-                const float2 xb01 = make_float2(xb.x, xb.y), xb23 = make_float2(xb.z, xb.w);
-                float2 t;
-                t = __ffma2_rn(px01, wx2, make_float2(ax[0], ax[1])); ax[0] = t.x; ax[1] = t.y;
-                t = __ffma2_rn(px23, wx2, make_float2(ax[2], ax[3])); ax[2] = t.x; ax[3] = t.y;
-                t = __ffma2_rn(xa01, a2, __ffma2_rn(xb01, b2, make_float2(ay[0], ay[1]))); ay[0] = t.x; ay[1] = t.y;
-                t = __ffma2_rn(xa23, a2, __ffma2_rn(xb23, b2, make_float2(ay[2], ay[3]))); ay[2] = t.x; ay[3] = t.y;
-                t = __ffma2_rn(xa01, c2, __ffma2_rn(xb01, d2, make_float2(az[0], az[1]))); az[0] = t.x; az[1] = t.y;
-                t = __ffma2_rn(xa23, c2, __ffma2_rn(xb23, d2, make_float2(az[2], az[3]))); az[2] = t.x; az[3] = t.y;
+                const float2 s = make_float2(wx.x, wx.x), a2 = make_float2(ja.x, ja.x), b2 = make_float2(jb.x, jb.x),
+                             c2 = make_float2(jc.x, jc.x), d2 = make_float2(jd.x, jd.x);
+                axA01 = __ffma2_rn(px01, s, axA01); axA23 = __ffma2_rn(px23, s, axA23);
+                ayA01 = __ffma2_rn(xa01, a2, __ffma2_rn(xb01, b2, ayA01)); ayA23 = __ffma2_rn(xa23, a2, __ffma2_rn(xb23, b2, ayA23));
+                azA01 = __ffma2_rn(xa01, c2, __ffma2_rn(xb01, d2, azA01)); azA23 = __ffma2_rn(xa23, c2, __ffma2_rn(xb23, d2, azA23));
             }
-#else
-            ax[0] = fmaf(qpsx.x, wx, ax[0]); ax[1] = fmaf(qpsx.y, wx, ax[1]);
-            ax[2] = fmaf(qpsx.z, wx, ax[2]); ax[3] = fmaf(qpsx.w, wx, ax[3]);
-            ay[0] = fmaf(xa.x, a, fmaf(xb.x, b, ay[0])); ay[1] = fmaf(xa.y, a, fmaf(xb.y, b, ay[1]));
-            ay[2] = fmaf(xa.z, a, fmaf(xb.z, b, ay[2])); ay[3] = fmaf(xa.w, a, fmaf(xb.w, b, ay[3]));
-            az[0] = fmaf(xa.x, c, fmaf(xb.x, d, az[0])); az[1] = fmaf(xa.y, c, fmaf(xb.y, d, az[1]));
-            az[2] = fmaf(xa.z, c, fmaf(xb.z, d, az[2])); az[3] = fmaf(xa.w, c, fmaf(xb.w, d, az[3]));
-#endif
+            {
+                const float2 s = make_float2(wx.y, wx.y), a2 = make_float2(ja.y, ja.y), b2 = make_float2(jb.y, jb.y),
+                             c2 = make_float2(jc.y, jc.y), d2 = make_float2(jd.y, jd.y);
+                axB01 = __ffma2_rn(px01, s, axB01); axB23 = __ffma2_rn(px23, s, axB23);
+                ayB01 = __ffma2_rn(xa01, a2, __ffma2_rn(xb01, b2, ayB01)); ayB23 = __ffma2_rn(xa23, a2, __ffma2_rn(xb23, b2, ayB23));
+                azB01 = __ffma2_rn(xa01, c2, __ffma2_rn(xb01, d2, azB01)); azB23 = __ffma2_rn(xa23, c2, __ffma2_rn(xb23, d2, azB23));
+            }
         }
         __syncwarp();
     }
-    if (have) {
-        const size_t idx0 = row_index<TILED>(mx, my, A.nty, (wrow & 0xFFFF) + j - 1, (wrow >> 16) + k - 1, wi - 2);
-        flush_planes<PS>(A.cx, A.cy, A.cz, idx0, wi, 4, ax, ay, az);
+    if (wi != CR_NOWIN) {
+#pragma unroll 1
+        for (int s = 0; s < 4; s++) flush_slide();
     }
 }
 
 int cellrun_supported(const tgpu_ctx *h)
 {
     return h->P.dim == 3 && (h->P.order == 1 || h->P.order == 2) && h->G.lot < (1ll << 30) && h->P.my < 65536 && h->P.mz < 32768;
+}
+
+template <int ORDER, bool FUSED, bool LAZY>
+static int launch_one(tgpu_ctx *h, const CRArgs &A)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(k_cellrun<ORDER, FUSED, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM_BYTES));
+        attr_set = true;
+    }
+    const unsigned per_block = CR_WARPS * 4u * CR_CHUNK;
+    const unsigned blocks = (A.n + per_block - 1) / per_block;
+    k_cellrun<ORDER, FUSED, LAZY><<<blocks, CR_WARPS * 32, CR_SMEM_BYTES, h->stream>>>(A);
+    CKK(h);
+    return 0;
+}
+template <bool FUSED>
+static int launch_any(tgpu_ctx *h, const CRArgs &A)
+{
+    const bool lazy = FUSED && A.perm != nullptr;
+    if (h->P.order == 2) return lazy ? launch_one<2, FUSED, FUSED>(h, A) : launch_one<2, FUSED, false>(h, A);
+    return lazy ? launch_one<1, FUSED, FUSED>(h, A) : launch_one<1, FUSED, false>(h, A);
+}
+
+static void fill_args(tgpu_ctx *h, int s, CRArgs &A, float *cx, float *cy, float *cz)
+{
+    A.prim8 = h->prim8; A.cx = cx; A.cy = cy; A.cz = cz; A.nty = h->nty; A.G = h->G;
+    A.qm = s ? h->P.qme : h->P.qmi; A.qs = s ? h->P.qe : h->P.qi;
+    A.keyoff = 1u + (unsigned)h->G.mx + (unsigned)h->G.mx * (unsigned)h->G.my;
+    A.general = !(h->G.perx && h->G.pery && h->G.perz) || h->G.sendy || h->G.sendz;
 }
 
 template <bool FUSED>
@@ -457,23 +497,13 @@ static int launch(tgpu_ctx *h, float *cx, float *cy, float *cz)
         Species &S = h->sp[s];
         if (S.n == 0) continue;
         CRArgs A;
-        A.s = S; A.d = S; A.perm = nullptr;
-        A.n = S.n; A.prim8 = h->prim8; A.cx = cx; A.cy = cy; A.cz = cz; A.nty = h->nty; A.G = h->G;
-        A.qm = s ? h->P.qme : h->P.qmi; A.qs = s ? h->P.qe : h->P.qi;
+        fill_args(h, s, A, cx, cy, cz);
+        A.s = S; A.d = S; A.perm = nullptr; A.n = (unsigned)S.n;
         const size_t nb = (size_t)h->G.lot + TGPU_NBIN_EXTRA;
         A.key = h->key[s]; A.slot = h->slot + (size_t)s * h->maxhlf; A.bincount = h->bincount + (size_t)s * nb;
         if (FUSED) CK(cudaMemsetAsync(A.bincount, 0, nb * sizeof(int32_t), h->stream));
         if (FUSED && h->lazy[s]) { A.perm = h->perm[s]; A.d = h->alt[s]; }     // gather through the pending permutation
-        long long warps = (S.n + 2 * CR_CHUNK - 1) / (2 * CR_CHUNK);
-        int blocks = (int)((warps + CR_WARPS - 1) / CR_WARPS);
-        if (h->P.order == 2) {
-            CK(cudaFuncSetAttribute(k_cellrun<2, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM_BYTES));
-            k_cellrun<2, FUSED><<<blocks, CR_WARPS * 32, CR_SMEM_BYTES, h->stream>>>(A);
-        } else {
-            CK(cudaFuncSetAttribute(k_cellrun<1, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM_BYTES));
-            k_cellrun<1, FUSED><<<blocks, CR_WARPS * 32, CR_SMEM_BYTES, h->stream>>>(A);
-        }
-        CKK(h);
+        int rc = launch_any<FUSED>(h, A); if (rc) return rc;
         if (FUSED && h->lazy[s]) {
             // the pushed records now sit, in sorted order and wrapped, in the other buffer
             int n = S.n;
@@ -512,22 +542,11 @@ int cellrun_move_deposit_range(tgpu_ctx *h, int s, int off, int cnt)
     CRArgs A;
     Species R = S;
     R.x += off; R.y += off; R.z += off; R.u += off; R.v += off; R.w += off; R.ch += off; R.ind += off; R.tag += off; R.n = cnt;
-    A.s = R; A.d = R; A.perm = nullptr;
-    A.n = cnt; A.prim8 = h->prim8; A.cx = h->shadow[0]; A.cy = h->shadow[1]; A.cz = h->shadow[2]; A.nty = h->nty; A.G = h->G;
-    A.qm = s ? h->P.qme : h->P.qmi; A.qs = s ? h->P.qe : h->P.qi;
+    fill_args(h, s, A, h->shadow[0], h->shadow[1], h->shadow[2]);
+    A.s = R; A.d = R; A.perm = nullptr; A.n = (unsigned)cnt;
     const size_t nb = (size_t)h->G.lot + TGPU_NBIN_EXTRA;
     A.key = h->key[s] + off; A.slot = h->slot + (size_t)s * h->maxhlf + off; A.bincount = h->bincount + (size_t)s * nb;
-    long long warps = ((long long)cnt + 2 * CR_CHUNK - 1) / (2 * CR_CHUNK);
-    int blocks = (int)((warps + CR_WARPS - 1) / CR_WARPS);
-    if (h->P.order == 2) {
-        CK(cudaFuncSetAttribute(k_cellrun<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM_BYTES));
-        k_cellrun<2, true><<<blocks, CR_WARPS * 32, CR_SMEM_BYTES, h->stream>>>(A);
-    } else {
-        CK(cudaFuncSetAttribute(k_cellrun<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM_BYTES));
-        k_cellrun<1, true><<<blocks, CR_WARPS * 32, CR_SMEM_BYTES, h->stream>>>(A);
-    }
-    CKK(h);
-    return 0;
+    return launch_any<true>(h, A);
 }
 
 // tgpu_deposit_particles fast path when the particles were moved elsewhere (mirror mode, tests)

@@ -12,6 +12,10 @@ __device__ __forceinline__ void red_nz(float *p, float v)
     asm volatile("{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %1, 0f00000000;\n\t@p red.global.add.f32 [%0], %1;\n\t}"
                  :: "l"(p), "f"(v) : "memory");
 }
+__device__ __forceinline__ void red_add(float *p, float v)
+{
+    asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
 // Asynchronous 4-byte global -> shared copy (LDGSTS): the particle record of the NEXT 16-particle step of a half-warp is
 // fetched into per-lane landing slots while the current step is being deposited, so neither the permutation lookup nor
 // the record loads sit on the critical path of phase 1 and no registers are held across phase 2.
