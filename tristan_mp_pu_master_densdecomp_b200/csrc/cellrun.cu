@@ -14,8 +14,7 @@
 //   phase 1 (lane = particle, 32 particles per warp step): read the landed record, [gather node-centred fields (packed
 //           FFMA2) + Boris push + store + sort key of the new cell + rank in its bin], build the 1-D factors of the
 //           Esirkepov sum from the old and new shapes and park them in shared memory (40 floats per particle).
-//           Deposit-only launches recompute the old position as the reference does (x - u/gamma*c); fused launches use
-//           the gather's shape at the true pre-push position (equal to round-off);
+//           The deposit's old position is recomputed from the new one as the reference does (x - u/gamma*c);
 //   phase 2 (QUARTER-warp = one footprint): lane (j, kp) of a quarter owns the 4 x-cells of the two footprint rows
 //           (j, kp) and (j, kp + 2) for all three components = 24 register accumulators (12 FFMA2 pairs).  It walks the 8
 //           particles its quarter staged; the four quarters run in lockstep.  The x-planes form a ring (plane of cell x
@@ -36,13 +35,25 @@
 #include "shapes.cuh"
 
 #ifndef CR_WARPS
-#define CR_WARPS 8
+#define CR_WARPS 4           // 4-warp blocks x 6 per SM (measured: 15.64 ms per lap against 15.94 for 8 x 3)
 #endif
 #ifndef CR_MINB
-#define CR_MINB 3
+#define CR_MINB 6
 #endif
 #ifndef CR_CHUNK
 #define CR_CHUNK 128          // particles per quarter-warp
+#endif
+#ifndef CR_P2UNROLL
+#define CR_P2UNROLL 4         // phase-2 unroll: the window-move code is inlined once per copy and the kernel has to stay inside
+                              // the instruction cache (fully unrolled: 4096 instructions, 29 % of the stall samples "no instruction")
+#endif
+#define CR_STR(x) #x
+#define CR_DO_PRAGMA(x) _Pragma(CR_STR(x))
+#ifndef CR_OLDPOS_REF
+#define CR_OLDPOS_REF 1       // fused launches recompute the deposit's old position as the reference does (0: reuse the gather's shape)
+#endif
+#ifndef CR_PREFETCH
+#define CR_PREFETCH 0
 #endif
 #define CR_STRIDE 44          // floats between the staged factors of consecutive particles (40 used; 44 keeps the
                               // phase-1 STS.128 of a quarter-warp conflict-free: 12 banks apart)
@@ -50,7 +61,11 @@
                                            // lockstep phase-2 loads never fall into the same banks
 #define CR_WARP_FLOATS (4 * CR_QFLOATS)
 #define CR_REC_WORDS (2 * 9 * 32)          // record landing slots of one warp: [buf][field][lane]
-#define CR_SMEM_BYTES (sizeof(float) * CR_WARPS * CR_WARP_FLOATS + sizeof(uint32_t) * CR_WARPS * CR_REC_WORDS)
+#ifndef CR_REGPF
+#define CR_REGPF 0            // 1: the next step's record is prefetched into registers (streaming loads that do not allocate
+                              // in L1); 0: 4-byte cp.async into per-lane shared-memory landing slots
+#endif
+#define CR_SMEM_BYTES (sizeof(float) * CR_WARPS * CR_WARP_FLOATS + (CR_REGPF ? 0 : sizeof(uint32_t) * CR_WARPS * CR_REC_WORDS))
 #define CR_NOWIN (-0x40000000)             // "no window yet"
 
 // staging layout of one particle (floats):
@@ -88,6 +103,20 @@ __device__ __forceinline__ float4 ldg_keep(const float4 *p)
     float4 v;
     asm("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
+}
+
+// particle records are read exactly once: do not let them displace the field lines in L1
+__device__ __forceinline__ float ldg_stream(const float *p)
+{
+    float v; asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ int ldg_stream(const int32_t *p)
+{
+    int v; asm volatile("ld.global.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ void prefetch_l1_keep(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
 }
 
 template <int NW>
@@ -215,7 +244,7 @@ __device__ __forceinline__ uint32_t sort_key(const DevGeom &G, unsigned keyoff, 
     return key;
 }
 
-template <int ORDER, bool FUSED, bool LAZY>
+template <int ORDER, bool FUSED, bool LAZY, bool FASTP>
 __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(const CRArgs A)
 {
     // dynamic shared memory (CR_SMEM_BYTES > 48 KB): the factor staging of phase 1 -> phase 2, then the record pipeline
@@ -236,7 +265,9 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(const CRArgs
     float *const st = sq + ql * CR_STRIDE;                   // phase 1: this lane's particle
     const float *const syl = sq + 12 + j;                    // phase 2: row j of the y block
     const float4 *const szl = reinterpret_cast<const float4 *>(sq + 24 + 4 * kp);   // phase 2: row pair kp of the z block
+#if !CR_REGPF
     uint32_t *const rec = reinterpret_cast<uint32_t *>(cr_smem + sizeof(float) * CR_WARPS * CR_WARP_FLOATS) + warp * CR_REC_WORDS + lane;
+#endif
 
     // window: cell wi (1-based), row id wrow = (j0 - 1) | (k0 - 1) << 16, element offsets of the lane's two rows at plane wi - 1
     int wi = CR_NOWIN, wrow = -1;
@@ -280,8 +311,23 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(const CRArgs
         }
     };
 
-    // ---- record pipeline: rec[buf][field][lane], fields x y z u v w ch ind tag; each lane only ever touches its own slots
+    // ---- record pipeline.  CR_REGPF: seven streaming loads per lane one step ahead, straight into registers (nothing touches
+    // them until the next step starts, so they are in flight during this step's phase 1 and phase 2; ind / tag are only
+    // copied and are loaded at the start of their own step).  Otherwise: rec[buf][field][lane] landing slots filled by
+    // 4-byte cp.async, fields x y z u v w ch ind tag; each lane only ever touches its own slots.
     constexpr int NIT = CR_CHUNK / 8;
+#if CR_REGPF
+    float nx_ = 0.f, ny_ = 0.f, nz_ = 0.f, nu_ = 0.f, nv_ = 0.f, nw_ = 0.f, nch_ = 0.f;
+    unsigned pcur = 0;
+    auto fetch = [&](int, unsigned tt, int pp32) {
+        if (tt < n) {
+            const unsigned pp = LAZY ? (unsigned)pp32 : tt;
+            nx_ = ldg_stream(A.s.x + pp); ny_ = ldg_stream(A.s.y + pp); nz_ = ldg_stream(A.s.z + pp);
+            nu_ = ldg_stream(A.s.u + pp); nv_ = ldg_stream(A.s.v + pp); nw_ = ldg_stream(A.s.w + pp);
+            nch_ = ldg_stream(A.s.ch + pp);
+        }
+    };
+#else
     auto fetch = [&](int buf, unsigned tt, int pp32) {
         if (tt < n) {
             const unsigned pp = LAZY ? (unsigned)pp32 : tt;
@@ -293,30 +339,50 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(const CRArgs
         }
         cp_async_commit();
     };
-    {
-        const unsigned t0 = base + ql;
-        fetch(0, t0, (LAZY && t0 < n) ? __ldcs(A.perm + t0) : 0);
-    }
+#endif
     // permutation entry of this lane's particle of the next step: loaded one step ahead and kept as the raw 32-bit
     // value (no instruction touches it until the following step, so the load never stalls the warp)
     int pnext = 0;
-    if (LAZY && base + 8 + ql < n) pnext = __ldcs(A.perm + base + 8 + ql);
+    {
+        const unsigned t0 = base + ql;
+        const int p0 = (LAZY && t0 < n) ? __ldcs(A.perm + t0) : 0;
+        fetch(0, t0, p0);
+        if (LAZY && base + 8 + ql < n) pnext = __ldcs(A.perm + base + 8 + ql);
+#if CR_REGPF
+        pcur = LAZY ? (unsigned)p0 : t0;
+#endif
+    }
 
 #pragma unroll 1
     for (int it = 0; it < NIT; ++it) {
         const unsigned t = base + it * 8 + ql;
         int ci = -1, crow = -1;                              // deposit base cell of this lane's particle
+#if CR_REGPF
+        float x = nx_, y = ny_, z = nz_, u = nu_, v = nv_, w = nw_;
+        const float ch = nch_;
+        int pind = 0, ptag = 0;
+        if (LAZY && t < n) { pind = ldg_stream(A.s.ind + pcur); ptag = ldg_stream(A.s.tag + pcur); }
+        if (it + 1 < NIT) {
+            pcur = LAZY ? (unsigned)pnext : t + 8;
+            fetch(0, t + 8, pnext);                          // next step's record, in flight during this step
+            if (LAZY && it + 2 < NIT && t + 16 < n) pnext = __ldcs(A.perm + t + 16);
+        }
+#else
         cp_async_wait_all();                                 // this step's record has landed in rec[it & 1]
         if (it + 1 < NIT) {
             fetch((it + 1) & 1, t + 8, pnext);               // next step's record, in flight during this step
             if (LAZY && it + 2 < NIT && t + 16 < n) pnext = __ldcs(A.perm + t + 16);
         }
+#endif
         // ------------------------------------------------------------------ phase 1: lane = particle
         if (t < n) {
+#if !CR_REGPF
             const uint32_t *r = rec + (it & 1) * (9 * 32);
             float x = __uint_as_float(r[0 * 32]), y = __uint_as_float(r[1 * 32]), z = __uint_as_float(r[2 * 32]);
             float u = __uint_as_float(r[3 * 32]), v = __uint_as_float(r[4 * 32]), w = __uint_as_float(r[5 * 32]);
             const float ch = __uint_as_float(r[6 * 32]);
+            const int pind = LAZY ? (int)r[7 * 32] : 0, ptag = LAZY ? (int)r[8 * 32] : 0;
+#endif
             if (LAZY) {
                 // lazily sorted input: the record still carries last lap's unwrapped position; apply the periodic wrap /
                 // frame shift its sort key was computed with (deposit_particles loop B), and carry the passive fields along
@@ -324,7 +390,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(const CRArgs
                 x = wrap1(x, G.minx, G.maxx, G.shiftx_lo, G.shiftx_hi, lo, hi);
                 y = wrap1(y, G.miny, G.maxy, G.shifty_lo, G.shifty_hi, lo, hi);
                 z = wrap1(z, G.minz, G.maxz, G.shiftz_lo, G.shiftz_hi, lo, hi);
-                A.d.ch[t] = ch; A.d.ind[t] = (int32_t)r[7 * 32]; A.d.tag[t] = (int32_t)r[8 * 32];
+                A.d.ch[t] = ch; A.d.ind[t] = pind; A.d.tag[t] = ptag;
             }
             const float q = ch * A.qs;
             float S1[4], S2[4];
@@ -343,6 +409,15 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(const CRArgs
                 if (fast) {
                     const float wxs[2] = {Wx[1], Wx[2]}, wys[2] = {Wy[1], Wy[2]}, wzs[2] = {Wz[1], Wz[2]};
                     const int nbase = (ip - 1) + mx * ((jp - 1) + my * (kq - 1));
+#if CR_PREFETCH
+                    // In sorted order the next step of this quarter works one or two cells further along x: its new x-node
+                    // column (2 x 2 rows) is not in L1 yet.  One prefetch per lane -- rows by (ql & 1, ql >> 1 & 1), nodes
+                    // ip + 2 (lanes 0-3) and ip + 3 (lanes 4-7) -- brings it in while phase 2 runs.
+                    {
+                        const unsigned pn = (unsigned)(nbase + 2 + (ql >> 2) + mx * ((ql & 1) + my * ((ql >> 1) & 1)));
+                        prefetch_l1_keep(A.prim8 + 2u * min(pn, (unsigned)G.lot - 1u));
+                    }
+#endif
                     gather_nodes<2>(A.prim8, nbase, mx, my, wxs, wys, wzs, e0, e1, e2, b0, b1, b2);
                 } else if (ORDER == 2) {
                     int lox, loy, loz;
@@ -366,13 +441,31 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(const CRArgs
                     b0 = b0 + G.ext[3] * 0.5f * qm * cinv; b1 = b1 + G.ext[4] * 0.5f * qm * cinv; b2 = b2 + G.ext[5] * 0.5f * qm * cinv;
                     e0 = e0 + G.ext[0] * 0.5f * qm; e1 = e1 + G.ext[1] * 0.5f * qm; e2 = e2 + G.ext[2] * 0.5f * qm;
                 }
-                push_particle<true>(G.c, G.pusher, e0, e1, e2, b0, b1, b2, x, y, z, u, v, w, cinv);
+                push_particle<FASTP>(G.c, G.pusher, e0, e1, e2, b0, b1, b2, x, y, z, u, v, w, cinv);
                 A.d.x[t] = x; A.d.y[t] = y; A.d.z[t] = z; A.d.u[t] = u; A.d.v[t] = v; A.d.w[t] = w;
                 // sort key of the pushed particle + its rank inside the destination bin; the rank comes back from L2 while
                 // the deposit factors are being staged and is stored at the end of the phase
                 const uint32_t ky = sort_key(G, A.keyoff, A.general, x, y, z);
                 A.key[t] = ky;
                 const int rank_in_bin = atomicAdd(&A.bincount[ky], 1);
+#if CR_OLDPOS_REF
+                // deposit_particles loop A: the old position is RECOMPUTED from the new one, x - u/gamma*c
+                // (particles_movedeposit.F90:1384-1390), not remembered -- at x ~ 130 one ulp of x is 7e-5 of a step, so the
+                // gather's shape at the true pre-push position would give currents that differ from the reference's by
+                // ~1e-5 of the gross current.  
+                {
+                    const float invgam = FASTP ? rsqrtf(1.f + u * u + v * v + w * w) : 1.f / sqrtf(1.f + u * u + v * v + w * w);
+                    const float x1 = x - u * invgam * G.c, y1 = y - v * invgam * G.c, z1 = z - w * invgam * G.c;
+                    const int i1 = (int)x1, j1 = (int)y1, k1 = (int)z1;
+                    crow = (j1 - 1) | ((k1 - 1) << 16); ci = i1;
+                    shape_window<ORDER>(x1 - i1, 0, S1); shape_window<ORDER>(x - (int)x, (int)x - i1, S2);
+                    stage_x(st, S1, S2, q, (i1 - 1) & 3);
+                    shape_window<ORDER>(y1 - j1, 0, S1); shape_window<ORDER>(y - (int)y, (int)y - j1, S2);
+                    stage_y(st, S1, S2, q);
+                    shape_window<ORDER>(z1 - k1, 0, S1); shape_window<ORDER>(z - (int)z, (int)z - k1, S2);
+                    stage_z(st, S1, S2, q, ci, crow);
+                }
+#else
                 // The deposit's "old" shape is the gather's shape at the true pre-push position (the reference
                 // recomputes it as x - u/gamma*c, particles_movedeposit.F90:1384-1388, equal to round-off).
                 crow = (jp - 1) | ((kq - 1) << 16); ci = ip;
@@ -383,6 +476,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(const CRArgs
                 stage_y(st, Wy, S2, q);
                 shape_window<ORDER>(z - kn, kn - kq, S2);
                 stage_z(st, Wz, S2, q, ci, crow);
+#endif
                 A.slot[t] = rank_in_bin;
             } else {
                 // deposit_particles loop A: old position recomputed from the new one (particles_movedeposit.F90:1384-1390)
@@ -412,7 +506,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32, CR_MINB) k_cellrun(const CRArgs
         __syncwarp();
         // ------------------------------------------------------------------ phase 2: quarter-warp = footprint
         // The four quarters walk their 8 particles in lockstep; only the window moves diverge.
-#pragma unroll 2
+CR_DO_PRAGMA(unroll CR_P2UNROLL)
         for (int tt = 0; tt < 8; ++tt) {
             const float4 v1 = szl[tt * (CR_STRIDE / 4) + 2];             // (qPz[kp], qPz[kp + 2], cell i, row id)
             if (any & (1u << tt)) {
@@ -460,17 +554,19 @@ int cellrun_supported(const tgpu_ctx *h)
     return h->P.dim == 3 && (h->P.order == 1 || h->P.order == 2) && h->G.lot < (1ll << 30) && h->P.my < 65536 && h->P.mz < 32768;
 }
 
-template <int ORDER, bool FUSED, bool LAZY>
+// FASTP (tgpu_set_option "fast_push", default 1): SFU reciprocal / reciprocal square root in the Boris push (<= 2 ulp)
+// instead of the IEEE division and square root; measured 3 % of the mover (15.33 against 15.79 ms per lap)
+template <int ORDER, bool FUSED, bool LAZY, bool FASTP>
 static int launch_one(tgpu_ctx *h, const CRArgs &A)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        CK(cudaFuncSetAttribute(k_cellrun<ORDER, FUSED, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_cellrun<ORDER, FUSED, LAZY, FASTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM_BYTES));
         attr_set = true;
     }
     const unsigned per_block = CR_WARPS * 4u * CR_CHUNK;
     const unsigned blocks = (A.n + per_block - 1) / per_block;
-    k_cellrun<ORDER, FUSED, LAZY><<<blocks, CR_WARPS * 32, CR_SMEM_BYTES, h->stream>>>(A);
+    k_cellrun<ORDER, FUSED, LAZY, FASTP><<<blocks, CR_WARPS * 32, CR_SMEM_BYTES, h->stream>>>(A);
     CKK(h);
     return 0;
 }
@@ -478,8 +574,12 @@ template <bool FUSED>
 static int launch_any(tgpu_ctx *h, const CRArgs &A)
 {
     const bool lazy = FUSED && A.perm != nullptr;
-    if (h->P.order == 2) return lazy ? launch_one<2, FUSED, FUSED>(h, A) : launch_one<2, FUSED, false>(h, A);
-    return lazy ? launch_one<1, FUSED, FUSED>(h, A) : launch_one<1, FUSED, false>(h, A);
+    if (FUSED && !h->opt_fast_push) {
+        if (h->P.order == 2) return lazy ? launch_one<2, FUSED, FUSED, false>(h, A) : launch_one<2, FUSED, false, false>(h, A);
+        return lazy ? launch_one<1, FUSED, FUSED, false>(h, A) : launch_one<1, FUSED, false, false>(h, A);
+    }
+    if (h->P.order == 2) return lazy ? launch_one<2, FUSED, FUSED, FUSED>(h, A) : launch_one<2, FUSED, false, FUSED>(h, A);
+    return lazy ? launch_one<1, FUSED, FUSED, FUSED>(h, A) : launch_one<1, FUSED, false, FUSED>(h, A);
 }
 
 static void fill_args(tgpu_ctx *h, int s, CRArgs &A, float *cx, float *cy, float *cz)

@@ -405,13 +405,21 @@ static size_t box_total(const Box &b) { return (size_t)3 * b.n[0] * b.n[1] * b.n
 // Move a box of three arrays from this rank's `src` to the `dst` box of the neighbour that lies in
 // direction `dir_to` (and receive the matching box from the opposite neighbour).  Local when the
 // axis has one rank.  recv_ok = 0 skips the unpack (open boundary, edge rank).
-static int box_shift(tgpu_ctx *h, Arr3 A, Box src, Box dst, int axis, int dir_to, int mode, int recv_ok)
+static int box_shift(tgpu_ctx *h, Arr3 A, Box src, Box dst, int axis, int dir_to, int mode, int recv_ok, bool buffered = false)
 {
     int m, g, per, sz, pos; axis_info(h, axis, &m, &g, &per, &sz, &pos);
     size_t total = box_total(src);
     if (total == 0) return 0;
     if (sz == 1) {
         if (!recv_ok) return 0;
+        if (buffered) {
+            // source and destination overlap (an axis narrower than its ghost zone): go through a buffer as the reference
+            // does (bufferin1y / bufferin2y, fieldboundaries.F90:1931-1948)
+            if (total > h->halo_floats) { tgpu_set_error("halo scratch too small"); return TGPU_EINVAL; }
+            k_box_get<<<cdiv(total, 256), 256, 0, h->stream>>>(A, src, h->halo, h->P.mx, h->P.my, total); CKK(h);
+            k_box_put<<<cdiv(total, 256), 256, 0, h->stream>>>(A, dst, h->halo, h->P.mx, h->P.my, mode, total); CKK(h);
+            return 0;
+        }
         k_box_copy<<<cdiv(total, 256), 256, 0, h->stream>>>(A, src, dst, h->P.mx, h->P.my, mode, total);
         CKK(h);
         return 0;
@@ -443,6 +451,18 @@ int fld_bc(tgpu_ctx *h, int first)
         if (!per && sz == 1 && axis != 2) continue;           // bc_b1: no copy at all
         if (!per && sz == 1 && axis == 2) continue;           // copy_layrz2 on a single rank: both receives skipped
         Box src = full_box(h), dst = full_box(h);
+        if (m - 2 * g - 1 < g) {
+            // fewer interior cells than ghost layers (user/input.twostream: my0 = 2): the outer ghost layers are images of
+            // layers that are ghosts themselves, so the reference's layer-by-layer order matters (do iter = 1, nghost/2 ...)
+            src.n[axis] = dst.n[axis] = 1;
+            for (int iter = 1; iter <= g; iter++) {
+                src.lo[axis] = m - (g + iter); dst.lo[axis] = g + 1 - iter;
+                int rc = box_shift(h, A, src, dst, axis, +1, 0, per || pos != 0); if (rc) return rc;
+                src.lo[axis] = g + iter; dst.lo[axis] = m - g - 1 + iter;
+                rc = box_shift(h, A, src, dst, axis, -1, 0, per || pos != sz - 1); if (rc) return rc;
+            }
+            continue;
+        }
         // send up: my layers [m-2g, m-g-1] become the + neighbour's low ghosts [1, g]
         src.lo[axis] = m - 2 * g; src.n[axis] = g; dst.lo[axis] = 1; dst.n[axis] = g;
         int rc = box_shift(h, A, src, dst, axis, +1, 0, per || pos != 0);
@@ -469,11 +489,12 @@ int fld_fold(tgpu_ctx *h)
         int ng = axis == 2 ? h->P.nghostz : h->P.nghost;
         if (sz == 1 && !per) continue;
         Box src = full_box(h), dst = full_box(h);
+        const bool overlap = m - ng < g + 1;                  // narrow axis: the target layers reach into the source ghosts
         src.lo[axis] = m - g; src.n[axis] = g + 1; dst.lo[axis] = g + 1; dst.n[axis] = g + 1;
-        int rc = box_shift(h, A, src, dst, axis, +1, 1, per || pos != 0);
+        int rc = box_shift(h, A, src, dst, axis, +1, 1, per || pos != 0, overlap);
         if (rc) return rc;
         src.lo[axis] = 1; src.n[axis] = g; dst.lo[axis] = m - (ng - 1); dst.n[axis] = g;
-        rc = box_shift(h, A, src, dst, axis, -1, 1, per || pos != sz - 1);
+        rc = box_shift(h, A, src, dst, axis, -1, 1, per || pos != sz - 1, overlap);
         if (rc) return rc;
     }
     return 0;

@@ -65,6 +65,7 @@ struct tgpu_ctx {
     float *shadow[3];        // tiled: [tz][ty][i][4x4 (y,z) tile] (cellrun.cu row_index), nty x ntz tiles
     int nty, ntz; size_t shadow_floats;
     int opt_fused;
+    int opt_fast_push;       // cell-run movers: SFU rcp / rsqrt in the Boris push (default 1)
     int hook_kind; float hook[5];   // user hooks for tgpu_step (1 = shock: leftwall, binit, btheta, bphi, beta)
     int keys_valid;          // key[]/slot[]/bincount[] already hold this lap's sort keys (written by the fused mover)
     cudaStream_t stream;     // the stream every launch helper uses (normally == stream_main)
