@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--e2e-plain", action="store_true", help="mirror lap as separate h2d / step / d2h calls instead of tgpu_step_mirror")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fused", type=int, default=1)
+    ap.add_argument("--peer", type=int, default=1, help="field halos over cudaIpc peer memory (1) or NCCL send/recv (0)")
     ap.add_argument("--order", type=int, default=ORDER, help="shape order (headline = 2)")
     ap.add_argument("--ppc", type=float, default=PPC)
     ap.add_argument("--cpu-cells", type=int, nargs=3, default=[128, 32, 32], help="CPU sample: cells per host-thread slab")
@@ -251,8 +252,11 @@ def main():
                        buffsize=max(int(nhalf_est * 0.05), 100000), device=local)
     ctx = tg.Context(P)
     ctx.set_option("fused", args.fused)
+    ctx.set_option("peer", args.peer)
     if world > 1:
         ctx.comm_init_torch()
+    halo_transport = ("peer memory (cudaIpc, halo kernels read the neighbours' arrays over NVLink)" if ctx.halo_transport()
+                      else "NCCL send/recv") if world > 1 else "none (one rank)"
     do_e2e = not args.no_e2e
     p, nhalf, fields, keep = make_state(tg, P, rank, pinned=do_e2e)
     ctx.fields_h2d(*fields)
@@ -395,7 +399,7 @@ def main():
     line = {"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": n, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "ns_per_particle_step": 1e9 / value * n,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, n), "particles": total_particles, "gpu_launches": launches,
+            "config": dict(workload_config(args, n), halo_transport=halo_transport), "particles": total_particles, "gpu_launches": launches,
             "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "hbm_roofline_frac_whole_step": (total_particles / n * B_PER_PARTICLE + 144.0 * cx * cy * cz) / (ms / args.steps * 1e-3) / 1e9 / peak}
     print(json.dumps(line))

@@ -189,8 +189,14 @@ int tgpu_timers(tgpu_ctx *h, double *out_ms, int reset);
 int64_t tgpu_launch_count(tgpu_ctx *h);
 /* the CUDA stream all kernels of this context are launched on (cudaStream_t as void*) */
 void *tgpu_stream(tgpu_ctx *h);
-/* select the particle path: 0 = generic per-particle kernels, 1 = cell-run fused kernels where available */
+/* options: "fused" (0 = generic per-particle kernels, 1 = cell-run fused kernels where available), "lazy", "overlap",
+   "timing", "fast_push" (SFU reciprocals in the cell-run Boris push), "peer" (before tgpu_comm_init: 1 = field halos over
+   cudaIpc peer memory, 0 = NCCL send/recv) */
 int tgpu_set_option(tgpu_ctx *h, const char *name, int value);
+/* which transport the field-side halo exchanges use after tgpu_comm_init: 1 = peer memory (the neighbours' arrays are
+   mapped with cudaIpc and read over NVLink by the halo kernels), 0 = NCCL send/recv (replaces the MPI_SendRecv pairs of
+   fieldboundaries.F90:1179-1204, 1319-1344, 1652-1677, 1990-2185 either way) */
+int tgpu_halo_transport(tgpu_ctx *h);
 
 #ifdef __cplusplus
 }

@@ -26,10 +26,14 @@ def _worker(rank, world, port, case, q):
         from oracle import oracle as O
         kw = dict(ppc=4.0, ntimes=3, delgam=0.05)
         kw.update(case)
+        peer = kw.pop("peer", 1)
         w = T.oracle_world(**kw)
         r = w.ranks[rank]
         ctx = tg.Context(T.gpu_params(tg, w, rank=rank, device=rank))
+        ctx.set_option("peer", peer)                 # 1: halos over cudaIpc peer memory; 0: NCCL send / recv
         ctx.comm_init_torch()
+        if ctx.halo_transport() != peer:
+            raise RuntimeError(f"halo transport {ctx.halo_transport()} != requested {peer} (cudaIpc mapping of the neighbours failed?)")
         T.upload(ctx, r)
         err = ""
         for lap in range(3):
@@ -68,10 +72,18 @@ CASES = {
         dict(dim=3, order=2, n=(16, 12, 16), sizes=(1, 1, 2), filter_kind=2, periodic=(0, 1, 1)),
         dict(dim=2, order=1, n=(24, 16, 1), sizes=(2, 1, 1), filter_kind=1, periodic=(0, 1, 1)),
         # 4th-order field solver across a slab boundary
-        dict(dim=3, order=2, n=(12, 12, 16), sizes=(1, 1, 2), filter_kind=2, highorder=1)],
+        dict(dim=3, order=2, n=(12, 12, 16), sizes=(1, 1, 2), filter_kind=2, highorder=1),
+        # the same exchanges through NCCL send / recv (peer memory switched off); uneven split (last rank takes the rest)
+        dict(dim=3, order=2, n=(12, 12, 16), sizes=(1, 1, 2), filter_kind=2, peer=0),
+        dict(dim=3, order=2, n=(12, 15, 12), sizes=(1, 2, 1), filter_kind=1),
+        dict(dim=3, order=2, n=(12, 12, 17), sizes=(1, 1, 2), filter_kind=2)],
     4: [dict(dim=3, order=2, n=(12, 16, 16), sizes=(1, 2, 2), filter_kind=2),
-        dict(dim=2, order=1, n=(16, 16, 1), sizes=(2, 2, 1), filter_kind=1)],
-    8: [dict(dim=3, order=2, n=(12, 16, 32), sizes=(1, 2, 4), filter_kind=2)],
+        dict(dim=2, order=1, n=(16, 16, 1), sizes=(2, 2, 1), filter_kind=1),
+        dict(dim=3, order=2, n=(16, 16, 16), sizes=(1, 2, 2), filter_kind=2, periodic=(0, 1, 1)),
+        dict(dim=3, order=2, n=(12, 16, 16), sizes=(1, 2, 2), filter_kind=1, peer=0)],
+    8: [dict(dim=3, order=2, n=(12, 16, 32), sizes=(1, 2, 4), filter_kind=2),
+        dict(dim=3, order=3, n=(12, 16, 32), sizes=(1, 2, 4), filter_kind=2),
+        dict(dim=3, order=1, n=(12, 16, 32), sizes=(1, 4, 2), filter_kind=1)],
 }
 
 
@@ -85,24 +97,30 @@ def _run(world, case):
     procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
+    try:
+        res = [q.get(timeout=180) for _ in range(world)]
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+        for p in procs:
+            if p.is_alive():                     # a rank that hangs must not take the whole session with it
+                p.kill()
     errs = [e for _, e, _ in res if e]
     assert not errs, errs
     assert sum(m for _, _, m in res) > 0, "no particle migrated"
 
 
-@pytest.mark.parametrize("case", CASES[2], ids=["3d-z", "3d-y", "3d-z-o3", "2d-x", "3d-z-openx", "2d-x-openx", "3d-z-highorder"])
+@pytest.mark.parametrize("case", CASES[2], ids=["3d-z", "3d-y", "3d-z-o3", "2d-x", "3d-z-openx", "2d-x-openx", "3d-z-highorder",
+                                                  "3d-z-nccl", "3d-y-uneven", "3d-z-uneven"])
 def test_two_gpus(tg, case):
     _run(2, case)
 
 
-@pytest.mark.parametrize("case", CASES[4], ids=["3d-yz", "2d-xy"])
+@pytest.mark.parametrize("case", CASES[4], ids=["3d-yz", "2d-xy", "3d-yz-openx", "3d-yz-nccl"])
 def test_four_gpus(tg, case):
     _run(4, case)
 
 
-@pytest.mark.parametrize("case", CASES[8], ids=["3d-2x4"])
+@pytest.mark.parametrize("case", CASES[8], ids=["3d-2x4", "3d-2x4-o3", "3d-4x2-o1"])
 def test_eight_gpus(tg, case):
     _run(8, case)

@@ -53,7 +53,7 @@ ABI_SYMBOLS = [
     "tgpu_add_current", "tgpu_bc_b1", "tgpu_bc_e1", "tgpu_bc_b2", "tgpu_bc_e2", "tgpu_exchange_current",
     "tgpu_apply_filter", "tgpu_apply_filter1_opt", "tgpu_apply_filter2_opt", "tgpu_move_particles",
     "tgpu_deposit_particles", "tgpu_exchange_particles", "tgpu_inject_others", "tgpu_reorder_particles",
-    "tgpu_meanq_fld_cur", "tgpu_spectrum_gamma_range", "tgpu_spectrum", "tgpu_select_particles", "tgpu_step_mirror", "tgpu_field_bc_user_shock", "tgpu_particle_bc_user_wall", "tgpu_set_user_hooks", "tgpu_step", "tgpu_timers", "tgpu_launch_count", "tgpu_stream", "tgpu_set_option",
+    "tgpu_meanq_fld_cur", "tgpu_spectrum_gamma_range", "tgpu_spectrum", "tgpu_select_particles", "tgpu_step_mirror", "tgpu_field_bc_user_shock", "tgpu_particle_bc_user_wall", "tgpu_set_user_hooks", "tgpu_step", "tgpu_timers", "tgpu_launch_count", "tgpu_stream", "tgpu_set_option", "tgpu_halo_transport",
 ]
 
 _lib = None
@@ -106,6 +106,7 @@ def load_library(path=None):
     L.tgpu_launch_count.argtypes = [vp]
     L.tgpu_stream.restype = vp
     L.tgpu_stream.argtypes = [vp]
+    L.tgpu_halo_transport.argtypes = [vp]
     L.tgpu_set_option.argtypes = [vp, C.c_char_p, ci]
     if path == LIB_PATH:
         _lib = L
@@ -281,6 +282,10 @@ class Context:
 
     def stream(self):
         return self.lib.tgpu_stream(self.h)
+
+    def halo_transport(self):
+        """1 = field halos over cudaIpc peer memory, 0 = NCCL send/recv"""
+        return int(self.lib.tgpu_halo_transport(self.h))
 
     def set_option(self, name, value):
         self._ck(self.lib.tgpu_set_option(self.h, name.encode(), int(value)), "set_option")

@@ -160,7 +160,7 @@ static int init_impl(tgpu_ctx *h, const tgpu_params *p, int ndev)
         rc |= dalloc(&h->sendbuf, (size_t)TGPU_NDIR * p->buffsize); rc |= dalloc(&h->recvbuf, (size_t)TGPU_NDIR * p->buffsize);
     }
     if (rc) { tgpu_set_error("device allocation failed: " + g_err); return TGPU_ECUDA; }
-    h->need_prim = 1; h->fused_pending = 0; h->keys_valid = 0; h->hook_kind = 0; h->in_step = 0; h->opt_fused = 1; h->opt_fast_push = 1; h->nccl_comm = nullptr; h->lap = 0; h->launches = 0; h->timing = 0;
+    h->need_prim = 1; h->fused_pending = 0; h->keys_valid = 0; h->hook_kind = 0; h->in_step = 0; h->opt_fused = 1; h->opt_fast_push = 1; h->opt_peer = 1; h->peer = nullptr; h->sig = nullptr; h->xseq = 0; h->nccl_comm = nullptr; h->lap = 0; h->launches = 0; h->timing = 0;
     for (int i = 0; i < TGPU_NPHASE; i++) h->phase_ms[i] = 0;
     CK(cudaDeviceSynchronize());
     return 0;
@@ -234,7 +234,8 @@ extern "C" int tgpu_fields_h2d(tgpu_ctx *h, const float *ex, const float *ey, co
 extern "C" int tgpu_fields_d2h(tgpu_ctx *h, float *ex, float *ey, float *ez, float *bx, float *by, float *bz)
 {
     ENTER(h); float *d[6] = {ex, ey, ez, bx, by, bz};
-    return arrays_copy(h, 0, 6, nullptr, d, false);
+    int rc = arrays_copy(h, 0, 6, nullptr, d, false);
+    return rc ? rc : comm_peer_check(h);          // a halo kernel that gave up waiting for a neighbour is reported here
 }
 extern "C" int tgpu_currents_h2d(tgpu_ctx *h, const float *cx, const float *cy, const float *cz)
 {
@@ -542,11 +543,13 @@ extern "C" int tgpu_timers(tgpu_ctx *h, double *out_ms, int reset)
 }
 extern "C" int64_t tgpu_launch_count(tgpu_ctx *h) { return h ? h->launches : 0; }
 extern "C" void *tgpu_stream(tgpu_ctx *h) { return h ? (void *)h->stream : nullptr; }
+extern "C" int tgpu_halo_transport(tgpu_ctx *h) { return h && h->peer ? 1 : 0; }
 extern "C" int tgpu_set_option(tgpu_ctx *h, const char *name, int value)
 {
     if (!h || !name) return TGPU_EINVAL;
     if (!strcmp(name, "fused")) { h->opt_fused = value; return 0; }
     if (!strcmp(name, "fast_push")) { h->opt_fast_push = value; return 0; }
+    if (!strcmp(name, "peer")) { h->opt_peer = value; return 0; }       // before tgpu_comm_init: 0 = halos through NCCL send/recv
     if (!strcmp(name, "timing")) { h->timing = value; return 0; }
     if (!strcmp(name, "overlap")) { h->opt_overlap = value; return 0; }
     if (!strcmp(name, "lazy_sort")) { h->opt_lazy = value; return 0; }

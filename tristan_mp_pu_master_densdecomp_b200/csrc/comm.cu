@@ -135,11 +135,119 @@ extern "C" int tgpu_comm_init(tgpu_ctx *h, const uint8_t id[128])
     CK(cudaStreamSynchronize(h->stream));
     nccl_comm_t c2; NCK(N.CommInitRank(&c2, h->size0, u2, h->P.rank));
     h->nccl_prt = c2;
+    // NCCL opens its point-to-point connections lazily, at the first send / recv between two ranks: hundreds of
+    // milliseconds that otherwise land in whichever lap (or phase timer) first migrates a particle to a diagonal
+    // neighbour.  One 4-byte exchange with all eight neighbours on both communicators, here.
+    for (int k = 0; k < 2; k++) {
+        h->nccl_comm = k ? h->nccl_prt : h->nccl_main;
+        rc = comm_group_begin(h); if (rc) return rc;
+        for (int cdir = 0; cdir < 9; cdir++) {
+            if (cdir == 4) continue;
+            const int da = cdir % 3 - 1, db = cdir / 3 - 1;
+            const int to = topo_neighbour2(h, da, db), from = topo_neighbour2(h, -da, -db);
+            comm_send(h, h->d_small + cdir, 4, to);
+            comm_recv(h, h->d_small + 16 + cdir, 4, from);
+        }
+        rc = comm_group_end(h); if (rc) return rc;
+    }
+    h->nccl_comm = h->nccl_main;
+    CK(cudaStreamSynchronize(h->stream));
+    return comm_peer_setup(h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer-memory transport for the field-side halo exchanges (C1, C2, C3 of SURVEY 2b: ghost refresh, current fold,
+// filter deep halo -- fieldboundaries.F90:1179-1204, 1319-1344, 1652-1677, 1990-2185; optimized_filters.F90:1665-1674,
+// 1838-1847).  One process per GPU stays; every rank exports its nine field arrays and a few signal words with cudaIpc,
+// the handles travel once over NCCL (all-gather), and each rank maps those of its axis neighbours.  After that a halo
+// step needs no NCCL call and no pack / unpack buffer: the consumer's kernel reads the neighbour's layers over NVLink
+// (fields.cu halo_step).  All ranks switch together or not at all (a second all-gather of the outcome).
+// ---------------------------------------------------------------------------------------------
+typedef int (*fn_AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t);
+
+static void peer_close(tgpu_ctx *h)
+{
+    if (h->peer) {
+        for (int r = 0; r < h->size0; r++)
+            if (h->peer[r].open) for (int a = 0; a < 10; a++) if (h->peer[r].base[a]) cudaIpcCloseMemHandle(h->peer[r].base[a]);
+        delete[] h->peer; h->peer = nullptr;
+    }
+}
+
+int comm_peer_setup(tgpu_ctx *h)
+{
+    h->peer = nullptr; h->xseq = 0;
+    const char *off = getenv("TGPU_NO_PEER");
+    int want = h->opt_peer && !(off && off[0] == '1');
+    fn_AllGather AllGather = (fn_AllGather)dlsym(N.lib, "ncclAllGather");
+    if (!AllGather) want = 0;
+    const int n = h->size0;
+    struct Pack { cudaIpcMemHandle_t hd[10]; int ok; int pad[15]; };
+    Pack mine; memset(&mine, 0, sizeof mine);
+    mine.ok = want;
+    if (want && !h->sig) {
+        if (cudaMalloc((void **)&h->sig, 64 * sizeof(uint32_t)) != cudaSuccess || cudaMemset(h->sig, 0, 64 * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+    }
+    for (int a = 0; a < 9 && mine.ok; a++) if (cudaIpcGetMemHandle(&mine.hd[a], h->f[a]) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+    if (mine.ok && cudaIpcGetMemHandle(&mine.hd[9], h->sig) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+    if (!AllGather) return 0;                                 // (every rank loads the same NCCL: same decision everywhere)
+    Pack *dsend = nullptr, *drecv = nullptr;
+    std::vector<Pack> all(n);
+    CK(cudaMalloc((void **)&dsend, sizeof(Pack))); CK(cudaMalloc((void **)&drecv, sizeof(Pack) * n));
+    auto gather = [&]() -> int {
+        CK(cudaMemcpyAsync(dsend, &mine, sizeof(Pack), cudaMemcpyHostToDevice, h->stream));
+        NCK(AllGather(dsend, drecv, sizeof(Pack), /*ncclInt8*/ 0, (nccl_comm_t)h->nccl_main, h->stream));
+        CK(cudaMemcpyAsync(all.data(), drecv, sizeof(Pack) * n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    };
+    int rc = gather();
+    if (rc) { cudaFree(dsend); cudaFree(drecv); return rc; }
+    int all_ok = 1;
+    for (int r = 0; r < n; r++) all_ok &= all[r].ok;
+    if (all_ok) {
+        h->peer = new PeerRank[n];
+        memset(h->peer, 0, sizeof(PeerRank) * n);
+        const tgpu_params &P = h->P;
+        for (int dir = 0; dir < 6 && mine.ok; dir++) {
+            const int axis = dir / 2;
+            if (axis == 2 && P.dim == 2) continue;
+            const int sz = axis == 0 ? P.sizex : axis == 1 ? P.sizey : P.sizez;
+            if (sz == 1) continue;
+            const int r = topo_neighbour(P.rank, P.sizex, P.sizey, P.sizez, dir);
+            if (r == P.rank || h->peer[r].open) continue;
+            for (int a = 0; a < 10 && mine.ok; a++) {
+                void *ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, all[r].hd[a], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; break; }
+                h->peer[r].base[a] = ptr;
+                if (a < 9) h->peer[r].f[a] = (float *)ptr; else h->peer[r].sig = (uint32_t *)ptr;
+            }
+            h->peer[r].open = 1;
+        }
+    } else mine.ok = 0;
+    // second round: did every rank manage to map its neighbours?
+    rc = gather();
+    cudaFree(dsend); cudaFree(drecv);
+    if (rc) return rc;
+    all_ok = 1;
+    for (int r = 0; r < n; r++) all_ok &= all[r].ok;
+    if (!all_ok) peer_close(h);
+    return 0;
+}
+
+int comm_peer_check(tgpu_ctx *h)
+{
+    if (!h->peer || !h->sig) return 0;
+    uint32_t t = 0;
+    CK(cudaMemcpy(&t, h->sig + TGPU_SIG_TIMEOUT, sizeof t, cudaMemcpyDeviceToHost));
+    if (t) { tgpu_set_error("halo exchange: timed out waiting for a neighbouring rank"); return TGPU_ENCCL; }
     return 0;
 }
 
 int comm_destroy(tgpu_ctx *h)
 {
+    peer_close(h);
+    if (h->sig) { cudaFree(h->sig); h->sig = nullptr; }
     if (h->nccl_main && N.CommDestroy) N.CommDestroy((nccl_comm_t)h->nccl_main);
     if (h->nccl_prt && N.CommDestroy) N.CommDestroy((nccl_comm_t)h->nccl_prt);
     h->nccl_comm = h->nccl_main = h->nccl_prt = nullptr;

@@ -439,6 +439,111 @@ static int box_shift(tgpu_ctx *h, Arr3 A, Box src, Box dst, int axis, int dir_to
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Halo step over peer memory (comm.cu comm_peer_setup).  Exchange number s of the run, on a split axis:
+//   1. k_sig_set:  READY = s in my own signal words, stream-ordered after everything I produced for this step;
+//   2. k_box_pull: for each of my two neighbours, wait until ITS READY reaches s (ld.acquire.sys over NVLink), then read the
+//      layers it would have sent me straight out of its arrays and store (ghost refresh) or add (current fold) them;
+//   3. k_sig_sync: PULLED = s in my words, then wait until both neighbours' PULLED reach s -- they read my arrays in
+//      their step 2, and what follows on my stream may overwrite those layers.
+// Every rank runs the same sequence of steps (SPMD), so one counter per rank is enough.  No pack / unpack buffers and no
+// NCCL call: three small launches per axis.  A wait gives up after 5 s and raises TGPU_SIG_TIMEOUT instead of hanging.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+__device__ __forceinline__ void sig_wait(const uint32_t *flag, uint32_t seq, uint32_t *timeout)
+{
+    const unsigned long long t0 = global_ns();
+    while ((int)(ld_acquire_sys(flag) - seq) < 0) {
+        if (global_ns() - t0 > 5000000000ull) { *timeout = 1u; return; }
+        __nanosleep(64);
+    }
+}
+__global__ void k_sig_set(uint32_t *flag, uint32_t seq)
+{
+    __threadfence_system();
+    st_release_sys(flag, seq);
+}
+__global__ void k_sig_sync(uint32_t *sig, uint32_t seq, const uint32_t *nb_a, const uint32_t *nb_b)
+{
+    __threadfence_system();
+    st_release_sys(sig + TGPU_SIG_PULLED, seq);
+    if (nb_a) sig_wait(nb_a + TGPU_SIG_PULLED, seq, sig + TGPU_SIG_TIMEOUT);
+    if (nb_b) sig_wait(nb_b + TGPU_SIG_PULLED, seq, sig + TGPU_SIG_TIMEOUT);
+}
+struct PullBox {
+    Box src, dst;              // src in the neighbour's index space, dst in mine; same extents
+    const float *rem[3];       // the neighbour's three arrays
+    int rmx, rmy;              // its x and y extents (strides)
+    const uint32_t *nb_sig;    // its signal words
+    unsigned long long total;  // 3 * volume; 0 = nothing to pull from this side
+};
+// blockIdx.y = 0 / 1: the box that comes from the lower / upper neighbour.  mode 0: dst = src ; 1: dst += src
+__global__ void __launch_bounds__(256) k_box_pull(Arr3 A, PullBox lo, PullBox hi, int mx, int my, int mode, uint32_t seq, uint32_t *sig)
+{
+    const PullBox &b = blockIdx.y ? hi : lo;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((size_t)blockIdx.x * blockDim.x >= b.total) return;
+    if (threadIdx.x == 0) sig_wait(b.nb_sig + TGPU_SIG_READY, seq, sig + TGPU_SIG_TIMEOUT);
+    __syncthreads();
+    if (idx >= b.total) return;
+    int c, i, j, k; box_decode(b.src, idx, c, i, j, k);
+    const size_t ls = (size_t)(b.src.lo[0] + i - 1) + (size_t)b.rmx * ((size_t)(b.src.lo[1] + j - 1) + (size_t)b.rmy * (size_t)(b.src.lo[2] + k - 1));
+    const size_t ld = LIDX(b.dst.lo[0] + i, b.dst.lo[1] + j, b.dst.lo[2] + k);
+    const float v = __ldcv(b.rem[c] + ls);              // never a stale line of an earlier step
+    if (mode) A.a[c][ld] = A.a[c][ld] + v; else A.a[c][ld] = v;
+}
+
+static const std::vector<int> &axis_extents(const tgpu_ctx *h, int axis) { return axis == 0 ? h->mxl : axis == 1 ? h->myl : h->mzl; }
+
+// One halo step on `axis` for the three arrays first..first+2.  The data that travels UP is the box of n_up layers that
+// starts at layer (up_from_m ? m_sender + up_off : up_off) of the sender and lands at layer dst_up of the receiver; same
+// for DOWN.  recv_*: whether this rank takes what arrives from below / above (open boundaries, edge ranks).
+static int halo_step(tgpu_ctx *h, int first, int axis, int n_up, bool up_from_m, int up_off, int dst_up, int recv_from_below,
+                     int n_dn, bool dn_from_m, int dn_off, int dst_dn, int recv_from_above, int mode)
+{
+    const tgpu_params &P = h->P;
+    const int below = topo_neighbour(P.rank, P.sizex, P.sizey, P.sizez, 2 * axis);
+    const int above = topo_neighbour(P.rank, P.sizex, P.sizey, P.sizez, 2 * axis + 1);
+    Arr3 A; for (int c = 0; c < 3; c++) A.a[c] = h->f[first + c];
+    const uint32_t seq = ++h->xseq;
+    k_sig_set<<<1, 1, 0, h->stream>>>(h->sig + TGPU_SIG_READY, seq); CKK(h);
+    PullBox pb[2];
+    for (int side = 0; side < 2; side++) {
+        PullBox &b = pb[side];
+        const int nb = side ? above : below;
+        const PeerRank &R = h->peer[nb];
+        b.src = full_box(h); b.dst = full_box(h);
+        const int m_nb = axis_extents(h, axis)[nb];
+        // from below comes what the lower neighbour sends UP; from above what the upper neighbour sends DOWN
+        const int n = side ? n_dn : n_up;
+        b.src.lo[axis] = side ? (dn_from_m ? m_nb + dn_off : dn_off) : (up_from_m ? m_nb + up_off : up_off);
+        b.dst.lo[axis] = side ? dst_dn : dst_up;
+        b.src.n[axis] = b.dst.n[axis] = n;
+        for (int c = 0; c < 3; c++) b.rem[c] = R.f[first + c];
+        b.rmx = h->mxl[nb]; b.rmy = h->myl[nb];
+        b.nb_sig = R.sig;
+        b.total = (side ? recv_from_above : recv_from_below) ? (unsigned long long)box_total(b.src) : 0ull;
+    }
+    const unsigned long long tmax = pb[0].total > pb[1].total ? pb[0].total : pb[1].total;
+    if (tmax) {
+        dim3 grid((unsigned)cdiv((long long)tmax, 256), 2);
+        k_box_pull<<<grid, 256, 0, h->stream>>>(A, pb[0], pb[1], P.mx, P.my, mode, seq, h->sig); CKK(h);
+    }
+    k_sig_sync<<<1, 1, 0, h->stream>>>(h->sig, seq, h->peer[below].sig, above != below ? h->peer[above].sig : nullptr); CKK(h);
+    return 0;
+}
+
 // bc_b1 / bc_e1: for iter = 1..g: low ghost g+1-iter <- (-nbr) m-(g+iter); high ghost m-g-1+iter <- (+nbr) g+iter.
 // All g layers of one side move as one box: [1..g] <- [m-2g..m-g-1], [m-g..m-1] <- [g+1..2g].  Axis order x,y,z with
 // full extents in the other axes so that corners propagate (fieldboundaries.F90:186-262).
@@ -451,6 +556,21 @@ int fld_bc(tgpu_ctx *h, int first)
         if (!per && sz == 1 && axis != 2) continue;           // bc_b1: no copy at all
         if (!per && sz == 1 && axis == 2) continue;           // copy_layrz2 on a single rank: both receives skipped
         Box src = full_box(h), dst = full_box(h);
+        if (sz > 1 && h->peer) {
+            // over peer memory: the low ghosts [1, g] are the lower neighbour's layers [m' - 2g, m' - g - 1] (m' = its extent),
+            // the high ghosts [m - g, m - 1] the upper neighbour's [g + 1, 2g]; layer by layer on a narrow axis
+            const int r_lo = per || pos != 0, r_hi = per || pos != sz - 1;
+            if (m - 2 * g - 1 < g) {
+                for (int iter = 1; iter <= g; iter++) {
+                    int rc = halo_step(h, first, axis, 1, true, -(g + iter), g + 1 - iter, r_lo, 1, false, g + iter, m - g - 1 + iter, r_hi, 0);
+                    if (rc) return rc;
+                }
+            } else {
+                int rc = halo_step(h, first, axis, g, true, -2 * g, 1, r_lo, g, false, g + 1, m - g, r_hi, 0);
+                if (rc) return rc;
+            }
+            continue;
+        }
         if (m - 2 * g - 1 < g) {
             // fewer interior cells than ghost layers (user/input.twostream: my0 = 2): the outer ghost layers are images of
             // layers that are ghosts themselves, so the reference's layer-by-layer order matters (do iter = 1, nghost/2 ...)
@@ -489,6 +609,13 @@ int fld_fold(tgpu_ctx *h)
         int ng = axis == 2 ? h->P.nghostz : h->P.nghost;
         if (sz == 1 && !per) continue;
         Box src = full_box(h), dst = full_box(h);
+        if (sz > 1 && h->peer && m - ng >= g + 1) {
+            // the lower neighbour's high ghosts [m' - g, m'] are added to my [g + 1, nghost]; the upper neighbour's low ghosts
+            // [1, g] to my [m - nghost + 1, m - g - 1].  Sources (ghosts) and targets (interior) are disjoint: one step.
+            int rc = halo_step(h, 6, axis, g + 1, true, -g, g + 1, per || pos != 0, g, false, 1, m - (ng - 1), per || pos != sz - 1, 1);
+            if (rc) return rc;
+            continue;
+        }
         const bool overlap = m - ng < g + 1;                  // narrow axis: the target layers reach into the source ghosts
         src.lo[axis] = m - g; src.n[axis] = g + 1; dst.lo[axis] = g + 1; dst.n[axis] = g + 1;
         int rc = box_shift(h, A, src, dst, axis, +1, 1, per || pos != 0, overlap);
@@ -562,6 +689,11 @@ int fld_filter1(tgpu_ctx *h)
             Box src = full_box(h), dst = full_box(h);
             src.n[axis] = dst.n[axis] = 1;
             // (lt,ls,nt,ns) = (g, m-g-1, m-g, g+1); copy_layr*2_opt on open axes skips the outer receive
+            if (sz > 1 && h->peer) {
+                int rc = halo_step(h, 6, axis, 1, true, -ga - 1, ga, per || pos != 0, 1, false, ga + 1, m - ga, per || pos != sz - 1, 0);
+                if (rc) return rc;
+                continue;
+            }
             src.lo[axis] = m - ga - 1; dst.lo[axis] = ga;
             int rc = box_shift(h, A, src, dst, axis, +1, 0, per || pos != 0);
             if (rc) return rc;
@@ -714,6 +846,32 @@ __global__ void __launch_bounds__(256) k_f2_pack(const float *__restrict__ cur, 
     buf[idx] = cur[f2_addr(f, first_cell + p, q1, q2)];
 }
 
+// filter2 deep halo over peer memory: my low halo is the last nt interior layers of the lower neighbour, my high halo the
+// first nt of the upper one (optimized_filters.F90:1665-1674, 1838-1847), read straight out of their cur arrays in the
+// [line][p] order k_filter2 wants.  blockIdx.y = 2 * component + side.
+struct F2Pull {
+    const float *rem[2][3]; float *buf[2][3];
+    int first[2], rmx[2], rmy[2], on[2];
+    const uint32_t *nb_sig[2];
+};
+__global__ void __launch_bounds__(256) k_f2_pull(F2 f, F2Pull a, uint32_t seq, uint32_t *sig)
+{
+    const int side = blockIdx.y & 1, c = blockIdx.y >> 1;
+    if (!a.on[side]) return;
+    if (threadIdx.x == 0) sig_wait(a.nb_sig[side] + TGPU_SIG_READY, seq, sig + TGPU_SIG_TIMEOUT);
+    __syncthreads();
+    const size_t total = (size_t)f.nt * f.q_n[0] * f.q_n[1];
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    // thread order follows the REMOTE array (x fastest) so that the NVLink reads are whole lines; the scattered side is the
+    // local store into the [line][p] order k_filter2 reads (a strided remote read was measured 2.5x slower than NCCL)
+    int p, q1, q2;
+    if (f.axis == 0) { p = (int)(idx % f.nt); const int line = (int)(idx / f.nt); q1 = line % f.q_n[0]; q2 = line / f.q_n[0]; }
+    else { q1 = (int)(idx % f.q_n[0]); const size_t r = idx / f.q_n[0]; p = (int)(r % f.nt); q2 = (int)(r / f.nt); }
+    F2 fr = f; fr.mx = a.rmx[side]; fr.my = a.rmy[side];
+    a.buf[side][c][(size_t)p + (size_t)f.nt * (q1 + (size_t)f.q_n[0] * q2)] = __ldcv(a.rem[side][c] + f2_addr(fr, a.first[side] + p, q1, q2));
+}
+
 int fld_filter2(tgpu_ctx *h)
 {
     const tgpu_params &P = h->P;
@@ -740,6 +898,28 @@ int fld_filter2(tgpu_ctx *h)
             if (12 * cnt > h->halo_floats) { tgpu_set_error("halo scratch too small for filter2"); return TGPU_EINVAL; }
             int up = topo_neighbour(P.rank, P.sizex, P.sizey, P.sizez, 2 * axis + 1);
             int dn = topo_neighbour(P.rank, P.sizex, P.sizey, P.sizez, 2 * axis);
+            if (h->peer) {
+                F2Pull a;
+                for (int side = 0; side < 2; side++) {
+                    const int nb = side ? up : dn;
+                    const int m_nb = axis_extents(h, axis)[nb];
+                    for (int c = 0; c < 3; c++) {
+                        a.rem[side][c] = h->peer[nb].f[6 + c];
+                        a.buf[side][c] = h->halo + (4 * c + 2 + side) * cnt;
+                    }
+                    // lower neighbour: its last nt interior layers; upper neighbour: its first nt
+                    a.first[side] = side ? f.str : f.str + (m_nb - 2 * g - 1) - f.nt;
+                    a.rmx[side] = h->mxl[nb]; a.rmy[side] = h->myl[nb];
+                    a.on[side] = side ? (per || pos != sz - 1) : (per || pos != 0);
+                    a.nb_sig[side] = h->peer[nb].sig;
+                }
+                for (int c = 0; c < 3; c++) { hlo_c[c] = a.buf[0][c]; hhi_c[c] = a.buf[1][c]; }
+                const uint32_t seq = ++h->xseq;
+                k_sig_set<<<1, 1, 0, h->stream>>>(h->sig + TGPU_SIG_READY, seq); CKK(h);
+                k_f2_pull<<<dim3(cdiv(cnt, 256), 6), 256, 0, h->stream>>>(f, a, seq, h->sig); CKK(h);
+                // the neighbours read my cur before I filter it in place
+                k_sig_sync<<<1, 1, 0, h->stream>>>(h->sig, seq, h->peer[dn].sig, up != dn ? h->peer[up].sig : nullptr); CKK(h);
+            } else {
             for (int c = 0; c < 3; c++) {
                 float *s_up = h->halo + (4 * c) * cnt, *s_dn = h->halo + (4 * c + 1) * cnt;
                 hlo_c[c] = h->halo + (4 * c + 2) * cnt; hhi_c[c] = h->halo + (4 * c + 3) * cnt;
@@ -754,6 +934,7 @@ int fld_filter2(tgpu_ctx *h)
                 comm_send(h, s_dn, cnt * 4, dn); comm_recv(h, hhi_c[c], cnt * 4, up);
             }
             rc = comm_group_end(h); if (rc) return rc;
+            }
             f.lowmode = (per || pos != 0) ? 1 : 2;
             f.highmode = (per || pos != sz - 1) ? 1 : 2;
         }

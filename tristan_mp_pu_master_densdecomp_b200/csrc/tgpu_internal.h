@@ -36,6 +36,18 @@ struct DevGeom {             // passed by value to kernels
     int mxcum, mycum, mzcum;
 };
 
+// Peer-memory halo transport (comm.cu comm_peer_setup, fields.cu halo_step): the nine field arrays and two signal words
+// of every neighbouring rank are mapped into this process with cudaIpc, and the halo kernels read them over NVLink.
+struct PeerRank {
+    float *f[9];             // the neighbour's ex..bz, curx..curz
+    uint32_t *sig;           // its signal words (TGPU_SIG_*)
+    void *base[10];          // what cudaIpcOpenMemHandle returned (for cudaIpcCloseMemHandle)
+    int open;
+};
+#define TGPU_SIG_READY 0     // "everything I produce before exchange number s is in memory"
+#define TGPU_SIG_PULLED 1    // "I have finished reading my neighbours' arrays for exchange number s"
+#define TGPU_SIG_TIMEOUT 2   // set by a kernel that gave up waiting (5 s): the job is broken, reported at the next host sync
+
 struct tgpu_ctx {
     tgpu_params P;
     DevGeom G;
@@ -79,6 +91,10 @@ struct tgpu_ctx {
     int opt_overlap;
     void *nccl_comm;         // ncclComm_t used on `stream` (normally == nccl_main)
     void *nccl_main, *nccl_prt;   // two communicators: NCCL calls from two streams must not share one
+    PeerRank *peer;          // [size0]; null = halo exchanges go through NCCL send/recv
+    uint32_t *sig;           // own signal words (device memory, mapped by the neighbours)
+    uint32_t xseq;           // exchange counter: every rank runs the same sequence of halo steps
+    int opt_peer;
     int lap;
     int64_t launches;
     double phase_ms[TGPU_NPHASE];
@@ -145,3 +161,5 @@ int comm_send(tgpu_ctx *h, const void *buf, size_t bytes, int peer);
 int comm_recv(tgpu_ctx *h, void *buf, size_t bytes, int peer);
 int topo_neighbour(int rank, int sx, int sy, int sz, int dir);
 int topo_neighbour2(const tgpu_ctx *h, int da, int db);   // neighbour over the two decomposed axes
+int comm_peer_setup(tgpu_ctx *h);     // map the neighbours' arrays (cudaIpc); all ranks or none
+int comm_peer_check(tgpu_ctx *h);     // TGPU_ENCCL if a halo kernel timed out waiting for a neighbour
