@@ -170,6 +170,7 @@ def measured_peak():
 def cpu_leg(cells, steps, warmup):
     """cells = (nx, ny_per_slab, nz_per_slab): one y/z slab per host thread (filter2 needs slabs at least ntimes thick)"""
     from oracle import oracle as O
+    O.use_timing_build()                                   # -O3 -march=native (timing only; parity uses the -O2 no-contraction build)
     cores = os.cpu_count() or 1
     sy = sz = 1
     while sy * sz * 2 <= cores:
@@ -197,14 +198,20 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    val, cores, npart, sec, cc = cpu_leg(args.cpu_cells, steps, min(args.warmup, 1))
-    sample = f"3D Weibel dd2 {PPC:g} ppc filter2 ntimes={NTIMES}, {cc[0]}x{cc[1]}x{cc[2]} cells " \
-             f"({npart} particles), {steps} laps, one y/z slab per OpenMP thread"
+    # same step and warm-up counts as the GPU arm (a lap of the sample takes about a second on 16 cores); capped so that
+    # an unusually long request still ends within minutes
+    steps, warmup = max(1, min(args.steps, 40)), max(0, min(args.warmup, 10))
+    val, cores, npart, sec, cc = cpu_leg(args.cpu_cells, steps, warmup)
+    sample = f"3D Weibel dd{ORDER} {PPC:g} ppc filter2 ntimes={NTIMES}, {cc[0]}x{cc[1]}x{cc[2]} cells " \
+             f"({npart} particles), {steps} laps after {warmup} warm-up, one y/z slab per OpenMP thread, {cores} threads, " \
+             f"gcc -O3 -march=native"
+    cfg = workload_config(args, args.gpus)
+    # the workload is the GPU arm's; what this arm actually steps is a bounded sample of it, stated here and in cpu_baseline
+    cfg["sample"] = f"bounded sample: {cc[0]}x{cc[1]}x{cc[2]} cells, {npart} particles (throughput is per particle-step, size-independent)"
     line = {"impl": "reference", "metric": "particle-steps/sec", "value": val, "unit": "particle-steps/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, args.gpus),
+            "config": cfg,
             "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = CPU oracle restatement of the Fortran routines (no Fortran/MPI toolchain in this image)"}
@@ -394,8 +401,9 @@ def main():
     if not args.no_cpu and world == 1:
         val, cores, npc, sec, cc = cpu_leg(args.cpu_cells, 2, 1)
         cpu = {"value": val, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-               "sample": f"{cc[0]}x{cc[1]}x{cc[2]} cells, {npc} particles, 2 laps, same "
-                         f"physics (dd2, {PPC:g} ppc, filter2 ntimes={NTIMES}); oracle restatement, one slab per thread"}
+               "sample": f"{cc[0]}x{cc[1]}x{cc[2]} cells, {npc} particles, 2 laps after 1 warm-up, same "
+                         f"physics (dd{ORDER}, {PPC:g} ppc, filter2 ntimes={NTIMES}); oracle restatement built -O3 -march=native, "
+                         f"one y/z slab per OpenMP thread, {cores} threads"}
     line = {"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": n, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "ns_per_particle_step": 1e9 / value * n,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

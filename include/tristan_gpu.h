@@ -74,7 +74,6 @@ typedef struct tgpu_params {
     int32_t external_fields;     /* constant external field model of get_external_fields */
     float ext[6];                /* ex,ey,ez,bx,by,bz */
     int32_t device;              /* CUDA device ordinal, or -1 for rank % device_count */
-    int32_t sort_every;          /* counting-sort cadence in laps for tgpu_step (reference: 10; 0 = library default) */
     int32_t highorder;           /* <algorithm> highorder: 1 = 4th-order `_42` field solver (fields.F90:1039-1361, dispatch :1407-1440) */
     int32_t wall_i2;             /* `wall` clamp of the _42 solver's x range, int(xinject2)+10 (fields.F90:1062-1065); 0 = no wall */
 } tgpu_params;

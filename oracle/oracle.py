@@ -46,13 +46,36 @@ def build(force=False):
 
 
 _lib = None
+_which = _LIB
+
+
+def use_timing_build():
+    """bench.py only: load the -O3 -march=native build (libpic_oracle_fast.so) instead of the bit-faithful -O2
+    -ffp-contract=off one.  Must be called before the first use of the library in this process."""
+    global _which
+    if _lib is not None:
+        raise RuntimeError("oracle library already loaded")
+    # -march=native code must be compiled on the machine that runs it (the repo snapshot travels to the GPU box with its
+    # built artefacts): one build per CPU model, keyed by a hash of the model name and flags
+    import hashlib
+    try:
+        info = [l for l in open("/proc/cpuinfo") if l.startswith(("model name", "flags"))][:2]
+    except OSError:
+        info = []
+    tag = hashlib.sha1("".join(info).encode()).hexdigest()[:10]
+    fast = os.path.join(_HERE, f"libpic_oracle_fast_{tag}.so")
+    src = os.path.join(_HERE, "pic_oracle.c")
+    if not os.path.exists(fast) or os.path.getmtime(fast) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "libpic_oracle_fast.so"])
+        os.replace(os.path.join(_HERE, "libpic_oracle_fast.so"), fast)
+    _which = fast
 
 
 def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(_LIB)
+        L = C.CDLL(_which)
         vp, ci, cf = C.c_void_p, C.c_int, C.c_float
         L.orc_world_create.restype = vp
         L.orc_world_create.argtypes = [C.POINTER(Params)]

@@ -13,7 +13,7 @@ A plan is a list of Shift(axis, direction, src_lo, src_hi, dst_lo, dst_hi, mode,
 """
 from collections import namedtuple
 
-from . import neighbour
+from tristan_mp_pu_master_densdecomp_b200 import neighbour
 
 Shift = namedtuple("Shift", "axis direction src_lo src_hi dst_lo dst_hi mode recv_ok arrays")
 

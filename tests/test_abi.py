@@ -87,3 +87,16 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(base, f)).read()
                 assert "pic_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_fortran_bridge_is_in_step_with_the_header():
+    """host/gpu_bridge.F90 (the ISO_C_BINDING module the Fortran driver uses) is generated from include/tristan_gpu.h:
+    regenerating it must reproduce the committed file, and every exported symbol must have an interface in it"""
+    import subprocess
+    import sys
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "scripts", "gen_gpu_bridge.py"), "--check"]) == 0, \
+        "host/gpu_bridge.F90 is stale: run scripts/gen_gpu_bridge.py"
+    f90 = open(os.path.join(ROOT, "host", "gpu_bridge.F90")).read()
+    import tristan_mp_pu_master_densdecomp_b200 as tgm
+    for sym in tgm.ABI_SYMBOLS:
+        assert f'bind(C, name="{sym}")' in f90, sym

@@ -2,7 +2,7 @@
 
 Each process owns ONE rank of a two-rank decomposition: it runs the per-rank phases of a lap on its slab and performs
 every exchange (ghost refresh, current fold, filter halos, particle migration incl. the second corner round) through
-tristan_mp_pu_master_densdecomp_b200.slabs plans over gloo send/recv.  The result must equal, bit for bit, the same
+tests/slabs.py plans over gloo send/recv.  The result must equal, bit for bit, the same
 rank of the in-process multi-rank oracle world (which moves the same boxes with memcpy)."""
 import ctypes as C
 import os
@@ -123,7 +123,7 @@ def _worker(rank, world, port, case, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        import tristan_mp_pu_master_densdecomp_b200.slabs as slabs
+        import slabs
         kw = dict(ppc=3.0, ntimes=3, delgam=0.05)
         kw.update(case)
         mine = T.oracle_world(**kw)          # this process drives rank `rank` of this copy over gloo

@@ -41,7 +41,7 @@ class Params(C.Structure):
                 ("mxl", C.POINTER(C.c_int32)), ("myl", C.POINTER(C.c_int32)), ("mzl", C.POINTER(C.c_int32)),
                 ("maxptl", C.c_int32), ("buffsize", C.c_int32), ("quirks", C.c_int32), ("pusher", C.c_int32),
                 ("external_fields", C.c_int32), ("ext", C.c_float * 6),
-                ("device", C.c_int32), ("sort_every", C.c_int32),
+                ("device", C.c_int32),
                 ("highorder", C.c_int32), ("wall_i2", C.c_int32)]
 
 
@@ -182,7 +182,6 @@ def make_params(dim=3, order=2, mx0=32, my0=32, mz0=32, sizex=1, sizey=1, sizez=
     for i in range(6):
         P.ext[i] = 0.0 if ext is None else ext[i]
     P.device = device
-    P.sort_every = 0
     P.highorder, P.wall_i2 = highorder, wall_i2
     return P
 
