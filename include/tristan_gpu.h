@@ -125,6 +125,10 @@ int tgpu_bc_b1(tgpu_ctx *h);                      /* fieldboundaries.F90:181-263
 int tgpu_bc_e1(tgpu_ctx *h);                      /* fieldboundaries.F90:306-392 */
 int tgpu_bc_b2(tgpu_ctx *h);                      /* :274-295, 493-606: radiation `surface` on radiating axes, then bc_b1 */
 int tgpu_bc_e2(tgpu_ctx *h);                      /* :403-426: `surface` (low faces, E<->B), then bc_e1 */
+int tgpu_pre_bc_b(tgpu_ctx *h);                   /* :114-131: preledge x3 + bc_b1 when all three axes of a 3D box radiate; else no-op */
+int tgpu_post_bc_b(tgpu_ctx *h);                  /* :437-452: postedge x3 + bc_b1, same condition (bodies :2200-2505) */
+int tgpu_pre_bc_e(tgpu_ctx *h);                   /* :148-163: preledge x3 (E <-> B, mirrored strides) + bc_e1 */
+int tgpu_post_bc_e(tgpu_ctx *h);                  /* :463-482: postedge x3 + bc_e1 */
 int tgpu_exchange_current(tgpu_ctx *h);           /* fieldboundaries.F90:1768-2189 */
 
 /* ---- filter: code/filter.F90, code/optimized_filters.F90 ------------------------------------- */

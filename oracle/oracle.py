@@ -18,6 +18,7 @@ ARR_NAMES = ["ex", "ey", "ez", "bx", "by", "bz", "curx", "cury", "curz"]
 (PH_BC_B1, PH_BC_E1, PH_BHALF, PH_MOVE, PH_EFULL, PH_RESET, PH_DEPOSIT, PH_EXCH_P, PH_EXCH_CUR,
  PH_FILTER, PH_ADD_CUR, PH_INJECT_OTHERS, PH_REORDER) = range(13)
 PH_SURF_B, PH_SURF_E = 100, 101   # the `surface` part of bc_b2 / bc_e2 (radiating axes)
+PH_PRE_B, PH_POST_B, PH_PRE_E, PH_POST_E = 102, 103, 104, 105   # preledge / postedge groups of an all-open 3D box
 Q_REFERENCE = 0xF
 
 PARTICLE_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4"), ("u", "f4"), ("v", "f4"), ("w", "f4"),
@@ -94,6 +95,7 @@ def lib():
                      "orc_deposit_particles", "orc_inject_others", "orc_reorder_particles",
                      "orc_filter1_pass", "orc_surface_b", "orc_surface_e"]:
             getattr(L, name).argtypes = [vp]
+        L.orc_edges.argtypes = [vp, ci]
         L.orc_deposit_one.argtypes = [vp] + [cf] * 7
         L.orc_mover_range.argtypes = [vp, ci, ci, cf]
         L.orc_bc_fields.argtypes = [vp, ci]

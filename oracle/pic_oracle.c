@@ -548,6 +548,93 @@ void orc_surface_e(orc_rank *r)
 }
 
 /* ------------------------------------------------------------------------- */
+/* edge fixes of an all-open 3D box: preledge (fieldboundaries.F90:2200-2244) and */
+/* postedge (:2371-2407), called three times each with rotated arrays by          */
+/* pre_bc_b / post_bc_b / pre_bc_e / post_bc_e (:114-163, 437-482) when all three  */
+/* axes radiate; each group is followed by bc_b1 / bc_e1.  Arguments keep the      */
+/* reference's meaning (1-based flat index n, strides ix,iy,iz, first element m).  */
+/* Only the #ifndef twoD bodies exist: the callers compile the calls out in 2D.    */
+/* ------------------------------------------------------------------------- */
+static void preledge(float *bx, float *by, float *bz, const float *ex, const float *ey, const float *ez,
+                     long ix, long iy, long iz, int mx, int my, int mz, long m, float c)
+{
+#define A1(a, n) (a)[(n) - 1]
+    const float s = .4142136f;
+    const float t = c / (2.f * c + 1.f + s);
+    for (long n = m + iy * (my - 1) + iz * (mz - 1) + ix, q = 0; q < mx - 2; q++, n += ix)
+        A1(bx, n) = A1(bx, n - iy - iz) + (1.f - 4.f * t) * A1(bx, n) + (1.f - 2.f * t) * (A1(bx, n - iy) + A1(bx, n - iz))
+            + s * t * (A1(by, n) - A1(by, n - ix) + A1(by, n - iz) - A1(by, n - ix - iz)
+                       + A1(bz, n) - A1(bz, n - ix) + A1(bz, n - iy) - A1(bz, n - ix - iy));
+    const float r = 4.f / (2.f * c + 2.f + s);
+    for (long n = m + iz * (mz - 1), q = 0; q < my - 1; q++, n += iy)
+        A1(bx, n) = (1.f - c * r) * (A1(bx, n) + A1(bx, n + ix)) + A1(bx, n - iz) + A1(bx, n + ix - iz) - r * (A1(bz, n)
+            + c * ((1.f - s) * (A1(ex, n + iy) - A1(ex, n)) + (1.f + s) * .25f * (A1(ez, n + iy)
+            - A1(ez, n) + A1(ez, n + ix + iy) - A1(ez, n + ix) + A1(ez, n + iy - iz) - A1(ez, n - iz)
+            + A1(ez, n + ix + iy - iz) - A1(ez, n + ix - iz))));
+    for (long n = m + iy * (my - 1), q = 0; q < mz - 1; q++, n += iz)
+        A1(bx, n) = (1.f - c * r) * (A1(bx, n) + A1(bx, n + ix)) + A1(bx, n - iy) + A1(bx, n + ix - iy)
+            - r * (A1(by, n) - c * ((1.f - s) * (A1(ex, n + iz) - A1(ex, n))
+            + (1.f + s) * .25f * (A1(ey, n + iz) - A1(ey, n) + A1(ey, n + ix + iz)
+            - A1(ey, n + ix) + A1(ey, n + iz - iy) - A1(ey, n - iy) + A1(ey, n + ix + iz - iy)
+            - A1(ey, n + ix - iy))));
+    const float p = (1.f + c) * 2.f / (1.f + 2.f * c * (1.f + c * s));
+    const float q_ = c * s * 2.f / (1.f + 2.f * c * (1.f + c * s));
+    for (long n = m + iy * (my - 1) + iz * (mz - 1), q = 0; q < mx - 1; q++, n += ix) {
+        const float temp = A1(bz, n) - .5f * c * (1.f - s) * (A1(ey, n + ix) - A1(ey, n) + A1(ey, n + ix - iy) - A1(ey, n - iy));
+        A1(bz, n) = A1(bz, n - iy) - A1(bz, n) + p * temp + q_ * A1(by, n);
+        A1(by, n) = A1(by, n - iz) - A1(by, n) + p * A1(by, n) + q_ * temp;
+    }
+#undef A1
+}
+static void postedge(float *bx, float *by, float *bz, const float *ex, const float *ey, const float *ez,
+                     long ix, long iy, long iz, int mx, int my, int mz, long m, float c)
+{
+#define A1(a, n) (a)[(n) - 1]
+    const float s = .4142136f;
+    const float p = (1.f + c) * 2.f / (1.f + 2.f * c * (1.f + c * s));
+    const float q_ = c * s * 2.f / (1.f + 2.f * c * (1.f + c * s));
+    for (long n = m + iy * (my - 1) + iz * (mz - 1), q = 0; q < mx - 1; q++, n += ix) {
+        const float temp = A1(by, n - iz) - .5f * c * (1.f - s) * (A1(ez, n + ix) - A1(ez, n) + A1(ez, n + ix - iz) - A1(ez, n - iz));
+        A1(bz, n) = A1(bz, n - iy) + A1(bz, n) - q_ * temp - p * A1(bz, n - iy);
+        A1(by, n) = A1(by, n - iz) + A1(by, n) - q_ * A1(bz, n - iy) - p * temp;
+    }
+    const float t = c / (2.f * c + 1.f + s);
+    for (long n = m + iy * (my - 1) + iz * (mz - 1) + ix, q = 0; q < mx - 2; q++, n += ix)
+        A1(bx, n) = A1(bx, n) - (1.f - 4.f * t) * A1(bx, n - iy - iz) - (1.f - 2.f * t) * (A1(bx, n - iy) + A1(bx, n - iz))
+            + s * t * (A1(by, n) - A1(by, n - ix) + A1(by, n - iz) - A1(by, n - ix - iz)
+                       + A1(bz, n) - A1(bz, n - ix) + A1(bz, n - iy) - A1(bz, n - ix - iy));
+    const float r = 4.f / (2.f * c + 2.f + s);
+    for (long n = m + iz * (mz - 1), q = 0; q < my - 1; q++, n += iy)
+        A1(bx, n) = A1(bx, n) - A1(bx, n + ix) - (1.f - c * r) * (A1(bx, n - iz) + A1(bx, n + ix - iz)) + r * A1(bz, n);
+    for (long n = m + iy * (my - 1), q = 0; q < mz - 1; q++, n += iz)
+        A1(bx, n) = A1(bx, n) - A1(bx, n + ix) - (1.f - c * r) * (A1(bx, n - iy) + A1(bx, n + ix - iy)) + r * A1(by, n);
+#undef A1
+}
+/* which = 0 pre_bc_b, 1 post_bc_b, 2 pre_bc_e, 3 post_bc_e: the three edge calls (the ghost refresh that follows is
+   orc_bc_fields).  No-op unless the box is 3D with all three axes open (fieldboundaries.F90:120, 154, 442, 468). */
+void orc_edges(orc_rank *r, int which)
+{
+    if (r->P.dim != 3 || r->P.periodicx || r->P.periodicy || r->P.periodicz) return;
+    float *ex = r->f[ORC_EX], *ey = r->f[ORC_EY], *ez = r->f[ORC_EZ];
+    float *bx = r->f[ORC_BX], *by = r->f[ORC_BY], *bz = r->f[ORC_BZ];
+    const long ix = 1, iy = r->mx, iz = (long)r->mx * r->my, lot = (long)r->lot;
+    const int mx = r->mx, my = r->my, mz = r->mz;
+    const float c = r->P.c;
+    void (*f)(float *, float *, float *, const float *, const float *, const float *, long, long, long, int, int, int, long, float) =
+        (which & 1) ? postedge : preledge;
+    if (which < 2) {
+        f(by, bz, bx, ey, ez, ex, iy, iz, ix, my, mz, mx, 1, c);
+        f(bz, bx, by, ez, ex, ey, iz, ix, iy, mz, mx, my, 1, c);
+        f(bx, by, bz, ex, ey, ez, ix, iy, iz, mx, my, mz, 1, c);
+    } else {
+        f(ey, ez, ex, by, bz, bx, -iy, -iz, -ix, my, mz, mx, lot, c);
+        f(ez, ex, ey, bz, bx, by, -iz, -ix, -iy, mz, mx, my, lot, c);
+        f(ex, ey, ez, bx, by, bz, -ix, -iy, -iz, mx, my, mz, lot, c);
+    }
+}
+static int all_open(const orc_world *w) { return w->P.dim == 3 && !w->P.periodicx && !w->P.periodicy && !w->P.periodicz; }
+
+/* ------------------------------------------------------------------------- */
 /* exchange_current: fieldboundaries.F90:1768-2189                              */
 /* high ghosts m-g..m (g+1 layers) are ADDED into the +neighbour's g+1..nghost; */
 /* low ghosts 1..g are added into the -neighbour's m-nghost+1..m-g-1.           */
@@ -1455,7 +1542,7 @@ void orc_reorder_particles(orc_rank *r)
 /* user hooks and injectors are in orc_step_shock; pre/post_bc_* edge fixes of an    */
 /* all-open box (fieldboundaries.F90:120,154,442,468) are outside this restatement) */
 /* ------------------------------------------------------------------------- */
-enum { PH_SURF_B = 100, PH_SURF_E };
+enum { PH_SURF_B = 100, PH_SURF_E, PH_PRE_B, PH_POST_B, PH_PRE_E, PH_POST_E };
 enum { PH_BC_B1, PH_BC_E1, PH_BHALF, PH_MOVE, PH_EFULL, PH_RESET, PH_DEPOSIT, PH_EXCH_P, PH_EXCH_CUR,
        PH_FILTER, PH_ADD_CUR, PH_INJECT_OTHERS, PH_REORDER };
 
@@ -1483,6 +1570,10 @@ void orc_step_phase(orc_world *w, int phase)
             case PH_REORDER: orc_reorder_particles(r); break;
             case PH_SURF_B: orc_surface_b(r); break;
             case PH_SURF_E: orc_surface_e(r); break;
+            case PH_PRE_B: orc_edges(r, 0); break;
+            case PH_POST_B: orc_edges(r, 1); break;
+            case PH_PRE_E: orc_edges(r, 2); break;
+            case PH_POST_E: orc_edges(r, 3); break;
             }
         }
     }
@@ -1491,6 +1582,8 @@ void orc_step_phase(orc_world *w, int phase)
 void orc_step(orc_world *w)
 {
     w->lap++;
+    const int edges = all_open(w);        /* pre_/post_bc_* only act in an all-open 3D box */
+    if (edges) { orc_step_phase(w, PH_PRE_B); orc_step_phase(w, PH_BC_B1); }     /* :114 pre_bc_b */
     orc_step_phase(w, PH_BC_B1);          /* :117 */
     orc_step_phase(w, PH_BC_E1);          /* :118 */
     orc_step_phase(w, PH_BHALF);          /* :119 */
@@ -1500,9 +1593,12 @@ void orc_step(orc_world *w)
     orc_step_phase(w, PH_BC_B1);          /* :140 */
     orc_step_phase(w, PH_SURF_B);         /* :145 bc_b2 = surface on every radiating axis ... */
     orc_step_phase(w, PH_BC_B1);          /*      ... then bc_b1 */
+    if (edges) { orc_step_phase(w, PH_POST_B); orc_step_phase(w, PH_BC_B1); }    /* :155 post_bc_b */
+    if (edges) { orc_step_phase(w, PH_PRE_E); orc_step_phase(w, PH_BC_E1); }     /* :157 pre_bc_e */
     orc_step_phase(w, PH_EFULL);          /* :159 */
     orc_step_phase(w, PH_SURF_E);         /* :164 bc_e2 = surface ... */
     orc_step_phase(w, PH_BC_E1);          /*      ... then bc_e1 */
+    if (edges) { orc_step_phase(w, PH_POST_E); orc_step_phase(w, PH_BC_E1); }    /* :165 post_bc_e */
     orc_step_phase(w, PH_RESET);          /* :171 */
     orc_step_phase(w, PH_BC_E1);          /* :181 */
     orc_step_phase(w, PH_BC_B1);          /* :182 */

@@ -178,6 +178,7 @@ void orc_init_uniform(orc_world *w, float ppc0, float beta_drift, float uth, uin
    ghost refresh that completes bc_b2 / bc_e2 is orc_bc_fields) */
 int orc_range42_ok(const orc_params *P);   /* 0: highorder = 1 with index ranges that are out of bounds in the reference */
 void orc_surface_b(orc_rank *r);
+void orc_edges(orc_rank *r, int which);   /* 0 pre_bc_b, 1 post_bc_b, 2 pre_bc_e, 3 post_bc_e: preledge / postedge (fieldboundaries.F90:2200-2505) */
 void orc_surface_e(orc_rank *r);
 void orc_field_bc_shock(orc_rank *r, float leftwall, float binit, float btheta, float bphi, float beta);   /* :342-373 */
 void orc_particle_bc_wall(orc_rank *r, float leftwall);                                                     /* :377-457 */

@@ -105,6 +105,43 @@ def test_radiation_surface_bit_exact(tgm, dim, periodic):
     ctx.close()
 
 
+def test_edge_fixes_all_open_box_bit_exact(tgm):
+    """pre_bc_b / post_bc_b / pre_bc_e / post_bc_e in a 3D box with three radiating axes: preledge / postedge
+    (fieldboundaries.F90:2200-2505) on the three rotated edge sets, then the ghost refresh; bit-exact, and no-ops elsewhere"""
+    w, ctx = make(tgm, dim=3, order=1, n=(20, 18, 14), ppc=1.0, periodic=(0, 0, 0))
+    r = w.ranks[0]
+    for _ in range(2):
+        for name, ph, bc in (("pre_bc_b", O.PH_PRE_B, O.PH_BC_B1), ("post_bc_b", O.PH_POST_B, O.PH_BC_B1),
+                             ("pre_bc_e", O.PH_PRE_E, O.PH_BC_E1), ("post_bc_e", O.PH_POST_E, O.PH_BC_E1)):
+            getattr(ctx, name)()
+            w.phase(ph); w.phase(bc)
+            fg = ctx.fields_d2h()
+            for a in range(6):
+                assert np.array_equal(fg[a], r.arr(a)), (name, O.ARR_NAMES[a])
+    ctx.close()
+    w2, ctx2 = make(tgm, dim=3, order=1, n=(12, 10, 8), ppc=1.0, periodic=(0, 0, 1))     # z periodic: nothing happens
+    before = ctx2.fields_d2h()
+    ctx2.pre_bc_b(); ctx2.post_bc_e()
+    after = ctx2.fields_d2h()
+    for a in range(6):
+        assert np.array_equal(before[a], after[a])
+    ctx2.close()
+
+
+def test_full_lap_all_open_box(tgm):
+    """laps of a 3D box open on all three axes: surface + the edge fixes at their mainloop positions (:114, 155, 157, 165)"""
+    w, ctx = make(tgm, dim=3, order=2, n=(20, 16, 12), ppc=4.0, ntimes=2, filter_kind=1, periodic=(0, 0, 0))
+    r = w.ranks[0]
+    for lap in range(2):
+        ctx.step(1); w.step()
+        fg = ctx.fields_d2h()
+        for a in range(6):
+            assert T.max_rel(T.interior(r, fg[a]), T.interior(r, r.arr(a))) < 2e-4, (lap, O.ARR_NAMES[a])
+        assert ctx.counts() == r.counts
+        T.upload(ctx, r)
+    ctx.close()
+
+
 @pytest.mark.parametrize("dim,order", [(3, 2), (2, 1)])
 def test_full_lap_open_x(tgm, dim, order):
     """laps with an open (radiating) x axis: leavers are discarded, bc_b2 / bc_e2 run `surface`"""

@@ -363,6 +363,36 @@ def test_radiation_boundary_y_faces_3d():
     assert h[-1] < 1e-3, h[-1]
 
 
+def test_all_open_box_radiates_a_central_burst_away():
+    """3D box open on all three axes: `surface` on the six faces plus the preledge / postedge edge fixes (fieldboundaries.F90:
+    114-163, 437-482, 2200-2505) at their mainloop positions.  Known answer: a compact burst of radiation in the middle of an
+    empty box leaves through faces, edges and corners -- the field energy never grows (the edge updates are stable) and after
+    a few light-crossing times only a small remainder is left."""
+    n = (24, 24, 24)
+    w = T.oracle_world(dim=3, order=1, n=n, ppc=0.0, init="none", seed_fields=0, periodic=(0, 0, 0))
+    r = w.ranks[0]
+    g = r.nghost // 2
+    z, y, x = np.meshgrid(*[np.arange(m, dtype=np.float64) for m in (r.mz, r.my, r.mx)], indexing="ij")
+    c0 = g + 12.0
+    psi = np.exp(-((x - c0) ** 2 + (y - c0) ** 2 + (z - c0) ** 2) / (2 * 2.0 ** 2))
+    # divergence-free on the Yee mesh: E = curl(psi z^) with psi on the cell corners, so nothing electrostatic stays behind
+    r.arr(O.EX)[...] = (psi - np.roll(psi, 1, 1)).astype(np.float32)
+    r.arr(O.EY)[...] = (-(psi - np.roll(psi, 1, 2))).astype(np.float32)
+
+    def energy():
+        return float(sum((T.interior(r, r.arr(a)).astype(np.float64) ** 2).sum() for a in range(6)))
+    e0 = energy()
+    hist = []
+    for lap in range(220):                                  # 220 * 0.45 = 99 cells = four crossing times of the half box
+        w.step()
+        hist.append(energy() / e0)
+    hist = np.array(hist)
+    assert np.all(np.isfinite(hist))
+    assert hist.max() < 1.15 and hist[20:].max() < 1.0      # (E^2 + B^2 at staggered times wobbles ~10 % at the start) no growth
+    assert hist[-1] < 1e-5, hist[-1]                        # faces, edges and corners let the burst out (measured: 4e-7)
+    assert np.all(hist[100:] <= hist[99] * 1.0001)          # and nothing comes back or grows afterwards
+
+
 @pytest.mark.parametrize("highorder", [0, 1])
 @pytest.mark.parametrize("dim,axis", [(2, 0), (3, 0), (3, 1), (3, 2)])
 def test_vacuum_dispersion_of_both_field_solvers(highorder, dim, axis):

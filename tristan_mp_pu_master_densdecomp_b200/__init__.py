@@ -53,7 +53,7 @@ ABI_SYMBOLS = [
     "tgpu_add_current", "tgpu_bc_b1", "tgpu_bc_e1", "tgpu_bc_b2", "tgpu_bc_e2", "tgpu_exchange_current",
     "tgpu_apply_filter", "tgpu_apply_filter1_opt", "tgpu_apply_filter2_opt", "tgpu_move_particles",
     "tgpu_deposit_particles", "tgpu_exchange_particles", "tgpu_inject_others", "tgpu_reorder_particles",
-    "tgpu_meanq_fld_cur", "tgpu_spectrum_gamma_range", "tgpu_spectrum", "tgpu_select_particles", "tgpu_step_mirror", "tgpu_field_bc_user_shock", "tgpu_particle_bc_user_wall", "tgpu_set_user_hooks", "tgpu_step", "tgpu_timers", "tgpu_launch_count", "tgpu_stream", "tgpu_set_option", "tgpu_halo_transport",
+    "tgpu_meanq_fld_cur", "tgpu_spectrum_gamma_range", "tgpu_spectrum", "tgpu_select_particles", "tgpu_step_mirror", "tgpu_field_bc_user_shock", "tgpu_particle_bc_user_wall", "tgpu_set_user_hooks", "tgpu_step", "tgpu_timers", "tgpu_launch_count", "tgpu_stream", "tgpu_set_option", "tgpu_halo_transport", "tgpu_pre_bc_b", "tgpu_post_bc_b", "tgpu_pre_bc_e", "tgpu_post_bc_e",
 ]
 
 _lib = None
@@ -90,7 +90,8 @@ def load_library(path=None):
     for name in ["tgpu_advance_b_halfstep", "tgpu_advance_e_fullstep", "tgpu_reset_currents", "tgpu_add_current",
                  "tgpu_bc_b1", "tgpu_bc_e1", "tgpu_bc_b2", "tgpu_bc_e2", "tgpu_exchange_current", "tgpu_apply_filter",
                  "tgpu_apply_filter1_opt", "tgpu_apply_filter2_opt", "tgpu_move_particles", "tgpu_deposit_particles",
-                 "tgpu_exchange_particles", "tgpu_inject_others", "tgpu_reorder_particles"]:
+                 "tgpu_exchange_particles", "tgpu_inject_others", "tgpu_reorder_particles",
+                 "tgpu_pre_bc_b", "tgpu_post_bc_b", "tgpu_pre_bc_e", "tgpu_post_bc_e"]:
         getattr(L, name).argtypes = [vp]
     L.tgpu_field_bc_user_shock.argtypes = [vp] + [C.c_float] * 5
     L.tgpu_meanq_fld_cur.argtypes = [vp, C.c_char_p]
@@ -345,7 +346,8 @@ def _add_procedure(name):
 
 for _n in ["advance_b_halfstep", "advance_e_fullstep", "reset_currents", "add_current", "bc_b1", "bc_e1", "bc_b2",
            "bc_e2", "exchange_current", "apply_filter", "apply_filter1_opt", "apply_filter2_opt", "move_particles",
-           "deposit_particles", "exchange_particles", "inject_others", "reorder_particles"]:
+           "deposit_particles", "exchange_particles", "inject_others", "reorder_particles",
+           "pre_bc_b", "post_bc_b", "pre_bc_e", "post_bc_e"]:
     _add_procedure(_n)
 
 

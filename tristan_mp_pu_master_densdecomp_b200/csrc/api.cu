@@ -305,6 +305,19 @@ extern "C" int tgpu_bc_e2(tgpu_ctx *h)
     { PhaseTimer t(h, TGPU_PH_BC); int rc = fld_surface(h, 1); if (rc) return rc; }
     return tgpu_bc_e1(h);
 }
+// pre_bc_b / post_bc_b / pre_bc_e / post_bc_e (fieldboundaries.F90:114-163, 437-482): the preledge / postedge edge fixes
+// of a 3D box whose three axes all radiate, each followed by bc_b1 / bc_e1; no-ops otherwise, as in the reference
+static bool all_open3(const tgpu_ctx *h) { return h->P.dim == 3 && !h->P.periodicx && !h->P.periodicy && !h->P.periodicz; }
+static int edges_then_bc(tgpu_ctx *h, int which)
+{
+    if (!all_open3(h)) return 0;
+    { PhaseTimer t(h, TGPU_PH_BC); int rc = fld_edges(h, which); if (rc) return rc; }
+    return which < 2 ? tgpu_bc_b1(h) : tgpu_bc_e1(h);
+}
+extern "C" int tgpu_pre_bc_b(tgpu_ctx *h) { ENTER(h); return edges_then_bc(h, 0); }
+extern "C" int tgpu_post_bc_b(tgpu_ctx *h) { ENTER(h); return edges_then_bc(h, 1); }
+extern "C" int tgpu_pre_bc_e(tgpu_ctx *h) { ENTER(h); return edges_then_bc(h, 2); }
+extern "C" int tgpu_post_bc_e(tgpu_ctx *h) { ENTER(h); return edges_then_bc(h, 3); }
 extern "C" int tgpu_exchange_current(tgpu_ctx *h) { ENTER(h); PhaseTimer t(h, TGPU_PH_CUREXCH); return fld_fold(h); }
 extern "C" int tgpu_apply_filter1_opt(tgpu_ctx *h) { ENTER(h); PhaseTimer t(h, TGPU_PH_FILTER); return fld_filter1(h); }
 extern "C" int tgpu_apply_filter2_opt(tgpu_ctx *h) { ENTER(h); PhaseTimer t(h, TGPU_PH_FILTER); return fld_filter2(h); }
@@ -471,13 +484,16 @@ extern "C" int tgpu_step(tgpu_ctx *h, int nlaps)
         const float *q = h->hook;
         const int fused0 = h->opt_fused;
         h->lap++;
+        DO(tgpu_pre_bc_b(h));                                         // :114 (acts only in an all-open 3D box)
         DO(tgpu_bc_b1(h)); DO(tgpu_bc_e1(h)); DO(tgpu_advance_b_halfstep(h)); DO(tgpu_bc_b1(h));
         h->opt_fused = 0; rc = tgpu_move_particles(h); h->opt_fused = fused0; if (rc) { h->in_step = 0; return rc; }
         DO(tgpu_advance_b_halfstep(h)); DO(tgpu_bc_b1(h)); DO(tgpu_bc_b2(h));
         DO(fld_bc_shock(h, q[0], q[1], q[2], q[3], q[4]));            // :146
+        DO(tgpu_post_bc_b(h)); DO(tgpu_pre_bc_e(h));                  // :155, :157
         DO(tgpu_advance_e_fullstep(h));
         DO(fld_bc_shock(h, q[0], q[1], q[2], q[3], q[4]));            // :160
         DO(tgpu_bc_e2(h));
+        DO(tgpu_post_bc_e(h));                                        // :165
         DO(fld_bc_shock(h, q[0], q[1], q[2], q[3], q[4]));            // :166
         DO(tgpu_reset_currents(h));
         DO(prt_wall(h, q[0]));                                        // :177
@@ -488,6 +504,7 @@ extern "C" int tgpu_step(tgpu_ctx *h, int nlaps)
     }
     for (int l = 0; l < nlaps && h->hook_kind == 0; l++) {
         h->lap++;
+        if (rad) DO(tgpu_pre_bc_b(h));     // :114 (acts only in an all-open 3D box)
         DO(tgpu_bc_e1(h));                 // :118 (E changed by add_current)
         DO(tgpu_advance_b_halfstep(h));    // :119
         DO(tgpu_bc_b1(h));                 // :122
@@ -498,8 +515,9 @@ extern "C" int tgpu_step(tgpu_ctx *h, int nlaps)
             DO(tgpu_advance_b_halfstep(h));    // :139
             DO(tgpu_bc_b1(h));                 // :140
             if (rad) DO(tgpu_bc_b2(h));        // :145
+            if (rad) { DO(tgpu_post_bc_b(h)); DO(tgpu_pre_bc_e(h)); }   // :155, :157
             DO(tgpu_advance_e_fullstep(h));    // :159
-            if (rad) DO(tgpu_bc_e2(h));        // :164
+            if (rad) { DO(tgpu_bc_e2(h)); DO(tgpu_post_bc_e(h)); }      // :164, :165
             DO(tgpu_reset_currents(h));        // :171
             DO(fld_add_shadow(h)); h->fused_pending = 0;      // :183, current part of deposit_particles
             DO(tgpu_exchange_current(h));      // :203
@@ -518,8 +536,9 @@ extern "C" int tgpu_step(tgpu_ctx *h, int nlaps)
             DO(tgpu_advance_b_halfstep(h));    // :139
             DO(tgpu_bc_b1(h));                 // :140
             if (rad) DO(tgpu_bc_b2(h));        // :145
+            if (rad) { DO(tgpu_post_bc_b(h)); DO(tgpu_pre_bc_e(h)); }   // :155, :157
             DO(tgpu_advance_e_fullstep(h));    // :159
-            if (rad) DO(tgpu_bc_e2(h));        // :164
+            if (rad) { DO(tgpu_bc_e2(h)); DO(tgpu_post_bc_e(h)); }      // :164, :165
             DO(tgpu_reset_currents(h));        // :171
             DO(tgpu_deposit_particles(h));     // :183
             DO(tgpu_exchange_particles(h));    // :190, :257-272

@@ -1079,6 +1079,113 @@ int fld_surface(tgpu_ctx *h, int is_e)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Edge fixes of an all-open 3D box: preledge / postedge (fieldboundaries.F90:2200-2244, 2371-2407), the #ifndef twoD
+// bodies.  Each routine is four sweeps along one edge line of the rotated box; no sweep reads an element that the same
+// sweep writes at another n, so a sweep is one launch with one thread per n, and the launches follow the reference's order.
+// E1(a, n): the reference's 1-based flat index.  fields.cu is built with -fmad=false: same roundings as the oracle.
+// ---------------------------------------------------------------------------------------------
+struct EdgeArgs {
+    float *bx, *by, *bz; const float *ex, *ey, *ez;
+    long long ix, iy, iz, m; int mx, my, mz; float c;
+};
+#define E1(a, n) (a)[(n) - 1]
+template <int POST, int SWEEP>
+__global__ void __launch_bounds__(128) k_edge(EdgeArgs A)
+{
+    const long long ix = A.ix, iy = A.iy, iz = A.iz;
+    const float c = A.c, s = .4142136f;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    float *bx = A.bx, *by = A.by, *bz = A.bz; const float *ex = A.ex, *ey = A.ey, *ez = A.ez;
+    const float t = c / (2.f * c + 1.f + s), r = 4.f / (2.f * c + 2.f + s);
+    const float p = (1.f + c) * 2.f / (1.f + 2.f * c * (1.f + c * s)), q_ = c * s * 2.f / (1.f + 2.f * c * (1.f + c * s));
+    const long long corner = A.m + iy * (A.my - 1) + iz * (A.mz - 1);
+    if (SWEEP == 0) {                  // bx along x on the (y, z) = (my, mz) edge, n = corner + ix .. corner + ix*(mx-2)
+        if (q >= A.mx - 2) return;
+        const long long n = corner + ix * (q + 1);
+        const float cross = s * t * (E1(by, n) - E1(by, n - ix) + E1(by, n - iz) - E1(by, n - ix - iz)
+                                     + E1(bz, n) - E1(bz, n - ix) + E1(bz, n - iy) - E1(bz, n - ix - iy));
+        if (!POST) E1(bx, n) = E1(bx, n - iy - iz) + (1.f - 4.f * t) * E1(bx, n) + (1.f - 2.f * t) * (E1(bx, n - iy) + E1(bx, n - iz)) + cross;
+        else E1(bx, n) = E1(bx, n) - (1.f - 4.f * t) * E1(bx, n - iy - iz) - (1.f - 2.f * t) * (E1(bx, n - iy) + E1(bx, n - iz)) + cross;
+    } else if (SWEEP == 1) {           // bx along y on the z = mz face's first column
+        if (q >= A.my - 1) return;
+        const long long n = A.m + iz * (A.mz - 1) + iy * q;
+        if (!POST) E1(bx, n) = (1.f - c * r) * (E1(bx, n) + E1(bx, n + ix)) + E1(bx, n - iz) + E1(bx, n + ix - iz) - r * (E1(bz, n)
+                + c * ((1.f - s) * (E1(ex, n + iy) - E1(ex, n)) + (1.f + s) * .25f * (E1(ez, n + iy)
+                - E1(ez, n) + E1(ez, n + ix + iy) - E1(ez, n + ix) + E1(ez, n + iy - iz) - E1(ez, n - iz)
+                + E1(ez, n + ix + iy - iz) - E1(ez, n + ix - iz))));
+        else E1(bx, n) = E1(bx, n) - E1(bx, n + ix) - (1.f - c * r) * (E1(bx, n - iz) + E1(bx, n + ix - iz)) + r * E1(bz, n);
+    } else if (SWEEP == 2) {           // bx along z on the y = my face's first column
+        if (q >= A.mz - 1) return;
+        const long long n = A.m + iy * (A.my - 1) + iz * q;
+        if (!POST) E1(bx, n) = (1.f - c * r) * (E1(bx, n) + E1(bx, n + ix)) + E1(bx, n - iy) + E1(bx, n + ix - iy)
+                - r * (E1(by, n) - c * ((1.f - s) * (E1(ex, n + iz) - E1(ex, n))
+                + (1.f + s) * .25f * (E1(ey, n + iz) - E1(ey, n) + E1(ey, n + ix + iz)
+                - E1(ey, n + ix) + E1(ey, n + iz - iy) - E1(ey, n - iy) + E1(ey, n + ix + iz - iy)
+                - E1(ey, n + ix - iy))));
+        else E1(bx, n) = E1(bx, n) - E1(bx, n + ix) - (1.f - c * r) * (E1(bx, n - iy) + E1(bx, n + ix - iy)) + r * E1(by, n);
+    } else {                           // by, bz along x on the (my, mz) edge, n = corner .. corner + ix*(mx-2)
+        if (q >= A.mx - 1) return;
+        const long long n = corner + ix * q;
+        if (!POST) {
+            const float temp = E1(bz, n) - .5f * c * (1.f - s) * (E1(ey, n + ix) - E1(ey, n) + E1(ey, n + ix - iy) - E1(ey, n - iy));
+            const float byn = E1(by, n);
+            E1(bz, n) = E1(bz, n - iy) - E1(bz, n) + p * temp + q_ * byn;
+            E1(by, n) = E1(by, n - iz) - byn + p * byn + q_ * temp;
+        } else {
+            const float temp = E1(by, n - iz) - .5f * c * (1.f - s) * (E1(ez, n + ix) - E1(ez, n) + E1(ez, n + ix - iz) - E1(ez, n - iz));
+            const float bzl = E1(bz, n - iy);
+            E1(bz, n) = bzl + E1(bz, n) - q_ * temp - p * bzl;
+            E1(by, n) = E1(by, n - iz) + E1(by, n) - q_ * bzl - p * temp;
+        }
+    }
+}
+#undef E1
+template <int POST>
+static int edge_call(tgpu_ctx *h, float *bx, float *by, float *bz, const float *ex, const float *ey, const float *ez,
+                     long long ix, long long iy, long long iz, int mx, int my, int mz, long long m)
+{
+    EdgeArgs A; A.bx = bx; A.by = by; A.bz = bz; A.ex = ex; A.ey = ey; A.ez = ez; A.ix = ix; A.iy = iy; A.iz = iz; A.m = m;
+    A.mx = mx; A.my = my; A.mz = mz; A.c = h->P.c;
+    // preledge: sweeps 0, 1, 2, 3 (:2218-2243); postedge: the by/bz sweep first, then 0, 1, 2 (:2393-2413)
+    if (POST) { k_edge<POST, 3><<<cdiv(mx - 1, 128), 128, 0, h->stream>>>(A); CKK(h); }
+    if (mx > 2) { k_edge<POST, 0><<<cdiv(mx - 2, 128), 128, 0, h->stream>>>(A); CKK(h); }
+    k_edge<POST, 1><<<cdiv(my - 1, 128), 128, 0, h->stream>>>(A); CKK(h);
+    k_edge<POST, 2><<<cdiv(mz - 1, 128), 128, 0, h->stream>>>(A); CKK(h);
+    if (!POST) { k_edge<POST, 3><<<cdiv(mx - 1, 128), 128, 0, h->stream>>>(A); CKK(h); }
+    return 0;
+}
+// which = 0 pre_bc_b, 1 post_bc_b, 2 pre_bc_e, 3 post_bc_e (fieldboundaries.F90:114-163, 437-482): the three rotated edge
+// calls; the caller follows with bc_b1 / bc_e1.  Acts only in a 3D box whose three axes all radiate.
+int fld_edges(tgpu_ctx *h, int which)
+{
+    const tgpu_params &P = h->P;
+    if (P.dim != 3 || P.periodicx || P.periodicy || P.periodicz) return 0;
+    float *ex = h->f[0], *ey = h->f[1], *ez = h->f[2], *bx = h->f[3], *by = h->f[4], *bz = h->f[5];
+    const long long ix = 1, iy = P.mx, iz = (long long)P.mx * P.my, lot = h->G.lot;
+    const int mx = P.mx, my = P.my, mz = P.mz;
+    int rc = 0;
+    if (which == 0) {
+        rc |= edge_call<0>(h, by, bz, bx, ey, ez, ex, iy, iz, ix, my, mz, mx, 1);
+        rc |= edge_call<0>(h, bz, bx, by, ez, ex, ey, iz, ix, iy, mz, mx, my, 1);
+        rc |= edge_call<0>(h, bx, by, bz, ex, ey, ez, ix, iy, iz, mx, my, mz, 1);
+    } else if (which == 1) {
+        rc |= edge_call<1>(h, by, bz, bx, ey, ez, ex, iy, iz, ix, my, mz, mx, 1);
+        rc |= edge_call<1>(h, bz, bx, by, ez, ex, ey, iz, ix, iy, mz, mx, my, 1);
+        rc |= edge_call<1>(h, bx, by, bz, ex, ey, ez, ix, iy, iz, mx, my, mz, 1);
+    } else if (which == 2) {
+        rc |= edge_call<0>(h, ey, ez, ex, by, bz, bx, -iy, -iz, -ix, my, mz, mx, lot);
+        rc |= edge_call<0>(h, ez, ex, ey, bz, bx, by, -iz, -ix, -iy, mz, mx, my, lot);
+        rc |= edge_call<0>(h, ex, ey, ez, bx, by, bz, -ix, -iy, -iz, mx, my, mz, lot);
+    } else {
+        rc |= edge_call<1>(h, ey, ez, ex, by, bz, bx, -iy, -iz, -ix, my, mz, mx, lot);
+        rc |= edge_call<1>(h, ez, ex, ey, bz, bx, by, -iz, -ix, -iy, mz, mx, my, lot);
+        rc |= edge_call<1>(h, ex, ey, ez, bx, by, bz, -ix, -iy, -iz, mx, my, mz, lot);
+    }
+    h->need_prim = 1;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // field_bc_user of the shock problem: user/user_shock.F90:342-373
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fill_x(float *__restrict__ a, int mx, int my, int mz, int i1, int i2, float v)

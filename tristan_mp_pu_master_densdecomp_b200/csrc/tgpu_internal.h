@@ -136,6 +136,7 @@ int fld_filter1(tgpu_ctx *h);
 int fld_filter2(tgpu_ctx *h);
 int fld_add_shadow(tgpu_ctx *h);
 int fld_surface(tgpu_ctx *h, int is_e);     // radiation `surface` of bc_b2 (0) / bc_e2 (1)
+int fld_edges(tgpu_ctx *h, int which);      // preledge / postedge groups: 0 pre_bc_b, 1 post_bc_b, 2 pre_bc_e, 3 post_bc_e
 int fld_bc_shock(tgpu_ctx *h, float leftwall, float binit, float btheta, float bphi, float beta);
 // particles.cu
 int prt_h2d(tgpu_ctx *h, const tgpu_particle *p, int ions, int lecs);
