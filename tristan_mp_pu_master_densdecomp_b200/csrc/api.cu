@@ -18,6 +18,8 @@ int cellrun_move_deposit(tgpu_ctx *h);      // fused gather + push + deposit int
 int cellrun_deposit(tgpu_ctx *h);           // deposit only, into cur
 int cellrun3_supported(const tgpu_ctx *h);
 int cellrun3_deposit(tgpu_ctx *h);          // 3rd-order deposit only, into cur
+int cellrun3_move_deposit(tgpu_ctx *h);     // fused 3rd-order gather + push + deposit into shadow[]
+static int fused_mover_supported(const tgpu_ctx *h) { return cellrun_supported(h) || (cellrun3_supported(h) && h->G.lot < (1ll << 30)); }
 
 extern "C" int tgpu_device_count(void)
 {
@@ -340,8 +342,8 @@ extern "C" int tgpu_move_particles(tgpu_ctx *h)
 {
     ENTER(h); PhaseTimer t(h, TGPU_PH_MOVER);
     if (h->fused_pending) { tgpu_set_error("move_particles called twice without deposit_particles"); return TGPU_ESTATE; }
-    if (h->opt_fused && cellrun_supported(h)) {
-        int rc = cellrun_move_deposit(h); if (rc) return rc;
+    if (h->opt_fused && fused_mover_supported(h)) {
+        int rc = cellrun_supported(h) ? cellrun_move_deposit(h) : cellrun3_move_deposit(h); if (rc) return rc;
         h->fused_pending = 1;
         return 0;
     }
@@ -474,7 +476,7 @@ extern "C" int tgpu_step(tgpu_ctx *h, int nlaps)
     // Overlap: once the fused mover has written the sort keys, the scan + scatter + migration of the particles depends
     // on nothing the field phase does (and vice versa), so it runs on stream_prt while B-half/E-full/fold/filter/add run
     // on stream_main.  Needs the fused mover (keys in hand) and is skipped while per-phase timing is on.
-    const bool overlap = h->opt_overlap && h->opt_fused && cellrun_supported(h) && !h->timing;
+    const bool overlap = h->opt_overlap && h->opt_fused && fused_mover_supported(h) && !h->timing;
     // bc_b2 / bc_e2 differ from bc_b1 / bc_e1 only when an axis radiates (fieldboundaries.F90:90-94, 274-295, 403-426)
     const bool rad = !h->P.periodicx || !h->P.periodicy || (h->P.dim == 3 && !h->P.periodicz);
     h->in_step = 1;

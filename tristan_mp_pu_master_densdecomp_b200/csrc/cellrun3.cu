@@ -1,6 +1,8 @@
-// Cell-run deposit for 3D, 3rd-order shapes (-Ddd3): densdecomp_3ord, code/particles.F90:1112-1358, and loop A of
-// deposit_particles, code/particles_movedeposit.F90:1381-1401.  (The 3rd-order mover stays on the generic kernel: its
-// 4x4x4-node gather is load-bound and already fast; the deposit is what the per-particle atomics cripple.)
+// Cell-run kernel for 3D, 3rd-order shapes (-Ddd3): densdecomp_3ord, code/particles.F90:1112-1358, loop A of
+// deposit_particles, code/particles_movedeposit.F90:1381-1401, and -- in FUSED launches -- mover_3ord,
+// code/particles_movedeposit.F90:943-1271 (4x4x4-node gather of the node-centred fields + Boris push), the sort key of the
+// pushed particle and, through the lazy sort's permutation, the data-moving pass of the counting sort: one pass over the
+// particles per lap instead of three (mover, physical scatter, deposit).
 //
 // Same output-stationary idea as cellrun.cu, widened: the old shape sits on slots 2..5 and the new one on slots 2..5
 // shifted by -1/0/+1, so a cell's particles write a 6x6x6 footprint (slots 1..6).  One WARP owns one footprint: lane =
@@ -13,6 +15,7 @@
 // fixed sequence of 15 packed FMAs (FFMA2, register pairs (0,1) (2,3) (4,5)) with no rotation switch.
 #include "tgpu_internal.h"
 #include "shapes.cuh"
+#include "cellrun_common.cuh"
 
 #define C3_WARPS 8
 #define C3_STRIDE 68
@@ -20,11 +23,16 @@
 
 struct C3Args {
     Species s;
+    Species d;               // FUSED: destination records (logical order); aliases s unless a permutation is pending
+    const int32_t *perm;     // LAZY: logical position t reads physical record perm[t]
     long long n;
+    const float4 *prim8;     // FUSED: node-centred fields
     float *cx, *cy, *cz;     // the tiled shadow arrays (tgpu_internal.h row_index) when TGPU_SHADOW_TILED, else curx..curz
     int nty;
     DevGeom G;
-    float qs;
+    float qs, qm;
+    uint32_t *key; int32_t *slot, *bincount;     // FUSED: sort key / rank in bin of the pushed particle (prt_sort skips its classify pass)
+    unsigned keyoff; int general;
 };
 #define C3_TILED (TGPU_SHADOW_TILED != 0)
 #define C3_PS (C3_TILED ? 16 : 1)          // distance between consecutive x-planes of a row
@@ -59,7 +67,8 @@ __device__ __forceinline__ void red3c(float *cx, float *cy, float *cz, size_t id
     red_nz(cx + idx, vx); red_nz(cy + idx, vy); red_nz(cz + idx, vz);
 }
 
-__global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
+template <bool FUSED, bool LAZY>
+__global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(const C3Args A)
 {
     extern __shared__ __align__(16) float stage3[];        // [C3_WARPS][32][C3_STRIDE] factor staging, then the record pipeline
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -79,28 +88,72 @@ __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
 
     // record pipeline (same idea as cellrun.cu): the next step's seven floats per lane are fetched with 4-byte cp.async
     // into per-lane landing slots while the current step is being deposited
-    uint32_t *rec = reinterpret_cast<uint32_t *>(stage3 + (size_t)C3_WARPS * 32 * C3_STRIDE) + (size_t)warp * 2 * 7 * 32;
-    auto fetch = [&](int buf, long long tt) {
+    uint32_t *rec = reinterpret_cast<uint32_t *>(stage3 + (size_t)C3_WARPS * 32 * C3_STRIDE) + (size_t)warp * 2 * 9 * 32;
+    auto fetch = [&](int buf, long long tt, int pp32) {
         if (tt < A.n) {
-            uint32_t *r = rec + (size_t)buf * 7 * 32 + lane;
-            cp_async4(r + 0 * 32, A.s.x + tt); cp_async4(r + 1 * 32, A.s.y + tt); cp_async4(r + 2 * 32, A.s.z + tt);
-            cp_async4(r + 3 * 32, A.s.u + tt); cp_async4(r + 4 * 32, A.s.v + tt); cp_async4(r + 5 * 32, A.s.w + tt);
-            cp_async4(r + 6 * 32, A.s.ch + tt);
+            const long long pp = LAZY ? (long long)pp32 : tt;
+            uint32_t *r = rec + (size_t)buf * 9 * 32 + lane;
+            cp_async4(r + 0 * 32, A.s.x + pp); cp_async4(r + 1 * 32, A.s.y + pp); cp_async4(r + 2 * 32, A.s.z + pp);
+            cp_async4(r + 3 * 32, A.s.u + pp); cp_async4(r + 4 * 32, A.s.v + pp); cp_async4(r + 5 * 32, A.s.w + pp);
+            cp_async4(r + 6 * 32, A.s.ch + pp);
+            if (LAZY) { cp_async4(r + 7 * 32, A.s.ind + pp); cp_async4(r + 8 * 32, A.s.tag + pp); }
         }
         cp_async_commit();
     };
-    fetch(0, base + lane);
+    {
+        const long long t0 = base + lane;
+        fetch(0, t0, (LAZY && t0 < A.n) ? __ldcs(A.perm + t0) : 0);
+    }
+    int pnext = 0;                     // permutation entry of the next step's particle, loaded one step ahead
+    if (LAZY && base + 32 + lane < A.n) pnext = __ldcs(A.perm + base + 32 + lane);
     for (int it = 0; it < C3_CHUNK / 32; ++it) {
         const long long t = base + it * 32 + lane;
         float *st = wst + lane * C3_STRIDE;
         int ci = -1, crow = -1;
         cp_async_wait_all();
-        if (it + 1 < C3_CHUNK / 32) fetch((it + 1) & 1, t + 32);
+        if (it + 1 < C3_CHUNK / 32) {
+            fetch((it + 1) & 1, t + 32, pnext);
+            if (LAZY && it + 2 < C3_CHUNK / 32 && t + 64 < A.n) pnext = __ldcs(A.perm + t + 64);
+        }
         if (t < A.n) {
-            const uint32_t *r = rec + (size_t)(it & 1) * 7 * 32 + lane;
-            const float x = __uint_as_float(r[0 * 32]), y = __uint_as_float(r[1 * 32]), z = __uint_as_float(r[2 * 32]);
-            const float u = __uint_as_float(r[3 * 32]), v = __uint_as_float(r[4 * 32]), w = __uint_as_float(r[5 * 32]);
-            const float q = __uint_as_float(r[6 * 32]) * A.qs;
+            const uint32_t *r = rec + (size_t)(it & 1) * 9 * 32 + lane;
+            float x = __uint_as_float(r[0 * 32]), y = __uint_as_float(r[1 * 32]), z = __uint_as_float(r[2 * 32]);
+            float u = __uint_as_float(r[3 * 32]), v = __uint_as_float(r[4 * 32]), w = __uint_as_float(r[5 * 32]);
+            const float ch = __uint_as_float(r[6 * 32]);
+            const float q = ch * A.qs;
+            int rank_in_bin = 0;
+            if (FUSED) {
+                if (LAZY) {
+                    // the record still carries last lap's unwrapped position: apply the wrap its sort key was computed with
+                    bool lo, hi;
+                    x = wrap1(x, G.minx, G.maxx, G.shiftx_lo, G.shiftx_hi, lo, hi);
+                    y = wrap1(y, G.miny, G.maxy, G.shifty_lo, G.shifty_hi, lo, hi);
+                    z = wrap1(z, G.minz, G.maxz, G.shiftz_lo, G.shiftz_hi, lo, hi);
+                    A.d.ch[t] = ch; A.d.ind[t] = (int32_t)r[7 * 32]; A.d.tag[t] = (int32_t)r[8 * 32];
+                }
+                // mover_3ord (particles_movedeposit.F90:1035-1128, 1130-1160): cubic B-spline weights on slots 2..5 of each
+                // axis = nodes ip-1..ip+2; the six node-centred fields summed x innermost, then *Sy*Sz
+                const int ip = (int)x, jp = (int)y, kq = (int)z;
+                float W6[6], wxs[4], wys[4], wzs[4];
+                shape6(x - ip, 0, W6); wxs[0] = W6[1]; wxs[1] = W6[2]; wxs[2] = W6[3]; wxs[3] = W6[4];
+                shape6(y - jp, 0, W6); wys[0] = W6[1]; wys[1] = W6[2]; wys[2] = W6[3]; wys[3] = W6[4];
+                shape6(z - kq, 0, W6); wzs[0] = W6[1]; wzs[1] = W6[2]; wzs[2] = W6[3]; wzs[3] = W6[4];
+                float e0 = 0, e1 = 0, e2 = 0, b0 = 0, b1 = 0, b2 = 0;
+                const int nbase = (ip - 2) + mx * ((jp - 2) + my * (kq - 2));
+                gather_nodes<4>(A.prim8, nbase, mx, my, wxs, wys, wzs, e0, e1, e2, b0, b1, b2);
+                const float cinv = G.cinv, qm = A.qm;
+                e0 = 0.5f * e0 * qm; e1 = 0.5f * e1 * qm; e2 = 0.5f * e2 * qm;
+                b0 = 0.5f * b0 * qm * cinv; b1 = 0.5f * b1 * qm * cinv; b2 = 0.5f * b2 * qm * cinv;
+                if (G.external_fields) {
+                    b0 = b0 + G.ext[3] * 0.5f * qm * cinv; b1 = b1 + G.ext[4] * 0.5f * qm * cinv; b2 = b2 + G.ext[5] * 0.5f * qm * cinv;
+                    e0 = e0 + G.ext[0] * 0.5f * qm; e1 = e1 + G.ext[1] * 0.5f * qm; e2 = e2 + G.ext[2] * 0.5f * qm;
+                }
+                push_particle<false>(G.c, G.pusher, e0, e1, e2, b0, b1, b2, x, y, z, u, v, w);
+                A.d.x[t] = x; A.d.y[t] = y; A.d.z[t] = z; A.d.u[t] = u; A.d.v[t] = v; A.d.w[t] = w;
+                const uint32_t ky = sort_key(G, A.keyoff, A.general, x, y, z);
+                A.key[t] = ky;
+                rank_in_bin = atomicAdd(&A.bincount[ky], 1);
+            }
             // old position recomputed from the new one (particles_movedeposit.F90:1384-1390)
             const float invgam = 1.f / sqrtf(1 + u * u + v * v + w * w);
             const float x1 = x - u * invgam * G.c, y1 = y - v * invgam * G.c, z1 = z - w * invgam * G.c;
@@ -142,6 +195,7 @@ __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
                     *(float4 *)(st + 44 + 4 * s) = make_float4(S1[s], dSz[s], qPSz[s], __int_as_float(crow));
                 }
             }
+            if (FUSED) A.slot[t] = rank_in_bin;
             if (shj != 0 && shk != 0) {
                 // the one corner row this particle reaches: the old shape is zero there, only the dS*dS terms survive
                 const int jc = shj < 0 ? 0 : 5, kc = shk < 0 ? 0 : 5;
@@ -229,24 +283,78 @@ __global__ void __launch_bounds__(C3_WARPS * 32, 2) k_cellrun3(C3Args A)
 
 int cellrun3_supported(const tgpu_ctx *h) { return h->P.dim == 3 && h->P.order == 3 && h->P.my < 65536 && h->P.mz < 32768; }
 
-// tgpu_deposit_particles fast path for -Ddd3 (currents only; wrap / compaction / sort follow in prt_sort)
-int cellrun3_deposit(tgpu_ctx *h)
+#define C3_SMEM ((size_t)C3_WARPS * 32 * C3_STRIDE * sizeof(float) + (size_t)C3_WARPS * 2 * 9 * 32 * sizeof(uint32_t))
+
+template <bool FUSED, bool LAZY>
+static int launch3(tgpu_ctx *h, const C3Args &A)
 {
-    int rc = prt_materialize(h); if (rc) return rc;
-    const size_t smem = (size_t)C3_WARPS * 32 * C3_STRIDE * sizeof(float) + (size_t)C3_WARPS * 2 * 7 * 32 * sizeof(uint32_t);
-    CK(cudaFuncSetAttribute(k_cellrun3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(k_cellrun3<FUSED, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3_SMEM));
+        attr_set = true;
+    }
+    const long long warps = (A.n + C3_CHUNK - 1) / C3_CHUNK;
+    const int blocks = (int)((warps + C3_WARPS - 1) / C3_WARPS);
+    k_cellrun3<FUSED, LAZY><<<blocks, C3_WARPS * 32, C3_SMEM, h->stream>>>(A);
+    CKK(h);
+    return 0;
+}
+
+template <bool FUSED>
+static int run3(tgpu_ctx *h)
+{
     for (int s = 0; s < 2; s++) {
         Species &S = h->sp[s];
         if (S.n == 0) continue;
         C3Args A;
-        A.s = S; A.n = S.n; A.G = h->G; A.qs = s ? h->P.qe : h->P.qi; A.nty = h->nty;
+        A.s = S; A.d = S; A.perm = nullptr; A.n = S.n; A.G = h->G; A.nty = h->nty; A.prim8 = h->prim8;
+        A.qs = s ? h->P.qe : h->P.qi; A.qm = s ? h->P.qme : h->P.qmi;
         // deposits go to the shadow arrays (tiled: a flush touches a few 64 B tile rows instead of 32 cache lines) and
-        // are folded into curx..curz by fld_add_shadow below
+        // are folded into curx..curz by fld_add_shadow
         A.cx = h->shadow[0]; A.cy = h->shadow[1]; A.cz = h->shadow[2];
-        long long warps = (S.n + C3_CHUNK - 1) / C3_CHUNK;
-        int blocks = (int)((warps + C3_WARPS - 1) / C3_WARPS);
-        k_cellrun3<<<blocks, C3_WARPS * 32, smem, h->stream>>>(A);
-        CKK(h);
+        const size_t nb = (size_t)h->G.lot + TGPU_NBIN_EXTRA;
+        A.key = h->key[s]; A.slot = h->slot + (size_t)s * h->maxhlf; A.bincount = h->bincount + (size_t)s * nb;
+        A.keyoff = 1u + (unsigned)h->G.mx + (unsigned)h->G.mx * (unsigned)h->G.my;
+        A.general = !(h->G.perx && h->G.pery && h->G.perz) || h->G.sendy || h->G.sendz;
+        int rc;
+        if (FUSED) {
+            CK(cudaMemsetAsync(A.bincount, 0, nb * sizeof(int32_t), h->stream));
+            if (h->lazy[s]) { A.perm = h->perm[s]; A.d = h->alt[s]; rc = launch3<true, true>(h, A); }
+            else rc = launch3<true, false>(h, A);
+            if (rc) return rc;
+            if (h->lazy[s]) {
+                // the pushed records now sit, in sorted order and wrapped, in the other buffer
+                const int n = S.n;
+                Species tmp = h->sp[s]; h->sp[s] = h->alt[s]; h->alt[s] = tmp;
+                h->sp[s].n = n; h->lazy[s] = 0; h->nphys[s] = n;
+            }
+        } else {
+            rc = launch3<false, false>(h, A); if (rc) return rc;
+        }
     }
+    return 0;
+}
+
+// tgpu_move_particles fast path for -Ddd3: gather + push + deposit (into shadow[], folded into cur at deposit_particles time
+// because mainloop resets cur in between) + sort keys, one pass; the same life cycle as cellrun_move_deposit (cellrun.cu)
+int cellrun3_move_deposit(tgpu_ctx *h)
+{
+    int rc = fld_primal(h); if (rc) return rc;
+    if (h->G.lot >= (1ll << 30)) { tgpu_set_error("cellrun3: grid too large for 32-bit node indices"); return TGPU_EINVAL; }
+    if (h->presort) {
+        h->presort = 0;                       // host order -> cell order once (see cellrun_move_deposit)
+        rc = prt_sort(h, false); if (rc) return rc;
+    }
+    rc = run3<true>(h); if (rc) return rc;
+    h->keys_valid = 1;
+    return 0;
+}
+
+// tgpu_deposit_particles fast path for -Ddd3 when the particles were moved elsewhere (currents only; wrap / compaction /
+// sort follow in prt_sort)
+int cellrun3_deposit(tgpu_ctx *h)
+{
+    int rc = prt_materialize(h); if (rc) return rc;
+    rc = run3<false>(h); if (rc) return rc;
     return fld_add_shadow(h);
 }
