@@ -48,7 +48,162 @@ def parse():
     ap.add_argument("--order", type=int, default=ORDER, help="shape order (headline = 2)")
     ap.add_argument("--ppc", type=float, default=PPC)
     ap.add_argument("--cpu-cells", type=int, nargs=3, default=[128, 32, 32], help="CPU sample: cells per host-thread slab")
-    return ap.parse_args()
+    ap.add_argument("--config", default="default", choices=["default", "c0", "c1", "c3", "c4"],
+                    help="BASELINE.json configs: default = per-GPU share of configs[2] (the headline); c0 = configs[0] 2D Weibel "
+                         "128^2 dd1 (GPU against ONE CPU rank); c1 = configs[1] 2D two-stream 128x2 dd2; c3 = configs[3] 3D shock "
+                         "512x128x128 dd3 with wall, clamps and a per-lap injector; c4 = configs[4] 3D Weibel 64 ppc "
+                         "(256x256x128 per GPU, --order 1|2|3).  Only `default` is the driver's bench line.")
+    a = ap.parse_args()
+    if a.config == "c4":
+        a.cells, a.ppc = [256, 256, 128], 64.0
+    return a
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The other BASELINE.json configs (single GPU): small 2D problems and the shock.  Same metric, same JSON shape; these are
+# extra lines for profiles/, never the driver's headline.
+# ------------------------------------------------------------------------------------------------------------
+def beams(rng, n, lo, hi, zlo, zhi, drift, uth, x_sign=None):
+    """n particles, uniform in the box, drifting along +-x (alternating, or all along x_sign) with a thermal spread"""
+    import tristan_mp_pu_master_densdecomp_b200 as tg
+    p = np.zeros(n, tg.PARTICLE_DTYPE)
+    for k, (a, b) in zip("xyz", (lo[0:1] + hi[0:1], lo[1:2] + hi[1:2], [zlo, zhi])):
+        p[k] = (a + (b - a) * rng.random(n)).astype(np.float32)
+        np.minimum(p[k], np.nextafter(np.float32(b), np.float32(0)), out=p[k])
+    sign = np.where((np.arange(n) & 1) == 0, 1.0, -1.0) if x_sign is None else x_sign
+    gb = drift / np.sqrt(1 - drift * drift)
+    p["u"] = (sign * gb + uth * rng.standard_normal(n)).astype(np.float32)
+    p["v"] = (uth * rng.standard_normal(n)).astype(np.float32)
+    p["w"] = (uth * rng.standard_normal(n)).astype(np.float32)
+    p["ch"] = 1.0; p["splitlev"] = 1
+    return p
+
+
+def run_small_config(args):
+    import torch
+    import __graft_entry__ as ge
+    ge.build()
+    import tristan_mp_pu_master_densdecomp_b200 as tg
+    rng = np.random.default_rng(77)
+    cfg = args.config
+    if cfg == "c0":       # user/input.weibel: 128 x 128, dd1, 16 ppc, ntimes = 32, filter1 (default build), cold counter-streaming beams
+        kw = dict(dim=2, order=1, mx0=128, my0=128, ntimes=32, filter_kind=1, ppc0=16.0)
+        name = "configs[0]: 2D Weibel (user/input.weibel) 128x128, dd1, 16 ppc, filter1 ntimes=32, 262144 particles"
+        species, drift, uth, hooks = (1, 1), 0.5, 2e-3, None
+    elif cfg == "c1":     # user/input.twostream: 128 x 2, dd2, 64 ppc, electrons only
+        kw = dict(dim=2, order=2, mx0=128, my0=2, ntimes=32, filter_kind=1, ppc0=64.0)
+        name = "configs[1]: 2D two-stream (user/input.twostream) 128x2, dd2, 64 ppc, electrons only, 8192 particles"
+        species, drift, uth, hooks = (0, 1), 0.5, 2e-3, None
+    else:                 # user/input.shock made 3D (sizex = 1): dd3, open x, reflecting wall at leftwall, clamps, injector
+        kw = dict(dim=3, order=3, mx0=512, my0=128, mz0=128, ntimes=4, filter_kind=2, ppc0=16.0, periodic=(0, 1, 1))
+        name = "configs[3]: 3D shock (user/user_shock.F90 hooks) 512x128x128, dd3, 16 ppc upstream, wall at x=20, injector at the right edge"
+        species, drift, uth, hooks = (1, 1), 0.4, 0.05, (20.0, 0.05, 0.3, 1.2, 0.4)
+    ncell = kw["mx0"] * kw["my0"] * kw.get("mz0", 1)
+    nsp = int(0.5 * kw["ppc0"] * ncell)
+    P = tg.make_params(maxptl=int(2 * nsp * 1.6) + 8192, device=0, **kw)
+    ctx = tg.Context(P)
+    g, gz = P.nghost // 2, P.nghostz // 2
+    lo, hi = [g + 1.0, g + 1.0], [float(P.mx - g), float(P.my - g)]
+    zlo, zhi = (gz + 1.0, float(P.mz - gz)) if P.dim == 3 else (3.0, 4.0)      # 2D: minz = 3, maxz = 4 (particles_movedeposit.F90:1371)
+    if hooks:
+        lo[0] = hooks[0] + 0.5                                     # plasma only upstream of the wall, flowing towards it
+    maxhlf = P.maxptl // 2
+    host = np.zeros(P.maxptl, tg.PARTICLE_DTYPE)
+    n_i = nsp if species[0] else 0
+    n_e = nsp if species[1] else 0
+    for s, n, off in ((0, n_i, 0), (1, n_e, maxhlf)):
+        if n:
+            q = beams(rng, n, lo, hi, zlo, zhi, drift, uth, x_sign=(-1.0 if hooks else None))
+            q["ind"] = np.arange(1, n + 1, dtype=np.int32) * 2 - s
+            host[off:off + n] = q
+    ctx.particles_h2d(host, n_i, n_e)
+    zero = [np.zeros((P.mz, P.my, P.mx), np.float32) for _ in range(6)]
+    ctx.fields_h2d(*zero)
+    if hooks:
+        ctx.set_user_hooks(1, hooks)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", 0))
+    next_ind = [2 * nsp + 2]
+
+    def inject():
+        """the reference's host injector (user_shock.F90:303-331 -> inject_from_wall): ppc0 * c * beta particles per cell
+        face and lap enter at the right edge, moving towards the wall; host RNG, uploaded with tgpu_append_particles"""
+        if not hooks:
+            return 0
+        n = int(0.5 * kw["ppc0"] * kw["my0"] * kw["mz0"] * 0.45 * drift)
+        xr = float(P.mx - g)
+        q = np.zeros(2 * n, tg.PARTICLE_DTYPE)
+        for s in (0, 1):
+            b = beams(rng, n, [xr - 0.45 * drift, lo[1]], [xr, hi[1]], zlo, zhi, drift, uth, x_sign=-1.0)
+            b["ind"] = (next_ind[0] + 2 * np.arange(n, dtype=np.int32)) - s
+            q[s * n:(s + 1) * n] = b
+        next_ind[0] += 2 * n
+        ctx.append_particles(q, n, n)
+        return 2 * n
+
+    steps, warm = (args.steps, args.warmup) if cfg == "c3" else (max(args.steps, 200), max(args.warmup, 20))
+    for _ in range(warm):
+        inject(); ctx.step(1)
+    torch.cuda.synchronize()
+    n0 = sum(ctx.counts())
+    sampler = ClockSampler(0); sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    psteps = 0
+    injected = 0
+    t_host0 = time.perf_counter()
+    for _ in range(steps):
+        injected += inject()
+        ctx.step(1)
+        psteps += sum(ctx.counts()) if hooks else n0
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t_host0) * 1e3
+    ms = max(e0.elapsed_time(e1), 1e-6)
+    sampler.stop_flag = True
+    launches = ctx.launch_count() - l0
+    n1 = sum(ctx.counts())
+    # sanity: counts (injected - removed through the open faces), finite fields, energy
+    f = ctx.fields_d2h()
+    fe = float(sum((a.astype(np.float64) ** 2).sum() for a in f))
+    pp, ci, ce = ctx.particles_d2h()
+    gam = lambda q: np.sqrt(1.0 + q["u"].astype(np.float64) ** 2 + q["v"].astype(np.float64) ** 2 + q["w"].astype(np.float64) ** 2)
+    ke = float((gam(pp[:ci]) - 1).sum() + (gam(pp[maxhlf:maxhlf + ce]) - 1).sum())
+    sanity = {"particles_start": n0, "particles_end": n1, "injected": injected, "field_energy_sum_sq": fe, "kinetic_sum_gamma_minus_1": ke,
+              "finite": bool(np.isfinite(fe) and np.isfinite(ke))}
+    ctx.close()
+    value = psteps / (ms * 1e-3)
+    cpu = None
+    if cfg in ("c0", "c1") and not args.no_cpu:
+        # ONE CPU rank, as BASELINE.json configs[0] says: the oracle restatement on one thread, same problem from the seeded loader
+        os.environ["OMP_NUM_THREADS"] = "1"
+        from oracle import oracle as O
+        O.use_timing_build()
+        Pc = O.make_params(dim=2, order=kw["order"], mx0=kw["mx0"], my0=kw["my0"], ppc0=kw["ppc0"], ntimes=32, filter_kind=1)
+        w = O.World(Pc)
+        (w.init_weibel(ppc0=16.0, delgam=2e-5, distr_dim=2) if cfg == "c0" else w.init_twostream(ppc0=64.0, delgam=2e-5))
+        npc = sum(sum(r.counts) for r in w.ranks)
+        w.step()
+        t0 = time.perf_counter(); k = 0
+        while time.perf_counter() - t0 < 10.0:
+            w.step(); k += 1
+        dt = (time.perf_counter() - t0) / k
+        cpu = {"value": npc / dt, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+               "sample": f"the whole problem ({npc} particles), {k} laps in {k * dt:.1f} s on ONE thread (one CPU rank), oracle built -O3 -march=native"}
+    peak, peak_src = measured_peak()
+    line = {"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": steps, "warmup": warm,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "order": kw["order"], "ppc": kw["ppc0"],
+                       "l2": "small problem, resident in L2 by nature" if cfg != "c3" else "inputs larger than L2"},
+            "particles": n1, "gpu_launches": launches, "clocks": sampler.summary(), "host_wall_ms_per_step": wall_ms / steps,
+            "sanity": sanity, "cpu_baseline": cpu,
+            "roofline": {"bound": "hbm", "achieved": value * (52.0 + 36.0 / kw["ppc0"]) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": value * (52.0 + 36.0 / kw["ppc0"]) / 1e9 / peak, "traffic": None,
+                         "note": "whole lap against the mover+deposit algorithmic bytes; small configs are launch-latency bound", "peak_source": peak_src},
+            "e2e": None}
+    print(json.dumps(line))
+
+
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -220,8 +375,9 @@ def run_reference(args):
 
 def workload_config(args, n):
     sy, sz = GRID[n]
+    which = "configs[4] weak-scaling sweep" if getattr(args, "config", "default") == "c4" else "configs[2] share"
     return {"workload": f"3D Weibel, dd{ORDER} (order-{ORDER} Esirkepov), {PPC:g} ppc, filter2 ntimes={NTIMES}, per-GPU slab "
-                        f"{args.cells[0]}x{args.cells[1]}x{args.cells[2]} cells (configs[2] share), global "
+                        f"{args.cells[0]}x{args.cells[1]}x{args.cells[2]} cells ({which}), global "
                         f"{args.cells[0]}x{args.cells[1] * sy}x{args.cells[2] * sz}",
             "decomposition": f"sizey={sy} sizez={sz}", "ppc": PPC, "order": ORDER, "c": 0.45,
             "l2": "inputs (>= 9 GB of particle SoA per GPU) larger than L2; no flush needed"}
@@ -234,6 +390,8 @@ def main():
     B_PER_PARTICLE = 52.0 + 36.0 / PPC
     if args.impl == "reference":
         return run_reference(args)
+    if args.config in ("c0", "c1", "c3"):
+        return run_small_config(args)
     import __graft_entry__ as ge
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

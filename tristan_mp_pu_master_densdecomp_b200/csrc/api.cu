@@ -162,7 +162,7 @@ static int init_impl(tgpu_ctx *h, const tgpu_params *p, int ndev)
         rc |= dalloc(&h->sendbuf, (size_t)TGPU_NDIR * p->buffsize); rc |= dalloc(&h->recvbuf, (size_t)TGPU_NDIR * p->buffsize);
     }
     if (rc) { tgpu_set_error("device allocation failed: " + g_err); return TGPU_ECUDA; }
-    h->need_prim = 1; h->fused_pending = 0; h->keys_valid = 0; h->hook_kind = 0; h->in_step = 0; h->opt_fused = 1; h->opt_fast_push = 1; h->opt_peer = 1; h->peer = nullptr; h->sig = nullptr; h->xseq = 0; h->nccl_comm = nullptr; h->lap = 0; h->launches = 0; h->timing = 0;
+    h->need_prim = 1; h->fused_pending = 0; h->keys_valid = 0; h->hook_kind = 0; h->in_step = 0; h->opt_fused = 1; h->opt_fast_push = 1; h->opt_peer = 1; h->opt_graph = 1; h->f1_graph = nullptr; h->f1_graph_launches = 0; h->peer = nullptr; h->sig = nullptr; h->xseq = 0; h->nccl_comm = nullptr; h->lap = 0; h->launches = 0; h->timing = 0;
     for (int i = 0; i < TGPU_NPHASE; i++) h->phase_ms[i] = 0;
     CK(cudaDeviceSynchronize());
     return 0;
@@ -175,6 +175,7 @@ extern "C" int tgpu_finalize(tgpu_ctx *h)
     if (h->stream_main) cudaStreamSynchronize(h->stream_main);
     if (h->stream_prt) cudaStreamSynchronize(h->stream_prt);
     comm_destroy(h);
+    if (h->f1_graph) { cudaGraphExecDestroy((cudaGraphExec_t)h->f1_graph); h->f1_graph = nullptr; }
     for (int a = 0; a < 9; a++) cudaFree(h->f[a]);
     for (int a = 0; a < 3; a++) { cudaFree(h->ftmp[a]); cudaFree(h->shadow[a]); }
     if (h->prim8) cudaFree(h->prim8);
@@ -570,7 +571,8 @@ extern "C" int tgpu_set_option(tgpu_ctx *h, const char *name, int value)
     if (!h || !name) return TGPU_EINVAL;
     if (!strcmp(name, "fused")) { h->opt_fused = value; return 0; }
     if (!strcmp(name, "fast_push")) { h->opt_fast_push = value; return 0; }
-    if (!strcmp(name, "peer")) { h->opt_peer = value; return 0; }       // before tgpu_comm_init: 0 = halos through NCCL send/recv
+    if (!strcmp(name, "peer")) { h->opt_peer = value; return 0; }
+    if (!strcmp(name, "graph")) { h->opt_graph = value; return 0; }     // 0: launch the filter1 passes one by one       // before tgpu_comm_init: 0 = halos through NCCL send/recv
     if (!strcmp(name, "timing")) { h->timing = value; return 0; }
     if (!strcmp(name, "overlap")) { h->opt_overlap = value; return 0; }
     if (!strcmp(name, "lazy_sort")) { h->opt_lazy = value; return 0; }

@@ -673,7 +673,31 @@ __global__ void __launch_bounds__(128) k_filter1_back(Arr3 S, Arr3 D, int mx, in
     D.a[c][LIDX(i, j, k)] = S.a[c][LIDX(i, j, k)];
 }
 
+static int filter1_passes(tgpu_ctx *h);
+
+// On one rank the ntimes passes are a fixed sequence of small launches with fixed arguments (6 per pass: 192 for the
+// shipped ntimes = 32, which is what a 128 x 128 problem's lap consists of): captured once into a CUDA graph and replayed.
 int fld_filter1(tgpu_ctx *h)
+{
+    if (h->size0 > 1 || h->P.ntimes <= 0 || !h->opt_graph) return filter1_passes(h);
+    if (!h->f1_graph) {
+        const int64_t l0 = h->launches;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = filter1_passes(h);
+        cudaGraph_t gr = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(h->stream, &gr);
+        if (rc || e != cudaSuccess || !gr) { if (gr) cudaGraphDestroy(gr); cudaGetLastError(); h->opt_graph = 0; h->launches = l0; return filter1_passes(h); }
+        cudaGraphExec_t ex = nullptr;
+        if (cudaGraphInstantiate(&ex, gr, 0) != cudaSuccess) { cudaGraphDestroy(gr); cudaGetLastError(); h->opt_graph = 0; h->launches = l0; return filter1_passes(h); }
+        cudaGraphDestroy(gr);
+        h->f1_graph = ex; h->f1_graph_launches = (int)(h->launches - l0); h->launches = l0;
+    }
+    CK(cudaGraphLaunch((cudaGraphExec_t)h->f1_graph, h->stream));
+    h->launches += h->f1_graph_launches;          // kernels executed (one graph launch)
+    return 0;
+}
+
+static int filter1_passes(tgpu_ctx *h)
 {
     const tgpu_params &P = h->P;
     Arr3 A, T; for (int c = 0; c < 3; c++) { A.a[c] = h->f[6 + c]; T.a[c] = h->ftmp[c]; }

@@ -95,6 +95,8 @@ struct tgpu_ctx {
     uint32_t *sig;           // own signal words (device memory, mapped by the neighbours)
     uint32_t xseq;           // exchange counter: every rank runs the same sequence of halo steps
     int opt_peer;
+    int opt_graph;           // replay fixed launch sequences (filter1 passes on one rank) as CUDA graphs
+    void *f1_graph; int f1_graph_launches;
     int lap;
     int64_t launches;
     double phase_ms[TGPU_NPHASE];
