@@ -818,13 +818,17 @@ __global__ void __launch_bounds__(512) k_filter2(float *__restrict__ cur, const 
             for (int n = 0; n < f.nt; n++) {
                 const float left = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
                 const float right = __shfl_down_sync(0xffffffffu, v[0], 1);
-                float prev = left;
+                // (.25 * prev + .5 * c) + .25 * nx, the reference's order (optimized_filters.F90:487-516).  Scaling by 1/4 and
+                // 1/2 is exact, so the two explicit FMAs round exactly where the separate multiplies and adds would, and
+                // .25 * c is computed once and reused as the next element's first term: 3 instructions per element-pass
+                // instead of 4 (the kernel is issue-bound; this file is built with -fmad=false, fmaf() stays an FMA)
+                float tprev = .25f * left;
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     const float c = v[r];
                     const float nx = r < R - 1 ? v[r + 1] : right;
-                    v[r] = .25f * prev + .5f * c + .25f * nx;
-                    prev = c;
+                    v[r] = fmaf(.25f, nx, fmaf(.5f, c, tprev));
+                    tprev = .25f * c;
                 }
                 v[0] = first ? f0 : v[0];
                 v[R - 1] = last ? fl : v[R - 1];
@@ -833,15 +837,15 @@ __global__ void __launch_bounds__(512) k_filter2(float *__restrict__ cur, const 
         for (int n = 0; n < f.nt; n++) {
             const float left = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
             const float right = __shfl_down_sync(0xffffffffu, v[0], 1);
-            float prev = left;
+            float tprev = .25f * left;
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const int p = p0 + r;
                 const float c = v[r];
                 const float nx = r < R - 1 ? v[r + 1] : right;
-                const float nv = .25f * prev + .5f * c + .25f * nx;
+                const float nv = fmaf(.25f, nx, fmaf(.5f, c, tprev));
                 v[r] = (p == 0 || p >= L - 1) ? c : nv;
-                prev = c;
+                tprev = .25f * c;
             }
         }
 #pragma unroll
