@@ -339,16 +339,23 @@ def test_charge_conservation_on_device(tgm, order):
     ctx.close()
 
 
-def test_sort_is_a_permutation_and_sorted(tgm):
+@pytest.mark.parametrize("blocked", [0, 1])
+def test_sort_is_a_permutation_and_sorted(tgm, blocked):
+    """reorder_particles: a permutation, sorted by cell.  blocked = 0: the reference's key i-1 + mx*((j-1) + my*(k-1))
+    (particles.F90:441); blocked = 1 (the 3D default): the same with the (y,z) rows numbered in 8 x 8 blocks
+    (tgpu_internal.h cell_key) -- x stays the fastest index, neighbouring rows stay close in the sweep"""
     w, ctx = make(tgm, dim=3, order=2, n=(16, 14, 12), ppc=6.0)
+    ctx.set_option("blocked_rows", blocked)
     r = w.ranks[0]
     ctx.reorder_particles()
     p, ions, lecs = ctx.particles_d2h()
     assert (ions, lecs) == r.counts
+    nbj = (r.my + 7) // 8
     for lo, n in ((0, ions), (ctx.maxhlf, lecs)):
         q = p[lo:lo + n]
-        key = q["x"].astype(np.int64) - 1 + r.mx * ((q["y"].astype(np.int64) - 1) + r.my * (q["z"].astype(np.int64) - 1))
-        assert np.all(np.diff(key) >= 0)
+        i, j, k = (q[c].astype(np.int64) - 1 for c in ("x", "y", "z"))
+        row = (((k >> 3) * nbj + (j >> 3)) << 6 | (k & 7) << 3 | (j & 7)) if blocked else j + r.my * k
+        assert np.all(np.diff(i + r.mx * row) >= 0)
     gi, ge = T.gpu_particles(ctx)
     oi, oe = T.oracle_particles(r)
     T.assert_particles_close(gi, oi, rtol_pos=0, rtol_mom=0)

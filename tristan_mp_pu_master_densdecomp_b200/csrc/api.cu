@@ -111,6 +111,9 @@ static int init_impl(tgpu_ctx *h, const tgpu_params *p, int ndev)
     G.dim = p->dim; G.order = p->order; G.mx = p->mx; G.my = p->my; G.mz = p->mz;
     G.nghost = p->nghost; G.nghostz = p->nghostz; G.g = p->nghost / 2; G.gz = p->nghostz / 2;
     G.lot = (long long)p->mx * p->my * p->mz;
+    G.rowblk = p->dim == 3 ? 1 : 0; G.nbj = (p->my + 7) / 8;
+    G.nkeys = G.rowblk ? (long long)p->mx * 64 * G.nbj * ((p->mz + 7) / 8) : G.lot;
+    if (G.nkeys >= (1ll << 31) - 64) { G.rowblk = 0; G.nkeys = G.lot; }
     G.c = p->c; G.corr = p->corr; G.cinv = 1.f / p->c; G.quirks = p->quirks; G.pusher = p->pusher; G.external_fields = p->external_fields;
     for (int i = 0; i < 6; i++) G.ext[i] = p->ext[i];
     // particles_movedeposit.F90:1359-1374
@@ -146,7 +149,7 @@ static int init_impl(tgpu_ctx *h, const tgpu_params *p, int ndev)
         h->lazy[s] = 0; h->nphys[s] = 0;
     }
     rc |= dalloc(&h->slot, (size_t)2 * h->maxhlf);
-    size_t nb = lot + TGPU_NBIN_EXTRA;
+    size_t nb = (size_t)G.nkeys + TGPU_NBIN_EXTRA;
     rc |= dalloc(&h->bincount, 2 * nb); rc |= dalloc(&h->binoff, 2 * (nb + 1));
     h->cub_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, h->cub_bytes, h->bincount, h->binoff, (int)(nb + 1), h->stream);
@@ -572,7 +575,12 @@ extern "C" int tgpu_set_option(tgpu_ctx *h, const char *name, int value)
     if (!strcmp(name, "fused")) { h->opt_fused = value; return 0; }
     if (!strcmp(name, "fast_push")) { h->opt_fast_push = value; return 0; }
     if (!strcmp(name, "peer")) { h->opt_peer = value; return 0; }
-    if (!strcmp(name, "graph")) { h->opt_graph = value; return 0; }     // 0: launch the filter1 passes one by one       // before tgpu_comm_init: 0 = halos through NCCL send/recv
+    if (!strcmp(name, "graph")) { h->opt_graph = value; return 0; }
+    if (!strcmp(name, "blocked_rows")) {      // 0: sort by the reference's key i + mx*(j + my*k); 1 (3D default): rows in 8 x 8 blocks
+        if (value && (h->P.dim != 3 || (long long)h->P.mx * 64 * h->G.nbj * ((h->P.mz + 7) / 8) != h->G.nkeys)) return TGPU_EINVAL;
+        h->G.rowblk = value ? 1 : 0; h->keys_valid = 0;
+        return prt_materialize(h);
+    }     // 0: launch the filter1 passes one by one       // before tgpu_comm_init: 0 = halos through NCCL send/recv
     if (!strcmp(name, "timing")) { h->timing = value; return 0; }
     if (!strcmp(name, "overlap")) { h->opt_overlap = value; return 0; }
     if (!strcmp(name, "lazy_sort")) { h->opt_lazy = value; return 0; }

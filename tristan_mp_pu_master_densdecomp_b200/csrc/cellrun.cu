@@ -512,7 +512,7 @@ static int launch(tgpu_ctx *h, float *cx, float *cy, float *cz)
         CRArgs A;
         fill_args(h, s, A, cx, cy, cz);
         A.s = S; A.d = S; A.perm = nullptr; A.n = (unsigned)S.n;
-        const size_t nb = (size_t)h->G.lot + TGPU_NBIN_EXTRA;
+        const size_t nb = (size_t)h->G.nkeys + TGPU_NBIN_EXTRA;
         A.key = h->key[s]; A.slot = h->slot + (size_t)s * h->maxhlf; A.bincount = h->bincount + (size_t)s * nb;
         if (FUSED) CK(cudaMemsetAsync(A.bincount, 0, nb * sizeof(int32_t), h->stream));
         if (FUSED && h->lazy[s]) { A.perm = h->perm[s]; A.d = h->alt[s]; }     // gather through the pending permutation
@@ -557,7 +557,7 @@ int cellrun_move_deposit_range(tgpu_ctx *h, int s, int off, int cnt)
     R.x += off; R.y += off; R.z += off; R.u += off; R.v += off; R.w += off; R.ch += off; R.ind += off; R.tag += off; R.n = cnt;
     fill_args(h, s, A, h->shadow[0], h->shadow[1], h->shadow[2]);
     A.s = R; A.d = R; A.perm = nullptr; A.n = (unsigned)cnt;
-    const size_t nb = (size_t)h->G.lot + TGPU_NBIN_EXTRA;
+    const size_t nb = (size_t)h->G.nkeys + TGPU_NBIN_EXTRA;
     A.key = h->key[s] + off; A.slot = h->slot + (size_t)s * h->maxhlf + off; A.bincount = h->bincount + (size_t)s * nb;
     return launch_any<true>(h, A);
 }

@@ -312,7 +312,7 @@ static int run3(tgpu_ctx *h)
         // deposits go to the shadow arrays (tiled: a flush touches a few 64 B tile rows instead of 32 cache lines) and
         // are folded into curx..curz by fld_add_shadow
         A.cx = h->shadow[0]; A.cy = h->shadow[1]; A.cz = h->shadow[2];
-        const size_t nb = (size_t)h->G.lot + TGPU_NBIN_EXTRA;
+        const size_t nb = (size_t)h->G.nkeys + TGPU_NBIN_EXTRA;
         A.key = h->key[s]; A.slot = h->slot + (size_t)s * h->maxhlf; A.bincount = h->bincount + (size_t)s * nb;
         A.keyoff = 1u + (unsigned)h->G.mx + (unsigned)h->G.mx * (unsigned)h->G.my;
         A.general = !(h->G.perx && h->G.pery && h->G.perz) || h->G.sendy || h->G.sendz;

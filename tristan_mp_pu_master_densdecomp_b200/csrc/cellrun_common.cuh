@@ -2,18 +2,24 @@
 // keep-in-L1 loads, the packed node-centred field gather and the sort-key classification.
 #pragma once
 #include "tgpu_internal.h"
+#ifndef CR_LDG_PLAIN
+#define CR_LDG_PLAIN 1       // 0: ld.global.nc.L1::evict_last for the field nodes -- measured: no change in time, L1 hit rate or DRAM bytes
+#endif
 
 // sum over an NW^3 block of node-centred fields, in the reference's order: x innermost (sum()), then *Sy*Sz
 // (particles_movedeposit.F90:801-815); packed fp32 (FFMA2 / FMUL2): the six components sit in three aligned register
 // pairs straight out of the two 128-bit loads; same operations and roundings as the scalar form
-// node-centred fields are re-read by the following steps of the same warp (same or neighbouring cell) while the particle
-// records stream through L1 exactly once; with ~190 KB of the SM's 256 KB configured as shared memory only ~30 KB of L1
-// remain, so the field lines are loaded with the evict_last priority (ncu: L1 sector hit rate 19 % without it)
+// node-centred field loads.  (An L1::evict_last priority for them -- the particle records stream through L1 exactly once,
+// the field lines are re-read by the next steps -- was measured: no change in time, L1 hit rate or DRAM bytes.)
 __device__ __forceinline__ float4 ldg_keep(const float4 *p)
 {
+#if CR_LDG_PLAIN
+    return __ldg(p);
+#else
     float4 v;
     asm("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
+#endif
 }
 
 // particle records are read exactly once: do not let them displace the field lines in L1
@@ -76,8 +82,9 @@ __device__ __forceinline__ uint32_t sort_key(const DevGeom &G, unsigned keyoff, 
     const float ys = wrap1(y, G.miny, G.maxy, G.shifty_lo, G.shifty_hi, ly, hy);
     const float zs = wrap1(z, G.minz, G.maxz, G.shiftz_lo, G.shiftz_hi, lz, hz);
     // (a NaN position converts to 0 and the unsigned min below keeps the key inside the table)
-    uint32_t key = (uint32_t)((int)xs + G.mx * ((int)ys + G.my * (int)zs)) - keyoff;
-    key = min(key, (uint32_t)G.lot - 1u);
+    uint32_t key = G.rowblk ? cell_key(G, (int)xs, (int)ys, (int)zs)
+                            : (uint32_t)((int)xs + G.mx * ((int)ys + G.my * (int)zs)) - keyoff;
+    key = min(key, (uint32_t)G.nkeys - 1u);
     if (general) {                                           // kernel-uniform: open or split axes
         bool in = true;
         if (!G.perx) in = (x + G.mxcum > G.x1in) && (x + G.mxcum < G.x2in);
@@ -85,8 +92,8 @@ __device__ __forceinline__ uint32_t sort_key(const DevGeom &G, unsigned keyoff, 
         if (!G.perz && in) in = (z + G.mzcum > G.z1in) && (z + G.mzcum < G.z2in);
         const int dy = (int)hy - (int)ly, dz = (int)hz - (int)lz;
         const int code = ((G.sendy ? dy : 0) + 1) + 3 * ((G.sendz ? dz : 0) + 1);
-        if (code != 4) key = (uint32_t)G.lot + (uint32_t)code;
-        if (!in) key = (uint32_t)G.lot + 9u;
+        if (code != 4) key = (uint32_t)G.nkeys + (uint32_t)code;
+        if (!in) key = (uint32_t)G.nkeys + 9u;
     }
     return key;
 }

@@ -492,12 +492,12 @@ __global__ void __launch_bounds__(256) k_classify_key(Species s, int n, DevGeom 
     classify(G, x, y, z, code, discard);
     s.x[t] = x; s.y[t] = y; s.z[t] = z;
     uint32_t k;
-    if (discard) k = (uint32_t)G.lot + 9u;
-    else if (code != 4) k = (uint32_t)G.lot + (uint32_t)code;
+    if (discard) k = (uint32_t)G.nkeys + 9u;
+    else if (code != 4) k = (uint32_t)G.nkeys + (uint32_t)code;
     else {
         int i = (int)x, j = (int)y, kk = G.dim == 3 ? (int)z : 1;
         i = min(max(i, 1), G.mx); j = min(max(j, 1), G.my); kk = min(max(kk, 1), G.mz);
-        k = (uint32_t)((i - 1) + G.mx * ((j - 1) + G.my * (kk - 1)));
+        k = cell_key(G, i, j, kk);
     }
     key[t] = k;
     slot[t] = atomicAdd(&bincount[k], 1);
@@ -565,7 +565,7 @@ int prt_materialize(tgpu_ctx *h)
 // After prt_sort: sp[s].n = stayers; h_small[s*16 + c] / [s*16 + 8.. ] hold leaver ranges (offset table of the 11 tail bins).
 int prt_sort(tgpu_ctx *h, bool)
 {
-    const int nb = (int)h->G.lot + TGPU_NBIN_EXTRA;
+    const int nb = (int)h->G.nkeys + TGPU_NBIN_EXTRA;
     const bool have_keys = h->keys_valid != 0;      // written by the fused mover for the records as they now sit in sp[]
     h->keys_valid = 0;
     if (!have_keys) { int rc = prt_materialize(h); if (rc) return rc; }
@@ -592,7 +592,7 @@ int prt_sort(tgpu_ctx *h, bool)
             else k_scatter<false><<<cdiv(S.n, 256), 256, 0, h->stream>>>(S, h->alt[s], S.n, h->key[s], slot, off, h->G);
             CKK(h);
         }
-        CK(cudaMemcpyAsync(h->h_small + s * 16, off + (size_t)h->G.lot, 11 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_small + s * 16, off + (size_t)h->G.nkeys, 11 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
     for (int s = 0; s < 2; s++) {
@@ -902,7 +902,7 @@ int prt_mirror_stream(tgpu_ctx *h, tgpu_particle *p, int ions, int lecs)
     cudaStream_t sm = h->stream_main, sh = h->stream_prt, sd = h->stream_d2h;
     h->sp[0].n = ions; h->sp[1].n = lecs; h->keys_valid = 0;
     h->lazy[0] = h->lazy[1] = 0; h->nphys[0] = ions; h->nphys[1] = lecs;
-    const size_t nb = (size_t)h->G.lot + TGPU_NBIN_EXTRA;
+    const size_t nb = (size_t)h->G.nkeys + TGPU_NBIN_EXTRA;
     CK(cudaMemsetAsync(h->bincount, 0, 2 * nb * sizeof(int32_t), sm));
     for (int b = 0; b < 2; b++) { CK(cudaEventRecord(h->ev_stage_free[b], sm)); CK(cudaEventRecord(h->ev_out_free[b], sd)); }
     int i = 0;

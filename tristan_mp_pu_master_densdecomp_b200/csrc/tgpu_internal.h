@@ -24,6 +24,10 @@ struct DevGeom {             // passed by value to kernels
     int g, gz;               // nghost/2, nghostz/2
     int nghost, nghostz;
     long long lot;
+    // sort keys of the cells (tgpu_internal.h cell_key): nkeys bins; rowblk != 0: the (y,z) rows are numbered in 8 x 8 blocks
+    // (x stays the fastest index), so that rows that share field nodes and current cells are swept close together in time
+    long long nkeys;
+    int rowblk, nbj;
     float c, corr, cinv;
     int quirks, pusher, external_fields;
     float ext[6];
@@ -116,6 +120,22 @@ __device__ __forceinline__ size_t row_index(int mx, int my, int nty, int J, int 
     if (TILED) return ((size_t)(((K >> 2) * nty + (J >> 2)) * (long long)mx + i0) << 4) + (size_t)(((K & 3) << 2) | (J & 3));
     return (size_t)((long long)mx * (J + (long long)my * K) + i0);
 }
+
+// Sort key of cell (i, j, k) (1-based).  The reference's reorder key is i-1 + mx*((j-1) + my*(k-1)) (particles.F90:441).
+// With rowblk the rows are enumerated block by block: key = i-1 + mx * (((kb*nbj + jb) << 6) | kl << 3 | jl), (jb, jl) =
+// divmod(j-1, 8), (kb, kl) = divmod(k-1, 8).  Any bijection serves the counting sort; this one keeps a cell run contiguous
+// along x (what the cell-run kernels need) while rows j+-1 and k+-1 -- which read the same node-centred field sectors and
+// flush into the same current tiles -- are processed within ~64 rows of each other instead of my rows apart: their
+// sectors are still in L2 (ncu: DRAM traffic of the fused kernel 150 -> 133 B per particle, 7.52 -> 7.36 ms per launch).
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t cell_key(const DevGeom &G, int i, int j, int k)
+{
+    if (!G.rowblk) return (uint32_t)((i - 1) + G.mx * ((j - 1) + G.my * (k - 1)));
+    const int jj = j - 1, kk = k - 1;
+    const int row = ((((kk >> 3) * G.nbj + (jj >> 3)) << 6) | ((kk & 7) << 3)) | (jj & 7);
+    return (uint32_t)((i - 1) + G.mx * row);
+}
+#endif
 
 void tgpu_set_error(const std::string &s);
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
