@@ -311,6 +311,31 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and with them the first-touch placement of its pinned staging buffers) to the NUMA
+    node its GPU hangs off.  With 8 ranks copying at once, buffers on the wrong socket share one inter-socket link: round 1
+    measured 15-18 GB/s per GPU at N = 8 against 55 GB/s at N = 1.  Best effort: silently does nothing where sysfs does
+    not tell (containers without /sys/bus/pci, single-node hosts)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -400,6 +425,7 @@ def main():
     assert n in GRID and world in (1, n), "--gpus must be 1,2,4,8 and match WORLD_SIZE under torchrun"
     import torch
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -477,15 +503,16 @@ def main():
     achieved = alg_bytes / (md_ms * 1e-3) / 1e9 if md_ms > 0 else 0.0
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             tj = json.load(f)
-        if list(args.cells) == [512, 256, 128] and args.fused:
+        if list(args.cells) == [512, 256, 128] and args.fused and ORDER == 2 and PPC == 16.0:
             traffic = 2 * tj["traffic_per_launch"]            # two launches (ions, electrons) per lap
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_cellrun<2,fused> (gather + Boris push + Esirkepov deposit + sort keys), the two "
-                "launches (ions, electrons) of one lap",
+                "traffic": traffic, "kernel": (f"k_cellrun<{ORDER},fused,lazy> " if ORDER < 3 else "k_cellrun3<fused,lazy> ") +
+                "(gather + Boris push + Esirkepov deposit + sort keys + lazy-sort gather) + k_primal + k_add_shadow_tiled: "
+                "the mover and deposit phases of one lap (two cell-run launches, ions and electrons)",
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": md_ms, "peak_source": peak_src,
                 "phase_ms": ph}
 
@@ -541,7 +568,7 @@ def main():
             link[name] = (1 << 30) / (time.perf_counter() - t1) / 1e9
         del probe, dev
         e2e = {"value": total_particles / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": fbytes + pbytes,
-               "pcie_gbs_measured": link,
+               "pcie_gbs_measured": link, "host_numa_node": numa_node,
                "d2h_bytes_per_step": fbytes + pbytes,
                "mode": ("mirror: fields+particles H2D, one lap, fields+particles D2H as separate tgpu_* calls, pinned host buffers"
                         if args.e2e_plain else
