@@ -118,6 +118,7 @@ int main(int argc, char **argv)
     for (int lap = 1; lap <= laps; lap++) {
         if (mode == "calls") {
             // tristanmainloop.F90:117-272, line for line
+            CALL(tgpu_pre_bc_b, gpu);                                   // :114 (acts only in an all-open 3D box)
             CALL(tgpu_bc_b1, gpu); CALL(tgpu_bc_e1, gpu);               // :117-118
             CALL(tgpu_advance_b_halfstep, gpu);                         // :119
             CALL(tgpu_bc_b1, gpu);                                      // :122
@@ -125,8 +126,10 @@ int main(int argc, char **argv)
             CALL(tgpu_advance_b_halfstep, gpu);                         // :139
             CALL(tgpu_bc_b1, gpu);                                      // :140
             CALL(tgpu_bc_b2, gpu);                                      // :145
+            CALL(tgpu_post_bc_b, gpu); CALL(tgpu_pre_bc_e, gpu);        // :155, :157
             CALL(tgpu_advance_e_fullstep, gpu);                         // :159
             CALL(tgpu_bc_e2, gpu);                                      // :164
+            CALL(tgpu_post_bc_e, gpu);                                  // :165
             CALL(tgpu_reset_currents, gpu);                             // :171
             CALL(tgpu_bc_e1, gpu); CALL(tgpu_bc_b1, gpu);               // :181-182
             CALL(tgpu_deposit_particles, gpu);                          // :183
