@@ -4,6 +4,7 @@
 // on machines without a GPU or without libnccl.
 #include <dlfcn.h>
 #include <stdlib.h>
+#include <unistd.h>
 #include <string.h>
 #include "tgpu_internal.h"
 
@@ -165,8 +166,26 @@ extern "C" int tgpu_comm_init(tgpu_ctx *h, const uint8_t id[128])
 // ---------------------------------------------------------------------------------------------
 typedef int (*fn_AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t);
 
+// Tear-down handshake.  A neighbour's last k_sig_sync may still be polling my signal words when my own last lap is
+// complete (it sets its PULLED, which releases me, and only then reads mine).  So before anything is unmapped or freed:
+// raise FIN in my words, wait (bounded: 3 s) until every mapped neighbour has raised its own -- it does so after
+// synchronising its streams -- and then give the slower side 20 ms to finish the read that saw my FIN.
 static void peer_close(tgpu_ctx *h)
 {
+    if (h->peer && h->sig) {
+        const uint32_t one = 1;
+        cudaMemcpy(h->sig + TGPU_SIG_FIN, &one, sizeof one, cudaMemcpyHostToDevice);
+        for (int r = 0; r < h->size0; r++) {
+            if (!h->peer[r].open || !h->peer[r].sig) continue;
+            for (int tries = 0; tries < 6000; tries++) {
+                uint32_t v = 0;
+                if (cudaMemcpy(&v, h->peer[r].sig + TGPU_SIG_FIN, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); break; }
+                if (v) break;
+                usleep(500);
+            }
+        }
+        usleep(20000);
+    }
     if (h->peer) {
         for (int r = 0; r < h->size0; r++)
             if (h->peer[r].open) for (int a = 0; a < 10; a++) if (h->peer[r].base[a]) cudaIpcCloseMemHandle(h->peer[r].base[a]);

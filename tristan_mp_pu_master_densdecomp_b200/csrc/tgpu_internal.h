@@ -51,6 +51,7 @@ struct PeerRank {
 #define TGPU_SIG_READY 0     // "everything I produce before exchange number s is in memory"
 #define TGPU_SIG_PULLED 1    // "I have finished reading my neighbours' arrays for exchange number s"
 #define TGPU_SIG_TIMEOUT 2   // set by a kernel that gave up waiting (5 s): the job is broken, reported at the next host sync
+#define TGPU_SIG_FIN 3       // "my streams are drained, I am about to unmap and free" (comm.cu peer_close)
 
 struct tgpu_ctx {
     tgpu_params P;
