@@ -1,0 +1,659 @@
+"""A small Fortran-90-subset interpreter: runs subroutines of the REFERENCE'S OWN SOURCE TEXT in fp32.
+
+Why.  The reference (TRISTAN-MP, Fortran + MPI) cannot be compiled in the build image or on the GPU box (no Fortran compiler:
+profiles/r2_toolchain_probe.txt), so the CPU oracle (oracle/pic_oracle.c) -- a hand restatement of the hot-path routines --
+had never been checked against anything produced by the reference.  This module reads a subroutine straight out of
+/root/reference/code/*.F90, applies the cpp conditionals, translates the statements one by one into Python and executes them
+with numpy.float32 scalars (every operation rounds to fp32, in the source's order; integer division truncates; arrays are
+1-based, column-major, and -- as the reference relies on -- not bounds-checked on the first index).  tests/golden/
+make_ref_golden.py uses it to produce golden vectors (committed as tests/golden/ref_*.npz) that pin the oracle; nothing at test
+time or on the GPU box reads /root/reference.
+
+Subset: scalar / array assignments, whole-array assignments and expressions, array sections, do / do while / if-elseif-else,
+one-line if, call (to other translated subroutines or to Python stubs), derived-type components (p(n)%x), the intrinsics
+aint int real min max abs sqrt sum cshift mod modulo.  TEST INFRASTRUCTURE ONLY.
+"""
+import math
+import re
+
+import numpy as np
+
+F = np.float32
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# run-time support
+# ------------------------------------------------------------------------------------------------------------------
+class FArr:
+    """1-based, column-major Fortran array.  a(i,j,k) with an out-of-range first index addresses the flat storage, as the
+    reference's curx(l2,1,1) trick does (particles.F90:1058)."""
+
+    def __init__(self, shape, dtype=np.float32, data=None):
+        shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.shape = shape
+        self.flat = np.zeros(int(np.prod(shape)), dtype) if data is None else data
+        self.strides = [1]
+        for s in shape[:-1]:
+            self.strides.append(self.strides[-1] * s)
+
+    @classmethod
+    def from_c(cls, a):
+        """from a C-ordered numpy array shaped (mz, my, mx) == Fortran (mx, my, mz); shares memory"""
+        shape = tuple(reversed(a.shape))
+        return cls(shape, a.dtype, a.reshape(-1))
+
+    def nd(self):
+        return self.flat.reshape(self.shape, order="F")
+
+    def _scalar_index(self, key):
+        if not isinstance(key, tuple):
+            key = (key,)
+        off = 0
+        for k, st in zip(key, self.strides):
+            off += (int(k) - 1) * st
+        if off < 0 or off >= self.flat.size:
+            raise IndexError(f"flat index {off} outside the array ({self.flat.size})")
+        return off
+
+    @staticmethod
+    def _is_scalar_key(key):
+        key = key if isinstance(key, tuple) else (key,)
+        return all(not isinstance(k, slice) for k in key)
+
+    def _section(self, key):
+        key = key if isinstance(key, tuple) else (key,)
+        idx = []
+        for k, n in zip(key, self.shape):
+            if isinstance(k, slice):
+                lo = 1 if k.start is None else int(k.start)
+                hi = n if k.stop is None else int(k.stop)
+                idx.append(slice(lo - 1, hi))
+            else:
+                idx.append(int(k) - 1)
+        return tuple(idx)
+
+    def __getitem__(self, key):
+        if self._is_scalar_key(key):
+            return self.flat[self._scalar_index(key)]
+        return np.array(self.nd()[self._section(key)])                # sections are values
+
+    def __setitem__(self, key, val):
+        if self._is_scalar_key(key):
+            self.flat[self._scalar_index(key)] = val
+        else:
+            v = val.nd() if isinstance(val, FArr) else val
+            self.nd()[self._section(key)] = v
+
+    def set(self, val):
+        """whole-array assignment"""
+        self.nd()[...] = val.nd() if isinstance(val, FArr) else val
+
+    # whole-array arithmetic (elementwise, fp32)
+    def _bin(self, other, op, rev=False):
+        o = other.nd() if isinstance(other, FArr) else other
+        a = self.nd()
+        r = op(o, a) if rev else op(a, o)
+        out = FArr(self.shape, self.flat.dtype)
+        out.nd()[...] = r
+        return out
+
+    def __add__(self, o): return self._bin(o, np.add)
+    def __radd__(self, o): return self._bin(o, np.add, True)
+    def __sub__(self, o): return self._bin(o, np.subtract)
+    def __rsub__(self, o): return self._bin(o, np.subtract, True)
+    def __mul__(self, o): return self._bin(o, np.multiply)
+    def __rmul__(self, o): return self._bin(o, np.multiply, True)
+    def __truediv__(self, o): return self._bin(o, np.divide)
+    def __neg__(self): return self._bin(F(-1), np.multiply)
+
+
+class Record:
+    """one element of an array of derived type (type particle)"""
+
+    def __init__(self, arr, i):
+        object.__setattr__(self, "_a", arr)
+        object.__setattr__(self, "_i", i)
+
+    def __getattr__(self, name):
+        return self._a[name][self._i]
+
+    def __setattr__(self, name, val):
+        self._a[name][self._i] = val
+
+
+class RecArr:
+    """1-based array of derived type over a numpy structured array"""
+
+    def __init__(self, a):
+        self.a = a
+
+    def __getitem__(self, i):
+        return Record(self.a, int(i) - 1)
+
+
+def fdiv(a, b):
+    if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)):
+        return int(math.trunc(int(a) / int(b))) if abs(int(a)) < 2 ** 52 else int(a) // int(b)
+    return a / b
+
+
+def fpow(a, b):
+    if isinstance(b, (int, np.integer)) and not isinstance(a, (int, np.integer)):
+        r = F(1.0)
+        for _ in range(abs(int(b))):                                  # x**2 -> x*x as every compiler does
+            r = F(r * a) if not isinstance(a, (FArr, np.ndarray)) else r * a
+        return r if b >= 0 else F(1.0) / r
+    return a ** b
+
+
+def fsum(a):
+    """sum(): sequential, in fp32"""
+    v = a.nd().reshape(-1, order="F") if isinstance(a, FArr) else np.asarray(a).reshape(-1, order="F")
+    s = F(0.0)
+    for x in v:
+        s = F(s + x)
+    return s
+
+
+def fcshift(a, shift, dim=1):
+    """cshift(array, shift, dim): result(i) = array(i + shift), circular"""
+    out = FArr(a.shape, a.flat.dtype)
+    out.nd()[...] = np.roll(a.nd(), -int(shift), axis=int(dim) - 1)
+    return out
+
+
+def frange(a, b, c=1):
+    a, b, c = int(a), int(b), int(c)
+    return range(a, b + (1 if c > 0 else -1), c)
+
+
+def faint(x):
+    return F(np.trunc(F(x)))
+
+
+def fmodulo(a, b):
+    if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)):
+        return int(a) - int(b) * math.floor(int(a) / int(b))
+    return F(a - b * np.floor(a / b))
+
+
+def fmod(a, b):
+    if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)):
+        return int(math.fmod(int(a), int(b)))
+    return F(np.fmod(a, b))
+
+
+def fmin(*a):
+    return min(a)
+
+
+def fmax(*a):
+    return max(a)
+
+
+INTRINSICS = {"aint": "faint", "int": "int", "real": "F", "min": "fmin", "max": "fmax", "abs": "abs", "sqrt": "fsqrt", "sum": "fsum",
+              "cshift": "fcshift", "mod": "fmod", "modulo": "fmodulo", "float": "F", "nint": "fnint", "floor": "ffloor"}
+RUNTIME = {"F": F, "FArr": FArr, "fdiv": fdiv, "fpow": fpow, "fsum": fsum, "fcshift": fcshift, "frange": frange, "faint": faint,
+           "fmodulo": fmodulo, "fmod": fmod, "fmin": fmin, "fmax": fmax, "fsqrt": lambda x: F(np.sqrt(F(x))),
+           "fnint": lambda x: int(np.rint(x)), "ffloor": lambda x: int(np.floor(x)), "np": np}
+PYKW = {"in", "is", "lambda", "not", "and", "or", "if", "else", "for", "while", "def", "class", "pass", "del", "from", "as", "with"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# source handling: cpp conditionals, continuation lines, subroutine extraction
+# ------------------------------------------------------------------------------------------------------------------
+def preprocess(text, defines):
+    out, stack = [], []
+    for line in text.splitlines():
+        s = line.strip()
+        if s.startswith("#"):
+            m = re.match(r"#\s*(ifdef|ifndef|else|endif|if|elif|define|undef|include)\b\s*(.*)", s)
+            if not m:
+                continue
+            d, arg = m.group(1), m.group(2).strip()
+            if d == "ifdef":
+                stack.append(arg.split()[0] in defines)
+            elif d == "ifndef":
+                stack.append(arg.split()[0] not in defines)
+            elif d == "if":
+                raise NotImplementedError("#if " + arg)
+            elif d == "else":
+                stack[-1] = not stack[-1]
+            elif d == "endif":
+                stack.pop()
+            continue
+        if all(stack):
+            out.append(line)
+    return "\n".join(out)
+
+
+def strip_comment(line):
+    q = None
+    for i, ch in enumerate(line):
+        if q:
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+        elif ch == "!":
+            return line[:i]
+    return line
+
+
+def statements(text):
+    """comment-free, continuation-joined, lower-cased statements"""
+    out, cur = [], ""
+    for line in text.splitlines():
+        line = strip_comment(line).rstrip()
+        if not line.strip():
+            continue
+        s = line.strip()
+        if s.startswith("&"):
+            s = s[1:]
+        if s.endswith("&"):
+            cur += s[:-1] + " "
+            continue
+        cur += s
+        for part in cur.split(";") if ("'" not in cur and '"' not in cur) else [cur]:
+            if part.strip():
+                out.append(part.strip().lower())
+        cur = ""
+    return out
+
+
+def extract_subroutine(text, name):
+    m = re.search(r"^[ \t]*subroutine\s+" + name + r"\s*(\(|$)", text, flags=re.I | re.M)
+    if not m:
+        raise KeyError(name)
+    e = re.search(r"^[ \t]*end\s*subroutine\s+" + name + r"\b", text[m.start():], flags=re.I | re.M)
+    return text[m.start():m.start() + e.end()]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# expression translation (recursive descent over the Fortran expression grammar)
+# ------------------------------------------------------------------------------------------------------------------
+TOK = re.compile(r"\s*(\d+\.\d*(?:[ed][+-]?\d+)?|\.\d+(?:[ed][+-]?\d+)?|\d+[ed][+-]?\d+|\d+|\.[a-z]+\.|[a-z_]\w*|\*\*|==|/=|<=|>=|[-+*/(),:<>%=])")
+
+
+def tokenize(s):
+    toks, pos = [], 0
+    s = s.strip()
+    while pos < len(s):
+        m = TOK.match(s, pos)
+        if not m:
+            raise SyntaxError(f"cannot tokenize {s[pos:]!r} in {s!r}")
+        toks.append(m.group(1))
+        pos = m.end()
+    return toks
+
+
+class Expr:
+    def __init__(self, toks, ctx):
+        self.t, self.i, self.ctx = toks, 0, ctx
+
+    def peek(self):
+        return self.t[self.i] if self.i < len(self.t) else None
+
+    def next(self):
+        tok = self.t[self.i]
+        self.i += 1
+        return tok
+
+    def expect(self, tok):
+        if self.next() != tok:
+            raise SyntaxError(f"expected {tok} in {' '.join(self.t)}")
+
+    def parse(self):
+        r = self.p_or()
+        if self.peek() is not None:
+            raise SyntaxError(f"trailing {self.peek()!r} in {' '.join(self.t)}")
+        return r
+
+    def p_or(self):
+        l = self.p_and()
+        while self.peek() == ".or.":
+            self.next(); l = f"({l} or {self.p_and()})"
+        return l
+
+    def p_and(self):
+        l = self.p_not()
+        while self.peek() == ".and.":
+            self.next(); l = f"({l} and {self.p_not()})"
+        return l
+
+    def p_not(self):
+        if self.peek() == ".not.":
+            self.next()
+            return f"(not {self.p_not()})"
+        return self.p_rel()
+
+    REL = {".le.": "<=", ".lt.": "<", ".ge.": ">=", ".gt.": ">", ".eq.": "==", ".ne.": "!=", "==": "==", "/=": "!=", "<=": "<=", ">=": ">=",
+           "<": "<", ">": ">"}
+
+    def p_rel(self):
+        l = self.p_add()
+        if self.peek() in self.REL:
+            op = self.REL[self.next()]
+            l = f"({l} {op} {self.p_add()})"
+        return l
+
+    def p_add(self):
+        if self.peek() in ("-", "+"):
+            op = self.next()
+            l = f"({op}{self.p_mul()})"
+        else:
+            l = self.p_mul()
+        while self.peek() in ("+", "-"):
+            op = self.next()
+            l = f"({l} {op} {self.p_mul()})"
+        return l
+
+    def p_mul(self):
+        l = self.p_pow()
+        while self.peek() in ("*", "/"):
+            op = self.next()
+            r = self.p_pow()
+            l = f"({l} * {r})" if op == "*" else f"fdiv({l}, {r})"
+        return l
+
+    def p_pow(self):
+        b = self.p_unary()
+        if self.peek() == "**":
+            self.next()
+            return f"fpow({b}, {self.p_pow()})"
+        return b
+
+    def p_unary(self):
+        if self.peek() in ("-", "+"):
+            op = self.next()
+            return f"({op}{self.p_unary()})"
+        return self.p_primary()
+
+    def p_primary(self):
+        tok = self.next()
+        if tok == "(":
+            e = self.p_or()
+            self.expect(")")
+            r = f"({e})"
+        elif tok == ".true.":
+            r = "True"
+        elif tok == ".false.":
+            r = "False"
+        elif re.match(r"\d|\.\d", tok):
+            if re.fullmatch(r"\d+", tok):
+                r = tok
+            else:
+                r = f"F({tok.replace('d', 'e')})"
+        elif re.match(r"[a-z_]", tok):
+            r = self.p_name(tok)
+        else:
+            raise SyntaxError(f"unexpected {tok!r} in {' '.join(self.t)}")
+        while self.peek() == "%":
+            self.next()
+            r = f"{r}.{self.next()}"
+        return r
+
+    def p_args(self):
+        args = []
+        if self.peek() == ")":
+            self.next()
+            return args
+        while True:
+            # subscript triplet?
+            lo = hi = None
+            if self.peek() == ":":
+                self.next()
+                if self.peek() not in (",", ")"):
+                    hi = self.p_or()
+                args.append(f"slice(None, {hi})")
+            else:
+                lo = self.p_or()
+                if self.peek() == ":":
+                    self.next()
+                    if self.peek() not in (",", ")"):
+                        hi = self.p_or()
+                    args.append(f"slice({lo}, {hi})")
+                elif self.peek() == "=":                               # keyword argument (cshift(a, shift=1, dim=2))
+                    self.next()
+                    args.append(f"{lo.split('.')[-1]}={self.p_or()}")
+                else:
+                    args.append(lo)
+            tok = self.next()
+            if tok == ")":
+                return args
+            if tok != ",":
+                raise SyntaxError(f"expected , or ) in {' '.join(self.t)}")
+
+    def p_name(self, name):
+        ref = self.ctx.ref(name)
+        if self.peek() != "(":
+            return ref
+        self.next()
+        args = self.p_args()
+        if self.ctx.is_array(name):
+            return f"{ref}[{', '.join(args)}]"
+        if name in INTRINSICS:
+            return f"{INTRINSICS[name]}({', '.join(args)})"
+        return f"{ref}({', '.join(args)})"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# statement translation
+# ------------------------------------------------------------------------------------------------------------------
+class Sub:
+    def __init__(self, source, name, defines=(), global_arrays=(), global_ints=()):
+        self.name = name.lower()
+        self.local = {}                  # name -> ("int" | "real" | "logical", dims or None)
+        self.args = []
+        self.global_arrays = {a.lower() for a in global_arrays}
+        self.global_ints = {a.lower() for a in global_ints}
+        text = preprocess(source, set(defines))
+        self.stmts = statements(extract_subroutine(text, name))
+        self.py = self.translate()
+
+    # --- names -------------------------------------------------------------------------------------------------
+    def pyname(self, n):
+        return n + "_" if n in PYKW else n
+
+    def ref(self, n):
+        if n in self.local or n in self.args:
+            return self.pyname(n)
+        if n in INTRINSICS:
+            return INTRINSICS[n]
+        return "g." + self.pyname(n)
+
+    def is_array(self, n):
+        if n in self.local:
+            return self.local[n][1] is not None
+        return n in self.global_arrays
+
+    def kind(self, n):
+        if n in self.local:
+            return self.local[n][0]
+        if n in self.global_ints:
+            return "int"
+        return None
+
+    def ex(self, s):
+        return Expr(tokenize(s), self).parse()
+
+    # --- declarations ----------------------------------------------------------------------------------------------
+    DECL = re.compile(r"^(integer|real|logical|double precision)\b\s*(\([^)]*\))?\s*((?:,\s*[a-z]+(?:\([^)]*\))?\s*)*)(::)?\s*(.*)$")
+
+    def declare(self, st):
+        m = self.DECL.match(st)
+        if not m:
+            return False
+        base, attrs, ents = m.group(1), m.group(3) or "", m.group(5)
+        kind = {"integer": "int", "real": "real", "logical": "logical", "double precision": "real"}[base]
+        dims = None
+        dm = re.search(r"dimension\s*\(([^)]*(?:\([^)]*\)[^)]*)*)\)", attrs)
+        if dm:
+            dims = dm.group(1)
+        # split the entity list on top-level commas
+        parts, depth, cur = [], 0, ""
+        for ch in ents:
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            if ch == "," and depth == 0:
+                parts.append(cur); cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            parts.append(cur)
+        for p_ in parts:
+            p_ = p_.strip().split("=")[0].strip()
+            em = re.match(r"([a-z_]\w*)\s*(?:\((.*)\))?$", p_)
+            if not em:
+                raise SyntaxError("declaration entity " + p_)
+            self.local[em.group(1)] = (kind, em.group(2) or dims)
+        return True
+
+    # --- statements ------------------------------------------------------------------------------------------------
+    def assign(self, lhs, rhs):
+        lhs = lhs.strip()
+        r = self.ex(rhs)
+        m = re.match(r"([a-z_]\w*)\s*$", lhs)
+        if m:
+            n = m.group(1)
+            if self.is_array(n):
+                return f"{self.ref(n)}.set({r})"
+            k = self.kind(n)
+            if k == "int":
+                return f"{self.ref(n)} = int({r})"
+            if k == "real":
+                return f"{self.ref(n)} = F({r})"
+            if k == "logical":
+                return f"{self.ref(n)} = bool({r})"
+            return f"{self.ref(n)} = fassign_global({r})"
+        return f"{self.ex(lhs)} = {r}"
+
+    def split_assign(self, st):
+        depth = 0
+        for i, ch in enumerate(st):
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            elif ch == "=" and depth == 0 and st[i - 1] not in "<>/=" and st[i + 1:i + 2] != "=":
+                return st[:i], st[i + 1:]
+        return None
+
+    def simple(self, st):
+        if st.startswith("call "):
+            m = re.match(r"call\s+([a-z_]\w*)\s*(?:\((.*)\))?$", st)
+            args = Expr(tokenize("(" + (m.group(2) or "") + ")"), self)
+            args.next()
+            a = args.p_args()
+            return f"g.{m.group(1)}({', '.join(a)})"
+        if st in ("return",):
+            return "return"
+        if st in ("continue",):
+            return "pass"
+        if st.startswith("print") or st.startswith("write") or st.startswith("stop"):
+            return "pass"
+        sa = self.split_assign(st)
+        if sa:
+            return self.assign(*sa)
+        raise SyntaxError("statement: " + st)
+
+    def translate(self):
+        hdr = self.stmts[0]
+        m = re.match(r"subroutine\s+([a-z_]\w*)\s*(?:\((.*)\))?", hdr)
+        self.args = [a.strip() for a in (m.group(2) or "").split(",") if a.strip()]
+        body, ind = [], 1
+        decls_done = []
+
+        def emit(s):
+            body.append("    " * ind + s)
+        for st in self.stmts[1:]:
+            if st.startswith("end subroutine") or st.startswith("endsubroutine"):
+                break
+            if st.startswith("implicit") or st.startswith("use ") or st.startswith("intent") or st.startswith("external"):
+                continue
+            if self.declare(st):
+                continue
+            # allocate local arrays lazily, once, at the first executable statement
+            if not decls_done:
+                decls_done.append(1)
+                for n, (k, dims) in self.local.items():
+                    if n in self.args:
+                        continue
+                    if dims is not None:
+                        dd = ", ".join(self.ex(d) for d in self.split_dims(dims))
+                        emit(f"{self.pyname(n)} = FArr(({dd},), {'np.int64' if k == 'int' else 'np.float32'})")
+                    elif k == "real":
+                        emit(f"{self.pyname(n)} = F(0.0)")
+                    elif k == "int":
+                        emit(f"{self.pyname(n)} = 0")
+                    else:
+                        emit(f"{self.pyname(n)} = False")
+            m = re.match(r"if\s*\((.*)\)\s*then$", st)
+            if m:
+                emit(f"if {self.ex(m.group(1))}:"); ind += 1; continue
+            m = re.match(r"else\s*if\s*\((.*)\)\s*then$", st)
+            if m:
+                ind -= 1; emit(f"elif {self.ex(m.group(1))}:"); ind += 1; continue
+            if st == "else":
+                ind -= 1; emit("else:"); ind += 1; continue
+            if st in ("endif", "end if"):
+                emit("pass"); ind -= 1; continue
+            m = re.match(r"do\s+while\s*\((.*)\)$", st)
+            if m:
+                emit(f"while {self.ex(m.group(1))}:"); ind += 1; continue
+            m = re.match(r"do\s+([a-z_]\w*)\s*=\s*(.*)$", st)
+            if m:
+                parts = self.split_dims(m.group(2))
+                if self.ref(m.group(1)).startswith("g."):
+                    raise SyntaxError("loop variable must be local: " + st)
+                emit(f"for {self.ref(m.group(1))} in frange({', '.join(self.ex(p_) for p_ in parts)}):")
+                ind += 1; continue
+            if st in ("enddo", "end do"):
+                emit("pass"); ind -= 1; continue
+            m = re.match(r"if\s*\(", st)
+            if m:
+                # one-line if: find the matching parenthesis
+                depth, j = 0, st.index("(")
+                for j in range(st.index("("), len(st)):
+                    depth += st[j] == "("
+                    depth -= st[j] == ")"
+                    if depth == 0:
+                        break
+                cond, rest = st[st.index("(") + 1:j], st[j + 1:].strip()
+                emit(f"if {self.ex(cond)}:"); ind += 1; emit(self.simple(rest)); ind -= 1
+                continue
+            emit(self.simple(st))
+        args = ", ".join(["g"] + [self.pyname(a) for a in self.args])
+        return f"def {self.name}({args}):\n" + "\n".join(body or ["    pass"]) + "\n"
+
+    @staticmethod
+    def split_dims(s):
+        parts, depth, cur = [], 0, ""
+        for ch in s:
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            if ch == "," and depth == 0:
+                parts.append(cur.strip()); cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            parts.append(cur.strip())
+        return parts
+
+    def compile(self):
+        ns = dict(RUNTIME)
+        ns["fassign_global"] = lambda v: v
+        exec(compile(self.py, f"<f90:{self.name}>", "exec"), ns)
+        return ns[self.name]
+
+
+class Globals:
+    """module variables of the reference (m_fields, m_particles, ...) as attributes"""
+
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, v)

@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Golden vectors produced by the REFERENCE'S OWN SOURCE TEXT (run in THIS container, where /root/reference exists).
+
+The reference cannot be compiled anywhere we can reach (no Fortran compiler in the image or on the GPU box), so its hot-path
+subroutines are executed by the Fortran-subset interpreter tests/golden/f90run.py: the text of each subroutine is read from
+/root/reference/code/*.F90, cpp-preprocessed with the build's defines, translated statement by statement and run in fp32.
+The inputs (seeded, generated here) and the reference's outputs are stored in tests/golden/ref_*.npz; tests/test_ref_golden.py
+checks the CPU oracle against them (bit for bit) and tests/test_gpu_ref_golden.py the CUDA library.  Re-run:
+
+    python tests/golden/make_ref_golden.py            # needs /root/reference; takes a few minutes (a Python interpreter of Fortran)
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import f90run as R  # noqa: E402
+
+F = np.float32
+REF = os.environ.get("TRISTAN_REFERENCE", "/root/reference")
+
+
+def src(name):
+    return open(os.path.join(REF, "code", name)).read()
+
+
+def constants():
+    """particles.F90:238-250, evaluated as Fortran does (3/2. etc. are fp32 divisions)"""
+    return dict(three=F(3.), two=F(2.), thhalf=F(F(3) / F(2.)), nineighth=F(F(9) / F(8.)), one=F(1.), threeq=F(F(3) / F(4.)),
+                twoth=F(F(2) / F(3.)), half=F(F(1) / F(2.)), third=F(F(1) / F(3.)), quart=F(F(1) / F(4.)), sixth=F(F(1) / F(6.)),
+                negsixth=F(F(-1) / F(6.)), negone=F(-1.))
+
+
+GINTS = {"ix", "iy", "iz", "mx", "my", "mz", "lot", "nghost", "nghostz", "periodicx", "periodicy", "periodicz", "size0", "sizex", "sizey",
+         "sizez", "rank", "ions", "lecs", "maxhlf", "ntimes", "external_fields", "debug", "highorder"}
+GARR = {"ex", "ey", "ez", "bx", "by", "bz", "curx", "cury", "curz", "temp", "p"}
+
+
+def grid(dim, order, n):
+    ng = 5 if order <= 1 else 7
+    ngz = ng if dim == 3 else 5
+    mx, my = n[0] + ng, n[1] + ng
+    mz = n[2] + ngz if dim == 3 else 1
+    return ng, ngz, mx, my, mz
+
+
+# ------------------------------------------------------------------------------------------------------------
+# G1: the deposit kernels -- zigzag (particles.F90:550-669), densdecomp_{1,2,3}ord (:678-1358), 2D and 3D branches
+# ------------------------------------------------------------------------------------------------------------
+def gen_deposit():
+    out = {}
+    names = {0: "zigzag", 1: "densdecomp_1ord", 2: "densdecomp_2ord", 3: "densdecomp_3ord"}
+    text = src("particles.F90")
+    for dim in (2, 3):
+        for order in (0, 1, 2, 3):
+            defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+            sub = R.Sub(text, names[order], defines=defines, global_arrays=GARR, global_ints=GINTS).compile()
+            n = (9, 8, 7)
+            ng, ngz, mx, my, mz = grid(dim, order, n)
+            g = R.Globals(mx=mx, my=my, mz=mz, ix=1, iy=mx, iz=mx * my if dim == 3 else 0, lot=mx * my * mz,
+                          curx=R.FArr((mx, my, mz)), cury=R.FArr((mx, my, mz)), curz=R.FArr((mx, my, mz)), q=F(0), **constants())
+            rng = np.random.default_rng(100 * dim + order)
+            npart = 96
+            lo = ng // 2 + 1
+            x1 = (lo + rng.random(npart) * n[0]).astype(F)
+            y1 = (lo + rng.random(npart) * n[1]).astype(F)
+            z1 = ((ngz // 2 + 1) + rng.random(npart) * n[2]).astype(F) if dim == 3 else (3 + rng.random(npart)).astype(F)
+            d = ((rng.random((3, npart)) - 0.5) * 0.88).astype(F)
+            # a few particles exactly on cell boundaries / half cells, where the shape branches switch
+            x1[:6] = np.array([lo + 2, lo + 2.5, lo + 3, lo + 3.5, lo + 1, lo + 4.5], F)
+            d[0, :3] = np.array([0.25, -0.25, -0.4], F)
+            x2, y2, z2 = (x1 + d[0]).astype(F), (y1 + d[1]).astype(F), (z1 + d[2]).astype(F)
+            q = ((rng.random(npart) - 0.5) * 2).astype(F)
+            for i in range(npart):
+                g.q = F(q[i])
+                if order == 0:
+                    sub(g, x2[i], y2[i], z2[i], x1[i], y1[i], z1[i], False)
+                else:
+                    sub(g, x2[i], y2[i], z2[i], x1[i], y1[i], z1[i], False)
+            key = f"d{dim}o{order}"
+            for nm, a in (("x1", x1), ("y1", y1), ("z1", z1), ("x2", x2), ("y2", y2), ("z2", z2), ("q", q)):
+                out[f"{key}_{nm}"] = a
+            for nm in ("curx", "cury", "curz"):
+                out[f"{key}_{nm}"] = getattr(g, nm).nd().transpose(2, 1, 0).copy()        # C order (mz, my, mx)
+            out[f"{key}_n"] = np.array(n, np.int32)
+            print("deposit", key, "sum|curx| =", float(np.abs(out[f"{key}_curx"]).sum()))
+    np.savez_compressed(os.path.join(HERE, "ref_deposit.npz"), **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter"]
+    for w in which:
+        globals()["gen_" + w]()

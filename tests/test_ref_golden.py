@@ -1,0 +1,43 @@
+"""The CPU oracle against golden vectors produced by the REFERENCE'S OWN SOURCE TEXT.
+
+tests/golden/ref_*.npz were generated in the build container by tests/golden/make_ref_golden.py: the hot-path subroutines
+are read from /root/reference/code/*.F90 and executed in fp32 by the Fortran-subset interpreter tests/golden/f90run.py (the
+reference cannot be compiled anywhere we can reach).  These tests read only the committed .npz files.  They are what pins
+oracle/pic_oracle.c to the reference: bit-exact for the deposits, stencils and filters (same operations in the same order),
+a few ulp for the movers (sum order inside sum() and the compiler's contraction choices are not part of the source text).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+import pic_testlib as T
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("order", [0, 1, 2, 3])
+def test_deposit_kernels_match_the_reference_source(dim, order):
+    """zigzag / densdecomp_{1,2,3}ord (particles.F90:550-1358), 96 single-particle deposits accumulated in the reference's
+    order, including particles on cell boundaries and half cells where the shape branches switch: BIT-EXACT"""
+    z = load("ref_deposit.npz")
+    key = f"d{dim}o{order}"
+    n = tuple(int(v) for v in z[key + "_n"])
+    w = T.oracle_world(dim=dim, order=order, n=n, ppc=0.0, init="none", seed_fields=0)
+    r = w.ranks[0]
+    cf = C.c_float
+    for i in range(z[key + "_q"].size):
+        r.call("deposit_one", cf(z[key + "_x2"][i]), cf(z[key + "_y2"][i]), cf(z[key + "_z2"][i]),
+               cf(z[key + "_x1"][i]), cf(z[key + "_y1"][i]), cf(z[key + "_z1"][i]), cf(z[key + "_q"][i]))
+    for c, nm in enumerate(("curx", "cury", "curz")):
+        ref = z[f"{key}_{nm}"]
+        got = r.arr(6 + c)
+        assert got.shape == ref.shape
+        assert np.array_equal(got, ref), f"{key} {nm}: max |diff| {np.abs(got - ref).max():.3e} (max |ref| {np.abs(ref).max():.3e})"
