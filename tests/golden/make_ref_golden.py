@@ -89,6 +89,47 @@ def gen_deposit():
     np.savez_compressed(os.path.join(HERE, "ref_deposit.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G2: the Yee solver -- advance_b_halfstep (fields.F90:586-728), advance_e_fullstep (:739-870), index ranges included
+# ------------------------------------------------------------------------------------------------------------
+def field_globals(dim, order, n, periodic, rng, c=0.45, corr=1.025):
+    ng, ngz, mx, my, mz = grid(dim, order, n)
+    g = R.Globals(mx=mx, my=my, mz=mz, ix=1, iy=mx, iz=mx * my if dim == 3 else 0, lot=mx * my * mz, nghost=ng, nghostz=ngz,
+                  periodicx=periodic[0], periodicy=periodic[1], periodicz=periodic[2], size0=1, sizex=1, sizey=1, sizez=1, rank=0,
+                  c=F(c), corr=F(corr), **constants())
+    for nm in ("ex", "ey", "ez", "bx", "by", "bz", "curx", "cury", "curz"):
+        a = R.FArr((mx, my, mz))
+        a.flat[:] = (rng.standard_normal(a.flat.size) * 0.1).astype(F)
+        setattr(g, nm, a)
+    return g
+
+
+def c_order(a):
+    return a.nd().transpose(2, 1, 0).copy()
+
+
+def gen_fields():
+    out = {}
+    text = src("fields.F90")
+    cases = [(3, 2, (1, 1, 1)), (3, 1, (0, 1, 1)), (3, 2, (0, 0, 0)), (3, 2, (1, 0, 1)), (2, 1, (1, 1, 1)), (2, 2, (0, 1, 1)), (2, 2, (0, 0, 1))]
+    for ci, (dim, order, per) in enumerate(cases):
+        defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+        bhalf = R.Sub(text, "advance_b_halfstep", defines=defines, global_arrays=GARR, global_ints=GINTS).compile()
+        efull = R.Sub(text, "advance_e_fullstep", defines=defines, global_arrays=GARR, global_ints=GINTS).compile()
+        addc = R.Sub(text, "add_current", defines=defines, global_arrays=GARR, global_ints=GINTS).compile()
+        n = (8, 7, 6)
+        g = field_globals(dim, order, n, per, np.random.default_rng(200 + ci))
+        key = f"f{ci}"
+        out[key + "_meta"] = np.array([dim, order, *per, *n], np.int32)
+        for a, nm in enumerate(("ex", "ey", "ez", "bx", "by", "bz", "curx", "cury", "curz")):
+            out[f"{key}_in{a}"] = c_order(getattr(g, nm))
+        bhalf(g); efull(g); bhalf(g); addc(g)
+        for a, nm in enumerate(("ex", "ey", "ez", "bx", "by", "bz")):
+            out[f"{key}_out{a}"] = c_order(getattr(g, nm))
+        print("fields", key, dim, order, per)
+    np.savez_compressed(os.path.join(HERE, "ref_fields.npz"), **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["deposit", "fields", "mover", "filter"]
     for w in which:
