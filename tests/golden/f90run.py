@@ -28,6 +28,8 @@ class FArr:
     """1-based, column-major Fortran array.  a(i,j,k) with an out-of-range first index addresses the flat storage, as the
     reference's curx(l2,1,1) trick does (particles.F90:1058)."""
 
+    __array_ufunc__ = None               # numpy scalars defer to the reflected operators below
+
     def __init__(self, shape, dtype=np.float32, data=None):
         shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
         self.shape = shape
@@ -191,9 +193,9 @@ def fmax(*a):
     return max(a)
 
 
-INTRINSICS = {"aint": "faint", "int": "int", "real": "F", "min": "fmin", "max": "fmax", "abs": "abs", "sqrt": "fsqrt", "sum": "fsum",
+INTRINSICS = {"aint": "faint", "int": "int", "real": "freal", "min": "fmin", "max": "fmax", "abs": "abs", "sqrt": "fsqrt", "sum": "fsum",
               "cshift": "fcshift", "mod": "fmod", "modulo": "fmodulo", "float": "F", "nint": "fnint", "floor": "ffloor"}
-RUNTIME = {"F": F, "FArr": FArr, "fdiv": fdiv, "fpow": fpow, "fsum": fsum, "fcshift": fcshift, "frange": frange, "faint": faint,
+RUNTIME = {"freal": lambda x, *kind: F(x), "F": F, "FArr": FArr, "fdiv": fdiv, "fpow": fpow, "fsum": fsum, "fcshift": fcshift, "frange": frange, "faint": faint,
            "fmodulo": fmodulo, "fmod": fmod, "fmin": fmin, "fmax": fmax, "fsqrt": lambda x: F(np.sqrt(F(x))),
            "fnint": lambda x: int(np.rint(x)), "ffloor": lambda x: int(np.floor(x)), "np": np}
 PYKW = {"in", "is", "lambda", "not", "and", "or", "if", "else", "for", "while", "def", "class", "pass", "del", "from", "as", "with"}
@@ -460,7 +462,7 @@ class Sub:
             return self.pyname(n)
         if n in INTRINSICS:
             return INTRINSICS[n]
-        return "g." + self.pyname(n)
+        return "_g." + self.pyname(n)
 
     def is_array(self, n):
         if n in self.local:
@@ -547,7 +549,7 @@ class Sub:
             args = Expr(tokenize("(" + (m.group(2) or "") + ")"), self)
             args.next()
             a = args.p_args()
-            return f"g.{m.group(1)}({', '.join(a)})"
+            return f"_g.{m.group(1)}({', '.join(a)})"
         if st in ("return",):
             return "return"
         if st in ("continue",):
@@ -606,7 +608,7 @@ class Sub:
             m = re.match(r"do\s+([a-z_]\w*)\s*=\s*(.*)$", st)
             if m:
                 parts = self.split_dims(m.group(2))
-                if self.ref(m.group(1)).startswith("g."):
+                if self.ref(m.group(1)).startswith("_g."):
                     raise SyntaxError("loop variable must be local: " + st)
                 emit(f"for {self.ref(m.group(1))} in frange({', '.join(self.ex(p_) for p_ in parts)}):")
                 ind += 1; continue
@@ -625,7 +627,7 @@ class Sub:
                 emit(f"if {self.ex(cond)}:"); ind += 1; emit(self.simple(rest)); ind -= 1
                 continue
             emit(self.simple(st))
-        args = ", ".join(["g"] + [self.pyname(a) for a in self.args])
+        args = ", ".join(["_g"] + [self.pyname(a) for a in self.args])
         return f"def {self.name}({args}):\n" + "\n".join(body or ["    pass"]) + "\n"
 
     @staticmethod
