@@ -169,6 +169,13 @@ def frange(a, b, c=1):
     return range(a, b + (1 if c > 0 else -1), c)
 
 
+def fexit(a, b, c=1):
+    """value of a DO variable after normal termination"""
+    a, b, c = int(a), int(b), int(c)
+    n = max((b - a + c) // c, 0)
+    return a + n * c
+
+
 def faint(x):
     return F(np.trunc(F(x)))
 
@@ -195,7 +202,7 @@ def fmax(*a):
 
 INTRINSICS = {"aint": "faint", "int": "int", "real": "freal", "min": "fmin", "max": "fmax", "abs": "abs", "sqrt": "fsqrt", "sum": "fsum",
               "cshift": "fcshift", "mod": "fmod", "modulo": "fmodulo", "float": "F", "nint": "fnint", "floor": "ffloor"}
-RUNTIME = {"freal": lambda x, *kind: F(x), "F": F, "FArr": FArr, "fdiv": fdiv, "fpow": fpow, "fsum": fsum, "fcshift": fcshift, "frange": frange, "faint": faint,
+RUNTIME = {"freal": lambda x, *kind: F(x), "F": F, "FArr": FArr, "fdiv": fdiv, "fpow": fpow, "fsum": fsum, "fcshift": fcshift, "frange": frange, "fexit": fexit, "faint": faint,
            "fmodulo": fmodulo, "fmod": fmod, "fmin": fmin, "fmax": fmax, "fsqrt": lambda x: F(np.sqrt(F(x))),
            "fnint": lambda x: int(np.rint(x)), "ffloor": lambda x: int(np.floor(x)), "np": np}
 PYKW = {"in", "is", "lambda", "not", "and", "or", "if", "else", "for", "while", "def", "class", "pass", "del", "from", "as", "with"}
@@ -567,6 +574,7 @@ class Sub:
         self.args = [a.strip() for a in (m.group(2) or "").split(",") if a.strip()]
         body, ind = [], 1
         decls_done = []
+        loops, nloop = [], [0]
 
         def emit(s):
             body.append("    " * ind + s)
@@ -604,16 +612,26 @@ class Sub:
                 emit("pass"); ind -= 1; continue
             m = re.match(r"do\s+while\s*\((.*)\)$", st)
             if m:
-                emit(f"while {self.ex(m.group(1))}:"); ind += 1; continue
+                emit(f"while {self.ex(m.group(1))}:"); ind += 1; loops.append((None, None)); continue
             m = re.match(r"do\s+([a-z_]\w*)\s*=\s*(.*)$", st)
             if m:
                 parts = self.split_dims(m.group(2))
                 if self.ref(m.group(1)).startswith("_g."):
                     raise SyntaxError("loop variable must be local: " + st)
-                emit(f"for {self.ref(m.group(1))} in frange({', '.join(self.ex(p_) for p_ in parts)}):")
+                # Fortran evaluates the bounds once and leaves the variable at its first failing value after the loop
+                # (optimized_filters.F90 relies on that: "i = ntimes-1" after `do i=2,ntimes-2,2`)
+                nloop[0] += 1
+                b = f"_b{nloop[0]}"
+                emit(f"{b} = ({', '.join(self.ex(p_) for p_ in parts)},)")
+                emit(f"for {self.ref(m.group(1))} in frange(*{b}):")
+                loops.append((self.ref(m.group(1)), b))
                 ind += 1; continue
             if st in ("enddo", "end do"):
-                emit("pass"); ind -= 1; continue
+                emit("pass"); ind -= 1
+                var, b = loops.pop()
+                if var is not None:
+                    emit(f"{var} = fexit(*{b})")
+                continue
             m = re.match(r"if\s*\(", st)
             if m:
                 # one-line if: find the matching parenthesis

@@ -179,6 +179,87 @@ def gen_mover():
     np.savez_compressed(os.path.join(HERE, "ref_mover.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G4: the digital filters -- apply_filter1_opt (filter.F90:8-221) and filter_x / filter_y / filter_z
+#     (optimized_filters.F90:459-915).  The MPI layer copies a single periodic rank makes to itself are replaced by the
+#     reference's own local-copy routines copylayrx / copylayry (fieldboundaries.F90:714-785) and, for z, by the same
+#     operation on the third index (the reference has no local z variant: its z copies always go through MPI_SendRecv).
+# ------------------------------------------------------------------------------------------------------------
+def layer_copies(g, defines):
+    fb = src("fieldboundaries.F90")
+    cx = R.Sub(fb, "copylayrx", defines=defines, global_arrays=GARR, global_ints=GINTS).compile()
+    cy = R.Sub(fb, "copylayry", defines=defines, global_arrays=GARR, global_ints=GINTS).compile()
+
+    def cz(bx, by, bz, mx, my, mz, lt, ls, nt, ns):
+        for a in (bx, by, bz):
+            v = a.nd()
+            v[:, :, lt - 1] = v[:, :, ls - 1]
+        for a in (bx, by, bz):
+            v = a.nd()
+            v[:, :, nt - 1] = v[:, :, ns - 1]
+    g.copy_layrx1_opt = lambda *a: cx(g, *a)
+    g.copy_layry1_opt = lambda *a: cy(g, *a)
+    g.copy_layrz1_opt = cz
+
+
+def gen_filter():
+    out = {}
+    for ci, (dim, order, ntimes) in enumerate([(2, 1, 3), (3, 2, 2), (3, 1, 3), (2, 2, 4)]):
+        defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+        f1 = R.Sub(src("filter.F90"), "apply_filter1_opt", defines=defines, global_arrays=GARR, global_ints=GINTS).compile()
+        n = (8, 7, 6)
+        g = field_globals(dim, order, n, (1, 1, 1), np.random.default_rng(400 + ci))
+        g.ntimes = ntimes
+        g.temp = R.FArr((g.mx, g.my, g.mz))
+        layer_copies(g, defines)
+        key = f"f1_{ci}"
+        out[key + "_meta"] = np.array([dim, order, 1, 1, 1, *n, ntimes], np.int32)
+        for c, nm in enumerate(("curx", "cury", "curz")):
+            out[f"{key}_in{c}"] = c_order(getattr(g, nm))
+        f1(g)
+        for c, nm in enumerate(("curx", "cury", "curz")):
+            out[f"{key}_out{c}"] = c_order(getattr(g, nm))
+        print("filter1", key, dim, order, ntimes)
+    # filter_x / filter_y / filter_z on one component with given ghost slabs
+    text = src("optimized_filters.F90")
+    for ci, (dim, order, ntimes) in enumerate([(3, 2, 3), (3, 1, 4), (2, 2, 2), (3, 2, 5)]):
+        defines = {"MPI", "filter2"} | ({"twoD"} if dim == 2 else set())
+        n = (9, 8, 7)
+        rng = np.random.default_rng(500 + ci)
+        g = field_globals(dim, order, n, (1, 1, 1), rng)
+        g.ntimes = ntimes
+        key = f"f2_{ci}"
+        out[key + "_meta"] = np.array([dim, order, 1, 1, 1, *n, ntimes], np.int32)
+        gh = g.nghost // 2
+        ghz = g.nghostz // 2
+        rng_lo = (gh + 1, gh + 1, ghz + 1 if dim == 3 else 1)
+        rng_hi = (g.mx - gh - 1, g.my - gh - 1, g.mz - ghz - 1 if dim == 3 else 1)
+        out[key + "_in"] = c_order(g.curx)
+        for axis, nm in enumerate(("filter_x", "filter_y", "filter_z")):
+            if dim == 2 and axis == 2:
+                continue
+            sub = R.Sub(text, nm, defines=defines, global_arrays=GARR, global_ints=GINTS)
+            fn = sub.compile()
+            shape = [g.mx, g.my, g.mz]
+            shape[axis] = 2 * ntimes
+            ghost = R.FArr(tuple(shape))
+            # periodic single rank: low ghosts = my last ntimes interior cells, high ghosts = my first ntimes
+            cur = g.curx.nd()
+            sl_lo = [slice(None)] * 3; sl_hi = [slice(None)] * 3
+            sl_lo[axis] = slice(rng_hi[axis] - ntimes, rng_hi[axis]); sl_hi[axis] = slice(rng_lo[axis] - 1, rng_lo[axis] - 1 + ntimes)
+            gv = ghost.nd()
+            d_lo = [slice(None)] * 3; d_hi = [slice(None)] * 3
+            d_lo[axis] = slice(0, ntimes); d_hi[axis] = slice(ntimes, 2 * ntimes)
+            gv[tuple(d_lo)] = cur[tuple(sl_lo)]; gv[tuple(d_hi)] = cur[tuple(sl_hi)]
+            args = sub.args
+            vals = dict(cur=g.curx, ghost=ghost, xghost=ghost, yghost=ghost, zghost=ghost, istr=rng_lo[0], ifin=rng_hi[0], jstr=rng_lo[1],
+                        jfin=rng_hi[1], kstr=rng_lo[2], kfin=rng_hi[2], ntimes=ntimes, mx=g.mx, my=g.my, mz=g.mz)
+            fn(g, *[vals[a] for a in args])
+            out[f"{key}_after{axis}"] = c_order(g.curx)
+        print("filter2", key, dim, order, ntimes)
+    np.savez_compressed(os.path.join(HERE, "ref_filter.npz"), **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["deposit", "fields", "mover", "filter"]
     for w in which:

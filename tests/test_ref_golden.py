@@ -87,3 +87,38 @@ def test_movers_match_the_reference_source(dim, order):
         d = np.abs(p[k][:n].astype(np.float64) - pout[k].astype(np.float64))
         worst = max(worst, float(d.max()))
         assert np.array_equal(p[k][:n], pout[k]), f"{key} {k}: {int((d > 0).sum())} of {n} differ, max |diff| {d.max():.3e}"
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_filter1_matches_the_reference_source(case):
+    """apply_filter1_opt (filter.F90:8-221): ntimes passes of the 9- / 27-point stencil through `temp`, one ghost layer refreshed
+    per pass (the reference's MPI self-exchange replaced by its own local copylayrx / copylayry): BIT-EXACT on the interior
+    and on the refreshed ghost layers"""
+    z = load("ref_filter.npz")
+    key = f"f1_{case}"
+    meta = z[key + "_meta"]
+    w = _world_from_meta(meta[:8], ntimes=int(meta[8]), filter_kind=1)
+    r = w.ranks[0]
+    for c in range(3):
+        r.arr(6 + c)[...] = z[f"{key}_in{c}"]
+    w.call("apply_filter1")
+    for c in range(3):
+        assert np.array_equal(T.interior(r, r.arr(6 + c)), T.interior(r, z[f"{key}_out{c}"])), O.ARR_NAMES[6 + c]
+        assert np.array_equal(r.arr(6 + c), z[f"{key}_out{c}"]), ("ghost layers", O.ARR_NAMES[6 + c])
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_filter2_sweeps_match_the_reference_source(case):
+    """filter_x, filter_y, filter_z (optimized_filters.F90:459-915) on one component, each with an ntimes-deep ghost slab of a
+    periodic single rank: the in-place two-register sweep incl. its even / odd tails and its use of the loop variable after
+    the loop: BIT-EXACT on the interior"""
+    z = load("ref_filter.npz")
+    key = f"f2_{case}"
+    meta = z[key + "_meta"]
+    w = _world_from_meta(meta[:8], ntimes=int(meta[8]), filter_kind=2)
+    r = w.ranks[0]
+    r.arr(O.CURX)[...] = z[key + "_in"]
+    w.call("apply_filter2")
+    last = 2 if int(meta[0]) == 3 else 1
+    ref = z[f"{key}_after{last}"]
+    assert np.array_equal(T.interior(r, r.arr(O.CURX)), T.interior(r, ref)), float(np.abs(T.interior(r, r.arr(O.CURX)) - T.interior(r, ref)).max())
