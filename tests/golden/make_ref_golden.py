@@ -260,6 +260,43 @@ def gen_filter():
     np.savez_compressed(os.path.join(HERE, "ref_filter.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G5: radiation boundaries -- bc_b2 / bc_e2 -> surface (fieldboundaries.F90:274-295, 403-426, 493-606) and the edge fixes
+#     pre_bc_b / post_bc_b / pre_bc_e / post_bc_e -> preledge / postedge (:114-163, 437-482, 2200-2505).  The callers are
+#     executed too (their rotated argument lists are part of the source); the ghost refresh that follows each of them
+#     (bc_b1 / bc_e1, MPI) is stubbed out and tested separately.
+# ------------------------------------------------------------------------------------------------------------
+def gen_radiation():
+    out = {}
+    fb = src("fieldboundaries.F90")
+    cases = [(3, 1, (0, 0, 0)), (3, 2, (0, 1, 1)), (3, 2, (1, 0, 1)), (2, 1, (0, 1, 1)), (2, 2, (0, 0, 1)), (2, 1, (1, 0, 1))]
+    for ci, (dim, order, per) in enumerate(cases):
+        defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+        n = (8, 7, 6)
+        g = field_globals(dim, order, n, per, np.random.default_rng(600 + ci))
+        g.radiationx, g.radiationy, g.radiationz = 1 - per[0], 1 - per[1], 1 - per[2]
+        if dim == 2 and g.radiationy == 1:
+            g.radiationz = 1                                           # fieldboundaries.F90:91-93 (#ifdef twoD)
+        gi = GINTS | {"radiationx", "radiationy", "radiationz"}
+        sub = {nm: R.Sub(fb, nm, defines=defines, global_arrays=GARR, global_ints=gi).compile()
+               for nm in ("surface", "preledge", "postedge", "bc_b2", "bc_e2", "pre_bc_b", "post_bc_b", "pre_bc_e", "post_bc_e")}
+        for nm in ("surface", "preledge", "postedge"):
+            setattr(g, nm, (lambda f: (lambda *a: f(g, *a)))(sub[nm]))
+        g.bc_b1 = lambda: None
+        g.bc_e1 = lambda: None
+        key = f"r{ci}"
+        out[key + "_meta"] = np.array([dim, order, *per, *n], np.int32)
+        for a, nm in enumerate(("ex", "ey", "ez", "bx", "by", "bz")):
+            out[f"{key}_in{a}"] = c_order(getattr(g, nm))
+        seq = ["pre_bc_b", "bc_b2", "post_bc_b", "pre_bc_e", "bc_e2", "post_bc_e"]
+        for si, nm in enumerate(seq):
+            sub[nm](g)
+            for a, fn in enumerate(("ex", "ey", "ez", "bx", "by", "bz")):
+                out[f"{key}_s{si}_{a}"] = c_order(getattr(g, fn))
+        print("radiation", key, dim, order, per)
+    np.savez_compressed(os.path.join(HERE, "ref_radiation.npz"), **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["deposit", "fields", "mover", "filter"]
     for w in which:

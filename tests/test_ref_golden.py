@@ -122,3 +122,22 @@ def test_filter2_sweeps_match_the_reference_source(case):
     last = 2 if int(meta[0]) == 3 else 1
     ref = z[f"{key}_after{last}"]
     assert np.array_equal(T.interior(r, r.arr(O.CURX)), T.interior(r, ref)), float(np.abs(T.interior(r, r.arr(O.CURX)) - T.interior(r, ref)).max())
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_radiation_boundaries_match_the_reference_source(case):
+    """pre_bc_b, bc_b2, post_bc_b, pre_bc_e, bc_e2, post_bc_e with their rotated calls of surface / preledge / postedge
+    (fieldboundaries.F90:114-163, 274-295, 403-482, 493-606, 2200-2505), the ghost refresh after each left out on both sides:
+    BIT-EXACT after every one of the six calls"""
+    z = load("ref_radiation.npz")
+    key = f"r{case}"
+    w = _world_from_meta(z[key + "_meta"])
+    r = w.ranks[0]
+    for a in range(6):
+        r.arr(a)[...] = z[f"{key}_in{a}"]
+    steps = [("edges", 0), ("surface_b",), ("edges", 1), ("edges", 2), ("surface_e",), ("edges", 3)]
+    for si, st in enumerate(steps):
+        r.call(*st)
+        for a in range(6):
+            ref = z[f"{key}_s{si}_{a}"]
+            assert np.array_equal(r.arr(a), ref), (st, O.ARR_NAMES[a], float(np.abs(r.arr(a) - ref).max()))
