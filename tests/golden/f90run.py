@@ -11,7 +11,8 @@ time or on the GPU box reads /root/reference.
 
 Subset: scalar / array assignments, whole-array assignments and expressions, array sections, do / do while / if-elseif-else,
 one-line if, call (to other translated subroutines or to Python stubs), derived-type components (p(n)%x), the intrinsics
-aint int real min max abs sqrt sum cshift mod modulo.  TEST INFRASTRUCTURE ONLY.
+aint int real min max abs sqrt sum cshift mod modulo.  MPI: only the single-rank case is modelled -- MPI_SendRecv to oneself
+(what one rank on a periodic axis does) is "recvbuf = sendbuf"; other mpi_* calls are dropped.  TEST INFRASTRUCTURE ONLY.
 """
 import math
 import re
@@ -84,7 +85,14 @@ class FArr:
             self.flat[self._scalar_index(key)] = val
         else:
             v = val.nd() if isinstance(val, FArr) else val
-            self.nd()[self._section(key)] = v
+            dst = self.nd()[self._section(key)]
+            if isinstance(v, np.ndarray) and v.shape != dst.shape and v.ndim == dst.ndim:
+                # non-conforming section assignment (quirk Q6, fieldboundaries.F90:1938: g layers on the left, g + 1 on the
+                # right): compiled code loops over the LEFT side's extents; the surplus on the right is not copied
+                sl = tuple(slice(0, min(a, b)) for a, b in zip(dst.shape, v.shape))
+                dst[sl] = v[sl]
+            else:
+                dst[...] = v
 
     def set(self, val):
         """whole-array assignment"""
@@ -551,6 +559,13 @@ class Sub:
         return None
 
     def simple(self, st):
+        if st.startswith("call mpi_sendrecv"):
+            # one rank on a periodic axis exchanges with itself (plusrank == minusrank == rank, e.g. fieldboundaries.F90:
+            # 1168-1181): MPI_SendRecv(sendbuf, ..., recvbuf, ...) is then "recvbuf = sendbuf"
+            a = self.split_dims(st[st.index("(") + 1:st.rindex(")")])
+            return self.assign(a[5], a[0])
+        if st.startswith("call mpi_"):
+            return "pass"
         if st.startswith("call "):
             m = re.match(r"call\s+([a-z_]\w*)\s*(?:\((.*)\))?$", st)
             args = Expr(tokenize("(" + (m.group(2) or "") + ")"), self)

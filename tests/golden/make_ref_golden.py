@@ -181,25 +181,16 @@ def gen_mover():
 
 # ------------------------------------------------------------------------------------------------------------
 # G4: the digital filters -- apply_filter1_opt (filter.F90:8-221) and filter_x / filter_y / filter_z
-#     (optimized_filters.F90:459-915).  The MPI layer copies a single periodic rank makes to itself are replaced by the
-#     reference's own local-copy routines copylayrx / copylayry (fieldboundaries.F90:714-785) and, for z, by the same
-#     operation on the third index (the reference has no local z variant: its z copies always go through MPI_SendRecv).
+#     (optimized_filters.F90:459-915).  The layer copies are the reference's own copy_layr{x,y,z}1_opt (fieldboundaries.F90:
+#     1149-1677); their MPI_SendRecv to the rank itself is executed as "recvbuf = sendbuf" (f90run.py).
 # ------------------------------------------------------------------------------------------------------------
 def layer_copies(g, defines):
+    """bind the reference's own layer-copy routines (local and MPI-to-self variants) into the globals"""
     fb = src("fieldboundaries.F90")
-    cx = R.Sub(fb, "copylayrx", defines=defines, global_arrays=GARR, global_ints=GINTS).compile()
-    cy = R.Sub(fb, "copylayry", defines=defines, global_arrays=GARR, global_ints=GINTS).compile()
-
-    def cz(bx, by, bz, mx, my, mz, lt, ls, nt, ns):
-        for a in (bx, by, bz):
-            v = a.nd()
-            v[:, :, lt - 1] = v[:, :, ls - 1]
-        for a in (bx, by, bz):
-            v = a.nd()
-            v[:, :, nt - 1] = v[:, :, ns - 1]
-    g.copy_layrx1_opt = lambda *a: cx(g, *a)
-    g.copy_layry1_opt = lambda *a: cy(g, *a)
-    g.copy_layrz1_opt = cz
+    g.statsize, g.mpi_comm_world, g.mpi_read = 5, 0, 0
+    for nm in ("copylayrx", "copylayry", "copy_layrx1_opt", "copy_layry1_opt", "copy_layrz1_opt"):
+        f = R.Sub(fb, nm, defines=defines, global_arrays=GARR, global_ints=GINTS | {"statsize"}).compile()
+        setattr(g, nm, (lambda f_: (lambda *a: f_(g, *a)))(f))
 
 
 def gen_filter():
@@ -297,7 +288,48 @@ def gen_radiation():
     np.savez_compressed(os.path.join(HERE, "ref_radiation.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G6: ghost refresh and current fold on one periodic rank -- bc_b1 / bc_e1 (fieldboundaries.F90:181-263, 306-392) with
+#     copylayrx / copylayry / copy_layrz1_opt, and exchange_current (:1768-2189)
+# ------------------------------------------------------------------------------------------------------------
+def gen_halo():
+    out = {}
+    fb = src("fieldboundaries.F90")
+    for ci, (dim, order) in enumerate([(2, 1), (2, 2), (3, 1), (3, 3)]):
+        defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+        n = (8, 7, 6)
+        g = field_globals(dim, order, n, (1, 1, 1), np.random.default_rng(700 + ci))
+        layer_copies(g, defines)
+        g.highorder = False
+        ng = g.nghost
+        g.bufferin1x, g.bufferin2x = R.FArr((ng // 2 + 1, g.my, g.mz)), R.FArr((ng // 2, g.my, g.mz))
+        g.bufferin1y, g.bufferin2y = R.FArr((g.mx, ng // 2 + 1, g.mz)), R.FArr((g.mx, ng // 2, g.mz))
+        g.bufferin1, g.bufferin2 = R.FArr((g.mx, g.my, g.nghostz // 2 + 1)), R.FArr((g.mx, g.my, g.nghostz // 2))
+        ga = GARR | {"bufferin1x", "bufferin2x", "bufferin1y", "bufferin2y", "bufferin1", "bufferin2"}
+        gi = GINTS | {"statsize"}
+        bcb = R.Sub(fb, "bc_b1", defines=defines, global_arrays=ga, global_ints=gi).compile()
+        bce = R.Sub(fb, "bc_e1", defines=defines, global_arrays=ga, global_ints=gi).compile()
+        exc = R.Sub(fb, "exchange_current", defines=defines, global_arrays=ga, global_ints=gi).compile()
+        key = f"h{ci}"
+        out[key + "_meta"] = np.array([dim, order, 1, 1, 1, *n], np.int32)
+        names = ("ex", "ey", "ez", "bx", "by", "bz", "curx", "cury", "curz")
+        # the last layer (index m) of the currents never receives a deposit in a run; with it zero the shape typo of
+        # fieldboundaries.F90:1938 (a stale layer of the previous component is added) is invisible, as it is in the reference
+        for nm in ("curx", "cury", "curz"):
+            v = getattr(g, nm).nd()
+            v[-1, :, :] = 0; v[:, -1, :] = 0
+            if dim == 3:
+                v[:, :, -1] = 0
+        for a, nm in enumerate(names):
+            out[f"{key}_in{a}"] = c_order(getattr(g, nm))
+        bcb(g); bce(g); exc(g)
+        for a, nm in enumerate(names):
+            out[f"{key}_out{a}"] = c_order(getattr(g, nm))
+        print("halo", key, dim, order)
+    np.savez_compressed(os.path.join(HERE, "ref_halo.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo"]
     for w in which:
         globals()["gen_" + w]()

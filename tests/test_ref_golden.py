@@ -92,8 +92,8 @@ def test_movers_match_the_reference_source(dim, order):
 @pytest.mark.parametrize("case", range(4))
 def test_filter1_matches_the_reference_source(case):
     """apply_filter1_opt (filter.F90:8-221): ntimes passes of the 9- / 27-point stencil through `temp`, one ghost layer refreshed
-    per pass (the reference's MPI self-exchange replaced by its own local copylayrx / copylayry): BIT-EXACT on the interior
-    and on the refreshed ghost layers"""
+    per pass by the reference's own copy_layr{x,y,z}1_opt (their MPI_SendRecv to the rank itself executed as a copy):
+    BIT-EXACT on the interior and on the refreshed ghost layers"""
     z = load("ref_filter.npz")
     key = f"f1_{case}"
     meta = z[key + "_meta"]
@@ -141,3 +141,19 @@ def test_radiation_boundaries_match_the_reference_source(case):
         for a in range(6):
             ref = z[f"{key}_s{si}_{a}"]
             assert np.array_equal(r.arr(a), ref), (st, O.ARR_NAMES[a], float(np.abs(r.arr(a) - ref).max()))
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_ghost_refresh_and_fold_match_the_reference_source(case):
+    """bc_b1, bc_e1 (fieldboundaries.F90:181-263, 306-392: layer by layer, x then y then z) and exchange_current (:1768-2189:
+    ghost currents folded into the interior, x then y then z) on one periodic rank: BIT-EXACT, whole arrays"""
+    z = load("ref_halo.npz")
+    key = f"h{case}"
+    w = _world_from_meta(z[key + "_meta"])
+    r = w.ranks[0]
+    for a in range(9):
+        r.arr(a)[...] = z[f"{key}_in{a}"]
+    w.phase(O.PH_BC_B1); w.phase(O.PH_BC_E1); w.phase(O.PH_EXCH_CUR)
+    for a in range(9):
+        ref = z[f"{key}_out{a}"]
+        assert np.array_equal(r.arr(a), ref), (O.ARR_NAMES[a], float(np.abs(r.arr(a) - ref).max()))
