@@ -209,10 +209,11 @@ def fmax(*a):
 
 
 INTRINSICS = {"aint": "faint", "int": "int", "real": "freal", "min": "fmin", "max": "fmax", "abs": "abs", "sqrt": "fsqrt", "sum": "fsum",
-              "cshift": "fcshift", "mod": "fmod", "modulo": "fmodulo", "float": "F", "nint": "fnint", "floor": "ffloor"}
+              "cshift": "fcshift", "mod": "fmod", "modulo": "fmodulo", "float": "F", "nint": "fnint", "floor": "ffloor", "cos": "fcos",
+              "sin": "fsin"}
 RUNTIME = {"freal": lambda x, *kind: F(x), "F": F, "FArr": FArr, "fdiv": fdiv, "fpow": fpow, "fsum": fsum, "fcshift": fcshift, "frange": frange, "fexit": fexit, "faint": faint,
            "fmodulo": fmodulo, "fmod": fmod, "fmin": fmin, "fmax": fmax, "fsqrt": lambda x: F(np.sqrt(F(x))),
-           "fnint": lambda x: int(np.rint(x)), "ffloor": lambda x: int(np.floor(x)), "np": np}
+           "fcos": lambda x: F(np.cos(F(x))), "fsin": lambda x: F(np.sin(F(x))), "fnint": lambda x: int(np.rint(x)), "ffloor": lambda x: int(np.floor(x)), "np": np}
 PYKW = {"in", "is", "lambda", "not", "and", "or", "if", "else", "for", "while", "def", "class", "pass", "del", "from", "as", "with"}
 
 
@@ -279,10 +280,10 @@ def statements(text):
 
 
 def extract_subroutine(text, name):
-    m = re.search(r"^[ \t]*subroutine\s+" + name + r"\s*(\(|$)", text, flags=re.I | re.M)
+    m = re.search(r"^[ \t]*(?:(?:integer|real|logical)(?:\([a-z0-9_]*\))?\s+)?(subroutine|function)\s+" + name + r"\s*(\(|$)", text, flags=re.I | re.M)
     if not m:
         raise KeyError(name)
-    e = re.search(r"^[ \t]*end\s*subroutine\s+" + name + r"\b", text[m.start():], flags=re.I | re.M)
+    e = re.search(r"^[ \t]*end\s*" + m.group(1) + r"\s+" + name + r"\b", text[m.start():], flags=re.I | re.M)
     return text[m.start():m.start() + e.end()]
 
 
@@ -465,7 +466,7 @@ class Sub:
         self.global_arrays = {a.lower() for a in global_arrays}
         self.global_ints = {a.lower() for a in global_ints}
         text = preprocess(source, set(defines))
-        self.stmts = statements(extract_subroutine(text, name))
+        self.stmts = self.forward_gotos(statements(extract_subroutine(text, name)))
         self.py = self.translate()
 
     # --- names -------------------------------------------------------------------------------------------------
@@ -573,7 +574,7 @@ class Sub:
             a = args.p_args()
             return f"_g.{m.group(1)}({', '.join(a)})"
         if st in ("return",):
-            return "return"
+            return f"return {self.pyname(self.name)}" if getattr(self, "is_function", False) else "return"
         if st in ("continue",):
             return "pass"
         if st.startswith("print") or st.startswith("write") or st.startswith("stop"):
@@ -583,10 +584,31 @@ class Sub:
             return self.assign(*sa)
         raise SyntaxError("statement: " + st)
 
+    @staticmethod
+    def forward_gotos(stmts):
+        """An unconditional forward `goto N` ... `N continue` (fields.F90:1192-1210 disables a block this way): the statements in
+        between are never executed, so they are dropped.  Anything else with a goto is refused."""
+        out, i = [], 0
+        while i < len(stmts):
+            m = re.match(r"go\s*to\s+(\d+)$", stmts[i])
+            if m:
+                lab = re.compile(m.group(1) + r"\s+continue$")
+                j = next((k for k in range(i + 1, len(stmts)) if lab.match(stmts[k])), None)
+                if j is None:
+                    raise SyntaxError("goto without a forward label: " + stmts[i])
+                i = j + 1
+                continue
+            out.append(stmts[i])
+            i += 1
+        return out
+
     def translate(self):
         hdr = self.stmts[0]
-        m = re.match(r"subroutine\s+([a-z_]\w*)\s*(?:\((.*)\))?", hdr)
-        self.args = [a.strip() for a in (m.group(2) or "").split(",") if a.strip()]
+        m = re.match(r"(?:(integer|real|logical)(?:\([a-z0-9_]*\))?\s+)?(subroutine|function)\s+([a-z_]\w*)\s*(?:\((.*)\))?", hdr)
+        self.args = [a.strip() for a in (m.group(4) or "").split(",") if a.strip()]
+        self.is_function = m.group(2) == "function"
+        if self.is_function:             # the result variable carries the function's name and type
+            self.local[self.name] = ({"integer": "int", "real": "real", "logical": "logical"}[m.group(1) or "real"], None)
         body, ind = [], 1
         decls_done = []
         loops, nloop = [], [0]
@@ -594,7 +616,7 @@ class Sub:
         def emit(s):
             body.append("    " * ind + s)
         for st in self.stmts[1:]:
-            if st.startswith("end subroutine") or st.startswith("endsubroutine"):
+            if st.startswith("end subroutine") or st.startswith("endsubroutine") or st.startswith("end function"):
                 break
             if st.startswith("implicit") or st.startswith("use ") or st.startswith("intent") or st.startswith("external"):
                 continue
@@ -661,6 +683,8 @@ class Sub:
                 continue
             emit(self.simple(st))
         args = ", ".join(["_g"] + [self.pyname(a) for a in self.args])
+        if self.is_function:
+            body.append(f"    return {self.pyname(self.name)}")
         return f"def {self.name}({args}):\n" + "\n".join(body or ["    pass"]) + "\n"
 
     @staticmethod

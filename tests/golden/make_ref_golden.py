@@ -329,7 +329,101 @@ def gen_halo():
     np.savez_compressed(os.path.join(HERE, "ref_halo.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G7: the 4th-order `_42` solver -- advance_b_halfstep_42 (fields.F90:1039-1212), advance_e_fullstep_42 (:1223-1361); with
+#     and without the injector-side clamp of the x range (`wall`, xinject2)
+# ------------------------------------------------------------------------------------------------------------
+def gen_fields42():
+    out = {}
+    text = src("fields.F90")
+    cases = [(3, 2, (1, 1, 1), 0), (3, 2, (0, 1, 1), 0), (3, 2, (0, 1, 1), 6), (2, 2, (1, 1, 1), 0), (2, 2, (0, 1, 1), 5), (2, 2, (0, 0, 1), 0)]
+    for ci, (dim, order, per, xinj) in enumerate(cases):
+        defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+        bhalf = R.Sub(text, "advance_b_halfstep_42", defines=defines, global_arrays=GARR, global_ints=GINTS).compile()
+        efull = R.Sub(text, "advance_e_fullstep_42", defines=defines, global_arrays=GARR, global_ints=GINTS).compile()
+        n = (12, 9, 8)
+        g = field_globals(dim, order, n, per, np.random.default_rng(800 + ci))
+        g.wall = xinj > 0
+        g.xinject2 = F(xinj + 0.25)
+        g.radiationx, g.radiationy, g.radiationz = 1 - per[0], 1 - per[1], 1 - per[2]
+        key = f"g{ci}"
+        out[key + "_meta"] = np.array([dim, order, *per, *n], np.int32)
+        out[key + "_wall_i2"] = np.array([xinj + 10 if xinj else 0], np.int32)
+        for a, nm in enumerate(("ex", "ey", "ez", "bx", "by", "bz", "curx", "cury", "curz")):
+            out[f"{key}_in{a}"] = c_order(getattr(g, nm))
+        bhalf(g); efull(g); bhalf(g)
+        for a, nm in enumerate(("ex", "ey", "ez", "bx", "by", "bz")):
+            out[f"{key}_out{a}"] = c_order(getattr(g, nm))
+        print("fields42", key, dim, order, per, xinj)
+    np.savez_compressed(os.path.join(HERE, "ref_fields42.npz"), **out)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# G8: the shock problem's hooks -- field_bc_user / particle_bc_user (user/user_shock.F90:342-457) with the reference's own
+#     iloc / xglob (fields.F90:384-467) and zigzag (particles.F90:550-669); one rank, and the first / last rank of a 3-rank x split
+# ------------------------------------------------------------------------------------------------------------
+def gen_shock():
+    out = {}
+    user = open(os.path.join(REF, "user", "user_shock.F90")).read()
+    ftext, ptext = src("fields.F90"), src("particles.F90")
+    cases = [(3, 1, 40, 0, 40), (2, 2, 40, 0, 40), (2, 1, 60, 0, 20), (2, 1, 60, 40, 20)]     # dim, order, mx0, mxcum, local nx
+    for ci, (dim, order, mx0, mxcum, nx) in enumerate(cases):
+        defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+        gi = GINTS | {"mxcum", "mx0"}
+        n = (nx, 7, 6)
+        rng = np.random.default_rng(900 + ci)
+        g = field_globals(dim, order, n, (0, 1, 1), rng)
+        ng, ngz, mx, my, mz = grid(dim, order, n)
+        g.mx0, g.mxcum = mx0 + ng, mxcum                       # mx0 counts the ghost cells (fields.F90:292)
+        g.leftwall, g.binit, g.btheta, g.bphi, g.beta = F(15.0), F(0.05), F(1.1), F(0.4), F(0.3)
+        g.wall = True
+        g.qi, g.qe = F(0.07), F(-0.07)
+        for nm in ("iloc", "xglob"):
+            f = R.Sub(ftext, nm, defines=defines, global_arrays=GARR, global_ints=gi).compile()
+            setattr(g, nm, (lambda f: (lambda *a: f(g, *a)))(f))
+        zz = R.Sub(ptext, "zigzag", defines=defines, global_arrays=GARR, global_ints=gi).compile()
+        g.zigzag = lambda *a: zz(g, *a)
+        fbc = R.Sub(user, "field_bc_user", defines=defines, global_arrays=GARR, global_ints=gi).compile()
+        pbc = R.Sub(user, "particle_bc_user", defines=defines, global_arrays=GARR, global_ints=gi).compile()
+        # particles: half of each species has just crossed the wall (global x < leftwall after a push with u < 0)
+        nsp = 24
+        maxhlf = 32
+        p = np.zeros(2 * maxhlf, PDT)
+        for s0 in (0, maxhlf):
+            sl = slice(s0, s0 + nsp)
+            for k in "uvw":
+                p[k][sl] = (rng.standard_normal(nsp) * 0.5).astype(F)
+            p["u"][s0:s0 + nsp // 2] = -np.abs(p["u"][s0:s0 + nsp // 2]) - F(0.05)
+            gam = np.sqrt(1 + p["u"][sl].astype(np.float64) ** 2 + p["v"][sl] ** 2 + p["w"][sl] ** 2)
+            back = (rng.random(nsp) * 0.95 * np.abs(p["u"][sl] / gam) * 0.45).astype(F)       # how far behind the wall it ended
+            xg = np.where(np.arange(nsp) < nsp // 2, 15.0 - back, 15.0 + 0.01 + rng.random(nsp) * 8).astype(F)
+            p["x"][sl] = (xg - mxcum).astype(F)
+            p["y"][sl] = ((ng // 2 + 1) + rng.random(nsp) * n[1]).astype(F)
+            p["z"][sl] = ((ngz // 2 + 1) + rng.random(nsp) * n[2]).astype(F) if dim == 3 else (3 + rng.random(nsp)).astype(F)
+            p["ch"][sl] = 1.0
+        if mxcum:                      # a rank that does not hold the wall: nothing may happen to its particles
+            p["x"] = (p["x"] + F(mxcum) + F(6)).astype(F) - F(mxcum)
+        g.p = R.RecArr(p)
+        g.ions, g.lecs, g.maxhlf = nsp, nsp, maxhlf
+        g.q = F(0)
+        key = f"s{ci}"
+        out[key + "_meta"] = np.array([dim, order, 0, 1, 1, *n], np.int32)
+        out[key + "_geom"] = np.array([mx0, mxcum, maxhlf, nsp], np.int32)
+        out[key + "_par"] = np.array([g.leftwall, g.binit, g.btheta, g.bphi, g.beta, g.qi, g.qe], F)
+        for a, nm in enumerate(("ex", "ey", "ez", "bx", "by", "bz", "curx", "cury", "curz")):
+            out[f"{key}_in{a}"] = c_order(getattr(g, nm))
+        out[key + "_pin"] = p.copy()
+        fbc(g)
+        pbc(g)
+        for a, nm in enumerate(("ex", "ey", "ez", "bx", "by", "bz", "curx", "cury", "curz")):
+            out[f"{key}_out{a}"] = c_order(getattr(g, nm))
+        out[key + "_pout"] = p.copy()
+        moved = int((out[key + "_pin"]["u"] != p["u"]).sum())
+        print("shock", key, dim, order, "reflected", moved, "field cells changed", int(sum((out[f"{key}_in{a}"] != out[f"{key}_out{a}"]).sum() for a in range(6))))
+    np.savez_compressed(os.path.join(HERE, "ref_shock.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock"]
     for w in which:
         globals()["gen_" + w]()

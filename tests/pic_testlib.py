@@ -9,10 +9,12 @@ from oracle import oracle as O
 
 def oracle_world(dim=3, order=2, n=(16, 16, 16), sizes=(1, 1, 1), ppc=4.0, ntimes=0, filter_kind=1, delgam=1e-2,
                  quirks=O.Q_REFERENCE, init="weibel", seed_fields=1, periodic=(1, 1, 1), ext=None, pusher=0, gamma0=0.5,
-                 highorder=0):
+                 highorder=0, wall_i2=0, charges=None):
     P = O.make_params(dim=dim, order=order, mx0=n[0], my0=n[1], mz0=n[2], sizex=sizes[0], sizey=sizes[1], sizez=sizes[2],
                       ppc0=ppc if ppc > 0 else 16.0, ntimes=ntimes, maxptl=None if ppc > 0 else 65536, filter_kind=filter_kind, quirks=quirks, periodic=periodic, ext=ext,
-                      pusher=pusher, gamma0=gamma0, highorder=highorder)
+                      pusher=pusher, gamma0=gamma0, highorder=highorder, wall_i2=wall_i2)
+    if charges is not None:
+        P.qi, P.qe = charges
     w = O.World(P)
     if init == "weibel":
         w.init_weibel(ppc0=ppc, delgam=delgam, distr_dim=3 if dim == 3 else 2, gamma0=gamma0)

@@ -142,3 +142,66 @@ def test_movers_against_the_reference_source(tg, dim, order, fused):
     ref["ind"] = np.arange(1, n + 1); ref["splitlev"] = 1
     T.assert_particles_close(got, T.sort_particles(ref), what=key, extent=float(max(P2.mx, P2.my, P2.mz)))
     ctx.close()
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_42_solver_against_the_reference_source(tg, case):
+    """advance_{b_halfstep,e_fullstep}_42 (fields.F90:1039-1361) with the radiationx branches and the `wall` clamp: BIT-EXACT"""
+    z = load("ref_fields42.npz")
+    key = f"g{case}"
+    ctx, P = ctx_from_meta(tg, z[key + "_meta"], ntimes=0, highorder=1, wall_i2=int(z[key + "_wall_i2"][0]))
+    ctx.fields_h2d(*[np.ascontiguousarray(z[f"{key}_in{a}"]) for a in range(6)])
+    ctx.advance_b_halfstep(); ctx.advance_e_fullstep(); ctx.advance_b_halfstep()
+    got = ctx.fields_d2h()
+    for a in range(6):
+        assert np.array_equal(got[a], z[f"{key}_out{a}"]), a
+    ctx.close()
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_shock_hooks_against_the_reference_source(tg, case):
+    """field_bc_user / particle_bc_user (user/user_shock.F90:342-457).  Fields: bit-exact but for the fp32 cos/sin of the clamp
+    values (1 ulp: numpy's against the device's).  Reflected particles: the mover bars.  Wall currents (atomics): 1e-5 of the
+    largest current."""
+    z = load("ref_shock.npz")
+    key = f"s{case}"
+    dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
+    mx0, mxcum, maxhlf, nsp = (int(v) for v in z[key + "_geom"])
+    par = z[key + "_par"]
+    sx = mx0 // nx
+    P = tg.make_params(dim=dim, order=order, mx0=mx0, my0=ny, mz0=nz, sizex=sx, rank=mxcum // nx, periodic=(px, py, pz), maxptl=4096,
+                       device=0, ntimes=0)
+    P.qi, P.qe = float(par[5]), float(par[6])
+    ctx = tg.Context(P)
+    assert ctx.P.mxcum == mxcum
+    ctx.fields_h2d(*[np.ascontiguousarray(z[f"{key}_in{a}"]) for a in range(6)])
+    ctx.currents_h2d(*[np.ascontiguousarray(z[f"{key}_in{a}"]) for a in range(6, 9)])
+    pin, pout = z[key + "_pin"], z[key + "_pout"]
+    host = np.zeros(P.maxptl, tg.PARTICLE_DTYPE)
+    ref = np.zeros(2 * nsp, tg.PARTICLE_DTYPE)
+    for s0, d0, sign in ((0, 0, 1), (maxhlf, ctx.maxhlf, -1)):
+        for k in ("x", "y", "z", "u", "v", "w", "ch"):
+            host[k][d0:d0 + nsp] = pin[k][s0:s0 + nsp]
+            ref[k][(s0 > 0) * nsp:(s0 > 0) * nsp + nsp] = pout[k][s0:s0 + nsp]
+        host["ind"][d0:d0 + nsp] = sign * np.arange(1, nsp + 1)
+        host["splitlev"][d0:d0 + nsp] = 1
+    ctx.particles_h2d(host, nsp, nsp)
+    ctx.field_bc_user_shock(*[float(v) for v in par[:5]])
+    ctx.particle_bc_user_wall(float(par[0]))
+    got = ctx.fields_d2h()
+    for a in range(6):
+        refa = z[f"{key}_out{a}"]
+        assert float(np.abs(got[a] - refa).max()) <= np.spacing(np.abs(refa).max()), a
+    cur = ctx.currents_d2h()
+    scale = max(float(np.abs(z[f"{key}_out{a}"]).max()) for a in range(6, 9))
+    for a in range(3):
+        assert T.max_abs_diff(cur[a], z[f"{key}_out{6 + a}"]) <= 1e-5 * scale, a
+    gp, ions, lecs = ctx.particles_d2h()
+    assert (ions, lecs) == (nsp, nsp)
+    for sp, d0 in ((0, 0), (1, ctx.maxhlf)):
+        g1, r1 = gp[d0:d0 + nsp], ref[sp * nsp:(sp + 1) * nsp]
+        for k in ("x", "y", "z"):
+            assert np.abs(g1[k] - r1[k]).max() <= 2e-6 * max(P.mx, P.my, P.mz), (sp, k)
+        for k in ("u", "v", "w"):
+            assert np.abs(g1[k] - r1[k]).max() <= 2e-5 * max(np.abs(r1[k]).max(), 1.0), (sp, k)
+    ctx.close()

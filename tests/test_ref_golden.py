@@ -157,3 +157,63 @@ def test_ghost_refresh_and_fold_match_the_reference_source(case):
     for a in range(9):
         ref = z[f"{key}_out{a}"]
         assert np.array_equal(r.arr(a), ref), (O.ARR_NAMES[a], float(np.abs(r.arr(a) - ref).max()))
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_42_solver_matches_the_reference_source(case):
+    """advance_b_halfstep_42, advance_e_fullstep_42, advance_b_halfstep_42 (fields.F90:1039-1361) incl. the radiationx branches
+    and the injector clamp of the x range (`wall`, int(xinject2) + 10): BIT-EXACT"""
+    z = load("ref_fields42.npz")
+    key = f"g{case}"
+    w = _world_from_meta(z[key + "_meta"], highorder=1, wall_i2=int(z[key + "_wall_i2"][0]))
+    r = w.ranks[0]
+    for a in range(9):
+        r.arr(a)[...] = z[f"{key}_in{a}"]
+    for name in ("advance_b_halfstep", "advance_e_fullstep", "advance_b_halfstep"):
+        r.call(name)
+    for a in range(6):
+        assert np.array_equal(r.arr(a), z[f"{key}_out{a}"]), (O.ARR_NAMES[a], float(np.abs(r.arr(a) - z[f"{key}_out{a}"]).max()))
+
+
+def shock_case(z, case):
+    """the oracle rank a shock golden case was generated for (a 1-rank box, or the first / last rank of a 3-rank x split)"""
+    key = f"s{case}"
+    dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
+    mx0, mxcum, maxhlf, nsp = (int(v) for v in z[key + "_geom"])
+    sx = mx0 // nx
+    par = z[key + "_par"]
+    w = T.oracle_world(dim=dim, order=order, n=(mx0, ny, nz), sizes=(sx, 1, 1), ppc=0.0, init="none", seed_fields=0, periodic=(px, py, pz),
+                       charges=(float(par[5]), float(par[6])))
+    r = next(rk for rk in w.ranks if rk.mxcum == mxcum)
+    assert r.mx - r.nghost == nx
+    return key, w, r, maxhlf, nsp
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_shock_hooks_match_the_reference_source(case):
+    """field_bc_user and particle_bc_user of user/user_shock.F90:342-457, run with the reference's own iloc / xglob
+    (fields.F90:384-467) and zigzag: conductor behind the wall, upstream clamp, specular reflection with the two partial
+    deposits.  Fields, currents and particles BIT-EXACT except where cos/sin enter (numpy's fp32 cos against libm's: 1 ulp)"""
+    z = load("ref_shock.npz")
+    key, w, r, maxhlf, nsp = shock_case(z, case)
+    par = z[key + "_par"]
+    for a in range(9):
+        r.arr(a)[...] = z[f"{key}_in{a}"]
+    pin, pout = z[key + "_pin"], z[key + "_pout"]
+    p = r.particles()
+    assert r.maxhlf >= maxhlf
+    for s0, d0 in ((0, 0), (maxhlf, r.maxhlf)):
+        for k in ("x", "y", "z", "u", "v", "w", "ch"):
+            p[k][d0:d0 + nsp] = pin[k][s0:s0 + nsp]
+    r.set_counts(nsp, nsp)
+    cf = C.c_float
+    r.call("field_bc_shock", *(cf(float(v)) for v in par[:5]))
+    r.call("particle_bc_wall", cf(float(par[0])))
+    for a in range(9):
+        ref = z[f"{key}_out{a}"]
+        if a >= 6 or not np.array_equal(r.arr(a), ref):
+            ulp = np.spacing(np.abs(ref).max())
+            assert float(np.abs(r.arr(a) - ref).max()) <= (0 if a >= 6 else ulp), (O.ARR_NAMES[a], float(np.abs(r.arr(a) - ref).max()))
+    for s0, d0 in ((0, 0), (maxhlf, r.maxhlf)):
+        for k in ("x", "y", "z", "u", "v", "w"):
+            assert np.array_equal(p[k][d0:d0 + nsp], pout[k][s0:s0 + nsp]), (k, s0)
