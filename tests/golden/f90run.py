@@ -77,7 +77,8 @@ class FArr:
 
     def __getitem__(self, key):
         if self._is_scalar_key(key):
-            return self.flat[self._scalar_index(key)]
+            v = self.flat[self._scalar_index(key)]
+            return int(v) if self.flat.dtype.kind == "i" else v       # Fortran integers stay integers in mixed expressions
         return np.array(self.nd()[self._section(key)])                # sections are values
 
     def __setitem__(self, key, val):
@@ -210,10 +211,10 @@ def fmax(*a):
 
 INTRINSICS = {"aint": "faint", "int": "int", "real": "freal", "min": "fmin", "max": "fmax", "abs": "abs", "sqrt": "fsqrt", "sum": "fsum",
               "cshift": "fcshift", "mod": "fmod", "modulo": "fmodulo", "float": "F", "nint": "fnint", "floor": "ffloor", "cos": "fcos",
-              "sin": "fsin"}
+              "sin": "fsin", "sign": "fsign"}
 RUNTIME = {"freal": lambda x, *kind: F(x), "F": F, "FArr": FArr, "fdiv": fdiv, "fpow": fpow, "fsum": fsum, "fcshift": fcshift, "frange": frange, "fexit": fexit, "faint": faint,
            "fmodulo": fmodulo, "fmod": fmod, "fmin": fmin, "fmax": fmax, "fsqrt": lambda x: F(np.sqrt(F(x))),
-           "fcos": lambda x: F(np.cos(F(x))), "fsin": lambda x: F(np.sin(F(x))), "fnint": lambda x: int(np.rint(x)), "ffloor": lambda x: int(np.floor(x)), "np": np}
+           "fsign": lambda a, b: F(abs(a)) if not np.signbit(b) else F(-abs(a)), "fcos": lambda x: F(np.cos(F(x))), "fsin": lambda x: F(np.sin(F(x))), "fnint": lambda x: int(np.rint(x)), "ffloor": lambda x: int(np.floor(x)), "np": np}
 PYKW = {"in", "is", "lambda", "not", "and", "or", "if", "else", "for", "while", "def", "class", "pass", "del", "from", "as", "with"}
 
 
@@ -579,6 +580,13 @@ class Sub:
             return "pass"
         if st.startswith("print") or st.startswith("write") or st.startswith("stop"):
             return "pass"
+        m = re.match(r"go\s*to\s+(\d+)$", st)
+        if m:
+            if m.group(1) not in self.cyc:
+                raise SyntaxError("goto that is neither a forward skip nor a cycle: " + st)
+            return "continue"
+        if re.match(r"\d+\s+continue$", st):
+            return "pass"
         sa = self.split_assign(st)
         if sa:
             return self.assign(*sa)
@@ -589,9 +597,10 @@ class Sub:
         """An unconditional forward `goto N` ... `N continue` (fields.F90:1192-1210 disables a block this way): the statements in
         between are never executed, so they are dropped.  Anything else with a goto is refused."""
         out, i = [], 0
+        cyc = Sub.cycle_labels(stmts)
         while i < len(stmts):
             m = re.match(r"go\s*to\s+(\d+)$", stmts[i])
-            if m:
+            if m and m.group(1) not in cyc:
                 lab = re.compile(m.group(1) + r"\s+continue$")
                 j = next((k for k in range(i + 1, len(stmts)) if lab.match(stmts[k])), None)
                 if j is None:
@@ -602,7 +611,14 @@ class Sub:
             i += 1
         return out
 
+    @staticmethod
+    def cycle_labels(stmts):
+        """labels of `N continue` statements that are the last statement of a do loop: a `go to N` from inside that loop
+        (particles_movedeposit.F90:1652 `if(in) go to 58`) is a CYCLE"""
+        return {m.group(1) for a, b in zip(stmts, stmts[1:]) if (m := re.match(r"(\d+)\s+continue$", a)) and b in ("enddo", "end do")}
+
     def translate(self):
+        self.cyc = self.cycle_labels(self.stmts)
         hdr = self.stmts[0]
         m = re.match(r"(?:(integer|real|logical)(?:\([a-z0-9_]*\))?\s+)?(subroutine|function)\s+([a-z_]\w*)\s*(?:\((.*)\))?", hdr)
         self.args = [a.strip() for a in (m.group(4) or "").split(",") if a.strip()]

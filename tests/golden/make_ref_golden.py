@@ -423,7 +423,111 @@ def gen_shock():
     np.savez_compressed(os.path.join(HERE, "ref_shock.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G9: deposit_particles as a whole (particles_movedeposit.F90:1281-2051): the unwinding of the old position, the deposit
+#     calls, the periodic wrap / domain-exit classification with the neighbour-size shifts, the six out-buffers and the
+#     hole-filling compaction -- on single ranks and on one rank of a split box (no MPI inside this routine)
+# ------------------------------------------------------------------------------------------------------------
+def gen_depositp():
+    out = {}
+    mtext, ptext = src("particles_movedeposit.F90"), src("particles.F90")
+    dirs = ("outup", "outdwn", "inblw", "inabv", "outlft", "outrgt", "inlft", "inrgt", "outminus", "outplus", "inminus", "inplus")
+    gi = GINTS | {"mxcum", "mycum", "mzcum", "nionout", "nlecout", "lap"} | {f"len{s}{d}" for s in ("ion", "lec") for d in dirs}
+    ga = GARR | {"pind", "mxl", "myl", "mzl", "poutup", "poutdwn", "poutlft", "poutrgt", "poutminus", "poutplus"}
+    dep = {0: ("zzag", "zigzag"), 1: ("dd1", "densdecomp_1ord"), 2: ("dd2", "densdecomp_2ord"), 3: ("dd3", "densdecomp_3ord")}
+    #        dim order global n      sizes      rank periodic
+    cases = [(2, 1, (12, 10, 1), (1, 1, 1), 0, (1, 1, 1)),
+             (2, 2, (12, 10, 1), (1, 1, 1), 0, (0, 1, 1)),
+             (2, 0, (24, 20, 1), (2, 2, 1), 3, (1, 1, 1)),
+             (3, 2, (16, 12, 12), (2, 2, 2), 5, (1, 1, 1)),
+             (3, 1, (10, 8, 8), (1, 1, 1), 0, (1, 1, 1)),
+             (3, 3, (10, 16, 8), (1, 2, 1), 1, (1, 0, 1)),
+             (3, 0, (16, 8, 16), (2, 1, 2), 0, (0, 1, 0))]
+    for ci, (dim, order, ng_, sizes, rank, per) in enumerate(cases):
+        flag, name = dep[order]
+        defines = {"MPI", flag} | ({"twoD"} if dim == 2 else set())
+        n = tuple(a // s for a, s in zip(ng_, sizes))
+        rng = np.random.default_rng(1000 + ci)
+        g = field_globals(dim, order, n, per, rng)
+        ng, ngz, mx, my, mz = grid(dim, order, n)
+        sx, sy, sz = sizes
+        size0 = sx * sy * sz
+        g.size0, g.sizex, g.sizey, g.sizez, g.rank = size0, sx, sy, sz, rank
+        g.mxcum, g.mycum, g.mzcum = (rank % sx) * n[0], (rank // sx % sy) * n[1], (rank // (sx * sy)) * n[2]
+        for nm, m_ in (("mxl", mx), ("myl", my), ("mzl", mz)):
+            a = R.FArr((size0,), np.int64)
+            a.flat[:] = m_
+            setattr(g, nm, a)
+        # particles.F90:339-344 (mx0, my0, mz0 count the ghost cells)
+        g.x1in, g.x2in = F(1. * (ng // 2 + 1)), F(ng_[0] + ng - 1. * (ng // 2))
+        g.y1in, g.y2in = F(1. * (ng // 2 + 1)), F(ng_[1] + ng - 1. * (ng // 2))
+        g.z1in, g.z2in = F(1. * (ngz // 2 + 1)), F(ng_[2] + ngz - 1. * (ngz // 2))
+        g.qi, g.qe = F(0.07), F(-0.07)
+        g.debug, g.lap = False, 1
+        for nm in ("curx", "cury", "curz"):
+            getattr(g, nm).flat[:] = 0
+        maxhlf, nsp = 96, 80
+        p = np.zeros(2 * maxhlf, PDT)
+        for s0 in (0, maxhlf):
+            sl = slice(s0, s0 + nsp)
+            # positions AFTER the push: most inside, a band of them up to 0.4 cells outside each face (they are what leaves)
+            lo = np.array([ng // 2 + 1, ng // 2 + 1, ngz // 2 + 1], F)
+            ext = np.array([n[0], n[1], n[2] if dim == 3 else 1], F)
+            u01 = rng.random((3, nsp))
+            pos = lo[:, None] + (u01 * 1.16 - 0.08) * ext[:, None] if False else lo[:, None] + u01 * ext[:, None]
+            edge = rng.random((3, nsp))
+            pos = np.where(edge < 0.12, lo[:, None] - 0.4 * rng.random((3, nsp)), pos)
+            pos = np.where(edge > 0.88, lo[:, None] + ext[:, None] + 0.4 * rng.random((3, nsp)), pos)
+            p["x"][sl], p["y"][sl], p["z"][sl] = pos.astype(F)
+            for k in "uvw":
+                p[k][sl] = (rng.standard_normal(nsp) * 0.6).astype(F)
+            # a particle that is outside must have moved outwards: give its momentum the sign of its excursion
+            for k, ax in (("u", 0), ("v", 1), ("w", 2)):
+                below, above = pos[ax] < lo[ax], pos[ax] > lo[ax] + ext[ax]
+                p[k][sl] = np.where(below, -np.abs(p[k][sl]) - F(1.2), np.where(above, np.abs(p[k][sl]) + F(1.2), p[k][sl]))
+            p["ch"][sl] = (0.5 + rng.random(nsp)).astype(F)
+            p["ind"][sl] = np.arange(1, nsp + 1) * (1 if s0 == 0 else -1)
+            p["proc"][sl] = rank
+            p["splitlev"][sl] = 1
+        g.p = R.RecArr(p)
+        g.ions, g.lecs, g.maxhlf = nsp, nsp, maxhlf
+        g.pind = R.FArr((2 * maxhlf,), np.int64)
+        bufs = {}
+        for nm in ("poutup", "poutdwn", "poutlft", "poutrgt", "poutminus", "poutplus"):
+            bufs[nm] = np.zeros(2 * nsp, PDT)
+            setattr(g, nm, R.RecArr(bufs[nm]))
+        g.q = F(0)
+
+        def copyprt(a, b):                                  # particles.F90:263-276, field by field
+            for k in PDT.names:
+                setattr(b, k, getattr(a, k))
+        g.copyprt = copyprt
+        dsub = R.Sub(ptext, name, defines=defines, global_arrays=ga, global_ints=gi).compile()
+        setattr(g, name, lambda *a: dsub(g, *a))
+        sub = R.Sub(mtext, "deposit_particles", defines=defines, global_arrays=ga, global_ints=gi).compile()
+        key = f"p{ci}"
+        out[key + "_meta"] = np.array([dim, order, *per, *ng_], np.int32)
+        out[key + "_geom"] = np.array([*sizes, rank, maxhlf, nsp], np.int32)
+        out[key + "_pin"] = p.copy()
+        sub(g)
+        out[key + "_pout"] = p.copy()
+        out[key + "_counts"] = np.array([g.ions, g.lecs, g.nionout, g.nlecout], np.int32)
+        # out-buffers in the oracle's direction order: x-, x+, y-, y+, z-, z+; ions then electrons (the reference appends the
+        # electrons behind the ions in the same buffer: LenLecOut* counts on from LenIonOut*, :1990-2030)
+        lens = []
+        for d, (nm, suf) in enumerate((("poutminus", "outminus"), ("poutplus", "outplus"), ("poutlft", "outlft"), ("poutrgt", "outrgt"),
+                                       ("poutdwn", "outdwn"), ("poutup", "outup"))):
+            ni, nl = getattr(g, "lenion" + suf), getattr(g, "lenlec" + suf)
+            lens += [ni, nl]
+            out[f"{key}_box{d}"] = bufs[nm].copy()
+        out[key + "_boxlen"] = np.array(lens, np.int32)
+        for a, nm in enumerate(("curx", "cury", "curz")):
+            out[f"{key}_cur{a}"] = c_order(getattr(g, nm))
+        print("deposit_particles", key, dim, order, sizes, rank, per, "left:", int(g.ions), int(g.lecs), "boxes:", lens)
+    np.savez_compressed(os.path.join(HERE, "ref_depositp.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp"]
     for w in which:
         globals()["gen_" + w]()

@@ -205,3 +205,42 @@ def test_shock_hooks_against_the_reference_source(tg, case):
         for k in ("u", "v", "w"):
             assert np.abs(g1[k] - r1[k]).max() <= 2e-5 * max(np.abs(r1[k]).max(), 1.0), (sp, k)
     ctx.close()
+
+
+@pytest.mark.parametrize("case", range(7))
+@pytest.mark.parametrize("fused", [0, 1])
+def test_deposit_particles_against_the_reference_source(tg, case, fused):
+    """deposit_particles as a whole (particles_movedeposit.F90:1281-2051) on single ranks and on ranks of split boxes: the
+    currents within 1e-5 of the largest current (summation order, atomics), the survivors as a SET keyed by (proc, ind) with
+    their wrapped positions within 1e-6 of the box and momenta untouched.  `fused` deposits from the cell-run path where the
+    configuration has one (the old position is then recomputed the reference's way, CR_OLDPOS_REF)."""
+    z = load("ref_depositp.npz")
+    key = f"p{case}"
+    dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
+    sx, sy, sz, rank, maxhlf, nsp = (int(v) for v in z[key + "_geom"])
+    P = tg.make_params(dim=dim, order=order, mx0=nx, my0=ny, mz0=nz, sizex=sx, sizey=sy, sizez=sz, rank=rank, periodic=(px, py, pz),
+                       maxptl=4096, device=0, ntimes=0)
+    P.qi, P.qe = float(np.float32(0.07)), float(np.float32(-0.07))
+    ctx = tg.Context(P)
+    ctx.set_option("fused", fused)
+    pin, pout = z[key + "_pin"], z[key + "_pout"]
+    host = np.zeros(P.maxptl, tg.PARTICLE_DTYPE)
+    host[:nsp] = pin[:nsp]
+    host[ctx.maxhlf:ctx.maxhlf + nsp] = pin[maxhlf:maxhlf + nsp]
+    ctx.particles_h2d(host, nsp, nsp)
+    zero = np.zeros_like(z[f"{key}_cur0"])
+    ctx.currents_h2d(zero, zero, zero)
+    ctx.deposit_particles()
+    ions, lecs = (int(v) for v in z[key + "_counts"][:2])
+    cur = ctx.currents_d2h()
+    scale = max(float(np.abs(z[f"{key}_cur{a}"]).max()) for a in range(3))
+    for a in range(3):
+        assert T.max_abs_diff(cur[a], z[f"{key}_cur{a}"]) <= 1e-5 * scale, (a, T.max_abs_diff(cur[a], z[f"{key}_cur{a}"]) / scale)
+    gp, gi, gl = ctx.particles_d2h()
+    assert (gi, gl) == (ions, lecs)
+    ext = float(max(P.mx, P.my, P.mz))
+    T.assert_particles_close(T.sort_particles(gp[:ions].copy()), T.sort_particles(pout[:ions].copy()), rtol_pos=1e-6, rtol_mom=0.0,
+                             what=key + " ions", extent=ext)
+    T.assert_particles_close(T.sort_particles(gp[ctx.maxhlf:ctx.maxhlf + lecs].copy()), T.sort_particles(pout[maxhlf:maxhlf + lecs].copy()),
+                             rtol_pos=1e-6, rtol_mom=0.0, what=key + " lecs", extent=ext)
+    ctx.close()

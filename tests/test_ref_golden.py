@@ -217,3 +217,48 @@ def test_shock_hooks_match_the_reference_source(case):
     for s0, d0 in ((0, 0), (maxhlf, r.maxhlf)):
         for k in ("x", "y", "z", "u", "v", "w"):
             assert np.array_equal(p[k][d0:d0 + nsp], pout[k][s0:s0 + nsp]), (k, s0)
+
+
+def _box(r, which, d):
+    ni, nl = C.c_int(0), C.c_int(0)
+    addr = O.lib().orc_rank_box(r.h, which, d, C.byref(ni), C.byref(nl))
+    n = ni.value + nl.value
+    if n == 0:
+        return ni.value, nl.value, np.zeros(0, O.PARTICLE_DTYPE)
+    buf = (C.c_char * (n * 40)).from_address(addr)
+    return ni.value, nl.value, np.frombuffer(buf, dtype=O.PARTICLE_DTYPE).copy()
+
+
+@pytest.mark.parametrize("case", range(7))
+def test_deposit_particles_matches_the_reference_source(case):
+    """deposit_particles as a whole (particles_movedeposit.F90:1281-2051): unwinding of the old position, the deposit calls,
+    periodic wrap with the neighbour-size shifts, domain exits on open axes, the six out-buffers (ions then electrons) and the
+    hole-filling compaction, on single ranks and on ranks of split boxes: currents, the particle array IN ORDER, the buffers
+    IN ORDER and all counts BIT-EXACT"""
+    z = load("ref_depositp.npz")
+    key = f"p{case}"
+    dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
+    sx, sy, sz, rank, maxhlf, nsp = (int(v) for v in z[key + "_geom"])
+    w = T.oracle_world(dim=dim, order=order, n=(nx, ny, nz), sizes=(sx, sy, sz), ppc=0.0, init="none", seed_fields=0, periodic=(px, py, pz),
+                       charges=(float(np.float32(0.07)), float(np.float32(-0.07))))
+    r = w.ranks[rank]
+    pin, pout = z[key + "_pin"], z[key + "_pout"]
+    p = r.particles()
+    for s0, d0 in ((0, 0), (maxhlf, r.maxhlf)):
+        p[d0:d0 + nsp] = pin[s0:s0 + nsp]
+    r.set_counts(nsp, nsp)
+    for a in range(6, 9):
+        r.arr(a)[...] = 0
+    r.call("deposit_particles")
+    ions, lecs, nionout, nlecout = (int(v) for v in z[key + "_counts"])
+    assert r.counts == (ions, lecs)
+    for a in range(3):
+        ref = z[f"{key}_cur{a}"]
+        assert np.array_equal(r.arr(6 + a), ref), (O.ARR_NAMES[6 + a], float(np.abs(r.arr(6 + a) - ref).max()))
+    assert np.array_equal(p[:ions], pout[:ions])
+    assert np.array_equal(p[r.maxhlf:r.maxhlf + lecs], pout[maxhlf:maxhlf + lecs])
+    lens = z[key + "_boxlen"].reshape(6, 2)
+    for d in range(6):
+        ni, nl, box = _box(r, 0, d)
+        assert (ni, nl) == (int(lens[d, 0]), int(lens[d, 1])), d
+        assert np.array_equal(box, z[f"{key}_box{d}"][:ni + nl]), d
