@@ -84,6 +84,11 @@ class FArr:
     def __setitem__(self, key, val):
         if self._is_scalar_key(key):
             self.flat[self._scalar_index(key)] = val
+        elif isinstance(val, Payload):
+            dst = self.nd()[self._section(key)]
+            tmp = np.array(dst).reshape(-1, order="F")
+            tmp[:val.data.size] = val.data
+            dst[...] = tmp.reshape(dst.shape, order="F")
         else:
             v = val.nd() if isinstance(val, FArr) else val
             dst = self.nd()[self._section(key)]
@@ -97,6 +102,9 @@ class FArr:
 
     def set(self, val):
         """whole-array assignment"""
+        if isinstance(val, Payload):
+            self.flat[:val.data.size] = val.data
+            return
         self.nd()[...] = val.nd() if isinstance(val, FArr) else val
 
     # whole-array arithmetic (elementwise, fp32)
@@ -116,6 +124,72 @@ class FArr:
     def __rmul__(self, o): return self._bin(o, np.multiply, True)
     def __truediv__(self, o): return self._bin(o, np.divide)
     def __neg__(self): return self._bin(F(-1), np.multiply)
+
+
+class Payload:
+    """what an MPI message carries: `count` elements of the send buffer in Fortran (column-major) element order.  The receive
+    side stores them into the first `count` elements of ITS buffer, again in Fortran order -- shapes play no role."""
+
+    def __init__(self, data):
+        self.data = data                  # 1-D numpy array (plain or structured), already a copy
+
+
+def as_payload(buf, count):
+    if isinstance(buf, Payload):
+        return buf
+    if isinstance(buf, RecArr):
+        flat = buf.a
+    elif isinstance(buf, FArr):
+        flat = buf.flat
+    else:
+        flat = np.asarray(buf).reshape(-1, order="F")
+    n = int(count)
+    if n > flat.size:
+        # The reference does this once: the 3D x-fold of exchange_current sizes its second message with the x extent instead
+        # of the y extent (fieldboundaries.F90:1838), so with mx > my the count exceeds the section.  A compiled run sends
+        # the section's contiguous temporary plus whatever follows it on the heap and the receiver copies back only the
+        # section: the section's own elements arrive intact.  Modelled as "send what exists"; noted in OVERLONG.
+        if isinstance(buf, (RecArr, FArr)):
+            raise IndexError(f"MPI send of {n} elements from a buffer of {flat.size}")
+        OVERLONG.append((n, flat.size))
+        n = flat.size
+    return Payload(flat[:n].copy())
+
+
+OVERLONG = []
+
+
+class Comm:
+    """MPI_COMM_WORLD for ranks that run as Python threads: MPI_SendRecv = post the send, then block on the receive"""
+
+    def __init__(self, size, timeout=30.0):
+        import collections
+        import queue
+        self.size, self.timeout = size, timeout
+        self.q = collections.defaultdict(queue.Queue)
+
+    def sendrecv(self, rank, payload, dest, sendtag, source, recvtag):
+        self.q[(rank, int(dest), int(sendtag))].put(payload)
+        return self.q[(int(source), rank, int(recvtag))].get(timeout=self.timeout)
+
+
+def run_ranks(fns):
+    """run one callable per rank concurrently (they meet inside Comm.sendrecv); re-raises the first failure"""
+    import threading
+    err = []
+
+    def wrap(f):
+        try:
+            f()
+        except BaseException as e:        # noqa: BLE001 -- reported to the caller below
+            err.append(e)
+    th = [threading.Thread(target=wrap, args=(f,)) for f in fns]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if err:
+        raise err[0]
 
 
 class Record:
@@ -140,6 +214,11 @@ class RecArr:
 
     def __getitem__(self, i):
         return Record(self.a, int(i) - 1)
+
+    def set(self, val):
+        """whole-array assignment from a message or from another array of the type"""
+        v = val.data if isinstance(val, Payload) else val.a
+        self.a[:v.size] = v
 
 
 def fdiv(a, b):
@@ -564,8 +643,10 @@ class Sub:
         if st.startswith("call mpi_sendrecv"):
             # one rank on a periodic axis exchanges with itself (plusrank == minusrank == rank, e.g. fieldboundaries.F90:
             # 1168-1181): MPI_SendRecv(sendbuf, ..., recvbuf, ...) is then "recvbuf = sendbuf"
+            # With several ranks (Globals.comm set) the message goes through Comm; either way the transfer is `count` elements
+            # in Fortran order (Payload).
             a = self.split_dims(st[st.index("(") + 1:st.rindex(")")])
-            return self.assign(a[5], a[0])
+            return self.assign(a[5], f"mpi_xchg({a[0]}, {a[1]}, {a[3]}, {a[4]}, {a[8]}, {a[9]})")
         if st.startswith("call mpi_"):
             return "pass"
         if st.startswith("call "):
@@ -729,6 +810,14 @@ class Sub:
 class Globals:
     """module variables of the reference (m_fields, m_particles, ...) as attributes"""
 
+    comm = None
+
     def __init__(self, **kw):
         for k, v in kw.items():
             setattr(self, k, v)
+
+    def mpi_xchg(self, sendbuf, count, dest, sendtag, source, recvtag):
+        pay = as_payload(sendbuf, count)
+        if self.comm is None:
+            return pay                    # one rank: every neighbour is the rank itself
+        return self.comm.sendrecv(int(self.rank), pay, dest, sendtag, source, recvtag)

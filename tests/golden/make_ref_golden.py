@@ -188,7 +188,8 @@ def layer_copies(g, defines):
     """bind the reference's own layer-copy routines (local and MPI-to-self variants) into the globals"""
     fb = src("fieldboundaries.F90")
     g.statsize, g.mpi_comm_world, g.mpi_read = 5, 0, 0
-    for nm in ("copylayrx", "copylayry", "copy_layrx1_opt", "copy_layry1_opt", "copy_layrz1_opt"):
+    for nm in ("copylayrx", "copylayry", "copy_layrx1_opt", "copy_layry1_opt", "copy_layrz1_opt", "copy_layrx2_opt", "copy_layry2_opt",
+               "copy_layrz2_opt"):
         f = R.Sub(fb, nm, defines=defines, global_arrays=GARR, global_ints=GINTS | {"statsize"}).compile()
         setattr(g, nm, (lambda f_: (lambda *a: f_(g, *a)))(f))
 
@@ -527,7 +528,176 @@ def gen_depositp():
     np.savez_compressed(os.path.join(HERE, "ref_depositp.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G10: SEVERAL RANKS.  Every rank runs the reference's source in its own thread; MPI_SendRecv is a rendezvous between the
+#      threads (f90run.Comm), so neighbour ranks, tags, message sizes and the z -> y -> x order are the reference's own.
+#      bc_b1 / bc_e1 / exchange_current (fieldboundaries.F90:181-392, 1768-2189) and apply_filter1_opt (filter.F90:8-221)
+# ------------------------------------------------------------------------------------------------------------
+def rank_geometry(g, dim, order, nglob, sizes, rank):
+    sx, sy, sz = sizes
+    n = tuple(a // s_ for a, s_ in zip(nglob, sizes))
+    ng, ngz, mx, my, mz = grid(dim, order, n)
+    g.size0, g.sizex, g.sizey, g.sizez, g.rank = sx * sy * sz, sx, sy, sz, rank
+    g.mxcum, g.mycum, g.mzcum = (rank % sx) * n[0], (rank // sx % sy) * n[1], (rank // (sx * sy)) * n[2]
+    for nm, m_ in (("mxl", mx), ("myl", my), ("mzl", mz)):
+        a = R.FArr((g.size0,), np.int64)
+        a.flat[:] = m_
+        setattr(g, nm, a)
+    return n
+
+
+MR_CASES = [(2, 1, (16, 12, 1), (2, 2, 1), (1, 1, 1)),
+            (2, 2, (16, 12, 1), (2, 1, 1), (0, 1, 1)),
+            (3, 2, (16, 12, 12), (2, 2, 2), (1, 1, 1)),
+            (3, 1, (8, 12, 12), (1, 2, 2), (1, 0, 1)),
+            (3, 3, (24, 8, 8), (3, 1, 1), (0, 1, 1))]
+
+
+def gen_halo_mr():
+    out = {}
+    fb, ft = src("fieldboundaries.F90"), src("filter.F90")
+    names = ("ex", "ey", "ez", "bx", "by", "bz", "curx", "cury", "curz")
+    for ci, (dim, order, nglob, sizes, per) in enumerate(MR_CASES):
+        defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+        size0 = sizes[0] * sizes[1] * sizes[2]
+        comm = R.Comm(size0)
+        ga = GARR | {"bufferin1x", "bufferin2x", "bufferin1y", "bufferin2y", "bufferin1", "bufferin2", "mxl", "myl", "mzl"}
+        gi = GINTS | {"statsize", "mxcum", "mycum", "mzcum"}
+        subs = {nm: R.Sub(fb, nm, defines=defines, global_arrays=ga, global_ints=gi).compile() for nm in ("bc_b1", "bc_e1", "exchange_current")}
+        subs["apply_filter1_opt"] = R.Sub(ft, "apply_filter1_opt", defines=defines, global_arrays=ga, global_ints=gi).compile()
+        gs = []
+        key = f"x{ci}"
+        out[key + "_meta"] = np.array([dim, order, *per, *nglob], np.int32)
+        out[key + "_sizes"] = np.array(sizes, np.int32)
+        for rank in range(size0):
+            n = tuple(a // s_ for a, s_ in zip(nglob, sizes))
+            g = field_globals(dim, order, n, per, np.random.default_rng(1100 + 16 * ci + rank))
+            rank_geometry(g, dim, order, nglob, sizes, rank)
+            g.comm = comm
+            layer_copies(g, defines)
+            g.highorder = False
+            g.debug = False
+            g.ntimes = 2
+            g.temp = R.FArr((g.mx, g.my, g.mz))
+            ng = g.nghost
+            g.bufferin1x, g.bufferin2x = R.FArr((ng // 2 + 1, g.my, g.mz)), R.FArr((ng // 2, g.my, g.mz))
+            g.bufferin1y, g.bufferin2y = R.FArr((g.mx, ng // 2 + 1, g.mz)), R.FArr((g.mx, ng // 2, g.mz))
+            g.bufferin1, g.bufferin2 = R.FArr((g.mx, g.my, g.nghostz // 2 + 1)), R.FArr((g.mx, g.my, g.nghostz // 2))
+            for nm in ("curx", "cury", "curz"):            # see gen_halo: the last layer never holds a deposit
+                v = getattr(g, nm).nd()
+                v[-1, :, :] = 0; v[:, -1, :] = 0
+                if dim == 3:
+                    v[:, :, -1] = 0
+            for a, nm in enumerate(names):
+                out[f"{key}_r{rank}_in{a}"] = c_order(getattr(g, nm))
+            gs.append(g)
+
+        def lap(g):
+            subs["bc_b1"](g); subs["bc_e1"](g); subs["exchange_current"](g); subs["apply_filter1_opt"](g)
+        R.run_ranks([(lambda g=g: lap(g)) for g in gs])
+        for rank, g in enumerate(gs):
+            for a, nm in enumerate(names):
+                out[f"{key}_r{rank}_out{a}"] = c_order(getattr(g, nm))
+        print("halo_mr", key, dim, order, nglob, sizes, per)
+    np.savez_compressed(os.path.join(HERE, "ref_halo_mr.npz"), **out)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# G11: particle migration over several ranks -- deposit_particles, exchange_particles, inject_others, exchange_particles,
+#      inject_others (particles_movedeposit.F90:1281-2051, particles.F90:1368-2116; the call order of tristanmainloop.F90:
+#      183-249), ranks as threads (see G10).  Corner crossers take two hops (x/y first, z on the second exchange).
+# ------------------------------------------------------------------------------------------------------------
+def gen_migrate_mr():
+    out = {}
+    mtext, ptext = src("particles_movedeposit.F90"), src("particles.F90")
+    dirs = ("outup", "outdwn", "inblw", "inabv", "outlft", "outrgt", "inlft", "inrgt", "outminus", "outplus", "inminus", "inplus")
+    gi = GINTS | {"mxcum", "mycum", "mzcum", "nionout", "nlecout", "lap", "statsize", "buffsize", "receivedions", "receivedlecs"} \
+        | {f"len{s}{d}" for s in ("ion", "lec") for d in dirs}
+    pbufs = ("poutup", "poutdwn", "poutlft", "poutrgt", "poutminus", "poutplus", "pinblw", "pinabv", "pinlft", "pinrgt", "pinminus", "pinplus")
+    ga = GARR | {"pind", "mxl", "myl", "mzl"} | set(pbufs)
+    dep = {0: ("zzag", "zigzag"), 1: ("dd1", "densdecomp_1ord"), 2: ("dd2", "densdecomp_2ord"), 3: ("dd3", "densdecomp_3ord")}
+    cases = [(2, 1, (16, 12, 1), (2, 2, 1), (1, 1, 1)),
+             (2, 2, (16, 12, 1), (2, 1, 1), (0, 1, 1)),
+             (3, 2, (16, 12, 12), (2, 2, 2), (1, 1, 1)),
+             (3, 0, (8, 12, 12), (1, 2, 2), (1, 0, 1)),
+             (3, 1, (24, 8, 8), (3, 1, 1), (0, 1, 1))]
+    for ci, (dim, order, nglob, sizes, per) in enumerate(cases):
+        flag, name = dep[order]
+        defines = {"MPI", flag} | ({"twoD"} if dim == 2 else set())
+        size0 = sizes[0] * sizes[1] * sizes[2]
+        comm = R.Comm(size0)
+        subs = {nm: R.Sub(mtext if nm == "deposit_particles" else ptext, nm, defines=defines, global_arrays=ga, global_ints=gi).compile()
+                for nm in ("deposit_particles", "exchange_particles", "inject_others", name)}
+        key = f"y{ci}"
+        out[key + "_meta"] = np.array([dim, order, *per, *nglob], np.int32)
+        maxhlf, nsp = 160, 64
+        out[key + "_geom"] = np.array([*sizes, maxhlf, nsp], np.int32)
+        gs, ps = [], []
+        for rank in range(size0):
+            rng = np.random.default_rng(1200 + 16 * ci + rank)
+            n = tuple(a // s_ for a, s_ in zip(nglob, sizes))
+            g = field_globals(dim, order, n, per, rng)
+            rank_geometry(g, dim, order, nglob, sizes, rank)
+            ng, ngz, mx, my, mz = grid(dim, order, n)
+            g.comm = comm
+            g.x1in, g.x2in = F(1. * (ng // 2 + 1)), F(nglob[0] + ng - 1. * (ng // 2))
+            g.y1in, g.y2in = F(1. * (ng // 2 + 1)), F(nglob[1] + ng - 1. * (ng // 2))
+            g.z1in, g.z2in = F(1. * (ngz // 2 + 1)), F(nglob[2] + ngz - 1. * (ngz // 2))
+            g.qi, g.qe = F(0.07), F(-0.07)
+            g.debug, g.lap, g.statsize, g.buffsize = False, 1, 5, 4 * nsp
+            g.mpi_comm_world = g.mpi_integer = g.particletype = 0
+            g.mpi_wtime = lambda: 0.0                        # timers around the loops, not part of the result
+            for nm in ("curx", "cury", "curz"):
+                getattr(g, nm).flat[:] = 0
+            p = np.zeros(2 * maxhlf, PDT)
+            lo = np.array([ng // 2 + 1, ng // 2 + 1, ngz // 2 + 1], F)
+            ext = np.array([n[0], n[1], n[2] if dim == 3 else 1], F)
+            for s0 in (0, maxhlf):
+                sl = slice(s0, s0 + nsp)
+                pos = lo[:, None] + rng.random((3, nsp)) * ext[:, None]
+                edge = rng.random((3, nsp))
+                pos = np.where(edge < 0.15, lo[:, None] - 0.4 * rng.random((3, nsp)), pos)
+                pos = np.where(edge > 0.85, lo[:, None] + ext[:, None] + 0.4 * rng.random((3, nsp)), pos)
+                p["x"][sl], p["y"][sl], p["z"][sl] = pos.astype(F)
+                for k, ax in (("u", 0), ("v", 1), ("w", 2)):
+                    v = (rng.standard_normal(nsp) * 0.6).astype(F)
+                    below, above = pos[ax] < lo[ax], pos[ax] > lo[ax] + ext[ax]
+                    p[k][sl] = np.where(below, -np.abs(v) - F(1.2), np.where(above, np.abs(v) + F(1.2), v))
+                p["ch"][sl] = (0.5 + rng.random(nsp)).astype(F)
+                p["ind"][sl] = np.arange(1, nsp + 1) * (1 if s0 == 0 else -1)
+                p["proc"][sl] = rank
+                p["splitlev"][sl] = 1
+            g.p = R.RecArr(p)
+            g.ions, g.lecs, g.maxhlf = nsp, nsp, maxhlf
+            g.pind = R.FArr((2 * maxhlf,), np.int64)
+            for nm in pbufs:
+                setattr(g, nm, R.RecArr(np.zeros(g.buffsize, PDT)))
+            g.q = F(0)
+
+            def copyprt(a, b):
+                for k in PDT.names:
+                    setattr(b, k, getattr(a, k))
+            g.copyprt = copyprt
+            setattr(g, name, (lambda g_: (lambda *a: subs[name](g_, *a)))(g))
+            out[f"{key}_r{rank}_pin"] = p.copy()
+            gs.append(g); ps.append(p)
+
+        def lap(g):
+            subs["deposit_particles"](g); subs["exchange_particles"](g); subs["inject_others"](g)
+            subs["exchange_particles"](g); subs["inject_others"](g)
+        R.run_ranks([(lambda g=g: lap(g)) for g in gs])
+        tot = 0
+        for rank, (g, p) in enumerate(zip(gs, ps)):
+            out[f"{key}_r{rank}_pout"] = p.copy()
+            out[f"{key}_r{rank}_counts"] = np.array([g.ions, g.lecs], np.int32)
+            for a, nm in enumerate(("curx", "cury", "curz")):
+                out[f"{key}_r{rank}_cur{a}"] = c_order(getattr(g, nm))
+            tot += g.ions + g.lecs
+        print("migrate_mr", key, dim, order, nglob, sizes, per, "particles", 2 * nsp * size0, "->", tot, [int(g.ions) for g in gs])
+    np.savez_compressed(os.path.join(HERE, "ref_migrate_mr.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr"]
     for w in which:
         globals()["gen_" + w]()

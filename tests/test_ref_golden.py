@@ -262,3 +262,62 @@ def test_deposit_particles_matches_the_reference_source(case):
         ni, nl, box = _box(r, 0, d)
         assert (ni, nl) == (int(lens[d, 0]), int(lens[d, 1])), d
         assert np.array_equal(box, z[f"{key}_box{d}"][:ni + nl]), d
+
+
+MR_STAGES = ("PH_BC_B1", "PH_BC_E1", "PH_EXCH_CUR", "PH_FILTER")
+
+
+@pytest.mark.parametrize("case", range(5))
+def test_multirank_halo_fold_and_filter_match_the_reference_source(case):
+    """SEVERAL RANKS: every rank ran the reference's bc_b1, bc_e1, exchange_current and apply_filter1_opt (ntimes = 2) in its
+    own thread with MPI_SendRecv as a rendezvous (tests/golden/f90run.py: Comm), on 2x2 / 2x1 (2D) and 2x2x2 / 1x2x2 / 3x1x1
+    (3D) boxes with periodic and open axes.  The oracle's world phases must give the same arrays on every rank: BIT-EXACT."""
+    z = load("ref_halo_mr.npz")
+    key = f"x{case}"
+    dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
+    sizes = tuple(int(v) for v in z[key + "_sizes"])
+    w = T.oracle_world(dim=dim, order=order, n=(nx, ny, nz), sizes=sizes, ppc=0.0, init="none", seed_fields=0, periodic=(px, py, pz),
+                       ntimes=2, filter_kind=1)
+    for rk, r in enumerate(w.ranks):
+        for a in range(9):
+            r.arr(a)[...] = z[f"{key}_r{rk}_in{a}"]
+    for st in MR_STAGES:
+        w.phase(getattr(O, st))
+    for rk, r in enumerate(w.ranks):
+        for a in range(9):
+            ref = z[f"{key}_r{rk}_out{a}"]
+            assert np.array_equal(r.arr(a), ref), (rk, O.ARR_NAMES[a], float(np.abs(r.arr(a) - ref).max()))
+
+
+@pytest.mark.parametrize("case", range(5))
+def test_multirank_particle_migration_matches_the_reference_source(case):
+    """SEVERAL RANKS: deposit_particles, exchange_particles, inject_others, exchange_particles, inject_others run from the
+    reference's source on every rank (threads + MPI_SendRecv rendezvous).  15 % of the particles sit outside each face, so edge
+    and corner crossers (two hops) are common, and the few that cross three faces at once are dropped by the reference's
+    two-hop scheme.  Per rank: counts, the particle array IN ORDER and the currents BIT-EXACT."""
+    z = load("ref_migrate_mr.npz")
+    key = f"y{case}"
+    dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
+    sx, sy, sz, maxhlf, nsp = (int(v) for v in z[key + "_geom"])
+    w = T.oracle_world(dim=dim, order=order, n=(nx, ny, nz), sizes=(sx, sy, sz), ppc=0.0, init="none", seed_fields=0, periodic=(px, py, pz),
+                       charges=(float(np.float32(0.07)), float(np.float32(-0.07))))
+    for rk, r in enumerate(w.ranks):
+        pin = z[f"{key}_r{rk}_pin"]
+        p = r.particles()
+        assert r.maxhlf >= maxhlf
+        p[:nsp] = pin[:nsp]
+        p[r.maxhlf:r.maxhlf + nsp] = pin[maxhlf:maxhlf + nsp]
+        r.set_counts(nsp, nsp)
+        for a in range(6, 9):
+            r.arr(a)[...] = 0
+    for ph in (O.PH_DEPOSIT, O.PH_EXCH_P, O.PH_INJECT_OTHERS, O.PH_EXCH_P, O.PH_INJECT_OTHERS):
+        w.phase(ph)
+    for rk, r in enumerate(w.ranks):
+        ions, lecs = (int(v) for v in z[f"{key}_r{rk}_counts"])
+        assert r.counts == (ions, lecs), (rk, r.counts, (ions, lecs))
+        pout = z[f"{key}_r{rk}_pout"]
+        p = r.particles()
+        assert np.array_equal(p[:ions], pout[:ions]), rk
+        assert np.array_equal(p[r.maxhlf:r.maxhlf + lecs], pout[maxhlf:maxhlf + lecs]), rk
+        for a in range(3):
+            assert np.array_equal(r.arr(6 + a), z[f"{key}_r{rk}_cur{a}"]), (rk, a)
