@@ -215,6 +215,9 @@ class RecArr:
     def __getitem__(self, i):
         return Record(self.a, int(i) - 1)
 
+    def __setitem__(self, i, rec):
+        self.a[int(i) - 1] = rec._a[rec._i]               # tempp(j) = p(n)
+
     def set(self, val):
         """whole-array assignment from a message or from another array of the type"""
         v = val.data if isinstance(val, Payload) else val.a
@@ -364,6 +367,9 @@ def extract_subroutine(text, name):
     if not m:
         raise KeyError(name)
     e = re.search(r"^[ \t]*end\s*" + m.group(1) + r"\s+" + name + r"\b", text[m.start():], flags=re.I | re.M)
+    e0 = re.search(r"^[ \t]*end\s*" + m.group(1) + r"\b", text[m.start():], flags=re.I | re.M)      # `end subroutine` with no name
+    if e is None or e0.end() < e.start():
+        e = e0
     return text[m.start():m.start() + e.end()]
 
 
@@ -713,7 +719,7 @@ class Sub:
         def emit(s):
             body.append("    " * ind + s)
         for st in self.stmts[1:]:
-            if st.startswith("end subroutine") or st.startswith("endsubroutine") or st.startswith("end function"):
+            if re.match(r"end\s*(subroutine|function)\b", st):
                 break
             if st.startswith("implicit") or st.startswith("use ") or st.startswith("intent") or st.startswith("external"):
                 continue
@@ -750,8 +756,6 @@ class Sub:
             m = re.match(r"do\s+([a-z_]\w*)\s*=\s*(.*)$", st)
             if m:
                 parts = self.split_dims(m.group(2))
-                if self.ref(m.group(1)).startswith("_g."):
-                    raise SyntaxError("loop variable must be local: " + st)
                 # Fortran evaluates the bounds once and leaves the variable at its first failing value after the loop
                 # (optimized_filters.F90 relies on that: "i = ntimes-1" after `do i=2,ntimes-2,2`)
                 nloop[0] += 1

@@ -697,7 +697,151 @@ def gen_migrate_mr():
     np.savez_compressed(os.path.join(HERE, "ref_migrate_mr.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G12: WHOLE LAPS.  `mainloop` itself (tristanmainloop.F90:60-330) is executed: the order of the calls is the reference's
+#      text, every hot-path routine it calls is the reference's text, ranks are threads (G10).  Only the timers, the
+#      diagnostics / output, the domain-rebalancing calls and the problem's injector are bound to no-ops.
+# ------------------------------------------------------------------------------------------------------------
+LAP_CASES = [  # dim order nglob       sizes      periodic   laps highorder shock ppc
+    (2, 1, (16, 12, 1), (2, 2, 1), (1, 1, 1), 10, 0, 0, 2),
+    (3, 2, (12, 6, 12), (2, 1, 2), (1, 1, 1), 3, 0, 0, 1),
+    (3, 0, (7, 6, 6), (1, 1, 1), (0, 0, 0), 3, 0, 0, 2),
+    (2, 1, (40, 8, 1), (2, 1, 1), (0, 1, 1), 3, 0, 1, 2),
+    (3, 3, (6, 12, 6), (1, 2, 1), (1, 1, 1), 2, 1, 0, 1)]
+
+
+def gen_lap():
+    out = {}
+    T_ = {nm: src(nm + ".F90") for nm in ("tristanmainloop", "fields", "fieldboundaries", "filter", "particles", "particles_movedeposit")}
+    T_["user"] = open(os.path.join(REF, "user", "user_shock.F90")).read()
+    main_text = "\n".join(l for l in T_["tristanmainloop"].split("\n") if not l.strip().lower().startswith("call timer"))
+    dirs = ("outup", "outdwn", "inblw", "inabv", "outlft", "outrgt", "inlft", "inrgt", "outminus", "outplus", "inminus", "inplus")
+    gi = GINTS | {"mxcum", "mycum", "mzcum", "nionout", "nlecout", "lap", "lapst", "last", "statsize", "buffsize", "receivedions",
+                  "receivedlecs", "radiationx", "radiationy", "radiationz", "mx0", "lapreorder", "outcorner"} \
+        | {f"len{s_}{d}" for s_ in ("ion", "lec") for d in dirs}
+    pbufs = ("poutup", "poutdwn", "poutlft", "poutrgt", "poutminus", "poutplus", "pinblw", "pinabv", "pinlft", "pinrgt", "pinminus", "pinplus")
+    ga = GARR | {"pind", "pall", "tempp", "mxl", "myl", "mzl", "bufferin1x", "bufferin2x", "bufferin1y", "bufferin2y", "bufferin1", "bufferin2"} | set(pbufs)
+    mov = {0: ("zzag", "mover", "zigzag"), 1: ("dd1", "mover_1ord", "densdecomp_1ord"), 2: ("dd2", "mover_2ord", "densdecomp_2ord"),
+           3: ("dd3", "mover_3ord", "densdecomp_3ord")}
+    where = {"mainloop": "main", "advance_bhalfstep": "fields", "advance_efield": "fields", "advance_b_halfstep": "fields",
+             "advance_e_fullstep": "fields", "advance_b_halfstep_42": "fields", "advance_e_fullstep_42": "fields", "add_current": "fields",
+             "reset_currents": "fields", "iloc": "fields", "xglob": "fields",
+             "move_particles": "particles_movedeposit", "deposit_particles": "particles_movedeposit",
+             "exchange_particles": "particles", "inject_others": "particles", "reorder_particles": "particles",
+             "reorder_particles_": "particles", "zigzag": "particles",
+             "apply_filter1_opt": "filter", "field_bc_user": "user", "particle_bc_user": "user"}
+    for nm in ("bc_b1", "bc_e1", "bc_b2", "bc_e2", "pre_bc_b", "post_bc_b", "pre_bc_e", "post_bc_e", "surface", "preledge", "postedge",
+               "exchange_current", "copylayrx", "copylayry", "copy_layrx1_opt", "copy_layry1_opt", "copy_layrz1_opt", "copy_layrx2_opt",
+               "copy_layry2_opt", "copy_layrz2_opt"):
+        where[nm] = "fieldboundaries"
+    noop = ("diagnostics", "inject_particles", "check_overflow", "enlarge_domain", "redist_x_domain", "redist_y_domain", "shift_domain",
+            "redist_z_domain", "print_timers", "pause_simulation")
+    names9 = ("ex", "ey", "ez", "bx", "by", "bz", "curx", "cury", "curz")
+    for ci, (dim, order, nglob, sizes, per, laps, highorder, shock, ppc) in enumerate(LAP_CASES):
+        flag, mover, dname = mov[order]
+        defines = {"MPI", flag} | ({"twoD"} if dim == 2 else set())
+        size0 = sizes[0] * sizes[1] * sizes[2]
+        comm = R.Comm(size0, timeout=600.0)
+        need = dict(where)
+        need[mover] = "particles_movedeposit"
+        need[dname] = "particles"
+        if not shock:
+            del need["field_bc_user"], need["particle_bc_user"]
+        subs = {nm: R.Sub(main_text if f == "main" else T_[f], nm, defines=defines, global_arrays=ga, global_ints=gi).compile()
+                for nm, f in need.items()}
+        key = f"l{ci}"
+        out[key + "_meta"] = np.array([dim, order, *per, *nglob], np.int32)
+        n = tuple(a // s_ for a, s_ in zip(nglob, sizes))
+        ng, ngz, mx, my, mz = grid(dim, order, n)
+        ncell = n[0] * n[1] * (n[2] if dim == 3 else 1)
+        nsp = ppc * ncell
+        maxhlf = 2 * nsp + 64
+        out[key + "_geom"] = np.array([*sizes, maxhlf, nsp, laps, highorder, shock], np.int32)
+        gs, ps = [], []
+        for rank in range(size0):
+            rng = np.random.default_rng(1300 + 16 * ci + rank)
+            g = field_globals(dim, order, n, per, rng)
+            for nm in names9[:6]:                                   # small-amplitude fields
+                getattr(g, nm).flat[:] *= F(0.2)
+            rank_geometry(g, dim, order, nglob, sizes, rank)
+            g.comm = comm
+            g.radiationx, g.radiationy, g.radiationz = 1 - per[0], 1 - per[1], 1 - per[2]
+            if dim == 2 and g.radiationy == 1:
+                g.radiationz = 1
+            g.mx0 = nglob[0] + ng
+            g.x1in, g.x2in = F(1. * (ng // 2 + 1)), F(nglob[0] + ng - 1. * (ng // 2))
+            g.y1in, g.y2in = F(1. * (ng // 2 + 1)), F(nglob[1] + ng - 1. * (ng // 2))
+            g.z1in, g.z2in = F(1. * (ngz // 2 + 1)), F(nglob[2] + ngz - 1. * (ngz // 2))
+            g.qi, g.qe, g.qmi, g.qme = F(0.07), F(-0.07), F(0.5), F(-1.0)
+            g.debug, g.statsize, g.buffsize = False, 5, maxhlf
+            g.lap, g.lapst, g.last, g.lapreorder, g.outcorner = 0, 1, laps, -5, 0
+            g.highorder, g.external_fields, g.ntimes = bool(highorder), False, 2
+            g.wall, g.user_part_bcs = bool(shock), bool(shock)
+            g.delgam, g.qme_abs = F(1e-2), F(1.0)
+            g.xinject2 = F(nglob[0] + ng)
+            g.leftwall, g.binit, g.btheta, g.bphi, g.beta = F(8.0), F(0.02), F(1.1), F(0.4), F(0.3)
+            g.mpi_comm_world = g.mpi_integer = g.particletype = g.mpi_read = 0
+            g.mpi_wtime = lambda: 0.0
+            g.temp = R.FArr((g.mx, g.my, g.mz))
+            g.bufferin1x, g.bufferin2x = R.FArr((ng // 2 + 1, g.my, g.mz)), R.FArr((ng // 2, g.my, g.mz))
+            g.bufferin1y, g.bufferin2y = R.FArr((g.mx, ng // 2 + 1, g.mz)), R.FArr((g.mx, ng // 2, g.mz))
+            g.bufferin1, g.bufferin2 = R.FArr((g.mx, g.my, g.nghostz // 2 + 1)), R.FArr((g.mx, g.my, g.nghostz // 2))
+            for nm in ("curx", "cury", "curz"):
+                getattr(g, nm).flat[:] = 0
+            p = np.zeros(2 * maxhlf, PDT)
+            lo = np.array([ng // 2 + 1, ng // 2 + 1, ngz // 2 + 1], F)
+            ext = np.array([n[0], n[1], n[2] if dim == 3 else 1], F)
+            for s0 in (0, maxhlf):
+                sl = slice(s0, s0 + nsp)
+                pos = lo[:, None] + rng.random((3, nsp)) * ext[:, None]
+                if shock and rank == 0:                              # nothing starts behind the wall
+                    pos[0] = np.maximum(pos[0], 8.5)
+                p["x"][sl], p["y"][sl], p["z"][sl] = pos.astype(F)
+                for k in "uvw":
+                    p[k][sl] = (rng.standard_normal(nsp) * 0.5).astype(F)
+                if shock:
+                    p["u"][sl] -= F(0.6)                             # a stream towards the wall
+                p["ch"][sl] = 1.0
+                p["ind"][sl] = np.arange(1, nsp + 1) * (1 if s0 == 0 else -1)
+                p["proc"][sl] = rank
+                p["splitlev"][sl] = 1
+            g.p = R.RecArr(p)
+            g.tempp = R.RecArr(np.zeros(maxhlf, PDT))
+            g.pall = R.FArr((g.lot,), np.int64)
+            g.ions, g.lecs, g.maxhlf = nsp, nsp, maxhlf
+            g.pind = R.FArr((2 * maxhlf,), np.int64)
+            for nm in pbufs:
+                setattr(g, nm, R.RecArr(np.zeros(g.buffsize, PDT)))
+            g.q = F(0)
+
+            def copyprt(a, b):
+                for k in PDT.names:
+                    setattr(b, k, getattr(a, k))
+            g.copyprt = copyprt
+            for nm, f in subs.items():
+                setattr(g, nm, (lambda f_, g_: (lambda *a: f_(g_, *a)))(f, g))
+            for nm in noop:
+                setattr(g, nm, lambda *a: None)
+            if not shock:
+                g.field_bc_user = lambda: None
+                g.particle_bc_user = lambda: None
+            for a, nm in enumerate(names9[:6]):
+                out[f"{key}_r{rank}_in{a}"] = c_order(getattr(g, nm))
+            out[f"{key}_r{rank}_pin"] = p.copy()
+            gs.append(g); ps.append(p)
+        R.OVERLONG.clear()
+        R.run_ranks([(lambda g=g: g.mainloop()) for g in gs])
+        for rank, (g, p) in enumerate(zip(gs, ps)):
+            for a, nm in enumerate(names9):
+                out[f"{key}_r{rank}_out{a}"] = c_order(getattr(g, nm))
+            out[f"{key}_r{rank}_pout"] = p.copy()
+            out[f"{key}_r{rank}_counts"] = np.array([g.ions, g.lecs], np.int32)
+        out[key + "_par"] = np.array([gs[0].leftwall, gs[0].binit, gs[0].btheta, gs[0].bphi, gs[0].beta, gs[0].qi, gs[0].qe, gs[0].qmi, gs[0].qme], F)
+        print("lap", key, dim, order, nglob, sizes, per, "laps", laps, "counts", [(int(g.ions), int(g.lecs)) for g in gs], "overlong msgs", len(R.OVERLONG))
+    np.savez_compressed(os.path.join(HERE, "ref_lap.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap"]
     for w in which:
         globals()["gen_" + w]()

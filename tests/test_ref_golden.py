@@ -321,3 +321,47 @@ def test_multirank_particle_migration_matches_the_reference_source(case):
         assert np.array_equal(p[r.maxhlf:r.maxhlf + lecs], pout[maxhlf:maxhlf + lecs]), rk
         for a in range(3):
             assert np.array_equal(r.arr(6 + a), z[f"{key}_r{rk}_cur{a}"]), (rk, a)
+
+
+def lap_world(z, case):
+    key = f"l{case}"
+    dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
+    sx, sy, sz, maxhlf, nsp, laps, highorder, shock = (int(v) for v in z[key + "_geom"])
+    par = z[key + "_par"]
+    P = O.make_params(dim=dim, order=order, mx0=nx, my0=ny, mz0=nz, sizex=sx, sizey=sy, sizez=sz, ntimes=2, filter_kind=1,
+                      periodic=(px, py, pz), maxptl=2 * maxhlf, highorder=highorder, wall_i2=0)
+    P.qi, P.qe, P.qmi, P.qme = (float(v) for v in par[5:9])
+    w = O.World(P)
+    for rk, r in enumerate(w.ranks):
+        assert r.maxhlf == maxhlf
+        for a in range(6):
+            r.arr(a)[...] = z[f"{key}_r{rk}_in{a}"]
+        for a in range(6, 9):
+            r.arr(a)[...] = 0
+        r.particles()[:] = z[f"{key}_r{rk}_pin"]
+        r.set_counts(nsp, nsp)
+    return key, w, laps, shock, par, maxhlf
+
+
+@pytest.mark.parametrize("case", range(5))
+def test_whole_laps_match_the_reference_mainloop(case):
+    """WHOLE LAPS: the reference's `mainloop` (tristanmainloop.F90:60-330) executed from its own text on every rank, calling
+    the reference's own text for every routine on the path (solver, movers, deposit, migration, ghost refresh, radiation,
+    edges, fold, filter, add_current, reorder at lap 10, the shock hooks in case 3, the _42 solver in case 4).  The oracle's
+    orc_step / orc_step_shock from the same state: fields, currents, counts and the particle arrays IN ORDER, BIT-EXACT."""
+    z = load("ref_lap.npz")
+    key, w, laps, shock, par, maxhlf = lap_world(z, case)
+    for _ in range(laps):
+        if shock:
+            w.call("step_shock", *(C.c_float(float(v)) for v in par[:5]))
+        else:
+            w.step()
+    for rk, r in enumerate(w.ranks):
+        ions, lecs = (int(v) for v in z[f"{key}_r{rk}_counts"])
+        assert r.counts == (ions, lecs), (rk, r.counts, (ions, lecs))
+        for a in range(9):
+            ref = z[f"{key}_r{rk}_out{a}"]
+            assert np.array_equal(r.arr(a), ref), (rk, O.ARR_NAMES[a], float(np.abs(r.arr(a) - ref).max()), float(np.abs(ref).max()))
+        pout, p = z[f"{key}_r{rk}_pout"], r.particles()
+        assert np.array_equal(p[:ions], pout[:ions]), rk
+        assert np.array_equal(p[maxhlf:maxhlf + lecs], pout[maxhlf:maxhlf + lecs]), rk
