@@ -440,10 +440,10 @@ def gen_depositp():
     cases = [(2, 1, (12, 10, 1), (1, 1, 1), 0, (1, 1, 1)),
              (2, 2, (12, 10, 1), (1, 1, 1), 0, (0, 1, 1)),
              (2, 0, (24, 20, 1), (2, 2, 1), 3, (1, 1, 1)),
-             (3, 2, (16, 12, 12), (2, 2, 2), 5, (1, 1, 1)),
+             (3, 2, (8, 12, 12), (1, 2, 2), 3, (1, 1, 1)),           # 3D: sizex = 1 always (communications.F90:176-181)
              (3, 1, (10, 8, 8), (1, 1, 1), 0, (1, 1, 1)),
              (3, 3, (10, 16, 8), (1, 2, 1), 1, (1, 0, 1)),
-             (3, 0, (16, 8, 16), (2, 1, 2), 0, (0, 1, 0))]
+             (3, 0, (8, 8, 16), (1, 1, 2), 0, (0, 1, 0))]
     for ci, (dim, order, ng_, sizes, rank, per) in enumerate(cases):
         flag, name = dep[order]
         defines = {"MPI", flag} | ({"twoD"} if dim == 2 else set())
@@ -548,9 +548,10 @@ def rank_geometry(g, dim, order, nglob, sizes, rank):
 
 MR_CASES = [(2, 1, (16, 12, 1), (2, 2, 1), (1, 1, 1)),
             (2, 2, (16, 12, 1), (2, 1, 1), (0, 1, 1)),
-            (3, 2, (16, 12, 12), (2, 2, 2), (1, 1, 1)),
+            (3, 2, (8, 12, 12), (1, 2, 2), (1, 1, 1)),              # 3D: sizex = 1 always (communications.F90:176-181)
             (3, 1, (8, 12, 12), (1, 2, 2), (1, 0, 1)),
-            (3, 3, (24, 8, 8), (3, 1, 1), (0, 1, 1))]
+            (3, 3, (8, 24, 8), (1, 3, 1), (0, 1, 1)),
+            (2, 1, (24, 8, 1), (3, 1, 1), (0, 0, 1))]
 
 
 def gen_halo_mr():
@@ -618,9 +619,10 @@ def gen_migrate_mr():
     dep = {0: ("zzag", "zigzag"), 1: ("dd1", "densdecomp_1ord"), 2: ("dd2", "densdecomp_2ord"), 3: ("dd3", "densdecomp_3ord")}
     cases = [(2, 1, (16, 12, 1), (2, 2, 1), (1, 1, 1)),
              (2, 2, (16, 12, 1), (2, 1, 1), (0, 1, 1)),
-             (3, 2, (16, 12, 12), (2, 2, 2), (1, 1, 1)),
+             (3, 2, (8, 12, 12), (1, 2, 2), (1, 1, 1)),
              (3, 0, (8, 12, 12), (1, 2, 2), (1, 0, 1)),
-             (3, 1, (24, 8, 8), (3, 1, 1), (0, 1, 1))]
+             (3, 1, (8, 24, 8), (1, 3, 1), (0, 1, 1)),
+             (2, 0, (24, 8, 1), (3, 1, 1), (0, 0, 1))]
     for ci, (dim, order, nglob, sizes, per) in enumerate(cases):
         flag, name = dep[order]
         defines = {"MPI", flag} | ({"twoD"} if dim == 2 else set())
@@ -704,10 +706,15 @@ def gen_migrate_mr():
 # ------------------------------------------------------------------------------------------------------------
 LAP_CASES = [  # dim order nglob       sizes      periodic   laps highorder shock ppc
     (2, 1, (16, 12, 1), (2, 2, 1), (1, 1, 1), 10, 0, 0, 2),
-    (3, 2, (12, 6, 12), (2, 1, 2), (1, 1, 1), 3, 0, 0, 1),
+    (3, 2, (6, 12, 12), (1, 2, 2), (1, 1, 1), 3, 0, 0, 1),
     (3, 0, (7, 6, 6), (1, 1, 1), (0, 0, 0), 3, 0, 0, 2),
     (2, 1, (40, 8, 1), (2, 1, 1), (0, 1, 1), 3, 0, 1, 2),
-    (3, 3, (6, 12, 6), (1, 2, 1), (1, 1, 1), 2, 1, 0, 1)]
+    (3, 3, (6, 12, 6), (1, 2, 1), (1, 1, 1), 2, 1, 0, 1),
+    # one-rank boxes: these are also run through the CUDA library (tests/test_gpu_ref_golden.py)
+    (3, 2, (8, 8, 8), (1, 1, 1), (1, 1, 1), 3, 0, 0, 2),
+    (2, 1, (16, 12, 1), (1, 1, 1), (1, 1, 1), 3, 0, 0, 4),
+    (2, 2, (40, 8, 1), (1, 1, 1), (0, 1, 1), 3, 0, 1, 2),
+    (3, 3, (8, 6, 6), (1, 1, 1), (1, 1, 1), 2, 1, 0, 2)]
 
 
 def gen_lap():

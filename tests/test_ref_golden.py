@@ -267,11 +267,11 @@ def test_deposit_particles_matches_the_reference_source(case):
 MR_STAGES = ("PH_BC_B1", "PH_BC_E1", "PH_EXCH_CUR", "PH_FILTER")
 
 
-@pytest.mark.parametrize("case", range(5))
+@pytest.mark.parametrize("case", range(6))
 def test_multirank_halo_fold_and_filter_match_the_reference_source(case):
     """SEVERAL RANKS: every rank ran the reference's bc_b1, bc_e1, exchange_current and apply_filter1_opt (ntimes = 2) in its
-    own thread with MPI_SendRecv as a rendezvous (tests/golden/f90run.py: Comm), on 2x2 / 2x1 (2D) and 2x2x2 / 1x2x2 / 3x1x1
-    (3D) boxes with periodic and open axes.  The oracle's world phases must give the same arrays on every rank: BIT-EXACT."""
+    own thread with MPI_SendRecv as a rendezvous (tests/golden/f90run.py: Comm), on 2x2 / 2x1 / 3x1 (2D) and 1x2x2 / 1x3x1
+    (3D; the reference has sizex = 1 in 3D) boxes with periodic and open axes.  The oracle's world phases must give the same arrays on every rank: BIT-EXACT."""
     z = load("ref_halo_mr.npz")
     key = f"x{case}"
     dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
@@ -289,7 +289,7 @@ def test_multirank_halo_fold_and_filter_match_the_reference_source(case):
             assert np.array_equal(r.arr(a), ref), (rk, O.ARR_NAMES[a], float(np.abs(r.arr(a) - ref).max()))
 
 
-@pytest.mark.parametrize("case", range(5))
+@pytest.mark.parametrize("case", range(6))
 def test_multirank_particle_migration_matches_the_reference_source(case):
     """SEVERAL RANKS: deposit_particles, exchange_particles, inject_others, exchange_particles, inject_others run from the
     reference's source on every rank (threads + MPI_SendRecv rendezvous).  15 % of the particles sit outside each face, so edge
@@ -343,7 +343,7 @@ def lap_world(z, case):
     return key, w, laps, shock, par, maxhlf
 
 
-@pytest.mark.parametrize("case", range(5))
+@pytest.mark.parametrize("case", range(9))
 def test_whole_laps_match_the_reference_mainloop(case):
     """WHOLE LAPS: the reference's `mainloop` (tristanmainloop.F90:60-330) executed from its own text on every rank, calling
     the reference's own text for every routine on the path (solver, movers, deposit, migration, ghost refresh, radiation,
