@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product package never imports this module.
-PARITY UNPINNED: see the header of pic_oracle.h.
+PARITY: pinned against the reference's source text (tests/test_ref_golden.py); see the header of pic_oracle.h.
 """
 import ctypes as C
 import os

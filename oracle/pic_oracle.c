@@ -2,8 +2,9 @@
  * pic_oracle.c -- CPU restatement of the TRISTAN-MP (PU fork, Esirkepov branch)
  * per-timestep PIC hot path.  TEST INFRASTRUCTURE ONLY; see pic_oracle.h.
  *
- * PARITY UNPINNED (no golden vectors exist in the reference; it cannot be
- * built here).  Every routine cites the reference file:line it restates.
+ * PARITY: pinned bit-exact against the reference's own source text executed by
+ * tests/golden/f90run.py (tests/test_ref_golden.py); the reference cannot be
+ * compiled here.  Every routine cites the reference file:line it restates.
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared (oracle/Makefile).
  * -ffp-contract=off keeps every fp32 operation separately rounded, in the

@@ -5,11 +5,17 @@
  * libtristan_gpu.so) may include, link or call this.  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
  *
- * PARITY UNPINNED: the reference ships no golden vectors, no tests, and cannot
- * be compiled in this image (no Fortran compiler, no MPI).  This restatement
- * follows the reference source routine by routine (file:line cited at every
- * function, relative to the reference checkout) and is pinned only by physics
- * known-answer tests (tests/test_oracle_*.py).
+ * PARITY PINNED AGAINST THE REFERENCE'S SOURCE TEXT, not against a compiled
+ * reference: the reference ships no golden vectors or tests and cannot be
+ * compiled in this image or on the GPU box (no Fortran compiler, no MPI).  Its
+ * hot-path subroutines -- up to `mainloop` itself, on several ranks -- are
+ * executed from their text by the Fortran-subset interpreter
+ * tests/golden/f90run.py; tests/test_ref_golden.py holds this restatement
+ * BIT-EXACT against those outputs (tests/golden/ref_*.npz; 79 cases).  Not
+ * covered that way, and pinned only by the known-answer tests
+ * (tests/test_oracle_kat.py): the loaders, meanq / spectrum, multi-rank
+ * filter2, restart I/O.  See DESIGN.md section 2.  Every function cites the
+ * reference file:line it follows (relative to the reference checkout).
  *
  * Conventions: arrays are Fortran column-major (mx,my,mz), addressed here with
  * 1-based (i,j,k) through ORC_IDX so index arithmetic reads like the reference.

@@ -9,10 +9,18 @@ with numpy.float32 scalars (every operation rounds to fp32, in the source's orde
 make_ref_golden.py uses it to produce golden vectors (committed as tests/golden/ref_*.npz) that pin the oracle; nothing at test
 time or on the GPU box reads /root/reference.
 
-Subset: scalar / array assignments, whole-array assignments and expressions, array sections, do / do while / if-elseif-else,
-one-line if, call (to other translated subroutines or to Python stubs), derived-type components (p(n)%x), the intrinsics
-aint int real min max abs sqrt sum cshift mod modulo.  MPI: only the single-rank case is modelled -- MPI_SendRecv to oneself
-(what one rank on a periodic axis does) is "recvbuf = sendbuf"; other mpi_* calls are dropped.  TEST INFRASTRUCTURE ONLY.
+Subset: subroutines and functions (integer / real result), scalar / array assignments, whole-array assignments and
+expressions, array sections, do (local or module loop variable) / do while / if-elseif-else, one-line if, the two goto idioms
+of the path (an unconditional forward skip to `N continue`; `go to N` where `N continue` closes the loop = cycle), call (to
+other translated routines or to Python stand-ins), derived-type components (p(n)%x) and element assignment (tempp(j) = p(n)),
+integer arrays, the intrinsics aint int real min max abs sqrt sum cshift mod modulo sign cos sin nint floor.
+
+MPI.  MPI_SendRecv is executed, not stubbed: `count` elements of the send buffer in Fortran element order (Payload) go to
+`dest` with `sendtag`, and the message from `source` with `recvtag` lands in the first `count` elements of the receive buffer.
+With one rank (Globals.comm is None) every neighbour is the rank itself.  With several ranks each rank is a THREAD that runs
+the reference's text on its own Globals, and Comm.sendrecv is the rendezvous -- neighbour ranks, tags, counts and ordering
+are whatever the reference's source computes.  Other mpi_* calls (barrier, wtime as a stand-in) carry no data and are dropped.
+TEST INFRASTRUCTURE ONLY.
 """
 import math
 import re

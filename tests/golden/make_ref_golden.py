@@ -7,7 +7,12 @@ subroutines are executed by the Fortran-subset interpreter tests/golden/f90run.p
 The inputs (seeded, generated here) and the reference's outputs are stored in tests/golden/ref_*.npz; tests/test_ref_golden.py
 checks the CPU oracle against them (bit for bit) and tests/test_gpu_ref_golden.py the CUDA library.  Re-run:
 
-    python tests/golden/make_ref_golden.py            # needs /root/reference; takes a few minutes (a Python interpreter of Fortran)
+    python tests/golden/make_ref_golden.py            # needs /root/reference; ~10 minutes (a Python interpreter of Fortran)
+    python tests/golden/make_ref_golden.py lap        # one group: deposit fields mover filter radiation halo fields42 shock
+                                                      #            depositp halo_mr migrate_mr lap
+
+G1-G9 run single routines on one rank (or on one rank of a split box); G10-G12 run SEVERAL RANKS as threads with MPI_SendRecv
+as a rendezvous, up to whole laps of `mainloop` itself.  Seeds are fixed: re-running reproduces the committed files.
 """
 import os
 import sys
