@@ -111,6 +111,12 @@ class FArr:
     def set(self, val):
         """whole-array assignment"""
         if isinstance(val, Payload):
+            if isinstance(val.rtype, Subarray):
+                if self.shape != val.rtype.sizes:
+                    raise TypeError(f"subarray datatype {val.rtype.sizes} on a receive buffer of shape {self.shape}")
+                dst = self.nd()[val.rtype.box]
+                dst[...] = val.data.reshape(dst.shape, order="F")
+                return
             self.flat[:val.data.size] = val.data
             return
         self.nd()[...] = val.nd() if isinstance(val, FArr) else val
@@ -138,13 +144,26 @@ class Payload:
     """what an MPI message carries: `count` elements of the send buffer in Fortran (column-major) element order.  The receive
     side stores them into the first `count` elements of ITS buffer, again in Fortran order -- shapes play no role."""
 
-    def __init__(self, data):
+    def __init__(self, data, rtype=None):
         self.data = data                  # 1-D numpy array (plain or structured), already a copy
+        self.rtype = rtype                # receive-side derived datatype (Subarray) or None
 
 
-def as_payload(buf, count):
+class Subarray:
+    """MPI_Type_create_subarray(ndims, sizes, subsizes, starts, MPI_ORDER_FORTRAN, ...): a box inside an array"""
+
+    def __init__(self, sizes, subsizes, starts):
+        self.sizes = tuple(int(v) for v in sizes)
+        self.box = tuple(slice(int(a), int(a) + int(n)) for a, n in zip(starts, subsizes))
+
+
+def as_payload(buf, count, stype=None):
     if isinstance(buf, Payload):
         return buf
+    if isinstance(stype, Subarray):
+        if not isinstance(buf, FArr) or buf.shape != stype.sizes or int(count) != 1:
+            raise TypeError(f"subarray datatype {stype.sizes} on a buffer of shape {getattr(buf, 'shape', None)}, count {count}")
+        return Payload(buf.nd()[stype.box].reshape(-1, order="F").copy())
     if isinstance(buf, RecArr):
         flat = buf.a
     elif isinstance(buf, FArr):
@@ -660,7 +679,22 @@ class Sub:
             # With several ranks (Globals.comm set) the message goes through Comm; either way the transfer is `count` elements
             # in Fortran order (Payload).
             a = self.split_dims(st[st.index("(") + 1:st.rindex(")")])
-            return self.assign(a[5], f"mpi_xchg({a[0]}, {a[1]}, {a[3]}, {a[4]}, {a[8]}, {a[9]})")
+            return self.assign(a[5], f"mpi_xchg({a[0]}, {a[1]}, {a[3]}, {a[4]}, {a[8]}, {a[9]}, {a[2]}, {a[7]})")
+        if st.startswith("call mpi_type_create_subarray"):
+            # the derived datatypes of filter2's ghost exchange (fields.F90:1449-1600): keep the box the reference describes
+            a = self.split_dims(st[st.index("(") + 1:st.rindex(")")])
+            return self.assign(a[6], f"mpi_subarray({a[1]}, {a[2]}, {a[3]})")
+        m = re.match(r"allocate\s*\((.*)\)$", st)
+        if m:
+            outl = []
+            for ent in self.split_dims(m.group(1)):
+                em = re.match(r"([a-z_]\w*)\s*\((.*)\)$", ent.strip())
+                dd = ", ".join(self.ex(d) for d in self.split_dims(em.group(2)))
+                k = self.kind(em.group(1))
+                outl.append(f"{self.ref(em.group(1))} = FArr(({dd},), {'np.int64' if k == 'int' else 'np.float32'})")
+            return "; ".join(outl)
+        if st.startswith("deallocate"):
+            return "pass"
         if st.startswith("call mpi_"):
             return "pass"
         if st.startswith("call "):
@@ -739,7 +773,9 @@ class Sub:
                 for n, (k, dims) in self.local.items():
                     if n in self.args:
                         continue
-                    if dims is not None:
+                    if dims is not None and ":" in dims and not re.search(r"\w\s*:|:\s*\w", dims):
+                        emit(f"{self.pyname(n)} = None")                      # allocatable: created by `allocate`
+                    elif dims is not None:
                         dd = ", ".join(self.ex(d) for d in self.split_dims(dims))
                         emit(f"{self.pyname(n)} = FArr(({dd},), {'np.int64' if k == 'int' else 'np.float32'})")
                     elif k == "real":
@@ -828,8 +864,12 @@ class Globals:
         for k, v in kw.items():
             setattr(self, k, v)
 
-    def mpi_xchg(self, sendbuf, count, dest, sendtag, source, recvtag):
-        pay = as_payload(sendbuf, count)
-        if self.comm is None:
-            return pay                    # one rank: every neighbour is the rank itself
-        return self.comm.sendrecv(int(self.rank), pay, dest, sendtag, source, recvtag)
+    def mpi_xchg(self, sendbuf, count, dest, sendtag, source, recvtag, sendtype=None, recvtype=None):
+        pay = as_payload(sendbuf, count, sendtype)
+        if self.comm is not None:         # one rank: every neighbour is the rank itself
+            pay = self.comm.sendrecv(int(self.rank), pay, dest, sendtag, source, recvtag)
+        return Payload(pay.data, recvtype if isinstance(recvtype, Subarray) else None)
+
+    @staticmethod
+    def mpi_subarray(sizes, subsizes, starts):
+        return Subarray(sizes.flat, subsizes.flat, starts.flat)

@@ -719,7 +719,10 @@ LAP_CASES = [  # dim order nglob       sizes      periodic   laps highorder shoc
     (3, 2, (8, 8, 8), (1, 1, 1), (1, 1, 1), 3, 0, 0, 2),
     (2, 1, (16, 12, 1), (1, 1, 1), (1, 1, 1), 3, 0, 0, 4),
     (2, 2, (40, 8, 1), (1, 1, 1), (0, 1, 1), 3, 0, 1, 2),
-    (3, 3, (8, 6, 6), (1, 1, 1), (1, 1, 1), 2, 1, 0, 2)]
+    (3, 3, (8, 6, 6), (1, 1, 1), (1, 1, 1), 2, 1, 0, 2),
+    # the `filter2` build (3D only, tristanmainloop.F90:213-229): one rank (also run on the GPU) and 1x2x2
+    (3, 2, (8, 8, 8), (1, 1, 1), (1, 1, 1), 3, 0, 0, 2, 2),
+    (3, 1, (6, 12, 12), (1, 2, 2), (1, 1, 1), 2, 0, 0, 1, 2)]
 
 
 def gen_lap():
@@ -749,9 +752,15 @@ def gen_lap():
     noop = ("diagnostics", "inject_particles", "check_overflow", "enlarge_domain", "redist_x_domain", "redist_y_domain", "shift_domain",
             "redist_z_domain", "print_timers", "pause_simulation")
     names9 = ("ex", "ey", "ez", "bx", "by", "bz", "curx", "cury", "curz")
-    for ci, (dim, order, nglob, sizes, per, laps, highorder, shock, ppc) in enumerate(LAP_CASES):
+    otext = "\n".join(l for l in src("optimized_filters.F90").split("\n") if not l.strip().lower().startswith("call timer"))
+    f2names = ["apply_filter2_opt", "filter_x", "filter_y", "filter_z", "deep_copylayrx", "nonper_copylayrx"] + \
+              [f"deep_copy_layr{a}{v}" for a in "xyz" for v in "12"]
+    ga = ga | {"xghost", "yghost", "zghost"}
+    for ci, case in enumerate(LAP_CASES):
+        dim, order, nglob, sizes, per, laps, highorder, shock, ppc = case[:9]
+        fkind = case[9] if len(case) > 9 else 1
         flag, mover, dname = mov[order]
-        defines = {"MPI", flag} | ({"twoD"} if dim == 2 else set())
+        defines = {"MPI", flag} | ({"twoD"} if dim == 2 else set()) | ({"filter2"} if fkind == 2 else set())
         size0 = sizes[0] * sizes[1] * sizes[2]
         comm = R.Comm(size0, timeout=600.0)
         need = dict(where)
@@ -761,6 +770,11 @@ def gen_lap():
             del need["field_bc_user"], need["particle_bc_user"]
         subs = {nm: R.Sub(main_text if f == "main" else T_[f], nm, defines=defines, global_arrays=ga, global_ints=gi).compile()
                 for nm, f in need.items()}
+        if fkind == 2:
+            for nm in f2names:
+                subs[nm] = R.Sub(otext, nm, defines=defines, global_arrays=ga, global_ints=gi).compile()
+            subs["create_mpi_filter_datatypes"] = R.Sub(T_["fields"], "create_mpi_filter_datatypes", defines=defines, global_arrays=ga,
+                                                        global_ints=gi).compile()
         key = f"l{ci}"
         out[key + "_meta"] = np.array([dim, order, *per, *nglob], np.int32)
         n = tuple(a // s_ for a, s_ in zip(nglob, sizes))
@@ -768,7 +782,7 @@ def gen_lap():
         ncell = n[0] * n[1] * (n[2] if dim == 3 else 1)
         nsp = ppc * ncell
         maxhlf = 2 * nsp + 64
-        out[key + "_geom"] = np.array([*sizes, maxhlf, nsp, laps, highorder, shock], np.int32)
+        out[key + "_geom"] = np.array([*sizes, maxhlf, nsp, laps, highorder, shock, fkind], np.int32)
         gs, ps = [], []
         for rank in range(size0):
             rng = np.random.default_rng(1300 + 16 * ci + rank)
@@ -834,6 +848,12 @@ def gen_lap():
                 setattr(g, nm, (lambda f_, g_: (lambda *a: f_(g_, *a)))(f, g))
             for nm in noop:
                 setattr(g, nm, lambda *a: None)
+            if fkind == 2:                                          # allocate_fields, fields.F90:353, 363-365
+                nt = g.ntimes
+                g.mpi_order_fortran = 0
+                g.xghost, g.yghost, g.zghost = R.FArr((2 * nt, g.my, g.mz)), R.FArr((g.mx, 2 * nt, g.mz)), R.FArr((g.mx, g.my, 2 * nt))
+                g.create_mpi_filter_datatypes(ng // 2 + 1, g.mx - (ng // 2 + 1), ng // 2 + 1, g.my - (ng // 2 + 1), ngz // 2 + 1,
+                                              g.mz - (ngz // 2 + 1))
             if not shock:
                 g.field_bc_user = lambda: None
                 g.particle_bc_user = lambda: None
@@ -853,7 +873,60 @@ def gen_lap():
     np.savez_compressed(os.path.join(HERE, "ref_lap.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G13: filter2 over several ranks -- apply_filter2_opt (optimized_filters.F90:9-227) with its deep ghost exchange
+#      deep_copy_layr{x,y,z}{1,2} (:1387-1963) through the MPI derived datatypes the reference builds in
+#      create_MPI_filter_datatypes (fields.F90:1449-1600; MPI_Type_create_subarray is executed as "remember this box")
+# ------------------------------------------------------------------------------------------------------------
+F2_CASES = [(3, 2, (8, 12, 12), (1, 2, 2), (1, 1, 1), 3),
+            (3, 1, (8, 18, 6), (1, 3, 1), (0, 1, 1), 4),
+            (3, 3, (6, 8, 16), (1, 1, 2), (1, 0, 0), 2),
+            (3, 2, (9, 8, 7), (1, 1, 1), (1, 1, 1), 5)]
+
+
+def gen_filter2_mr():
+    out = {}
+    ftext = src("fields.F90")
+    otext = "\n".join(l for l in src("optimized_filters.F90").split("\n") if not l.strip().lower().startswith("call timer"))
+    caps = {a + b + "cap" for a in ("x", "y", "z", "xghost", "yghost", "zghost") for b in ("high", "low")}
+    ga = GARR | {"xghost", "yghost", "zghost", "mxl", "myl", "mzl"}
+    gi = GINTS | {"statsize", "mxcum", "mycum", "mzcum"}
+    onames = ["apply_filter2_opt", "filter_x", "filter_y", "filter_z", "deep_copylayrx", "nonper_copylayrx"] + \
+             [f"deep_copy_layr{a}{v}" for a in "xyz" for v in "12"]
+    for ci, (dim, order, nglob, sizes, per, ntimes) in enumerate(F2_CASES):
+        defines = {"MPI", "filter2"}
+        size0 = sizes[0] * sizes[1] * sizes[2]
+        comm = R.Comm(size0)
+        subs = {nm: R.Sub(otext, nm, defines=defines, global_arrays=ga, global_ints=gi).compile() for nm in onames}
+        subs["create_mpi_filter_datatypes"] = R.Sub(ftext, "create_mpi_filter_datatypes", defines=defines, global_arrays=ga, global_ints=gi).compile()
+        key = f"z{ci}"
+        out[key + "_meta"] = np.array([dim, order, *per, *nglob, ntimes], np.int32)
+        out[key + "_sizes"] = np.array(sizes, np.int32)
+        gs = []
+        for rank in range(size0):
+            n = tuple(a // s_ for a, s_ in zip(nglob, sizes))
+            g = field_globals(dim, order, n, per, np.random.default_rng(1400 + 16 * ci + rank))
+            rank_geometry(g, dim, order, nglob, sizes, rank)
+            g.comm, g.ntimes, g.debug, g.statsize = comm, ntimes, False, 5
+            g.mpi_comm_world = g.mpi_read = g.mpi_order_fortran = 0
+            for nm, f in subs.items():
+                setattr(g, nm, (lambda f_, g_: (lambda *a: f_(g_, *a)))(f, g))
+            # allocate_fields, fields.F90:353, 363-365
+            g.xghost, g.yghost, g.zghost = R.FArr((2 * ntimes, g.my, g.mz)), R.FArr((g.mx, 2 * ntimes, g.mz)), R.FArr((g.mx, g.my, 2 * ntimes))
+            ng, ngz = g.nghost, g.nghostz
+            g.create_mpi_filter_datatypes(ng // 2 + 1, g.mx - (ng // 2 + 1), ng // 2 + 1, g.my - (ng // 2 + 1), ngz // 2 + 1, g.mz - (ngz // 2 + 1))
+            for c, nm in enumerate(("curx", "cury", "curz")):
+                out[f"{key}_r{rank}_in{c}"] = c_order(getattr(g, nm))
+            gs.append(g)
+        R.run_ranks([(lambda g=g: g.apply_filter2_opt()) for g in gs])
+        for rank, g in enumerate(gs):
+            for c, nm in enumerate(("curx", "cury", "curz")):
+                out[f"{key}_r{rank}_out{c}"] = c_order(getattr(g, nm))
+        print("filter2_mr", key, dim, order, nglob, sizes, per, ntimes)
+    np.savez_compressed(os.path.join(HERE, "ref_filter2_mr.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr"]
     for w in which:
         globals()["gen_" + w]()

@@ -141,11 +141,11 @@ def _golden_worker(rank, world, port, case, q):
         z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_lap.npz"))
         key = f"l{case}"
         dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
-        sx, sy, sz, maxhlf, nsp, laps, highorder, shock = (int(v) for v in z[key + "_geom"])
+        sx, sy, sz, maxhlf, nsp, laps, highorder, shock, fkind = (int(v) for v in z[key + "_geom"])
         assert sx * sy * sz == world
         par = z[key + "_par"]
         P = tg.make_params(dim=dim, order=order, mx0=nx, my0=ny, mz0=nz, sizex=sx, sizey=sy, sizez=sz, rank=rank, periodic=(px, py, pz),
-                           maxptl=2 * maxhlf, device=rank, ntimes=2, filter_kind=1, highorder=highorder)
+                           maxptl=2 * maxhlf, device=rank, ntimes=2, filter_kind=fkind, highorder=highorder)
         P.qi, P.qe, P.qmi, P.qme = (float(v) for v in par[5:9])
         ctx = tg.Context(P)
         ctx.comm_init_torch()
@@ -217,6 +217,6 @@ def test_two_gpus_against_the_reference_mainloop(tg, case):
     _run_golden(2, case)
 
 
-@pytest.mark.parametrize("case", [0, 1], ids=["2d-2x2-10laps-reorder", "3d-o2-1x2x2"])
+@pytest.mark.parametrize("case", [0, 1, 10], ids=["2d-2x2-10laps-reorder", "3d-o2-1x2x2", "3d-o1-1x2x2-filter2"])
 def test_four_gpus_against_the_reference_mainloop(tg, case):
     _run_golden(4, case)

@@ -256,7 +256,7 @@ def test_deposit_particles_against_the_reference_source(tg, case, fused):
     ctx.close()
 
 
-@pytest.mark.parametrize("case", [2, 5, 6, 7, 8])
+@pytest.mark.parametrize("case", [2, 5, 6, 7, 8, 9])
 def test_whole_laps_against_the_reference_mainloop(tg, case):
     """tgpu_step against the reference's `mainloop` run from its own text (tests/golden/ref_lap.npz, the one-rank boxes):
     all-open 3D zigzag box (radiation + edge fixes + exits), periodic 3D order 2, periodic 2D order 1, the 2D shock problem
@@ -265,11 +265,11 @@ def test_whole_laps_against_the_reference_mainloop(tg, case):
     z = load("ref_lap.npz")
     key = f"l{case}"
     dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
-    sx, sy, sz, maxhlf, nsp, laps, highorder, shock = (int(v) for v in z[key + "_geom"])
+    sx, sy, sz, maxhlf, nsp, laps, highorder, shock, fkind = (int(v) for v in z[key + "_geom"])
     assert (sx, sy, sz) == (1, 1, 1)
     par = z[key + "_par"]
     P = tg.make_params(dim=dim, order=order, mx0=nx, my0=ny, mz0=nz, periodic=(px, py, pz), maxptl=2 * maxhlf, device=0, ntimes=2,
-                       filter_kind=1, highorder=highorder)
+                       filter_kind=fkind, highorder=highorder)
     P.qi, P.qe, P.qmi, P.qme = (float(v) for v in par[5:9])
     ctx = tg.Context(P)
     assert ctx.maxhlf == maxhlf

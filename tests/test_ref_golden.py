@@ -326,9 +326,9 @@ def test_multirank_particle_migration_matches_the_reference_source(case):
 def lap_world(z, case):
     key = f"l{case}"
     dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
-    sx, sy, sz, maxhlf, nsp, laps, highorder, shock = (int(v) for v in z[key + "_geom"])
+    sx, sy, sz, maxhlf, nsp, laps, highorder, shock, fkind = (int(v) for v in z[key + "_geom"])
     par = z[key + "_par"]
-    P = O.make_params(dim=dim, order=order, mx0=nx, my0=ny, mz0=nz, sizex=sx, sizey=sy, sizez=sz, ntimes=2, filter_kind=1,
+    P = O.make_params(dim=dim, order=order, mx0=nx, my0=ny, mz0=nz, sizex=sx, sizey=sy, sizez=sz, ntimes=2, filter_kind=fkind,
                       periodic=(px, py, pz), maxptl=2 * maxhlf, highorder=highorder, wall_i2=0)
     P.qi, P.qe, P.qmi, P.qme = (float(v) for v in par[5:9])
     w = O.World(P)
@@ -343,7 +343,7 @@ def lap_world(z, case):
     return key, w, laps, shock, par, maxhlf
 
 
-@pytest.mark.parametrize("case", range(9))
+@pytest.mark.parametrize("case", range(11))
 def test_whole_laps_match_the_reference_mainloop(case):
     """WHOLE LAPS: the reference's `mainloop` (tristanmainloop.F90:60-330) executed from its own text on every rank, calling
     the reference's own text for every routine on the path (solver, movers, deposit, migration, ghost refresh, radiation,
@@ -365,3 +365,24 @@ def test_whole_laps_match_the_reference_mainloop(case):
         pout, p = z[f"{key}_r{rk}_pout"], r.particles()
         assert np.array_equal(p[:ions], pout[:ions]), rk
         assert np.array_equal(p[maxhlf:maxhlf + lecs], pout[maxhlf:maxhlf + lecs]), rk
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_multirank_filter2_matches_the_reference_source(case):
+    """SEVERAL RANKS: apply_filter2_opt (optimized_filters.F90:9-227) with its ntimes-deep ghost exchange deep_copy_layr*
+    (:1387-1963) through the MPI derived datatypes of create_MPI_filter_datatypes (fields.F90:1449-1600), every rank running
+    the reference's text; 1x2x2, 1x3x1 with open x, 1x1x2 with open y and z, and one rank: BIT-EXACT, whole arrays"""
+    z = load("ref_filter2_mr.npz")
+    key = f"z{case}"
+    dim, order, px, py, pz, nx, ny, nz, ntimes = (int(v) for v in z[key + "_meta"])
+    sizes = tuple(int(v) for v in z[key + "_sizes"])
+    w = T.oracle_world(dim=dim, order=order, n=(nx, ny, nz), sizes=sizes, ppc=0.0, init="none", seed_fields=0, periodic=(px, py, pz),
+                       ntimes=ntimes, filter_kind=2)
+    for rk, r in enumerate(w.ranks):
+        for c in range(3):
+            r.arr(6 + c)[...] = z[f"{key}_r{rk}_in{c}"]
+    w.phase(O.PH_FILTER)
+    for rk, r in enumerate(w.ranks):
+        for c in range(3):
+            ref = z[f"{key}_r{rk}_out{c}"]
+            assert np.array_equal(r.arr(6 + c), ref), (rk, O.ARR_NAMES[6 + c], float(np.abs(r.arr(6 + c) - ref).max()))
