@@ -138,6 +138,17 @@ class FArr:
     def __rmul__(self, o): return self._bin(o, np.multiply, True)
     def __truediv__(self, o): return self._bin(o, np.divide)
     def __neg__(self): return self._bin(F(-1), np.multiply)
+    def __ne__(self, o): return self.nd() != (o.nd() if isinstance(o, FArr) else o)      # masks of WHERE constructs
+    def __eq__(self, o): return self.nd() == (o.nd() if isinstance(o, FArr) else o)
+    def __gt__(self, o): return self.nd() > (o.nd() if isinstance(o, FArr) else o)
+    def __lt__(self, o): return self.nd() < (o.nd() if isinstance(o, FArr) else o)
+    __hash__ = None
+
+    def where_set(self, mask, val):
+        """a = val inside WHERE (mask)"""
+        with np.errstate(all="ignore"):
+            v = val.nd() if isinstance(val, FArr) else val
+            self.nd()[mask] = v[mask] if isinstance(v, np.ndarray) else v
 
 
 class Payload:
@@ -403,7 +414,7 @@ def extract_subroutine(text, name):
 # ------------------------------------------------------------------------------------------------------------------
 # expression translation (recursive descent over the Fortran expression grammar)
 # ------------------------------------------------------------------------------------------------------------------
-TOK = re.compile(r"\s*(\d+\.\d*(?:[ed][+-]?\d+)?|\.\d+(?:[ed][+-]?\d+)?|\d+[ed][+-]?\d+|\d+|\.[a-z]+\.|[a-z_]\w*|\*\*|==|/=|<=|>=|[-+*/(),:<>%=])")
+TOK = re.compile(r"\s*('[^']*'|\d+\.\d*(?:[ed][+-]?\d+)?|\.\d+(?:[ed][+-]?\d+)?|\d+[ed][+-]?\d+|\d+|\.[a-z]+\.|[a-z_]\w*|\*\*|==|/=|<=|>=|[-+*/(),:<>%=])")
 
 
 def tokenize(s):
@@ -506,6 +517,8 @@ class Expr:
             e = self.p_or()
             self.expect(")")
             r = f"({e})"
+        elif tok.startswith("'"):
+            r = repr(tok[1:-1])
         elif tok == ".true.":
             r = "True"
         elif tok == ".false.":
@@ -707,6 +720,10 @@ class Sub:
             return f"return {self.pyname(self.name)}" if getattr(self, "is_function", False) else "return"
         if st in ("continue",):
             return "pass"
+        if st == "cycle":
+            return "continue"
+        if st == "exit":
+            return "break"
         if st.startswith("print") or st.startswith("write") or st.startswith("stop"):
             return "pass"
         m = re.match(r"go\s*to\s+(\d+)$", st)
@@ -763,7 +780,8 @@ class Sub:
         for st in self.stmts[1:]:
             if re.match(r"end\s*(subroutine|function)\b", st):
                 break
-            if st.startswith("implicit") or st.startswith("use ") or st.startswith("intent") or st.startswith("external"):
+            if st.startswith("implicit") or st.startswith("use ") or st.startswith("intent") or st.startswith("external") \
+                    or st.startswith("character"):
                 continue
             if self.declare(st):
                 continue
@@ -794,6 +812,28 @@ class Sub:
                 ind -= 1; emit("else:"); ind += 1; continue
             if st in ("endif", "end if"):
                 emit("pass"); ind -= 1; continue
+            m = re.match(r"select\s*case\s*\((.*)\)$", st)
+            if m:
+                emit(f"_sel = {self.ex(m.group(1))}"); emit("if False:"); ind += 1; continue
+            m = re.match(r"case\s*\((.*)\)$", st)
+            if m:
+                emit("pass"); ind -= 1; emit(f"elif _sel in ({', '.join(self.ex(v) for v in self.split_dims(m.group(1)))},):"); ind += 1; continue
+            if st == "case default":
+                emit("pass"); ind -= 1; emit("else:"); ind += 1; continue
+            if st in ("end select", "endselect"):
+                emit("pass"); ind -= 1; continue
+            m = re.match(r"where\s*\((.*)\)$", st)
+            if m:
+                emit(f"_w = {self.ex(m.group(1))}"); self.in_where = True; continue
+            if st == "elsewhere":
+                emit("_w = ~_w"); continue
+            if st in ("endwhere", "end where"):
+                self.in_where = False; continue
+            if getattr(self, "in_where", False):
+                lhs, rhs = self.split_assign(st)
+                with_err = f"{self.ref(lhs.strip())}.where_set(_w, {self.ex(rhs)})"
+                emit("with np.errstate(all='ignore'):"); ind += 1; emit(with_err); ind -= 1
+                continue
             m = re.match(r"do\s+while\s*\((.*)\)$", st)
             if m:
                 emit(f"while {self.ex(m.group(1))}:"); ind += 1; loops.append((None, None)); continue

@@ -926,7 +926,70 @@ def gen_filter2_mr():
     np.savez_compressed(os.path.join(HERE, "ref_filter2_mr.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G14: output-side moments -- meanq_fld_cur(totname) (output.F90:5229-5486): box deposit of half-width idx = idy = idz = 2
+#      (idz = 0 in 2D), exchange_current, normalisation by the clipped box volume, ratio to the weight; one and several ranks
+# ------------------------------------------------------------------------------------------------------------
+MEANQ_NAMES = ("tdens", "idens", "hdens", "ldens", "btden", "tbetx", "ebety", "ibetz", "tmomx", "imomy", "eener", "iener", "eetx2", "iety2")
+MEANQ_CASES = [(2, 1, (12, 10, 1), (1, 1, 1)), (3, 2, (8, 8, 6), (1, 1, 1)), (2, 2, (16, 12, 1), (2, 2, 1)), (3, 1, (6, 12, 12), (1, 2, 2))]
+
+
+def gen_meanq():
+    out = {}
+    fb, otext = src("fieldboundaries.F90"), src("output.F90")
+    out["names"] = np.array(MEANQ_NAMES)
+    for ci, (dim, order, nglob, sizes) in enumerate(MEANQ_CASES):
+        defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+        size0 = sizes[0] * sizes[1] * sizes[2]
+        comm = R.Comm(size0)
+        ga = GARR | {"bufferin1x", "bufferin2x", "bufferin1y", "bufferin2y", "bufferin1", "bufferin2", "mxl", "myl", "mzl"}
+        gi = GINTS | {"statsize", "mxcum", "mycum", "mzcum", "maxptl", "idx", "idy", "idz"}
+        exc = R.Sub(fb, "exchange_current", defines=defines, global_arrays=ga, global_ints=gi).compile()
+        mq = R.Sub(otext, "meanq_fld_cur", defines=defines, global_arrays=ga, global_ints=gi).compile()
+        key = f"q{ci}"
+        n = tuple(a // s_ for a, s_ in zip(nglob, sizes))
+        ncell = n[0] * n[1] * (n[2] if dim == 3 else 1)
+        nsp, maxhlf = 3 * ncell, 3 * ncell + 32
+        out[key + "_meta"] = np.array([dim, order, 1, 1, 1, *nglob], np.int32)
+        out[key + "_geom"] = np.array([*sizes, maxhlf, nsp], np.int32)
+        gs = []
+        for rank in range(size0):
+            rng = np.random.default_rng(1500 + 16 * ci + rank)
+            g = field_globals(dim, order, n, (1, 1, 1), rng)
+            rank_geometry(g, dim, order, nglob, sizes, rank)
+            ng, ngz, mx, my, mz = grid(dim, order, n)
+            g.comm, g.debug, g.statsize, g.mpi_comm_world, g.mpi_read = comm, False, 5, 0, 0
+            g.idx, g.idy, g.idz = 2, 2, (2 if dim == 3 else 0)                 # output.F90:189-195
+            g.bufferin1x, g.bufferin2x = R.FArr((ng // 2 + 1, g.my, g.mz)), R.FArr((ng // 2, g.my, g.mz))
+            g.bufferin1y, g.bufferin2y = R.FArr((g.mx, ng // 2 + 1, g.mz)), R.FArr((g.mx, ng // 2, g.mz))
+            g.bufferin1, g.bufferin2 = R.FArr((g.mx, g.my, g.nghostz // 2 + 1)), R.FArr((g.mx, g.my, g.nghostz // 2))
+            p = np.zeros(2 * maxhlf, PDT)
+            lo = np.array([ng // 2 + 1, ng // 2 + 1, ngz // 2 + 1], F)
+            ext = np.array([n[0], n[1], n[2] if dim == 3 else 1], F)
+            for s0 in (0, maxhlf):
+                sl = slice(s0, s0 + nsp)
+                pos = lo[:, None] + rng.random((3, nsp)) * ext[:, None]
+                p["x"][sl], p["y"][sl], p["z"][sl] = pos.astype(F)
+                for k in "uvw":
+                    p[k][sl] = (rng.standard_normal(nsp) * 0.7).astype(F)
+                p["ch"][sl] = (0.5 + rng.random(nsp)).astype(F)
+                p["ind"][sl] = np.arange(1, nsp + 1) * np.where(rng.random(nsp) < 0.3, -1, 1)
+                p["proc"][sl] = rank
+                p["splitlev"][sl] = 1
+            g.p = R.RecArr(p)
+            g.ions, g.lecs, g.maxhlf, g.maxptl = nsp, nsp, maxhlf, 2 * maxhlf
+            g.exchange_current = (lambda g_: (lambda: exc(g_)))(g)
+            out[f"{key}_r{rank}_pin"] = p.copy()
+            gs.append(g)
+        for ni, name in enumerate(MEANQ_NAMES):
+            R.run_ranks([(lambda g=g: mq(g, name)) for g in gs])
+            for rank, g in enumerate(gs):
+                out[f"{key}_r{rank}_{name}"] = c_order(g.curx)
+        print("meanq", key, dim, order, nglob, sizes, "max tdens", float(out[f"{key}_r0_tdens"].max()))
+    np.savez_compressed(os.path.join(HERE, "ref_meanq.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq"]
     for w in which:
         globals()["gen_" + w]()

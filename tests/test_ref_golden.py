@@ -386,3 +386,25 @@ def test_multirank_filter2_matches_the_reference_source(case):
         for c in range(3):
             ref = z[f"{key}_r{rk}_out{c}"]
             assert np.array_equal(r.arr(6 + c), ref), (rk, O.ARR_NAMES[6 + c], float(np.abs(r.arr(6 + c) - ref).max()))
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_meanq_fld_cur_matches_the_reference_source(case):
+    """meanq_fld_cur(totname) (output.F90:5229-5486) for 14 of its quantities (densities, 3-velocities, momenta, energies,
+    velocity squares; species / beam selections): box deposit, the reference's own exchange_current between ranks, volume
+    normalisation, ratio to the weight -- one rank and 2x2 / 1x2x2: BIT-EXACT on every rank"""
+    z = load("ref_meanq.npz")
+    key = f"q{case}"
+    dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
+    sx, sy, sz, maxhlf, nsp = (int(v) for v in z[key + "_geom"])
+    P = O.make_params(dim=dim, order=order, mx0=nx, my0=ny, mz0=nz, sizex=sx, sizey=sy, sizez=sz, periodic=(px, py, pz), maxptl=2 * maxhlf)
+    w = O.World(P)
+    for rk, r in enumerate(w.ranks):
+        assert r.maxhlf == maxhlf
+        r.particles()[:] = z[f"{key}_r{rk}_pin"]
+        r.set_counts(nsp, nsp)
+    for name in z["names"]:
+        w.meanq_fld_cur(str(name))
+        for rk, r in enumerate(w.ranks):
+            ref = z[f"{key}_r{rk}_{name}"]
+            assert np.array_equal(r.arr(6), ref), (str(name), rk, float(np.abs(r.arr(6) - ref).max()), float(np.abs(ref).max()))
