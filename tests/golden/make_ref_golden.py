@@ -25,6 +25,7 @@ import f90run as R  # noqa: E402
 
 F = np.float32
 REF = os.environ.get("TRISTAN_REFERENCE", "/root/reference")
+OUT = os.environ.get("TRISTAN_GOLDEN_OUT", HERE)          # where the .npz files go (the tests re-generate into a tmp dir)
 
 
 def src(name):
@@ -91,7 +92,7 @@ def gen_deposit():
                 out[f"{key}_{nm}"] = getattr(g, nm).nd().transpose(2, 1, 0).copy()        # C order (mz, my, mx)
             out[f"{key}_n"] = np.array(n, np.int32)
             print("deposit", key, "sum|curx| =", float(np.abs(out[f"{key}_curx"]).sum()))
-    np.savez_compressed(os.path.join(HERE, "ref_deposit.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_deposit.npz"), **out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -132,7 +133,7 @@ def gen_fields():
         for a, nm in enumerate(("ex", "ey", "ez", "bx", "by", "bz")):
             out[f"{key}_out{a}"] = c_order(getattr(g, nm))
         print("fields", key, dim, order, per)
-    np.savez_compressed(os.path.join(HERE, "ref_fields.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_fields.npz"), **out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -181,7 +182,7 @@ def gen_mover():
             sub(g, 1, npart, qm)
             out[key + "_pout"] = p.copy()
             print("mover", key, "mean |dx| =", float(np.abs(out[key + "_pout"]["x"] - out[key + "_pin"]["x"]).mean()))
-    np.savez_compressed(os.path.join(HERE, "ref_mover.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_mover.npz"), **out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -254,7 +255,7 @@ def gen_filter():
             fn(g, *[vals[a] for a in args])
             out[f"{key}_after{axis}"] = c_order(g.curx)
         print("filter2", key, dim, order, ntimes)
-    np.savez_compressed(os.path.join(HERE, "ref_filter.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_filter.npz"), **out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -291,7 +292,7 @@ def gen_radiation():
             for a, fn in enumerate(("ex", "ey", "ez", "bx", "by", "bz")):
                 out[f"{key}_s{si}_{a}"] = c_order(getattr(g, fn))
         print("radiation", key, dim, order, per)
-    np.savez_compressed(os.path.join(HERE, "ref_radiation.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_radiation.npz"), **out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -332,7 +333,7 @@ def gen_halo():
         for a, nm in enumerate(names):
             out[f"{key}_out{a}"] = c_order(getattr(g, nm))
         print("halo", key, dim, order)
-    np.savez_compressed(os.path.join(HERE, "ref_halo.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_halo.npz"), **out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -361,7 +362,7 @@ def gen_fields42():
         for a, nm in enumerate(("ex", "ey", "ez", "bx", "by", "bz")):
             out[f"{key}_out{a}"] = c_order(getattr(g, nm))
         print("fields42", key, dim, order, per, xinj)
-    np.savez_compressed(os.path.join(HERE, "ref_fields42.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_fields42.npz"), **out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -426,7 +427,7 @@ def gen_shock():
         out[key + "_pout"] = p.copy()
         moved = int((out[key + "_pin"]["u"] != p["u"]).sum())
         print("shock", key, dim, order, "reflected", moved, "field cells changed", int(sum((out[f"{key}_in{a}"] != out[f"{key}_out{a}"]).sum() for a in range(6))))
-    np.savez_compressed(os.path.join(HERE, "ref_shock.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_shock.npz"), **out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -530,7 +531,7 @@ def gen_depositp():
         for a, nm in enumerate(("curx", "cury", "curz")):
             out[f"{key}_cur{a}"] = c_order(getattr(g, nm))
         print("deposit_particles", key, dim, order, sizes, rank, per, "left:", int(g.ions), int(g.lecs), "boxes:", lens)
-    np.savez_compressed(os.path.join(HERE, "ref_depositp.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_depositp.npz"), **out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -605,7 +606,7 @@ def gen_halo_mr():
             for a, nm in enumerate(names):
                 out[f"{key}_r{rank}_out{a}"] = c_order(getattr(g, nm))
         print("halo_mr", key, dim, order, nglob, sizes, per)
-    np.savez_compressed(os.path.join(HERE, "ref_halo_mr.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_halo_mr.npz"), **out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -701,7 +702,7 @@ def gen_migrate_mr():
                 out[f"{key}_r{rank}_cur{a}"] = c_order(getattr(g, nm))
             tot += g.ions + g.lecs
         print("migrate_mr", key, dim, order, nglob, sizes, per, "particles", 2 * nsp * size0, "->", tot, [int(g.ions) for g in gs])
-    np.savez_compressed(os.path.join(HERE, "ref_migrate_mr.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_migrate_mr.npz"), **out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -870,7 +871,7 @@ def gen_lap():
             out[f"{key}_r{rank}_counts"] = np.array([g.ions, g.lecs], np.int32)
         out[key + "_par"] = np.array([gs[0].leftwall, gs[0].binit, gs[0].btheta, gs[0].bphi, gs[0].beta, gs[0].qi, gs[0].qe, gs[0].qmi, gs[0].qme], F)
         print("lap", key, dim, order, nglob, sizes, per, "laps", laps, "counts", [(int(g.ions), int(g.lecs)) for g in gs], "overlong msgs", len(R.OVERLONG))
-    np.savez_compressed(os.path.join(HERE, "ref_lap.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_lap.npz"), **out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -923,7 +924,7 @@ def gen_filter2_mr():
             for c, nm in enumerate(("curx", "cury", "curz")):
                 out[f"{key}_r{rank}_out{c}"] = c_order(getattr(g, nm))
         print("filter2_mr", key, dim, order, nglob, sizes, per, ntimes)
-    np.savez_compressed(os.path.join(HERE, "ref_filter2_mr.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_filter2_mr.npz"), **out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -986,7 +987,7 @@ def gen_meanq():
             for rank, g in enumerate(gs):
                 out[f"{key}_r{rank}_{name}"] = c_order(g.curx)
         print("meanq", key, dim, order, nglob, sizes, "max tdens", float(out[f"{key}_r0_tdens"].max()))
-    np.savez_compressed(os.path.join(HERE, "ref_meanq.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "ref_meanq.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,280 @@
+"""The Fortran-subset interpreter (tests/golden/f90run.py) on hand-written snippets whose results follow from the Fortran
+standard alone.  The interpreter is what pins the oracle to the reference's source, so its own semantics
+are checked here independently of any PIC code: integer division, fp32 rounding of every operation, DO-variable exit
+values, column-major storage and the out-of-range first index, sections, the two goto idioms, functions, select case,
+where, MPI_SendRecv as an element-count transfer (also between threads) and MPI subarray datatypes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import f90run as R  # noqa: E402
+
+F = np.float32
+
+
+def run(text, name, g=None, args=(), arrays=(), ints=(), defines=()):
+    g = g or R.Globals()
+    f = R.Sub(text, name, defines=set(defines), global_arrays=set(arrays), global_ints=set(ints)).compile()
+    return f(g, *args), g
+
+
+def test_integer_division_truncates_and_mixed_arithmetic_promotes():
+    src = """
+    subroutine t()
+      integer :: i, j
+      real :: a
+      i = 7/2
+      j = -7/2
+      a = 7/2 + 7/2.
+      r1 = i
+      r2 = j
+      r3 = a
+    end subroutine t
+    """
+    _, g = run(src, "t")
+    assert (g.r1, g.r2) == (3, -3)
+    assert g.r3 == F(6.5) and isinstance(g.r3, np.float32)
+
+
+def test_every_operation_rounds_to_fp32():
+    src = """
+    subroutine t()
+      real :: a, b, c
+      a = 16777216.
+      b = 1.
+      c = (a + b) - a
+      r1 = c
+      c = 0.1*3.
+      r2 = c
+    end subroutine t
+    """
+    _, g = run(src, "t")
+    assert g.r1 == F(0.0)                                   # 2^24 + 1 is not representable: the sum rounds back to 2^24
+    assert g.r2 == F(F(0.1) * F(3.0)) and g.r2 != np.float64(0.1) * 3
+
+
+def test_do_variable_after_the_loop_and_zero_trip_loops():
+    src = """
+    subroutine t()
+      integer :: i, n
+      n = 0
+      do i = 2, 9, 3
+        n = n + i
+      enddo
+      r1 = i
+      r2 = n
+      do i = 5, 4
+        n = -1
+      enddo
+      r3 = i
+      r4 = n
+    end subroutine t
+    """
+    _, g = run(src, "t")
+    assert (g.r1, g.r2, g.r3, g.r4) == (11, 2 + 5 + 8, 5, 15)
+
+
+def test_column_major_storage_sections_and_the_flat_first_index():
+    src = """
+    subroutine t()
+      integer :: i, j
+      do j = 1, 3
+        do i = 1, 4
+          a(i, j) = 10*j + i
+        enddo
+      enddo
+      r1 = a(6, 1)
+      b(1:2, 1) = a(3:4, 2)
+      b(:, 2) = a(2, :)
+      r2 = sum(a(2:3, 3))
+    end subroutine t
+    """
+    g = R.Globals(a=R.FArr((4, 3)), b=R.FArr((3, 2)))
+    run(src, "t", g, arrays=("a", "b"))
+    assert g.r1 == F(22)                                    # a(6,1) is the 6th element in storage order = a(2,2)
+    assert list(g.a.flat[:5]) == [11, 12, 13, 14, 21]
+    assert g.b.nd().tolist() == [[23, 12], [24, 22], [0, 32]]
+    assert g.r2 == F(32 + 33)
+
+
+def test_forward_goto_skips_and_goto_to_loop_end_cycles():
+    src = """
+    subroutine t()
+      integer :: i, n
+      n = 0
+      do i = 1, 6
+        if (modulo(i, 2) .eq. 0) go to 58
+        n = n + i
+ 58     continue
+      enddo
+      r1 = n
+      goto 70
+      n = -100
+ 70   continue
+      r2 = n
+    end subroutine t
+    """
+    _, g = run(src, "t")
+    assert (g.r1, g.r2) == (1 + 3 + 5, 9)
+
+
+def test_functions_sign_modulo_and_aint():
+    src = """
+    integer function wrapidx(i)
+      integer :: i
+      wrapidx = modulo(i - 1, n0) + 1
+    end function wrapidx
+
+    subroutine t()
+      r1 = wrapidx(0)
+      r2 = wrapidx(9)
+      r3 = sign(2.5, -0.1) + sign(2.5, 3.)
+      r4 = mod(-7, 3)
+      r5 = modulo(-7, 3)
+      r6 = aint(-2.7)
+      r7 = int(2.999)
+    end subroutine t
+    """
+    g = R.Globals(n0=4)
+    f = R.Sub(src, "wrapidx", global_ints={"n0"}).compile()
+    g.wrapidx = lambda i: f(g, i)
+    run(src, "t", g, ints=("n0",))
+    assert (g.r1, g.r2, g.r3, g.r4, g.r5, g.r6, g.r7) == (4, 1, F(0.0), -1, 2, F(-2.0), 2)
+
+
+def test_cpp_conditionals_select_the_build():
+    src = """
+    subroutine t()
+#ifdef twoD
+      r1 = 2
+#else
+      r1 = 3
+#endif
+#ifndef MPI
+      r1 = -1
+#endif
+    end subroutine t
+    """
+    assert run(src, "t", defines=("MPI", "twoD"))[1].r1 == 2
+    assert run(src, "t", defines=("MPI",))[1].r1 == 3
+
+
+def test_select_case_where_cycle_and_exit():
+    src = """
+    subroutine t(name)
+      character (len=5) name
+      integer :: i, n
+      n = 0
+      select case(name)
+      case('tdens')
+        n = 1
+      case('idens')
+        n = 2
+      end select
+      r1 = n
+      do i = 1, 10
+        if (i .eq. 2) cycle
+        if (i .gt. 4) exit
+        n = n + i
+      enddo
+      r2 = n
+      where (w .ne. 0.)
+        a = a/w
+      elsewhere
+        a = 0.
+      endwhere
+    end subroutine t
+    """
+    g = R.Globals(a=R.FArr((4,)), w=R.FArr((4,)))
+    g.a.flat[:] = [2, 3, 4, 5]
+    g.w.flat[:] = [2, 0, 8, 0]
+    run(src, "t", g, args=("idens",), arrays=("a", "w"))
+    assert (g.r1, g.r2) == (2, 2 + 1 + 3 + 4)
+    assert list(g.a.flat) == [1, 0, 0.5, 0]
+
+
+SENDRECV = """
+subroutine swap()
+  integer :: plusrank, minusrank, count
+  plusrank = modulo(rank + 1, size0)
+  minusrank = modulo(rank - 1, size0)
+  count = 3
+  call MPI_SendRecv(a(2, :), count, mpi_read, plusrank, 100, &
+                    b(1, :), count, mpi_read, minusrank, 100, comm, status, ierr)
+end subroutine swap
+"""
+
+
+def test_mpi_sendrecv_to_oneself_moves_count_elements_in_storage_order():
+    g = R.Globals(a=R.FArr((2, 4)), b=R.FArr((2, 4)), rank=0, size0=1, comm=None, mpi_read=0, status=0, ierr=0)
+    g.a.flat[:] = np.arange(8)
+    g.b.flat[:] = -1
+    f = R.Sub(SENDRECV, "swap", global_arrays={"a", "b"}, global_ints={"rank", "size0"}).compile()
+    f(g)
+    assert g.b.nd()[0].tolist() == [1, 3, 5, -1]            # 3 elements of a(2,:) land in the first 3 of b(1,:)
+    assert g.b.nd()[1].tolist() == [-1, -1, -1, -1]
+
+
+def test_mpi_sendrecv_between_three_ranks_is_a_ring_shift():
+    comm = R.Comm(3)
+    gs = []
+    f = R.Sub(SENDRECV, "swap", global_arrays={"a", "b"}, global_ints={"rank", "size0"}).compile()
+    for rk in range(3):
+        g = R.Globals(a=R.FArr((2, 4)), b=R.FArr((2, 4)), rank=rk, size0=3, mpi_read=0, status=0, ierr=0)
+        g.comm = comm
+        g.a.flat[:] = 100 * rk + np.arange(8)
+        gs.append(g)
+    R.run_ranks([(lambda g=g: f(g)) for g in gs])
+    for rk in range(3):
+        src_rank = (rk - 1) % 3
+        assert gs[rk].b.nd()[0].tolist() == [100 * src_rank + 1, 100 * src_rank + 3, 100 * src_rank + 5, 0]
+
+
+def test_mpi_subarray_datatypes_describe_boxes():
+    src = """
+    subroutine mk()
+      integer, allocatable, dimension(:) :: sizes, subsizes, starts
+      allocate(sizes(2), subsizes(2), starts(2))
+      sizes(1) = 4
+      sizes(2) = 3
+      subsizes(1) = 2
+      subsizes(2) = 2
+      starts(1) = 1
+      starts(2) = 0
+      call MPI_Type_create_subarray(2, sizes, subsizes, starts, MPI_ORDER_FORTRAN, mpi_read, lowcap, ierr)
+      starts(1) = 2
+      starts(2) = 1
+      call MPI_Type_create_subarray(2, sizes, subsizes, starts, MPI_ORDER_FORTRAN, mpi_read, highcap, ierr)
+    end subroutine mk
+
+    subroutine xchg()
+      call MPI_SendRecv(a, 1, lowcap, 0, 7, b, 1, highcap, 0, 7, comm, status, ierr)
+    end subroutine xchg
+    """
+    g = R.Globals(a=R.FArr((4, 3)), b=R.FArr((4, 3)), rank=0, mpi_read=0, mpi_order_fortran=0, status=0, ierr=0)
+    g.a.nd()[...] = np.arange(12).reshape(3, 4).T              # a(i,j) = (i-1) + 4*(j-1)
+    R.Sub(src, "mk", global_arrays={"a", "b"}).compile()(g)
+    R.Sub(src, "xchg", global_arrays={"a", "b"}).compile()(g)
+    want = np.zeros((4, 3), F)
+    want[2:4, 1:3] = g.a.nd()[1:3, 0:2]
+    assert np.array_equal(g.b.nd(), want)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("TRISTAN_REFERENCE", "/root/reference")), reason="reference checkout not present")
+def test_committed_goldens_are_what_the_generator_makes(tmp_path, monkeypatch):
+    """in the build container: re-run two fast generator groups and compare with the committed files"""
+    import importlib
+    monkeypatch.setenv("TRISTAN_GOLDEN_OUT", str(tmp_path))
+    gen = importlib.import_module("make_ref_golden")
+    gen = importlib.reload(gen)
+    gen.gen_deposit()
+    gen.gen_shock()
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name in ("ref_deposit.npz", "ref_shock.npz"):
+        a, b = np.load(os.path.join(here, name)), np.load(os.path.join(str(tmp_path), name))
+        assert set(a.files) == set(b.files)
+        for k in a.files:
+            assert np.array_equal(a[k], b[k]), (name, k)
