@@ -13,7 +13,11 @@ Subset: subroutines and functions (integer / real result), scalar / array assign
 expressions, array sections, do (local or module loop variable) / do while / if-elseif-else, one-line if, the two goto idioms
 of the path (an unconditional forward skip to `N continue`; `go to N` where `N continue` closes the loop = cycle), call (to
 other translated routines or to Python stand-ins), derived-type components (p(n)%x) and element assignment (tempp(j) = p(n)),
-integer arrays, the intrinsics aint int real min max abs sqrt sum cshift mod modulo sign cos sin nint floor.
+integer arrays, real(dprec) / double precision entities and d-exponent literals, DATA, optional arguments with present(),
+select case on strings, where / elsewhere, cycle / exit, allocate, the intrinsics aint int real dble min max abs sqrt sum cshift mod
+dmod modulo sign ceiling nint floor and exp log log10 cos sin atan tan ** (these through glibc's libm, float or double entry
+point by operand kind).  Scalar actual arguments of a `call` receive the callee's final dummy values (by-reference semantics);
+functions that update an argument inside an expression (random(dseed)) work through `alias_globals`.
 
 MPI.  MPI_SendRecv is executed, not stubbed: `count` elements of the send buffer in Fortran element order (Payload) go to
 `dest` with `sendtag`, and the message from `source` with `recvtag` lands in the first `count` elements of the receive buffer.
@@ -125,7 +129,8 @@ class FArr:
     def _bin(self, other, op, rev=False):
         o = other.nd() if isinstance(other, FArr) else other
         a = self.nd()
-        r = op(o, a) if rev else op(a, o)
+        with np.errstate(all="ignore"):
+            r = op(o, a) if rev else op(a, o)
         out = FArr(self.shape, self.flat.dtype)
         out.nd()[...] = r
         return out
@@ -206,6 +211,28 @@ class Comm:
         self.size, self.timeout = size, timeout
         self.q = collections.defaultdict(queue.Queue)
 
+    def allreduce(self, rank, val, op):
+        """all ranks contribute, everybody gets the rank-ordered combination (op: 'sum' | 'max' | 'min')"""
+        import threading
+        if not hasattr(self, "_ar"):
+            self._ar = {"lock": threading.Lock(), "vals": {}, "gen": 0, "cv": None, "res": None}
+            self._ar["cv"] = threading.Condition(self._ar["lock"])
+        st = self._ar
+        with st["cv"]:
+            gen = st["gen"]
+            st["vals"][rank] = val
+            if len(st["vals"]) == self.size:
+                vs = [st["vals"][r] for r in range(self.size)]
+                acc = vs[0]
+                for v in vs[1:]:
+                    acc = (acc + v) if op == "sum" else (np.maximum(acc, v) if op == "max" else np.minimum(acc, v))
+                st["res"], st["vals"], st["gen"] = acc, {}, gen + 1
+                st["cv"].notify_all()
+            else:
+                if not st["cv"].wait_for(lambda: st["gen"] != gen, timeout=self.timeout):
+                    raise TimeoutError("allreduce: a rank did not arrive")
+            return st["res"]
+
     def sendrecv(self, rank, payload, dest, sendtag, source, recvtag):
         self.q[(rank, int(dest), int(sendtag))].put(payload)
         return self.q[(int(source), rank, int(recvtag))].get(timeout=self.timeout)
@@ -270,11 +297,16 @@ def fdiv(a, b):
 
 def fpow(a, b):
     if isinstance(b, (int, np.integer)) and not isinstance(a, (int, np.integer)):
-        r = F(1.0)
+        K = np.float64 if isinstance(a, np.float64) else F
+        r = K(1.0)
         for _ in range(abs(int(b))):                                  # x**2 -> x*x as every compiler does
-            r = F(r * a) if not isinstance(a, (FArr, np.ndarray)) else r * a
-        return r if b >= 0 else F(1.0) / r
-    return a ** b
+            r = K(r * a) if not isinstance(a, (FArr, np.ndarray)) else r * a
+        return r if b >= 0 else K(1.0) / r
+    if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)):
+        return int(a) ** int(b)
+    if isinstance(a, np.float64) or isinstance(b, np.float64):
+        return np.float64(_libm().pow(float(a), float(b)))
+    return F(_libm().powf(float(F(a)), float(F(b))))                  # real ** real: libm's powf, as a compiled build calls
 
 
 def fsum(a):
@@ -306,19 +338,21 @@ def fexit(a, b, c=1):
 
 
 def faint(x):
-    return F(np.trunc(F(x)))
+    return np.trunc(x) if isinstance(x, np.float64) else F(np.trunc(F(x)))
 
 
 def fmodulo(a, b):
     if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)):
         return int(a) - int(b) * math.floor(int(a) / int(b))
-    return F(a - b * np.floor(a / b))
+    r = a - b * np.floor(a / b)
+    return r if isinstance(r, np.float64) else F(r)
 
 
 def fmod(a, b):
     if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)):
         return int(math.fmod(int(a), int(b)))
-    return F(np.fmod(a, b))
+    r = np.fmod(a, b)
+    return r if isinstance(r, np.float64) else F(r)
 
 
 def fmin(*a):
@@ -329,12 +363,78 @@ def fmax(*a):
     return max(a)
 
 
-INTRINSICS = {"aint": "faint", "int": "int", "real": "freal", "min": "fmin", "max": "fmax", "abs": "abs", "sqrt": "fsqrt", "sum": "fsum",
+_LIBM = None
+
+
+def _libm():
+    """glibc's libm: a compiled reference calls its float / double entry points (cosf, expf, log10f ...), and so does the
+    oracle; numpy's own SIMD versions can differ from them in the last bit"""
+    global _LIBM
+    if _LIBM is None:
+        import ctypes
+        import ctypes.util
+        _LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        for nm in ("cos", "sin", "exp", "log", "log10", "atan", "tan"):
+            getattr(_LIBM, nm).restype = ctypes.c_double
+            getattr(_LIBM, nm).argtypes = [ctypes.c_double]
+            getattr(_LIBM, nm + "f").restype = ctypes.c_float
+            getattr(_LIBM, nm + "f").argtypes = [ctypes.c_float]
+        _LIBM.pow.restype, _LIBM.pow.argtypes = ctypes.c_double, [ctypes.c_double, ctypes.c_double]
+        _LIBM.powf.restype, _LIBM.powf.argtypes = ctypes.c_float, [ctypes.c_float, ctypes.c_float]
+    return _LIBM
+
+
+def elementary(name):
+    def f(x):
+        if isinstance(x, FArr):
+            out = FArr(x.shape, x.flat.dtype)
+            out.flat[:] = [f(v) for v in x.flat]
+            return out
+        if isinstance(x, np.float64):
+            return np.float64(getattr(_libm(), name)(float(x)))
+        return F(getattr(_libm(), name + "f")(float(F(x))))
+    return f
+
+
+def fsqrt(x):
+    """IEEE square root in the operand's kind (correctly rounded everywhere)"""
+    if isinstance(x, FArr):
+        out = FArr(x.shape, x.flat.dtype)
+        with np.errstate(all="ignore"):
+            out.flat[:] = np.sqrt(x.flat)
+        return out
+    with np.errstate(all="ignore"):
+        return np.sqrt(x) if isinstance(x, np.float64) else F(np.sqrt(F(x)))
+
+
+def freal(x, kind=4):
+    if isinstance(x, FArr):
+        out = FArr(x.shape, np.float64 if int(kind) == 8 else np.float32)
+        out.flat[:] = x.flat
+        return out
+    return np.float64(x) if int(kind) == 8 else F(x)
+
+
+def fint(x):
+    """int(): truncation; a non-finite or out-of-range operand gives what x86's cvttss2si gives a compiled build, the
+    "integer indefinite" -2**31 (output.F90:497 relies on such a bin index simply failing its range test)"""
+    if isinstance(x, (int, np.integer)):
+        return int(x)
+    if not np.isfinite(x) or abs(float(x)) >= 2.0 ** 31:
+        return -2 ** 31
+    return int(x)
+
+
+INTRINSICS = {"exp": "fexp", "log": "flog", "alog": "flog", "log10": "flog10", "alog10": "flog10", "atan": "fatan", "tan": "ftan",
+              "dmod": "fdmod", "dble": "np.float64", "ceiling": "fceiling", "present": "fpresent",
+              "aint": "faint", "int": "fint", "real": "freal", "min": "fmin", "max": "fmax", "abs": "abs", "sqrt": "fsqrt", "sum": "fsum",
               "cshift": "fcshift", "mod": "fmod", "modulo": "fmodulo", "float": "F", "nint": "fnint", "floor": "ffloor", "cos": "fcos",
               "sin": "fsin", "sign": "fsign"}
-RUNTIME = {"freal": lambda x, *kind: F(x), "F": F, "FArr": FArr, "fdiv": fdiv, "fpow": fpow, "fsum": fsum, "fcshift": fcshift, "frange": frange, "fexit": fexit, "faint": faint,
-           "fmodulo": fmodulo, "fmod": fmod, "fmin": fmin, "fmax": fmax, "fsqrt": lambda x: F(np.sqrt(F(x))),
-           "fsign": lambda a, b: F(abs(a)) if not np.signbit(b) else F(-abs(a)), "fcos": lambda x: F(np.cos(F(x))), "fsin": lambda x: F(np.sin(F(x))), "fnint": lambda x: int(np.rint(x)), "ffloor": lambda x: int(np.floor(x)), "np": np}
+RUNTIME = {"fint": fint, "freal": freal, "fexp": elementary("exp"), "flog": elementary("log"), "flog10": elementary("log10"),
+           "fatan": elementary("atan"), "ftan": elementary("tan"), "fdmod": lambda a, b: np.float64(np.fmod(np.float64(a), np.float64(b))),
+           "fceiling": lambda x: int(math.ceil(x)), "fpresent": lambda x: x is not None, "F": F, "FArr": FArr, "fdiv": fdiv, "fpow": fpow, "fsum": fsum, "fcshift": fcshift, "frange": frange, "fexit": fexit, "faint": faint,
+           "fmodulo": fmodulo, "fmod": fmod, "fmin": fmin, "fmax": fmax, "fsqrt": fsqrt,
+           "fsign": lambda a, b: (abs(a) if not np.signbit(b) else -abs(a)) if isinstance(a, np.float64) else (F(abs(a)) if not np.signbit(b) else F(-abs(a))), "fcos": elementary("cos"), "fsin": elementary("sin"), "fnint": lambda x: int(np.rint(x)), "ffloor": lambda x: int(np.floor(x)), "np": np}
 PYKW = {"in", "is", "lambda", "not", "and", "or", "if", "else", "for", "while", "def", "class", "pass", "del", "from", "as", "with"}
 
 
@@ -526,8 +626,10 @@ class Expr:
         elif re.match(r"\d|\.\d", tok):
             if re.fullmatch(r"\d+", tok):
                 r = tok
+            elif "d" in tok:
+                r = f"np.float64({tok.replace('d', 'e')})"
             else:
-                r = f"F({tok.replace('d', 'e')})"
+                r = f"F({tok})"
         elif re.match(r"[a-z_]", tok):
             r = self.p_name(tok)
         else:
@@ -585,10 +687,16 @@ class Expr:
 # statement translation
 # ------------------------------------------------------------------------------------------------------------------
 class Sub:
-    def __init__(self, source, name, defines=(), global_arrays=(), global_ints=()):
+    def __init__(self, source, name, defines=(), global_arrays=(), global_ints=(), alias_globals=()):
+        """alias_globals: dummy arguments that every caller binds to the module variable of the same name (`dseed`): they are
+        read and written as that module variable, which gives functions called inside expressions -- random(dseed) -- the
+        by-reference update a plain Python argument cannot have."""
         self.name = name.lower()
-        self.local = {}                  # name -> ("int" | "real" | "logical", dims or None)
+        self.local = {}                  # name -> ("int" | "real" | "real8" | "logical", dims or None)
         self.args = []
+        self.alias = {a.lower() for a in alias_globals}
+        self.optional = set()
+        self.data_inits = []
         self.global_arrays = {a.lower() for a in global_arrays}
         self.global_ints = {a.lower() for a in global_ints}
         text = preprocess(source, set(defines))
@@ -629,7 +737,9 @@ class Sub:
         if not m:
             return False
         base, attrs, ents = m.group(1), m.group(3) or "", m.group(5)
-        kind = {"integer": "int", "real": "real", "logical": "logical", "double precision": "real"}[base]
+        kind = {"integer": "int", "real": "real", "logical": "logical", "double precision": "real8"}[base]
+        if base == "real" and re.sub(r"\s|kind=", "", m.group(2) or "") in ("(dprec)", "(8)"):
+            kind = "real8"
         dims = None
         dm = re.search(r"dimension\s*\(([^)]*(?:\([^)]*\)[^)]*)*)\)", attrs)
         if dm:
@@ -652,7 +762,11 @@ class Sub:
             em = re.match(r"([a-z_]\w*)\s*(?:\((.*)\))?$", p_)
             if not em:
                 raise SyntaxError("declaration entity " + p_)
+            if em.group(1) in self.alias:
+                continue
             self.local[em.group(1)] = (kind, em.group(2) or dims)
+            if "optional" in attrs:
+                self.optional.add(em.group(1))
         return True
 
     # --- statements ------------------------------------------------------------------------------------------------
@@ -666,9 +780,11 @@ class Sub:
                 return f"{self.ref(n)}.set({r})"
             k = self.kind(n)
             if k == "int":
-                return f"{self.ref(n)} = int({r})"
+                return f"{self.ref(n)} = fint({r})"
             if k == "real":
                 return f"{self.ref(n)} = F({r})"
+            if k == "real8":
+                return f"{self.ref(n)} = np.float64({r})"
             if k == "logical":
                 return f"{self.ref(n)} = bool({r})"
             return f"{self.ref(n)} = fassign_global({r})"
@@ -693,6 +809,9 @@ class Sub:
             # in Fortran order (Payload).
             a = self.split_dims(st[st.index("(") + 1:st.rindex(")")])
             return self.assign(a[5], f"mpi_xchg({a[0]}, {a[1]}, {a[3]}, {a[4]}, {a[8]}, {a[9]}, {a[2]}, {a[7]})")
+        if st.startswith("call mpi_allreduce"):
+            a = self.split_dims(st[st.index("(") + 1:st.rindex(")")])
+            return self.assign(a[1], f"mpi_allreduce({a[0]}, {a[2]}, {a[4]})")
         if st.startswith("call mpi_type_create_subarray"):
             # the derived datatypes of filter2's ghost exchange (fields.F90:1449-1600): keep the box the reference describes
             a = self.split_dims(st[st.index("(") + 1:st.rindex(")")])
@@ -715,9 +834,26 @@ class Sub:
             args = Expr(tokenize("(" + (m.group(2) or "") + ")"), self)
             args.next()
             a = args.p_args()
-            return f"_g.{m.group(1)}({', '.join(a)})"
+            call = f"_g.{m.group(1)}({', '.join(a)})"
+            # scalar actual arguments that are variables get the callee's final value of the dummy (by-reference semantics)
+            back = []
+            for i, raw in enumerate(self.split_dims(m.group(2) or "")):
+                raw = raw.strip()
+                if "=" in raw and not re.search(r"[<>=/]=|==", raw):
+                    continue                                           # keyword argument
+                idm = re.fullmatch(r"[a-z_]\w*", raw)
+                if idm and not self.is_array(raw) and raw not in INTRINSICS:
+                    k = self.kind(raw)
+                    cast = {"int": "int", "real": "F", "real8": "np.float64", "logical": "bool"}.get(k, "")
+                    back.append(f"{self.ref(raw)} = {cast}(_r[{i}])")
+                elif re.fullmatch(r"[a-z_]\w*\s*\(.*\)\s*%\s*[a-z_]\w*", raw) or \
+                        (re.fullmatch(r"([a-z_]\w*)\s*\(([^:]*)\)", raw) and self.is_array(raw.split("(")[0].strip())):
+                    back.append(f"{self.ex(raw)} = _r[{i}]")
+            if not back:
+                return call
+            return f"_r = {call}\n" + "".join("@IND@if _r is not None: " + b + "\n" for b in back).rstrip("\n")
         if st in ("return",):
-            return f"return {self.pyname(self.name)}" if getattr(self, "is_function", False) else "return"
+            return f"return {self.result()}"
         if st in ("continue",):
             return "pass"
         if st == "cycle":
@@ -767,7 +903,8 @@ class Sub:
         self.cyc = self.cycle_labels(self.stmts)
         hdr = self.stmts[0]
         m = re.match(r"(?:(integer|real|logical)(?:\([a-z0-9_]*\))?\s+)?(subroutine|function)\s+([a-z_]\w*)\s*(?:\((.*)\))?", hdr)
-        self.args = [a.strip() for a in (m.group(4) or "").split(",") if a.strip()]
+        self.dummies = [a.strip() for a in (m.group(4) or "").split(",") if a.strip()]
+        self.args = [a for a in self.dummies if a not in self.alias]
         self.is_function = m.group(2) == "function"
         if self.is_function:             # the result variable carries the function's name and type
             self.local[self.name] = ({"integer": "int", "real": "real", "logical": "logical"}[m.group(1) or "real"], None)
@@ -776,7 +913,8 @@ class Sub:
         loops, nloop = [], [0]
 
         def emit(s):
-            body.append("    " * ind + s)
+            for ln in s.split("\n"):
+                body.append("    " * ind + ln.replace("@IND@", ""))
         for st in self.stmts[1:]:
             if re.match(r"end\s*(subroutine|function)\b", st):
                 break
@@ -784,6 +922,9 @@ class Sub:
                     or st.startswith("character"):
                 continue
             if self.declare(st):
+                continue
+            if st.startswith("data "):                               # DATA a/1.d0/, b/2.d0/
+                self.data_inits += re.findall(r"([a-z_]\w*)\s*/\s*([^/]+?)\s*/", st[5:])
                 continue
             # allocate local arrays lazily, once, at the first executable statement
             if not decls_done:
@@ -795,13 +936,17 @@ class Sub:
                         emit(f"{self.pyname(n)} = None")                      # allocatable: created by `allocate`
                     elif dims is not None:
                         dd = ", ".join(self.ex(d) for d in self.split_dims(dims))
-                        emit(f"{self.pyname(n)} = FArr(({dd},), {'np.int64' if k == 'int' else 'np.float32'})")
+                        emit(f"{self.pyname(n)} = FArr(({dd},), {'np.int64' if k == 'int' else 'np.float64' if k == 'real8' else 'np.float32'})")
                     elif k == "real":
                         emit(f"{self.pyname(n)} = F(0.0)")
+                    elif k == "real8":
+                        emit(f"{self.pyname(n)} = np.float64(0.0)")
                     elif k == "int":
                         emit(f"{self.pyname(n)} = 0")
                     else:
                         emit(f"{self.pyname(n)} = False")
+                for lhs_, rhs_ in self.data_inits:
+                    emit(self.assign(lhs_, rhs_))
             m = re.match(r"if\s*\((.*)\)\s*then$", st)
             if m:
                 emit(f"if {self.ex(m.group(1))}:"); ind += 1; continue
@@ -867,10 +1012,17 @@ class Sub:
                 emit(f"if {self.ex(cond)}:"); ind += 1; emit(self.simple(rest)); ind -= 1
                 continue
             emit(self.simple(st))
-        args = ", ".join(["_g"] + [self.pyname(a) for a in self.args])
-        if self.is_function:
-            body.append(f"    return {self.pyname(self.name)}")
+        args = ", ".join(["_g"] + [("_alias_" + a if a in self.alias else self.pyname(a)) + ("=None" if a in self.optional else "")
+                                   for a in self.dummies])
+        body.append(f"    return {self.result()}")
         return f"def {self.name}({args}):\n" + "\n".join(body or ["    pass"]) + "\n"
+
+    def result(self):
+        """a function returns its result variable; a subroutine returns its dummies in order, so that the caller can copy
+        scalar results back into its actual arguments (Fortran passes by reference)"""
+        if self.is_function:
+            return self.pyname(self.name)
+        return "(" + "".join(self.ref(a) + ", " for a in self.dummies) + ")"
 
     @staticmethod
     def split_dims(s):
@@ -909,6 +1061,17 @@ class Globals:
         if self.comm is not None:         # one rank: every neighbour is the rank itself
             pay = self.comm.sendrecv(int(self.rank), pay, dest, sendtag, source, recvtag)
         return Payload(pay.data, recvtype if isinstance(recvtype, Subarray) else None)
+
+    def mpi_allreduce(self, sendbuf, count, op):
+        """MPI_Allreduce(sendbuf, recvbuf, count, type, op, ...): every contribution is logged as it crosses the MPI boundary
+        (allreduce_log) -- the per-rank value the reference computed; ranks are combined in rank order"""
+        val = as_payload(sendbuf, count).data if isinstance(sendbuf, (FArr, np.ndarray)) else sendbuf
+        if not hasattr(self, "allreduce_log"):
+            self.allreduce_log = []
+        self.allreduce_log.append(np.array(val).copy())
+        if self.comm is not None:
+            val = self.comm.allreduce(int(self.rank), val, op)
+        return Payload(np.atleast_1d(val)) if isinstance(sendbuf, (FArr, np.ndarray)) else val
 
     @staticmethod
     def mpi_subarray(sizes, subsizes, starts):

@@ -990,7 +990,147 @@ def gen_meanq():
     np.savez_compressed(os.path.join(OUT, "ref_meanq.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G15: the seeded loader -- init_particle_distribution_user of user/user_weibel.F90:250-296 calling inject_plasma_region
+#      (particles.F90:2549-2938), init_maxw_table (:2126-2163), maxwell_dist (:2176-2273), random / poisson (aux.F90:82-134,
+#      fp64 MINSTD), reorder_particles (:394-497).  exp / cos / sin go through libm's float entry points (f90run.elementary),
+#      as in a compiled build.  `dseed` is the module variable every call site passes (alias_globals).
+# ------------------------------------------------------------------------------------------------------------
+LOADER_CASES = [  # dim order nglob      sizes      ppc0 distr_dim delgam  gamma0
+    (2, 1, (12, 10, 1), (1, 1, 1), 8.0, 2, 2e-5, 0.5),
+    (3, 2, (6, 5, 4), (1, 1, 1), 4.0, 3, 1e-2, 0.5),
+    (2, 2, (16, 12, 1), (2, 2, 1), 4.0, 3, 5e-3, 3.0),
+    (2, 1, (3, 2, 1), (1, 1, 1), 3.0, 2, 1e-3, 0.3),            # numps < 10: the Poisson branch
+    (3, 3, (6, 8, 8), (1, 2, 2), 2.0, 3, 2e-5, 0.5)]
+
+
+def gen_loader():
+    out = {}
+    aux, ptext = src("aux.F90"), src("particles.F90")
+    user = open(os.path.join(REF, "user", "user_weibel.F90")).read()
+    gi = GINTS | {"mxcum", "mycum", "mzcum", "lap", "lapreorder", "totalpartnum", "injectedions", "injectedlecs", "pdf_sz", "mx0", "my0",
+                  "mz0", "myall", "mzall"}
+    ga = GARR | {"pall", "tempp"}
+    for ci, (dim, order, nglob, sizes, ppc0, distr_dim, delgam, gamma0) in enumerate(LOADER_CASES):
+        defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+        kw = dict(defines=defines, global_arrays=ga, global_ints=gi, alias_globals={"dseed"})
+        subs = {nm: R.Sub(aux, nm, **kw).compile() for nm in ("random", "poisson")}
+        for nm in ("init_maxw_table", "maxwell_dist", "inject_plasma_region", "reorder_particles", "reorder_particles_"):
+            subs[nm] = R.Sub(ptext, nm, **kw).compile()
+        subs["init_particle_distribution_user"] = R.Sub(user, "init_particle_distribution_user", **kw).compile()
+        size0 = sizes[0] * sizes[1] * sizes[2]
+        key = f"w{ci}"
+        n = tuple(a // s_ for a, s_ in zip(nglob, sizes))
+        ncell = n[0] * n[1] * (n[2] if dim == 3 else 1)
+        maxhlf = int(2 * ppc0 * ncell) + 64
+        out[key + "_meta"] = np.array([dim, order, 1, 1, 1, *nglob], np.int32)
+        out[key + "_geom"] = np.array([*sizes, maxhlf, distr_dim], np.int32)
+        out[key + "_par"] = np.array([ppc0, gamma0, delgam], F)
+        for rank in range(size0):
+            g = field_globals(dim, order, n, (1, 1, 1), np.random.default_rng(1))
+            rank_geometry(g, dim, order, nglob, sizes, rank)
+            ng, ngz, mx, my, mz = grid(dim, order, n)
+            g.mx0, g.my0, g.mz0 = nglob[0] + ng, nglob[1] + ng, (nglob[2] + ngz if dim == 3 else 1)
+            g.myall, g.mzall = g.my0, g.mz0
+            g.pdf_sz = 1000                                                  # particles.F90:45
+            g.pi = np.float64(F(3.1415927))                                  # :73, 292 -- an fp32 literal in an fp64 variable
+            g.dseed = np.float64(123457.0) + rank                            # communications.F90:228-229
+            g.pcosthmult = F(0.0) if (dim == 2 and distr_dim == 2) else F(1.0)       # user_weibel.F90:160-167
+            g.sigma, g.c_omp, g.ppc0, g.delgam = F(0.0), F(10.0), F(ppc0), F(delgam)
+            g.me, g.mi, g.temperature_ratio = F(1.0), F(1.0), F(1.0)
+            g0 = F(gamma0)
+            g.gamma0 = F(np.sqrt(F(F(1.) / F(F(1.) - F(g0 * g0))))) if g0 < 1 else g0          # particles.F90:213
+            g.xinject = g.xinject2 = F(0)
+            g.debug, g.lap, g.lapreorder = False, 0, 0
+            g.totalpartnum = g.injectedions = g.injectedlecs = 0
+            p = np.zeros(2 * maxhlf, PDT)
+            g.p, g.tempp, g.pall = R.RecArr(p), R.RecArr(np.zeros(maxhlf, PDT)), R.FArr((g.lot,), np.int64)
+            g.ions, g.lecs, g.maxhlf = 0, 0, maxhlf
+            for nm, f in subs.items():
+                setattr(g, nm, (lambda f_, g_: (lambda *a, **k: f_(g_, *a, **k)))(f, g))
+            g.check_overflow = g.check_overflow_num = lambda *a: None
+
+            def copyprt(a, b):
+                for k in PDT.names:
+                    setattr(b, k, getattr(a, k))
+            g.copyprt = copyprt
+            g.init_particle_distribution_user()
+            out[f"{key}_r{rank}_p"] = p.copy()
+            out[f"{key}_r{rank}_counts"] = np.array([g.ions, g.lecs, g.totalpartnum], np.int64)
+            out[f"{key}_r{rank}_dseed"] = np.array([g.dseed], np.float64)
+            print("loader", key, "rank", rank, "ions", g.ions, "lecs", g.lecs, "dseed", g.dseed, "mean u", float(p["u"][:g.ions].mean()) if g.ions else 0)
+    np.savez_compressed(os.path.join(OUT, "ref_loader.npz"), **out)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# G16: save_spectrum (output.F90:380-633), the computing part: gamma range, lab-frame and flow-frame spectra per x slice.
+#      The routine is executed up to the line where it starts writing files.  What each rank contributes is captured where it
+#      crosses the MPI boundary (the send buffers of the routine's six MPI_Allreduce calls, f90run.Globals.allreduce_log).
+# ------------------------------------------------------------------------------------------------------------
+SPEC_CASES = [(2, 1, (260, 6, 1), (1, 1, 1)), (3, 2, (210, 4, 4), (1, 1, 1)), (2, 1, (440, 6, 1), (2, 1, 1))]
+
+
+def gen_spectrum():
+    out = {}
+    text = src("output.F90")
+    import re
+    a = re.search(r"^[ \t]*subroutine save_spectrum", text, flags=re.I | re.M).start()
+    b = text.lower().index('"done spec calculation', a)
+    b = text.rfind("\n", 0, b)
+    text = text[a:b] + "\n\tendif\nend subroutine save_spectrum\n"
+    gi = GINTS | {"mxcum", "lap", "pltstart", "interval", "mx0", "mpi_status_size"}
+    for ci, (dim, order, nglob, sizes) in enumerate(SPEC_CASES):
+        defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+        sub = R.Sub(text, "save_spectrum", defines=defines, global_arrays=GARR, global_ints=gi).compile()
+        size0 = sizes[0] * sizes[1] * sizes[2]
+        comm = R.Comm(size0) if size0 > 1 else None
+        key = f"e{ci}"
+        n = tuple(a_ // s_ for a_, s_ in zip(nglob, sizes))
+        ng, ngz, mx, my, mz = grid(dim, order, n)
+        nsp, maxhlf = 600, 640
+        out[key + "_meta"] = np.array([dim, order, 1, 1, 1, *nglob], np.int32)
+        out[key + "_geom"] = np.array([*sizes, maxhlf, nsp], np.int32)
+        gs = []
+        for rank in range(size0):
+            rng = np.random.default_rng(1600 + 16 * ci + rank)
+            g = field_globals(dim, order, n, (1, 1, 1), rng)
+            rank_geometry(g, dim, order, nglob, sizes, rank)
+            g.comm = comm
+            g.mx0 = nglob[0] + ng
+            g.lap, g.pltstart, g.interval, g.debug = 0, 0, 50, False
+            g.splitratio = F(10.0)
+            g.mpi_status_size, g.mpi_read, g.mpi_comm_world = 5, 0, 0
+            g.mpi_max, g.mpi_min, g.mpi_sum = "max", "min", "sum"
+            p = np.zeros(2 * maxhlf, PDT)
+            for s0 in (0, maxhlf):
+                sl = slice(s0, s0 + nsp)
+                p["x"][sl] = ((ng // 2 + 1) + rng.random(nsp) * n[0]).astype(F)
+                p["y"][sl] = ((ng // 2 + 1) + rng.random(nsp) * n[1]).astype(F)
+                p["z"][sl] = ((ngz // 2 + 1) + rng.random(nsp) * (n[2] if dim == 3 else 1)).astype(F)
+                spread = np.exp(rng.standard_normal(nsp) * 1.2) * 0.3              # a wide range of energies
+                for k in "uvw":
+                    p[k][sl] = (rng.standard_normal(nsp) * spread).astype(F)
+                p["u"][sl] += F(0.4)                                                  # a mean flow to boost out of
+                p["ch"][sl] = (0.5 + rng.random(nsp)).astype(F)
+                p["splitlev"][sl] = np.where(rng.random(nsp) < 0.2, 2, 1)
+                p["ind"][sl] = np.arange(1, nsp + 1)
+                p["proc"][sl] = rank
+            g.p = R.RecArr(p)
+            g.ions, g.lecs, g.maxhlf = nsp, nsp, maxhlf
+            out[f"{key}_r{rank}_pin"] = p.copy()
+            gs.append(g)
+        R.run_ranks([(lambda g=g: sub(g)) for g in gs])
+        for rank, g in enumerate(gs):
+            log = g.allreduce_log            # gammax, gammin, specp, specpprime, spece, speceprime
+            assert len(log) == 6
+            out[f"{key}_r{rank}_range"] = np.array([log[1], log[0]], F).reshape(2)
+            for nm, v in zip(("specp", "specpprime", "spece", "speceprime"), log[2:]):
+                out[f"{key}_r{rank}_{nm}"] = np.asarray(v, F)
+        print("spectrum", key, dim, order, nglob, sizes, "range", out[f"{key}_r0_range"], "counts in spectrum", float(out[f"{key}_r0_specp"].sum()))
+    np.savez_compressed(os.path.join(OUT, "ref_spectrum.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq", "loader", "spectrum"]
     for w in which:
         globals()["gen_" + w]()

@@ -278,3 +278,99 @@ def test_committed_goldens_are_what_the_generator_makes(tmp_path, monkeypatch):
         assert set(a.files) == set(b.files)
         for k in a.files:
             assert np.array_equal(a[k], b[k]), (name, k)
+
+
+def test_double_precision_entities_data_and_the_minstd_step():
+    src = """
+    real function lcg(dseed)
+      real(dprec) :: dseed
+      real(dprec) :: s2p31, s2p31m, seed
+      data s2p31m/2147483647.d0/, s2p31/2147483648.d0/
+      seed = dseed
+      seed = dmod(16807.d0*seed, s2p31m)
+      lcg = seed/s2p31
+      dseed = seed
+    end function lcg
+    """
+    g = R.Globals(dseed=np.float64(123457.0))
+    f = R.Sub(src, "lcg", alias_globals={"dseed"}).compile()
+    v = f(g, None)
+    assert g.dseed == np.float64((16807 * 123457) % 2147483647) and isinstance(g.dseed, np.float64)
+    assert v == F(g.dseed / 2147483648.0) and isinstance(v, np.float32)
+    v2 = f(g, None)
+    assert g.dseed == np.float64((16807 * ((16807 * 123457) % 2147483647)) % 2147483647) and v2 != v
+
+
+def test_scalar_arguments_are_passed_by_reference_and_optional_arguments():
+    src = """
+    subroutine polar(r, phi, x, y, scale)
+      real :: r, phi, x, y
+      real, optional :: scale
+      x = r*cos(phi)
+      y = r*sin(phi)
+      if (present(scale)) then
+        x = x*scale
+      endif
+    end subroutine polar
+
+    subroutine t()
+      real :: a, b
+      call polar(2., 0.5, a, b)
+      r1 = a
+      r2 = b
+      call polar(2., 0.5, q(2), b, 3.)
+    end subroutine t
+    """
+    g = R.Globals(q=R.FArr((3,)))
+    f = R.Sub(src, "polar").compile()
+    g.polar = lambda *a: f(g, *a)
+    run(src, "t", g, arrays=("q",))
+    import ctypes
+    import ctypes.util
+    m = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    m.cosf.restype = m.sinf.restype = ctypes.c_float
+    m.cosf.argtypes = m.sinf.argtypes = [ctypes.c_float]
+    cx, sy = F(F(2) * F(m.cosf(0.5))), F(F(2) * F(m.sinf(0.5)))
+    assert (g.r1, g.r2) == (cx, sy)
+    assert g.q.flat[1] == F(cx * F(3)) and g.q.flat[0] == 0
+
+
+def test_int_of_a_non_finite_value_is_the_integer_indefinite():
+    src = """
+    subroutine t()
+      integer :: k
+      real :: a
+      a = 0.
+      k = int(alog10(a))
+      r1 = k
+      r2 = 10.**2.5
+    end subroutine t
+    """
+    _, g = run(src, "t")
+    assert g.r1 == -2 ** 31
+    assert abs(float(g.r2) - 10 ** 2.5) < 1e-4 * 10 ** 2.5 and isinstance(g.r2, np.float32)
+
+
+def test_mpi_allreduce_between_ranks_and_its_log():
+    src = """
+    subroutine t()
+      real :: lo, lo1
+      lo = 10. + rank
+      call mpi_allreduce(lo, lo1, 1, mpi_read, mpi_min, mpi_comm_world, ierr)
+      r1 = lo1
+      call mpi_allreduce(h, hin, 4, mpi_read, mpi_sum, mpi_comm_world, ierr)
+    end subroutine t
+    """
+    comm = R.Comm(3)
+    f = R.Sub(src, "t", global_arrays={"h", "hin"}, global_ints={"rank"}).compile()
+    gs = []
+    for rk in range(3):
+        g = R.Globals(rank=rk, h=R.FArr((2, 2)), hin=R.FArr((2, 2)), mpi_read=0, mpi_min="min", mpi_sum="sum", mpi_comm_world=0, ierr=0)
+        g.comm = comm
+        g.h.flat[:] = rk + 1
+        gs.append(g)
+    R.run_ranks([(lambda g=g: f(g)) for g in gs])
+    for rk, g in enumerate(gs):
+        assert g.r1 == F(10.0)
+        assert list(g.hin.flat) == [6, 6, 6, 6]
+        assert float(g.allreduce_log[0]) == 10.0 + rk and list(g.allreduce_log[1]) == [rk + 1] * 4
