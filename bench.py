@@ -125,8 +125,12 @@ def run_small_config(args):
     next_ind = [2 * nsp + 2]
 
     def inject():
-        """the reference's host injector (user_shock.F90:303-331 -> inject_from_wall): ppc0 * c * beta particles per cell
-        face and lap enter at the right edge, moving towards the wall; host RNG, uploaded with tgpu_append_particles"""
+        """A stand-in for the reference's host injector (user_shock.F90:303-331 -> inject_from_wall): the same number of
+        particles per lap, ppc0/2 * c * beta per cell face and species, drawn with numpy in the slab the plane source fills in
+        one step and uploaded with tgpu_append_particles.  Two deliberate differences: the draws are not the reference's
+        MINSTD / Juttner sequence (the oracle has that: orc_inject_particles_shock, pinned in tests/test_ref_golden.py), and
+        the plane sits at the last interior node mx - g, because the reference's hard-coded x = mx0 - 2 is outside the
+        interior when nghost = 7 (dd2 / dd3) and its injector then adds nothing (same test, case 3)."""
         if not hooks:
             return 0
         n = int(0.5 * kw["ppc0"] * kw["my0"] * kw["mz0"] * 0.45 * drift)

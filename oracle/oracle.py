@@ -124,6 +124,7 @@ def lib():
         L.orc_init_weibel.argtypes = [vp, cf, cf, cf, cf, cf, cf, ci]
         L.orc_init_twostream.argtypes = [vp, cf, cf, cf, cf, cf, cf]
         L.orc_init_uniform.argtypes = [vp, cf, cf, cf, C.c_uint64]
+        L.orc_inject_particles_shock.argtypes = [vp, cf, cf, cf, cf, cf, cf, ci, cf]
         L.orc_field_bc_shock.argtypes = [vp, cf, cf, cf, cf, cf]
         L.orc_particle_bc_wall.argtypes = [vp, cf]
         L.orc_step_shock.argtypes = [vp, cf, cf, cf, cf, cf]
@@ -253,6 +254,10 @@ class World:
 
     def init_weibel(self, ppc0=16.0, gamma0=0.5, delgam=2e-5, me=1.0, mi=1.0, tratio=1.0, distr_dim=2):
         lib().orc_init_weibel(self.h, ppc0, gamma0, delgam, me, mi, tratio, distr_dim)
+
+    def inject_particles_shock(self, ppc0=16.0, gamma0=0.5, delgam=2e-5, me=1.0, mi=1.0, tratio=1.0, pcosthmult=0, sigma=0.0):
+        """the shock problem's per-lap plane source on every rank (user/user_shock.F90:303-331 -> inject_from_wall)"""
+        lib().orc_inject_particles_shock(self.h, ppc0, gamma0, delgam, me, mi, tratio, pcosthmult, sigma)
 
     def init_twostream(self, ppc0=64.0, gamma0=0.5, delgam=2e-5, me=1.0, mi=1.0, tratio=1.0):
         lib().orc_init_twostream(self.h, ppc0, gamma0, delgam, me, mi, tratio)

@@ -1739,6 +1739,36 @@ void orc_inject_plasma_region(orc_rank *r, float x1, float x2, float y1, float y
     }
 }
 
+/* inject_from_wall: particles.F90:2439-2538 (upsamp_e = upsamp_i = 1) -- the slab a plane source fills in one step */
+void orc_inject_from_wall(orc_rank *r, float x1, float x2, float y1, float y2, float z1, float z2, float ppc, float gamma_drift,
+                          float delgam_i, float delgam_e, float wall_speed, float weight, int pcosthmult, float sigma)
+{
+    const float c = r->P.c;
+    float beta_wall, beta_inj, xt;
+    int direction = 0;                                      /* undefined in the reference when no pair coincides */
+    if (fabsf(wall_speed) >= 1) beta_wall = fsign(sqrtf(1 - 1 / (wall_speed * wall_speed)), wall_speed);
+    else beta_wall = wall_speed;
+    if (fabsf(gamma_drift) >= 1) beta_inj = fsign(sqrtf(1 - 1.f / (gamma_drift * gamma_drift)), gamma_drift);
+    else beta_inj = gamma_drift;
+    float x1n = x1, x2n = x2, y1n = y1, y2n = y2, z1n = z1, z2n = z2;
+    if (x1 == x2) { x2n = x1 + (beta_inj - beta_wall) * c; direction = 1; if (x2n < x1n) { xt = x1n; x1n = x2n; x2n = xt; } }
+    if (y1 == y2) { y2n = y1 + (beta_inj - beta_wall) * c; direction = 2; if (y2n < y1n) { xt = y1n; y1n = y2n; y2n = xt; } }
+    if (z1 == z2) { z2n = z1 + (beta_inj - beta_wall) * c; direction = 3; if (z2n < z1n) { xt = z1n; z1n = z2n; z2n = xt; } }
+    orc_inject_plasma_region(r, x1n, x2n, y1n, y2n, z1n, z2n, ppc, gamma_drift, delgam_i, delgam_e, weight, direction, pcosthmult, sigma);
+}
+/* inject_particles_user of the shock problem: user/user_shock.F90:303-331 (a non-receding plane source at x = mx0 - 2) */
+void orc_inject_particles_shock(orc_world *w, float ppc0, float gamma0_in, float delgam, float me, float mi,
+                                float temperature_ratio, int pcosthmult, float sigma)
+{
+    float gamma0 = gamma0_in;
+    if (gamma0 < 1) gamma0 = sqrtf(1.f / (1.f - gamma0 * gamma0));                       /* particles.F90:213 */
+    for (int rk = 0; rk < w->size0; rk++) {
+        const float x1 = w->mx0g - 2.f, y1 = 3.f, y2 = w->my0g - 2.f, z1 = 3.f, z2 = w->mz0g - 2.f;
+        orc_inject_from_wall(w->r[rk], x1, x1, y1, y2, z1, z2, ppc0, -gamma0, delgam, delgam * mi / me * temperature_ratio, 0.f, 1.f,
+                             pcosthmult, sigma);
+    }
+}
+
 /* read_input_particles: particles.F90:219-235 */
 void orc_charge_normalisation(orc_params *P, float ppc0, float c_omp, float gamma0, float me, float mi)
 {

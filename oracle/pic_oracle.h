@@ -11,9 +11,9 @@
  * hot-path subroutines -- up to `mainloop` itself, on several ranks -- are
  * executed from their text by the Fortran-subset interpreter
  * tests/golden/f90run.py; tests/test_ref_golden.py holds this restatement
- * BIT-EXACT against those outputs (tests/golden/ref_*.npz; 97 cases).  Not
+ * BIT-EXACT against those outputs (tests/golden/ref_*.npz; 102 cases).  Not
  * covered that way, and pinned only by the known-answer tests
- * (tests/test_oracle_kat.py): particle sampling (prtl.tot), the shock injector, restart I/O.  See DESIGN.md section 2.  Every function cites the
+ * (tests/test_oracle_kat.py): particle sampling (prtl.tot), restart I/O.  See DESIGN.md section 2.  Every function cites the
  * reference file:line it follows (relative to the reference checkout).
  *
  * Conventions: arrays are Fortran column-major (mx,my,mz), addressed here with
@@ -169,6 +169,11 @@ void orc_maxwell_dist(int dim, int pcosthmult, float sigma, float gamma0, float 
 void orc_inject_plasma_region(orc_rank *r, float x1, float x2, float y1, float y2, float z1, float z2,
                               float ppc, float gamma_drift_in, float delgam_i, float delgam_e,
                               float weight, int direction, int pcosthmult, float sigma);
+/* plane source: inject_from_wall (particles.F90:2439-2538) and the shock problem's per-lap injector (user/user_shock.F90:303-331) */
+void orc_inject_from_wall(orc_rank *r, float x1, float x2, float y1, float y2, float z1, float z2, float ppc, float gamma_drift,
+                          float delgam_i, float delgam_e, float wall_speed, float weight, int pcosthmult, float sigma);
+void orc_inject_particles_shock(orc_world *w, float ppc0, float gamma0_in, float delgam, float me, float mi,
+                                float temperature_ratio, int pcosthmult, float sigma);
 /* problem setups: user/user_weibel.F90:255-313, user/user_twostream.F90:226-270 */
 void orc_charge_normalisation(orc_params *P, float ppc0, float c_omp, float gamma0, float me, float mi);
 void orc_init_weibel(orc_world *w, float ppc0, float gamma0_in, float delgam, float me, float mi,

@@ -1001,17 +1001,21 @@ LOADER_CASES = [  # dim order nglob      sizes      ppc0 distr_dim delgam  gamma
     (3, 2, (6, 5, 4), (1, 1, 1), 4.0, 3, 1e-2, 0.5),
     (2, 2, (16, 12, 1), (2, 2, 1), 4.0, 3, 5e-3, 3.0),
     (2, 1, (3, 2, 1), (1, 1, 1), 3.0, 2, 1e-3, 0.3),            # numps < 10: the Poisson branch
-    (3, 3, (6, 8, 8), (1, 2, 2), 2.0, 3, 2e-5, 0.5)]
+    (3, 3, (6, 8, 8), (1, 2, 2), 2.0, 3, 2e-5, 0.5),
+    # user/user_twostream.F90:226-270 (configs[1]: dd2, a 2-cell-wide y axis, electrons only)
+    (2, 2, (32, 2, 1), (1, 1, 1), 16.0, 2, 2e-5, 0.5, "twostream")]
 
 
 def gen_loader():
     out = {}
     aux, ptext = src("aux.F90"), src("particles.F90")
-    user = open(os.path.join(REF, "user", "user_weibel.F90")).read()
+    users = {u: open(os.path.join(REF, "user", f"user_{u}.F90")).read() for u in ("weibel", "twostream")}
     gi = GINTS | {"mxcum", "mycum", "mzcum", "lap", "lapreorder", "totalpartnum", "injectedions", "injectedlecs", "pdf_sz", "mx0", "my0",
                   "mz0", "myall", "mzall"}
     ga = GARR | {"pall", "tempp"}
-    for ci, (dim, order, nglob, sizes, ppc0, distr_dim, delgam, gamma0) in enumerate(LOADER_CASES):
+    for ci, case in enumerate(LOADER_CASES):
+        dim, order, nglob, sizes, ppc0, distr_dim, delgam, gamma0 = case[:8]
+        user = users[case[8] if len(case) > 8 else "weibel"]
         defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
         kw = dict(defines=defines, global_arrays=ga, global_ints=gi, alias_globals={"dseed"})
         subs = {nm: R.Sub(aux, nm, **kw).compile() for nm in ("random", "poisson")}
@@ -1024,7 +1028,7 @@ def gen_loader():
         ncell = n[0] * n[1] * (n[2] if dim == 3 else 1)
         maxhlf = int(2 * ppc0 * ncell) + 64
         out[key + "_meta"] = np.array([dim, order, 1, 1, 1, *nglob], np.int32)
-        out[key + "_geom"] = np.array([*sizes, maxhlf, distr_dim], np.int32)
+        out[key + "_geom"] = np.array([*sizes, maxhlf, distr_dim, 1 if len(case) > 8 else 0], np.int32)
         out[key + "_par"] = np.array([ppc0, gamma0, delgam], F)
         for rank in range(size0):
             g = field_globals(dim, order, n, (1, 1, 1), np.random.default_rng(1))
@@ -1130,7 +1134,64 @@ def gen_spectrum():
     np.savez_compressed(os.path.join(OUT, "ref_spectrum.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G17: the shock problem's per-lap injector -- inject_particles_user (user/user_shock.F90:303-331) -> inject_from_wall
+#      (particles.F90:2439-2538) -> inject_plasma_region; three consecutive calls append to the same arrays
+# ------------------------------------------------------------------------------------------------------------
+# With nghost = 7 (dd2, dd3) the hard-coded source plane x = mx0 - 2 (an nghost = 5 number) lies outside the interior, whose last
+# node is mx0 - 3: inject_plasma_region clamps the slab to zero width and the injector adds nothing (the last case pins that).
+INJ_CASES = [(2, 1, (40, 12, 1), (2, 1, 1), 8.0, 2e-3, 0.5, 0), (3, 1, (20, 6, 5), (1, 1, 1), 4.0, 1e-2, 4.0, 1), (2, 0, (30, 3, 1), (1, 1, 1), 2.0, 1e-3, 0.3, 0),
+             (3, 3, (20, 6, 5), (1, 1, 1), 4.0, 1e-2, 0.5, 1)]
+
+
+def gen_injector():
+    out = {}
+    aux, ptext = src("aux.F90"), src("particles.F90")
+    user = open(os.path.join(REF, "user", "user_shock.F90")).read()
+    gi = GINTS | {"mxcum", "mycum", "mzcum", "lap", "totalpartnum", "injectedions", "injectedlecs", "pdf_sz", "mx0", "my0", "mz0", "myall", "mzall"}
+    for ci, (dim, order, nglob, sizes, ppc0, delgam, gamma0, pcm) in enumerate(INJ_CASES):
+        defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+        kw = dict(defines=defines, global_arrays=GARR, global_ints=gi, alias_globals={"dseed"})
+        subs = {nm: R.Sub(aux, nm, **kw).compile() for nm in ("random", "poisson")}
+        for nm in ("init_maxw_table", "maxwell_dist", "inject_plasma_region", "inject_from_wall"):
+            subs[nm] = R.Sub(ptext, nm, **kw).compile()
+        subs["inject_particles_user"] = R.Sub(user, "inject_particles_user", **kw).compile()
+        size0 = sizes[0] * sizes[1] * sizes[2]
+        key = f"j{ci}"
+        n = tuple(a // s_ for a, s_ in zip(nglob, sizes))
+        maxhlf = 2000
+        out[key + "_meta"] = np.array([dim, order, 0, 1, 1, *nglob], np.int32)
+        out[key + "_geom"] = np.array([*sizes, maxhlf, pcm], np.int32)
+        out[key + "_par"] = np.array([ppc0, gamma0, delgam], F)
+        for rank in range(size0):
+            g = field_globals(dim, order, n, (0, 1, 1), np.random.default_rng(1))
+            rank_geometry(g, dim, order, nglob, sizes, rank)
+            ng, ngz, mx, my, mz = grid(dim, order, n)
+            g.mx0, g.my0, g.mz0 = nglob[0] + ng, nglob[1] + ng, (nglob[2] + ngz if dim == 3 else 1)
+            g.myall, g.mzall, g.pdf_sz = g.my0, g.mz0, 1000
+            g.pi = np.float64(F(3.1415927))
+            g.dseed = np.float64(123457.0) + rank
+            g.pcosthmult, g.sigma, g.c_omp, g.ppc0, g.delgam = F(pcm), F(0.0), F(10.0), F(ppc0), F(delgam)
+            g.me, g.mi, g.temperature_ratio = F(1.0), F(1.0), F(1.0)
+            g0 = F(gamma0)
+            g.gamma0 = F(np.sqrt(F(F(1.) / F(F(1.) - F(g0 * g0))))) if g0 < 1 else g0
+            g.debug, g.lap = False, 1
+            g.totalpartnum = g.injectedions = g.injectedlecs = 0
+            p = np.zeros(2 * maxhlf, PDT)
+            g.p = R.RecArr(p)
+            g.ions, g.lecs, g.maxhlf = 0, 0, maxhlf
+            for nm, f in subs.items():
+                setattr(g, nm, (lambda f_, g_: (lambda *a, **k: f_(g_, *a, **k)))(f, g))
+            g.check_overflow = g.check_overflow_num = lambda *a: None
+            for call in range(3):
+                g.inject_particles_user()
+                out[f"{key}_r{rank}_counts{call}"] = np.array([g.ions, g.lecs], np.int64)
+            out[f"{key}_r{rank}_p"] = p.copy()
+            print("injector", key, "rank", rank, "ions", g.ions, "lecs", g.lecs, "x range", (float(p["x"][:g.ions].min()), float(p["x"][:g.ions].max())) if g.ions else None)
+    np.savez_compressed(os.path.join(OUT, "ref_injector.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq", "loader", "spectrum"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq", "loader", "spectrum", "injector"]
     for w in which:
         globals()["gen_" + w]()

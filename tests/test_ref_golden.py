@@ -408,21 +408,24 @@ def test_meanq_fld_cur_matches_the_reference_source(case):
             assert np.array_equal(r.arr(6), ref), (str(name), rk, float(np.abs(r.arr(6) - ref).max()), float(np.abs(ref).max()))
 
 
-@pytest.mark.parametrize("case", range(5))
+@pytest.mark.parametrize("case", range(6))
 def test_seeded_loader_matches_the_reference_source(case):
-    """init_particle_distribution_user of user/user_weibel.F90 with inject_plasma_region, init_maxw_table, maxwell_dist,
+    """init_particle_distribution_user of user/user_weibel.F90 (cases 0-4) and user/user_twostream.F90 (case 5) with inject_plasma_region, init_maxw_table, maxwell_dist,
     random / poisson (fp64 MINSTD, dseed = 123457 + rank) and the reorder that ends it, from the reference's text: the draw
     order, the table look-up, the Juttner flip, the Poisson branch for tiny regions.  Particle arrays IN ORDER, identities and
     counts BIT-EXACT (exp / cos / sin are libm's float functions on both sides)."""
     z = load("ref_loader.npz")
     key = f"w{case}"
     dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
-    sx, sy, sz, maxhlf, distr_dim = (int(v) for v in z[key + "_geom"])
+    sx, sy, sz, maxhlf, distr_dim, twostream = (int(v) for v in z[key + "_geom"])
     ppc0, gamma0, delgam = (float(v) for v in z[key + "_par"])
     P = O.make_params(dim=dim, order=order, mx0=nx, my0=ny, mz0=nz, sizex=sx, sizey=sy, sizez=sz, periodic=(px, py, pz), maxptl=2 * maxhlf,
                       ppc0=ppc0, gamma0=gamma0)
     w = O.World(P)
-    w.init_weibel(ppc0=ppc0, gamma0=gamma0, delgam=delgam, me=1.0, mi=1.0, tratio=1.0, distr_dim=distr_dim)
+    if twostream:                       # user/user_twostream.F90:226-270, case 5
+        w.init_twostream(ppc0=ppc0, gamma0=gamma0, delgam=delgam, me=1.0, mi=1.0, tratio=1.0)
+    else:
+        w.init_weibel(ppc0=ppc0, gamma0=gamma0, delgam=delgam, me=1.0, mi=1.0, tratio=1.0, distr_dim=distr_dim)
     for rk, r in enumerate(w.ranks):
         assert r.maxhlf == maxhlf
         ions, lecs, total = (int(v) for v in z[f"{key}_r{rk}_counts"])
@@ -459,3 +462,31 @@ def test_spectrum_matches_the_reference_source(case):
             ref = z[f"{key}_r{rk}_{nm}"]
             assert ref.sum() > 100
             assert np.array_equal(got.reshape(-1), ref.reshape(-1)), (rk, nm, int((got.reshape(-1) != ref.reshape(-1)).sum()))
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_shock_injector_matches_the_reference_source(case):
+    """inject_particles_user (user/user_shock.F90:303-331) -> inject_from_wall (particles.F90:2439-2538) ->
+    inject_plasma_region, three consecutive calls: counts after each call and the particle arrays IN ORDER, BIT-EXACT.
+    Case 3 pins a reference quirk: with nghost = 7 the hard-coded plane x = mx0 - 2 is outside the interior and the
+    injector adds nothing."""
+    z = load("ref_injector.npz")
+    key = f"j{case}"
+    dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
+    sx, sy, sz, maxhlf, pcm = (int(v) for v in z[key + "_geom"])
+    ppc0, gamma0, delgam = (float(v) for v in z[key + "_par"])
+    P = O.make_params(dim=dim, order=order, mx0=nx, my0=ny, mz0=nz, sizex=sx, sizey=sy, sizez=sz, periodic=(px, py, pz), maxptl=2 * maxhlf)
+    w = O.World(P)
+    for call in range(3):
+        w.inject_particles_shock(ppc0=ppc0, gamma0=gamma0, delgam=delgam, pcosthmult=pcm)
+        for rk, r in enumerate(w.ranks):
+            assert r.counts == tuple(int(v) for v in z[f"{key}_r{rk}_counts{call}"]), (call, rk)
+    total = 0
+    for rk, r in enumerate(w.ranks):
+        ions, lecs = r.counts
+        total += ions
+        ref, p = z[f"{key}_r{rk}_p"], r.particles()
+        for sl in (slice(0, ions), slice(maxhlf, maxhlf + lecs)):
+            for k in ref.dtype.names:
+                assert np.array_equal(p[k][sl], ref[k][sl]), (rk, k)
+    assert (total == 0) == (case == 3)
