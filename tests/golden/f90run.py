@@ -82,7 +82,7 @@ class FArr:
             if isinstance(k, slice):
                 lo = 1 if k.start is None else int(k.start)
                 hi = n if k.stop is None else int(k.stop)
-                idx.append(slice(lo - 1, hi))
+                idx.append(slice(lo - 1, hi, None if k.step is None else int(k.step)))
             else:
                 idx.append(int(k) - 1)
         return tuple(idx)
@@ -223,8 +223,8 @@ class Comm:
             st["vals"][rank] = val
             if len(st["vals"]) == self.size:
                 vs = [st["vals"][r] for r in range(self.size)]
-                acc = vs[0]
-                for v in vs[1:]:
+                acc = vs if op == "gather" else vs[0]
+                for v in ([] if op == "gather" else vs[1:]):
                     acc = (acc + v) if op == "sum" else (np.maximum(acc, v) if op == "max" else np.minimum(acc, v))
                 st["res"], st["vals"], st["gen"] = acc, {}, gen + 1
                 st["cv"].notify_all()
@@ -312,9 +312,12 @@ def fpow(a, b):
 def fsum(a):
     """sum(): sequential, in fp32"""
     v = a.nd().reshape(-1, order="F") if isinstance(a, FArr) else np.asarray(a).reshape(-1, order="F")
-    s = F(0.0)
+    if v.dtype.kind == "i":
+        return int(v.sum())
+    K = np.float64 if v.dtype == np.float64 else F
+    s = K(0.0)
     for x in v:
-        s = F(s + x)
+        s = K(s + x)
     return s
 
 
@@ -656,9 +659,13 @@ class Expr:
                 lo = self.p_or()
                 if self.peek() == ":":
                     self.next()
-                    if self.peek() not in (",", ")"):
+                    if self.peek() not in (",", ")", ":"):
                         hi = self.p_or()
-                    args.append(f"slice({lo}, {hi})")
+                    if self.peek() == ":":                             # lo:hi:stride
+                        self.next()
+                        args.append(f"slice({lo}, {hi}, {self.p_or()})")
+                    else:
+                        args.append(f"slice({lo}, {hi})")
                 elif self.peek() == "=":                               # keyword argument (cshift(a, shift=1, dim=2))
                     self.next()
                     args.append(f"{lo.split('.')[-1]}={self.p_or()}")
@@ -809,6 +816,9 @@ class Sub:
             # in Fortran order (Payload).
             a = self.split_dims(st[st.index("(") + 1:st.rindex(")")])
             return self.assign(a[5], f"mpi_xchg({a[0]}, {a[1]}, {a[3]}, {a[4]}, {a[8]}, {a[9]}, {a[2]}, {a[7]})")
+        if st.startswith("call mpi_allgather"):
+            a = self.split_dims(st[st.index("(") + 1:st.rindex(")")])
+            return self.assign(a[3], f"mpi_allgather({a[0]})")
         if st.startswith("call mpi_allreduce"):
             a = self.split_dims(st[st.index("(") + 1:st.rindex(")")])
             return self.assign(a[1], f"mpi_allreduce({a[0]}, {a[2]}, {a[4]})")
@@ -1061,6 +1071,11 @@ class Globals:
         if self.comm is not None:         # one rank: every neighbour is the rank itself
             pay = self.comm.sendrecv(int(self.rank), pay, dest, sendtag, source, recvtag)
         return Payload(pay.data, recvtype if isinstance(recvtype, Subarray) else None)
+
+    def mpi_allgather(self, val):
+        """MPI_Allgather of one value per rank into an array indexed by rank"""
+        vals = [val] if self.comm is None else self.comm.allreduce(int(self.rank), val, "gather")
+        return Payload(np.array(vals))
 
     def mpi_allreduce(self, sendbuf, count, op):
         """MPI_Allreduce(sendbuf, recvbuf, count, type, op, ...): every contribution is logged as it crosses the MPI boundary

@@ -1191,7 +1191,86 @@ def gen_injector():
     np.savez_compressed(os.path.join(OUT, "ref_injector.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G18: the domain decomposition -- the block of allocate_fields (fields.F90:246-330) that splits the box: local sizes with
+#      the remainder on the last rank of an axis, MPI_Allgather of the sizes, cumulative offsets, strides.  The block is cut
+#      out of the routine (which otherwise allocates and parses input) and wrapped in `subroutine decomp`; ranks are threads.
+# ------------------------------------------------------------------------------------------------------------
+DECOMP_CASES = [(2, 1, (23, 17, 1), (3, 2, 1)), (2, 2, (40, 9, 1), (4, 1, 1)), (3, 2, (10, 14, 9), (1, 3, 2)), (3, 1, (8, 12, 12), (1, 2, 2)),
+                (3, 3, (6, 7, 23), (1, 1, 4)), (2, 0, (16, 16, 1), (1, 1, 1))]
+
+
+def gen_decomp():
+    import re
+    out = {}
+    text = src("fields.F90")
+    a = re.search(r"^[ \t]*if \(irestart \.ne\. 1\) then\s*$", text, flags=re.M).start()
+    b = text.index("#ifdef filter2", a)
+    body = text[a:b]
+    assert "mxcum=sum(mxl(i1:i2)-nghost)-(mxl(i2)-nghost)" in body and "lot=iz*mz" in body
+    wrapped = "subroutine decomp()\n\timplicit none\n\tinteger :: i1, i2, j1, j2, k1, k2, error\n" + body + "\nend subroutine decomp\n"
+    gi = GINTS | {"mxcum", "mycum", "mzcum", "mx0", "my0", "mz0", "irestart"}
+    for ci, (dim, order, nglob, sizes) in enumerate(DECOMP_CASES):
+        defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+        sub = R.Sub(wrapped, "decomp", defines=defines, global_arrays={"mxl", "myl", "mzl"}, global_ints=gi).compile()
+        size0 = sizes[0] * sizes[1] * sizes[2]
+        comm = R.Comm(size0) if size0 > 1 else None
+        ng = 5 if order <= 1 else 7
+        ngz = ng if dim == 3 else 5
+        gs = []
+        for rank in range(size0):
+            g = R.Globals(rank=rank, size0=size0, sizex=sizes[0], sizey=sizes[1], sizez=sizes[2], nghost=ng, nghostz=ngz, irestart=0,
+                          mx0=nglob[0] + ng, my0=nglob[1] + ng, mz0=(nglob[2] + ngz if dim == 3 else 1),
+                          mx=0, my=0, mz=1, mxcum=0, mycum=0, mzcum=0, mpi_integer=0, mpi_comm_world=0,
+                          mxl=R.FArr((size0,), np.int64), myl=R.FArr((size0,), np.int64), mzl=R.FArr((size0,), np.int64))
+            g.comm = comm
+            gs.append(g)
+        R.run_ranks([(lambda g=g: sub(g)) for g in gs])
+        key = f"c{ci}"
+        out[key + "_meta"] = np.array([dim, order, *nglob, *sizes], np.int32)
+        out[key + "_ranks"] = np.array([[g.mx, g.my, g.mz, g.mxcum, g.mycum, g.mzcum, g.ix, g.iy, g.iz, g.lot] for g in gs], np.int64)
+        print("decomp", key, dim, order, nglob, sizes, out[key + "_ranks"][:, :6].tolist())
+    np.savez_compressed(os.path.join(OUT, "ref_decomp.npz"), **out)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# G19: who talks to whom -- the neighbour ranks the reference's layer-copy routines address (copy_layrx1_opt /
+#      copy_layry1_opt / copy_layrz1_opt, fieldboundaries.F90:1149-1677): each routine is run on every rank of a grid with
+#      an MPI_SendRecv that only records (dest, source) of the first, "plus"-direction message
+# ------------------------------------------------------------------------------------------------------------
+def gen_neighbours():
+    out = {}
+    fb = src("fieldboundaries.F90")
+
+    class Spy(R.Globals):
+        def mpi_xchg(self, sendbuf, count, dest, sendtag, source, recvtag, sendtype=None, recvtype=None):
+            self.seen.append((int(dest), int(source)))
+            return R.as_payload(sendbuf, count)
+
+    for ci, (dim, sizes) in enumerate([(2, (3, 2, 1)), (2, (4, 1, 1)), (3, (1, 3, 2)), (3, (1, 2, 4)), (3, (1, 1, 1))]):
+        defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
+        subs = [R.Sub(fb, nm, defines=defines, global_arrays=GARR, global_ints=GINTS | {"statsize"}).compile()
+                for nm in ("copy_layrx1_opt", "copy_layry1_opt", "copy_layrz1_opt")]
+        size0 = sizes[0] * sizes[1] * sizes[2]
+        table = np.zeros((size0, 6), np.int32)
+        for rank in range(size0):
+            g = Spy(rank=rank, size0=size0, sizex=sizes[0], sizey=sizes[1], sizez=sizes[2], statsize=5, mpi_comm_world=0, mpi_read=0)
+            a = [R.FArr((4, 4, 4)) for _ in range(3)]
+            for ax, f in enumerate(subs):
+                g.seen = []
+                f(g, *a, 4, 4, 4, 1, 3, 4, 2)
+                if not g.seen:                        # 2D build: copy_layrz1_opt has no exchange
+                    table[rank, 2 * ax], table[rank, 2 * ax + 1] = -1, -1
+                    continue
+                plus, minus = g.seen[0]
+                table[rank, 2 * ax], table[rank, 2 * ax + 1] = minus, plus          # direction order: x-, x+, y-, y+, z-, z+
+        out[f"n{ci}_sizes"] = np.array([dim, *sizes], np.int32)
+        out[f"n{ci}_table"] = table
+        print("neighbours", dim, sizes, table.tolist()[:4])
+    np.savez_compressed(os.path.join(OUT, "ref_neighbours.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq", "loader", "spectrum", "injector"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq", "loader", "spectrum", "injector", "decomp", "neighbours"]
     for w in which:
         globals()["gen_" + w]()

@@ -490,3 +490,38 @@ def test_shock_injector_matches_the_reference_source(case):
             for k in ref.dtype.names:
                 assert np.array_equal(p[k][sl], ref[k][sl]), (rk, k)
     assert (total == 0) == (case == 3)
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_domain_decomposition_matches_the_reference_source(case):
+    """the box-splitting block of allocate_fields (fields.F90:246-330), run by every rank with MPI_Allgather between them:
+    local sizes (remainder on the last rank of an axis), cumulative offsets.  Checked against the oracle's world AND against
+    the product library's host-only tgpu_decompose (no GPU needed for that call)."""
+    import tristan_mp_pu_master_densdecomp_b200 as tg
+    z = load("ref_decomp.npz")
+    key = f"c{case}"
+    dim, order, nx, ny, nz, sx, sy, sz = (int(v) for v in z[key + "_meta"])
+    ref = z[key + "_ranks"]
+    w = T.oracle_world(dim=dim, order=order, n=(nx, ny, nz), sizes=(sx, sy, sz), ppc=0.0, init="none", seed_fields=0)
+    for rk, r in enumerate(w.ranks):
+        want = tuple(int(v) for v in ref[rk, :6])
+        assert (r.mx, r.my, r.mz, r.mxcum, r.mycum, r.mzcum) == want, rk
+        assert tuple(tg.decompose(dim, order, nx, ny, nz, sx, sy, sz, rk)) == want, rk
+
+
+@pytest.mark.parametrize("case", range(5))
+def test_neighbour_ranks_match_the_reference_source(case):
+    """the ranks copy_layrx1_opt / copy_layry1_opt / copy_layrz1_opt (fieldboundaries.F90:1149-1677) send to and receive from,
+    recorded from the reference's text on every rank of a grid, against the product library's host-only tgpu_neighbour and
+    the oracle's orc_neighbour; direction order x-, x+, y-, y+, z-, z+"""
+    import tristan_mp_pu_master_densdecomp_b200 as tg
+    z = load("ref_neighbours.npz")
+    dim, sx, sy, sz = (int(v) for v in z[f"n{case}_sizes"])
+    table = z[f"n{case}_table"]
+    w = T.oracle_world(dim=dim, order=1, n=(4 * sx, 4 * sy, 4 * sz), sizes=(sx, sy, sz), ppc=0.0, init="none", seed_fields=0)
+    for rank in range(sx * sy * sz):
+        for d in range(6):
+            if table[rank, d] < 0:
+                continue                                      # no z exchange in a 2D build
+            assert tg.neighbour(rank, sx, sy, sz, d) == table[rank, d], (rank, d)
+            assert O.lib().orc_neighbour(w.ranks[rank].h, d) == table[rank, d], (rank, d)
