@@ -498,7 +498,11 @@ def statements(text):
         cur += s
         for part in cur.split(";") if ("'" not in cur and '"' not in cur) else [cur]:
             if part.strip():
-                out.append(part.strip().lower())
+                st = part.strip().lower()
+                # kind-suffixed literals: 1.e7_sprec is a default real, 1._dprec a double
+                st = re.sub(r"(?<=[\d.])_sprec\b", "", st)
+                st = re.sub(r"(\d+\.?\d*|\.\d+)(?:e([+-]?\d+))?_dprec\b", lambda m: f"{m.group(1)}d{m.group(2) or 0}", st)
+                out.append(st)
         cur = ""
     return out
 
@@ -517,7 +521,7 @@ def extract_subroutine(text, name):
 # ------------------------------------------------------------------------------------------------------------------
 # expression translation (recursive descent over the Fortran expression grammar)
 # ------------------------------------------------------------------------------------------------------------------
-TOK = re.compile(r"\s*('[^']*'|\d+\.\d*(?:[ed][+-]?\d+)?|\.\d+(?:[ed][+-]?\d+)?|\d+[ed][+-]?\d+|\d+|\.[a-z]+\.|[a-z_]\w*|\*\*|==|/=|<=|>=|[-+*/(),:<>%=])")
+TOK = re.compile(r"\s*('[^']*'|\"[^\"]*\"|\d+\.\d*(?:[ed][+-]?\d+)?|\.\d+(?:[ed][+-]?\d+)?|\d+[ed][+-]?\d+|\d+|\.[a-z]+\.|[a-z_]\w*|\*\*|==|/=|<=|>=|[-+*/(),:<>%=])")
 
 
 def tokenize(s):
@@ -620,7 +624,7 @@ class Expr:
             e = self.p_or()
             self.expect(")")
             r = f"({e})"
-        elif tok.startswith("'"):
+        elif tok[0] in "'\"":
             r = repr(tok[1:-1])
         elif tok == ".true.":
             r = "True"

@@ -1270,7 +1270,34 @@ def gen_neighbours():
     np.savez_compressed(os.path.join(OUT, "ref_neighbours.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G20: the scalars the kernels need -- read_input_particles (particles.F90:189-256): gamma0 from a velocity, the charge
+#      normalisation qe, qi, the rescaled masses, qme, qmi, and the fp32 constants (3/2., 9/8., 2/3., 1/6. ...).  The input
+#      parser calls are stand-ins that hand back the case's values.
+# ------------------------------------------------------------------------------------------------------------
+def gen_scalars():
+    out = {}
+    sub = R.Sub(src("particles.F90"), "read_input_particles", defines={"MPI"}, global_ints=GINTS | {"upsamp_e", "upsamp_i", "maxptl0"}).compile()
+    cases = [dict(ppc0=16., c_omp=10., gamma0=.5, me=1., mi=1., sigma=0.), dict(ppc0=64., c_omp=10., gamma0=.5, me=1., mi=1., sigma=0.),
+             dict(ppc0=4., c_omp=8., gamma0=15., me=1., mi=100., sigma=0.1), dict(ppc0=2., c_omp=5., gamma0=.1, me=1., mi=20., sigma=0.)]
+    names = ("qe", "qi", "qme", "qmi", "me", "mi", "gamma0", "beta", "binit", "three", "two", "thhalf", "nineighth", "one", "threeq", "twoth",
+             "half", "third", "quart", "sixth", "negsixth", "negone")
+    out["names"] = np.array(names)
+    for ci, vals in enumerate(cases):
+        g = R.Globals(c=F(0.45), sigma=F(0), ppc0=F(0), delgam=F(0), me=F(0), mi=F(0), gamma0=F(0), c_omp=F(0), upsamp_e=0, upsamp_i=0)
+
+        def getd(sec, name, default, var, vals=vals):
+            return (sec, name, default, F(vals.get(name, default)))
+        g.inputpar_getd_def = getd
+        g.inputpar_geti_def = lambda sec, name, default, var: (sec, name, default, default)
+        sub(g)
+        out[f"k{ci}_in"] = np.array([vals[k] for k in ("ppc0", "c_omp", "gamma0", "me", "mi", "sigma")], F)
+        out[f"k{ci}_out"] = np.array([getattr(g, nm) for nm in names], F)
+        print("scalars", ci, dict(zip(names[:7], out[f"k{ci}_out"][:7])))
+    np.savez_compressed(os.path.join(OUT, "ref_scalars.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq", "loader", "spectrum", "injector", "decomp", "neighbours"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq", "loader", "spectrum", "injector", "decomp", "neighbours", "scalars"]
     for w in which:
         globals()["gen_" + w]()

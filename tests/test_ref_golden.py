@@ -525,3 +525,25 @@ def test_neighbour_ranks_match_the_reference_source(case):
                 continue                                      # no z exchange in a 2D build
             assert tg.neighbour(rank, sx, sy, sz, d) == table[rank, d], (rank, d)
             assert O.lib().orc_neighbour(w.ranks[rank].h, d) == table[rank, d], (rank, d)
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_charge_normalisation_and_constants_match_the_reference_source(case):
+    """read_input_particles (particles.F90:189-256) from the reference's text: gamma0 from a velocity, qe, qi, qme, qmi and the
+    fp32 constants of the shape functions, against the oracle's orc_charge_normalisation, the product package's
+    charge_normalisation and the constants the golden generators use: BIT-EXACT"""
+    import tristan_mp_pu_master_densdecomp_b200 as tg
+    z = load("ref_scalars.npz")
+    ref = dict(zip((str(n) for n in z["names"]), z[f"k{case}_out"]))
+    ppc0, c_omp, gamma0, me, mi, sigma = (float(v) for v in z[f"k{case}_in"])
+    P = O.make_params(dim=2, order=1, mx0=8, my0=8, ppc0=ppc0, c_omp=c_omp, gamma0=gamma0, me=me, mi=mi)
+    for k in ("qe", "qi", "qme", "qmi"):
+        assert np.float32(getattr(P, k)) == ref[k], k
+    got = tg.charge_normalisation(0.45, c_omp, ppc0, gamma0, me, mi)
+    assert tuple(np.float32(v) for v in got) == (ref["qe"], ref["qi"], ref["qme"], ref["qmi"])
+    F = np.float32
+    consts = dict(three=F(3.), two=F(2.), thhalf=F(F(3) / F(2.)), nineighth=F(F(9) / F(8.)), one=F(1.), threeq=F(F(3) / F(4.)),
+                  twoth=F(F(2) / F(3.)), half=F(F(1) / F(2.)), third=F(F(1) / F(3.)), quart=F(F(1) / F(4.)), sixth=F(F(1) / F(6.)),
+                  negsixth=F(F(-1) / F(6.)), negone=F(-1.))
+    for k, v in consts.items():
+        assert ref[k] == v, k
