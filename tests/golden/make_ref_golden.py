@@ -723,7 +723,12 @@ LAP_CASES = [  # dim order nglob       sizes      periodic   laps highorder shoc
     (3, 3, (8, 6, 6), (1, 1, 1), (1, 1, 1), 2, 1, 0, 2),
     # the `filter2` build (3D only, tristanmainloop.F90:213-229): one rank (also run on the GPU) and 1x2x2
     (3, 2, (8, 8, 8), (1, 1, 1), (1, 1, 1), 3, 0, 0, 2, 2),
-    (3, 1, (6, 12, 12), (1, 2, 2), (1, 1, 1), 2, 0, 0, 1, 2)]
+    (3, 1, (6, 12, 12), (1, 2, 2), (1, 1, 1), 2, 0, 0, 1, 2),
+    # remaining order x dimension builds and radiating axes that are split over ranks (oracle side only)
+    (2, 3, (12, 10, 1), (1, 1, 1), (1, 1, 1), 3, 0, 0, 2),
+    (2, 0, (12, 10, 1), (1, 1, 1), (1, 0, 1), 3, 0, 0, 2),
+    (3, 2, (6, 12, 6), (1, 2, 1), (1, 0, 1), 3, 0, 0, 1),
+    (2, 2, (16, 12, 1), (2, 2, 1), (0, 0, 1), 3, 0, 0, 2)]
 
 
 def gen_lap():
