@@ -1065,6 +1065,7 @@ class Globals:
     """module variables of the reference (m_fields, m_particles, ...) as attributes"""
 
     comm = None
+    sprec, dprec = 4, 8                  # the kind parameters of the reference (real(x, sprec), real(x, dprec))
 
     def __init__(self, **kw):
         for k, v in kw.items():

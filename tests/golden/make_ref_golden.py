@@ -148,40 +148,46 @@ def gen_mover():
     out = {}
     text = src("particles_movedeposit.F90")
     names = {0: "mover", 1: "mover_1ord", 2: "mover_2ord", 3: "mover_3ord"}
+    EXT = tuple(F(v) for v in (0.01, -0.02, 0.015, 0.05, -0.03, 0.04))       # ex, ey, ez, bx, by, bz of get_external_fields
     for dim in (2, 3):
         for order in (0, 1, 2, 3):
-            defines = {"MPI"} | ({"twoD"} if dim == 2 else set())
-            sub = R.Sub(text, names[order], defines=defines, global_arrays=GARR, global_ints=GINTS).compile()
-            n = (9, 8, 7)
-            rng = np.random.default_rng(300 + 10 * dim + order)
-            g = field_globals(dim, order, n, (1, 1, 1), rng)
-            ng, ngz, mx, my, mz = grid(dim, order, n)
-            npart = 64
-            p = np.zeros(npart, PDT)
-            lo = ng // 2 + 1
-            p["x"] = (lo + rng.random(npart) * n[0]).astype(F)
-            p["y"] = (lo + rng.random(npart) * n[1]).astype(F)
-            p["z"] = ((ngz // 2 + 1) + rng.random(npart) * n[2]).astype(F) if dim == 3 else (3 + rng.random(npart)).astype(F)
-            # particles exactly on nodes and on half cells: the branch points of the shapes and of quirk Q1
-            p["x"][:4] = np.array([lo + 2, lo + 2.5, lo + 3, lo + 4.5], F)
-            p["y"][2:6] = np.array([lo + 1, lo + 1.5, lo + 2, lo + 3.5], F)
-            for k in "uvw":
-                p[k] = (rng.standard_normal(npart) * 0.4).astype(F)
-            p["ch"] = 1.0
-            g.p = R.RecArr(p)
-            g.external_fields = False
-            g.delgam = F(1e-2)
-            g.qme_abs = F(1.0)
-            key = f"m{dim}o{order}"
-            out[key + "_meta"] = np.array([dim, order, 1, 1, 1, *n], np.int32)
-            for a, nm in enumerate(("ex", "ey", "ez", "bx", "by", "bz")):
-                out[f"{key}_f{a}"] = c_order(getattr(g, nm))
-            out[key + "_pin"] = p.copy()
-            qm = F(-0.8)
-            out[key + "_qm"] = np.array([qm], F)
-            sub(g, 1, npart, qm)
-            out[key + "_pout"] = p.copy()
-            print("mover", key, "mean |dx| =", float(np.abs(out[key + "_pout"]["x"] - out[key + "_pin"]["x"]).mean()))
+            # variants: "" = Boris; "v" = the `vay` build (Vay 2008 pusher); "x" = external_fields through get_external_fields
+            for variant in ("", "v", "x"):
+                defines = {"MPI"} | ({"twoD"} if dim == 2 else set()) | ({"vay"} if variant == "v" else set())
+                sub = R.Sub(text, names[order], defines=defines, global_arrays=GARR, global_ints=GINTS).compile()
+                n = (9, 8, 7)
+                rng = np.random.default_rng(300 + 10 * dim + order)
+                g = field_globals(dim, order, n, (1, 1, 1), rng)
+                ng, ngz, mx, my, mz = grid(dim, order, n)
+                npart = 64
+                p = np.zeros(npart, PDT)
+                lo = ng // 2 + 1
+                p["x"] = (lo + rng.random(npart) * n[0]).astype(F)
+                p["y"] = (lo + rng.random(npart) * n[1]).astype(F)
+                p["z"] = ((ngz // 2 + 1) + rng.random(npart) * n[2]).astype(F) if dim == 3 else (3 + rng.random(npart)).astype(F)
+                # particles exactly on nodes and on half cells: the branch points of the shapes and of quirk Q1
+                p["x"][:4] = np.array([lo + 2, lo + 2.5, lo + 3, lo + 4.5], F)
+                p["y"][2:6] = np.array([lo + 1, lo + 1.5, lo + 2, lo + 3.5], F)
+                for k in "uvw":
+                    p[k] = (rng.standard_normal(npart) * 0.4).astype(F)
+                p["ch"] = 1.0
+                g.p = R.RecArr(p)
+                g.external_fields = variant == "x"
+                # the problem's get_external_fields(x, y, z, ex, ey, ez, bx, by, bz [, qm, n]): a uniform field here
+                g.get_external_fields = lambda *a: tuple(a[:3]) + EXT + tuple(a[9:])
+                g.delgam = F(1e-2)
+                g.qme_abs = F(1.0)
+                key = f"m{dim}o{order}{variant}"
+                out[key + "_meta"] = np.array([dim, order, 1, 1, 1, *n], np.int32)
+                for a, nm in enumerate(("ex", "ey", "ez", "bx", "by", "bz")):
+                    out[f"{key}_f{a}"] = c_order(getattr(g, nm))
+                out[key + "_pin"] = p.copy()
+                qm = F(-0.8)
+                out[key + "_qm"] = np.array([qm], F)
+                out[key + "_ext"] = np.array(EXT, F)
+                sub(g, 1, npart, qm)
+                out[key + "_pout"] = p.copy()
+                print("mover", key, "mean |dx| =", float(np.abs(out[key + "_pout"]["x"] - out[key + "_pin"]["x"]).mean()))
     np.savez_compressed(os.path.join(OUT, "ref_mover.npz"), **out)
 
 

@@ -66,12 +66,20 @@ def test_yee_solver_matches_the_reference_source(case):
 
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("order", [0, 1, 2, 3])
-def test_movers_match_the_reference_source(dim, order):
+@pytest.mark.parametrize("variant", ["", "v", "x"], ids=["boris", "vay", "external-fields"])
+def test_movers_match_the_reference_source(dim, order, variant):
     """mover / mover_{1,2,3}ord (particles_movedeposit.F90:98-1271): node-centring by cshift, shape weights (with the loop-range
-    quirk Q1 of mover_2ord), gather, Boris push, position advance -- 64 particles incl. some on nodes and half cells"""
+    quirk Q1 of mover_2ord), gather, Boris push, position advance -- 64 particles incl. some on nodes and half cells.
+    Variants: the `vay` build (Vay 2008 pusher, :273-300 and its copies) and external_fields (a uniform
+    get_external_fields, :250-262, 518-530, ...): BIT-EXACT"""
     z = load("ref_mover.npz")
-    key = f"m{dim}o{order}"
-    w = _world_from_meta(z[key + "_meta"])
+    key = f"m{dim}o{order}{variant}"
+    kw = {}
+    if variant == "v":
+        kw["pusher"] = 1
+    if variant == "x":
+        kw["ext"] = [float(v) for v in z[key + "_ext"]]
+    w = _world_from_meta(z[key + "_meta"], **kw)
     r = w.ranks[0]
     for a in range(6):
         r.arr(a)[...] = z[f"{key}_f{a}"]
@@ -82,10 +90,8 @@ def test_movers_match_the_reference_source(dim, order):
         p[k][:n] = pin[k]
     r.set_counts(n, 0)
     r.call("mover_range", 1, n, C.c_float(float(z[key + "_qm"][0])))
-    worst = 0.0
     for k in ("x", "y", "z", "u", "v", "w"):
         d = np.abs(p[k][:n].astype(np.float64) - pout[k].astype(np.float64))
-        worst = max(worst, float(d.max()))
         assert np.array_equal(p[k][:n], pout[k]), f"{key} {k}: {int((d > 0).sum())} of {n} differ, max |diff| {d.max():.3e}"
 
 
