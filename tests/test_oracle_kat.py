@@ -1,5 +1,6 @@
-"""Known-answer tests that pin the CPU oracle (the reference ships no golden vectors; see oracle/pic_oracle.h).
-Each test checks a property the reference algorithm must have, derived independently of the oracle's code."""
+"""Known-answer tests of the CPU oracle: properties the reference algorithm must have, derived independently of the
+oracle's code (physics and arithmetic identities).  They complement tests/test_ref_golden.py, where the oracle is held
+bit-exact against the reference's own source text; see oracle/pic_oracle.h."""
 import ctypes as C
 
 import numpy as np
