@@ -15,6 +15,7 @@ G1-G9 run single routines on one rank (or on one rank of a split box); G10-G12 r
 as a rendezvous, up to whole laps of `mainloop` itself.  Seeds are fixed: re-running reproduces the committed files.
 """
 import os
+import re
 import sys
 
 import numpy as np
@@ -1308,7 +1309,27 @@ def gen_scalars():
     np.savez_compressed(os.path.join(OUT, "ref_scalars.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G21: the order of the calls in one lap of `mainloop` (tristanmainloop.F90:107-330), read from the text for the 2D build
+#      and for the 3D filter2 build: what host/tristan_mainloop.cpp and INTEGRATION.md section 4 must reproduce
+# ------------------------------------------------------------------------------------------------------------
+def gen_calllist():
+    out = {}
+    text = src("tristanmainloop.F90")
+    for tag, defines in (("2d", {"MPI", "twoD", "dd1"}), ("3d", {"MPI", "dd2"}), ("3d_filter2", {"MPI", "dd2", "filter2"})):
+        st = R.statements(R.extract_subroutine(R.preprocess(text, defines), "mainloop"))
+        i0 = next(i for i, s_ in enumerate(st) if s_.startswith("do lap"))
+        calls = []
+        for s_ in st[i0:]:
+            m = re.search(r"\bcall\s+([a-z_]\w*)", s_)
+            if m and m.group(1) not in ("timer", "mpi_barrier"):
+                calls.append(m.group(1))
+        out[tag] = np.array(calls)
+        print("calllist", tag, len(calls), calls[:8], "...")
+    np.savez_compressed(os.path.join(OUT, "ref_calllist.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq", "loader", "spectrum", "injector", "decomp", "neighbours", "scalars"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq", "loader", "spectrum", "injector", "decomp", "neighbours", "scalars", "calllist"]
     for w in which:
         globals()["gen_" + w]()

@@ -553,3 +553,29 @@ def test_charge_normalisation_and_constants_match_the_reference_source(case):
                   negsixth=F(F(-1) / F(6.)), negone=F(-1.))
     for k, v in consts.items():
         assert ref[k] == v, k
+
+
+def test_host_driver_call_order_is_the_reference_mainloops():
+    """host/tristan_mainloop.cpp ("calls" mode) and the Fortran swap of INTEGRATION.md section 4(a) must issue the hot-path
+    procedures in the order of `mainloop` (tristanmainloop.F90:107-330; list read from the reference's text for the 3D
+    filter2 build).  Procedures outside the path (diagnostics, domain rebalancing, the problem's injector and hooks -- the
+    hooks are installed once with tgpu_set_user_hooks) are dropped from the reference list; its two filter calls are the one
+    tgpu_apply_filter."""
+    import re
+    ref = [str(v) for v in load("ref_calllist.npz")["3d_filter2"]]
+    rename = {"advance_bhalfstep": "advance_b_halfstep", "advance_efield": "advance_e_fullstep", "apply_filter2_opt": "apply_filter",
+              "apply_filter1_opt": None}
+    outside = {"diagnostics", "field_bc_user", "particle_bc_user", "inject_particles", "check_overflow", "enlarge_domain", "redist_x_domain",
+               "redist_y_domain", "shift_domain", "redist_z_domain", "print_timers", "pause_simulation"}
+    want = [rename.get(c, c) for c in ref if c not in outside]
+    want = [c for c in want if c is not None]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "host", "tristan_mainloop.cpp")).read()
+    body = src[src.index('if (mode == "calls")'):src.index("CALL(tgpu_step, gpu, 1)")]
+    got = re.findall(r"CALL\(tgpu_(\w+), gpu\)", body)
+    assert got == want, (got, want)
+    # the Fortran side of INTEGRATION.md 4(a): same order
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    sec = md[md.index("## 4."):md.index("## 5.")]
+    calls_md = re.findall(r"tgpu_(\w+)\(gpu\)", sec.split("#else")[0])
+    assert calls_md == want, (calls_md, want)
