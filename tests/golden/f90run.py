@@ -507,6 +507,22 @@ def statements(text):
     return out
 
 
+def module_kind(text, name):
+    """kind of a module variable, from its declaration in the specification part of the (preprocessed) module text:
+    'int' | 'int8' | 'real' | 'real8' | 'logical'"""
+    head = text.lower().split("\ncontains")[0]
+    probe = Sub.__new__(Sub)
+    probe.local, probe.alias, probe.optional = {}, set(), set()
+    for st in statements(head):
+        try:
+            probe.declare(st)
+        except SyntaxError:
+            continue
+    if name.lower() not in probe.local:
+        raise KeyError(name)
+    return "int8" if name.lower() in getattr(probe, "int8", set()) else probe.local[name.lower()][0]
+
+
 def extract_subroutine(text, name):
     m = re.search(r"^[ \t]*(?:(?:integer|real|logical)(?:\([a-z0-9_]*\))?\s+)?(subroutine|function)\s+" + name + r"\s*(\(|$)", text, flags=re.I | re.M)
     if not m:
@@ -751,6 +767,7 @@ class Sub:
         kind = {"integer": "int", "real": "real", "logical": "logical", "double precision": "real8"}[base]
         if base == "real" and re.sub(r"\s|kind=", "", m.group(2) or "") in ("(dprec)", "(8)"):
             kind = "real8"
+        wide_int = base == "integer" and re.sub(r"\s|kind=", "", m.group(2) or "") == "(8)"
         dims = None
         dm = re.search(r"dimension\s*\(([^)]*(?:\([^)]*\)[^)]*)*)\)", attrs)
         if dm:
@@ -776,6 +793,8 @@ class Sub:
             if em.group(1) in self.alias:
                 continue
             self.local[em.group(1)] = (kind, em.group(2) or dims)
+            if wide_int:
+                self.int8 = getattr(self, "int8", set()) | {em.group(1)}
             if "optional" in attrs:
                 self.optional.add(em.group(1))
         return True
@@ -874,6 +893,19 @@ class Sub:
             return "continue"
         if st == "exit":
             return "break"
+        m = re.match(r"write\s*\(\s*(\d+)\s*\)\s*(.+)$", st)
+        if m:                                                          # unformatted sequential WRITE(unit) io-list
+            items = []
+            for it in self.split_dims(m.group(2)):
+                it = it.strip()
+                parts = self.split_dims(it[1:-1]) if it.startswith("(") and it.endswith(")") else []
+                if len(parts) >= 3 and re.match(r"[a-z_]\w*\s*=", parts[-2]):          # implied DO: (expr..., n=lo,hi)
+                    var, lo = (v.strip() for v in parts[-2].split("=", 1))
+                    exprs = ", ".join(self.ex(e) for e in parts[:-2])
+                    items.append(f"[[{exprs}] for {self.ref(var)} in frange({self.ex(lo)}, {self.ex(parts[-1])})]")
+                else:
+                    items.append(self.ex(it))
+            return f"_g.fwrite({m.group(1)}, [{', '.join(items)}])"
         if st.startswith("print") or st.startswith("write") or st.startswith("stop"):
             return "pass"
         m = re.match(r"go\s*to\s+(\d+)$", st)
@@ -1076,6 +1108,29 @@ class Globals:
         if self.comm is not None:         # one rank: every neighbour is the rank itself
             pay = self.comm.sendrecv(int(self.rank), pay, dest, sendtag, source, recvtag)
         return Payload(pay.data, recvtype if isinstance(recvtype, Subarray) else None)
+
+    def fwrite(self, unit, items):
+        """one unformatted sequential record as gfortran lays it out: 4-byte length, the items back to back in their own
+        kinds (default integer and real 4 bytes, double precision 8, arrays in storage order), 4-byte length"""
+        def enc(v):
+            if isinstance(v, (list, tuple)):
+                return b"".join(enc(x) for x in v)
+            if isinstance(v, FArr):
+                return np.ascontiguousarray(v.flat).tobytes()
+            if isinstance(v, (bool, np.bool_)):
+                return np.int32(bool(v)).tobytes()
+            if isinstance(v, (int, np.integer)):
+                return np.int32(v).tobytes()
+            if isinstance(v, np.float64):
+                return v.tobytes()
+            if isinstance(v, (np.float32, float)):
+                return np.float32(v).tobytes()
+            raise TypeError(f"cannot write {type(v)}")
+        body = enc(items)
+        mark = np.int32(len(body)).tobytes()
+        if not hasattr(self, "units"):
+            self.units = {}
+        self.units.setdefault(int(unit), []).append(mark + body + mark)
 
     def mpi_allgather(self, val):
         """MPI_Allgather of one value per rank into an array indexed by rank"""

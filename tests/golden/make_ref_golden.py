@@ -1329,7 +1329,57 @@ def gen_calllist():
     np.savez_compressed(os.path.join(OUT, "ref_calllist.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G22: the restart dump -- the two unformatted WRITE statements of output.F90:2194-2222 (restflds.*, restprtl.*), executed
+#      from the text; the kind of every item comes from its declaration in the module headers (fields.F90, particles.F90,
+#      aux.F90).  The byte streams are the golden; the package's restart.py must write exactly these and read them back.
+# ------------------------------------------------------------------------------------------------------------
+def gen_restart():
+    out = {}
+    text = R.preprocess(src("output.F90"), {"MPI"})            # LOCALRESTART (an older dump without walloc, :2112-2141) is not defined
+    w7 = re.search(r"^[ \t]*write\(7\)mx,my,mz.*?(?=^[ \t]*close\(7\))", text, flags=re.M | re.S).group(0)
+    w8 = re.search(r"^[ \t]*write\(8\)ions,lecs.*?(?=^[ \t]*close\(8\))", text, flags=re.M | re.S).group(0)
+    wrapped = "subroutine dump()\n\timplicit none\n\tinteger :: n\n" + w7 + "\n" + w8 + "\nend subroutine dump\n"
+    heads = {f: R.preprocess(src(f), {"MPI"}) for f in ("fields.F90", "particles.F90", "aux.F90")}
+
+    def kind_of(name):
+        for t in heads.values():
+            try:
+                return R.module_kind(t, name)
+            except KeyError:
+                pass
+        raise KeyError(name)
+    cast = {"int": int, "real": F, "real8": np.float64}
+    rng = np.random.default_rng(1700)
+    for ci, (dim, n) in enumerate([(2, (6, 5, 1)), (3, (5, 4, 3))]):
+        ng, ngz, mx, my, mz = grid(dim, 2, n)
+        vals = dict(mx=mx, my=my, mz=mz, dseed=123457.0 * 16807 % 2147483647, lap=1234 + ci, xinject=3.25, xinject2=mx - 2.5, xinject3=0.125,
+                    leftwall=15.5, walloc=20.75, ions=7 + ci, lecs=5, maxptl=40, maxhlf=20, totalpartnum=99 + ci)
+        g = R.Globals(**{k: cast[kind_of(k)](v) for k, v in vals.items()})
+        sub = R.Sub(wrapped, "dump", defines={"MPI"}, global_arrays=GARR, global_ints={k for k in vals if kind_of(k) == "int"}).compile()
+        for nm in ("ex", "ey", "ez", "bx", "by", "bz"):
+            a = R.FArr((mx, my, mz))
+            a.flat[:] = rng.standard_normal(a.flat.size).astype(F)
+            setattr(g, nm, a)
+        p = np.zeros(vals["maxptl"], PDT)
+        for k in PDT.names:
+            p[k] = (rng.standard_normal(p.size) * 3).astype(PDT[k]) if PDT[k].kind == "f" else rng.integers(-50, 50, p.size)
+        g.p = R.RecArr(p)
+        sub(g)
+        key = f"t{ci}"
+        out[key + "_kinds"] = np.array([f"{k}:{kind_of(k)}" for k in vals])
+        out[key + "_scalars"] = np.array([float(v) for v in vals.values()], np.float64)
+        out[key + "_names"] = np.array(list(vals))
+        for a, nm in enumerate(("ex", "ey", "ez", "bx", "by", "bz")):
+            out[f"{key}_f{a}"] = c_order(getattr(g, nm))
+        out[key + "_p"] = p.copy()
+        out[key + "_restflds"] = np.frombuffer(b"".join(g.units[7]), np.uint8)
+        out[key + "_restprtl"] = np.frombuffer(b"".join(g.units[8]), np.uint8)
+        print("restart", key, "restflds", out[key + "_restflds"].size, "bytes, restprtl", out[key + "_restprtl"].size, "bytes;", list(out[key + "_kinds"]))
+    np.savez_compressed(os.path.join(OUT, "ref_restart.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq", "loader", "spectrum", "injector", "decomp", "neighbours", "scalars", "calllist"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq", "loader", "spectrum", "injector", "decomp", "neighbours", "scalars", "calllist", "restart"]
     for w in which:
         globals()["gen_" + w]()

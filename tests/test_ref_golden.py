@@ -579,3 +579,34 @@ def test_host_driver_call_order_is_the_reference_mainloops():
     sec = md[md.index("## 4."):md.index("## 5.")]
     calls_md = re.findall(r"tgpu_(\w+)\(gpu\)", sec.split("#else")[0])
     assert calls_md == want, (calls_md, want)
+
+
+@pytest.mark.parametrize("case", range(2))
+def test_restart_dumps_are_byte_identical_to_the_reference_writes(case, tmp_path):
+    """The two unformatted WRITE statements of output.F90:2194-2222 executed from the reference's text, every item in the kind
+    its module declaration gives it (3 f64 + f32 + f64 scalar tail included): the package's restart.write_fields /
+    write_particles must produce exactly those bytes, and read_fields / read_particles must read the reference's bytes back."""
+    from tristan_mp_pu_master_densdecomp_b200 import restart
+    z = load("ref_restart.npz")
+    key = f"t{case}"
+    v = dict(zip((str(n) for n in z[key + "_names"]), z[key + "_scalars"]))
+    fields = [z[f"{key}_f{a}"] for a in range(6)]
+    p = z[key + "_p"]
+    fld, prt = str(tmp_path / "restflds.d"), str(tmp_path / "restprtl.d")
+    restart.write_fields(fld, fields, dseed=v["dseed"], lap=int(v["lap"]), xinject=v["xinject"], xinject2=v["xinject2"], xinject3=v["xinject3"],
+                         leftwall=v["leftwall"], walloc=v["walloc"])
+    restart.write_particles(prt, p, int(v["ions"]), int(v["lecs"]), int(v["maxptl"]), totalpartnum=int(v["totalpartnum"]))
+    assert open(fld, "rb").read() == z[key + "_restflds"].tobytes()
+    assert open(prt, "rb").read() == z[key + "_restprtl"].tobytes()
+    # and the reader on the reference's own bytes
+    open(fld, "wb").write(z[key + "_restflds"].tobytes()); open(prt, "wb").write(z[key + "_restprtl"].tobytes())
+    got, scal = restart.read_fields(fld)
+    for a in range(6):
+        assert np.array_equal(got[a], fields[a])
+    assert (scal["dseed"], scal["lap"], scal["xinject"], scal["xinject2"], scal["xinject3"], scal["walloc"]) == \
+        (v["dseed"], int(v["lap"]), v["xinject"], v["xinject2"], v["xinject3"], v["walloc"])
+    assert np.float32(scal["leftwall"]) == np.float32(v["leftwall"])
+    q, ions, lecs, hdr = restart.read_particles(prt)
+    maxhlf = int(v["maxhlf"])
+    assert (ions, lecs, hdr["totalpartnum"]) == (int(v["ions"]), int(v["lecs"]), int(v["totalpartnum"]))
+    assert np.array_equal(q[:ions], p[:ions]) and np.array_equal(q[maxhlf:maxhlf + lecs], p[maxhlf:maxhlf + lecs])
