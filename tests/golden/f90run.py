@@ -14,7 +14,8 @@ expressions, array sections, do (local or module loop variable) / do while / if-
 of the path (an unconditional forward skip to `N continue`; `go to N` where `N continue` closes the loop = cycle), call (to
 other translated routines or to Python stand-ins), derived-type components (p(n)%x) and element assignment (tempp(j) = p(n)),
 integer arrays, real(dprec) / double precision entities and d-exponent literals, DATA, optional arguments with present(),
-select case on strings, where / elsewhere, cycle / exit, allocate, the intrinsics aint int real dble min max abs sqrt sum cshift mod
+select case on strings, where / elsewhere, cycle / exit, allocate, unformatted sequential READ / WRITE with implied DO (records
+framed as gfortran frames them), the intrinsics aint int real dble min max abs sqrt sum cshift mod
 dmod modulo sign ceiling nint floor and exp log log10 cos sin atan tan ** (these through glibc's libm, float or double entry
 point by operand kind).  Scalar actual arguments of a `call` receive the callee's final dummy values (by-reference semantics);
 functions that update an argument inside an expression (random(dseed)) work through `alias_globals`.
@@ -255,6 +256,39 @@ def run_ranks(fns):
         t.join()
     if err:
         raise err[0]
+
+
+class RecordReader:
+    """READ(unit) io-list on one unformatted record: items are taken in order, each in the kind of its target; reading past
+    the end of the record is the run-time error it is in Fortran, reading less than the record holds is allowed"""
+    KIND = {"int": ("<i4", int), "real": ("<f4", F), "real8": ("<f8", np.float64), "logical": ("<i4", bool)}
+
+    def __init__(self, rec):
+        n = int(np.frombuffer(rec[:4], "<i4")[0])
+        if len(rec) != n + 8 or rec[-4:] != rec[:4]:
+            raise IOError("bad record markers")
+        self.b, self.pos = rec[4:-4], 0
+
+    def take(self, dt):
+        dt = np.dtype(dt)
+        if self.pos + dt.itemsize > len(self.b):
+            raise IOError(f"end of record: wanted {dt.itemsize} bytes at offset {self.pos} of {len(self.b)}")
+        v = np.frombuffer(self.b, dt, 1, self.pos)[0]
+        self.pos += dt.itemsize
+        return v
+
+    def scalar(self, kind):
+        dt, cast = self.KIND[kind]
+        return cast(self.take(dt))
+
+    def elem(self, arr, idx):
+        arr[idx if len(idx) > 1 else idx[0]] = self.take(arr.flat.dtype.newbyteorder("<"))
+
+    def comp(self, recarr, i, name):
+        recarr.a[name][int(i) - 1] = self.take(recarr.a.dtype[name].newbyteorder("<"))
+
+    def close(self):
+        self.left = len(self.b) - self.pos
 
 
 class Record:
@@ -714,7 +748,7 @@ class Expr:
 # statement translation
 # ------------------------------------------------------------------------------------------------------------------
 class Sub:
-    def __init__(self, source, name, defines=(), global_arrays=(), global_ints=(), alias_globals=()):
+    def __init__(self, source, name, defines=(), global_arrays=(), global_ints=(), alias_globals=(), global_kinds=None):
         """alias_globals: dummy arguments that every caller binds to the module variable of the same name (`dseed`): they are
         read and written as that module variable, which gives functions called inside expressions -- random(dseed) -- the
         by-reference update a plain Python argument cannot have."""
@@ -722,6 +756,7 @@ class Sub:
         self.local = {}                  # name -> ("int" | "real" | "real8" | "logical", dims or None)
         self.args = []
         self.alias = {a.lower() for a in alias_globals}
+        self.global_kinds = dict(global_kinds or {})      # module scalars that are not default real: name -> kind (for READ)
         self.optional = set()
         self.data_inits = []
         self.global_arrays = {a.lower() for a in global_arrays}
@@ -893,6 +928,35 @@ class Sub:
             return "continue"
         if st == "exit":
             return "break"
+        m = re.match(r"read\s*\(\s*(\d+)\s*\)\s*(.+)$", st)
+        if m:                                                          # unformatted sequential READ(unit) io-list
+            lines = [f"_rd = _g.fread({m.group(1)})"]
+
+            def target(t, depth):
+                t = t.strip()
+                pad = "    " * depth
+                parts = self.split_dims(t[1:-1]) if t.startswith("(") and t.endswith(")") else []
+                if len(parts) >= 3 and re.match(r"[a-z_]\w*\s*=", parts[-2]):          # implied DO, possibly nested
+                    var, lo = (v.strip() for v in parts[-2].split("=", 1))
+                    lines.append(f"{pad}for {self.ref(var)} in frange({self.ex(lo)}, {self.ex(parts[-1])}):")
+                    for inner in parts[:-2]:
+                        target(inner, depth + 1)
+                    return
+                mc = re.fullmatch(r"([a-z_]\w*)\s*\((.*)\)\s*%\s*([a-z_]\w*)", t)
+                if mc:
+                    lines.append(f"{pad}_rd.comp({self.ref(mc.group(1))}, {self.ex(mc.group(2))}, {mc.group(3)!r})")
+                    return
+                ma = re.fullmatch(r"([a-z_]\w*)\s*\((.*)\)", t)
+                if ma and self.is_array(ma.group(1)):
+                    idx = ", ".join(self.ex(e) for e in self.split_dims(ma.group(2)))
+                    lines.append(f"{pad}_rd.elem({self.ref(ma.group(1))}, ({idx},))")
+                    return
+                k = self.kind(t) or self.global_kinds.get(t, "real")
+                lines.append(f"{pad}{self.ref(t)} = _rd.scalar({k!r})")
+            for it in self.split_dims(m.group(2)):
+                target(it, 0)
+            lines.append("_rd.close()")
+            return "\n".join(lines)
         m = re.match(r"write\s*\(\s*(\d+)\s*\)\s*(.+)$", st)
         if m:                                                          # unformatted sequential WRITE(unit) io-list
             items = []
@@ -906,7 +970,7 @@ class Sub:
                 else:
                     items.append(self.ex(it))
             return f"_g.fwrite({m.group(1)}, [{', '.join(items)}])"
-        if st.startswith("print") or st.startswith("write") or st.startswith("stop"):
+        if st.startswith("print") or st.startswith("write") or st.startswith("stop") or re.match(r"(open|close|rewind)\b", st):
             return "pass"
         m = re.match(r"go\s*to\s+(\d+)$", st)
         if m:
@@ -1108,6 +1172,17 @@ class Globals:
         if self.comm is not None:         # one rank: every neighbour is the rank itself
             pay = self.comm.sendrecv(int(self.rank), pay, dest, sendtag, source, recvtag)
         return Payload(pay.data, recvtype if isinstance(recvtype, Subarray) else None)
+
+    def fread(self, unit):
+        """the next unformatted record of `unit` (self.units[unit]: list of marker-framed records) as a reader"""
+        if not hasattr(self, "_rpos"):
+            self._rpos = {}
+        i = self._rpos.get(int(unit), 0)
+        self._rpos[int(unit)] = i + 1
+        if not hasattr(self, "readers"):
+            self.readers = {}
+        self.readers[int(unit)] = RecordReader(self.units[int(unit)][i])     # kept: .left = bytes the READ did not consume
+        return self.readers[int(unit)]
 
     def fwrite(self, unit, items):
         """one unformatted sequential record as gfortran lays it out: 4-byte length, the items back to back in their own

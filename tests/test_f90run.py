@@ -374,3 +374,53 @@ def test_mpi_allreduce_between_ranks_and_its_log():
         assert g.r1 == F(10.0)
         assert list(g.hin.flat) == [6, 6, 6, 6]
         assert float(g.allreduce_log[0]) == 10.0 + rk and list(g.allreduce_log[1]) == [rk + 1] * 4
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("TRISTAN_REFERENCE", "/root/reference")), reason="reference checkout not present")
+def test_the_references_restart_reader_accepts_files_written_by_the_package(tmp_path):
+    """in the build container: restart() of code/restart.F90:209-253, run from its text, reads restflds / restprtl files that
+    tristan_mp_pu_master_densdecomp_b200.restart wrote -- all items, no end-of-record, nothing left over"""
+    from tristan_mp_pu_master_densdecomp_b200 import restart
+    ref = os.environ.get("TRISTAN_REFERENCE", "/root/reference")
+    heads = {f: R.preprocess(open(os.path.join(ref, "code", f)).read(), {"MPI"}) for f in ("fields.F90", "particles.F90", "aux.F90")}
+
+    def kind_of(name):
+        for t in heads.values():
+            try:
+                return R.module_kind(t, name)
+            except KeyError:
+                pass
+        return "real"
+    names = ("mxrest", "myrest", "mzrest", "dseed", "lapst", "xinject", "xinject2", "xinject3", "leftwall", "walloc", "totalpartnum")
+    kinds = {n: kind_of(n) for n in names}
+    assert kinds["dseed"] == kinds["xinject"] == kinds["walloc"] == "real8" and kinds["leftwall"] == "real"
+    rng = np.random.default_rng(5)
+    mx, my, mz, maxptl, ions, lecs = 7, 6, 5, 40, 9, 6
+    fields = [rng.standard_normal((mz, my, mx)).astype(F) for _ in range(6)]
+    p = np.zeros(maxptl, restart.PARTICLE_DTYPE)
+    for k in p.dtype.names:
+        p[k] = (rng.standard_normal(maxptl) * 3).astype(p.dtype[k]) if p.dtype[k].kind == "f" else rng.integers(-50, 50, maxptl)
+    fld, prt = str(tmp_path / "restflds.d"), str(tmp_path / "restprtl.d")
+    restart.write_fields(fld, fields, dseed=987654321.0, lap=77, xinject=3.5, xinject2=101.25, xinject3=0.5, leftwall=15.0, walloc=20.125)
+    restart.write_particles(prt, p, ions, lecs, maxptl, totalpartnum=4242)
+    text = open(os.path.join(ref, "code", "restart.F90")).read()
+    ints = {"ions", "lecs", "maxptl", "maxhlf", "maxptl0", "size0", "rank", "debug", "mpi_status_size"} | {n for n, k in kinds.items() if k == "int"}
+    sub = R.Sub(text, "restart", defines={"MPI"}, global_arrays={"ex", "ey", "ez", "bx", "by", "bz", "p"}, global_ints=ints,
+                global_kinds=kinds).compile()
+    g = R.Globals(rank=0, size0=1, debug=False, maxptl0=maxptl, maxptl=0, maxhlf=0, ions=0, lecs=0, mpi_status_size=5,
+                  frestartfldlap="", frestartprtlap="", mpi_comm_world=0, mpi_integer=0,
+                  **{nm: R.FArr((mx, my, mz)) for nm in ("ex", "ey", "ez", "bx", "by", "bz")})
+    q = np.zeros(maxptl, p.dtype)
+    g.p = R.RecArr(q)
+    g.units = {7: [open(fld, "rb").read()], 8: [open(prt, "rb").read()]}
+    g.reorder_particles = lambda: None
+    for nm in ("mpi_irecv", "mpi_wait", "mpi_isend"):
+        setattr(g, nm, lambda *a: None)
+    sub(g)
+    assert (g.mxrest, g.myrest, g.mzrest) == (mx, my, mz)
+    assert g.readers[7].left == 0 and g.readers[8].left == 0          # every byte of both records was asked for
+    for a, nm in enumerate(("ex", "ey", "ez", "bx", "by", "bz")):
+        assert np.array_equal(getattr(g, nm).nd().transpose(2, 1, 0), fields[a]), nm
+    assert (g.dseed, g.lapst, g.xinject, g.xinject2, g.xinject3, g.leftwall, g.walloc) == (987654321.0, 77 + 1, 3.5, 101.25, 0.5, F(15.0), 20.125)
+    assert (g.ions, g.lecs, g.totalpartnum, g.maxhlf) == (ions, lecs, 4242, maxptl // 2)
+    assert np.array_equal(q[:ions], p[:ions]) and np.array_equal(q[maxptl // 2:maxptl // 2 + lecs], p[maxptl // 2:maxptl // 2 + lecs])
