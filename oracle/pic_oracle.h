@@ -11,9 +11,8 @@
  * hot-path subroutines -- up to `mainloop` itself, on several ranks -- are
  * executed from their text by the Fortran-subset interpreter
  * tests/golden/f90run.py; tests/test_ref_golden.py holds this restatement
- * BIT-EXACT against those outputs (tests/golden/ref_*.npz; 140 cases).  Not
- * covered that way, and pinned only by the known-answer tests
- * (tests/test_oracle_kat.py): the prtl.tot particle sampling.  See DESIGN.md section 2.  Every function cites the
+ * BIT-EXACT against those outputs (tests/golden/ref_*.npz; 145 cases).  Not
+ * covered that way: nothing this file restates.  See DESIGN.md section 2.  Every function cites the
  * reference file:line it follows (relative to the reference checkout).
  *
  * Conventions: arrays are Fortran column-major (mx,my,mz), addressed here with

@@ -571,7 +571,7 @@ def extract_subroutine(text, name):
 # ------------------------------------------------------------------------------------------------------------------
 # expression translation (recursive descent over the Fortran expression grammar)
 # ------------------------------------------------------------------------------------------------------------------
-TOK = re.compile(r"\s*('[^']*'|\"[^\"]*\"|\d+\.\d*(?:[ed][+-]?\d+)?|\.\d+(?:[ed][+-]?\d+)?|\d+[ed][+-]?\d+|\d+|\.[a-z]+\.|[a-z_]\w*|\*\*|==|/=|<=|>=|[-+*/(),:<>%=])")
+TOK = re.compile(r"\s*('[^']*'|\"[^\"]*\"|\d+\.(?![a-z]+\.)\d*(?:[ed][+-]?\d+)?|\.\d+(?:[ed][+-]?\d+)?|\d+[ed][+-]?\d+|\d+|\.[a-z]+\.|[a-z_]\w*|\*\*|==|/=|<=|>=|[-+*/(),:<>%=])")
 
 
 def tokenize(s):

@@ -1379,7 +1379,37 @@ def gen_restart():
     np.savez_compressed(os.path.join(OUT, "ref_restart.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# G23: which particles go into prtl.tot -- the index-building block of save_param / particle output (output.F90:3331-3393):
+#      modulo(p(n)%ind/2, stride) == 0 with Fortran's truncating division and floor modulo, ions then electrons.  The block
+#      is cut out of the HDF5 writer and wrapped in `subroutine pick`.
+# ------------------------------------------------------------------------------------------------------------
+def gen_select():
+    out = {}
+    text = R.preprocess(src("output.F90"), {"MPI"})
+    a = text.index("     strd_ions = 0\n     tmp1 = ions")
+    b = text.index("     all_ions_lng=all_ions", a)
+    wrapped = ("subroutine pick()\n\timplicit none\n\tinteger :: n, tmp1, error\n\tinteger :: all_strd_ions(size0), all_strd_lecs(size0), all_ions(size0), "
+               "all_lecs(size0)\n" + text[a:b] + "\nend subroutine pick\n")
+    gi = GINTS | {"stride", "strd_ions", "strd_lecs", "ions_str_ind", "lecs_str_ind"}
+    sub = R.Sub(wrapped, "pick", defines={"MPI"}, global_arrays={"p", "ions_str_ind", "lecs_str_ind"}, global_ints=gi).compile()
+    rng = np.random.default_rng(1800)
+    maxhlf, ions, lecs = 64, 50, 41
+    p = np.zeros(2 * maxhlf, PDT)
+    p["ind"] = rng.integers(-200, 200, p.size)
+    out["p_ind"] = p["ind"].copy()
+    out["geom"] = np.array([maxhlf, ions, lecs], np.int32)
+    for stride in (1, 2, 3, 7, 20):
+        g = R.Globals(p=R.RecArr(p), ions=ions, lecs=lecs, maxhlf=maxhlf, stride=stride, size0=1, rank=0, debug=False, mpi_integer=0,
+                      mpi_comm_world=0, strd_ions=0, strd_lecs=0, ions_str_ind=None, lecs_str_ind=None)
+        sub(g)
+        out[f"s{stride}_ions"] = np.array(g.ions_str_ind.flat[:g.strd_ions], np.int64)
+        out[f"s{stride}_lecs"] = np.array(g.lecs_str_ind.flat[:g.strd_lecs], np.int64)
+        print("select stride", stride, g.strd_ions, g.strd_lecs)
+    np.savez_compressed(os.path.join(OUT, "ref_select.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq", "loader", "spectrum", "injector", "decomp", "neighbours", "scalars", "calllist", "restart"]
+    which = sys.argv[1:] or ["deposit", "fields", "mover", "filter", "radiation", "halo", "fields42", "shock", "depositp", "halo_mr", "migrate_mr", "lap", "filter2_mr", "meanq", "loader", "spectrum", "injector", "decomp", "neighbours", "scalars", "calllist", "restart", "select"]
     for w in which:
         globals()["gen_" + w]()

@@ -610,3 +610,17 @@ def test_restart_dumps_are_byte_identical_to_the_reference_writes(case, tmp_path
     maxhlf = int(v["maxhlf"])
     assert (ions, lecs, hdr["totalpartnum"]) == (int(v["ions"]), int(v["lecs"]), int(v["totalpartnum"]))
     assert np.array_equal(q[:ions], p[:ions]) and np.array_equal(q[maxhlf:maxhlf + lecs], p[maxhlf:maxhlf + lecs])
+
+
+@pytest.mark.parametrize("stride", [1, 2, 3, 7, 20])
+def test_prtl_tot_selection_rule_matches_the_reference_source(stride):
+    """which particles the reference writes to prtl.tot (output.F90:3331-3393, run from its text): modulo(ind/2, stride) == 0
+    with Fortran's truncating division, ions then electrons, in array order.  tests/test_gpu_parity.py checks the library's
+    select_particles against exactly this predicate (np.trunc(ind / 2) % stride == 0); here the predicate itself is pinned."""
+    z = load("ref_select.npz")
+    maxhlf, ions, lecs = (int(v) for v in z["geom"])
+    ind = z["p_ind"]
+    for first, cnt, key in ((0, ions, "ions"), (maxhlf, lecs, "lecs")):
+        keep = (np.trunc(ind[first:first + cnt] / 2).astype(np.int64) % stride) == 0
+        want = np.nonzero(keep)[0] + first + 1                       # 1-based indices into p(:)
+        assert np.array_equal(z[f"s{stride}_{key}"], want), key
