@@ -11,9 +11,10 @@
  * hot-path subroutines -- up to `mainloop` itself, on several ranks -- are
  * executed from their text by the Fortran-subset interpreter
  * tests/golden/f90run.py; tests/test_ref_golden.py holds this restatement
- * BIT-EXACT against those outputs (tests/golden/ref_*.npz; 145 cases).  Not
- * covered that way: nothing this file restates.  See DESIGN.md section 2.  Every function cites the
- * reference file:line it follows (relative to the reference checkout).
+ * BIT-EXACT against those outputs (tests/golden/ref_*.npz; 145 cases), every
+ * reference routine restated here included (DESIGN.md section 2 has the table).
+ * Every function cites the reference file:line it follows (relative to the
+ * reference checkout).
  *
  * Conventions: arrays are Fortran column-major (mx,my,mz), addressed here with
  * 1-based (i,j,k) through ORC_IDX so index arithmetic reads like the reference.
