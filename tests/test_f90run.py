@@ -424,3 +424,57 @@ def test_the_references_restart_reader_accepts_files_written_by_the_package(tmp_
     assert (g.dseed, g.lapst, g.xinject, g.xinject2, g.xinject3, g.leftwall, g.walloc) == (987654321.0, 77 + 1, 3.5, 101.25, 0.5, F(15.0), 20.125)
     assert (g.ions, g.lecs, g.totalpartnum, g.maxhlf) == (ions, lecs, 4242, maxptl // 2)
     assert np.array_equal(q[:ions], p[:ions]) and np.array_equal(q[maxptl // 2:maxptl // 2 + lecs], p[maxptl // 2:maxptl // 2 + lecs])
+
+
+def test_operator_precedence_and_associativity_follow_the_standard():
+    src = """
+    subroutine t()
+      real :: a, b, c
+      logical :: p, q, s
+      a = 2.
+      b = 3.
+      c = 4.
+      r1 = -a**2
+      r2 = a**b**2
+      r3 = a - b + c
+      r4 = a/b*c
+      r5 = -a*b
+      r6 = a + b*c**2
+      r7 = 7/2*2
+      r8 = 2*7/2
+      p = .true.
+      q = .false.
+      s = .false.
+      l1 = .not. q .and. s
+      l2 = p .or. q .and. s
+      l3 = a .lt. b .and. b .lt. c
+      l4 = .not. a .gt. b
+    end subroutine t
+    """
+    _, g = run(src, "t")
+    assert g.r1 == F(-4.0)                      # ** binds tighter than unary minus
+    assert g.r2 == F(512.0)                     # ** associates to the right: 2**(3**2)
+    assert g.r3 == F(3.0) and g.r4 == F(F(F(2) / F(3)) * F(4))
+    assert g.r5 == F(-6.0) and g.r6 == F(50.0)
+    assert g.r7 == 6 and g.r8 == 7              # integer division, left to right
+    assert bool(g.l1) is False                  # (.not. q) .and. s
+    assert bool(g.l2) is True                   # .and. before .or.
+    assert bool(g.l3) is True and bool(g.l4) is True     # relational before .not.
+
+
+def test_cshift_sum_and_whole_array_expressions():
+    src = """
+    subroutine t()
+      b = cshift(a, 1, 1)
+      c = cshift(a, -1, 2)
+      d = 0.5*(a + b)
+      r1 = sum(a(2, :))
+    end subroutine t
+    """
+    g = R.Globals(**{n: R.FArr((3, 2)) for n in "abcd"})
+    g.a.nd()[...] = np.array([[1, 4], [2, 5], [3, 6]], F)
+    run(src, "t", g, arrays="abcd")
+    assert g.b.nd().tolist() == [[2, 5], [3, 6], [1, 4]]           # result(i) = a(i + shift), circular, along dim 1
+    assert g.c.nd().tolist() == [[4, 1], [5, 2], [6, 3]]           # shift -1 along dim 2
+    assert g.d.nd().tolist() == [[1.5, 4.5], [2.5, 5.5], [2.0, 5.0]]
+    assert g.r1 == F(7.0)
