@@ -136,6 +136,7 @@ def test_functions_sign_modulo_and_aint():
       r5 = modulo(-7, 3)
       r6 = aint(-2.7)
       r7 = int(2.999)
+      r8 = nint(2.5) + 10*nint(-2.5) + 100*nint(3.49)
     end subroutine t
     """
     g = R.Globals(n0=4)
@@ -143,6 +144,7 @@ def test_functions_sign_modulo_and_aint():
     g.wrapidx = lambda i: f(g, i)
     run(src, "t", g, ints=("n0",))
     assert (g.r1, g.r2, g.r3, g.r4, g.r5, g.r6, g.r7) == (4, 1, F(0.0), -1, 2, F(-2.0), 2)
+    assert g.r8 == 3 - 30 + 300                     # nint rounds halves away from zero
 
 
 def test_cpp_conditionals_select_the_build():
