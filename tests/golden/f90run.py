@@ -471,7 +471,7 @@ RUNTIME = {"fint": fint, "freal": freal, "fexp": elementary("exp"), "flog": elem
            "fatan": elementary("atan"), "ftan": elementary("tan"), "fdmod": lambda a, b: np.float64(np.fmod(np.float64(a), np.float64(b))),
            "fceiling": lambda x: int(math.ceil(x)), "fpresent": lambda x: x is not None, "F": F, "FArr": FArr, "fdiv": fdiv, "fpow": fpow, "fsum": fsum, "fcshift": fcshift, "frange": frange, "fexit": fexit, "faint": faint,
            "fmodulo": fmodulo, "fmod": fmod, "fmin": fmin, "fmax": fmax, "fsqrt": fsqrt,
-           "fsign": lambda a, b: (abs(a) if not np.signbit(b) else -abs(a)) if isinstance(a, np.float64) else (F(abs(a)) if not np.signbit(b) else F(-abs(a))), "fcos": elementary("cos"), "fsin": elementary("sin"), "fnint": lambda x: int(math.copysign(math.floor(abs(float(x)) + 0.5), float(x))),      # half away from zero "ffloor": lambda x: int(np.floor(x)), "np": np}
+           "fsign": lambda a, b: (abs(a) if not np.signbit(b) else -abs(a)) if isinstance(a, np.float64) else (F(abs(a)) if not np.signbit(b) else F(-abs(a))), "fcos": elementary("cos"), "fsin": elementary("sin"), "fnint": lambda x: int(math.copysign(math.floor(abs(float(x)) + 0.5), float(x))), "ffloor": lambda x: int(np.floor(x)), "np": np}
 PYKW = {"in", "is", "lambda", "not", "and", "or", "if", "else", "for", "while", "def", "class", "pass", "del", "from", "as", "with"}
 
 
