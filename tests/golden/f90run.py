@@ -331,11 +331,18 @@ def fdiv(a, b):
 
 def fpow(a, b):
     if isinstance(b, (int, np.integer)) and not isinstance(a, (int, np.integer)):
-        K = np.float64 if isinstance(a, np.float64) else F
-        r = K(1.0)
-        for _ in range(abs(int(b))):                                  # x**2 -> x*x as every compiler does
-            r = K(r * a) if not isinstance(a, (FArr, np.ndarray)) else r * a
-        return r if b >= 0 else K(1.0) / r
+        # x**n with an integer n: multiplications by repeated squaring, as gcc's __builtin_powi and every compiler's
+        # expansion of x**2, x**3 do (x**2 = x*x, x**3 = x*(x*x), x**4 = (x*x)*(x*x))
+        K = (lambda v: v) if isinstance(a, (FArr, np.ndarray)) else (np.float64 if isinstance(a, np.float64) else F)
+        n, x = abs(int(b)), a
+        r = x if n & 1 else (np.float64(1.0) if isinstance(a, np.float64) else F(1.0))
+        n >>= 1
+        while n:
+            x = K(x * x)
+            if n & 1:
+                r = K(r * x)
+            n >>= 1
+        return r if b >= 0 else K((np.float64(1.0) if isinstance(a, np.float64) else F(1.0)) / r)
     if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)):
         return int(a) ** int(b)
     if isinstance(a, np.float64) or isinstance(b, np.float64):

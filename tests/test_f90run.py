@@ -480,3 +480,20 @@ def test_cshift_sum_and_whole_array_expressions():
     assert g.c.nd().tolist() == [[4, 1], [5, 2], [6, 3]]           # shift -1 along dim 2
     assert g.d.nd().tolist() == [[1.5, 4.5], [2.5, 5.5], [2.0, 5.0]]
     assert g.r1 == F(7.0)
+
+
+def test_integer_powers_multiply_by_repeated_squaring():
+    src = """
+    subroutine t()
+      real :: x
+      x = 1.1
+      r2 = x**2
+      r3 = x**3
+      r4 = x**4
+      r5 = x**(-2)
+    end subroutine t
+    """
+    _, g = run(src, "t")
+    x = F(1.1)
+    x2 = F(x * x)
+    assert g.r2 == x2 and g.r3 == F(x * x2) and g.r4 == F(x2 * x2) and g.r5 == F(F(1) / x2)
