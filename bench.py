@@ -194,7 +194,7 @@ def run_small_config(args):
         dt = (time.perf_counter() - t0) / k
         cpu = {"value": npc / dt, "unit": "particle-steps/s", "cores": 1, "kind": "port",
                "sample": f"the whole problem ({npc} particles), {k} laps in {k * dt:.1f} s on ONE thread (one CPU rank), oracle built -O3 -march=native",
-               "pin": "same C source as the parity build, which is bit-exact against the reference's own source text on 145 cases (tests/test_ref_golden.py); this -O3 -march=native build is for timing only"}
+               "pin": "same C source as the parity build, which is bit-exact against the reference's own source text on 147 cases (tests/test_ref_golden.py); this -O3 -march=native build is for timing only"}
     peak, peak_src = measured_peak()
     line = {"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": steps, "warmup": warm,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -398,7 +398,7 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
             "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample,
-                             "pin": "same C source as the parity build, which is bit-exact against the reference's own source text on 145 cases (tests/test_ref_golden.py); this -O3 -march=native build is for timing only"},
+                             "pin": "same C source as the parity build, which is bit-exact against the reference's own source text on 147 cases (tests/test_ref_golden.py); this -O3 -march=native build is for timing only"},
             "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = CPU oracle restatement of the Fortran routines (no Fortran/MPI toolchain in this image)"}
     print(json.dumps(line))
@@ -595,7 +595,7 @@ def main():
                "sample": f"{cc[0]}x{cc[1]}x{cc[2]} cells, {npc} particles, 2 laps after 1 warm-up, same "
                          f"physics (dd{ORDER}, {PPC:g} ppc, filter2 ntimes={NTIMES}); oracle restatement built -O3 -march=native, "
                          f"one y/z slab per OpenMP thread, {cores} threads",
-               "pin": "same C source as the parity build, which is bit-exact against the reference's own source text on 145 cases (tests/test_ref_golden.py); this -O3 -march=native build is for timing only"}
+               "pin": "same C source as the parity build, which is bit-exact against the reference's own source text on 147 cases (tests/test_ref_golden.py); this -O3 -march=native build is for timing only"}
     line = {"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": n, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "ns_per_particle_step": 1e9 / value * n,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

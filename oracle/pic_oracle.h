@@ -11,7 +11,7 @@
  * hot-path subroutines -- up to `mainloop` itself, on several ranks -- are
  * executed from their text by the Fortran-subset interpreter
  * tests/golden/f90run.py; tests/test_ref_golden.py holds this restatement
- * BIT-EXACT against those outputs (tests/golden/ref_*.npz; 145 cases), every
+ * BIT-EXACT against those outputs (tests/golden/ref_*.npz; 147 cases), every
  * reference routine restated here included (DESIGN.md section 2 has the table).
  * Every function cites the reference file:line it follows (relative to the
  * reference checkout).

@@ -735,7 +735,10 @@ LAP_CASES = [  # dim order nglob       sizes      periodic   laps highorder shoc
     (2, 3, (12, 10, 1), (1, 1, 1), (1, 1, 1), 3, 0, 0, 2),
     (2, 0, (12, 10, 1), (1, 1, 1), (1, 0, 1), 3, 0, 0, 2),
     (3, 2, (6, 12, 6), (1, 2, 1), (1, 0, 1), 3, 0, 0, 1),
-    (2, 2, (16, 12, 1), (2, 2, 1), (0, 0, 1), 3, 0, 0, 2)]
+    (2, 2, (16, 12, 1), (2, 2, 1), (0, 0, 1), 3, 0, 0, 2),
+    # two-rank periodic boxes, also driven over gloo through the slab-exchange plan (tests/test_gloo_slabs.py)
+    (2, 2, (16, 12, 1), (2, 1, 1), (1, 1, 1), 3, 0, 0, 2),
+    (3, 2, (6, 6, 12), (1, 1, 2), (1, 1, 1), 2, 0, 0, 1, 2)]
 
 
 def gen_lap():

@@ -163,3 +163,58 @@ def test_two_rank_lap_over_gloo(case):
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert sum(m for _, _, m in res) > 0, "no particle migrated between the two ranks"
+
+
+# ---- the same protocol against WHOLE LAPS OF THE REFERENCE'S OWN MAINLOOP (tests/golden/ref_lap.npz, two-rank cases) ----
+def _golden_worker(rank, world, port, case, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import slabs
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_lap.npz"))
+        key = f"l{case}"
+        dim, order, px, py, pz, nx, ny, nz = (int(v) for v in z[key + "_meta"])
+        sx, sy, sz, maxhlf, nsp, laps, highorder, shock, fkind = (int(v) for v in z[key + "_geom"])
+        par = z[key + "_par"]
+        P = O.make_params(dim=dim, order=order, mx0=nx, my0=ny, mz0=nz, sizex=sx, sizey=sy, sizez=sz, ntimes=2, filter_kind=fkind,
+                          periodic=(px, py, pz), maxptl=2 * maxhlf, highorder=highorder)
+        P.qi, P.qe, P.qmi, P.qme = (float(v) for v in par[5:9])
+        w = O.World(P)
+        r = w.ranks[rank]                                   # this process drives only its own rank of the world
+        for a in range(6):
+            r.arr(a)[...] = z[f"{key}_r{rank}_in{a}"]
+        for a in range(6, 9):
+            r.arr(a)[...] = 0
+        r.particles()[:] = z[f"{key}_r{rank}_pin"]
+        r.set_counts(nsp, nsp)
+        drv = Driver(slabs, w, rank)
+        for lap in range(1, laps + 1):
+            drv.lap(lap)
+        ions, lecs = (int(v) for v in z[f"{key}_r{rank}_counts"])
+        ok = r.counts == (ions, lecs)
+        for a in range(9):
+            ok = ok and np.array_equal(r.arr(a), z[f"{key}_r{rank}_out{a}"])
+        pout, p = z[f"{key}_r{rank}_pout"], r.particles()
+        ok = ok and np.array_equal(p[:ions], pout[:ions]) and np.array_equal(p[maxhlf:maxhlf + lecs], pout[maxhlf:maxhlf + lecs])
+        q.put((rank, bool(ok), int((pout["proc"][:ions] != rank).sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", [4, 15, 16], ids=["3d-o3-highorder-1x2x1", "2d-o2-2x1", "3d-o2-filter2-1x1x2"])
+def test_two_rank_protocol_against_the_reference_mainloop(case):
+    """the slab-exchange plan (tests/slabs.py = the protocol csrc/fields.cu and csrc/particles.cu run over NCCL / peer
+    memory), driven over gloo by two processes, against two laps of the reference's mainloop run from its own text:
+    every array and the particle arrays in order, BIT-EXACT"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_golden_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert sum(m for _, _, m in res) > 0, "no particle migrated between the two ranks"

@@ -347,7 +347,7 @@ def lap_world(z, case):
     return key, w, laps, shock, par, maxhlf
 
 
-@pytest.mark.parametrize("case", range(15))
+@pytest.mark.parametrize("case", range(17))
 def test_whole_laps_match_the_reference_mainloop(case):
     """WHOLE LAPS: the reference's `mainloop` (tristanmainloop.F90:60-330) executed from its own text on every rank, calling
     the reference's own text for every routine on the path (solver, movers, deposit, migration, ghost refresh, radiation,
